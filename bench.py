@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- PD step throughput on B200 (see DESIGN.md section 7 for the measurement contract).
+
+  python bench.py --gpus N --steps K --warmup W [--workload grid139] [--impl reference]
+
+One "step" = one PdSolver::Update (predictor, `num of iterations` x (local step + global sweep),
+velocity update, fixed-body response) of the synthetic Kuhn-grid workload; metric =
+Mtet-updates/s = numTets x PD iterations / second, whole job.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+WORKLOADS = {
+    # name: (cells per axis, PD iterations per step, description)   SURVEY.md section 8d
+    "grid139": (139, 100, "Kuhn 6-tet grid 139^3 cells (2,744,000 verts, 16,113,714 tets), float PD, Chebyshev-Jacobi 100 it/step"),
+    "grid55": (55, 100, "Kuhn 6-tet grid 55^3 cells (175,616 verts, 998,250 tets), float PD, Chebyshev-Jacobi 100 it/step"),
+    "grid24": (24, 100, "Kuhn 6-tet grid 24^3 cells (82,944 tets) -- CPU-sized sample"),
+}
+DT, GRAVITY, MU, MASS, JITTER, SEED = 1.0 / 60.0, 9.8, 2e5, 1.0, 0.05, 12345
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_scene(pd, workload):
+    cells, iters, _ = WORKLOADS[workload]
+    sc = pd.Scene.kuhn_grid(cells, cells, cells, 1.0, JITTER, SEED, (0.0, 10.0, 0.0), MASS, MU)
+    p = pd.SolverParams(dt=DT, gravity=GRAVITY, num_iterations=iters)
+    sc.params = p
+    sc.add_fixed(pd.fixed_body(pd.PD_PLANE, pos=(0, 0, 0), scale=(450, 450, 450)))
+    return sc, p
+
+
+def initial_velocity(X):
+    """v = 0.5 sin(x/7) y^   so that F is non-trivial from the first iteration."""
+    V = np.zeros_like(X)
+    V[:, 1] = 0.5 * np.sin(X[:, 0] / 7.0)
+    return V
+
+
+def cpu_baseline(workload_iters, threads):
+    """The oracle port (oracle/pd_oracle.c, OpenMP) on a bounded sample of the same workload family."""
+    import oracle as O
+    pd = importlib.import_module("soft-body-simulation-cuda_b200")
+    cells = 24
+    sc = pd.Scene.kuhn_grid(cells, cells, cells, 1.0, JITTER, SEED, (0.0, 10.0, 0.0), MASS, MU)
+    a = sc.arrays()
+    osc = O.Scene(a["X"], a["Tet"], a["mass"], a["mu"], planes=[(np.zeros(3, np.float32), np.array([0, 1, 0], np.float32))])
+    osc.set(V=initial_velocity(a["X"]))
+    p = O.make_params(dt=DT, gravity=GRAVITY, num_iterations=workload_iters, threads=threads)
+    osc.step(p, 1)                      # warm-up (also builds the setup products)
+    t0 = time.perf_counter()
+    nsteps = 2
+    osc.step(p, nsteps)
+    dt = time.perf_counter() - t0
+    nT = a["Tet"].shape[0]
+    val = nT * workload_iters * nsteps / dt / 1e6
+    return {"value": val, "unit": "Mtet-updates/s", "cores": threads, "kind": "port",
+            "sample": f"oracle/pd_oracle.c (OpenMP, {threads} threads): {nsteps} steps x {workload_iters} it of the {cells}^3-cell Kuhn grid ({nT} tets), {dt:.1f} s"}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def max_over_ranks(x, world, local):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=torch.device("cuda", local))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_b200(args):
+    import torch
+    pd = importlib.import_module("soft-body-simulation-cuda_b200")
+    rank, world, local = dist_setup(args.gpus)
+    if world > 1:
+        raise SystemExit("multi-GPU partitioned PD step is not wired into bench.py yet (round 1: N=1)")
+    torch.cuda.set_device(local)
+    sc, p = make_scene(pd, args.workload)
+    nV, nT = sc.counts()[:2]
+    iters = p["num_iterations"]
+    eng = pd.PdSolver(sc, device=local)
+    X0 = sc.arrays()["X"]
+    V0 = initial_velocity(X0)
+    eng.upload(V=V0)
+    info = eng.info()
+    launches_per_step = 2 + 2 * iters
+
+    # ---- device-resident timing: inputs already in HBM, K steps bracketed by sync + events
+    for _ in range(args.warmup):
+        eng.Update(1)
+    eng.synchronize(); torch.cuda.synchronize(); barrier(world)
+    sampler = ClockSampler(local); sampler.start()
+    perf0 = eng.GetPerformanceData()[1].kernel_launches
+    # the engine launches on its own stream, so the CUDA events are recorded there (pd_step_timed)
+    dev_ms = eng.step_timed(args.steps)
+    clocks = sampler.stop()
+    barrier(world)
+    ms_step = max_over_ranks(dev_ms / args.steps, world, local)
+    launches = eng.GetPerformanceData()[1].kernel_launches - perf0
+
+    # ---- kernel-level roofline, measured live with CUDA events on the engine's stream
+    t_local_ms, t_vertex_ms = eng.time_kernels(reps=20)
+    peak, peak_src = peaks()
+    bytes_local = 56.0 * nT + 24.0 * nV
+    bytes_iter = 56.0 * nT + 68.0 * nV
+    ach_local = bytes_local / (t_local_ms * 1e-3) / 1e9
+    ach_iter = bytes_iter / ((t_local_ms + t_vertex_ms) * 1e-3) / 1e9
+
+    # ---- end to end: HOST (pinned) state in -> H2D, step, D2H -> host state out, every step
+    import ctypes as C
+    nbytes = X0.nbytes
+    bufs = [pd.lib().pd_alloc_pinned(nbytes) for _ in range(6)]
+    arr = [np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_float)), shape=(nV, 3)) for b in bufs]
+    X, V, XT = eng.download()
+    arr[0][:] = X; arr[1][:] = V; arr[2][:] = XT
+    e2e_steps = max(1, min(args.steps, 5))
+    eng.step_host_ptr(1, bufs[0], bufs[1], bufs[2], bufs[3], bufs[4], bufs[5])       # warm-up
+    barrier(world)
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        i, o = (0, 3) if s % 2 == 0 else (3, 0)
+        eng.step_host_ptr(1, bufs[i], bufs[i + 1], bufs[i + 2], bufs[o], bufs[o + 1], bufs[o + 2])
+    t1 = time.perf_counter()
+    e2e_ms = max_over_ranks((t1 - t0) * 1e3 / e2e_steps, world, local)
+    final = arr[3] if e2e_steps % 2 == 1 else arr[0]
+    finite = bool(np.isfinite(final).all())
+    for b in bufs:
+        pd.lib().pd_free_pinned(b)
+
+    if rank != 0:
+        return
+    value = nT * iters / (ms_step * 1e-3) / 1e6
+    line = {
+        "metric": "Mtet-updates/s & PD iters/s at 1/2/4/8 B200; % of HBM roofline",
+        "value": value, "unit": "Mtet-updates/s", "pd_iters_per_s": iters / (ms_step * 1e-3),
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "description": WORKLOADS[args.workload][2], "num_verts": nV, "num_tets": nT,
+                   "pd_iterations_per_step": iters, "global_solver": "chebyshev-jacobi", "dt": DT, "gravity": GRAVITY, "mu": MU,
+                   "initial_velocity": "0.5*sin(x/7) y^", "l2": f"inputs larger than L2: tile stream {info['tile_stream_bytes'] / 1e6:.0f} MB per iteration, no flush needed",
+                   "finite": finite},
+        "clocks": clocks,
+        "e2e": {"value": nT * iters / (e2e_ms * 1e-3) / 1e6, "unit": "Mtet-updates/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": 3 * nbytes, "d2h_bytes_per_step": 3 * nbytes, "steps": e2e_steps,
+                "api": "pd_step_host (include/pd_b200.h): pinned host X,V,XTilde in and out every step"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k_local (local step: F, rotation, ordered RHS partials)",
+                     "achieved": ach_local, "peak": peak, "unit": "GB/s", "frac": ach_local / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_local, "launch_ms": t_local_ms,
+                     "fused_iteration": {"achieved": ach_iter, "frac": ach_iter / peak, "algorithmic_bytes": bytes_iter,
+                                         "ms": t_local_ms + t_vertex_ms, "vertex_kernel_ms": t_vertex_ms},
+                     "frac_of_8TBs_nominal": ach_local / 8000.0},
+        "cpu_baseline": cpu_baseline(iters, os.cpu_count() or 1) if not args.no_cpu_baseline else None,
+    }
+    print(json.dumps(line))
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CUDA kernels (oracle/_ref, compiled verbatim from
+    /root/reference) replayed launch for launch on ONE B200, same workload/metric.  If the prebuilt
+    harness is absent, the oracle port on the host cores stands in (kind 'port')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import ref
+    pd = importlib.import_module("soft-body-simulation-cuda_b200")      # host-side scene generator only
+    sc, p = make_scene(pd, args.workload)
+    nV, nT = sc.counts()[:2]
+    iters = p["num_iterations"]
+    a = sc.arrays()
+    cores = os.cpu_count() or 1
+    base = {"metric": "Mtet-updates/s & PD iters/s at 1/2/4/8 B200; % of HBM roofline", "unit": "Mtet-updates/s",
+            "impl": "reference", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": WORKLOADS[args.workload][2], "num_verts": nV, "num_tets": nT,
+                       "pd_iterations_per_step": iters}}
+    cpu = cpu_baseline(iters, cores)
+    if ref.available():
+        rs = ref.RefScene(a["X"], a["Tet"], a["mass"], a["mu"], planes=[(np.zeros(3, np.float32), np.array([0, 1, 0], np.float32))])
+        rs.set(V=initial_velocity(a["X"]))
+        kw = dict(dt=DT, gravity=GRAVITY, rho=p["rho"], muN=p["muN"], muT=p["muT"], num_iterations=iters)
+        rs.step(args.warmup, **kw); rs.sync()
+        sampler = ClockSampler(0); sampler.start()
+        t0 = time.perf_counter()
+        rs.step(args.steps, perf=False, **kw); rs.sync()
+        t1 = time.perf_counter()
+        clocks = sampler.stop()
+        ms = (t1 - t0) * 1e3 / args.steps
+        t0 = time.perf_counter()
+        rs.step(max(1, args.steps // 2), perf=True, **kw); rs.sync()     # as shipped: SetPerf(true), 2 event syncs per iteration
+        ms_perf = (time.perf_counter() - t0) * 1e3 / max(1, args.steps // 2)
+        val = nT * iters / (ms * 1e-3) / 1e6
+        base.update({"value": val, "ms_per_step": ms, "pd_iters_per_s": iters / (ms * 1e-3), "clocks": clocks,
+                     "reference_kind": "the reference's CUDA kernels (pdUtil.cu, svd3_cuda.h, computeInvDmV0) compiled verbatim for sm_100a, replayed by oracle/ref_harness.cu on one B200",
+                     "value_perf_true": nT * iters / (ms_perf * 1e-3) / 1e6, "ms_per_step_perf_true": ms_perf,
+                     "gpu_launches": int(args.steps * (5 + 4 * iters + 1)),
+                     "cpu_baseline": cpu,
+                     "e2e": {"value": val, "unit": "Mtet-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    else:
+        base.update({"value": cpu["value"], "ms_per_step": None, "cpu_baseline": cpu,
+                     "reference_kind": "oracle port on host cores (oracle/_ref/libpd_ref.so not present)",
+                     "e2e": {"value": cpu["value"], "unit": "Mtet-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(base))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="grid139", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -1,0 +1,181 @@
+/*
+ * pd_b200.h -- C ABI of the B200-native projective-dynamics (PD) step engine.
+ *
+ * Drop-in boundary for the float PD path of GrahamZen/Soft-Body-Simulation-CUDA.  The
+ * reference has no C ABI; its boundary is the C++ plugin interface
+ *     template<typename Scalar> class Solver            src/simulation/solver/solver.h:11-28
+ *     class PdSolver : public FEMSolver<float>          src/simulation/solver/projective/pdSolver.h:12-44
+ * driven by SimulationCUDAContext (src/simulation/simulationContext.cpp:79-114).  Every entry
+ * point below names the reference interface it replaces.  INTEGRATION.md shows the adapter
+ * (`class B200PdSolver : public Solver<float>`, include/b200_pd_solver.h) a maintainer adds.
+ *
+ * Conventions: plain pointers and sizes only; all functions returning int return 0 on success
+ * and a negative pd_status otherwise; the message is available from pd_last_error() (thread
+ * local).  One engine = one simulation context on one GPU, driven by one host thread at a
+ * time, on its own non-blocking CUDA stream.  There is no CPU fallback: creating an engine
+ * without a sm_100 device fails loudly.
+ *
+ * Host arrays use the reference's layouts: positions/velocities are AoS float[3*numVerts]
+ * (glm::vec3), tets are uint32[4*numTets] (indexType, def.h:4), original vertex numbering.
+ */
+#ifndef PD_B200_H
+#define PD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pd_engine pd_engine;   /* one SimulationCUDAContext::Impl<float> + PdSolver        */
+typedef struct pd_scene pd_scene;     /* host-side merged scene (DataLoader output), no GPU needed */
+typedef struct pd_layout pd_layout;   /* host-side device-layout builder output, no GPU needed     */
+
+enum pd_status {
+    PD_OK = 0,
+    PD_ERR_INVALID = -1,      /* bad argument                                   */
+    PD_ERR_IO = -2,           /* file / parse error                             */
+    PD_ERR_CUDA = -3,         /* CUDA runtime error or no usable device         */
+    PD_ERR_UNSUPPORTED = -4   /* feature outside the PD hot path                */
+};
+
+/* PdSolver::SolverType, pdSolver.h:15-18 (+ the PCG back-end of linear/pcgJacobi.cu) */
+enum pd_global_solver { PD_JACOBI = 0, PD_CHOLESKY = 1, PD_PCG_JACOBI = 2 };
+
+/* FixedBody subclasses, src/collision/rigid/{plane,sphere,cylinder}.h */
+enum pd_fixed_body_type { PD_PLANE = 0, PD_SPHERE = 1, PD_CYLINDER = 2 };
+
+typedef struct {
+    int type;          /* pd_fixed_body_type                                                  */
+    float model[16];   /* FixedBody::m_model, glm column-major (utilities.cpp:141-150)        */
+    float radius;      /* Sphere::m_radius / Cylinder::m_radius ; unused for planes           */
+} pd_fixed_body;
+
+/* SolverParams<float>, src/def.h:82-100, plus the solver choice of PdSolver::SetGlobalSolver */
+typedef struct {
+    float dt, gravity, muN, muT, rho, tol, damp;
+    int num_iterations;       /* context.json "num of iterations"                             */
+    int global_solver;        /* pd_global_solver                                             */
+    int pcg_max_iter;         /* PCGJacobiSolver max_iter (pcgJacobi.h)                       */
+    float pcg_tol;            /* PCGJacobiSolver tolerance on ||r||_2                         */
+    int handle_collision;     /* must be 0: mesh-mesh BVH/CCD is outside the hot path         */
+    int threads_per_block;    /* accepted for interface parity, ignored                       */
+} pd_params;
+
+/* SolverData<float> as DataLoader::AllocData leaves it (dataLoader.cu:291-378), host side */
+typedef struct {
+    int num_verts, num_tets;
+    const float* X;           /* 3*num_verts rest positions (already transformed)             */
+    const uint32_t* Tet;      /* 4*num_tets                                                   */
+    const float* mass;        /* num_verts  (SoftBodyAttribute::mass per vertex)              */
+    const float* mu;          /* num_tets                                                     */
+    const float* DBC;         /* num_verts, 1 = pinned (may be NULL = none)                   */
+    int num_fixed;
+    const pd_fixed_body* fixed;
+} pd_scene_desc;
+
+typedef struct {
+    int device;               /* CUDA device ordinal                                          */
+    int rot_mode;             /* 0 Newton polar + SVD fallback (default), 1 always Jacobi SVD  */
+    int reorder;              /* 1 (default) Morton tet order + first-touch vertex renumbering */
+    int use_graph;            /* 1 (default) one CUDA graph per step                          */
+    int ctas_per_sm;          /* 0 = occupancy query                                          */
+} pd_engine_options;
+
+/* PdSolver::GetPerformanceData (solver.h:20, pdSolver.cu:26): the four named counters, ms */
+typedef struct {
+    float local_step_ms, global_step_ms, collision_fixed_ms, collision_mesh_ms;
+    double step_ms_total;
+    long long steps, pd_iterations, inner_iterations, kernel_launches;
+} pd_perf;
+
+const char* pd_last_error(void);
+const char* pd_version(void);
+void pd_default_params(pd_params* p);                 /* def.h:82-100 defaults                 */
+void pd_default_options(pd_engine_options* o);
+
+/* ---- scene (host only) : Context::LoadSimContext + Impl::Init + DataLoader -------------- */
+/* context.cpp:319-387, simulationContext.cu:34-123.  context_name NULL/"" = first loadable.
+ * asset_root NULL = resolve "../assets/..." like the reference does from its build dir.    */
+pd_scene* pd_scene_load_json(const char* json_path, const char* context_name, const char* asset_root);
+pd_scene* pd_scene_from_desc(const pd_scene_desc* desc, const pd_params* params);
+/* synthetic Kuhn 6-tet grid (bench configs 3/4) */
+pd_scene* pd_scene_kuhn_grid(int nx, int ny, int nz, float h, float jitter, uint32_t seed,
+                             const float origin[3], float mass, float mu);
+void pd_scene_free(pd_scene*);
+int pd_scene_counts(const pd_scene*, int* num_verts, int* num_tets, int* num_fixed, int* num_bodies);
+int pd_scene_get(const pd_scene*, float* X, uint32_t* Tet, float* mass, float* mu, float* DBC,
+                 pd_fixed_body* fixed, int* body_vert_start);
+int pd_scene_get_params(const pd_scene*, pd_params* out);
+int pd_scene_set_params(pd_scene*, const pd_params* in);
+int pd_scene_add_fixed(pd_scene*, const pd_fixed_body* fb);
+int pd_scene_write_tetgen(const pd_scene*, const char* node_path, const char* ele_path);
+/* dataLoader.cu:131-173 / :38-66 ; caller frees with pd_free */
+int pd_load_node(const char* path, int centralize, float** X, int* num_verts);
+int pd_load_ele(const char* path, int start_index, uint32_t** Tet, int* num_tets);
+void pd_free(void*);
+/* utilities.cpp:141-150 / dataLoader.cu:214-220, rigid/plane.cpp:9 */
+void pd_model_matrix(const float pos[3], const float rot_deg[3], const float scale[3], int soft_body_order, float M[16]);
+void pd_transform_vertices(float* X, int num_verts, const float M[16]);
+void pd_plane_up(const float M[16], float up[3]);
+
+/* ---- device layout (host only) : bit-exact partition / reorder / incidence checks -------- */
+pd_layout* pd_layout_build(const pd_scene*, int reorder);
+void pd_layout_free(pd_layout*);
+int pd_layout_counts(const pd_layout*, int* num_tiles, uint32_t* num_slots, size_t* record_bytes, int* max_local);
+int pd_layout_get(const pd_layout*, uint32_t* tet_order, uint32_t* vert_order, uint32_t* tet_new,
+                  uint32_t* tile_tet_start, uint64_t* tile_rec_off, uint8_t* records,
+                  uint32_t* vslot_ptr, uint32_t* vslot);
+int pd_morton_keys(const float* X, const uint32_t* Tet, int num_tets, uint32_t* keys);
+int pd_partition_vertices(int num_verts, int world, int* vbeg /* world+1 */);
+
+/* ---- engine : PdSolver behind SimulationCUDAContext -------------------------------------- */
+/* PdSolver::PdSolver + FEMSolver ctor (pdSolver.cu:22-27, femSolver.cu:6-17) */
+pd_engine* pd_create(const pd_scene*, const pd_engine_options* opt /* NULL = defaults */);
+pd_engine* pd_create_from_json(const char* json_path, const char* context_name, const char* asset_root,
+                               const pd_engine_options* opt);
+void pd_destroy(pd_engine*);
+/* SimulationCUDAContext::Update -> PdSolver::Update (simulationContext.cpp:79-86, pdSolver.cu:210-232) */
+int pd_step(pd_engine*, int n_steps);
+int pd_synchronize(pd_engine*);
+/* pd_step bracketed by CUDA events on the engine's stream; *device_ms = elapsed device time */
+int pd_step_timed(pd_engine*, int n_steps, float* device_ms);
+/* CopyUIToParams before every Update (simulationContext.cpp:17-35,85) */
+int pd_set_params(pd_engine*, const pd_params*);
+int pd_get_params(const pd_engine*, pd_params*);
+/* SimulationCUDAContext::SetGlobalSolver (simulationContext.cpp:104-114) */
+int pd_set_global_solver(pd_engine*, int solver);
+/* SimulationCUDAContext::Reset + Solver::Reset (simulationContext.cu:233-243, solver.h:39-43) */
+int pd_reset(pd_engine*);
+/* Solver::SetPerf / GetPerformanceData (solver.h:19-20) */
+int pd_set_perf(pd_engine*, int on);
+int pd_get_perf(const pd_engine*, pd_perf* out);
+/* state in the reference's host layout; any pointer may be NULL */
+int pd_download(pd_engine*, float* X, float* V, float* XTilde);
+int pd_upload_state(pd_engine*, const float* X, const float* V, const float* XTilde);
+/* end to end on HOST buffers: upload state, n steps, download state (all inside the call) */
+int pd_step_host(pd_engine*, int n_steps, const float* X_in, const float* V_in, const float* XTilde_in,
+                 float* X_out, float* V_out, float* XTilde_out);
+/* adopt the reference's DEVICE arrays (SolverData<float>::X/V/XTilde, glm::vec3*, original
+ * numbering): import -> n steps -> export, all on the engine's stream, then synchronise.
+ * This is what B200PdSolver::Update calls (include/b200_pd_solver.h). */
+int pd_update_device(pd_engine*, int n_steps, float* dX, float* dV, float* dXTilde);
+/* setup products for parity checks (original numbering): matrix_diag, massDt_2s, DmInv(9/tet,row-major), V0 */
+int pd_get_setup(pd_engine*, float* matrix_diag, float* mass_dt2, float* DmInv, float* V0);
+/* measurement helpers used by bench.py: average device time (ms) of one launch of the local /
+ * vertex kernel over `reps` back-to-back launches, CUDA events on the engine's stream */
+int pd_time_kernels(pd_engine*, int reps, float* local_ms, float* vertex_ms);
+int pd_engine_info(const pd_engine*, int* num_verts, int* num_tets, int* num_tiles, uint32_t* num_slots,
+                   size_t* tile_stream_bytes, size_t* device_bytes, int* local_grid);
+/* test hook: the corotational projection (pdUtil.cu:112-122) of n row-major 3x3 matrices on
+ * `device`; rot_mode as in pd_engine_options; used_fast (may be NULL) reports the path taken */
+int pd_rotation_batch(int device, int rot_mode, int n, const float* F, float* R, int* used_fast);
+/* pinned host memory for the e2e path */
+void* pd_alloc_pinned(size_t bytes);
+void pd_free_pinned(void*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PD_B200_H */

@@ -1,0 +1,95 @@
+"""ctypes loader for oracle/_ref/libpd_ref.so: the REFERENCE's own CUDA kernels (compiled verbatim
+from /root/reference by oracle/Makefile) behind the replay harness oracle/ref_harness.cu.
+TEST INFRASTRUCTURE: parity pin + the reference arm of bench.py.  Needs a GPU to run."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PATH = os.path.join(_HERE, "_ref", "libpd_ref.so")
+SVD_CPU_PATH = os.path.join(_HERE, "_ref", "libref_svd_cpu.so")
+_lib = None
+
+
+def available():
+    return os.path.exists(PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(PATH)
+        L.ref_create.restype = C.c_void_p
+        L.ref_create.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.ref_destroy.argtypes = [C.c_void_p]
+        L.ref_step.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.ref_reset.argtypes = [C.c_void_p]
+        L.ref_get.argtypes = [C.c_void_p] * 4
+        L.ref_set.argtypes = [C.c_void_p] * 4
+        L.ref_get_setup.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 4
+        L.ref_get_perf.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_rotation.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class RefScene:
+    def __init__(self, X, Tet, mass, mu, DBC=None, planes=(), spheres=(), cylinders=(), threads_per_block=128):
+        """planes [(p0, up)], spheres [(c, r)], cylinders [(c, axis, r)] as for oracle.Scene"""
+        X = np.ascontiguousarray(X, np.float32); Tet = np.ascontiguousarray(Tet, np.uint32)
+        self.nV, self.nT = X.shape[0], Tet.shape[0]
+        mass = np.ascontiguousarray(np.broadcast_to(np.asarray(mass, np.float32), (self.nV,)))
+        mu = np.ascontiguousarray(np.broadcast_to(np.asarray(mu, np.float32), (self.nT,)))
+        dbc = None if DBC is None else np.ascontiguousarray(DBC, np.float32)
+        pl = np.ascontiguousarray(np.array([np.concatenate([p[0], p[1]]) for p in planes], np.float32).reshape(-1))
+        sp = np.ascontiguousarray(np.array([np.concatenate([s[0], [s[1]]]) for s in spheres], np.float32).reshape(-1))
+        cy = np.ascontiguousarray(np.array([np.concatenate([c[0], c[1], [c[2]]]) for c in cylinders], np.float32).reshape(-1))
+        p = lambda a: None if a is None or a.size == 0 else a.ctypes.data
+        self._h = lib().ref_create(self.nV, self.nT, p(X), p(Tet), p(mass), p(mu), p(dbc), len(planes), p(pl), len(spheres), p(sp),
+                                   len(cylinders), p(cy), threads_per_block)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().ref_destroy(self._h)
+            self._h = None
+
+    def step(self, n=1, dt=1 / 60, gravity=9.8, rho=0.9992, muN=0.5, muT=0.5, num_iterations=100, perf=False):
+        rc = lib().ref_step(self._h, np.float32(dt), gravity, rho, muN, muT, num_iterations, n, int(perf))
+        if rc:
+            raise RuntimeError(f"reference harness CUDA error {rc}")
+
+    def sync(self):
+        return lib().ref_sync()
+
+    def reset(self):
+        lib().ref_reset(self._h)
+
+    def get(self):
+        X = np.zeros((self.nV, 3), np.float32); V = np.zeros_like(X); XT = np.zeros_like(X)
+        lib().ref_get(self._h, X.ctypes.data, V.ctypes.data, XT.ctypes.data)
+        return X, V, XT
+
+    def set(self, X=None, V=None, XTilde=None):
+        a = [None if t is None else np.ascontiguousarray(t, np.float32) for t in (X, V, XTilde)]
+        lib().ref_set(self._h, *[None if t is None else t.ctypes.data for t in a])
+
+    def setup(self, dt):
+        md = np.zeros(self.nV, np.float32); c = np.zeros(self.nV, np.float32)
+        B = np.zeros((self.nT, 3, 3), np.float32); V0 = np.zeros(self.nT, np.float32)
+        lib().ref_get_setup(self._h, np.float32(dt), md.ctypes.data, c.ctypes.data, B.ctypes.data, V0.ctypes.data)
+        return md, c, B.transpose(0, 2, 1).copy(), V0     # glm [col][row] -> row-major
+
+    def perf(self):
+        out = np.zeros(4, np.float32)
+        lib().ref_get_perf(self._h, out.ctypes.data)
+        return out
+
+
+def rotation(F):
+    F = np.ascontiguousarray(F, np.float32).reshape(-1, 9)
+    R = np.zeros_like(F)
+    rc = lib().ref_rotation(F.shape[0], F.ctypes.data, R.ctypes.data)
+    if rc:
+        raise RuntimeError(f"reference harness CUDA error {rc}")
+    return R.reshape(-1, 3, 3)

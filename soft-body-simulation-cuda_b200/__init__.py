@@ -1,0 +1,378 @@
+"""B200-native projective-dynamics step engine -- Python host bindings over the C ABI.
+
+The product is the shared library `libpd_b200.so` (CUDA kernels for sm_100a + C++ host code,
+sources under csrc/, C ABI in include/pd_b200.h).  This module only binds it with ctypes so
+that tests and bench.py can drive it; it contains no numerics and has NO CPU fallback: the
+engine constructors raise if the library or a sm_100 GPU is missing.
+
+The class/method names mirror the reference's interface for this path
+(src/simulation/solver/solver.h:11-28, projective/pdSolver.h:12-44,
+src/simulation/simulationContext.h:17-84):  SolverParams, PdSolver.Update/Reset/SetPerf/
+GetPerformanceData/SetGlobalSolver, SimulationContext.Update/Reset.
+
+Import with  importlib.import_module("soft-body-simulation-cuda_b200")  (the hyphens rule out
+a plain `import` statement).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpd_b200.so")
+
+PD_JACOBI, PD_CHOLESKY, PD_PCG_JACOBI = 0, 1, 2
+PD_PLANE, PD_SPHERE, PD_CYLINDER = 0, 1, 2
+
+
+class PdError(RuntimeError):
+    pass
+
+
+class pd_fixed_body(C.Structure):
+    _fields_ = [("type", C.c_int), ("model", C.c_float * 16), ("radius", C.c_float)]
+
+
+class pd_params(C.Structure):
+    _fields_ = [("dt", C.c_float), ("gravity", C.c_float), ("muN", C.c_float), ("muT", C.c_float),
+                ("rho", C.c_float), ("tol", C.c_float), ("damp", C.c_float),
+                ("num_iterations", C.c_int), ("global_solver", C.c_int), ("pcg_max_iter", C.c_int),
+                ("pcg_tol", C.c_float), ("handle_collision", C.c_int), ("threads_per_block", C.c_int)]
+
+
+class pd_scene_desc(C.Structure):
+    _fields_ = [("num_verts", C.c_int), ("num_tets", C.c_int), ("X", C.c_void_p), ("Tet", C.c_void_p),
+                ("mass", C.c_void_p), ("mu", C.c_void_p), ("DBC", C.c_void_p),
+                ("num_fixed", C.c_int), ("fixed", C.POINTER(pd_fixed_body))]
+
+
+class pd_engine_options(C.Structure):
+    _fields_ = [("device", C.c_int), ("rot_mode", C.c_int), ("reorder", C.c_int), ("use_graph", C.c_int),
+                ("ctas_per_sm", C.c_int)]
+
+
+class pd_perf(C.Structure):
+    _fields_ = [("local_step_ms", C.c_float), ("global_step_ms", C.c_float), ("collision_fixed_ms", C.c_float),
+                ("collision_mesh_ms", C.c_float), ("step_ms_total", C.c_double), ("steps", C.c_longlong),
+                ("pd_iterations", C.c_longlong), ("inner_iterations", C.c_longlong), ("kernel_launches", C.c_longlong)]
+
+
+# every symbol include/pd_b200.h declares: name -> (restype, argtypes)
+_VP, _I, _F, _CP = C.c_void_p, C.c_int, C.c_float, C.c_char_p
+_PI, _PF = C.POINTER(C.c_int), C.POINTER(C.c_float)
+SYMBOLS = {
+    "pd_last_error": (_CP, []),
+    "pd_version": (_CP, []),
+    "pd_default_params": (None, [C.POINTER(pd_params)]),
+    "pd_default_options": (None, [C.POINTER(pd_engine_options)]),
+    "pd_scene_load_json": (_VP, [_CP, _CP, _CP]),
+    "pd_scene_from_desc": (_VP, [C.POINTER(pd_scene_desc), C.POINTER(pd_params)]),
+    "pd_scene_kuhn_grid": (_VP, [_I, _I, _I, _F, _F, C.c_uint32, _VP, _F, _F]),
+    "pd_scene_free": (None, [_VP]),
+    "pd_scene_counts": (_I, [_VP, _PI, _PI, _PI, _PI]),
+    "pd_scene_get": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "pd_scene_get_params": (_I, [_VP, C.POINTER(pd_params)]),
+    "pd_scene_set_params": (_I, [_VP, C.POINTER(pd_params)]),
+    "pd_scene_add_fixed": (_I, [_VP, C.POINTER(pd_fixed_body)]),
+    "pd_scene_write_tetgen": (_I, [_VP, _CP, _CP]),
+    "pd_load_node": (_I, [_CP, _I, C.POINTER(_VP), _PI]),
+    "pd_load_ele": (_I, [_CP, _I, C.POINTER(_VP), _PI]),
+    "pd_free": (None, [_VP]),
+    "pd_model_matrix": (None, [_VP, _VP, _VP, _I, _VP]),
+    "pd_transform_vertices": (None, [_VP, _I, _VP]),
+    "pd_plane_up": (None, [_VP, _VP]),
+    "pd_layout_build": (_VP, [_VP, _I]),
+    "pd_layout_free": (None, [_VP]),
+    "pd_layout_counts": (_I, [_VP, _PI, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t), _PI]),
+    "pd_layout_get": (_I, [_VP] * 9),
+    "pd_morton_keys": (_I, [_VP, _VP, _I, _VP]),
+    "pd_partition_vertices": (_I, [_I, _I, _VP]),
+    "pd_create": (_VP, [_VP, C.POINTER(pd_engine_options)]),
+    "pd_create_from_json": (_VP, [_CP, _CP, _CP, C.POINTER(pd_engine_options)]),
+    "pd_destroy": (None, [_VP]),
+    "pd_step": (_I, [_VP, _I]),
+    "pd_synchronize": (_I, [_VP]),
+    "pd_step_timed": (_I, [_VP, _I, _PF]),
+    "pd_set_params": (_I, [_VP, C.POINTER(pd_params)]),
+    "pd_get_params": (_I, [_VP, C.POINTER(pd_params)]),
+    "pd_set_global_solver": (_I, [_VP, _I]),
+    "pd_reset": (_I, [_VP]),
+    "pd_set_perf": (_I, [_VP, _I]),
+    "pd_get_perf": (_I, [_VP, C.POINTER(pd_perf)]),
+    "pd_download": (_I, [_VP, _VP, _VP, _VP]),
+    "pd_upload_state": (_I, [_VP, _VP, _VP, _VP]),
+    "pd_step_host": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "pd_update_device": (_I, [_VP, _I, _VP, _VP, _VP]),
+    "pd_get_setup": (_I, [_VP, _VP, _VP, _VP, _VP]),
+    "pd_time_kernels": (_I, [_VP, _I, _PF, _PF]),
+    "pd_engine_info": (_I, [_VP, _PI, _PI, _PI, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), _PI]),
+    "pd_rotation_batch": (_I, [_I, _I, _I, _VP, _VP, _VP]),
+    "pd_alloc_pinned": (_VP, [C.c_size_t]),
+    "pd_free_pinned": (None, [_VP]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libpd_b200.so (built by build.py / __graft_entry__.build()); fail loudly if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PdError(f"{LIB_PATH} is missing: build it with `python {os.path.join(_HERE, 'build.py')}`; "
+                          "there is no CPU fallback for the PD engine")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)          # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _err():
+    return lib().pd_last_error().decode()
+
+
+def _check(rc):
+    if rc != 0:
+        raise PdError(f"pd_b200 error {rc}: {_err()}")
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+class SolverParams:
+    """SolverParams<float> (src/def.h:82-100)."""
+
+    def __init__(self, **kw):
+        self.c = pd_params()
+        lib().pd_default_params(C.byref(self.c))
+        for k, v in kw.items():
+            self[k] = v
+
+    _alias = {"numIterations": "num_iterations", "globalSolver": "global_solver", "handleCollision": "handle_collision"}
+
+    def __setitem__(self, k, v):
+        k = self._alias.get(k, k)
+        if not hasattr(self.c, k):
+            raise KeyError(k)
+        if k == "dt":
+            v = float(np.float32(v))
+        setattr(self.c, k, v)
+
+    def __getitem__(self, k):
+        return getattr(self.c, self._alias.get(k, k))
+
+
+def fixed_body(kind, pos=(0, 0, 0), rot=(0, 0, 0), scale=(1, 1, 1), radius=1.0):
+    """Build a pd_fixed_body the way Context::ReadFixedBodies does (context.cpp:222-317)."""
+    fb = pd_fixed_body()
+    fb.type = kind
+    M = np.zeros(16, np.float32)
+    if kind == PD_SPHERE:
+        scale = (radius, radius, radius)
+    elif kind == PD_CYLINDER:
+        radius = scale[0]
+        scale = (scale[0], scale[1], scale[0])
+    lib().pd_model_matrix(_p(np.asarray(pos, np.float32)), _p(np.asarray(rot, np.float32)),
+                          _p(np.asarray(scale, np.float32)), 0, _p(M))
+    fb.model[:] = M.tolist()
+    fb.radius = float(radius)
+    return fb
+
+
+class Scene:
+    """Host-side merged scene: what DataLoader::AllocData + Impl::Init produce (no GPU needed)."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise PdError(_err())
+        self._h = handle
+
+    @classmethod
+    def from_json(cls, json_path, context_name=None, asset_root=None):
+        enc = lambda s: None if s is None else str(s).encode()
+        return cls(lib().pd_scene_load_json(enc(json_path), enc(context_name), enc(asset_root)))
+
+    @classmethod
+    def from_arrays(cls, X, Tet, mass, mu, DBC=None, fixed=(), params=None):
+        X = np.ascontiguousarray(X, np.float32); Tet = np.ascontiguousarray(Tet, np.uint32)
+        nV, nT = X.shape[0], Tet.shape[0]
+        mass = np.ascontiguousarray(np.broadcast_to(np.asarray(mass, np.float32), (nV,)))
+        mu = np.ascontiguousarray(np.broadcast_to(np.asarray(mu, np.float32), (nT,)))
+        dbc = None if DBC is None else np.ascontiguousarray(DBC, np.float32)
+        arr = (pd_fixed_body * max(len(fixed), 1))(*fixed)
+        d = pd_scene_desc(nV, nT, _p(X), _p(Tet), _p(mass), _p(mu), _p(dbc), len(fixed), arr)
+        return cls(lib().pd_scene_from_desc(C.byref(d), C.byref(params.c) if params else None))
+
+    @classmethod
+    def kuhn_grid(cls, nx, ny, nz, h=1.0, jitter=0.05, seed=12345, origin=(0, 0, 0), mass=1.0, mu=2e5):
+        o = np.asarray(origin, np.float32)
+        return cls(lib().pd_scene_kuhn_grid(nx, ny, nz, h, jitter, seed, _p(o), mass, mu))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.pd_scene_free(self._h)
+            self._h = None
+
+    def counts(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(lib().pd_scene_counts(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
+    def arrays(self):
+        nV, nT, nF, nB = self.counts()
+        X = np.zeros((nV, 3), np.float32); T = np.zeros((nT, 4), np.uint32)
+        mass = np.zeros(nV, np.float32); mu = np.zeros(nT, np.float32); dbc = np.zeros(nV, np.float32)
+        fixed = (pd_fixed_body * max(nF, 1))()
+        bvs = np.zeros(max(nB, 1), np.int32)
+        _check(lib().pd_scene_get(self._h, _p(X), _p(T), _p(mass), _p(mu), _p(dbc), C.cast(fixed, C.c_void_p), _p(bvs)))
+        return dict(X=X, Tet=T, mass=mass, mu=mu, DBC=dbc, fixed=[fixed[i] for i in range(nF)], body_vert_start=bvs[:nB])
+
+    @property
+    def params(self):
+        p = SolverParams()
+        _check(lib().pd_scene_get_params(self._h, C.byref(p.c)))
+        return p
+
+    @params.setter
+    def params(self, p):
+        _check(lib().pd_scene_set_params(self._h, C.byref(p.c)))
+
+    def add_fixed(self, fb):
+        _check(lib().pd_scene_add_fixed(self._h, C.byref(fb)))
+
+    def write_tetgen(self, node_path, ele_path):
+        _check(lib().pd_scene_write_tetgen(self._h, str(node_path).encode(), str(ele_path).encode()))
+
+    def layout(self, reorder=True):
+        return Layout(self, reorder)
+
+
+class Layout:
+    """Device layout (tet order, vertex renumbering, tile records, slot CSR), host only."""
+
+    def __init__(self, scene, reorder=True):
+        self._h = lib().pd_layout_build(scene._h, int(reorder))
+        if not self._h:
+            raise PdError(_err())
+        nV, nT, _, _ = scene.counts()
+        nt, ns, rb, ml = C.c_int(), C.c_uint32(), C.c_size_t(), C.c_int()
+        _check(lib().pd_layout_counts(self._h, C.byref(nt), C.byref(ns), C.byref(rb), C.byref(ml)))
+        self.num_tiles, self.num_slots, self.record_bytes, self.max_local = nt.value, ns.value, rb.value, ml.value
+        self.tet_order = np.zeros(nT, np.uint32); self.vert_order = np.zeros(nV, np.uint32)
+        self.tet_new = np.zeros((nT, 4), np.uint32)
+        self.tile_tet_start = np.zeros(self.num_tiles + 1, np.uint32)
+        self.tile_rec_off = np.zeros(self.num_tiles + 1, np.uint64)
+        self.records = np.zeros(self.record_bytes, np.uint8)
+        self.vslot_ptr = np.zeros(nV + 1, np.uint32); self.vslot = np.zeros(self.num_slots, np.uint32)
+        _check(lib().pd_layout_get(self._h, _p(self.tet_order), _p(self.vert_order), _p(self.tet_new), _p(self.tile_tet_start),
+                                   _p(self.tile_rec_off), _p(self.records), _p(self.vslot_ptr), _p(self.vslot)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.pd_layout_free(self._h)
+            self._h = None
+
+
+class PdSolver:
+    """PdSolver behind SimulationCUDAContext, on one B200 (pdSolver.h:12-44, simulationContext.h:17-84)."""
+
+    SolverType = {"Jacobi": PD_JACOBI, "CuSolverCholesky": PD_CHOLESKY, "EigenCholesky": PD_CHOLESKY, "PCGJacobi": PD_PCG_JACOBI}
+
+    def __init__(self, scene, device=0, rot_mode=0, reorder=1, use_graph=1, ctas_per_sm=0):
+        o = pd_engine_options(device, rot_mode, reorder, use_graph, ctas_per_sm)
+        self._h = lib().pd_create(scene._h, C.byref(o))
+        if not self._h:
+            raise PdError(_err())
+        self.num_verts, self.num_tets = scene.counts()[:2]
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.pd_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # --- Solver<float> interface
+    def Update(self, n_steps=1, params=None):
+        if params is not None:
+            _check(lib().pd_set_params(self._h, C.byref(params.c)))
+        _check(lib().pd_step(self._h, n_steps))
+
+    def step_timed(self, n_steps):
+        """n x Update bracketed by CUDA events on the engine's stream -> device milliseconds."""
+        ms = C.c_float()
+        _check(lib().pd_step_timed(self._h, n_steps, C.byref(ms)))
+        return ms.value
+
+    def Reset(self):
+        _check(lib().pd_reset(self._h))
+
+    def SetPerf(self, on):
+        _check(lib().pd_set_perf(self._h, int(on)))
+
+    def SetGlobalSolver(self, solver):
+        _check(lib().pd_set_global_solver(self._h, self.SolverType.get(solver, solver)))
+
+    def GetPerformanceData(self):
+        p = pd_perf()
+        _check(lib().pd_get_perf(self._h, C.byref(p)))
+        return [("local step", p.local_step_ms), ("global step", p.global_step_ms),
+                ("collision handling(fixed)", p.collision_fixed_ms), ("collision handling(mesh)", p.collision_mesh_ms)], p
+
+    # --- state
+    def synchronize(self):
+        _check(lib().pd_synchronize(self._h))
+
+    def set_params(self, params):
+        _check(lib().pd_set_params(self._h, C.byref(params.c)))
+
+    def get_params(self):
+        p = SolverParams()
+        _check(lib().pd_get_params(self._h, C.byref(p.c)))
+        return p
+
+    def download(self):
+        X = np.zeros((self.num_verts, 3), np.float32); V = np.zeros_like(X); XT = np.zeros_like(X)
+        _check(lib().pd_download(self._h, _p(X), _p(V), _p(XT)))
+        return X, V, XT
+
+    def upload(self, X=None, V=None, XTilde=None):
+        a = [None if t is None else np.ascontiguousarray(t, np.float32) for t in (X, V, XTilde)]
+        _check(lib().pd_upload_state(self._h, *[_p(t) for t in a]))
+
+    def step_host_ptr(self, n, xin, vin, xtin, xout, vout, xtout):
+        """e2e step on raw host pointers (ints), e.g. pinned buffers."""
+        _check(lib().pd_step_host(self._h, n, xin, vin, xtin, xout, vout, xtout))
+
+    def update_device_ptr(self, n, dX, dV, dXT):
+        _check(lib().pd_update_device(self._h, n, dX, dV, dXT))
+
+    def setup(self):
+        md = np.zeros(self.num_verts, np.float32); c = np.zeros(self.num_verts, np.float32)
+        B = np.zeros((self.num_tets, 9), np.float32); V0 = np.zeros(self.num_tets, np.float32)
+        _check(lib().pd_get_setup(self._h, _p(md), _p(c), _p(B), _p(V0)))
+        return md, c, B.reshape(-1, 3, 3), V0
+
+    def time_kernels(self, reps=20):
+        a, b = C.c_float(), C.c_float()
+        _check(lib().pd_time_kernels(self._h, reps, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def info(self):
+        nv, nt, ntl, lg = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        ns = C.c_uint32(); sb, db = C.c_size_t(), C.c_size_t()
+        _check(lib().pd_engine_info(self._h, C.byref(nv), C.byref(nt), C.byref(ntl), C.byref(ns), C.byref(sb), C.byref(db), C.byref(lg)))
+        return dict(num_verts=nv.value, num_tets=nt.value, num_tiles=ntl.value, num_slots=ns.value,
+                    tile_stream_bytes=sb.value, device_bytes=db.value, local_grid=lg.value)
+
+
+def rotation_batch(F, rot_mode=0, device=0):
+    """Corotational projection of a batch of 3x3 matrices on the GPU (test hook)."""
+    F = np.ascontiguousarray(F, np.float32).reshape(-1, 9)
+    R = np.zeros_like(F); used = np.zeros(F.shape[0], np.int32)
+    _check(lib().pd_rotation_batch(device, rot_mode, F.shape[0], _p(F), _p(R), _p(used)))
+    return R.reshape(-1, 3, 3), used

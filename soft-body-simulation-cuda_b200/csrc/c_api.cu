@@ -1,0 +1,361 @@
+// extern "C" boundary (include/pd_b200.h).  No exceptions cross it.
+#include "../../include/pd_b200.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <exception>
+#include <string>
+
+#include <cuda_runtime.h>
+
+#include "layout.hpp"
+#include "pd_engine.hpp"
+#include "scene.hpp"
+
+using namespace pdb200;
+
+struct pd_scene { Scene s; };
+struct pd_layout { Layout L; };
+struct pd_engine { Engine* e; };
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& m) { g_err = m; return code; }
+
+#define PD_TRY try {
+#define PD_CATCH_INT                                                                                   \
+    } catch (const std::exception& ex) {                                                              \
+        const std::string m = ex.what();                                                               \
+        int code = PD_ERR_INVALID;                                                                     \
+        if (m.find("CUDA") != std::string::npos) code = PD_ERR_CUDA;                                   \
+        else if (m.find("open") != std::string::npos || m.find("json") != std::string::npos) code = PD_ERR_IO; \
+        else if (m.find("outside the PD hot path") != std::string::npos || m.find("out of scope") != std::string::npos) code = PD_ERR_UNSUPPORTED; \
+        return fail(code, m);                                                                          \
+    } catch (...) { return fail(PD_ERR_INVALID, "unknown exception"); }
+#define PD_CATCH_PTR                                                                                   \
+    } catch (const std::exception& ex) { g_err = ex.what(); return nullptr;                           \
+    } catch (...) { g_err = "unknown exception"; return nullptr; }
+
+static void to_c(const SolverParams& p, pd_params* o)
+{
+    o->dt = p.dt; o->gravity = p.gravity; o->muN = p.muN; o->muT = p.muT; o->rho = p.rho; o->tol = p.tol; o->damp = p.damp;
+    o->num_iterations = p.numIterations; o->global_solver = p.globalSolver; o->pcg_max_iter = p.pcgMaxIter;
+    o->pcg_tol = p.pcgTol; o->handle_collision = p.handleCollision; o->threads_per_block = p.threadsPerBlock;
+}
+static void from_c(const pd_params* i, SolverParams& p)
+{
+    p.dt = i->dt; p.gravity = i->gravity; p.muN = i->muN; p.muT = i->muT; p.rho = i->rho; p.damp = i->damp;
+    p.tol = i->tol < 1e-6f ? 1e-6f : i->tol;     // CopyUIToParams clamp, simulationContext.cpp:28-31
+    p.numIterations = i->num_iterations; p.globalSolver = i->global_solver; p.pcgMaxIter = i->pcg_max_iter;
+    p.pcgTol = i->pcg_tol; p.handleCollision = i->handle_collision; p.threadsPerBlock = i->threads_per_block;
+}
+
+extern "C" {
+
+const char* pd_last_error(void) { return g_err.c_str(); }
+const char* pd_version(void) { return "pd_b200 0.1 (sm_100a)"; }
+
+void pd_default_params(pd_params* p) { SolverParams d; to_c(d, p); }
+void pd_default_options(pd_engine_options* o) { o->device = 0; o->rot_mode = 0; o->reorder = 1; o->use_graph = 1; o->ctas_per_sm = 0; }
+
+// ------------------------------------------------------------------ scene
+pd_scene* pd_scene_load_json(const char* json_path, const char* context_name, const char* asset_root)
+{
+    PD_TRY
+    if (!json_path) { g_err = "json_path is NULL"; return nullptr; }
+    pd_scene* s = new pd_scene;
+    try { s->s = load_context_json(json_path, context_name ? context_name : "", asset_root ? asset_root : ""); }
+    catch (...) { delete s; throw; }
+    return s;
+    PD_CATCH_PTR
+}
+
+pd_scene* pd_scene_from_desc(const pd_scene_desc* d, const pd_params* params)
+{
+    PD_TRY
+    if (!d || d->num_verts <= 0 || d->num_tets <= 0 || !d->X || !d->Tet || !d->mass || !d->mu) { g_err = "invalid scene description"; return nullptr; }
+    for (size_t i = 0; i < 4 * (size_t)d->num_tets; ++i)
+        if (d->Tet[i] >= (uint32_t)d->num_verts) { g_err = "tet references vertex out of range"; return nullptr; }
+    pd_scene* s = new pd_scene;
+    Scene& sc = s->s;
+    sc.name = "desc";
+    sc.numVerts = d->num_verts; sc.numTets = d->num_tets;
+    sc.X.assign(d->X, d->X + 3 * (size_t)d->num_verts);
+    sc.Tet.assign(d->Tet, d->Tet + 4 * (size_t)d->num_tets);
+    sc.mass.assign(d->mass, d->mass + d->num_verts);
+    sc.mu.assign(d->mu, d->mu + d->num_tets);
+    sc.lambda.assign((size_t)d->num_tets, 0.f);
+    if (d->DBC) sc.DBC.assign(d->DBC, d->DBC + d->num_verts); else sc.DBC.assign((size_t)d->num_verts, 0.f);
+    sc.bodyVertStart = {0}; sc.bodyTetStart = {0}; sc.bodyNames = {"desc"};
+    for (int i = 0; i < d->num_fixed; ++i) {
+        FixedBody f; f.type = d->fixed[i].type; std::memcpy(f.model, d->fixed[i].model, 64); f.radius = d->fixed[i].radius;
+        sc.fixed.push_back(f);
+    }
+    if (params) from_c(params, sc.params);
+    return s;
+    PD_CATCH_PTR
+}
+
+pd_scene* pd_scene_kuhn_grid(int nx, int ny, int nz, float h, float jitter, uint32_t seed, const float origin[3], float mass, float mu)
+{
+    PD_TRY
+    if (nx <= 0 || ny <= 0 || nz <= 0) { g_err = "grid dimensions must be positive"; return nullptr; }
+    pd_scene* s = new pd_scene;
+    const float o0[3] = {0, 0, 0};
+    s->s = make_kuhn_grid(nx, ny, nz, h, jitter, seed, origin ? origin : o0, mass, mu);
+    return s;
+    PD_CATCH_PTR
+}
+
+void pd_scene_free(pd_scene* s) { delete s; }
+
+int pd_scene_counts(const pd_scene* s, int* nv, int* nt, int* nf, int* nb)
+{
+    if (!s) return fail(PD_ERR_INVALID, "scene is NULL");
+    if (nv) *nv = s->s.numVerts;
+    if (nt) *nt = s->s.numTets;
+    if (nf) *nf = (int)s->s.fixed.size();
+    if (nb) *nb = (int)s->s.bodyVertStart.size();
+    return PD_OK;
+}
+
+int pd_scene_get(const pd_scene* s, float* X, uint32_t* Tet, float* mass, float* mu, float* DBC, pd_fixed_body* fixed, int* bvs)
+{
+    if (!s) return fail(PD_ERR_INVALID, "scene is NULL");
+    const Scene& sc = s->s;
+    if (X) std::memcpy(X, sc.X.data(), sc.X.size() * 4);
+    if (Tet) std::memcpy(Tet, sc.Tet.data(), sc.Tet.size() * 4);
+    if (mass) std::memcpy(mass, sc.mass.data(), sc.mass.size() * 4);
+    if (mu) std::memcpy(mu, sc.mu.data(), sc.mu.size() * 4);
+    if (DBC) std::memcpy(DBC, sc.DBC.data(), sc.DBC.size() * 4);
+    if (fixed)
+        for (size_t i = 0; i < sc.fixed.size(); ++i) {
+            fixed[i].type = sc.fixed[i].type; std::memcpy(fixed[i].model, sc.fixed[i].model, 64); fixed[i].radius = sc.fixed[i].radius;
+        }
+    if (bvs) for (size_t i = 0; i < sc.bodyVertStart.size(); ++i) bvs[i] = sc.bodyVertStart[i];
+    return PD_OK;
+}
+
+int pd_scene_get_params(const pd_scene* s, pd_params* out)
+{
+    if (!s || !out) return fail(PD_ERR_INVALID, "NULL argument");
+    to_c(s->s.params, out);
+    return PD_OK;
+}
+int pd_scene_set_params(pd_scene* s, const pd_params* in)
+{
+    if (!s || !in) return fail(PD_ERR_INVALID, "NULL argument");
+    from_c(in, s->s.params);
+    return PD_OK;
+}
+int pd_scene_add_fixed(pd_scene* s, const pd_fixed_body* fb)
+{
+    if (!s || !fb) return fail(PD_ERR_INVALID, "NULL argument");
+    if (fb->type < 0 || fb->type > 2) return fail(PD_ERR_INVALID, "unknown fixed body type");
+    FixedBody f; f.type = fb->type; std::memcpy(f.model, fb->model, 64); f.radius = fb->radius;
+    s->s.fixed.push_back(f);
+    return PD_OK;
+}
+int pd_scene_write_tetgen(const pd_scene* s, const char* np, const char* ep)
+{
+    PD_TRY
+    if (!s || !np || !ep) return fail(PD_ERR_INVALID, "NULL argument");
+    write_tetgen(s->s, np, ep);
+    return PD_OK;
+    PD_CATCH_INT
+}
+
+int pd_load_node(const char* path, int centralize, float** X, int* nv)
+{
+    PD_TRY
+    if (!path || !X || !nv) return fail(PD_ERR_INVALID, "NULL argument");
+    std::vector<float> v = load_node_file(path, centralize != 0);
+    *X = (float*)std::malloc(v.size() * 4);
+    std::memcpy(*X, v.data(), v.size() * 4);
+    *nv = (int)(v.size() / 3);
+    return PD_OK;
+    PD_CATCH_INT
+}
+int pd_load_ele(const char* path, int start_index, uint32_t** T, int* nt)
+{
+    PD_TRY
+    if (!path || !T || !nt) return fail(PD_ERR_INVALID, "NULL argument");
+    std::vector<uint32_t> v = load_ele_file(path, start_index);
+    *T = (uint32_t*)std::malloc(v.size() * 4);
+    std::memcpy(*T, v.data(), v.size() * 4);
+    *nt = (int)(v.size() / 4);
+    return PD_OK;
+    PD_CATCH_INT
+}
+void pd_free(void* p) { std::free(p); }
+
+void pd_model_matrix(const float pos[3], const float rot[3], const float scale[3], int sbo, float M[16]) { model_matrix(pos, rot, scale, sbo != 0, M); }
+void pd_transform_vertices(float* X, int nv, const float M[16]) { transform_vertices(X, nv, M); }
+void pd_plane_up(const float M[16], float up[3]) { plane_up(M, up); }
+
+// ------------------------------------------------------------------ layout
+pd_layout* pd_layout_build(const pd_scene* s, int reorder)
+{
+    PD_TRY
+    if (!s) { g_err = "scene is NULL"; return nullptr; }
+    pd_layout* l = new pd_layout;
+    try { build_layout(s->s.numVerts, s->s.numTets, s->s.X.data(), s->s.Tet.data(), s->s.mu.data(), reorder != 0, l->L); }
+    catch (...) { delete l; throw; }
+    return l;
+    PD_CATCH_PTR
+}
+void pd_layout_free(pd_layout* l) { delete l; }
+int pd_layout_counts(const pd_layout* l, int* nTiles, uint32_t* nSlots, size_t* recBytes, int* maxLocal)
+{
+    if (!l) return fail(PD_ERR_INVALID, "layout is NULL");
+    if (nTiles) *nTiles = l->L.nTiles;
+    if (nSlots) *nSlots = l->L.nSlots;
+    if (recBytes) *recBytes = l->L.records.size();
+    if (maxLocal) *maxLocal = l->L.maxLocal;
+    return PD_OK;
+}
+int pd_layout_get(const pd_layout* l, uint32_t* tetOrder, uint32_t* vertOrder, uint32_t* tetNew, uint32_t* tileTetStart,
+                  uint64_t* tileRecOff, uint8_t* records, uint32_t* vslotPtr, uint32_t* vslot)
+{
+    if (!l) return fail(PD_ERR_INVALID, "layout is NULL");
+    const Layout& L = l->L;
+    if (tetOrder) std::memcpy(tetOrder, L.tetOrder.data(), L.tetOrder.size() * 4);
+    if (vertOrder) std::memcpy(vertOrder, L.vertOrder.data(), L.vertOrder.size() * 4);
+    if (tetNew) std::memcpy(tetNew, L.tetNew.data(), L.tetNew.size() * 4);
+    if (tileTetStart) std::memcpy(tileTetStart, L.tileTetStart.data(), L.tileTetStart.size() * 4);
+    if (tileRecOff) std::memcpy(tileRecOff, L.tileRecOff.data(), L.tileRecOff.size() * 8);
+    if (records) std::memcpy(records, L.records.data(), L.records.size());
+    if (vslotPtr) std::memcpy(vslotPtr, L.vslotPtr.data(), L.vslotPtr.size() * 4);
+    if (vslot) std::memcpy(vslot, L.vslot.data(), L.vslot.size() * 4);
+    return PD_OK;
+}
+int pd_morton_keys(const float* X, const uint32_t* Tet, int nT, uint32_t* keys)
+{
+    PD_TRY
+    if (!X || !Tet || !keys || nT < 0) return fail(PD_ERR_INVALID, "bad argument");
+    std::vector<uint32_t> k;
+    morton_keys(X, Tet, nT, k);
+    std::memcpy(keys, k.data(), k.size() * 4);
+    return PD_OK;
+    PD_CATCH_INT
+}
+int pd_partition_vertices(int nV, int world, int* vbeg)
+{
+    if (nV < 0 || world <= 0 || !vbeg) return fail(PD_ERR_INVALID, "bad argument");
+    std::vector<int> v;
+    partition_vertices(nV, world, v);
+    std::memcpy(vbeg, v.data(), v.size() * sizeof(int));
+    return PD_OK;
+}
+
+// ------------------------------------------------------------------ engine
+pd_engine* pd_create(const pd_scene* s, const pd_engine_options* o)
+{
+    PD_TRY
+    if (!s) { g_err = "scene is NULL"; return nullptr; }
+    EngineOptions eo;
+    if (o) { eo.device = o->device; eo.rotMode = o->rot_mode; eo.reorder = o->reorder; eo.useGraph = o->use_graph; eo.ctasPerSm = o->ctas_per_sm; }
+    pd_engine* e = new pd_engine{nullptr};
+    try { e->e = new Engine(s->s, eo); } catch (...) { delete e; throw; }
+    return e;
+    PD_CATCH_PTR
+}
+
+pd_engine* pd_create_from_json(const char* json_path, const char* context_name, const char* asset_root, const pd_engine_options* o)
+{
+    pd_scene* s = pd_scene_load_json(json_path, context_name, asset_root);
+    if (!s) return nullptr;
+    pd_engine* e = nullptr;
+    if (s->s.precision != "float" && s->s.precision != "fp32") g_err = "context '" + s->s.name + "' is not a float (PD) context";
+    else e = pd_create(s, o);
+    pd_scene_free(s);
+    return e;
+}
+
+void pd_destroy(pd_engine* e) { if (e) { delete e->e; delete e; } }
+
+#define ENGINE_CALL(body)                                   \
+    PD_TRY                                                  \
+    if (!e || !e->e) return fail(PD_ERR_INVALID, "engine is NULL"); \
+    body;                                                   \
+    return PD_OK;                                           \
+    PD_CATCH_INT
+
+int pd_step(pd_engine* e, int n) { ENGINE_CALL(if (n < 0) return fail(PD_ERR_INVALID, "n_steps < 0"); e->e->step(n)) }
+int pd_synchronize(pd_engine* e) { ENGINE_CALL(e->e->synchronize()) }
+int pd_step_timed(pd_engine* e, int n, float* ms)
+{
+    ENGINE_CALL(if (n < 0 || !ms) return fail(PD_ERR_INVALID, "bad argument"); *ms = e->e->stepTimed(n))
+}
+int pd_set_params(pd_engine* e, const pd_params* p)
+{
+    ENGINE_CALL(if (!p) return fail(PD_ERR_INVALID, "params is NULL"); SolverParams sp = e->e->params(); from_c(p, sp); e->e->setParams(sp))
+}
+int pd_get_params(const pd_engine* e, pd_params* p)
+{
+    if (!e || !e->e || !p) return fail(PD_ERR_INVALID, "NULL argument");
+    to_c(e->e->params(), p);
+    return PD_OK;
+}
+int pd_set_global_solver(pd_engine* e, int solver)
+{
+    ENGINE_CALL(if (solver < 0 || solver > 2) return fail(PD_ERR_INVALID, "unknown solver"); SolverParams sp = e->e->params(); sp.globalSolver = solver; e->e->setParams(sp))
+}
+int pd_reset(pd_engine* e) { ENGINE_CALL(e->e->reset()) }
+int pd_set_perf(pd_engine* e, int on) { ENGINE_CALL(e->e->setPerf(on != 0)) }
+int pd_get_perf(const pd_engine* e, pd_perf* o)
+{
+    if (!e || !e->e || !o) return fail(PD_ERR_INVALID, "NULL argument");
+    const PerfCounters& c = e->e->perf();
+    o->local_step_ms = c.localStep; o->global_step_ms = c.globalStep; o->collision_fixed_ms = c.collisionFixed; o->collision_mesh_ms = c.collisionMesh;
+    o->step_ms_total = c.stepMsTotal; o->steps = c.steps; o->pd_iterations = c.pdIterations; o->inner_iterations = c.innerIterations;
+    o->kernel_launches = c.kernelLaunches;
+    return PD_OK;
+}
+int pd_download(pd_engine* e, float* X, float* V, float* XT) { ENGINE_CALL(e->e->download(X, V, XT)) }
+int pd_upload_state(pd_engine* e, const float* X, const float* V, const float* XT) { ENGINE_CALL(e->e->upload(X, V, XT); e->e->synchronize()) }
+int pd_step_host(pd_engine* e, int n, const float* Xi, const float* Vi, const float* XTi, float* Xo, float* Vo, float* XTo)
+{
+    ENGINE_CALL(if (n < 0) return fail(PD_ERR_INVALID, "n_steps < 0"); e->e->stepHost(n, Xi, Vi, XTi, Xo, Vo, XTo))
+}
+int pd_update_device(pd_engine* e, int n, float* dX, float* dV, float* dXT)
+{
+    ENGINE_CALL(if (n < 0) return fail(PD_ERR_INVALID, "n_steps < 0");
+                e->e->importDevice(dX, dV, dXT); e->e->step(n); e->e->exportDevice(dX, dV, dXT); e->e->synchronize())
+}
+int pd_get_setup(pd_engine* e, float* md, float* mdt2, float* DmInv, float* V0) { ENGINE_CALL(e->e->getSetup(md, mdt2, DmInv, V0)) }
+int pd_time_kernels(pd_engine* e, int reps, float* lms, float* vms)
+{
+    ENGINE_CALL(if (reps <= 0) return fail(PD_ERR_INVALID, "reps <= 0");
+                if (lms) *lms = e->e->timeLocalKernelMs(reps); if (vms) *vms = e->e->timeVertexKernelMs(reps))
+}
+int pd_engine_info(const pd_engine* e, int* nv, int* nt, int* ntiles, uint32_t* nslots, size_t* streamBytes, size_t* devBytes, int* lgrid)
+{
+    if (!e || !e->e) return fail(PD_ERR_INVALID, "engine is NULL");
+    if (nv) *nv = e->e->numVerts();
+    if (nt) *nt = e->e->numTets();
+    if (ntiles) *ntiles = e->e->layout().nTiles;
+    if (nslots) *nslots = e->e->layout().nSlots;
+    if (streamBytes) *streamBytes = e->e->tileStreamBytes();
+    if (devBytes) *devBytes = e->e->deviceBytes();
+    if (lgrid) *lgrid = e->e->localGrid();
+    return PD_OK;
+}
+
+int pd_rotation_batch(int device, int rot_mode, int n, const float* F, float* R, int* used_fast)
+{
+    PD_TRY
+    if (n <= 0 || !F || !R) return fail(PD_ERR_INVALID, "bad argument");
+    rotation_batch(device, rot_mode, n, F, R, used_fast);
+    return PD_OK;
+    PD_CATCH_INT
+}
+
+void* pd_alloc_pinned(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { g_err = "cudaMallocHost failed"; return nullptr; }
+    return p;
+}
+void pd_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

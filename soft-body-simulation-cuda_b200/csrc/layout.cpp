@@ -1,0 +1,260 @@
+// Layout builder (see layout.hpp and DESIGN.md section 3).  Compiled with -ffp-contract=off so
+// the few float operations here (centroids, rest shape) round exactly once per operation and
+// can be reproduced by numpy float32 arithmetic in the tests.
+#include "layout.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+
+namespace pdb200 {
+
+static inline uint32_t spread3(uint32_t x)
+{   // 10 bits -> every third bit
+    x &= 0x3ffu;
+    x = (x | (x << 16)) & 0x030000ffu;
+    x = (x | (x << 8)) & 0x0300f00fu;
+    x = (x | (x << 4)) & 0x030c30c3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+
+void morton_keys(const float* X, const uint32_t* Tet, int nT, std::vector<uint32_t>& keys)
+{
+    keys.assign((size_t)nT, 0u);
+    if (nT == 0) return;
+    std::vector<float> cen((size_t)nT * 3);
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int t = 0; t < nT; ++t) {
+        const uint32_t* tv = Tet + 4 * (size_t)t;
+        for (int k = 0; k < 3; ++k) {
+            const float c = ((X[3 * (size_t)tv[0] + k] + X[3 * (size_t)tv[1] + k]) +
+                             (X[3 * (size_t)tv[2] + k] + X[3 * (size_t)tv[3] + k])) * 0.25f;
+            cen[3 * (size_t)t + k] = c;
+            lo[k] = std::min(lo[k], c);
+            hi[k] = std::max(hi[k], c);
+        }
+    }
+    float ext = std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+    if (!(ext > 0.f)) ext = 1.f;
+    const float scale = 1023.0f / ext;
+    for (int t = 0; t < nT; ++t) {
+        uint32_t q[3];
+        for (int k = 0; k < 3; ++k) {
+            const float f = (cen[3 * (size_t)t + k] - lo[k]) * scale;
+            int qi = (int)f;                       // truncation, f >= 0
+            q[k] = (uint32_t)std::min(std::max(qi, 0), 1023);
+        }
+        keys[t] = spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);
+    }
+}
+
+void rest_shape(const float* X, const uint32_t* Tet, int nT, float* DmInv, float* V0)
+{
+    for (int t = 0; t < nT; ++t) {
+        const uint32_t* tv = Tet + 4 * (size_t)t;
+        const float *x0 = X + 3 * (size_t)tv[0], *x1 = X + 3 * (size_t)tv[1], *x2 = X + 3 * (size_t)tv[2], *x3 = X + 3 * (size_t)tv[3];
+        float m[3][3];   // m[c][r], column c = x_{c+1} - x_0  (glm layout)
+        for (int r = 0; r < 3; ++r) { m[0][r] = x1[r] - x0[r]; m[1][r] = x2[r] - x0[r]; m[2][r] = x3[r] - x0[r]; }
+        const float det = +m[0][0] * (m[1][1] * m[2][2] - m[2][1] * m[1][2])
+                          - m[1][0] * (m[0][1] * m[2][2] - m[2][1] * m[0][2])
+                          + m[2][0] * (m[0][1] * m[1][2] - m[1][1] * m[0][2]);
+        const float ood = 1.0f / det;
+        float inv[3][3];
+        inv[0][0] = +(m[1][1] * m[2][2] - m[2][1] * m[1][2]) * ood;
+        inv[1][0] = -(m[1][0] * m[2][2] - m[2][0] * m[1][2]) * ood;
+        inv[2][0] = +(m[1][0] * m[2][1] - m[2][0] * m[1][1]) * ood;
+        inv[0][1] = -(m[0][1] * m[2][2] - m[2][1] * m[0][2]) * ood;
+        inv[1][1] = +(m[0][0] * m[2][2] - m[2][0] * m[0][2]) * ood;
+        inv[2][1] = -(m[0][0] * m[2][1] - m[2][0] * m[0][1]) * ood;
+        inv[0][2] = +(m[0][1] * m[1][2] - m[1][1] * m[0][2]) * ood;
+        inv[1][2] = -(m[0][0] * m[1][2] - m[1][0] * m[0][2]) * ood;
+        inv[2][2] = +(m[0][0] * m[1][1] - m[1][0] * m[0][1]) * ood;
+        float* B = DmInv + 9 * (size_t)t;
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) B[r * 3 + c] = inv[c][r];
+        V0[t] = std::fabs(det) / 6.0f;
+    }
+}
+
+static inline size_t rup(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// tiles + records + slots for a mesh whose vertex ids are final
+static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv, const float* w, Layout& L)
+{
+    L.tileTetStart.clear(); L.tileRecOff.clear(); L.records.clear();
+    std::vector<int> mark((size_t)nV, -1);
+    std::vector<uint32_t> lidx((size_t)nV, 0);
+    std::vector<uint32_t> slotBase;
+    std::vector<uint32_t> vcount((size_t)nV + 1, 0);
+    L.maxLocal = 0;
+    uint32_t slot = 0;
+    int t0 = 0, tile = 0;
+    std::vector<uint32_t> vl;
+    L.tileTetStart.push_back(0);
+    L.tileRecOff.push_back(0);
+    while (t0 < nT) {
+        // greedy tile: up to TILE_T tets and TILE_NLMAX distinct vertices
+        vl.clear();
+        int t1 = t0;
+        while (t1 < nT && t1 - t0 < TILE_T) {
+            int added = 0;
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t v = tet[4 * (size_t)t1 + k];
+                if (mark[v] != tile) { mark[v] = tile; vl.push_back(v); ++added; }
+            }
+            if ((int)vl.size() > TILE_NLMAX) {       // undo this tet and close the tile
+                for (int a = 0; a < added; ++a) { mark[vl.back()] = -1; vl.pop_back(); }
+                break;
+            }
+            ++t1;
+        }
+        if (t1 == t0) throw std::runtime_error("tile builder: empty tile");
+        std::sort(vl.begin(), vl.end());
+        const uint32_t nLocal = (uint32_t)vl.size(), nTets = (uint32_t)(t1 - t0);
+        for (uint32_t l = 0; l < nLocal; ++l) { lidx[vl[l]] = l; vcount[vl[l] + 1]++; }
+        L.maxLocal = std::max(L.maxLocal, (int)nLocal);
+        const size_t nLp = rup(nLocal, 4), nTp = rup(nTets, 4);
+        const size_t offV = 16, offC = offV + 4 * nLp, offB = offC + 8 * nTp, offW = offB + 36 * nTp,
+                     offIO = offW + 4 * nTp, offI = offIO + rup(2 * ((size_t)nLocal + 1), 16),
+                     recBytes = offI + rup(2 * 4 * (size_t)nTets, 16);
+        const size_t base = L.records.size();
+        L.records.resize(base + recBytes, 0);
+        uint8_t* rec = L.records.data() + base;
+        TileHeader h{nTets, nLocal, slot, (uint32_t)recBytes};
+        std::memcpy(rec, &h, 16);
+        std::memcpy(rec + offV, vl.data(), 4 * (size_t)nLocal);
+        uint16_t* cidx = reinterpret_cast<uint16_t*>(rec + offC);
+        float* Bm = reinterpret_cast<float*>(rec + offB);
+        float* ww = reinterpret_cast<float*>(rec + offW);
+        uint16_t* incOff = reinterpret_cast<uint16_t*>(rec + offIO);
+        uint16_t* inc = reinterpret_cast<uint16_t*>(rec + offI);
+        std::vector<uint16_t> deg((size_t)nLocal + 1, 0);
+        for (uint32_t tl = 0; tl < nTets; ++tl) {
+            const size_t t = (size_t)t0 + tl;
+            for (int k = 0; k < 4; ++k) {
+                const uint16_t l = (uint16_t)lidx[tet[4 * t + k]];
+                cidx[4 * tl + k] = l;
+                deg[l + 1]++;
+            }
+            for (int e = 0; e < 9; ++e) Bm[e * nTp + tl] = DmInv[9 * t + e];
+            ww[tl] = w[t];
+        }
+        for (uint32_t l = 0; l < nLocal; ++l) deg[l + 1] = (uint16_t)(deg[l + 1] + deg[l]);
+        std::memcpy(incOff, deg.data(), 2 * ((size_t)nLocal + 1));
+        std::vector<uint16_t> fill(deg.begin(), deg.end() - 1);
+        for (uint32_t tl = 0; tl < nTets; ++tl)
+            for (int k = 0; k < 4; ++k) inc[fill[cidx[4 * tl + k]]++] = (uint16_t)(tl * 4 + k);
+        slotBase.push_back(slot);
+        slot += nLocal;
+        t0 = t1;
+        ++tile;
+        L.tileTetStart.push_back((uint32_t)t0);
+        L.tileRecOff.push_back((uint64_t)L.records.size());
+    }
+    L.nTiles = tile;
+    L.nSlots = slot;
+    // vertex -> slots CSR, ascending (tiles are visited in ascending order)
+    for (int v = 0; v < nV; ++v) vcount[v + 1] += vcount[v];
+    L.vslotPtr.assign(vcount.begin(), vcount.end());
+    L.vslot.assign((size_t)slot, 0u);
+    std::vector<uint32_t> fillv(vcount.begin(), vcount.end() - 1);
+    for (int ti = 0; ti < L.nTiles; ++ti) {
+        const uint8_t* rec = L.records.data() + L.tileRecOff[ti];
+        TileHeader h; std::memcpy(&h, rec, 16);
+        const uint32_t* vlist = reinterpret_cast<const uint32_t*>(rec + 16);
+        for (uint32_t l = 0; l < h.nLocal; ++l) L.vslot[fillv[vlist[l]]++] = h.slotBase + l;
+    }
+}
+
+void build_layout(int nV, int nT, const float* X, const uint32_t* Tet, const float* mu, bool reorder, Layout& L)
+{
+    L = Layout();
+    L.nV = nV; L.nT = nT;
+    // 1. tet order: stable sort by Morton key of the centroid
+    L.tetOrder.resize((size_t)nT);
+    std::iota(L.tetOrder.begin(), L.tetOrder.end(), 0u);
+    if (reorder && nT > 1) {
+        std::vector<uint32_t> keys;
+        morton_keys(X, Tet, nT, keys);
+        std::stable_sort(L.tetOrder.begin(), L.tetOrder.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    }
+    // 2. vertex renumbering: first touch over the reordered tets; untouched vertices last
+    L.vertNewOfOld.assign((size_t)nV, 0xffffffffu);
+    L.vertOrder.clear(); L.vertOrder.reserve((size_t)nV);
+    for (int t = 0; t < nT; ++t)
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t v = Tet[4 * (size_t)L.tetOrder[t] + k];
+            if (v >= (uint32_t)nV) throw std::runtime_error("tet references vertex out of range");
+            if (L.vertNewOfOld[v] == 0xffffffffu) { L.vertNewOfOld[v] = (uint32_t)L.vertOrder.size(); L.vertOrder.push_back(v); }
+        }
+    for (int v = 0; v < nV; ++v)
+        if (L.vertNewOfOld[v] == 0xffffffffu) { L.vertNewOfOld[v] = (uint32_t)L.vertOrder.size(); L.vertOrder.push_back((uint32_t)v); }
+    L.tetNew.resize((size_t)nT * 4);
+    for (int t = 0; t < nT; ++t)
+        for (int k = 0; k < 4; ++k) L.tetNew[4 * (size_t)t + k] = L.vertNewOfOld[Tet[4 * (size_t)L.tetOrder[t] + k]];
+    // 3. rest shape in the ORIGINAL numbering/order (same arithmetic as the reference), then permuted
+    std::vector<float> B((size_t)nT * 9), V0((size_t)nT), Br((size_t)nT * 9), wr((size_t)nT);
+    rest_shape(X, Tet, nT, B.data(), V0.data());
+    for (int t = 0; t < nT; ++t) {
+        const size_t o = L.tetOrder[t];
+        std::memcpy(&Br[9 * (size_t)t], &B[9 * o], 36);
+        wr[t] = std::fabs(V0[o]) * mu[o];
+    }
+    build_tiles(nV, nT, L.tetNew.data(), Br.data(), wr.data(), L);
+}
+
+void build_system_matrix(const Layout& L, const float*, const float* DmInv, const float* w, const float* c,
+                         CsrMatrix& A, std::vector<float>& matrixDiag)
+{
+    const int nV = L.nV, nT = L.nT;
+    // incidence (ascending reordered tet order)
+    std::vector<int> ptr((size_t)nV + 1, 0);
+    for (size_t i = 0; i < (size_t)nT * 4; ++i) ptr[L.tetNew[i] + 1]++;
+    for (int v = 0; v < nV; ++v) ptr[v + 1] += ptr[v];
+    std::vector<int> inc((size_t)nT * 4), fill(ptr.begin(), ptr.end() - 1);
+    for (int t = 0; t < nT; ++t) for (int k = 0; k < 4; ++k) inc[fill[L.tetNew[4 * (size_t)t + k]]++] = 4 * t + k;
+    matrixDiag.assign((size_t)nV, 0.f);
+    A.n = nV; A.rowPtr.assign((size_t)nV + 1, 0); A.col.clear(); A.val.clear();
+    struct Ent { int c; float v; int seq; };
+    std::vector<Ent> e;
+    for (int v = 0; v < nV; ++v) {
+        e.clear();
+        int seq = 0;
+        float md = 0.f;
+        for (int q = ptr[v]; q < ptr[v + 1]; ++q) {
+            const int t = inc[q] >> 2, i = inc[q] & 3;
+            const float* B = DmInv + 9 * (size_t)t;
+            float cols[4][3];
+            for (int r = 0; r < 3; ++r) {
+                const float m0 = B[0 * 3 + r], m1 = B[1 * 3 + r], m2 = B[2 * 3 + r];
+                cols[0][r] = m0 * -1.0f + m1 * -1.0f + m2 * -1.0f;
+                cols[1][r] = m0; cols[2][r] = m1; cols[3][r] = m2;
+            }
+            for (int j = 0; j < 4; ++j) {
+                const float kji = cols[i][0] * cols[j][0] + cols[i][1] * cols[j][1] + cols[i][2] * cols[j][2];
+                e.push_back({(int)L.tetNew[4 * (size_t)t + j], kji * w[t], seq++});
+                if (j == i) md += kji * w[t];
+            }
+        }
+        matrixDiag[v] = md;
+        e.push_back({v, c[v], seq++});
+        std::sort(e.begin(), e.end(), [](const Ent& a, const Ent& b) { return a.c != b.c ? a.c < b.c : a.seq < b.seq; });
+        A.rowPtr[v] = (int)A.col.size();
+        for (size_t a = 0; a < e.size();) {
+            const int cc = e[a].c; float acc = 0.f;
+            while (a < e.size() && e[a].c == cc) { acc += e[a].v; ++a; }
+            A.col.push_back(cc); A.val.push_back(acc);
+        }
+    }
+    A.rowPtr[nV] = (int)A.col.size();
+}
+
+void partition_vertices(int nV, int world, std::vector<int>& vbeg)
+{
+    vbeg.assign((size_t)world + 1, 0);
+    for (int r = 0; r <= world; ++r) vbeg[r] = (int)(((long long)nV * r) / world);
+}
+
+}  // namespace pdb200

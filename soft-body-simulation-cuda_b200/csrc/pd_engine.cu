@@ -1,0 +1,464 @@
+// Engine implementation (see pd_engine.hpp).
+#include "pd_engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+#include "pd_kernels.cuh"
+
+namespace pdb200 {
+
+#define CUDA_CHECK(call)                                                                                  \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            throw std::runtime_error(std::string("CUDA error ") + cudaGetErrorName(e__) + " (" +          \
+                                     cudaGetErrorString(e__) + ") at " + __FILE__ + ":" +                 \
+                                     std::to_string(__LINE__) + ": " #call);                              \
+    } while (0)
+
+struct Engine::Impl {
+    // tile stream
+    uint8_t* records = nullptr;
+    unsigned long long* recOff = nullptr;
+    uint32_t *vslotPtr = nullptr, *vslot = nullptr;
+    float* P = nullptr;
+    // per-vertex state (renumbered, padded float4)
+    float4* q[3] = {nullptr, nullptr, nullptr};
+    float4 *so4 = nullptr, *X = nullptr, *V = nullptr, *XT = nullptr, *X0 = nullptr;
+    float2* cc = nullptr;
+    float *mass = nullptr, *dbc = nullptr, *md = nullptr;
+    uint32_t* oldOfNew = nullptr;
+    float* stage3 = nullptr;          // 3 x (3 nV) floats, AoS staging for import/export
+    float* fbData = nullptr;
+    DevFixedBodies fb{};
+    LocalSmem lay{};
+    cudaGraphExec_t graphExec = nullptr;
+    cudaGraph_t graph = nullptr;
+    std::vector<cudaEvent_t> events;
+    std::vector<void*> allocs;
+    std::vector<float> hostMd;        // renumbered
+};
+
+template <typename T>
+T* Engine::dalloc(size_t n)
+{
+    void* p = nullptr;
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    CUDA_CHECK(cudaMalloc(&p, bytes));
+    d_->allocs.push_back(p);
+    devBytes_ += bytes;
+    return static_cast<T*>(p);
+}
+
+Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), params_(scene.params), opt_(opt), d_(new Impl)
+{
+    nV_ = scene.numVerts;
+    nT_ = scene.numTets;
+    if (nV_ <= 0 || nT_ <= 0) throw std::runtime_error("empty scene");
+    if (params_.handleCollision)
+        throw std::runtime_error("handleCollision=true (mesh-mesh BVH/CCD) is outside the PD hot path; set it to false");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw std::runtime_error("no CUDA device: the PD engine has no CPU fallback");
+    CUDA_CHECK(cudaSetDevice(opt.device));
+    cudaDeviceProp prop{};
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, opt.device));
+    if (prop.major < 10)
+        throw std::runtime_error("this build targets sm_100a (B200); found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor));
+    numSms_ = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+
+    build_layout(nV_, nT_, scene_.X.data(), scene_.Tet.data(), scene_.mu.data(), opt.reorder != 0, L_);
+
+    // ---- device buffers
+    Impl& d = *d_;
+    d.records = dalloc<uint8_t>(L_.records.size());
+    d.recOff = dalloc<unsigned long long>(L_.tileRecOff.size());
+    d.vslotPtr = dalloc<uint32_t>(L_.vslotPtr.size());
+    d.vslot = dalloc<uint32_t>(L_.vslot.size());
+    d.P = dalloc<float>(3 * (size_t)L_.nSlots);
+    for (int k = 0; k < 3; ++k) d.q[k] = dalloc<float4>(nV_);
+    d.so4 = dalloc<float4>(nV_); d.X = dalloc<float4>(nV_); d.V = dalloc<float4>(nV_);
+    d.XT = dalloc<float4>(nV_); d.X0 = dalloc<float4>(nV_);
+    d.cc = dalloc<float2>(nV_);
+    d.mass = dalloc<float>(nV_); d.dbc = dalloc<float>(nV_); d.md = dalloc<float>(nV_);
+    d.oldOfNew = dalloc<uint32_t>(nV_);
+    d.stage3 = dalloc<float>(9 * (size_t)nV_);
+
+    CUDA_CHECK(cudaMemcpy(d.records, L_.records.data(), L_.records.size(), cudaMemcpyHostToDevice));
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
+    CUDA_CHECK(cudaMemcpy(d.recOff, L_.tileRecOff.data(), L_.tileRecOff.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(d.vslotPtr, L_.vslotPtr.data(), L_.vslotPtr.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(d.vslot, L_.vslot.data(), L_.vslot.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(d.oldOfNew, L_.vertOrder.data(), (size_t)nV_ * 4, cudaMemcpyHostToDevice));
+    {
+        std::vector<float> m(nV_), b(nV_);
+        std::vector<float4> x0(nV_);
+        for (int v = 0; v < nV_; ++v) {
+            const uint32_t o = L_.vertOrder[v];
+            m[v] = scene_.mass[o]; b[v] = scene_.DBC[o];
+            x0[v] = make_float4(scene_.X[3 * (size_t)o], scene_.X[3 * (size_t)o + 1], scene_.X[3 * (size_t)o + 2], 0.f);
+        }
+        CUDA_CHECK(cudaMemcpy(d.mass, m.data(), (size_t)nV_ * 4, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(d.dbc, b.data(), (size_t)nV_ * 4, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(d.X0, x0.data(), (size_t)nV_ * 16, cudaMemcpyHostToDevice));
+    }
+    // fixed bodies -> the three arrays the collision kernels consume
+    {
+        std::vector<float> planes, spheres, cyls;
+        for (const FixedBody& f : scene_.fixed) {
+            if (f.type == FB_PLANE) {
+                float up[3]; plane_up(f.model, up);
+                planes.insert(planes.end(), {f.model[12], f.model[13], f.model[14], up[0], up[1], up[2]});
+            } else if (f.type == FB_SPHERE) {
+                spheres.insert(spheres.end(), {f.model[12], f.model[13], f.model[14], f.radius});
+            } else if (f.type == FB_CYLINDER) {
+                float ax[3]; cylinder_axis(f.model, ax);
+                cyls.insert(cyls.end(), {f.model[12], f.model[13], f.model[14], ax[0], ax[1], ax[2], f.radius});
+            }
+        }
+        const size_t n = planes.size() + spheres.size() + cyls.size();
+        d.fbData = dalloc<float>(n);
+        std::vector<float> all;
+        all.insert(all.end(), planes.begin(), planes.end());
+        all.insert(all.end(), spheres.begin(), spheres.end());
+        all.insert(all.end(), cyls.begin(), cyls.end());
+        if (n) CUDA_CHECK(cudaMemcpy(d.fbData, all.data(), n * 4, cudaMemcpyHostToDevice));
+        d.fb.nPlanes = (int)(planes.size() / 6); d.fb.nSpheres = (int)(spheres.size() / 4); d.fb.nCyls = (int)(cyls.size() / 7);
+        d.fb.planes = d.fbData; d.fb.spheres = d.fbData + planes.size(); d.fb.cyls = d.fbData + planes.size() + spheres.size();
+    }
+    // local kernel geometry
+    uint32_t maxRec = 0;
+    for (int t = 0; t < L_.nTiles; ++t) maxRec = std::max<uint32_t>(maxRec, (uint32_t)(L_.tileRecOff[t + 1] - L_.tileRecOff[t]));
+    d.lay = local_smem_layout(maxRec);
+    auto setAttr = [&](const void* fn) {
+        CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.lay.total));
+    };
+    setAttr((const void*)k_local<0, true>); setAttr((const void*)k_local<0, false>);
+    setAttr((const void*)k_local<1, true>); setAttr((const void*)k_local<1, false>);
+    int perSm = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_local<0, true>, TILE_T, d.lay.total));
+    if (perSm < 1) throw std::runtime_error("local kernel does not fit on an SM");
+    if (opt.ctasPerSm > 0) perSm = std::min(perSm, opt.ctasPerSm);
+    localGrid_ = std::min(L_.nTiles, numSms_ * perSm);
+
+    reset();
+}
+
+Engine::~Engine()
+{
+    if (d_) {
+        cudaSetDevice(opt_.device);
+        if (stream_) cudaStreamSynchronize(stream_);
+        if (d_->graphExec) cudaGraphExecDestroy(d_->graphExec);
+        if (d_->graph) cudaGraphDestroy(d_->graph);
+        for (cudaEvent_t ev : d_->events) cudaEventDestroy(ev);
+        for (void* p : d_->allocs) cudaFree(p);
+        if (stream_) cudaStreamDestroy(stream_);
+    }
+}
+
+void Engine::synchronize()
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+void Engine::setParams(const SolverParams& p)
+{
+    if (p.handleCollision) throw std::runtime_error("handleCollision=true is outside the PD hot path");
+    const SolverParams& o = params_;
+    const bool same = o.dt == p.dt && o.gravity == p.gravity && o.muN == p.muN && o.muT == p.muT && o.rho == p.rho &&
+                      o.tol == p.tol && o.numIterations == p.numIterations && o.globalSolver == p.globalSolver &&
+                      o.pcgMaxIter == p.pcgMaxIter && o.pcgTol == p.pcgTol;
+    params_ = p;
+    if (!same) graphValid_ = false;
+}
+
+void Engine::reset()
+{   // SimulationCUDAContext::Reset (simulationContext.cu:233-243): X = XTilde = X0, V = 0, re-prepare
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    Impl& d = *d_;
+    CUDA_CHECK(cudaMemcpyAsync(d.X, d.X0, (size_t)nV_ * 16, cudaMemcpyDeviceToDevice, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(d.XT, d.X0, (size_t)nV_ * 16, cudaMemcpyDeviceToDevice, stream_));
+    CUDA_CHECK(cudaMemsetAsync(d.V, 0, (size_t)nV_ * 16, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    ready_ = false;
+    perfc_ = PerfCounters();
+}
+
+void Engine::prepare()
+{   // PdSolver::SolverPrepare (pdSolver.cu:40-139): matrix_diag and the dt baked into DBC rows.
+    // matrix_diag[v] = sum over incident tets (ascending reordered order) of w_t |col_i(B^T G)|^2
+    Impl& d = *d_;
+    d.hostMd.assign((size_t)nV_, 0.f);
+    for (int ti = 0; ti < L_.nTiles; ++ti) {
+        const uint8_t* rec = L_.records.data() + L_.tileRecOff[ti];
+        TileHeader h; std::memcpy(&h, rec, 16);
+        const uint32_t nLp = (h.nLocal + 3u) & ~3u, nTp = (h.nTets + 3u) & ~3u;
+        const uint32_t* vlist = reinterpret_cast<const uint32_t*>(rec + 16);
+        const uint16_t* cidx = reinterpret_cast<const uint16_t*>(rec + 16 + 4 * nLp);
+        const float* Bm = reinterpret_cast<const float*>(rec + 16 + 4 * nLp + 8 * nTp);
+        const float* w = Bm + 9 * nTp;
+        for (uint32_t t = 0; t < h.nTets; ++t) {
+            float B[9];
+            for (int e = 0; e < 9; ++e) B[e] = Bm[e * nTp + t];
+            for (int i = 0; i < 4; ++i) {
+                float col[3];
+                for (int r = 0; r < 3; ++r)
+                    col[r] = (i == 0) ? (B[0 * 3 + r] * -1.0f + B[1 * 3 + r] * -1.0f + B[2 * 3 + r] * -1.0f) : B[(i - 1) * 3 + r];
+                const float kii = col[0] * col[0] + col[1] * col[1] + col[2] * col[2];
+                d.hostMd[vlist[cidx[4 * t + i]]] += kii * w[t];
+            }
+        }
+    }
+    CUDA_CHECK(cudaMemcpyAsync(d.md, d.hostMd.data(), (size_t)nV_ * 4, cudaMemcpyHostToDevice, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    dt2Prepared_ = params_.dt * params_.dt;
+    ready_ = true;
+    graphValid_ = false;
+}
+
+// The launch sequence of one PdSolver::Update in Jacobi mode.  `timed` brackets the local /
+// global / collision parts with events (perf mode, no host sync inside the loop).
+void Engine::enqueueStep(bool timed)
+{
+    Impl& d = *d_;
+    const SolverParams& p = params_;
+    const int vb = 256, vg = (nV_ + vb - 1) / vb;
+    const float dt = p.dt, dtInv = 1.0f / dt;
+    const float wdbc = 1e6f * (dtInv * dtInv);
+    size_t ev = 0;
+    auto rec = [&]() { if (timed) CUDA_CHECK(cudaEventRecord(d.events[ev++], stream_)); };
+
+    k_predict<<<vg, vb, 0, stream_>>>(nV_, d.X, d.V, d.mass, d.dbc, d.md, d.X0, dt, dt2Prepared_, p.gravity,
+                                      d.q[0], d.q[2], d.so4, d.cc);
+    float omega = 1.0f;
+    for (int i = 0; i < p.numIterations; ++i) {
+        const float4* cur = d.q[i % 3];
+        const float4* prev = d.q[(i + 2) % 3];
+        float4* next = d.q[(i + 1) % 3];
+        rec();
+        if (opt_.rotMode == 0)
+            k_local<0, true><<<localGrid_, TILE_T, d.lay.total, stream_>>>(d.records, d.recOff, L_.nTiles, cur, d.P, d.lay);
+        else
+            k_local<1, true><<<localGrid_, TILE_T, d.lay.total, stream_>>>(d.records, d.recOff, L_.nTiles, cur, d.P, d.lay);
+        rec();
+        // omega recurrence in float, pdSolver.cu:196-198
+        if (i <= 10) omega = 1;
+        else if (i == 11) omega = 2 / (2 - p.rho * p.rho);
+        else omega = 4 / (4 - p.rho * p.rho * omega);
+        k_vertex_jacobi<<<vg, vb, 0, stream_>>>(nV_, cur, prev, next, d.so4, d.cc, d.vslotPtr, d.vslot, d.P, omega, wdbc);
+        rec();
+    }
+    rec();
+    k_finish<<<vg, vb, 0, stream_>>>(nV_, d.q[p.numIterations % 3], dtInv, d.X, d.XT, d.V, d.fb, p.muT, p.muN);
+    rec();
+}
+
+void Engine::buildGraph()
+{
+    Impl& d = *d_;
+    if (d.graphExec) { cudaGraphExecDestroy(d.graphExec); d.graphExec = nullptr; }
+    if (d.graph) { cudaGraphDestroy(d.graph); d.graph = nullptr; }
+    CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    enqueueStep(false);
+    CUDA_CHECK(cudaStreamEndCapture(stream_, &d.graph));
+    CUDA_CHECK(cudaGraphInstantiate(&d.graphExec, d.graph, 0));
+    graphValid_ = true;
+}
+
+void Engine::step(int nSteps)
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    if (params_.globalSolver != 0)
+        throw std::runtime_error("global solver " + std::to_string(params_.globalSolver) + " not built into this engine instance");
+    if (!ready_) prepare();
+    Impl& d = *d_;
+    const int launchesPerStep = 2 + 2 * params_.numIterations;
+    if (perf_) {
+        const size_t need = 3 * (size_t)params_.numIterations + 2;
+        while (d.events.size() < need) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); d.events.push_back(e); }
+        for (int s = 0; s < nSteps; ++s) {
+            enqueueStep(true);
+            CUDA_CHECK(cudaStreamSynchronize(stream_));
+            size_t ev = 0;
+            for (int i = 0; i < params_.numIterations; ++i) {
+                float a = 0, b = 0;
+                CUDA_CHECK(cudaEventElapsedTime(&a, d.events[ev], d.events[ev + 1]));
+                CUDA_CHECK(cudaEventElapsedTime(&b, d.events[ev + 1], d.events[ev + 2]));
+                perfc_.localStep += a; perfc_.globalStep += b;
+                ev += 3;
+            }
+            float c = 0;
+            CUDA_CHECK(cudaEventElapsedTime(&c, d.events[ev], d.events[ev + 1]));
+            perfc_.collisionFixed += c;
+        }
+    } else if (opt_.useGraph) {
+        if (!graphValid_) buildGraph();
+        for (int s = 0; s < nSteps; ++s) CUDA_CHECK(cudaGraphLaunch(d.graphExec, stream_));
+    } else {
+        for (int s = 0; s < nSteps; ++s) enqueueStep(false);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    perfc_.steps += nSteps;
+    perfc_.pdIterations += (long long)nSteps * params_.numIterations;
+    perfc_.kernelLaunches += (long long)nSteps * launchesPerStep;
+}
+
+float Engine::stepTimed(int nSteps)
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    if (!ready_) prepare();
+    if (opt_.useGraph && !perf_ && !graphValid_) buildGraph();
+    cudaEvent_t a, b;
+    CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    CUDA_CHECK(cudaEventRecord(a, stream_));
+    step(nSteps);
+    CUDA_CHECK(cudaEventRecord(b, stream_));
+    CUDA_CHECK(cudaEventSynchronize(b));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    perfc_.stepMsTotal += ms;
+    return ms;
+}
+
+// ---------------------------------------------------------------- state transfer
+void Engine::importDevice(const float* dX, const float* dV, const float* dXTilde)
+{
+    Impl& d = *d_;
+    const int vb = 256, vg = (nV_ + vb - 1) / vb;
+    if (dX) k_import3<<<vg, vb, 0, stream_>>>(nV_, dX, d.oldOfNew, d.X);
+    if (dV) k_import3<<<vg, vb, 0, stream_>>>(nV_, dV, d.oldOfNew, d.V);
+    if (dXTilde) k_import3<<<vg, vb, 0, stream_>>>(nV_, dXTilde, d.oldOfNew, d.XT);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void Engine::exportDevice(float* dX, float* dV, float* dXTilde)
+{
+    Impl& d = *d_;
+    const int vb = 256, vg = (nV_ + vb - 1) / vb;
+    if (dX) k_export3<<<vg, vb, 0, stream_>>>(nV_, d.X, d.oldOfNew, dX);
+    if (dV) k_export3<<<vg, vb, 0, stream_>>>(nV_, d.V, d.oldOfNew, dV);
+    if (dXTilde) k_export3<<<vg, vb, 0, stream_>>>(nV_, d.XT, d.oldOfNew, dXTilde);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void Engine::upload(const float* X, const float* V, const float* XTilde)
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    Impl& d = *d_;
+    const size_t n = 3 * (size_t)nV_ * sizeof(float);
+    float *sx = d.stage3, *sv = d.stage3 + 3 * (size_t)nV_, *st = d.stage3 + 6 * (size_t)nV_;
+    if (X) CUDA_CHECK(cudaMemcpyAsync(sx, X, n, cudaMemcpyHostToDevice, stream_));
+    if (V) CUDA_CHECK(cudaMemcpyAsync(sv, V, n, cudaMemcpyHostToDevice, stream_));
+    if (XTilde) CUDA_CHECK(cudaMemcpyAsync(st, XTilde, n, cudaMemcpyHostToDevice, stream_));
+    importDevice(X ? sx : nullptr, V ? sv : nullptr, XTilde ? st : nullptr);
+}
+
+void Engine::download(float* X, float* V, float* XTilde)
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    Impl& d = *d_;
+    const size_t n = 3 * (size_t)nV_ * sizeof(float);
+    float *sx = d.stage3, *sv = d.stage3 + 3 * (size_t)nV_, *st = d.stage3 + 6 * (size_t)nV_;
+    exportDevice(X ? sx : nullptr, V ? sv : nullptr, XTilde ? st : nullptr);
+    if (X) CUDA_CHECK(cudaMemcpyAsync(X, sx, n, cudaMemcpyDeviceToHost, stream_));
+    if (V) CUDA_CHECK(cudaMemcpyAsync(V, sv, n, cudaMemcpyDeviceToHost, stream_));
+    if (XTilde) CUDA_CHECK(cudaMemcpyAsync(XTilde, st, n, cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+void Engine::stepHost(int nSteps, const float* Xin, const float* Vin, const float* XTin, float* Xout, float* Vout, float* XTout)
+{
+    upload(Xin, Vin, XTin);
+    step(nSteps);
+    download(Xout, Vout, XTout);
+}
+
+void Engine::getSetup(float* matrixDiag, float* massDt2, float* DmInv, float* V0)
+{
+    if (!ready_) prepare();
+    const float dt2 = params_.dt * params_.dt;
+    for (int v = 0; v < nV_; ++v) {
+        const uint32_t o = L_.vertOrder[v];
+        if (matrixDiag) matrixDiag[o] = d_->hostMd[v];
+        if (massDt2) massDt2[o] = (scene_.mass[o] + scene_.DBC[o] * 1e6f) / dt2;
+    }
+    if (DmInv || V0) {
+        std::vector<float> B((size_t)nT_ * 9), v0((size_t)nT_);
+        rest_shape(scene_.X.data(), scene_.Tet.data(), nT_, B.data(), v0.data());
+        if (DmInv) std::memcpy(DmInv, B.data(), B.size() * 4);
+        if (V0) std::memcpy(V0, v0.data(), v0.size() * 4);
+    }
+}
+
+// ---------------------------------------------------------------- kernel timing helpers (bench)
+float Engine::timeLocalKernelMs(int reps)
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    if (!ready_) prepare();
+    Impl& d = *d_;
+    cudaEvent_t a, b;
+    CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    CUDA_CHECK(cudaEventRecord(a, stream_));
+    for (int r = 0; r < reps; ++r) {
+        if (opt_.rotMode == 0)
+            k_local<0, true><<<localGrid_, TILE_T, d.lay.total, stream_>>>(d.records, d.recOff, L_.nTiles, d.XT, d.P, d.lay);
+        else
+            k_local<1, true><<<localGrid_, TILE_T, d.lay.total, stream_>>>(d.records, d.recOff, L_.nTiles, d.XT, d.P, d.lay);
+    }
+    CUDA_CHECK(cudaEventRecord(b, stream_));
+    CUDA_CHECK(cudaEventSynchronize(b));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return ms / (float)reps;
+}
+
+float Engine::timeVertexKernelMs(int reps)
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    if (!ready_) prepare();
+    Impl& d = *d_;
+    const int vb = 256, vg = (nV_ + vb - 1) / vb;
+    cudaEvent_t a, b;
+    CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+    // a valid so4/cc is needed: run the predictor once
+    k_predict<<<vg, vb, 0, stream_>>>(nV_, d.X, d.V, d.mass, d.dbc, d.md, d.X0, params_.dt, dt2Prepared_, params_.gravity,
+                                      d.q[0], d.q[2], d.so4, d.cc);
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    CUDA_CHECK(cudaEventRecord(a, stream_));
+    for (int r = 0; r < reps; ++r)
+        k_vertex_jacobi<<<vg, vb, 0, stream_>>>(nV_, d.q[0], d.q[2], d.q[1], d.so4, d.cc, d.vslotPtr, d.vslot, d.P, 1.0f, 1.0f);
+    CUDA_CHECK(cudaEventRecord(b, stream_));
+    CUDA_CHECK(cudaEventSynchronize(b));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return ms / (float)reps;
+}
+
+void rotation_batch(int device, int rotMode, int n, const float* F, float* R, int* usedFast)
+{
+    CUDA_CHECK(cudaSetDevice(device));
+    float *dF = nullptr, *dR = nullptr; int* dU = nullptr;
+    CUDA_CHECK(cudaMalloc(&dF, 36ull * n)); CUDA_CHECK(cudaMalloc(&dR, 36ull * n)); CUDA_CHECK(cudaMalloc(&dU, 4ull * n));
+    CUDA_CHECK(cudaMemcpy(dF, F, 36ull * n, cudaMemcpyHostToDevice));
+    if (rotMode == 0) k_rotation_batch<0><<<(n + 127) / 128, 128>>>(n, dF, dR, dU);
+    else k_rotation_batch<1><<<(n + 127) / 128, 128>>>(n, dF, dR, dU);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpy(R, dR, 36ull * n, cudaMemcpyDeviceToHost));
+    if (usedFast) CUDA_CHECK(cudaMemcpy(usedFast, dU, 4ull * n, cudaMemcpyDeviceToHost));
+    cudaFree(dF); cudaFree(dR); cudaFree(dU);
+}
+
+}  // namespace pdb200

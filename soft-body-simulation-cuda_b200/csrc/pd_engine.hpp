@@ -1,0 +1,91 @@
+// PD step engine: owns the device-resident state of one simulation context and replays
+// PdSolver::Update (src/simulation/solver/projective/pdSolver.cu:210-232) on one B200.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "layout.hpp"
+#include "scene.hpp"
+
+namespace pdb200 {
+
+struct PerfCounters {      // PdSolver::performanceData, pdSolver.cu:26 (milliseconds, accumulated)
+    float localStep = 0, globalStep = 0, collisionFixed = 0, collisionMesh = 0;
+    // extras
+    double stepMsTotal = 0; long long steps = 0, pdIterations = 0, innerIterations = 0, kernelLaunches = 0;
+};
+
+struct EngineOptions {
+    int device = 0;
+    int rotMode = 0;        // 0 Newton polar + SVD fallback (default), 1 always the Jacobi SVD
+    int reorder = 1;        // Morton reordering of tets / first-touch renumbering of vertices
+    int useGraph = 1;       // replay each step as one CUDA graph
+    int ctasPerSm = 0;      // 0 = occupancy query
+};
+
+class Engine {
+public:
+    Engine(const Scene& scene, const EngineOptions& opt);
+    ~Engine();
+    Engine(const Engine&) = delete;
+    Engine& operator=(const Engine&) = delete;
+
+    void setParams(const SolverParams& p);
+    const SolverParams& params() const { return params_; }
+    void step(int nSteps);                                  // PdSolver::Update x n
+    float stepTimed(int nSteps);                            // same, returns device ms (events on the engine stream)
+    void reset();                                           // SimulationCUDAContext::Reset
+    void setPerf(bool on) { perf_ = on; }
+    void synchronize();
+    // host <-> device state in the reference's layout (AoS float3, original vertex numbering)
+    void download(float* X, float* V, float* XTilde);
+    void upload(const float* X, const float* V, const float* XTilde);
+    // device <-> device against the reference's SolverData arrays (glm::vec3*, original numbering)
+    void importDevice(const float* dX, const float* dV, const float* dXTilde);
+    void exportDevice(float* dX, float* dV, float* dXTilde);
+    // end-to-end step on host buffers (pinned or pageable): upload, n steps, download
+    void stepHost(int nSteps, const float* Xin, const float* Vin, const float* XTin, float* Xout, float* Vout, float* XTout);
+
+    const PerfCounters& perf() const { return perfc_; }
+    void resetPerf() { perfc_ = PerfCounters(); }
+    const Layout& layout() const { return L_; }
+    int numVerts() const { return nV_; }
+    int numTets() const { return nT_; }
+    // setup products in the ORIGINAL numbering/order (for parity checks against the oracle)
+    void getSetup(float* matrixDiag, float* massDt2, float* DmInv, float* V0);
+    // launch geometry, for the bench's launch count / roofline bookkeeping
+    int localGrid() const { return localGrid_; }
+    size_t deviceBytes() const { return devBytes_; }
+    size_t tileStreamBytes() const { return L_.records.size(); }
+    cudaStream_t stream() const { return stream_; }
+    // timing of one kernel family, measured with events over `reps` launches on the engine's stream
+    float timeLocalKernelMs(int reps);
+    float timeVertexKernelMs(int reps);
+
+private:
+    struct Impl;
+    void prepare();
+    void buildGraph();
+    void enqueueStep(bool timed);
+    template <typename T> T* dalloc(size_t n);
+
+    int nV_ = 0, nT_ = 0;
+    Scene scene_;             // host copy (original numbering)
+    Layout L_;
+    SolverParams params_;
+    EngineOptions opt_;
+    bool ready_ = false, perf_ = false, graphValid_ = false;
+    float dt2Prepared_ = 0.f;
+    PerfCounters perfc_;
+    int localGrid_ = 0, numSms_ = 0;
+    size_t devBytes_ = 0;
+    cudaStream_t stream_ = nullptr;
+    std::unique_ptr<Impl> d_;
+};
+
+// test hook: corotation() of n row-major 3x3 matrices on `device` (host pointers)
+void rotation_batch(int device, int rotMode, int n, const float* F, float* R, int* usedFast);
+
+}  // namespace pdb200

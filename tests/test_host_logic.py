@@ -1,0 +1,181 @@
+"""CPU tests (no GPU): C-ABI library loads and exports every declared symbol, the scene loader
+matches the oracle's loader, and the device layout is bit-exact against the numpy restatement."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import layout_oracle as LO
+import meshes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+def test_library_exports_every_declared_symbol(pd):
+    hdr = open(os.path.join(ROOT, "include", "pd_b200.h")).read()
+    declared = set(re.findall(r"\b(pd_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"pd_status"}
+    L = ctypes.CDLL(pd.LIB_PATH)
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, missing
+    # the python binding covers exactly the header
+    assert declared == set(pd.SYMBOLS), declared ^ set(pd.SYMBOLS)
+    assert b"sm_100a" in pd.lib().pd_version()
+
+
+def test_error_convention(pd):
+    assert pd.lib().pd_scene_load_json(b"/nonexistent/context.json", None, None) is None
+    assert "open" in pd.lib().pd_last_error().decode().lower()
+    assert pd.lib().pd_step(None, 1) < 0
+    with pytest.raises(pd.PdError):
+        pd.Scene.from_arrays(np.zeros((4, 3), np.float32), np.array([[0, 1, 2, 9]], np.uint32), 1.0, 1.0)
+
+
+def test_json_loader_matches_oracle_loader(pd, O, assets):
+    for ctx in ["C1 cube", "C2 armadillo&bunny", "Armadillo&house", "C5 house&sphere"]:
+        sc = pd.Scene.from_json(assets["json"], ctx)
+        a = sc.arrays()
+        osc, op = meshes.oracle_scene(O, assets, ctx)
+        assert a["X"].shape == osc.X0.shape
+        assert np.array_equal(a["X"].view(np.uint32), osc.X0.view(np.uint32)), ctx      # bit-exact transform
+        assert np.array_equal(a["Tet"], osc.Tet)
+        p = sc.params
+        assert p["num_iterations"] == 100 and abs(p["dt"] - op["dt"]) < 1e-9 and p["gravity"] == op["gravity"]
+    # context selection rules (context.cpp:366-369): first loadable when unnamed, explicit name otherwise
+    assert pd.Scene.from_json(assets["json"]).counts()[:2] == (8, 6)
+    assert pd.Scene.from_json(assets["json"], "not loaded").counts()[:2] == (4, 1)
+    with pytest.raises(pd.PdError):
+        pd.Scene.from_json(assets["json"], "no such context")
+
+
+def test_fixed_bodies_match_oracle(pd, O, assets):
+    sc = pd.Scene.from_json(assets["json"], "Armadillo&house")
+    fixed = sc.arrays()["fixed"]
+    kinds = [f.type for f in fixed]
+    assert kinds.count(pd.PD_CYLINDER) == 5 and kinds.count(pd.PD_PLANE) == 6
+    cfg = json.load(open(assets["json"]))
+    fdefs = {d["name"]: d for d in cfg["fixedBodies"]}
+    ctx = [c for c in cfg["contexts"] if c["name"] == "Armadillo&house"][0]
+    for f, fb in zip(fixed, ctx["fixedBodies"]):
+        d = fdefs[fb["name"]]
+        pos = fb.get("pos", d.get("pos", [0, 0, 0])); rot = fb.get("rot", d.get("rot", [0, 0, 0])); sc3 = fb.get("scale", d.get("scale", [1, 1, 1]))
+        if d["type"] == "cylinder":
+            sc3 = [sc3[0], sc3[1], sc3[0]]
+            assert f.radius == sc3[0]
+        M = O.model_matrix(pos, rot, sc3, 0)
+        assert np.array_equal(np.array(f.model[:], np.float32).view(np.uint32), M.view(np.uint32))
+        if d["type"] == "plane":
+            up = np.zeros(3, np.float32)
+            pd.lib().pd_plane_up(np.array(f.model[:], np.float32).ctypes.data, up.ctypes.data)
+            assert np.array_equal(up.view(np.uint32), O.plane_up(M).view(np.uint32))
+
+
+def test_centralize_swaps_y_z_and_fixes_orientation(pd, assets):
+    X, E, _ = meshes.raw_mesh("house2")
+    path = os.path.join(assets["assets"], "house2", "house2.node")
+    p = ctypes.c_void_p(); n = ctypes.c_int()
+    assert pd.lib().pd_load_node(path.encode(), 1, ctypes.byref(p), ctypes.byref(n)) == 0
+    Xc = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_float)), shape=(n.value, 3)).copy()
+    pd.lib().pd_free(p)
+    T = E[:, 1:5] - 1
+    vol = lambda P: np.einsum("ij,ij->i", np.cross(P[T[:, 1]] - P[T[:, 0]], P[T[:, 2]] - P[T[:, 0]]), P[T[:, 3]] - P[T[:, 0]])
+    assert (vol(X.astype(np.float64)) < 0).all() and (vol(Xc.astype(np.float64)) > 0).all()
+    assert abs(Xc.mean(0)).max() < 1e-3
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_fixture_equals_reference_assets(pd, O):
+    """Pins tests/golden/meshes.npz: the product's loader on the reference's own files gives the fixture."""
+    for name in ["cube", "house2", "sphere", "bunny", "armadillo0"]:
+        X, E, idx0 = meshes.raw_mesh(name)
+        node, ele = [str(s) for s in meshes.npz()[name + "_files"]]
+        Xo = O.load_node(os.path.join(REF, "assets", node), False)
+        assert np.array_equal(Xo.view(np.uint32), X.view(np.uint32)), name
+        start = 0 if name == "armadillo0" else 1
+        To = O.load_ele(os.path.join(REF, "assets", ele), start)
+        assert np.array_equal(To, (E[:, 1:5] - start).astype(np.uint32))
+        p = ctypes.c_void_p(); n = ctypes.c_int()
+        assert pd.lib().pd_load_node(os.path.join(REF, "assets", node).encode(), 0, ctypes.byref(p), ctypes.byref(n)) == 0
+        Xp = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_float)), shape=(n.value, 3)).copy()
+        pd.lib().pd_free(p)
+        assert np.array_equal(Xp.view(np.uint32), X.view(np.uint32))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_loads_the_reference_context_json(pd):
+    sc = pd.Scene.from_json(os.path.join(REF, "context.json"), "Armadillo&house")
+    nV, nT, nF, nB = sc.counts()
+    assert (nV, nT, nB) == (13054 + 400 + 482 + 8, 41960 + 1389 + 1217 + 6, 4) and nF == 11
+    p = sc.params
+    assert abs(p["dt"] - 0.01) < 1e-9 and p["gravity"] == 98 and p["num_iterations"] == 100
+
+
+def _check_layout(pd, sc, reorder=True):
+    a = sc.arrays()
+    Lc = sc.layout(reorder)
+    Lo = LO.build(a["X"], a["Tet"], a["mu"], reorder)
+    for k in ["tet_order", "vert_order", "tet_new", "tile_tet_start", "tile_rec_off", "vslot_ptr", "vslot"]:
+        assert np.array_equal(getattr(Lc, k), Lo[k]), k
+    assert (Lc.num_tiles, Lc.num_slots, Lc.max_local) == (Lo["num_tiles"], Lo["num_slots"], Lo["max_local"])
+    assert Lc.records.tobytes() == Lo["records"].tobytes()       # incl. DmInv/w bits and incidence CSR
+    return Lc
+
+
+def test_layout_bit_exact_small_meshes(pd, assets):
+    for ctx in ["C1 cube", "C5 house&sphere", "not loaded"]:
+        _check_layout(pd, pd.Scene.from_json(assets["json"], ctx))
+    _check_layout(pd, pd.Scene.from_json(assets["json"], "C5 house&sphere"), reorder=False)
+
+
+def test_layout_bit_exact_bunny_and_grid(pd, assets):
+    X, E, _ = meshes.raw_mesh("bunny")
+    sc = pd.Scene.from_arrays(X * np.float32(35), (E[:, 1:5] - 1).astype(np.uint32), 10.0, 2e6)
+    L = _check_layout(pd, sc)
+    assert L.num_tiles == -(-8417 // 256) and L.max_local <= 512
+    g = pd.Scene.kuhn_grid(7, 6, 5, 1.0, 0.05, 12345, (0, 10, 0), 1.0, 2e5)
+    assert g.counts()[:2] == (8 * 7 * 6, 6 * 7 * 6 * 5)
+    _check_layout(pd, g)
+
+
+def test_layout_invariants(pd, assets):
+    sc = pd.Scene.from_json(assets["json"], "C2 armadillo&bunny")
+    nV, nT = sc.counts()[:2]
+    L = sc.layout()
+    assert sorted(L.tet_order.tolist()) == list(range(nT)) and sorted(L.vert_order.tolist()) == list(range(nV))
+    # every (tile, local vertex) slot appears exactly once in the vertex->slot CSR, ascending per vertex
+    assert sorted(L.vslot.tolist()) == list(range(L.num_slots))
+    for v in range(0, nV, 997):
+        s = L.vslot[L.vslot_ptr[v]:L.vslot_ptr[v + 1]]
+        assert (np.diff(s.astype(np.int64)) > 0).all() and len(s) >= 1
+    # tiles hold <= 256 tets and <= 512 vertices; Morton order keeps them compact
+    assert np.diff(L.tile_tet_start.astype(np.int64)).max() <= 256 and L.max_local <= 512
+    assert L.num_slots < 1.2 * nT      # ~0.9 slots per tet on armadillo+bunny (compactness regression guard)
+
+
+def test_kuhn_grid_generator(pd):
+    g = pd.Scene.kuhn_grid(3, 4, 2, 1.5, 0.0, 1, (1, 2, 3), 2.0, 1e5)
+    a = g.arrays()
+    X, T = a["X"].astype(np.float64), a["Tet"].astype(np.int64)
+    vol = np.einsum("ij,ij->i", np.cross(X[T[:, 1]] - X[T[:, 0]], X[T[:, 2]] - X[T[:, 0]]), X[T[:, 3]] - X[T[:, 0]]) / 6
+    assert (vol > 0).all() and np.isclose(vol.sum(), 3 * 4 * 2 * 1.5 ** 3)
+    assert np.allclose(X.min(0), [1, 2, 3]) and np.allclose(X.max(0), [1 + 4.5, 2 + 6, 3 + 3])
+    # jitter stream = mt19937(seed) 24-bit uniforms, reproducible with numpy's legacy seeding
+    g2 = pd.Scene.kuhn_grid(2, 2, 2, 1.0, 0.05, 12345, (0, 0, 0), 1.0, 1.0).arrays()["X"]
+    rs = np.random.RandomState(12345)
+    raw = np.array([rs.randint(0, 2 ** 32, dtype=np.uint64) for _ in range(81)], np.uint64)
+    u = ((raw >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)).reshape(27, 3)
+    base = np.stack(np.meshgrid(np.arange(3), np.arange(3), np.arange(3), indexing="ij"), -1).transpose(2, 1, 0, 3).reshape(27, 3).astype(np.float32)
+    exp = base + np.float32(0.05) * (np.float32(2.0) * u - np.float32(1.0))
+    assert np.array_equal(g2.view(np.uint32), exp.astype(np.float32).view(np.uint32))
+
+
+def test_partition_vertices(pd):
+    for nV, w in [(10, 3), (2744000, 8), (7, 8), (1, 1)]:
+        vb = np.zeros(w + 1, np.int32)
+        assert pd.lib().pd_partition_vertices(nV, w, vb.ctypes.data) == 0
+        assert np.array_equal(vb, LO.partition_vertices(nV, w))
+        assert vb[0] == 0 and vb[-1] == nV and (np.diff(vb) >= 0).all()
