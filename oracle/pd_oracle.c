@@ -2,9 +2,15 @@
  * pd_oracle.c -- CPU restatement of the reference's float PD step (see pd_oracle.h).
  * TEST INFRASTRUCTURE ONLY -- never linked into the product.
  *
- * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC (oracle/Makefile).
+ * Build: gcc -O2 -ffp-contract=off -mfma -fopenmp -shared -fPIC (oracle/Makefile).
  * -ffp-contract=off keeps one rounding per float operation, which is what the
- * reference's SVD does explicitly (__fadd_rn/__fsub_rn, svd3_cuda.h:65-97).
+ * reference's SVD does explicitly (__fadd_rn/__fsub_rn, svd3_cuda.h:65-97).  Everywhere
+ * else the reference is plain C++/glm that nvcc compiles with FMA contraction; the fused
+ * operations are written out here with fmaf()/fma() exactly where nvcc 12.9 places them in
+ * the sm_100a build of the reference kernels (read off `cuobjdump -sass oracle/_ref/libpd_ref.so`):
+ *   a0*b0 + a1*b1 + a2*b2  (glm mat3*mat3, glm::dot)   ->  fma(a2,b2, fma(a0,b0, a1*b1))
+ *   a*b - c*d                                          ->  fma(a,b, -(c*d))
+ * and the per-kernel forms quoted at each use below.
  */
 #include "pd_oracle.h"
 
@@ -25,6 +31,9 @@
 /* svd3_cuda.h:25-30 */
 /* the reference stores sin/cos(pi/8) as integer bit patterns (svd3_cuda.h:26-27); the cosine
  * is 1 ulp above the correctly rounded value, so the patterns are reproduced exactly */
+/* a0*b0 + a1*b1 + a2*b2 as contracted by nvcc: the k=1 product is rounded, k=0 and k=2 are fused */
+#define DOT3_NV(a0, b0, a1, b1, a2, b2) fmaf((a2), (b2), fmaf((a0), (b0), (a1) * (b1)))
+
 static inline float bits2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 #define O_SIN_PI8   bits2f(1053028117u)
 #define O_COS_PI8   bits2f(1064076127u)
@@ -263,11 +272,8 @@ void o_rotation(const float F[9], float R[9])
     o_svd3(F, U, S, V);
     for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) {
-            /* glm mat3*mat3: sum over k left to right */
-            float acc = U[r * 3 + 0] * V[c * 3 + 0];
-            acc = acc + U[r * 3 + 1] * V[c * 3 + 1];
-            acc = acc + U[r * 3 + 2] * V[c * 3 + 2];
-            R[r * 3 + c] = acc;
+            /* glm mat3*mat3 as nvcc contracts it (computeLocal SASS): fma(a2,b2, fma(a0,b0, a1*b1)) */
+            R[r * 3 + c] = DOT3_NV(U[r * 3 + 0], V[c * 3 + 0], U[r * 3 + 1], V[c * 3 + 1], U[r * 3 + 2], V[c * 3 + 2]);
         }
     float det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[3] * (R[1] * R[8] - R[7] * R[2]) +
                 R[6] * (R[1] * R[5] - R[4] * R[2]);
@@ -691,10 +697,7 @@ static void local_one(const float *q, const uint32_t *tv, const float *Bi, float
     for (int r = 0; r < 3; r++) { Ds[r * 3 + 0] = v1[r] - v0[r]; Ds[r * 3 + 1] = v2[r] - v0[r]; Ds[r * 3 + 2] = v3[r] - v0[r]; }
     for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) {
-            float acc = Ds[r * 3 + 0] * Bi[0 * 3 + c];
-            acc = acc + Ds[r * 3 + 1] * Bi[1 * 3 + c];
-            acc = acc + Ds[r * 3 + 2] * Bi[2 * 3 + c];
-            F[r * 3 + c] = acc;
+            F[r * 3 + c] = DOT3_NV(Ds[r * 3 + 0], Bi[0 * 3 + c], Ds[r * 3 + 1], Bi[1 * 3 + c], Ds[r * 3 + 2], Bi[2 * 3 + c]);
         }
     o_rotation(F, R);
     if (is_jacobi) for (int k = 0; k < 9; k++) R[k] = R[k] - F[k];
@@ -703,13 +706,10 @@ static void local_one(const float *q, const uint32_t *tv, const float *Bi, float
     for (int k = 0; k < 9; k++) M1[k] = sc * R[k];
     for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) {   /* M1 * transpose(DmInv): (r,c) = sum_k M1[r][k]*Bi[c][k] */
-            float acc = M1[r * 3 + 0] * Bi[c * 3 + 0];
-            acc = acc + M1[r * 3 + 1] * Bi[c * 3 + 1];
-            acc = acc + M1[r * 3 + 2] * Bi[c * 3 + 2];
-            M2[r * 3 + c] = acc;
+            M2[r * 3 + c] = DOT3_NV(M1[r * 3 + 0], Bi[c * 3 + 0], M1[r * 3 + 1], Bi[c * 3 + 1], M1[r * 3 + 2], Bi[c * 3 + 2]);
         }
     for (int r = 0; r < 3; r++) {
-        H[0 * 3 + r] = M2[r * 3 + 0] * -1.0f + M2[r * 3 + 1] * -1.0f + M2[r * 3 + 2] * -1.0f;
+        H[0 * 3 + r] = (-M2[r * 3 + 0] - M2[r * 3 + 1]) - M2[r * 3 + 2];   /* FADD(-a,-b); FADD(-c, .) in the SASS */
         H[1 * 3 + r] = M2[r * 3 + 0];
         H[2 * 3 + r] = M2[r * 3 + 1];
         H[3 * 3 + r] = M2[r * 3 + 2];
@@ -744,8 +744,9 @@ static void local_step(o_scene *s, const o_params *p, int is_jacobi)
 }
 
 /* fixed bodies, fixedBodyData.cu:67-148, order spheres -> planes -> cylinders */
-static inline float len3(const float *v) { return sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
-static inline float dot3(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+/* glm::dot / glm::length as nvcc contracts them (refFloor SASS: FMUL y, FFMA x, FFMA z; IEEE sqrt) */
+static inline float dot3(const float *a, const float *b) { return DOT3_NV(a[0], b[0], a[1], b[1], a[2], b[2]); }
+static inline float len3(const float *v) { return sqrtf(dot3(v, v)); }
 
 static void respond(float *V, const float *n, float muT, float muN)
 {
@@ -754,7 +755,7 @@ static void respond(float *V, const float *n, float muT, float muN)
     float vT[3] = {V[0] - vN[0], V[1] - vN[1], V[2] - vN[2]};
     float mag = len3(vT);
     float a = mag == 0 ? 0 : fmaxf(1 - muT * (1 + muN) * len3(vN) / mag, 0.0f);
-    for (int k = 0; k < 3; k++) V[k] = -muN * vN[k] + a * vT[k];
+    for (int k = 0; k < 3; k++) V[k] = fmaf(vT[k], a, -(vN[k] * muN));   /* FMUL vN*muN; FFMA(vT, a, -.) */
 }
 
 static void fixed_bodies(o_scene *s, float muT, float muN)
@@ -769,7 +770,7 @@ static void fixed_bodies(o_scene *s, float muT, float muN)
             if (d < r) {
                 float inv = 1.0f / sqrtf(dot3(tc, tc));   /* glm::normalize = v * inversesqrt(dot) */
                 float n[3] = {tc[0] * inv, tc[1] * inv, tc[2] * inv};
-                for (int k = 0; k < 3; k++) x[k] += (r - d) * n[k];
+                for (int k = 0; k < 3; k++) x[k] = fmaf(r - d, n[k], x[k]);
                 respond(v, n, muT, muN);
             }
         }
@@ -781,7 +782,7 @@ static void fixed_bodies(o_scene *s, float muT, float muN)
             float rel[3] = {x[0] - p0[0], x[1] - p0[1], x[2] - p0[2]};
             float sd = dot3(rel, up);
             if (sd < 0 && dot3(v, up) < 0) {
-                for (int k = 0; k < 3; k++) x[k] -= sd * up[k];
+                for (int k = 0; k < 3; k++) x[k] = fmaf(-up[k], sd, x[k]);   /* FFMA(-up, sd, x) */
                 respond(v, up, muT, muN);
             }
         }
@@ -797,13 +798,13 @@ static void fixed_bodies(o_scene *s, float muT, float muN)
                 float m0 = (k == 0 ? 1.0f : 0.0f) - ax[0] * ax[k];
                 float m1 = (k == 1 ? 1.0f : 0.0f) - ax[1] * ax[k];
                 float m2 = (k == 2 ? 1.0f : 0.0f) - ax[2] * ax[k];
-                nn[k] = m0 * rel[0] + m1 * rel[1] + m2 * rel[2];
+                nn[k] = DOT3_NV(m0, rel[0], m1, rel[1], m2, rel[2]);
             }
             float d = len3(nn);
             if (d < r) {
                 float inv = 1.0f / sqrtf(dot3(nn, nn));
                 float n[3] = {nn[0] * inv, nn[1] * inv, nn[2] * inv};
-                for (int k = 0; k < 3; k++) x[k] += (r - d) * n[k];
+                for (int k = 0; k < 3; k++) x[k] = fmaf(r - d, n[k], x[k]);
                 respond(v, n, muT, muN);
             }
         }
@@ -923,7 +924,7 @@ static int solver_step(o_scene *s, const o_params *p)
     for (int v = 0; v < nV; v++) {   /* computeSn pdUtil.cu:73-95 */
         float dt2_m_1 = 1.0f / s->massDt_2s[v];
         for (int k = 0; k < 3; k++)
-            s->sn[3 * v + k] = s->X[3 * v + k] + dt * s->V[3 * v + k] + dt2_m_1 * s->ExtForce[3 * v + k];
+            s->sn[3 * v + k] = fmaf(s->ExtForce[3 * v + k], dt2_m_1, fmaf(s->V[3 * v + k], dt, s->X[3 * v + k]));   /* computeSn SASS: 2 FFMA */
     }
     memcpy(s->sn_old, s->sn, N * sizeof(float));
     int jacobi = (p->global_solver == 0);
@@ -938,14 +939,14 @@ static int solver_step(o_scene *s, const o_params *p)
             for (int v = 0; v < nV; v++) {   /* getErrorKern pdUtil.cu:195-214 */
                 float c = s->massDt_2s[v], md = s->matrix_diag[v];
                 for (int k = 0; k < 3; k++)
-                    s->next_x[3 * v + k] = (s->b[3 * v + k] - c * s->sn[3 * v + k]) / (c + md) + s->sn[3 * v + k];
+                    s->next_x[3 * v + k] = fmaf(-c, s->sn[3 * v + k], s->b[3 * v + k]) / (c + md) + s->sn[3 * v + k];   /* FFMA(-c,q,b); IEEE div; FADD */
             }
             if (i <= 10) omega = 1;                                   /* pdSolver.cu:196-198 */
             else if (i == 11) omega = 2 / (2 - p->rho * p->rho);
             else omega = 4 / (4 - p->rho * p->rho * omega);
             for (size_t k = 0; k < N; k++) {  /* chebyshevKern pdUtil.cu:216-226 (0.9 is a double) */
-                float nx = (float)(0.9 * (double)(s->next_x[k] - s->sn[k]) + (double)s->sn[k]);
-                nx = (nx - s->prev_x[k]) * omega + s->prev_x[k];
+                float nx = (float)fma((double)(s->next_x[k] - s->sn[k]), 0.9, (double)s->sn[k]);   /* DFMA */
+                nx = fmaf(nx - s->prev_x[k], omega, s->prev_x[k]);                                /* FFMA */
                 s->next_x[k] = nx;
                 s->prev_x[k] = s->sn[k];
                 s->sn[k] = nx;

@@ -111,41 +111,41 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
             ++t1;
         }
         if (t1 == t0) throw std::runtime_error("tile builder: empty tile");
-        std::sort(vl.begin(), vl.end());
         const uint32_t nLocal = (uint32_t)vl.size(), nTets = (uint32_t)(t1 - t0);
+        // in-tile incidence count of every touched vertex, then order: count descending, id ascending
+        for (uint32_t l = 0; l < nLocal; ++l) lidx[vl[l]] = 0;
+        for (int t = t0; t < t1; ++t) for (int k = 0; k < 4; ++k) lidx[tet[4 * (size_t)t + k]]++;
+        std::sort(vl.begin(), vl.end(), [&](uint32_t a, uint32_t b) { return lidx[a] != lidx[b] ? lidx[a] > lidx[b] : a < b; });
+        std::vector<uint16_t> deg((size_t)nLocal + 1, 0);
+        for (uint32_t l = 0; l < nLocal; ++l) { deg[l + 1] = (uint16_t)(deg[l] + lidx[vl[l]]); }
         for (uint32_t l = 0; l < nLocal; ++l) { lidx[vl[l]] = l; vcount[vl[l] + 1]++; }
         L.maxLocal = std::max(L.maxLocal, (int)nLocal);
-        const size_t nLp = rup(nLocal, 4), nTp = rup(nTets, 4);
-        const size_t offV = 16, offC = offV + 4 * nLp, offB = offC + 8 * nTp, offW = offB + 36 * nTp,
-                     offIO = offW + 4 * nTp, offI = offIO + rup(2 * ((size_t)nLocal + 1), 16),
-                     recBytes = offI + rup(2 * 4 * (size_t)nTets, 16);
+        const size_t offI = tile_off_inc(nTets), offIO = tile_off_incoff(nTets), offV = tile_off_vlist(nTets, nLocal),
+                     recBytes = tile_rec_bytes(nTets, nLocal);
         const size_t base = L.records.size();
         L.records.resize(base + recBytes, 0);
         uint8_t* rec = L.records.data() + base;
         TileHeader h{nTets, nLocal, slot, (uint32_t)recBytes};
         std::memcpy(rec, &h, 16);
         std::memcpy(rec + offV, vl.data(), 4 * (size_t)nLocal);
-        uint16_t* cidx = reinterpret_cast<uint16_t*>(rec + offC);
-        float* Bm = reinterpret_cast<float*>(rec + offB);
-        float* ww = reinterpret_cast<float*>(rec + offW);
         uint16_t* incOff = reinterpret_cast<uint16_t*>(rec + offIO);
         uint16_t* inc = reinterpret_cast<uint16_t*>(rec + offI);
-        std::vector<uint16_t> deg((size_t)nLocal + 1, 0);
-        for (uint32_t tl = 0; tl < nTets; ++tl) {
-            const size_t t = (size_t)t0 + tl;
-            for (int k = 0; k < 4; ++k) {
-                const uint16_t l = (uint16_t)lidx[tet[4 * t + k]];
-                cidx[4 * tl + k] = l;
-                deg[l + 1]++;
-            }
-            for (int e = 0; e < 9; ++e) Bm[e * nTp + tl] = DmInv[9 * t + e];
-            ww[tl] = w[t];
-        }
-        for (uint32_t l = 0; l < nLocal; ++l) deg[l + 1] = (uint16_t)(deg[l + 1] + deg[l]);
         std::memcpy(incOff, deg.data(), 2 * ((size_t)nLocal + 1));
         std::vector<uint16_t> fill(deg.begin(), deg.end() - 1);
-        for (uint32_t tl = 0; tl < nTets; ++tl)
-            for (int k = 0; k < 4; ++k) inc[fill[cidx[4 * tl + k]]++] = (uint16_t)(tl * 4 + k);
+        for (uint32_t tl = 0; tl < nTets; ++tl) {
+            const size_t t = (size_t)t0 + tl;
+            float* tr = reinterpret_cast<float*>(rec + 16 + 48 * (size_t)tl);
+            for (int e = 0; e < 9; ++e) tr[e] = DmInv[9 * t + e];
+            tr[9] = w[t];
+            uint32_t c[4];
+            for (int k = 0; k < 4; ++k) {
+                c[k] = lidx[tet[4 * t + k]];
+                inc[fill[c[k]]++] = (uint16_t)(k * TILE_HSTRIDE + tl * 16);
+            }
+            const uint32_t c01 = (c[0] * 16u) | ((c[1] * 16u) << 16), c23 = (c[2] * 16u) | ((c[3] * 16u) << 16);
+            std::memcpy(&tr[10], &c01, 4);
+            std::memcpy(&tr[11], &c23, 4);
+        }
         slotBase.push_back(slot);
         slot += nLocal;
         t0 = t1;
@@ -163,7 +163,7 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
     for (int ti = 0; ti < L.nTiles; ++ti) {
         const uint8_t* rec = L.records.data() + L.tileRecOff[ti];
         TileHeader h; std::memcpy(&h, rec, 16);
-        const uint32_t* vlist = reinterpret_cast<const uint32_t*>(rec + 16);
+        const uint32_t* vlist = reinterpret_cast<const uint32_t*>(rec + tile_off_vlist(h.nTets, h.nLocal));
         for (uint32_t l = 0; l < h.nLocal; ++l) L.vslot[fillv[vlist[l]]++] = h.slotBase + l;
     }
 }

@@ -8,20 +8,31 @@
 
 namespace pdb200 {
 
-constexpr int TILE_T = 256;     // tets per tile (= threads per CTA of the local kernel)
-constexpr int TILE_NLMAX = 512; // max distinct vertices per tile (tile is closed early beyond)
+constexpr int TILE_T = 256;      // tets per tile (= threads per CTA of the local kernel)
+constexpr int TILE_NLMAX = 384;  // max distinct vertices per tile (a tile is closed early beyond)
+constexpr int TILE_HSTRIDE = TILE_T * 16;   // bytes between corner planes of the per-tile H scratch
 
-// Header of one packed tile record (16 bytes), followed by the sections described in DESIGN.md:
-//   vlist   u32[nLp]            global (renumbered) vertex id of each tile-local vertex, ascending
-//   cidx    u16[4][nTp] as uint2[nTp]   tile-local corner indices of each tet
-//   Bm      f32[9][nTp]         DmInv, row-major entries, SoA over tets
-//   w       f32[nTp]            |V0| * mu
-//   incOff  u16[nLocal+1]       tile-local incidence CSR offsets   (padded to 16 B)
-//   inc     u16[4*nTets]        entries tetLocal*4 + corner, ascending (padded to 16 B)
-// nLp = roundup(nLocal,4), nTp = roundup(nTets,4).
+// One packed tile record, moved to shared memory by ONE bulk copy:
+//   +0      TileHeader                                                   16 B
+//   +16     tet records, 48 B each: f32 B[9] (DmInv, row-major), f32 w = |V0|*mu,
+//           u32 c01, u32 c23 -- the four tile-local corner indices * 16 (byte offsets into the
+//           staged vertex array), two u16 per word                       48*nTets
+//   offI    inc  u16[4*nTets]: per tile-local vertex, ascending (tet, corner), each entry the byte
+//           offset corner*TILE_HSTRIDE + tet*16 of that contribution in the H scratch   (pad 16)
+//   offIO   incOff u16[nLocal+1]: tile-local incidence CSR offsets        (pad 16)
+//   offV    vlist u32[nLocal]: global (renumbered) id of each tile-local vertex, ordered by
+//           (in-tile incidence count descending, id ascending) so that the lanes of a warp
+//           walk incidence lists of similar length                        (pad 16)
 struct TileHeader {
     uint32_t nTets, nLocal, slotBase, recBytes;
 };
+inline uint32_t rup16(uint32_t x) { return (x + 15u) & ~15u; }
+inline uint32_t tile_off_inc(uint32_t nTets) { return 16u + 48u * nTets; }
+inline uint32_t tile_off_incoff(uint32_t nTets) { return tile_off_inc(nTets) + rup16(8u * nTets); }
+inline uint32_t tile_off_vlist(uint32_t nTets, uint32_t nLocal) { return tile_off_incoff(nTets) + rup16(2u * (nLocal + 1u)); }
+inline uint32_t tile_rec_bytes(uint32_t nTets, uint32_t nLocal) { return tile_off_vlist(nTets, nLocal) + rup16(4u * nLocal); }
+// largest possible record, rounded to 128 B: the size of one TMA landing buffer
+constexpr uint32_t TILE_RECMAX = ((16u + 48u * TILE_T + 8u * TILE_T + ((2u * (TILE_NLMAX + 1u) + 15u) & ~15u) + 4u * TILE_NLMAX) + 127u) & ~127u;
 
 struct Layout {
     int nV = 0, nT = 0;

@@ -25,7 +25,7 @@ struct Engine::Impl {
     uint8_t* records = nullptr;
     unsigned long long* recOff = nullptr;
     uint32_t *vslotPtr = nullptr, *vslot = nullptr;
-    float* P = nullptr;
+    float4* P = nullptr;             // one partial RHS sum per (tile, tile-local vertex) slot
     // per-vertex state (renumbered, padded float4)
     float4* q[3] = {nullptr, nullptr, nullptr};
     float4 *so4 = nullptr, *X = nullptr, *V = nullptr, *XT = nullptr, *X0 = nullptr;
@@ -35,7 +35,6 @@ struct Engine::Impl {
     float* stage3 = nullptr;          // 3 x (3 nV) floats, AoS staging for import/export
     float* fbData = nullptr;
     DevFixedBodies fb{};
-    LocalSmem lay{};
     cudaGraphExec_t graphExec = nullptr;
     cudaGraph_t graph = nullptr;
     std::vector<cudaEvent_t> events;
@@ -81,7 +80,7 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     d.recOff = dalloc<unsigned long long>(L_.tileRecOff.size());
     d.vslotPtr = dalloc<uint32_t>(L_.vslotPtr.size());
     d.vslot = dalloc<uint32_t>(L_.vslot.size());
-    d.P = dalloc<float>(3 * (size_t)L_.nSlots);
+    d.P = dalloc<float4>((size_t)L_.nSlots);
     for (int k = 0; k < 3; ++k) d.q[k] = dalloc<float4>(nV_);
     d.so4 = dalloc<float4>(nV_); d.X = dalloc<float4>(nV_); d.V = dalloc<float4>(nV_);
     d.XT = dalloc<float4>(nV_); d.X0 = dalloc<float4>(nV_);
@@ -132,17 +131,14 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
         d.fb.nPlanes = (int)(planes.size() / 6); d.fb.nSpheres = (int)(spheres.size() / 4); d.fb.nCyls = (int)(cyls.size() / 7);
         d.fb.planes = d.fbData; d.fb.spheres = d.fbData + planes.size(); d.fb.cyls = d.fbData + planes.size() + spheres.size();
     }
-    // local kernel geometry
-    uint32_t maxRec = 0;
-    for (int t = 0; t < L_.nTiles; ++t) maxRec = std::max<uint32_t>(maxRec, (uint32_t)(L_.tileRecOff[t + 1] - L_.tileRecOff[t]));
-    d.lay = local_smem_layout(maxRec);
+    // local kernel geometry: fixed shared-memory carve-up (pd_kernels.cuh), persistent CTAs
     auto setAttr = [&](const void* fn) {
-        CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.lay.total));
+        CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOCAL_SMEM_BYTES));
     };
     setAttr((const void*)k_local<0, true>); setAttr((const void*)k_local<0, false>);
     setAttr((const void*)k_local<1, true>); setAttr((const void*)k_local<1, false>);
     int perSm = 0;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_local<0, true>, TILE_T, d.lay.total));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_local<0, true>, TILE_T, LOCAL_SMEM_BYTES));
     if (perSm < 1) throw std::runtime_error("local kernel does not fit on an SM");
     if (opt.ctasPerSm > 0) perSm = std::min(perSm, opt.ctasPerSm);
     localGrid_ = std::min(L_.nTiles, numSms_ * perSm);
@@ -200,20 +196,18 @@ void Engine::prepare()
     for (int ti = 0; ti < L_.nTiles; ++ti) {
         const uint8_t* rec = L_.records.data() + L_.tileRecOff[ti];
         TileHeader h; std::memcpy(&h, rec, 16);
-        const uint32_t nLp = (h.nLocal + 3u) & ~3u, nTp = (h.nTets + 3u) & ~3u;
-        const uint32_t* vlist = reinterpret_cast<const uint32_t*>(rec + 16);
-        const uint16_t* cidx = reinterpret_cast<const uint16_t*>(rec + 16 + 4 * nLp);
-        const float* Bm = reinterpret_cast<const float*>(rec + 16 + 4 * nLp + 8 * nTp);
-        const float* w = Bm + 9 * nTp;
+        const uint32_t* vlist = reinterpret_cast<const uint32_t*>(rec + tile_off_vlist(h.nTets, h.nLocal));
         for (uint32_t t = 0; t < h.nTets; ++t) {
-            float B[9];
-            for (int e = 0; e < 9; ++e) B[e] = Bm[e * nTp + t];
+            const float* B = reinterpret_cast<const float*>(rec + 16 + 48 * (size_t)t);
+            const float w = B[9];
+            uint32_t cw[2]; std::memcpy(cw, B + 10, 8);
+            const uint32_t loc[4] = {(cw[0] & 0xffffu) >> 4, cw[0] >> 20, (cw[1] & 0xffffu) >> 4, cw[1] >> 20};
             for (int i = 0; i < 4; ++i) {
                 float col[3];
                 for (int r = 0; r < 3; ++r)
                     col[r] = (i == 0) ? (B[0 * 3 + r] * -1.0f + B[1 * 3 + r] * -1.0f + B[2 * 3 + r] * -1.0f) : B[(i - 1) * 3 + r];
                 const float kii = col[0] * col[0] + col[1] * col[1] + col[2] * col[2];
-                d.hostMd[vlist[cidx[4 * t + i]]] += kii * w[t];
+                d.hostMd[vlist[loc[i]]] += kii * w;
             }
         }
     }
@@ -245,9 +239,9 @@ void Engine::enqueueStep(bool timed)
         float4* next = d.q[(i + 1) % 3];
         rec();
         if (opt_.rotMode == 0)
-            k_local<0, true><<<localGrid_, TILE_T, d.lay.total, stream_>>>(d.records, d.recOff, L_.nTiles, cur, d.P, d.lay);
+            k_local<0, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.recOff, L_.nTiles, cur, d.P);
         else
-            k_local<1, true><<<localGrid_, TILE_T, d.lay.total, stream_>>>(d.records, d.recOff, L_.nTiles, cur, d.P, d.lay);
+            k_local<1, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.recOff, L_.nTiles, cur, d.P);
         rec();
         // omega recurrence in float, pdSolver.cu:196-198
         if (i <= 10) omega = 1;
@@ -412,9 +406,9 @@ float Engine::timeLocalKernelMs(int reps)
     CUDA_CHECK(cudaEventRecord(a, stream_));
     for (int r = 0; r < reps; ++r) {
         if (opt_.rotMode == 0)
-            k_local<0, true><<<localGrid_, TILE_T, d.lay.total, stream_>>>(d.records, d.recOff, L_.nTiles, d.XT, d.P, d.lay);
+            k_local<0, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.recOff, L_.nTiles, d.XT, d.P);
         else
-            k_local<1, true><<<localGrid_, TILE_T, d.lay.total, stream_>>>(d.records, d.recOff, L_.nTiles, d.XT, d.P, d.lay);
+            k_local<1, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.recOff, L_.nTiles, d.XT, d.P);
     }
     CUDA_CHECK(cudaEventRecord(b, stream_));
     CUDA_CHECK(cudaEventSynchronize(b));

@@ -81,37 +81,37 @@ __global__ void k_predict(int nV, const float4* __restrict__ X, const float4* __
 }
 
 // ------------------------------------------------------------------ local step (the hot kernel)
-// PdUtil::computeLocal (pdUtil.cu:97-145) for one tile of tets per CTA iteration:
-//   TMA bulk copy of the packed tile record -> shared memory (double buffered, mbarrier),
-//   gather of the tile's vertex positions -> shared,
-//   per tet F = Ds*DmInv, rotation, H = w (R - F) DmInv^T G (or w R DmInv^T G) -> shared,
-//   deterministic tile-local gather over the incidence CSR -> one partial sum per (tile, vertex).
-// No atomics anywhere: the reference's 12 float atomicAdds per tet become ordered sums.
-struct LocalSmem {
-    // dynamic shared memory carve-up (bytes), computed on the host by local_smem_layout()
-    uint32_t bufBytes;   // per TMA buffer (>= largest record, multiple of 128)
-    uint32_t offQs, offHs, offBar, total;
-};
-inline LocalSmem local_smem_layout(uint32_t maxRecBytes)
-{
-    LocalSmem s;
-    s.bufBytes = (maxRecBytes + 127u) / 128u * 128u;
-    s.offQs = 2 * s.bufBytes;
-    s.offHs = s.offQs + 16u * TILE_NLMAX;
-    s.offBar = s.offHs + 4u * 12u * TILE_T;
-    s.total = s.offBar + 16u;
-    return s;
+// PdUtil::computeLocal (pdUtil.cu:97-145) for one tile of <= TILE_T tets per CTA iteration:
+//   0. ONE bulk asynchronous copy (TMA, cp.async.bulk + mbarrier) lands the packed tile record in
+//      shared memory, double buffered: tile i+1 streams in while tile i is computed;
+//   A. the tile's distinct vertex positions are gathered once into shared memory;
+//   B. one tet per thread: 3 x LDS.128 (48-byte record: DmInv, w, corner offsets; the 48-byte
+//      stride is bank-conflict free), 4 x LDS.128 positions, F = Ds*DmInv, rotation,
+//      H = w (R - F) DmInv^T G (or w R DmInv^T G), 4 x STS.128 into the H scratch;
+//   C. one tile-local vertex per thread: ordered sum over the vertex's incidence list (entries are
+//      ready-made byte offsets into the H scratch) -> ONE partial sum per (tile, vertex) slot.
+// No atomics anywhere: the reference's 12 float atomicAdds per tet become ordered sums, so results
+// are run-to-run bit-identical.  Two __syncthreads per tile.
+// F and H are written with the fused/rounded operation pattern nvcc gives the reference's glm
+// expressions (see oracle/pd_oracle.c header), so that with ROT_MODE 1 every tet contribution is
+// bit-identical to the reference kernel's.
+constexpr uint32_t LOCAL_OFF_QS = 2u * TILE_RECMAX;
+constexpr uint32_t LOCAL_OFF_HS = LOCAL_OFF_QS + 16u * TILE_NLMAX;
+constexpr uint32_t LOCAL_OFF_BAR = LOCAL_OFF_HS + 4u * TILE_HSTRIDE;
+constexpr uint32_t LOCAL_SMEM_BYTES = LOCAL_OFF_BAR + 16u;
+
+__device__ __forceinline__ float dot3_nv(float a0, float b0, float a1, float b1, float a2, float b2)
+{   // a0*b0 + a1*b1 + a2*b2 as nvcc contracts the reference's glm products
+    return __fmaf_rn(a2, b2, __fmaf_rn(a0, b0, __fmul_rn(a1, b1)));
 }
 
 template <int ROT_MODE, bool JACOBI>
-__global__ void __launch_bounds__(TILE_T, 3)
+__global__ void __launch_bounds__(TILE_T, 4)
 k_local(const uint8_t* __restrict__ records, const unsigned long long* __restrict__ recOff, int nTiles,
-        const float4* __restrict__ q, float* __restrict__ P, LocalSmem lay)
+        const float4* __restrict__ q, float4* __restrict__ P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    float4* qs = reinterpret_cast<float4*>(smem + lay.offQs);
-    float* Hs = reinterpret_cast<float*>(smem + lay.offHs);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lay.offBar);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + LOCAL_OFF_BAR);
     const int tid = threadIdx.x;
 
     if (tid == 0) {
@@ -131,81 +131,87 @@ k_local(const uint8_t* __restrict__ records, const unsigned long long* __restric
     }
     for (int it = 0; tile < nTiles; tile += gridDim.x, ++it) {
         const int b = it & 1;
+        mbar_wait(&bar[b], (uint32_t)((it >> 1) & 1));
+
+        const uint8_t* rec = smem + b * TILE_RECMAX;
+        const uint4 hdr = *reinterpret_cast<const uint4*>(rec);      // nTets, nLocal, slotBase, recBytes
+        const uint32_t nTets = hdr.x, nLocal = hdr.y;
+        const uint32_t offI = 16u + 48u * nTets;
+        const uint32_t offIO = offI + ((8u * nTets + 15u) & ~15u);
+        const uint32_t offV = offIO + ((2u * (nLocal + 1u) + 15u) & ~15u);
+
+        // phase A: stage the tile's vertex positions
+        {
+            const uint32_t* vlist = reinterpret_cast<const uint32_t*>(rec + offV);
+            float4* qs = reinterpret_cast<float4*>(smem + LOCAL_OFF_QS);
+            for (uint32_t l = tid; l < nLocal; l += TILE_T) qs[l] = __ldg(&q[vlist[l]]);
+        }
+        __syncthreads();   // positions staged; every warp is past phase C of the previous tile
+
+        // the other buffer and the H scratch are free now: stream the next record in
         const int nextTile = tile + gridDim.x;
-        if (tid == 0 && nextTile < nTiles) {      // prefetch the next record into the other buffer
+        if (tid == 0 && nextTile < nTiles) {
             const unsigned long long o = recOff[nextTile];
             const uint32_t bytes = (uint32_t)(recOff[nextTile + 1] - o);
             mbar_expect_tx(&bar[b ^ 1], bytes);
-            bulk_g2s(smem + (b ^ 1) * lay.bufBytes, records + o, bytes, &bar[b ^ 1]);
+            bulk_g2s(smem + (b ^ 1) * TILE_RECMAX, records + o, bytes, &bar[b ^ 1]);
         }
-        mbar_wait(&bar[b], (uint32_t)((it >> 1) & 1));
-
-        const uint8_t* rec = smem + b * lay.bufBytes;
-        const TileHeader h = *reinterpret_cast<const TileHeader*>(rec);
-        const uint32_t nLp = (h.nLocal + 3u) & ~3u, nTp = (h.nTets + 3u) & ~3u;
-        const uint32_t* vlist = reinterpret_cast<const uint32_t*>(rec + 16);
-        const uint2* cidx = reinterpret_cast<const uint2*>(rec + 16 + 4 * nLp);
-        const float* Bm = reinterpret_cast<const float*>(rec + 16 + 4 * nLp + 8 * nTp);
-        const float* wv = Bm + 9 * nTp;
-        const uint16_t* incOff = reinterpret_cast<const uint16_t*>(wv + nTp);
-        const uint16_t* inc = incOff + ((h.nLocal + 1u + 7u) & ~7u);
-
-        // phase A: stage the tile's vertex positions
-        for (uint32_t l = tid; l < h.nLocal; l += TILE_T) qs[l] = __ldg(&q[vlist[l]]);
-        __syncthreads();
 
         // phase B: one tet per thread
-        if ((uint32_t)tid < h.nTets) {
-            const uint2 ci = cidx[tid];
-            const float4 p0 = qs[ci.x & 0xffffu], p1 = qs[ci.x >> 16], p2 = qs[ci.y & 0xffffu], p3 = qs[ci.y >> 16];
-            float B[9];
-#pragma unroll
-            for (int e = 0; e < 9; ++e) B[e] = Bm[e * nTp + tid];
-            const float w = wv[tid];
+        if ((uint32_t)tid < nTets) {
+            const float4* tr = reinterpret_cast<const float4*>(rec + 16 + 48 * tid);
+            const float4 r0 = tr[0], r1 = tr[1], r2 = tr[2];
+            const float B0 = r0.x, B1 = r0.y, B2 = r0.z, B3 = r0.w, B4 = r1.x, B5 = r1.y, B6 = r1.z, B7 = r1.w, B8 = r2.x;
+            const float w = r2.y;
+            const uint32_t c01 = __float_as_uint(r2.z), c23 = __float_as_uint(r2.w);
+            const uint8_t* qsb = smem + LOCAL_OFF_QS;
+            const float4 p0 = *reinterpret_cast<const float4*>(qsb + (c01 & 0xffffu));
+            const float4 p1 = *reinterpret_cast<const float4*>(qsb + (c01 >> 16));
+            const float4 p2 = *reinterpret_cast<const float4*>(qsb + (c23 & 0xffffu));
+            const float4 p3 = *reinterpret_cast<const float4*>(qsb + (c23 >> 16));
             // Ds columns = edges; F = Ds * DmInv  (row-major F[r][c] = sum_k Ds[r][k] B[k][c])
             const float d00 = p1.x - p0.x, d01 = p2.x - p0.x, d02 = p3.x - p0.x;
             const float d10 = p1.y - p0.y, d11 = p2.y - p0.y, d12 = p3.y - p0.y;
             const float d20 = p1.z - p0.z, d21 = p2.z - p0.z, d22 = p3.z - p0.z;
             Mat3 F, R;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                F.m[0 + c] = d00 * B[c] + d01 * B[3 + c] + d02 * B[6 + c];
-                F.m[3 + c] = d10 * B[c] + d11 * B[3 + c] + d12 * B[6 + c];
-                F.m[6 + c] = d20 * B[c] + d21 * B[3 + c] + d22 * B[6 + c];
-            }
+            F.m[0] = dot3_nv(d00, B0, d01, B3, d02, B6); F.m[1] = dot3_nv(d00, B1, d01, B4, d02, B7); F.m[2] = dot3_nv(d00, B2, d01, B5, d02, B8);
+            F.m[3] = dot3_nv(d10, B0, d11, B3, d12, B6); F.m[4] = dot3_nv(d10, B1, d11, B4, d12, B7); F.m[5] = dot3_nv(d10, B2, d11, B5, d12, B8);
+            F.m[6] = dot3_nv(d20, B0, d21, B3, d22, B6); F.m[7] = dot3_nv(d20, B1, d21, B4, d22, B7); F.m[8] = dot3_nv(d20, B2, d21, B5, d22, B8);
             corotation<ROT_MODE>(F, R);
             float M[9];
 #pragma unroll
-            for (int e = 0; e < 9; ++e) M[e] = w * (JACOBI ? (R.m[e] - F.m[e]) : R.m[e]);
+            for (int e = 0; e < 9; ++e) M[e] = __fmul_rn(w, JACOBI ? __fsub_rn(R.m[e], F.m[e]) : R.m[e]);
             // H = M * DmInv^T ; column j (vertex j+1): H[r][j] = sum_k M[r][k] B[j][k] ; vertex 0: -(sum of columns)
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const float h1 = M[3 * r] * B[0] + M[3 * r + 1] * B[1] + M[3 * r + 2] * B[2];
-                const float h2 = M[3 * r] * B[3] + M[3 * r + 1] * B[4] + M[3 * r + 2] * B[5];
-                const float h3 = M[3 * r] * B[6] + M[3 * r + 1] * B[7] + M[3 * r + 2] * B[8];
-                Hs[(0 + r) * TILE_T + tid] = -h1 - h2 - h3;
-                Hs[(3 + r) * TILE_T + tid] = h1;
-                Hs[(6 + r) * TILE_T + tid] = h2;
-                Hs[(9 + r) * TILE_T + tid] = h3;
-            }
+            float4 h0, h1, h2, h3;
+            h1.x = dot3_nv(M[0], B0, M[1], B1, M[2], B2); h2.x = dot3_nv(M[0], B3, M[1], B4, M[2], B5); h3.x = dot3_nv(M[0], B6, M[1], B7, M[2], B8);
+            h1.y = dot3_nv(M[3], B0, M[4], B1, M[5], B2); h2.y = dot3_nv(M[3], B3, M[4], B4, M[5], B5); h3.y = dot3_nv(M[3], B6, M[4], B7, M[5], B8);
+            h1.z = dot3_nv(M[6], B0, M[7], B1, M[8], B2); h2.z = dot3_nv(M[6], B3, M[7], B4, M[8], B5); h3.z = dot3_nv(M[6], B6, M[7], B7, M[8], B8);
+            h0.x = __fsub_rn(__fsub_rn(-h1.x, h2.x), h3.x);
+            h0.y = __fsub_rn(__fsub_rn(-h1.y, h2.y), h3.y);
+            h0.z = __fsub_rn(__fsub_rn(-h1.z, h2.z), h3.z);
+            h0.w = h1.w = h2.w = h3.w = 0.f;
+            float4* Hs = reinterpret_cast<float4*>(smem + LOCAL_OFF_HS) + tid;
+            Hs[0] = h0; Hs[TILE_T] = h1; Hs[2 * TILE_T] = h2; Hs[3 * TILE_T] = h3;
         }
-        __syncthreads();
+        __syncthreads();   // H scratch complete
 
-        // phase C: ordered gather per tile-local vertex -> partial sum slot
-        for (uint32_t l = tid; l < h.nLocal; l += TILE_T) {
-            const uint32_t e0 = incOff[l], e1 = incOff[l + 1];
-            float sx = 0.f, sy = 0.f, sz = 0.f;
-            for (uint32_t e = e0; e < e1; ++e) {
-                const uint32_t ent = inc[e];
-                const uint32_t base = (ent & 3u) * (3u * TILE_T) + (ent >> 2);
-                sx += Hs[base];
-                sy += Hs[base + TILE_T];
-                sz += Hs[base + 2 * TILE_T];
+        // phase C: ordered gather per tile-local vertex -> partial-sum slot
+        {
+            const uint16_t* incOff = reinterpret_cast<const uint16_t*>(rec + offIO);
+            const uint16_t* inc = reinterpret_cast<const uint16_t*>(rec + offI);
+            const uint8_t* Hb = smem + LOCAL_OFF_HS;
+            for (uint32_t l = tid; l < nLocal; l += TILE_T) {
+                const uint32_t e0 = incOff[l], e1 = incOff[l + 1];
+                float sx = 0.f, sy = 0.f, sz = 0.f;
+                for (uint32_t e = e0; e < e1; ++e) {
+                    const float4 h = *reinterpret_cast<const float4*>(Hb + inc[e]);
+                    sx += h.x; sy += h.y; sz += h.z;
+                }
+                P[hdr.z + l] = make_float4(sx, sy, sz, 0.f);
             }
-            float* dst = P + 3ull * (h.slotBase + l);
-            dst[0] = sx; dst[1] = sy; dst[2] = sz;
         }
-        __syncthreads();   // Hs/qs and buffer b are free for reuse after this point
+        // no barrier here: the next iteration's first barrier (after its phase A, which touches
+        // neither the H scratch nor this record buffer) orders phase C against every later write
     }
 }
 
@@ -215,7 +221,7 @@ k_local(const uint8_t* __restrict__ records, const unsigned long long* __restric
 __global__ void k_vertex_jacobi(int nV, const float4* __restrict__ qcur, const float4* __restrict__ qprev,
                                 float4* __restrict__ qnext, const float4* __restrict__ so4,
                                 const float2* __restrict__ cc, const uint32_t* __restrict__ vslotPtr,
-                                const uint32_t* __restrict__ vslot, const float* __restrict__ P,
+                                const uint32_t* __restrict__ vslot, const float4* __restrict__ P,
                                 float omega, float wdbc)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -230,8 +236,8 @@ __global__ void k_vertex_jacobi(int nV, const float4* __restrict__ qcur, const f
         bx = c * so.x; by = c * so.y; bz = c * so.z;
         const uint32_t e0 = vslotPtr[v], e1 = vslotPtr[v + 1];
         for (uint32_t e = e0; e < e1; ++e) {
-            const float* p = P + 3ull * vslot[e];
-            bx += p[0]; by += p[1]; bz += p[2];
+            const float4 p = __ldg(&P[vslot[e]]);
+            bx += p.x; by += p.y; bz += p.z;
         }
     }
     const float4 q = qcur[v], pr = qprev[v];
@@ -252,7 +258,7 @@ __global__ void k_vertex_jacobi(int nV, const float4* __restrict__ qcur, const f
 // right-hand side for the direct / CG global solves: b = c*s_old + sum of partials (R, not R-F)
 __global__ void k_vertex_rhs(int nV, const float4* __restrict__ so4, const float2* __restrict__ cc,
                              const uint32_t* __restrict__ vslotPtr, const uint32_t* __restrict__ vslot,
-                             const float* __restrict__ P, float wdbc, float4* __restrict__ rhs)
+                             const float4* __restrict__ P, float wdbc, float4* __restrict__ rhs)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nV) return;
@@ -265,8 +271,8 @@ __global__ void k_vertex_rhs(int nV, const float4* __restrict__ so4, const float
         bx = c * so.x; by = c * so.y; bz = c * so.z;
         const uint32_t e0 = vslotPtr[v], e1 = vslotPtr[v + 1];
         for (uint32_t e = e0; e < e1; ++e) {
-            const float* p = P + 3ull * vslot[e];
-            bx += p[0]; by += p[1]; bz += p[2];
+            const float4 p = __ldg(&P[vslot[e]]);
+            bx += p.x; by += p.y; bz += p.z;
         }
     }
     rhs[v] = make_float4(bx, by, bz, 0.f);

@@ -144,11 +144,13 @@ __device__ __forceinline__ void qr_givens(float* B, float* U, int rp, int rq, in
 }
 }  // namespace svd_detail
 
-// Full SVD-based rotation (reference semantics, bit-identical to oracle o_rotation).
-__device__ __noinline__ void rotation_svd(const Mat3& Fm, Mat3& Rm)
+// Full SVD-based rotation (reference semantics, bit-identical to oracle o_rotation).  Out of line
+// (it is the rare path); operands travel by value so that the caller keeps F and R in registers.
+__device__ __noinline__ Mat3 rotation_svd_call(float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7, float a8)
 {
     using namespace svd_detail;
-    const float* A = Fm.m;
+    const float A[9] = {a0, a1, a2, a3, a4, a5, a6, a7, a8};
+    Mat3 Rm;
     float s11 = mul(A[0], A[0]); s11 = add(mul(A[3], A[3]), s11); s11 = add(mul(A[6], A[6]), s11);
     float s21 = mul(A[1], A[0]); s21 = add(mul(A[4], A[3]), s21); s21 = add(mul(A[7], A[6]), s21);
     float s31 = mul(A[2], A[0]); s31 = add(mul(A[5], A[3]), s31); s31 = add(mul(A[8], A[6]), s31);
@@ -198,21 +200,23 @@ __device__ __noinline__ void rotation_svd(const Mat3& Fm, Mat3& Rm)
     qr_givens(B, U, 0, 1, 0);
     qr_givens(B, U, 0, 2, 0);
     qr_givens(B, U, 1, 2, 1);
-    // R = U * V^T (glm product order), then the reference's det<0 column flip (pdUtil.cu:119-122)
+    // R = U * V^T exactly as nvcc contracts the reference's glm product (computeLocal SASS: the
+    // k=1 product is rounded, k=0 and k=2 are fused), then the det<0 column flip (pdUtil.cu:119-122)
     float* R = Rm.m;
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float acc = mul(U[r * 3 + 0], V[c * 3 + 0]);
-            acc = add(acc, mul(U[r * 3 + 1], V[c * 3 + 1]));
-            acc = add(acc, mul(U[r * 3 + 2], V[c * 3 + 2]));
-            R[r * 3 + c] = acc;
-        }
+        for (int c = 0; c < 3; ++c)
+            R[r * 3 + c] = __fmaf_rn(U[r * 3 + 2], V[c * 3 + 2], __fmaf_rn(U[r * 3 + 0], V[c * 3 + 0], mul(U[r * 3 + 1], V[c * 3 + 1])));
     const float det = add(sub(mul(R[0], sub(mul(R[4], R[8]), mul(R[5], R[7]))),
                               mul(R[3], sub(mul(R[1], R[8]), mul(R[7], R[2])))),
                           mul(R[6], sub(mul(R[1], R[5]), mul(R[4], R[2]))));
     if (det < 0.f) { R[2] = -R[2]; R[5] = -R[5]; R[8] = -R[8]; }
+    return Rm;
+}
+__device__ __forceinline__ void rotation_svd(const Mat3& F, Mat3& R)
+{
+    R = rotation_svd_call(F.m[0], F.m[1], F.m[2], F.m[3], F.m[4], F.m[5], F.m[6], F.m[7], F.m[8]);
 }
 
 // ------------------------------------------------------------------ fast path: Newton polar

@@ -4,7 +4,8 @@ the bit-exact reorder / renumber / tile / incidence / slot checks.  Independent 
 import numpy as np
 
 TILE_T = 256
-TILE_NLMAX = 512
+TILE_NLMAX = 384
+TILE_HSTRIDE = TILE_T * 16
 
 
 def spread3(x):
@@ -88,29 +89,36 @@ def build(X, Tet, mu, reorder=True):
             if len(seen) + len(new) > TILE_NLMAX:
                 break
             seen.update(new); t1 += 1
-        vl = np.array(sorted(seen), np.uint32)
-        nLocal, nTets = len(vl), t1 - t0
+        tl_tets = tet_new[t0:t1].astype(np.int64)
+        nTets = t1 - t0
+        ids, counts = np.unique(tl_tets.reshape(-1), return_counts=True)
+        order = np.lexsort((ids, -counts))                 # in-tile incidence count descending, id ascending
+        vl = ids[order].astype(np.uint32)
+        nLocal = len(vl)
         max_local = max(max_local, nLocal)
-        nLp, nTp = rup(nLocal, 4), rup(nTets, 4)
-        lidx = {int(v): i for i, v in enumerate(vl)}
-        cidx = np.zeros((nTp, 4), np.uint16)
-        cidx[:nTets] = np.vectorize(lidx.get)(tet_new[t0:t1]).astype(np.uint16)
-        Bm = np.zeros((9, nTp), np.float32); Bm[:, :nTets] = Br[t0:t1].T
-        w = np.zeros(nTp, np.float32); w[:nTets] = wr[t0:t1]
-        ent = np.arange(4 * nTets, dtype=np.uint16)             # tl*4+k, ascending
-        owner = cidx[:nTets].reshape(-1)
-        order = np.argsort(owner, kind="stable")
-        inc = ent[order]
+        lidx = np.zeros(nV, np.int64); lidx[vl] = np.arange(nLocal)
+        cidx = lidx[tl_tets]                               # (nTets, 4) tile-local corner indices
+        # 48-byte tet records: B[9], w, c01, c23 (corner index * 16, two u16 per word)
+        trec = np.zeros((nTets, 12), np.uint32)
+        trec[:, :9] = Br[t0:t1].view(np.uint32)
+        trec[:, 9] = wr[t0:t1].view(np.uint32)
+        trec[:, 10] = (cidx[:, 0] * 16) | ((cidx[:, 1] * 16) << 16)
+        trec[:, 11] = (cidx[:, 2] * 16) | ((cidx[:, 3] * 16) << 16)
+        # incidence lists: per tile-local vertex, ascending (tet, corner); entry = corner*HSTRIDE + tet*16
+        owner = cidx.reshape(-1)
+        tl = np.repeat(np.arange(nTets), 4); k = np.tile(np.arange(4), nTets)
+        ent = (k * TILE_HSTRIDE + tl * 16).astype(np.uint16)
+        inc = ent[np.argsort(owner, kind="stable")]
         inc_off = np.zeros(nLocal + 1, np.uint16)
         inc_off[1:] = np.cumsum(np.bincount(owner, minlength=nLocal)).astype(np.uint16)
+        i_bytes = rup(8 * nTets, 16); io_bytes = rup(2 * (nLocal + 1), 16); v_bytes = rup(4 * nLocal, 16)
+        rec_bytes = 16 + 48 * nTets + i_bytes + io_bytes + v_bytes
         rec = bytearray()
-        io_bytes = rup(2 * (nLocal + 1), 16); i_bytes = rup(8 * nTets, 16)
-        rec_bytes = 16 + 4 * nLp + 8 * nTp + 36 * nTp + 4 * nTp + io_bytes + i_bytes
         rec += np.array([nTets, nLocal, slot, rec_bytes], np.uint32).tobytes()
-        rec += vl.tobytes() + b"\0" * (4 * (nLp - nLocal))
-        rec += cidx.tobytes() + Bm.tobytes() + w.tobytes()
-        rec += inc_off.tobytes() + b"\0" * (io_bytes - 2 * (nLocal + 1))
+        rec += trec.tobytes()
         rec += inc.tobytes() + b"\0" * (i_bytes - 8 * nTets)
+        rec += inc_off.tobytes() + b"\0" * (io_bytes - 2 * (nLocal + 1))
+        rec += vl.tobytes() + b"\0" * (v_bytes - 4 * nLocal)
         assert len(rec) == rec_bytes
         recs.append(bytes(rec))
         for l, v in enumerate(vl):
