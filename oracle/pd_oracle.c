@@ -291,20 +291,25 @@ static void rest_one(const float *X, const uint32_t *t, float *Bi, float *V0)
     /* m[c][r]: column c = x_{c+1} - x0 */
     float m[3][3];
     for (int r = 0; r < 3; r++) { m[0][r] = x1[r] - x0[r]; m[1][r] = x2[r] - x0[r]; m[2][r] = x3[r] - x0[r]; }
-    float det = +m[0][0] * (m[1][1] * m[2][2] - m[2][1] * m[1][2])
-                - m[1][0] * (m[0][1] * m[2][2] - m[2][1] * m[0][2])
-                + m[2][0] * (m[0][1] * m[1][2] - m[1][1] * m[0][2]);
+    /* glm::inverse / glm::determinant as nvcc contracts them in computeInvDmV0 (SASS of the sm_100a
+     * build): every 2x2 minor a*b - c*d is fma(a, b, -(c*d)); det = fma(m20, C2, fma(m00, C0, -(m10*C1))) */
+#define MINOR(a, b, c, d) fmaf((a), (b), -((c) * (d)))
+    float c0 = MINOR(m[1][1], m[2][2], m[2][1], m[1][2]);
+    float c1 = MINOR(m[0][1], m[2][2], m[2][1], m[0][2]);
+    float c2 = MINOR(m[0][1], m[1][2], m[1][1], m[0][2]);
+    float det = fmaf(m[2][0], c2, fmaf(m[0][0], c0, -(m[1][0] * c1)));
     float ood = 1.0f / det;
     float inv[3][3]; /* inv[c][r] */
-    inv[0][0] = +(m[1][1] * m[2][2] - m[2][1] * m[1][2]) * ood;
-    inv[1][0] = -(m[1][0] * m[2][2] - m[2][0] * m[1][2]) * ood;
-    inv[2][0] = +(m[1][0] * m[2][1] - m[2][0] * m[1][1]) * ood;
-    inv[0][1] = -(m[0][1] * m[2][2] - m[2][1] * m[0][2]) * ood;
-    inv[1][1] = +(m[0][0] * m[2][2] - m[2][0] * m[0][2]) * ood;
-    inv[2][1] = -(m[0][0] * m[2][1] - m[2][0] * m[0][1]) * ood;
-    inv[0][2] = +(m[0][1] * m[1][2] - m[1][1] * m[0][2]) * ood;
-    inv[1][2] = -(m[0][0] * m[1][2] - m[1][0] * m[0][2]) * ood;
-    inv[2][2] = +(m[0][0] * m[1][1] - m[1][0] * m[0][1]) * ood;
+    inv[0][0] = +c0 * ood;
+    inv[1][0] = -(MINOR(m[1][0], m[2][2], m[2][0], m[1][2]) * ood);
+    inv[2][0] = +MINOR(m[1][0], m[2][1], m[2][0], m[1][1]) * ood;
+    inv[0][1] = -(c1 * ood);
+    inv[1][1] = +MINOR(m[0][0], m[2][2], m[2][0], m[0][2]) * ood;
+    inv[2][1] = -(MINOR(m[0][0], m[2][1], m[2][0], m[0][1]) * ood);
+    inv[0][2] = +c2 * ood;
+    inv[1][2] = -(MINOR(m[0][0], m[1][2], m[1][0], m[0][2]) * ood);
+    inv[2][2] = +MINOR(m[0][0], m[1][1], m[1][0], m[0][1]) * ood;
+#undef MINOR
     for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) Bi[r * 3 + c] = inv[c][r];
     *V0 = fabsf(det) / 6.0f;
@@ -581,7 +586,7 @@ static void aisi_cols(const float *Bi, float cols[4][3])
 {
     for (int r = 0; r < 3; r++) {
         float m0 = Bi[0 * 3 + r], m1 = Bi[1 * 3 + r], m2 = Bi[2 * 3 + r]; /* M[k][r] = DmInv row k, comp r */
-        cols[0][r] = m0 * -1.0f + m1 * -1.0f + m2 * -1.0f;
+        cols[0][r] = (-m0 - m1) - m2;   /* FADD(-a,-b); FADD(-c, .) in the computeSiTSi SASS */
         cols[1][r] = m0; cols[2][r] = m1; cols[3][r] = m2;
     }
 }
@@ -597,7 +602,7 @@ static void prepare(o_scene *s, const o_params *p)
         aisi_cols(s->DmInv + 9 * t, cols);
         float coef = s->V0[t] * s->mu[t];
         for (int i = 0; i < 4; i++) {
-            float kii = cols[i][0] * cols[i][0] + cols[i][1] * cols[i][1] + cols[i][2] * cols[i][2];
+            float kii = DOT3_NV(cols[i][0], cols[i][0], cols[i][1], cols[i][1], cols[i][2], cols[i][2]);
             s->matrix_diag[s->Tet[4 * t + i]] += kii * coef;
         }
     }
@@ -795,9 +800,9 @@ static void fixed_bodies(o_scene *s, float muT, float muN)
             /* n = (I - a a^T) rel, as a matrix-vector product (fixedBodyData.cu:117-119) */
             float nn[3];
             for (int k = 0; k < 3; k++) {
-                float m0 = (k == 0 ? 1.0f : 0.0f) - ax[0] * ax[k];
-                float m1 = (k == 1 ? 1.0f : 0.0f) - ax[1] * ax[k];
-                float m2 = (k == 2 ? 1.0f : 0.0f) - ax[2] * ax[k];
+                float m0 = fmaf(-ax[0], ax[k], k == 0 ? 1.0f : 0.0f);   /* FFMA(-a, a, 1|0) in the SASS */
+                float m1 = fmaf(-ax[1], ax[k], k == 1 ? 1.0f : 0.0f);
+                float m2 = fmaf(-ax[2], ax[k], k == 2 ? 1.0f : 0.0f);
                 nn[k] = DOT3_NV(m0, rel[0], m1, rel[1], m2, rel[2]);
             }
             float d = len3(nn);

@@ -38,7 +38,7 @@ if __name__ == "__main__":
             kw = dict(dt=p["dt"], gravity=p["gravity"], rho=p["rho"], muN=p["muN"], muT=p["muT"], num_iterations=p["num_iterations"])
             refA = ref.RefScene(a["X"], a["Tet"], a["mass"], a["mu"], planes=planes, spheres=spheres, cylinders=cyls)
             refB = ref.RefScene(a["X"], a["Tet"], a["mass"], a["mu"], planes=planes, spheres=spheres, cylinders=cyls)
-            e0 = pd.PdSolver(sc, rot_mode=0); e1 = pd.PdSolver(sc, rot_mode=1)
+            e0 = pd.PdSolver(sc, rot_mode=0); e1 = pd.PdSolver(sc, rot_mode=1, reorder=0)   # eng1 = faithful mode: reference SVD, input tet order
             osc, _ = meshes.oracle_scene(O, assets, ctx)
             osc64 = meshes.oracle_scene(O, assets, ctx)[0] if with_f64 else None
             op = O.make_params(dt=p["dt"], gravity=p["gravity"], muN=p["muN"], muT=p["muT"], rho=p["rho"],

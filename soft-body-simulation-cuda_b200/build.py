@@ -15,7 +15,7 @@ HOSTCXX = os.environ.get("PD_HOSTCXX", "/usr/bin/g++")
 
 SOURCES = ["scene.cpp", "layout.cpp", "pd_engine.cu", "c_api.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-std=c++17", "-O3", "-lineinfo", "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall"]
+COMMON = ["-std=c++17", "-O3", "-lineinfo", "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-ffp-contract=off,-mfma,-Wall"]
 
 
 def _newest_src():

@@ -58,20 +58,24 @@ void rest_shape(const float* X, const uint32_t* Tet, int nT, float* DmInv, float
         const float *x0 = X + 3 * (size_t)tv[0], *x1 = X + 3 * (size_t)tv[1], *x2 = X + 3 * (size_t)tv[2], *x3 = X + 3 * (size_t)tv[3];
         float m[3][3];   // m[c][r], column c = x_{c+1} - x_0  (glm layout)
         for (int r = 0; r < 3; ++r) { m[0][r] = x1[r] - x0[r]; m[1][r] = x2[r] - x0[r]; m[2][r] = x3[r] - x0[r]; }
-        const float det = +m[0][0] * (m[1][1] * m[2][2] - m[2][1] * m[1][2])
-                          - m[1][0] * (m[0][1] * m[2][2] - m[2][1] * m[0][2])
-                          + m[2][0] * (m[0][1] * m[1][2] - m[1][1] * m[0][2]);
+        // glm::inverse / glm::determinant with the fused operations nvcc gives the reference's
+        // computeInvDmV0 on sm_100a: minors as fma(a, b, -(c*d)), det = fma(m20, C2, fma(m00, C0, -(m10*C1)))
+        auto minor = [](float a, float b, float c, float d) { return std::fma(a, b, -(c * d)); };
+        const float c0 = minor(m[1][1], m[2][2], m[2][1], m[1][2]);
+        const float c1 = minor(m[0][1], m[2][2], m[2][1], m[0][2]);
+        const float c2 = minor(m[0][1], m[1][2], m[1][1], m[0][2]);
+        const float det = std::fma(m[2][0], c2, std::fma(m[0][0], c0, -(m[1][0] * c1)));
         const float ood = 1.0f / det;
         float inv[3][3];
-        inv[0][0] = +(m[1][1] * m[2][2] - m[2][1] * m[1][2]) * ood;
-        inv[1][0] = -(m[1][0] * m[2][2] - m[2][0] * m[1][2]) * ood;
-        inv[2][0] = +(m[1][0] * m[2][1] - m[2][0] * m[1][1]) * ood;
-        inv[0][1] = -(m[0][1] * m[2][2] - m[2][1] * m[0][2]) * ood;
-        inv[1][1] = +(m[0][0] * m[2][2] - m[2][0] * m[0][2]) * ood;
-        inv[2][1] = -(m[0][0] * m[2][1] - m[2][0] * m[0][1]) * ood;
-        inv[0][2] = +(m[0][1] * m[1][2] - m[1][1] * m[0][2]) * ood;
-        inv[1][2] = -(m[0][0] * m[1][2] - m[1][0] * m[0][2]) * ood;
-        inv[2][2] = +(m[0][0] * m[1][1] - m[1][0] * m[0][1]) * ood;
+        inv[0][0] = +c0 * ood;
+        inv[1][0] = -(minor(m[1][0], m[2][2], m[2][0], m[1][2]) * ood);
+        inv[2][0] = +minor(m[1][0], m[2][1], m[2][0], m[1][1]) * ood;
+        inv[0][1] = -(c1 * ood);
+        inv[1][1] = +minor(m[0][0], m[2][2], m[2][0], m[0][2]) * ood;
+        inv[2][1] = -(minor(m[0][0], m[2][1], m[2][0], m[0][1]) * ood);
+        inv[0][2] = +c2 * ood;
+        inv[1][2] = -(minor(m[0][0], m[1][2], m[1][0], m[0][2]) * ood);
+        inv[2][2] = +minor(m[0][0], m[1][1], m[1][0], m[0][1]) * ood;
         float* B = DmInv + 9 * (size_t)t;
         for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) B[r * 3 + c] = inv[c][r];
         V0[t] = std::fabs(det) / 6.0f;
@@ -83,7 +87,7 @@ static inline size_t rup(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // tiles + records + slots for a mesh whose vertex ids are final
 static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv, const float* w, Layout& L)
 {
-    L.tileTetStart.clear(); L.tileRecOff.clear(); L.records.clear();
+    L.tileTetStart.clear(); L.tileRecOff.clear(); L.records.clear(); L.tileTab.clear();
     std::vector<int> mark((size_t)nV, -1);
     std::vector<uint32_t> lidx((size_t)nV, 0);
     std::vector<uint32_t> slotBase;
@@ -94,8 +98,9 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
     std::vector<uint32_t> vl;
     L.tileTetStart.push_back(0);
     L.tileRecOff.push_back(0);
+    std::vector<uint32_t> cnt;
     while (t0 < nT) {
-        // greedy tile: up to TILE_T tets and TILE_NLMAX distinct vertices
+        // greedy tile: up to TILE_T tets and TILE_NLMAX distinct vertices ...
         vl.clear();
         int t1 = t0;
         while (t1 < nT && t1 - t0 < TILE_T) {
@@ -111,41 +116,67 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
             ++t1;
         }
         if (t1 == t0) throw std::runtime_error("tile builder: empty tile");
-        const uint32_t nLocal = (uint32_t)vl.size(), nTets = (uint32_t)(t1 - t0);
-        // in-tile incidence count of every touched vertex, then order: count descending, id ascending
-        for (uint32_t l = 0; l < nLocal; ++l) lidx[vl[l]] = 0;
-        for (int t = t0; t < t1; ++t) for (int k = 0; k < 4; ++k) lidx[tet[4 * (size_t)t + k]]++;
-        std::sort(vl.begin(), vl.end(), [&](uint32_t a, uint32_t b) { return lidx[a] != lidx[b] ? lidx[a] > lidx[b] : a < b; });
-        std::vector<uint16_t> deg((size_t)nLocal + 1, 0);
-        for (uint32_t l = 0; l < nLocal; ++l) { deg[l + 1] = (uint16_t)(deg[l] + lidx[vl[l]]); }
+        // ... and at most TILE_ROWSMAX incidence rows: halve the tile until it fits
+        uint32_t nLocal = 0, nTets = 0, nGroups = 0, nRows = 0;
+        uint32_t gRowBase[TILE_NGROUPS], gRows[TILE_NGROUPS];
+        for (;;) {
+            nTets = (uint32_t)(t1 - t0);
+            vl.clear();
+            for (int t = t0; t < t1; ++t) for (int k = 0; k < 4; ++k) {
+                const uint32_t v = tet[4 * (size_t)t + k];
+                if (mark[v] != -2 - tile) { mark[v] = -2 - tile; vl.push_back(v); lidx[v] = 0; }
+                lidx[v]++;
+            }
+            for (uint32_t v : vl) mark[v] = -1;
+            // order: in-tile incidence count descending, id ascending
+            std::sort(vl.begin(), vl.end(), [&](uint32_t a, uint32_t b) { return lidx[a] != lidx[b] ? lidx[a] > lidx[b] : a < b; });
+            nLocal = (uint32_t)vl.size();
+            nGroups = (nLocal + 31u) / 32u;
+            nRows = 0;
+            for (uint32_t g = 0; g < nGroups; ++g) {
+                gRowBase[g] = nRows;
+                gRows[g] = (lidx[vl[32 * g]] + 1u) / 2u;        // the group's first vertex has its largest count
+                nRows += gRows[g];
+            }
+            if (nRows <= (uint32_t)TILE_ROWSMAX || nTets == 1) break;
+            t1 = t0 + (int)(nTets / 2);
+        }
+        if (nRows > (uint32_t)TILE_ROWSMAX) throw std::runtime_error("tile builder: a single tet exceeds the incidence row budget");
+        cnt.assign(nLocal, 0);
+        for (uint32_t l = 0; l < nLocal; ++l) { cnt[l] = lidx[vl[l]]; }
         for (uint32_t l = 0; l < nLocal; ++l) { lidx[vl[l]] = l; vcount[vl[l] + 1]++; }
         L.maxLocal = std::max(L.maxLocal, (int)nLocal);
-        const size_t offI = tile_off_inc(nTets), offIO = tile_off_incoff(nTets), offV = tile_off_vlist(nTets, nLocal),
-                     recBytes = tile_rec_bytes(nTets, nLocal);
+        const size_t offV = tile_off_vlist(nTets), abBytes = tile_ab_bytes(nTets, nLocal), cBytes = 128 * (size_t)nRows;
         const size_t base = L.records.size();
-        L.records.resize(base + recBytes, 0);
+        L.records.resize(base + abBytes + cBytes, 0);
         uint8_t* rec = L.records.data() + base;
-        TileHeader h{nTets, nLocal, slot, (uint32_t)recBytes};
-        std::memcpy(rec, &h, 16);
-        std::memcpy(rec + offV, vl.data(), 4 * (size_t)nLocal);
-        uint16_t* incOff = reinterpret_cast<uint16_t*>(rec + offIO);
-        uint16_t* inc = reinterpret_cast<uint16_t*>(rec + offI);
-        std::memcpy(incOff, deg.data(), 2 * ((size_t)nLocal + 1));
-        std::vector<uint16_t> fill(deg.begin(), deg.end() - 1);
+        TileHeader h{nTets, nLocal, slot, (uint32_t)abBytes, (uint32_t)cBytes, nGroups, (uint32_t)(base & 0xffffffffu), (uint32_t)((uint64_t)base >> 32)};
+        std::memcpy(rec, &h, 32);
+        uint32_t* gtab = reinterpret_cast<uint32_t*>(rec + 32);
+        for (uint32_t g = 0; g < nGroups; ++g) gtab[g] = gRowBase[g] | (gRows[g] << 16);
+        uint32_t* vlist = reinterpret_cast<uint32_t*>(rec + offV);
+        for (uint32_t l = 0; l < nLocal; ++l) vlist[l] = vl[l];       // owner bits are set once all tiles are known
+        uint16_t* incT = reinterpret_cast<uint16_t*>(rec + abBytes);
+        for (size_t i = 0; i < cBytes / 2; ++i) incT[i] = (uint16_t)TILE_ZERO_OFF;
+        std::vector<uint32_t> fill(nLocal, 0);
         for (uint32_t tl = 0; tl < nTets; ++tl) {
             const size_t t = (size_t)t0 + tl;
-            float* tr = reinterpret_cast<float*>(rec + 16 + 48 * (size_t)tl);
+            float* tr = reinterpret_cast<float*>(rec + TILE_OFF_TETS + 48 * (size_t)tl);
             for (int e = 0; e < 9; ++e) tr[e] = DmInv[9 * t + e];
             tr[9] = w[t];
             uint32_t c[4];
             for (int k = 0; k < 4; ++k) {
-                c[k] = lidx[tet[4 * t + k]];
-                inc[fill[c[k]]++] = (uint16_t)(k * TILE_HSTRIDE + tl * 16);
+                const uint32_t l = lidx[tet[4 * t + k]];
+                c[k] = l;
+                const uint32_t e = fill[l]++, g = l / 32u, lane = l % 32u;
+                // row (gRowBase[g] + e/2), lane, half e%2
+                incT[((size_t)(gRowBase[g] + e / 2u) * 32u + lane) * 2u + (e & 1u)] = (uint16_t)(k * TILE_HSTRIDE + tile_swz(tl) * 16u);
             }
             const uint32_t c01 = (c[0] * 16u) | ((c[1] * 16u) << 16), c23 = (c[2] * 16u) | ((c[3] * 16u) << 16);
             std::memcpy(&tr[10], &c01, 4);
             std::memcpy(&tr[11], &c23, 4);
         }
+        L.tileTab.push_back(TileEntry{(uint64_t)base, (uint32_t)abBytes, (uint32_t)cBytes});
         slotBase.push_back(slot);
         slot += nLocal;
         t0 = t1;
@@ -161,10 +192,14 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
     L.vslot.assign((size_t)slot, 0u);
     std::vector<uint32_t> fillv(vcount.begin(), vcount.end() - 1);
     for (int ti = 0; ti < L.nTiles; ++ti) {
-        const uint8_t* rec = L.records.data() + L.tileRecOff[ti];
-        TileHeader h; std::memcpy(&h, rec, 16);
-        const uint32_t* vlist = reinterpret_cast<const uint32_t*>(rec + tile_off_vlist(h.nTets, h.nLocal));
-        for (uint32_t l = 0; l < h.nLocal; ++l) L.vslot[fillv[vlist[l]]++] = h.slotBase + l;
+        uint8_t* rec = L.records.data() + L.tileRecOff[ti];
+        TileHeader h; std::memcpy(&h, rec, 32);
+        uint32_t* vlist = reinterpret_cast<uint32_t*>(rec + tile_off_vlist(h.nTets));
+        for (uint32_t l = 0; l < h.nLocal; ++l) {
+            const uint32_t v = vlist[l];
+            if (fillv[v] == L.vslotPtr[v]) vlist[l] = v | TILE_OWNER_BIT;     // first slot of the vertex = owner
+            L.vslot[fillv[v]++] = h.slotBase + l;
+        }
     }
 }
 

@@ -8,31 +8,42 @@
 
 namespace pdb200 {
 
-constexpr int TILE_T = 256;      // tets per tile (= threads per CTA of the local kernel)
-constexpr int TILE_NLMAX = 384;  // max distinct vertices per tile (a tile is closed early beyond)
-constexpr int TILE_HSTRIDE = TILE_T * 16;   // bytes between corner planes of the per-tile H scratch
+constexpr int TILE_T = 256;       // tets per tile (= threads per CTA of the local kernel)
+constexpr int TILE_NLMAX = 256;   // max distinct vertices per tile (a tile is closed early beyond); = TILE_T: one vertex per thread
+constexpr int TILE_NGROUPS = TILE_NLMAX / 32;   // tile-local vertices are handled in groups of 32 (one warp)
+constexpr int TILE_ROWSMAX = 56;  // max incidence rows per tile (a tile is shrunk beyond)
+constexpr uint32_t TILE_HSTRIDE = TILE_T * 16;           // bytes between corner planes of the per-tile H scratch
+constexpr uint32_t TILE_ZERO_OFF = 4u * TILE_HSTRIDE;    // byte offset of the all-zero float4 padding entries point at
+constexpr uint32_t TILE_OWNER_BIT = 0x80000000u;         // vlist flag: this slot is the vertex's first (owner) slot
 
-// One packed tile record, moved to shared memory by ONE bulk copy:
-//   +0      TileHeader                                                   16 B
-//   +16     tet records, 48 B each: f32 B[9] (DmInv, row-major), f32 w = |V0|*mu,
-//           u32 c01, u32 c23 -- the four tile-local corner indices * 16 (byte offsets into the
-//           staged vertex array), two u16 per word                       48*nTets
-//   offI    inc  u16[4*nTets]: per tile-local vertex, ascending (tet, corner), each entry the byte
-//           offset corner*TILE_HSTRIDE + tet*16 of that contribution in the H scratch   (pad 16)
-//   offIO   incOff u16[nLocal+1]: tile-local incidence CSR offsets        (pad 16)
-//   offV    vlist u32[nLocal]: global (renumbered) id of each tile-local vertex, ordered by
-//           (in-tile incidence count descending, id ascending) so that the lanes of a warp
-//           walk incidence lists of similar length                        (pad 16)
+// One packed tile record = two parts, each moved to shared memory by ONE
+// bulk copy (TMA).  Part AB (phases A and B of the local kernel, double buffered):
+//   +0    TileHeader                                                          32 B
+//   +32   group table u32[12]: rowBase | nRows << 16 of each 32-vertex group (8 used)  48 B
+//   +80   tet records, 48 B each: f32 B[9] (DmInv, row-major), f32 w = |V0|*mu, u32 c01, u32 c23 --
+//         the four tile-local corner indices * 16 (byte offsets into the staged vertex array)
+//   offV  vlist u32[nLocal]: global (renumbered) vertex id of each tile-local vertex | TILE_OWNER_BIT,
+//         ordered by (in-tile incidence count descending, id ascending)     (pad 16)
+// Part C (phase C, single buffered): the tile-local incidence lists, transposed per group of 32
+// vertices: row r of group g holds, for each of the 32 lanes (vertices), entries 2r and 2r+1 of that
+// vertex's list packed as two u16 in one u32.  An entry is the byte offset of one tet-corner
+// contribution in the H scratch, corner*TILE_HSTRIDE + swz(tet)*16 with swz(t) = t ^ ((t>>3)&7);
+// lists are ascending in (tet, corner) and padded with TILE_ZERO_OFF.  128 B per row.
 struct TileHeader {
-    uint32_t nTets, nLocal, slotBase, recBytes;
+    uint32_t nTets, nLocal, slotBase, abBytes, cBytes, nGroups, offLo, offHi;   // off = this record's byte offset in the stream
+};
+struct TileEntry {   // per-tile entry of the device tile table
+    uint64_t off;    // byte offset of part AB in the record stream (part C follows at off + abBytes)
+    uint32_t abBytes, cBytes;
 };
 inline uint32_t rup16(uint32_t x) { return (x + 15u) & ~15u; }
-inline uint32_t tile_off_inc(uint32_t nTets) { return 16u + 48u * nTets; }
-inline uint32_t tile_off_incoff(uint32_t nTets) { return tile_off_inc(nTets) + rup16(8u * nTets); }
-inline uint32_t tile_off_vlist(uint32_t nTets, uint32_t nLocal) { return tile_off_incoff(nTets) + rup16(2u * (nLocal + 1u)); }
-inline uint32_t tile_rec_bytes(uint32_t nTets, uint32_t nLocal) { return tile_off_vlist(nTets, nLocal) + rup16(4u * nLocal); }
-// largest possible record, rounded to 128 B: the size of one TMA landing buffer
-constexpr uint32_t TILE_RECMAX = ((16u + 48u * TILE_T + 8u * TILE_T + ((2u * (TILE_NLMAX + 1u) + 15u) & ~15u) + 4u * TILE_NLMAX) + 127u) & ~127u;
+constexpr uint32_t TILE_OFF_TETS = 80u;
+inline uint32_t tile_off_vlist(uint32_t nTets) { return TILE_OFF_TETS + 48u * nTets; }
+inline uint32_t tile_ab_bytes(uint32_t nTets, uint32_t nLocal) { return tile_off_vlist(nTets) + rup16(4u * nLocal); }
+inline uint32_t tile_swz(uint32_t t) { return t ^ ((t >> 3) & 7u); }
+// TMA landing buffers (multiples of 128 B)
+constexpr uint32_t TILE_ABMAX = ((TILE_OFF_TETS + 48u * TILE_T + 4u * TILE_NLMAX) + 127u) & ~127u;
+constexpr uint32_t TILE_CMAX = 128u * TILE_ROWSMAX;
 
 struct Layout {
     int nV = 0, nT = 0;
@@ -45,6 +56,7 @@ struct Layout {
     int nTiles = 0;
     std::vector<uint32_t> tileTetStart; // nTiles+1, into the reordered tet list
     std::vector<uint64_t> tileRecOff;   // nTiles+1, byte offsets into `records` (16-B aligned)
+    std::vector<TileEntry> tileTab;     // nTiles, what the local kernel's producer thread reads
     std::vector<uint8_t> records;       // packed tile records
     // partial-sum slots: slot = slotBase[tile] + localVertex
     uint32_t nSlots = 0;

@@ -23,12 +23,12 @@ namespace pdb200 {
 struct Engine::Impl {
     // tile stream
     uint8_t* records = nullptr;
-    unsigned long long* recOff = nullptr;
+    uint4* tileTab = nullptr;         // per tile: record offset (lo, hi), part AB bytes, part C bytes
     uint32_t *vslotPtr = nullptr, *vslot = nullptr;
     float4* P = nullptr;             // one partial RHS sum per (tile, tile-local vertex) slot
     // per-vertex state (renumbered, padded float4)
     float4* q[3] = {nullptr, nullptr, nullptr};
-    float4 *so4 = nullptr, *X = nullptr, *V = nullptr, *XT = nullptr, *X0 = nullptr;
+    float4 *b0 = nullptr, *X = nullptr, *V = nullptr, *XT = nullptr, *X0 = nullptr;
     float2* cc = nullptr;
     float *mass = nullptr, *dbc = nullptr, *md = nullptr;
     uint32_t* oldOfNew = nullptr;
@@ -77,12 +77,12 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     // ---- device buffers
     Impl& d = *d_;
     d.records = dalloc<uint8_t>(L_.records.size());
-    d.recOff = dalloc<unsigned long long>(L_.tileRecOff.size());
+    d.tileTab = dalloc<uint4>(L_.tileTab.size());
     d.vslotPtr = dalloc<uint32_t>(L_.vslotPtr.size());
     d.vslot = dalloc<uint32_t>(L_.vslot.size());
     d.P = dalloc<float4>((size_t)L_.nSlots);
     for (int k = 0; k < 3; ++k) d.q[k] = dalloc<float4>(nV_);
-    d.so4 = dalloc<float4>(nV_); d.X = dalloc<float4>(nV_); d.V = dalloc<float4>(nV_);
+    d.b0 = dalloc<float4>(nV_); d.X = dalloc<float4>(nV_); d.V = dalloc<float4>(nV_);
     d.XT = dalloc<float4>(nV_); d.X0 = dalloc<float4>(nV_);
     d.cc = dalloc<float2>(nV_);
     d.mass = dalloc<float>(nV_); d.dbc = dalloc<float>(nV_); d.md = dalloc<float>(nV_);
@@ -90,8 +90,8 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     d.stage3 = dalloc<float>(9 * (size_t)nV_);
 
     CUDA_CHECK(cudaMemcpy(d.records, L_.records.data(), L_.records.size(), cudaMemcpyHostToDevice));
-    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
-    CUDA_CHECK(cudaMemcpy(d.recOff, L_.tileRecOff.data(), L_.tileRecOff.size() * 8, cudaMemcpyHostToDevice));
+    static_assert(sizeof(TileEntry) == sizeof(uint4), "tile table entry layout");
+    CUDA_CHECK(cudaMemcpy(d.tileTab, L_.tileTab.data(), L_.tileTab.size() * sizeof(TileEntry), cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(d.vslotPtr, L_.vslotPtr.data(), L_.vslotPtr.size() * 4, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(d.vslot, L_.vslot.data(), L_.vslot.size() * 4, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(d.oldOfNew, L_.vertOrder.data(), (size_t)nV_ * 4, cudaMemcpyHostToDevice));
@@ -195,19 +195,20 @@ void Engine::prepare()
     d.hostMd.assign((size_t)nV_, 0.f);
     for (int ti = 0; ti < L_.nTiles; ++ti) {
         const uint8_t* rec = L_.records.data() + L_.tileRecOff[ti];
-        TileHeader h; std::memcpy(&h, rec, 16);
-        const uint32_t* vlist = reinterpret_cast<const uint32_t*>(rec + tile_off_vlist(h.nTets, h.nLocal));
+        TileHeader h; std::memcpy(&h, rec, sizeof(h));
+        const uint32_t* vlist = reinterpret_cast<const uint32_t*>(rec + tile_off_vlist(h.nTets));
         for (uint32_t t = 0; t < h.nTets; ++t) {
-            const float* B = reinterpret_cast<const float*>(rec + 16 + 48 * (size_t)t);
+            const float* B = reinterpret_cast<const float*>(rec + TILE_OFF_TETS + 48 * (size_t)t);
             const float w = B[9];
             uint32_t cw[2]; std::memcpy(cw, B + 10, 8);
             const uint32_t loc[4] = {(cw[0] & 0xffffu) >> 4, cw[0] >> 20, (cw[1] & 0xffffu) >> 4, cw[1] >> 20};
             for (int i = 0; i < 4; ++i) {
                 float col[3];
                 for (int r = 0; r < 3; ++r)
-                    col[r] = (i == 0) ? (B[0 * 3 + r] * -1.0f + B[1 * 3 + r] * -1.0f + B[2 * 3 + r] * -1.0f) : B[(i - 1) * 3 + r];
-                const float kii = col[0] * col[0] + col[1] * col[1] + col[2] * col[2];
-                d.hostMd[vlist[loc[i]]] += kii * w;
+                    col[r] = (i == 0) ? ((-B[0 * 3 + r] - B[1 * 3 + r]) - B[2 * 3 + r]) : B[(i - 1) * 3 + r];
+                // computeSiTSi as nvcc fuses it: fma(c2,c2, fma(c0,c0, c1*c1)), then * (V0*mu)
+                const float kii = std::fma(col[2], col[2], std::fma(col[0], col[0], col[1] * col[1]));
+                d.hostMd[vlist[loc[i]] & ~TILE_OWNER_BIT] += kii * w;
             }
         }
     }
@@ -230,8 +231,8 @@ void Engine::enqueueStep(bool timed)
     size_t ev = 0;
     auto rec = [&]() { if (timed) CUDA_CHECK(cudaEventRecord(d.events[ev++], stream_)); };
 
-    k_predict<<<vg, vb, 0, stream_>>>(nV_, d.X, d.V, d.mass, d.dbc, d.md, d.X0, dt, dt2Prepared_, p.gravity,
-                                      d.q[0], d.q[2], d.so4, d.cc);
+    k_predict<<<vg, vb, 0, stream_>>>(nV_, d.X, d.V, d.mass, d.dbc, d.md, dt, dt2Prepared_, p.gravity,
+                                      d.q[0], d.q[2], d.b0, d.cc);
     float omega = 1.0f;
     for (int i = 0; i < p.numIterations; ++i) {
         const float4* cur = d.q[i % 3];
@@ -239,15 +240,15 @@ void Engine::enqueueStep(bool timed)
         float4* next = d.q[(i + 1) % 3];
         rec();
         if (opt_.rotMode == 0)
-            k_local<0, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.recOff, L_.nTiles, cur, d.P);
+            k_local<0, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, cur, d.b0, d.P);
         else
-            k_local<1, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.recOff, L_.nTiles, cur, d.P);
+            k_local<1, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, cur, d.b0, d.P);
         rec();
         // omega recurrence in float, pdSolver.cu:196-198
         if (i <= 10) omega = 1;
         else if (i == 11) omega = 2 / (2 - p.rho * p.rho);
         else omega = 4 / (4 - p.rho * p.rho * omega);
-        k_vertex_jacobi<<<vg, vb, 0, stream_>>>(nV_, cur, prev, next, d.so4, d.cc, d.vslotPtr, d.vslot, d.P, omega, wdbc);
+        k_vertex_jacobi<<<vg, vb, 0, stream_>>>(nV_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega, wdbc);
         rec();
     }
     rec();
@@ -406,9 +407,9 @@ float Engine::timeLocalKernelMs(int reps)
     CUDA_CHECK(cudaEventRecord(a, stream_));
     for (int r = 0; r < reps; ++r) {
         if (opt_.rotMode == 0)
-            k_local<0, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.recOff, L_.nTiles, d.XT, d.P);
+            k_local<0, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.XT, d.b0, d.P);
         else
-            k_local<1, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.recOff, L_.nTiles, d.XT, d.P);
+            k_local<1, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.XT, d.b0, d.P);
     }
     CUDA_CHECK(cudaEventRecord(b, stream_));
     CUDA_CHECK(cudaEventSynchronize(b));
@@ -427,12 +428,12 @@ float Engine::timeVertexKernelMs(int reps)
     cudaEvent_t a, b;
     CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
     // a valid so4/cc is needed: run the predictor once
-    k_predict<<<vg, vb, 0, stream_>>>(nV_, d.X, d.V, d.mass, d.dbc, d.md, d.X0, params_.dt, dt2Prepared_, params_.gravity,
-                                      d.q[0], d.q[2], d.so4, d.cc);
+    k_predict<<<vg, vb, 0, stream_>>>(nV_, d.X, d.V, d.mass, d.dbc, d.md, params_.dt, dt2Prepared_, params_.gravity,
+                                      d.q[0], d.q[2], d.b0, d.cc);
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     CUDA_CHECK(cudaEventRecord(a, stream_));
     for (int r = 0; r < reps; ++r)
-        k_vertex_jacobi<<<vg, vb, 0, stream_>>>(nV_, d.q[0], d.q[2], d.q[1], d.so4, d.cc, d.vslotPtr, d.vslot, d.P, 1.0f, 1.0f);
+        k_vertex_jacobi<<<vg, vb, 0, stream_>>>(nV_, d.q[0], d.q[2], d.q[1], d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, 1.0f, 1.0f);
     CUDA_CHECK(cudaEventRecord(b, stream_));
     CUDA_CHECK(cudaEventSynchronize(b));
     float ms = 0;

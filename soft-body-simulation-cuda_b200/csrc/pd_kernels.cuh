@@ -47,119 +47,195 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// L2 cache policies (the encodings CUTLASS uses for createpolicy.fractional.L2::evict_*): the tile
+// stream is read once per iteration and is far larger than L2 -> evict_first; the per-vertex arrays the
+// gathers hit (positions, b0) are re-read every iteration and fit in L2 -> evict_last.
+constexpr unsigned long long L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, unsigned long long policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+// 16-byte asynchronous gather global -> shared (LDGSTS), no register staging
+__device__ __forceinline__ void cp_async16_hint(void* dst, const void* src, unsigned long long policy)
+{
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ float4 ldg_hint(const float4* p, unsigned long long policy)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
+
 // ------------------------------------------------------------------ predictor
-// gravity transform + setMDt_2MoreDBC + computeSn + the two D2D copies
-// (pdSolver.cu:154-160, pdUtil.cu:56-95).  moreDBC == 0 (no mouse drag on the headless path).
-// Writes q0 = prev = s, so4 = (s | DBCX, dbcFlag), cc = (c, c + matrix_diag).
+// gravity transform + setMDt_2MoreDBC + computeSn + the two D2D copies + addM_h2Sn
+// (pdSolver.cu:154-160, pdUtil.cu:56-95,168-179).  moreDBC == 0 (no mouse drag on the headless path).
+// Writes q0 = prev = s, b0 = c * s_old (what addM_h2Sn recomputes every iteration; constant over
+// a step), cc = (+-c, c + matrix_diag) with a NEGATIVE c marking a pinned (DBC) vertex.
+// Arithmetic forms follow the reference's SASS: s = fma(f, 1/c, fma(v, dt, x)).
 __global__ void k_predict(int nV, const float4* __restrict__ X, const float4* __restrict__ V,
                           const float* __restrict__ mass, const float* __restrict__ dbc,
-                          const float* __restrict__ md, const float4* __restrict__ X0,
-                          float dt, float dt2Prepared, float gravity,
-                          float4* __restrict__ q0, float4* __restrict__ qprev, float4* __restrict__ so4,
+                          const float* __restrict__ md, float dt, float dt2Prepared, float gravity,
+                          float4* __restrict__ q0, float4* __restrict__ qprev, float4* __restrict__ b0,
                           float2* __restrict__ cc)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nV) return;
     const float m = mass[v], isDbc = dbc[v];
-    const float dt2 = dt * dt;
+    const float dt2 = __fmul_rn(dt, dt);
     // DBC vertices keep the massDt_2s computed by setMDt_2 at prepare time (pdUtil.cu:48,59)
-    const float c = (isDbc == 0.f) ? m / dt2 : (m + isDbc * 1e6f) / dt2Prepared;
+    const float c = (isDbc == 0.f) ? __fdiv_rn(m, dt2) : __fdiv_rn(__fadd_rn(m, __fmul_rn(isDbc, 1e6f)), dt2Prepared);
     const float4 x = X[v], vel = V[v];
-    const float fy = -gravity * m;
-    const float dt2_m_1 = 1.0f / c;
+    const float fy = __fmul_rn(-gravity, m);
+    const float dt2_m_1 = __fdiv_rn(1.0f, c);
     float4 s;
-    s.x = x.x + dt * vel.x + dt2_m_1 * 0.0f;
-    s.y = x.y + dt * vel.y + dt2_m_1 * fy;
-    s.z = x.z + dt * vel.z + dt2_m_1 * 0.0f;
+    s.x = __fmaf_rn(0.0f, dt2_m_1, __fmaf_rn(vel.x, dt, x.x));
+    s.y = __fmaf_rn(fy, dt2_m_1, __fmaf_rn(vel.y, dt, x.y));
+    s.z = __fmaf_rn(0.0f, dt2_m_1, __fmaf_rn(vel.z, dt, x.z));
     s.w = 0.f;
     q0[v] = s;
     qprev[v] = s;
-    float4 so = s;
-    if (isDbc > 0.f) { const float4 d = X0[v]; so = make_float4(d.x, d.y, d.z, 1.0f); }   // DBCX = X0 (pdSolver.cu:134)
-    so4[v] = so;
-    cc[v] = make_float2(c, c + md[v]);
+    b0[v] = make_float4(__fmul_rn(c, s.x), __fmul_rn(c, s.y), __fmul_rn(c, s.z), 0.f);
+    cc[v] = make_float2(isDbc > 0.f ? -c : c, __fadd_rn(c, md[v]));
 }
 
 // ------------------------------------------------------------------ local step (the hot kernel)
-// PdUtil::computeLocal (pdUtil.cu:97-145) for one tile of <= TILE_T tets per CTA iteration:
-//   0. ONE bulk asynchronous copy (TMA, cp.async.bulk + mbarrier) lands the packed tile record in
-//      shared memory, double buffered: tile i+1 streams in while tile i is computed;
-//   A. the tile's distinct vertex positions are gathered once into shared memory;
+// PdUtil::addM_h2Sn + computeLocal (pdUtil.cu:97-145,168-179), one tile of <= TILE_T tets per
+// iteration of a persistent CTA (4 CTAs per SM).  Per tile:
+//   0. two bulk asynchronous copies (TMA, cp.async.bulk + mbarrier, L2 evict_first) land the packed
+//      tile record in shared memory: part AB (tet records, vertex list; double buffered, fetched two
+//      tiles ahead) and part C (transposed incidence rows; fetched while phase B runs);
+//   A. the tile's distinct vertex positions are gathered into shared memory by 16-byte cp.async
+//      (LDGSTS), issued one tile ahead so that the gather latency hides behind phase C of the
+//      previous tile;
 //   B. one tet per thread: 3 x LDS.128 (48-byte record: DmInv, w, corner offsets; the 48-byte
 //      stride is bank-conflict free), 4 x LDS.128 positions, F = Ds*DmInv, rotation,
-//      H = w (R - F) DmInv^T G (or w R DmInv^T G), 4 x STS.128 into the H scratch;
-//   C. one tile-local vertex per thread: ordered sum over the vertex's incidence list (entries are
-//      ready-made byte offsets into the H scratch) -> ONE partial sum per (tile, vertex) slot.
+//      H = w (R - F) DmInv^T G (or w R DmInv^T G), 4 x STS.128 into the (swizzled) H scratch;
+//   C. (deferred until the next tile's gather is in flight) one tile-local vertex per thread, 32
+//      vertices of similar incidence count per warp: ordered sum over the vertex's incidence list
+//      (one conflict-free LDS.32 yields two ready-made byte offsets into the H scratch) -> ONE
+//      partial sum per (tile, vertex) slot.  The vertex's first (owner) slot starts from
+//      b0 = (M/h^2) s_old, so a vertex whose tets all sit in one tile gets exactly the reference's
+//      sequential  b = c*s; b += h1; b += h2; ...  (tet order).
 // No atomics anywhere: the reference's 12 float atomicAdds per tet become ordered sums, so results
 // are run-to-run bit-identical.  Two __syncthreads per tile.
 // F and H are written with the fused/rounded operation pattern nvcc gives the reference's glm
 // expressions (see oracle/pd_oracle.c header), so that with ROT_MODE 1 every tet contribution is
 // bit-identical to the reference kernel's.
-constexpr uint32_t LOCAL_OFF_QS = 2u * TILE_RECMAX;
+constexpr uint32_t LOCAL_OFF_C = 2u * TILE_ABMAX;
+constexpr uint32_t LOCAL_OFF_QS = LOCAL_OFF_C + TILE_CMAX;
 constexpr uint32_t LOCAL_OFF_HS = LOCAL_OFF_QS + 16u * TILE_NLMAX;
-constexpr uint32_t LOCAL_OFF_BAR = LOCAL_OFF_HS + 4u * TILE_HSTRIDE;
-constexpr uint32_t LOCAL_SMEM_BYTES = LOCAL_OFF_BAR + 16u;
+constexpr uint32_t LOCAL_OFF_BAR = LOCAL_OFF_HS + TILE_ZERO_OFF + 16u;
+constexpr uint32_t LOCAL_SMEM_BYTES = LOCAL_OFF_BAR + 32u;
+static_assert(4u * (LOCAL_SMEM_BYTES + 1024u) <= 233472u, "4 CTAs of the local kernel must fit one SM's shared memory");
+static_assert(TILE_NLMAX == TILE_T, "one tile-local vertex per thread");
 
 __device__ __forceinline__ float dot3_nv(float a0, float b0, float a1, float b1, float a2, float b2)
 {   // a0*b0 + a1*b1 + a2*b2 as nvcc contracts the reference's glm products
     return __fmaf_rn(a2, b2, __fmaf_rn(a0, b0, __fmul_rn(a1, b1)));
 }
 
+// phase C of one tile: `ve` = this thread's vlist entry (0xffffffff if it has no vertex), gt = this
+// warp's group-table word, slot0 = the tile's first slot
+__device__ __forceinline__ void local_phase_c(const uint8_t* smem, uint32_t ve, uint32_t gt, uint32_t slot0, int tid,
+                                              const float4* __restrict__ b0, float4* __restrict__ P)
+{
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(smem + LOCAL_OFF_C) + (gt & 0xffffu) * 32u + (tid & 31);
+    const uint32_t nR = gt >> 16;
+    const uint8_t* Hb = smem + LOCAL_OFF_HS;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    if (ve != 0xffffffffu && (ve & TILE_OWNER_BIT)) {
+        const float4 bb = ldg_hint(&b0[ve & ~TILE_OWNER_BIT], L2_EVICT_LAST);
+        sx = bb.x; sy = bb.y; sz = bb.z;
+    }
+    for (uint32_t r = 0; r < nR; ++r) {
+        const uint32_t e2 = row[32u * r];
+        const float4 ha = *reinterpret_cast<const float4*>(Hb + (e2 & 0xffffu));
+        const float4 hb = *reinterpret_cast<const float4*>(Hb + (e2 >> 16));
+        sx = __fadd_rn(sx, ha.x); sy = __fadd_rn(sy, ha.y); sz = __fadd_rn(sz, ha.z);
+        sx = __fadd_rn(sx, hb.x); sy = __fadd_rn(sy, hb.y); sz = __fadd_rn(sz, hb.z);
+    }
+    if (ve != 0xffffffffu) P[slot0 + tid] = make_float4(sx, sy, sz, 0.f);
+}
+
 template <int ROT_MODE, bool JACOBI>
 __global__ void __launch_bounds__(TILE_T, 4)
-k_local(const uint8_t* __restrict__ records, const unsigned long long* __restrict__ recOff, int nTiles,
-        const float4* __restrict__ q, float4* __restrict__ P)
+k_local(const uint8_t* __restrict__ records, const uint4* __restrict__ tileTab, int nTiles,
+        const float4* __restrict__ q, const float4* __restrict__ b0, float4* __restrict__ P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + LOCAL_OFF_BAR);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + LOCAL_OFF_BAR);   // [0],[1]: part AB buffers, [2]: part C
     const int tid = threadIdx.x;
+    const int nIt = ((int)blockIdx.x < nTiles) ? (nTiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    if (nIt == 0) return;
 
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
+        mbar_init(&bar[2], 1);
         fence_barrier_init();
+        *reinterpret_cast<float4*>(smem + LOCAL_OFF_HS + TILE_ZERO_OFF) = make_float4(0.f, 0.f, 0.f, 0.f);
         fence_proxy_async();
     }
     __syncthreads();
 
-    int tile = blockIdx.x;
-    if (tid == 0 && tile < nTiles) {
-        const unsigned long long o = recOff[tile];
-        const uint32_t bytes = (uint32_t)(recOff[tile + 1] - o);
-        mbar_expect_tx(&bar[0], bytes);
-        bulk_g2s(smem, records + o, bytes, &bar[0]);
-    }
-    for (int it = 0; tile < nTiles; tile += gridDim.x, ++it) {
-        const int b = it & 1;
-        mbar_wait(&bar[b], (uint32_t)((it >> 1) & 1));
-
-        const uint8_t* rec = smem + b * TILE_RECMAX;
-        const uint4 hdr = *reinterpret_cast<const uint4*>(rec);      // nTets, nLocal, slotBase, recBytes
-        const uint32_t nTets = hdr.x, nLocal = hdr.y;
-        const uint32_t offI = 16u + 48u * nTets;
-        const uint32_t offIO = offI + ((8u * nTets + 15u) & ~15u);
-        const uint32_t offV = offIO + ((2u * (nLocal + 1u) + 15u) & ~15u);
-
-        // phase A: stage the tile's vertex positions
-        {
-            const uint32_t* vlist = reinterpret_cast<const uint32_t*>(rec + offV);
-            float4* qs = reinterpret_cast<float4*>(smem + LOCAL_OFF_QS);
-            for (uint32_t l = tid; l < nLocal; l += TILE_T) qs[l] = __ldg(&q[vlist[l]]);
+    // producer (thread 0): part AB of tile number k of this CTA -> buffer k & 1
+    auto fetch_ab = [&](int k) {
+        const uint4 te = __ldg(&tileTab[blockIdx.x + k * gridDim.x]);
+        mbar_expect_tx(&bar[k & 1], te.z);
+        bulk_g2s_hint(smem + (k & 1) * TILE_ABMAX, records + (((unsigned long long)te.y << 32) | te.x), te.z, &bar[k & 1], L2_EVICT_FIRST);
+    };
+    // all threads: wait for part AB of tile k, start the asynchronous gather of its vertex positions
+    // (thread l <-> tile-local vertex l); returns this thread's vlist entry
+    auto start_gather = [&](int k) -> uint32_t {
+        mbar_wait(&bar[k & 1], (uint32_t)((k >> 1) & 1));
+        const uint8_t* rec = smem + (k & 1) * TILE_ABMAX;
+        const uint2 h = *reinterpret_cast<const uint2*>(rec);        // nTets, nLocal
+        uint32_t ve = 0xffffffffu;
+        if ((uint32_t)tid < h.y) {
+            ve = *reinterpret_cast<const uint32_t*>(rec + TILE_OFF_TETS + 48u * h.x + 4u * tid);
+            cp_async16_hint(smem + LOCAL_OFF_QS + 16 * tid, &q[ve & ~TILE_OWNER_BIT], L2_EVICT_LAST);
+            if (ve & TILE_OWNER_BIT) prefetch_l2(&b0[ve & ~TILE_OWNER_BIT]);
         }
+        cp_async_commit();
+        return ve;
+    };
+
+    if (tid == 0) {
+        fetch_ab(0);
+        if (nIt > 1) fetch_ab(1);
+    }
+    uint32_t ve = start_gather(0);
+    uint32_t vePrev = 0xffffffffu, gtPrev = 0, slotPrev = 0;
+    // H scratch address of this thread's tet (swizzled so that phase C's gathers spread over banks)
+    float4* const Hst = reinterpret_cast<float4*>(smem + LOCAL_OFF_HS) + (tid ^ ((tid >> 3) & 7));
+
+    for (int it = 0; it < nIt; ++it) {
+        const int b = it & 1;
+        const uint8_t* rec = smem + b * TILE_ABMAX;
+        // deferred phase C of the previous tile: runs while this tile's position gather is in flight
+        if (it > 0) {
+            mbar_wait(&bar[2], (uint32_t)((it - 1) & 1));
+            local_phase_c(smem, vePrev, gtPrev, slotPrev, tid, b0, P);
+        }
+        cp_async_wait_all();
         __syncthreads();   // positions staged; every warp is past phase C of the previous tile
 
-        // the other buffer and the H scratch are free now: stream the next record in
-        const int nextTile = tile + gridDim.x;
-        if (tid == 0 && nextTile < nTiles) {
-            const unsigned long long o = recOff[nextTile];
-            const uint32_t bytes = (uint32_t)(recOff[nextTile + 1] - o);
-            mbar_expect_tx(&bar[b ^ 1], bytes);
-            bulk_g2s(smem + (b ^ 1) * TILE_RECMAX, records + o, bytes, &bar[b ^ 1]);
+        const uint4 hdr = *reinterpret_cast<const uint4*>(rec);      // nTets, nLocal, slotBase, abBytes
+        if (tid == 0) {    // the part C buffer is free now: stream this tile's incidence rows in
+            const uint4 h2 = *reinterpret_cast<const uint4*>(rec + 16);      // cBytes, nGroups, offLo, offHi
+            mbar_expect_tx(&bar[2], h2.x);
+            bulk_g2s_hint(smem + LOCAL_OFF_C, records + ((((unsigned long long)h2.w << 32) | h2.z) + hdr.w), h2.x, &bar[2], L2_EVICT_FIRST);
         }
 
         // phase B: one tet per thread
-        if ((uint32_t)tid < nTets) {
-            const float4* tr = reinterpret_cast<const float4*>(rec + 16 + 48 * tid);
+        if ((uint32_t)tid < hdr.x) {
+            const float4* tr = reinterpret_cast<const float4*>(rec + TILE_OFF_TETS + 48 * tid);
             const float4 r0 = tr[0], r1 = tr[1], r2 = tr[2];
             const float B0 = r0.x, B1 = r0.y, B2 = r0.z, B3 = r0.w, B4 = r1.x, B5 = r1.y, B6 = r1.z, B7 = r1.w, B8 = r2.x;
             const float w = r2.y;
@@ -190,89 +266,84 @@ k_local(const uint8_t* __restrict__ records, const unsigned long long* __restric
             h0.y = __fsub_rn(__fsub_rn(-h1.y, h2.y), h3.y);
             h0.z = __fsub_rn(__fsub_rn(-h1.z, h2.z), h3.z);
             h0.w = h1.w = h2.w = h3.w = 0.f;
-            float4* Hs = reinterpret_cast<float4*>(smem + LOCAL_OFF_HS) + tid;
-            Hs[0] = h0; Hs[TILE_T] = h1; Hs[2 * TILE_T] = h2; Hs[3 * TILE_T] = h3;
+            Hst[0] = h0; Hst[TILE_T] = h1; Hst[2 * TILE_T] = h2; Hst[3 * TILE_T] = h3;
         }
-        __syncthreads();   // H scratch complete
+        // context of this tile's (deferred) phase C
+        vePrev = ve;
+        gtPrev = *reinterpret_cast<const uint32_t*>(rec + 32 + 4 * (tid >> 5));
+        slotPrev = hdr.z;
+        __syncthreads();   // H scratch complete; this AB buffer and the staged positions are free
 
-        // phase C: ordered gather per tile-local vertex -> partial-sum slot
-        {
-            const uint16_t* incOff = reinterpret_cast<const uint16_t*>(rec + offIO);
-            const uint16_t* inc = reinterpret_cast<const uint16_t*>(rec + offI);
-            const uint8_t* Hb = smem + LOCAL_OFF_HS;
-            for (uint32_t l = tid; l < nLocal; l += TILE_T) {
-                const uint32_t e0 = incOff[l], e1 = incOff[l + 1];
-                float sx = 0.f, sy = 0.f, sz = 0.f;
-                for (uint32_t e = e0; e < e1; ++e) {
-                    const float4 h = *reinterpret_cast<const float4*>(Hb + inc[e]);
-                    sx += h.x; sy += h.y; sz += h.z;
-                }
-                P[hdr.z + l] = make_float4(sx, sy, sz, 0.f);
-            }
+        if (it + 1 < nIt) {
+            if (tid == 0 && it + 2 < nIt) fetch_ab(it + 2);     // into the buffer just freed
+            ve = start_gather(it + 1);
         }
-        // no barrier here: the next iteration's first barrier (after its phase A, which touches
-        // neither the H scratch nor this record buffer) orders phase C against every later write
     }
+    mbar_wait(&bar[2], (uint32_t)((nIt - 1) & 1));
+    local_phase_c(smem, vePrev, gtPrev, slotPrev, tid, b0, P);
 }
 
 // ------------------------------------------------------------------ global step (Jacobi + Chebyshev)
-// addM_h2Sn + computeDBCLocal + getErrorKern + chebyshevKern fused per vertex
-// (pdUtil.cu:147-179,195-226).  Reads the ordered partial sums of the local step.
+// computeDBCLocal + getErrorKern + chebyshevKern fused per vertex (pdUtil.cu:147-166,195-226).
+// b = ordered sum of the vertex's partial-sum slots (the first one already carries (M/h^2) s_old).
+// Arithmetic forms follow the reference's SASS: next = fma(-c,q,b)/(c+md) + q (IEEE division);
+// under-relaxation as one DFMA (the reference's `0.9 *` literal is a double); Chebyshev as one FFMA.
 __global__ void k_vertex_jacobi(int nV, const float4* __restrict__ qcur, const float4* __restrict__ qprev,
-                                float4* __restrict__ qnext, const float4* __restrict__ so4,
+                                float4* __restrict__ qnext, const float4* __restrict__ X0, const float4* __restrict__ b0,
                                 const float2* __restrict__ cc, const uint32_t* __restrict__ vslotPtr,
                                 const uint32_t* __restrict__ vslot, const float4* __restrict__ P,
                                 float omega, float wdbc)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nV) return;
-    const float4 so = so4[v];
     const float2 c2 = cc[v];
-    const float c = c2.x;
+    const float c = fabsf(c2.x);
     float bx, by, bz;
-    if (so.w > 0.f) {                 // computeDBCLocal overwrites b for pinned vertices
-        bx = so.x * wdbc; by = so.y * wdbc; bz = so.z * wdbc;
+    if (c2.x < 0.f) {                 // computeDBCLocal overwrites b for pinned vertices; DBCX = X0 (pdSolver.cu:134)
+        const float4 d = X0[v];
+        bx = __fmul_rn(d.x, wdbc); by = __fmul_rn(d.y, wdbc); bz = __fmul_rn(d.z, wdbc);
     } else {
-        bx = c * so.x; by = c * so.y; bz = c * so.z;
         const uint32_t e0 = vslotPtr[v], e1 = vslotPtr[v + 1];
-        for (uint32_t e = e0; e < e1; ++e) {
+        const float4 p0 = (e0 < e1) ? __ldg(&P[vslot[e0]]) : b0[v];    // a vertex without tets keeps b = (M/h^2) s_old
+        bx = p0.x; by = p0.y; bz = p0.z;
+        for (uint32_t e = e0 + 1; e < e1; ++e) {
             const float4 p = __ldg(&P[vslot[e]]);
-            bx += p.x; by += p.y; bz += p.z;
+            bx = __fadd_rn(bx, p.x); by = __fadd_rn(by, p.y); bz = __fadd_rn(bz, p.z);
         }
     }
     const float4 q = qcur[v], pr = qprev[v];
     const float den = c2.y;
-    float nx = (bx - c * q.x) / den + q.x;
-    float ny = (by - c * q.y) / den + q.y;
-    float nz = (bz - c * q.z) / den + q.z;
+    float nx = __fadd_rn(__fdiv_rn(__fmaf_rn(-c, q.x, bx), den), q.x);
+    float ny = __fadd_rn(__fdiv_rn(__fmaf_rn(-c, q.y, by), den), q.y);
+    float nz = __fadd_rn(__fdiv_rn(__fmaf_rn(-c, q.z, bz), den), q.z);
     // under-relaxation in double, as the reference's `0.9 *` literal (pdUtil.cu:221)
-    nx = (float)(0.9 * (double)(nx - q.x) + (double)q.x);
-    ny = (float)(0.9 * (double)(ny - q.y) + (double)q.y);
-    nz = (float)(0.9 * (double)(nz - q.z) + (double)q.z);
-    nx = (nx - pr.x) * omega + pr.x;
-    ny = (ny - pr.y) * omega + pr.y;
-    nz = (nz - pr.z) * omega + pr.z;
+    nx = (float)__fma_rn((double)__fsub_rn(nx, q.x), 0.9, (double)q.x);
+    ny = (float)__fma_rn((double)__fsub_rn(ny, q.y), 0.9, (double)q.y);
+    nz = (float)__fma_rn((double)__fsub_rn(nz, q.z), 0.9, (double)q.z);
+    nx = __fmaf_rn(__fsub_rn(nx, pr.x), omega, pr.x);
+    ny = __fmaf_rn(__fsub_rn(ny, pr.y), omega, pr.y);
+    nz = __fmaf_rn(__fsub_rn(nz, pr.z), omega, pr.z);
     qnext[v] = make_float4(nx, ny, nz, 0.f);
 }
 
 // right-hand side for the direct / CG global solves: b = c*s_old + sum of partials (R, not R-F)
-__global__ void k_vertex_rhs(int nV, const float4* __restrict__ so4, const float2* __restrict__ cc,
+__global__ void k_vertex_rhs(int nV, const float4* __restrict__ X0, const float4* __restrict__ b0, const float2* __restrict__ cc,
                              const uint32_t* __restrict__ vslotPtr, const uint32_t* __restrict__ vslot,
                              const float4* __restrict__ P, float wdbc, float4* __restrict__ rhs)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nV) return;
-    const float4 so = so4[v];
-    const float c = cc[v].x;
     float bx, by, bz;
-    if (so.w > 0.f) {
-        bx = so.x * wdbc; by = so.y * wdbc; bz = so.z * wdbc;
+    if (cc[v].x < 0.f) {
+        const float4 d = X0[v];
+        bx = __fmul_rn(d.x, wdbc); by = __fmul_rn(d.y, wdbc); bz = __fmul_rn(d.z, wdbc);
     } else {
-        bx = c * so.x; by = c * so.y; bz = c * so.z;
         const uint32_t e0 = vslotPtr[v], e1 = vslotPtr[v + 1];
-        for (uint32_t e = e0; e < e1; ++e) {
+        const float4 p0 = (e0 < e1) ? __ldg(&P[vslot[e0]]) : b0[v];    // a vertex without tets keeps b = (M/h^2) s_old
+        bx = p0.x; by = p0.y; bz = p0.z;
+        for (uint32_t e = e0 + 1; e < e1; ++e) {
             const float4 p = __ldg(&P[vslot[e]]);
-            bx += p.x; by += p.y; bz += p.z;
+            bx = __fadd_rn(bx, p.x); by = __fadd_rn(by, p.y); bz = __fadd_rn(bz, p.z);
         }
     }
     rhs[v] = make_float4(bx, by, bz, 0.f);
@@ -281,17 +352,21 @@ __global__ void k_vertex_rhs(int nV, const float4* __restrict__ so4, const float
 // ------------------------------------------------------------------ end of step
 // updateVelPos (pdUtil.cu:180-193), X <- XTilde (pdSolver.cu:227), then the three fixed-body
 // kernels of FixedBodyData::HandleCollisions (fixedBodyData.cu:67-148) in their launch order.
-__device__ __forceinline__ void fb_respond(float3& vel, const float3 n, float muT, float muN)
-{
-    const float vn = vel.x * n.x + vel.y * n.y + vel.z * n.z;
-    const float3 vN = make_float3(vn * n.x, vn * n.y, vn * n.z);
-    const float3 vT = make_float3(vel.x - vN.x, vel.y - vN.y, vel.z - vN.z);
-    const float magT = sqrtf(vT.x * vT.x + vT.y * vT.y + vT.z * vT.z);
-    const float magN = sqrtf(vN.x * vN.x + vN.y * vN.y + vN.z * vN.z);
-    const float a = magT == 0.f ? 0.f : fmaxf(1.f - muT * (1.f + muN) * magN / magT, 0.f);
-    vel.x = -muN * vN.x + a * vT.x;
-    vel.y = -muN * vN.y + a * vT.y;
-    vel.z = -muN * vN.z + a * vT.z;
+// Operation forms (which products are fused) follow the SASS nvcc produces for those kernels.
+__device__ __forceinline__ void fb_respond(float3& vel, const float3 n, float kf, float muN)
+{   // kf = (1 + muN) * muT
+    const float vn = dot3_nv(vel.x, n.x, vel.y, n.y, vel.z, n.z);
+    const float3 vN = make_float3(__fmul_rn(vn, n.x), __fmul_rn(vn, n.y), __fmul_rn(vn, n.z));
+    const float3 vT = make_float3(__fsub_rn(vel.x, vN.x), __fsub_rn(vel.y, vN.y), __fsub_rn(vel.z, vN.z));
+    const float magT = __fsqrt_rn(dot3_nv(vT.x, vT.x, vT.y, vT.y, vT.z, vT.z));
+    float a = 0.f;
+    if (magT != 0.f) {
+        const float magN = __fsqrt_rn(dot3_nv(vN.x, vN.x, vN.y, vN.y, vN.z, vN.z));
+        a = fmaxf(__fsub_rn(1.f, __fdiv_rn(__fmul_rn(kf, magN), magT)), 0.f);
+    }
+    vel.x = __fmaf_rn(vT.x, a, -__fmul_rn(vN.x, muN));
+    vel.y = __fmaf_rn(vT.y, a, -__fmul_rn(vN.y, muN));
+    vel.z = __fmaf_rn(vT.z, a, -__fmul_rn(vN.z, muN));
 }
 
 __global__ void k_finish(int nV, const float4* __restrict__ qfinal, float dtInv, float4* __restrict__ X,
@@ -300,48 +375,47 @@ __global__ void k_finish(int nV, const float4* __restrict__ qfinal, float dtInv,
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nV) return;
     const float4 q = qfinal[v], xt = XTilde[v];
-    float3 vel = make_float3((q.x - xt.x) * dtInv, (q.y - xt.y) * dtInv, (q.z - xt.z) * dtInv);
+    float3 vel = make_float3(__fmul_rn(__fsub_rn(q.x, xt.x), dtInv), __fmul_rn(__fsub_rn(q.y, xt.y), dtInv), __fmul_rn(__fsub_rn(q.z, xt.z), dtInv));
     float3 x = make_float3(q.x, q.y, q.z);
     X[v] = make_float4(x.x, x.y, x.z, 0.f);      // X keeps the un-projected position
+    const float kf = __fmul_rn(__fadd_rn(muN, 1.f), muT);
     for (int j = 0; j < fb.nSpheres; ++j) {
         const float* s = fb.spheres + 4 * j;
-        const float3 tc = make_float3(x.x - s[0], x.y - s[1], x.z - s[2]);
-        const float d2 = tc.x * tc.x + tc.y * tc.y + tc.z * tc.z;
-        const float d = sqrtf(d2);
+        const float3 tc = make_float3(__fsub_rn(x.x, s[0]), __fsub_rn(x.y, s[1]), __fsub_rn(x.z, s[2]));
+        const float d = __fsqrt_rn(dot3_nv(tc.x, tc.x, tc.y, tc.y, tc.z, tc.z));
         if (d < s[3]) {
-            const float inv = 1.0f / sqrtf(d2);
-            const float3 n = make_float3(tc.x * inv, tc.y * inv, tc.z * inv);
-            const float push = s[3] - d;
-            x.x += push * n.x; x.y += push * n.y; x.z += push * n.z;
-            fb_respond(vel, n, muT, muN);
+            const float inv = __fdiv_rn(1.0f, d);
+            const float3 n = make_float3(__fmul_rn(tc.x, inv), __fmul_rn(tc.y, inv), __fmul_rn(tc.z, inv));
+            const float push = __fsub_rn(s[3], d);
+            x.x = __fmaf_rn(n.x, push, x.x); x.y = __fmaf_rn(n.y, push, x.y); x.z = __fmaf_rn(n.z, push, x.z);
+            fb_respond(vel, n, kf, muN);
         }
     }
     for (int j = 0; j < fb.nPlanes; ++j) {
         const float* p = fb.planes + 6 * j;
         const float3 up = make_float3(p[3], p[4], p[5]);
-        const float sd = (x.x - p[0]) * up.x + (x.y - p[1]) * up.y + (x.z - p[2]) * up.z;
-        if (sd < 0.f && (vel.x * up.x + vel.y * up.y + vel.z * up.z) < 0.f) {
-            x.x -= sd * up.x; x.y -= sd * up.y; x.z -= sd * up.z;
-            fb_respond(vel, up, muT, muN);
+        const float sd = dot3_nv(__fsub_rn(x.x, p[0]), up.x, __fsub_rn(x.y, p[1]), up.y, __fsub_rn(x.z, p[2]), up.z);
+        if (sd < 0.f && dot3_nv(vel.x, up.x, vel.y, up.y, vel.z, up.z) < 0.f) {
+            x.x = __fmaf_rn(-up.x, sd, x.x); x.y = __fmaf_rn(-up.y, sd, x.y); x.z = __fmaf_rn(-up.z, sd, x.z);
+            fb_respond(vel, up, kf, muN);
         }
     }
     for (int j = 0; j < fb.nCyls; ++j) {
         const float* c = fb.cyls + 7 * j;
         const float3 ax = make_float3(c[3], c[4], c[5]);
-        const float3 rel = make_float3(x.x - c[0], x.y - c[1], x.z - c[2]);
+        const float3 rel = make_float3(__fsub_rn(x.x, c[0]), __fsub_rn(x.y, c[1]), __fsub_rn(x.z, c[2]));
         // n = (I - a a^T) rel as the reference's matrix-vector product
         float3 nn;
-        nn.x = (1.f - ax.x * ax.x) * rel.x + (0.f - ax.y * ax.x) * rel.y + (0.f - ax.z * ax.x) * rel.z;
-        nn.y = (0.f - ax.x * ax.y) * rel.x + (1.f - ax.y * ax.y) * rel.y + (0.f - ax.z * ax.y) * rel.z;
-        nn.z = (0.f - ax.x * ax.z) * rel.x + (0.f - ax.y * ax.z) * rel.y + (1.f - ax.z * ax.z) * rel.z;
-        const float d2 = nn.x * nn.x + nn.y * nn.y + nn.z * nn.z;
-        const float d = sqrtf(d2);
+        nn.x = dot3_nv(__fmaf_rn(-ax.x, ax.x, 1.f), rel.x, __fmaf_rn(-ax.y, ax.x, 0.f), rel.y, __fmaf_rn(-ax.z, ax.x, 0.f), rel.z);
+        nn.y = dot3_nv(__fmaf_rn(-ax.x, ax.y, 0.f), rel.x, __fmaf_rn(-ax.y, ax.y, 1.f), rel.y, __fmaf_rn(-ax.z, ax.y, 0.f), rel.z);
+        nn.z = dot3_nv(__fmaf_rn(-ax.x, ax.z, 0.f), rel.x, __fmaf_rn(-ax.y, ax.z, 0.f), rel.y, __fmaf_rn(-ax.z, ax.z, 1.f), rel.z);
+        const float d = __fsqrt_rn(dot3_nv(nn.x, nn.x, nn.y, nn.y, nn.z, nn.z));
         if (d < c[6]) {
-            const float inv = 1.0f / sqrtf(d2);
-            const float3 n = make_float3(nn.x * inv, nn.y * inv, nn.z * inv);
-            const float push = c[6] - d;
-            x.x += push * n.x; x.y += push * n.y; x.z += push * n.z;
-            fb_respond(vel, n, muT, muN);
+            const float inv = __fdiv_rn(1.0f, d);
+            const float3 n = make_float3(__fmul_rn(nn.x, inv), __fmul_rn(nn.y, inv), __fmul_rn(nn.z, inv));
+            const float push = __fsub_rn(c[6], d);
+            x.x = __fmaf_rn(n.x, push, x.x); x.y = __fmaf_rn(n.y, push, x.y); x.z = __fmaf_rn(n.z, push, x.z);
+            fb_respond(vel, n, kf, muN);
         }
     }
     XTilde[v] = make_float4(x.x, x.y, x.z, 0.f);

@@ -4,8 +4,12 @@ the bit-exact reorder / renumber / tile / incidence / slot checks.  Independent 
 import numpy as np
 
 TILE_T = 256
-TILE_NLMAX = 384
+TILE_NLMAX = 256
+TILE_ROWSMAX = 56
 TILE_HSTRIDE = TILE_T * 16
+TILE_ZERO_OFF = 4 * TILE_HSTRIDE
+TILE_OWNER_BIT = 0x80000000
+TILE_OFF_TETS = 80
 
 
 def spread3(x):
@@ -31,30 +35,14 @@ def morton_keys(X, Tet):
 
 
 def rest_shape(X, Tet):
-    """solverUtil.cuh:98-116 with glm's cofactor inverse, float32, one rounding per op."""
-    X = X.astype(np.float32); T = Tet.astype(np.int64)
-    x0 = X[T[:, 0]]
-    m = [X[T[:, 1]] - x0, X[T[:, 2]] - x0, X[T[:, 3]] - x0]   # m[c][:, r]
-    M = lambda c, r: m[c][:, r]
-    det = (M(0, 0) * (M(1, 1) * M(2, 2) - M(2, 1) * M(1, 2)) - M(1, 0) * (M(0, 1) * M(2, 2) - M(2, 1) * M(0, 2))
-           + M(2, 0) * (M(0, 1) * M(1, 2) - M(1, 1) * M(0, 2)))
-    ood = np.float32(1.0) / det
-    inv = {}
-    inv[0, 0] = +(M(1, 1) * M(2, 2) - M(2, 1) * M(1, 2)) * ood
-    inv[1, 0] = -(M(1, 0) * M(2, 2) - M(2, 0) * M(1, 2)) * ood
-    inv[2, 0] = +(M(1, 0) * M(2, 1) - M(2, 0) * M(1, 1)) * ood
-    inv[0, 1] = -(M(0, 1) * M(2, 2) - M(2, 1) * M(0, 2)) * ood
-    inv[1, 1] = +(M(0, 0) * M(2, 2) - M(2, 0) * M(0, 2)) * ood
-    inv[2, 1] = -(M(0, 0) * M(2, 1) - M(2, 0) * M(0, 1)) * ood
-    inv[0, 2] = +(M(0, 1) * M(1, 2) - M(1, 1) * M(0, 2)) * ood
-    inv[1, 2] = -(M(0, 0) * M(1, 2) - M(1, 0) * M(0, 2)) * ood
-    inv[2, 2] = +(M(0, 0) * M(1, 1) - M(1, 0) * M(0, 1)) * ood
-    B = np.zeros((T.shape[0], 3, 3), np.float32)      # row-major B[r][c] = inv[c][r]
-    for r in range(3):
-        for c in range(3):
-            B[:, r, c] = inv[c, r]
-    V0 = np.abs(det) / np.float32(6.0)
-    return B, V0.astype(np.float32)
+    """solverUtil.cuh:98-116 (glm::inverse, |det|/6) with the fused operations of the reference's nvcc
+    build -- fma() cannot be written in numpy, so the values come from the C oracle's o_rest_shape
+    (oracle/pd_oracle.c:rest_one), which tests pin bit-for-bit against the reference kernel on the GPU."""
+    import oracle as O
+    X = np.ascontiguousarray(X, np.float32); T = np.ascontiguousarray(Tet, np.uint32)
+    B = np.zeros((T.shape[0], 9), np.float32); V0 = np.zeros(T.shape[0], np.float32)
+    O.lib().o_rest_shape(X.reshape(-1), T.reshape(-1), T.shape[0], B.reshape(-1), V0)
+    return B.reshape(-1, 3, 3), V0
 
 
 def rup(x, a):
@@ -82,6 +70,7 @@ def build(X, Tet, mu, reorder=True):
     tile_tet_start = [0]; tile_rec_off = [0]; recs = []; slot = 0
     vslots = [[] for _ in range(nV)]
     t0 = 0; max_local = 0
+    seen_before = np.zeros(nV, bool)            # vertex already has a slot in an earlier tile
     while t0 < nT:
         seen = set(); t1 = t0
         while t1 < nT and t1 - t0 < TILE_T:
@@ -89,43 +78,61 @@ def build(X, Tet, mu, reorder=True):
             if len(seen) + len(new) > TILE_NLMAX:
                 break
             seen.update(new); t1 += 1
-        tl_tets = tet_new[t0:t1].astype(np.int64)
-        nTets = t1 - t0
-        ids, counts = np.unique(tl_tets.reshape(-1), return_counts=True)
-        order = np.lexsort((ids, -counts))                 # in-tile incidence count descending, id ascending
-        vl = ids[order].astype(np.uint32)
-        nLocal = len(vl)
+        while True:                              # shrink until the incidence rows fit
+            nTets = t1 - t0
+            tl_tets = tet_new[t0:t1].astype(np.int64)
+            ids, counts = np.unique(tl_tets.reshape(-1), return_counts=True)
+            order = np.lexsort((ids, -counts))   # in-tile incidence count descending, id ascending
+            vl = ids[order]; cnt = counts[order]
+            nLocal = len(vl); nGroups = (nLocal + 31) // 32
+            g_rows = [(int(cnt[32 * g]) + 1) // 2 for g in range(nGroups)]
+            g_base = np.concatenate([[0], np.cumsum(g_rows)]).astype(np.int64)
+            nRows = int(g_base[-1])
+            if nRows <= TILE_ROWSMAX or nTets == 1:
+                break
+            t1 = t0 + nTets // 2
         max_local = max(max_local, nLocal)
         lidx = np.zeros(nV, np.int64); lidx[vl] = np.arange(nLocal)
-        cidx = lidx[tl_tets]                               # (nTets, 4) tile-local corner indices
-        # 48-byte tet records: B[9], w, c01, c23 (corner index * 16, two u16 per word)
+        cidx = lidx[tl_tets]                     # (nTets, 4) tile-local corner indices
         trec = np.zeros((nTets, 12), np.uint32)
         trec[:, :9] = Br[t0:t1].view(np.uint32)
         trec[:, 9] = wr[t0:t1].view(np.uint32)
         trec[:, 10] = (cidx[:, 0] * 16) | ((cidx[:, 1] * 16) << 16)
         trec[:, 11] = (cidx[:, 2] * 16) | ((cidx[:, 3] * 16) << 16)
-        # incidence lists: per tile-local vertex, ascending (tet, corner); entry = corner*HSTRIDE + tet*16
+        # transposed incidence rows: entry e of local vertex l -> row g_base[l//32] + e//2, lane l%32, half e%2
+        incT = np.full((nRows, 32, 2), TILE_ZERO_OFF, np.uint16)
         owner = cidx.reshape(-1)
         tl = np.repeat(np.arange(nTets), 4); k = np.tile(np.arange(4), nTets)
-        ent = (k * TILE_HSTRIDE + tl * 16).astype(np.uint16)
-        inc = ent[np.argsort(owner, kind="stable")]
-        inc_off = np.zeros(nLocal + 1, np.uint16)
-        inc_off[1:] = np.cumsum(np.bincount(owner, minlength=nLocal)).astype(np.uint16)
-        i_bytes = rup(8 * nTets, 16); io_bytes = rup(2 * (nLocal + 1), 16); v_bytes = rup(4 * nLocal, 16)
-        rec_bytes = 16 + 48 * nTets + i_bytes + io_bytes + v_bytes
+        swz = tl ^ ((tl >> 3) & 7)
+        ent = (k * TILE_HSTRIDE + swz * 16).astype(np.uint16)
+        o = np.argsort(owner, kind="stable")     # per vertex, ascending (tet, corner)
+        ow = owner[o]
+        start = np.concatenate([[0], np.cumsum(np.bincount(owner, minlength=nLocal))])
+        e = np.arange(len(o)) - start[ow]
+        incT[g_base[ow // 32] + e // 2, ow % 32, e % 2] = ent[o]
+        vlist = vl.astype(np.uint32)
+        first = ~seen_before[vl]
+        vlist = np.where(first, vlist | np.uint32(TILE_OWNER_BIT), vlist).astype(np.uint32)
+        seen_before[vl] = True
+        ab_bytes = TILE_OFF_TETS + 48 * nTets + rup(4 * nLocal, 16); c_bytes = 128 * nRows
+        base = tile_rec_off[-1]
+        gtab = np.zeros(12, np.uint32)
+        for g in range(nGroups):
+            gtab[g] = int(g_base[g]) | (g_rows[g] << 16)
         rec = bytearray()
-        rec += np.array([nTets, nLocal, slot, rec_bytes], np.uint32).tobytes()
+        rec += np.array([nTets, nLocal, slot, ab_bytes, c_bytes, nGroups, base & 0xffffffff, base >> 32], np.uint32).tobytes()
+        rec += gtab.tobytes()
         rec += trec.tobytes()
-        rec += inc.tobytes() + b"\0" * (i_bytes - 8 * nTets)
-        rec += inc_off.tobytes() + b"\0" * (io_bytes - 2 * (nLocal + 1))
-        rec += vl.tobytes() + b"\0" * (v_bytes - 4 * nLocal)
-        assert len(rec) == rec_bytes
+        rec += vlist.tobytes() + b"\0" * (rup(4 * nLocal, 16) - 4 * nLocal)
+        assert len(rec) == ab_bytes
+        rec += incT.tobytes()
+        assert len(rec) == ab_bytes + c_bytes
         recs.append(bytes(rec))
         for l, v in enumerate(vl):
             vslots[int(v)].append(slot + l)
         slot += nLocal
         t0 = t1
-        tile_tet_start.append(t0); tile_rec_off.append(tile_rec_off[-1] + rec_bytes)
+        tile_tet_start.append(t0); tile_rec_off.append(base + ab_bytes + c_bytes)
     vslot_ptr = np.zeros(nV + 1, np.uint32)
     vslot_ptr[1:] = np.cumsum([len(s) for s in vslots])
     vslot = np.array([s for ss in vslots for s in ss], np.uint32)

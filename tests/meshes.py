@@ -57,6 +57,8 @@ CONTEXTS = [
     dict(name="C2 armadillo&bunny", precision="float", load=True, dt=0.01, gravity=98, damp=0.999, muN=0.5, muT=0.5, tolerance=1e-2,
          softBodies=[dict(name="armadillo0", pos=[2.0, 80.0, 0.0]), dict(name="bunny", pos=[60.0, 40.0, 0.0])],
          fixedBodies=[dict(name="bottom plane", pos=[0.0, 0.0, 0.0])] + WALLS),
+    dict(name="C2 armadillo", precision="float", load=True, dt=0.01, gravity=98, damp=0.999, muN=0.5, muT=0.5, tolerance=1e-2,
+         softBodies=[dict(name="armadillo0", pos=[2.0, 80.0, 0.0])], fixedBodies=[dict(name="bottom plane", pos=[0.0, 0.0, 0.0])] + WALLS),
     # the shipped float context, all three fixed-body kinds (context.json:120-151), mesh collision off
     dict(name="Armadillo&house", precision="float", load=True, dt=0.01, gravity=98, damp=0.999, muN=0.5, muT=0.5, tolerance=1e-2,
          softBodies=[dict(name="armadillo0", pos=[2.0, 80.0, 0.0]), dict(name="house1", pos=[0.0, 180.0, 0.0], rot=[0.0, 0.0, 75.0]),

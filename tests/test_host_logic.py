@@ -135,7 +135,7 @@ def test_layout_bit_exact_bunny_and_grid(pd, assets):
     X, E, _ = meshes.raw_mesh("bunny")
     sc = pd.Scene.from_arrays(X * np.float32(35), (E[:, 1:5] - 1).astype(np.uint32), 10.0, 2e6)
     L = _check_layout(pd, sc)
-    assert L.num_tiles == -(-8417 // 256) and L.max_local <= 384
+    assert L.num_tiles == -(-8417 // 256) and L.max_local <= 256
     g = pd.Scene.kuhn_grid(7, 6, 5, 1.0, 0.05, 12345, (0, 10, 0), 1.0, 2e5)
     assert g.counts()[:2] == (8 * 7 * 6, 6 * 7 * 6 * 5)
     _check_layout(pd, g)
@@ -151,8 +151,8 @@ def test_layout_invariants(pd, assets):
     for v in range(0, nV, 997):
         s = L.vslot[L.vslot_ptr[v]:L.vslot_ptr[v + 1]]
         assert (np.diff(s.astype(np.int64)) > 0).all() and len(s) >= 1
-    # tiles hold <= 256 tets and <= 384 vertices; Morton order keeps them compact
-    assert np.diff(L.tile_tet_start.astype(np.int64)).max() <= 256 and L.max_local <= 384
+    # tiles hold <= 256 tets and <= 256 vertices; Morton order keeps them compact
+    assert np.diff(L.tile_tet_start.astype(np.int64)).max() <= 256 and L.max_local <= 256
     assert L.num_slots < 1.2 * nT      # ~0.9 slots per tet on armadillo+bunny (compactness regression guard)
 
 
