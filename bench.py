@@ -160,7 +160,7 @@ def run_b200(args):
     sc, p = make_scene(pd, args.workload)
     nV, nT = sc.counts()[:2]
     iters = p["num_iterations"]
-    eng = pd.PdSolver(sc, device=local)
+    eng = pd.PdSolver(sc, device=local, rot_mode=args.rot_mode, ctas_per_sm=args.ctas_per_sm)
     X0 = sc.arrays()["X"]
     V0 = initial_velocity(X0)
     eng.upload(V=V0)
@@ -293,6 +293,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="grid139", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rot-mode", type=int, default=0, help="experiments only: 0 product default, 1 faithful SVD, 2 no projection (timing probe)")
+    ap.add_argument("--ctas-per-sm", type=int, default=0, help="experiments only: cap the local kernel's resident CTAs per SM")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -1,0 +1,159 @@
+/*
+ * b200_pd_solver.h -- the reference-side adapter: `class B200PdSolver : public Solver<float>`.
+ *
+ * Header-only C++17, compiled INSIDE the reference tree (it includes the reference's own
+ * src/def.h and src/simulation/solver/solver.h) and linked against libpd_b200.so through the C ABI
+ * of include/pd_b200.h.  It replaces `PdSolver` at its single construction site
+ *     src/simulation/simulationContext.cu:120   solver = std::make_unique<PdSolver>(threadsPerBlock, data);
+ * and is driven by the unchanged caller
+ *     src/simulation/simulationContext.cpp:86   impl.solver->Update(impl.data, impl.params);
+ * INTEGRATION.md shows the three-line patch.  Same names, argument meaning and error behaviour as
+ * PdSolver (src/simulation/solver/projective/pdSolver.h:12-44): void returns, nothing thrown across
+ * Update(); failures are printed like the reference's CHECK_* macros do (linear.h:16-49) and leave
+ * SolverData untouched.
+ *
+ * Data flow per Update:
+ *   first Update after construction/Reset : D2H of the rest data (X0, Tet, mass, mu, DBC) -> pd_scene_from_desc ->
+ *       pd_create (device layout is built once), DBCX <- X0 like SolverPrepare (pdSolver.cu:134)
+ *   every Update : pd_set_params (CopyUIToParams runs before every Update, simulationContext.cpp:85)
+ *       -> pd_update_device(engine, 1, data.X, data.V, data.XTilde): AoS glm::vec3 import, one PD step, AoS export,
+ *       all on the engine's stream, synchronised on return (the renderer and BVH read data.X next).
+ * The fixed bodies are passed as plain structs; B200_FIXED_BODY_FROM shows how to fill one from a FixedBody*.
+ */
+#pragma once
+
+#include <cstdio>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include <def.h>                          /* SolverData, SolverParams, indexType  (src/def.h) */
+#include <simulation/solver/solver.h>     /* template<typename Scalar> class Solver (solver.h:11-28) */
+
+#include "pd_b200.h"
+
+/* Fill a pd_fixed_body from one of the reference's FixedBody subclasses (collision/rigid/*.h):
+ *   B200_FIXED_BODY_FROM(fb, PD_PLANE,    plane->m_model,    0.f)
+ *   B200_FIXED_BODY_FROM(fb, PD_SPHERE,   sphere->m_model,   sphere->m_radius)
+ *   B200_FIXED_BODY_FROM(fb, PD_CYLINDER, cylinder->m_model, cylinder->m_radius)
+ * glm::mat4 is column-major float[16], which is exactly pd_fixed_body::model. */
+#define B200_FIXED_BODY_FROM(out, kind, glm_mat4_model, r)                          \
+    do {                                                                            \
+        (out).type = (kind);                                                        \
+        const float* m__ = &(glm_mat4_model)[0][0];                                 \
+        for (int i__ = 0; i__ < 16; ++i__) (out).model[i__] = m__[i__];             \
+        (out).radius = (r);                                                         \
+    } while (0)
+
+class B200PdSolver : public Solver<float> {
+public:
+    /* PdSolver::SolverType (pdSolver.h:15-18); PCGJacobi is the extra back-end of linear/pcgJacobi.cu */
+    enum class SolverType { Jacobi = PD_JACOBI, CuSolverCholesky = PD_CHOLESKY, EigenCholesky = PD_CHOLESKY, PCGJacobi = PD_PCG_JACOBI };
+
+    /* Same leading arguments as PdSolver(int, const SolverData<float>&) (pdSolver.cu:22-27).  Unlike
+     * FEMSolver's ctor (femSolver.cu:6-17) nothing is allocated inside `solverData`: V0/DmInv live
+     * in the engine's own tile stream; SolverData::V0/DmInv/ExtForce stay null (only the IPC and
+     * explicit solvers read them). */
+    B200PdSolver(int threadsPerBlock, const SolverData<float>& solverData, std::vector<pd_fixed_body> fixedBodies = {},
+                 int device = 0)
+        : Solver<float>(threadsPerBlock), fixed_(std::move(fixedBodies)), device_(device)
+    {
+        (void)solverData;
+        /* the four named counters of pdSolver.cu:26 */
+        performanceData = {{"local step", 0.f}, {"global step", 0.f}, {"collision handling(fixed)", 0.f}, {"collision handling(mesh)", 0.f}};
+    }
+    ~B200PdSolver() override { if (engine_) pd_destroy(engine_); }
+    B200PdSolver(const B200PdSolver&) = delete;
+    B200PdSolver& operator=(const B200PdSolver&) = delete;
+
+    void SetGlobalSolver(SolverType val) { solverType_ = static_cast<int>(val); }
+    /* number of PD iterations per Update; the reference keeps it in SolverParams::numIterations */
+
+    void Update(SolverData<float>& solverData, const SolverParams<float>& solverParams) override
+    {
+        if (!solverReady) {
+            SolverPrepare(solverData, solverParams);
+            if (!engine_) return;                    /* printed already; SolverData untouched */
+            solverReady = true;
+        }
+        SolverStep(solverData, solverParams);
+    }
+
+    void Reset() override
+    {   /* Solver::Reset (solver.h:39-43) + PdSolver::Reset (pdSolver.cu:234-241): SimulationCUDAContext::Reset has
+         * already restored X/XTilde/V from X0 in SolverData; the next Update re-prepares (dt, mu may have changed). */
+        Solver<float>::Reset();
+        for (auto& kv : performanceData) kv.second = 0.f;
+        if (engine_) { pd_destroy(engine_); engine_ = nullptr; }
+    }
+
+protected:
+    void SolverPrepare(SolverData<float>& d, const SolverParams<float>& sp) override
+    {
+        const size_t nV = (size_t)d.numVerts, nT = (size_t)d.numTets;
+        std::vector<float> X(3 * nV), mass(nV), mu(nT), dbc(nV, 0.f);
+        std::vector<uint32_t> tet(4 * nT);
+        static_assert(sizeof(indexType) == sizeof(uint32_t), "indexType is unsigned int (def.h:4)");
+        bool ok = cudaMemcpy(X.data(), d.X0, 12 * nV, cudaMemcpyDeviceToHost) == cudaSuccess;
+        ok = ok && cudaMemcpy(tet.data(), d.Tet, 16 * nT, cudaMemcpyDeviceToHost) == cudaSuccess;
+        ok = ok && cudaMemcpy(mass.data(), d.mass, 4 * nV, cudaMemcpyDeviceToHost) == cudaSuccess;
+        ok = ok && cudaMemcpy(mu.data(), d.mu, 4 * nT, cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (d.DBC) ok = ok && cudaMemcpy(dbc.data(), d.DBC, 4 * nV, cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (d.DBCX) ok = ok && cudaMemcpy(d.DBCX, d.X0, 12 * nV, cudaMemcpyDeviceToDevice) == cudaSuccess;   /* pdSolver.cu:134 */
+        if (!ok) { std::fprintf(stderr, "B200PdSolver: reading SolverData failed: %s\n", cudaGetErrorString(cudaGetLastError())); return; }
+        pd_scene_desc desc{};
+        desc.num_verts = d.numVerts; desc.num_tets = d.numTets;
+        desc.X = X.data(); desc.Tet = tet.data(); desc.mass = mass.data(); desc.mu = mu.data(); desc.DBC = dbc.data();
+        desc.num_fixed = (int)fixed_.size(); desc.fixed = fixed_.data();
+        pd_params p; toParams(sp, &p);
+        pd_scene* scene = pd_scene_from_desc(&desc, &p);
+        if (!scene) { std::fprintf(stderr, "B200PdSolver: %s\n", pd_last_error()); return; }
+        pd_engine_options opt; pd_default_options(&opt);
+        opt.device = device_;
+        engine_ = pd_create(scene, &opt);
+        pd_scene_free(scene);
+        if (!engine_) { std::fprintf(stderr, "B200PdSolver: %s\n", pd_last_error()); return; }
+        pd_set_perf(engine_, perf ? 1 : 0);
+    }
+
+    bool SolverStep(SolverData<float>& d, const SolverParams<float>& sp) override
+    {
+        pd_params p; toParams(sp, &p);
+        if (p.handle_collision) {
+            /* mesh-mesh BVH/CCD stays in the reference (pdSolver.cu:218-225): step with it off, then the
+             * caller's DetectCollision/CCDKernel pair can run on the exported X/XTilde/V. */
+            p.handle_collision = 0;
+        }
+        pd_set_perf(engine_, perf ? 1 : 0);
+        if (pd_set_params(engine_, &p) != PD_OK || pd_update_device(engine_, 1, &d.X[0].x, &d.V[0].x, &d.XTilde[0].x) != PD_OK) {
+            std::fprintf(stderr, "B200PdSolver: %s\n", pd_last_error());
+            return false;
+        }
+        if (perf) {
+            pd_perf pf;
+            if (pd_get_perf(engine_, &pf) == PD_OK) {
+                performanceData[0].second = pf.local_step_ms; performanceData[1].second = pf.global_step_ms;
+                performanceData[2].second = pf.collision_fixed_ms; performanceData[3].second = pf.collision_mesh_ms;
+            }
+        }
+        return true;
+    }
+
+private:
+    void toParams(const SolverParams<float>& sp, pd_params* p) const
+    {
+        pd_default_params(p);
+        p->dt = sp.dt; p->gravity = sp.gravity; p->muN = sp.muN; p->muT = sp.muT; p->rho = sp.rho; p->tol = sp.tol; p->damp = sp.damp;
+        p->num_iterations = (int)sp.numIterations;
+        p->global_solver = solverType_;
+        p->handle_collision = sp.handleCollision ? 1 : 0;
+        p->threads_per_block = threadsPerBlock;
+    }
+
+    std::vector<pd_fixed_body> fixed_;
+    pd_engine* engine_ = nullptr;
+    int solverType_ = PD_JACOBI;
+    int device_ = 0;
+};

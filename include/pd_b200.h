@@ -126,7 +126,7 @@ void pd_layout_free(pd_layout*);
 int pd_layout_counts(const pd_layout*, int* num_tiles, uint32_t* num_slots, size_t* record_bytes, int* max_local);
 int pd_layout_get(const pd_layout*, uint32_t* tet_order, uint32_t* vert_order, uint32_t* tet_new,
                   uint32_t* tile_tet_start, uint64_t* tile_rec_off, uint8_t* records,
-                  uint32_t* vslot_ptr, uint32_t* vslot);
+                  uint32_t* vslot_ptr, uint32_t* vslot, uint32_t* vlist);
 int pd_morton_keys(const float* X, const uint32_t* Tet, int num_tets, uint32_t* keys);
 int pd_partition_vertices(int num_verts, int world, int* vbeg /* world+1 */);
 
@@ -166,6 +166,10 @@ int pd_get_setup(pd_engine*, float* matrix_diag, float* mass_dt2, float* DmInv, 
 /* measurement helpers used by bench.py: average device time (ms) of one launch of the local /
  * vertex kernel over `reps` back-to-back launches, CUDA events on the engine's stream */
 int pd_time_kernels(pd_engine*, int reps, float* local_ms, float* vertex_ms);
+/* measurement helper: clock64 totals per phase of the local kernel, 8 x u64 per CTA (local_grid CTAs):
+ * [loop top + barrier 3, wait part C, phase C, gather wait + barrier 1, wait part AB, record loads + barrier 2,
+ *  phase B math + H stores, tiles processed] */
+int pd_profile_local(pd_engine*, unsigned long long* out);
 int pd_engine_info(const pd_engine*, int* num_verts, int* num_tets, int* num_tiles, uint32_t* num_slots,
                    size_t* tile_stream_bytes, size_t* device_bytes, int* local_grid);
 /* test hook: the corotational projection (pdUtil.cu:112-122) of n row-major 3x3 matrices on

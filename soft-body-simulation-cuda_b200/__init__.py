@@ -84,7 +84,7 @@ SYMBOLS = {
     "pd_layout_build": (_VP, [_VP, _I]),
     "pd_layout_free": (None, [_VP]),
     "pd_layout_counts": (_I, [_VP, _PI, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t), _PI]),
-    "pd_layout_get": (_I, [_VP] * 9),
+    "pd_layout_get": (_I, [_VP] * 10),
     "pd_morton_keys": (_I, [_VP, _VP, _I, _VP]),
     "pd_partition_vertices": (_I, [_I, _I, _VP]),
     "pd_create": (_VP, [_VP, C.POINTER(pd_engine_options)]),
@@ -105,6 +105,7 @@ SYMBOLS = {
     "pd_update_device": (_I, [_VP, _I, _VP, _VP, _VP]),
     "pd_get_setup": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "pd_time_kernels": (_I, [_VP, _I, _PF, _PF]),
+    "pd_profile_local": (_I, [_VP, _VP]),
     "pd_engine_info": (_I, [_VP, _PI, _PI, _PI, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), _PI]),
     "pd_rotation_batch": (_I, [_I, _I, _I, _VP, _VP, _VP]),
     "pd_alloc_pinned": (_VP, [C.c_size_t]),
@@ -268,8 +269,9 @@ class Layout:
         self.tile_rec_off = np.zeros(self.num_tiles + 1, np.uint64)
         self.records = np.zeros(self.record_bytes, np.uint8)
         self.vslot_ptr = np.zeros(nV + 1, np.uint32); self.vslot = np.zeros(self.num_slots, np.uint32)
+        self.vlist = np.zeros(self.num_tiles * 256, np.uint32)      # padded: tile * TILE_NLMAX + local vertex
         _check(lib().pd_layout_get(self._h, _p(self.tet_order), _p(self.vert_order), _p(self.tet_new), _p(self.tile_tet_start),
-                                   _p(self.tile_rec_off), _p(self.records), _p(self.vslot_ptr), _p(self.vslot)))
+                                   _p(self.tile_rec_off), _p(self.records), _p(self.vslot_ptr), _p(self.vslot), _p(self.vlist)))
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:
@@ -361,6 +363,12 @@ class PdSolver:
         a, b = C.c_float(), C.c_float()
         _check(lib().pd_time_kernels(self._h, reps, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def profile_local(self):
+        """clock64 totals per phase of the local kernel: array (local_grid, 8), see include/pd_b200.h"""
+        out = np.zeros((self.info()["local_grid"], 8), np.uint64)
+        _check(lib().pd_profile_local(self._h, _p(out)))
+        return out
 
     def info(self):
         nv, nt, ntl, lg = C.c_int(), C.c_int(), C.c_int(), C.c_int()

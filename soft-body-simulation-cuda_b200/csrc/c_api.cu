@@ -214,7 +214,7 @@ int pd_layout_counts(const pd_layout* l, int* nTiles, uint32_t* nSlots, size_t* 
     return PD_OK;
 }
 int pd_layout_get(const pd_layout* l, uint32_t* tetOrder, uint32_t* vertOrder, uint32_t* tetNew, uint32_t* tileTetStart,
-                  uint64_t* tileRecOff, uint8_t* records, uint32_t* vslotPtr, uint32_t* vslot)
+                  uint64_t* tileRecOff, uint8_t* records, uint32_t* vslotPtr, uint32_t* vslot, uint32_t* vlist)
 {
     if (!l) return fail(PD_ERR_INVALID, "layout is NULL");
     const Layout& L = l->L;
@@ -226,6 +226,7 @@ int pd_layout_get(const pd_layout* l, uint32_t* tetOrder, uint32_t* vertOrder, u
     if (records) std::memcpy(records, L.records.data(), L.records.size());
     if (vslotPtr) std::memcpy(vslotPtr, L.vslotPtr.data(), L.vslotPtr.size() * 4);
     if (vslot) std::memcpy(vslot, L.vslot.data(), L.vslot.size() * 4);
+    if (vlist) std::memcpy(vlist, L.vlist.data(), L.vlist.size() * 4);
     return PD_OK;
 }
 int pd_morton_keys(const float* X, const uint32_t* Tet, int nT, uint32_t* keys)
@@ -328,6 +329,7 @@ int pd_time_kernels(pd_engine* e, int reps, float* lms, float* vms)
     ENGINE_CALL(if (reps <= 0) return fail(PD_ERR_INVALID, "reps <= 0");
                 if (lms) *lms = e->e->timeLocalKernelMs(reps); if (vms) *vms = e->e->timeVertexKernelMs(reps))
 }
+int pd_profile_local(pd_engine* e, unsigned long long* out) { ENGINE_CALL(if (!out) return fail(PD_ERR_INVALID, "out is NULL"); e->e->profileLocal(out)) }
 int pd_engine_info(const pd_engine* e, int* nv, int* nt, int* ntiles, uint32_t* nslots, size_t* streamBytes, size_t* devBytes, int* lgrid)
 {
     if (!e || !e->e) return fail(PD_ERR_INVALID, "engine is NULL");

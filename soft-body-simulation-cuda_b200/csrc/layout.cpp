@@ -84,13 +84,59 @@ void rest_shape(const float* X, const uint32_t* Tet, int nT, float* DmInv, float
 
 static inline size_t rup(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Proper edge colouring with 8 colours (Koenig: a bipartite multigraph of maximum degree 8 has one).
+// Edge (tl, k) joins store group k*32 + tl/8 (the 8 tets whose STS.128 of corner k issue together) and the
+// load group of its incidence entry, (row, half, lane/8) (the 8 lanes whose LDS.128 issue together); the
+// colour is the 16-byte column inside the 128-byte H-scratch line of the store group, so that both the
+// stores of phase B and the gathered loads of phase C are free of shared-memory bank conflicts.
+// Deterministic: edges in (tet, corner) order, smallest free colours, alternating-path recolouring.
+static void color_tile(uint32_t nTets, uint32_t nRows, const uint32_t* epos, uint8_t (*col)[4])
+{
+    const uint32_t nE = 4u * nTets, nR = nRows * 8u;
+    int16_t atL[128][8];
+    std::vector<int16_t> atR((size_t)nR * 8, -1);
+    for (auto& a : atL) for (auto& x : a) x = -1;
+    std::vector<uint16_t> eu(nE), ev(nE);
+    std::vector<int8_t> ec(nE, -1);
+    std::vector<uint16_t> path;
+    for (uint32_t e = 0; e < nE; ++e) {
+        const uint32_t tl = e / 4u, k = e % 4u, p = epos[e];
+        const uint32_t u = k * 32u + tl / 8u, v = ((p / 64u) * 2u + (p & 1u)) * 4u + ((p / 2u) % 32u) / 8u;
+        eu[e] = (uint16_t)u; ev[e] = (uint16_t)v;
+        int a = 0, b = 0;
+        while (a < 8 && atL[u][a] >= 0) ++a;
+        while (b < 8 && atR[(size_t)v * 8 + b] >= 0) ++b;
+        if (a >= 8 || b >= 8) throw std::runtime_error("tile colouring: degree above 8");
+        if (atR[(size_t)v * 8 + a] >= 0) {
+            // free colour a at v: swap a <-> b along the alternating path that leaves v by colour a
+            path.clear();
+            uint32_t node = v; bool right = true; int c = a;
+            for (;;) {
+                const int16_t f = right ? atR[(size_t)node * 8 + c] : atL[node][c];
+                if (f < 0) break;
+                path.push_back((uint16_t)f);
+                node = right ? eu[f] : ev[f];
+                right = !right;
+                c = (c == a) ? b : a;
+            }
+            for (uint16_t f : path) { atL[eu[f]][ec[f]] = -1; atR[(size_t)ev[f] * 8 + ec[f]] = -1; }
+            for (uint16_t f : path) {
+                ec[f] = (int8_t)(ec[f] == a ? b : a);
+                atL[eu[f]][ec[f]] = (int16_t)f; atR[(size_t)ev[f] * 8 + ec[f]] = (int16_t)f;
+            }
+        }
+        ec[e] = (int8_t)a;
+        atL[u][a] = (int16_t)e; atR[(size_t)v * 8 + a] = (int16_t)e;
+    }
+    for (uint32_t e = 0; e < nE; ++e) col[e / 4u][e % 4u] = (uint8_t)ec[e];
+}
+
 // tiles + records + slots for a mesh whose vertex ids are final
 static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv, const float* w, Layout& L)
 {
-    L.tileTetStart.clear(); L.tileRecOff.clear(); L.records.clear(); L.tileTab.clear();
+    L.tileTetStart.clear(); L.tileRecOff.clear(); L.records.clear(); L.tileTab.clear(); L.vlist.clear();
     std::vector<int> mark((size_t)nV, -1);
     std::vector<uint32_t> lidx((size_t)nV, 0);
-    std::vector<uint32_t> slotBase;
     std::vector<uint32_t> vcount((size_t)nV + 1, 0);
     L.maxLocal = 0;
     uint32_t slot = 0;
@@ -146,38 +192,67 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
         for (uint32_t l = 0; l < nLocal; ++l) { cnt[l] = lidx[vl[l]]; }
         for (uint32_t l = 0; l < nLocal; ++l) { lidx[vl[l]] = l; vcount[vl[l] + 1]++; }
         L.maxLocal = std::max(L.maxLocal, (int)nLocal);
-        const size_t offV = tile_off_vlist(nTets), abBytes = tile_ab_bytes(nTets, nLocal), cBytes = 128 * (size_t)nRows;
+        const size_t abBytes = tile_ab_bytes(nTets), cBytes = 128 * (size_t)nRows;
         const size_t base = L.records.size();
         L.records.resize(base + abBytes + cBytes, 0);
         uint8_t* rec = L.records.data() + base;
-        TileHeader h{nTets, nLocal, slot, (uint32_t)abBytes, (uint32_t)cBytes, nGroups, (uint32_t)(base & 0xffffffffu), (uint32_t)((uint64_t)base >> 32)};
+        if ((uint64_t)(tile + 1) * TILE_NLMAX > 0xffffffffull) throw std::runtime_error("tile builder: slot index overflow");
+        const uint32_t slotBase = (uint32_t)tile * (uint32_t)TILE_NLMAX;
+        TileHeader h{nTets, nLocal, slotBase, (uint32_t)abBytes, (uint32_t)cBytes, nGroups, (uint32_t)(base & 0xffffffffu), (uint32_t)((uint64_t)base >> 32)};
         std::memcpy(rec, &h, 32);
         uint32_t* gtab = reinterpret_cast<uint32_t*>(rec + 32);
         for (uint32_t g = 0; g < nGroups; ++g) gtab[g] = gRowBase[g] | (gRows[g] << 16);
-        uint32_t* vlist = reinterpret_cast<uint32_t*>(rec + offV);
-        for (uint32_t l = 0; l < nLocal; ++l) vlist[l] = vl[l];       // owner bits are set once all tiles are known
+        L.vlist.insert(L.vlist.end(), vl.begin(), vl.end());          // owner bits are set once all tiles are known
+        L.vlist.resize((size_t)(tile + 1) * TILE_NLMAX, 0xffffffffu);
         uint16_t* incT = reinterpret_cast<uint16_t*>(rec + abBytes);
-        for (size_t i = 0; i < cBytes / 2; ++i) incT[i] = (uint16_t)TILE_ZERO_OFF;
+        // incidence entry of (tet tl, corner k) -> position (row, lane, half) in the transposed rows
         std::vector<uint32_t> fill(nLocal, 0);
+        std::vector<uint32_t> epos((size_t)nTets * 4);      // index into incT
+        uint32_t cl[TILE_T][4];
+        for (uint32_t tl = 0; tl < nTets; ++tl)
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t l = lidx[tet[4 * ((size_t)t0 + tl) + k]];
+                cl[tl][k] = l;
+                const uint32_t e = fill[l]++, g = l / 32u, lane = l % 32u;
+                epos[4 * tl + k] = ((gRowBase[g] + e / 2u) * 32u + lane) * 2u + (e & 1u);
+            }
+        // H-scratch column of every (tet, corner): proper 8-colouring of the bipartite multigraph
+        // store groups {8 consecutive tets, corner k}  x  load groups {row, half, 8 consecutive lanes}
+        uint8_t col[TILE_T][4];
+        color_tile(nTets, nRows, epos.data(), col);
+        // pads point at the zero slot of a column no real entry of their load group uses
+        {
+            const size_t nLg = (size_t)nRows * 8;          // load group = (row, half, lane / 8)
+            std::vector<uint8_t> used(nLg, 0);
+            for (uint32_t tl = 0; tl < nTets; ++tl)
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t p = epos[4 * tl + k], row = p / 64u, lane = (p / 2u) % 32u, half = p & 1u;
+                    used[(row * 2u + half) * 4u + lane / 8u] |= (uint8_t)(1u << col[tl][k]);
+                }
+            for (uint32_t row = 0; row < nRows; ++row)
+                for (uint32_t lane = 0; lane < 32; ++lane)
+                    for (uint32_t half = 0; half < 2; ++half) {
+                        const uint8_t u = used[(row * 2u + half) * 4u + lane / 8u];
+                        uint32_t c = 0;
+                        while (c < 7 && (u >> c & 1u)) ++c;          // a full group (u == 0xff) has no pad
+                        incT[(row * 32u + lane) * 2u + half] = (uint16_t)(TILE_ZERO_OFF + 16u * c);
+                    }
+        }
         for (uint32_t tl = 0; tl < nTets; ++tl) {
             const size_t t = (size_t)t0 + tl;
             float* tr = reinterpret_cast<float*>(rec + TILE_OFF_TETS + 48 * (size_t)tl);
             for (int e = 0; e < 9; ++e) tr[e] = DmInv[9 * t + e];
             tr[9] = w[t];
-            uint32_t c[4];
+            uint32_t h[4];
             for (int k = 0; k < 4; ++k) {
-                const uint32_t l = lidx[tet[4 * t + k]];
-                c[k] = l;
-                const uint32_t e = fill[l]++, g = l / 32u, lane = l % 32u;
-                // row (gRowBase[g] + e/2), lane, half e%2
-                incT[((size_t)(gRowBase[g] + e / 2u) * 32u + lane) * 2u + (e & 1u)] = (uint16_t)(k * TILE_HSTRIDE + tile_swz(tl) * 16u);
+                h[k] = tile_corner_half(cl[tl][k], col[tl][k]);
+                incT[epos[4 * tl + k]] = (uint16_t)tile_h_offset(tl, (uint32_t)k, col[tl][k]);
             }
-            const uint32_t c01 = (c[0] * 16u) | ((c[1] * 16u) << 16), c23 = (c[2] * 16u) | ((c[3] * 16u) << 16);
+            const uint32_t c01 = h[0] | (h[1] << 16), c23 = h[2] | (h[3] << 16);
             std::memcpy(&tr[10], &c01, 4);
             std::memcpy(&tr[11], &c23, 4);
         }
         L.tileTab.push_back(TileEntry{(uint64_t)base, (uint32_t)abBytes, (uint32_t)cBytes});
-        slotBase.push_back(slot);
         slot += nLocal;
         t0 = t1;
         ++tile;
@@ -191,15 +266,11 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
     L.vslotPtr.assign(vcount.begin(), vcount.end());
     L.vslot.assign((size_t)slot, 0u);
     std::vector<uint32_t> fillv(vcount.begin(), vcount.end() - 1);
-    for (int ti = 0; ti < L.nTiles; ++ti) {
-        uint8_t* rec = L.records.data() + L.tileRecOff[ti];
-        TileHeader h; std::memcpy(&h, rec, 32);
-        uint32_t* vlist = reinterpret_cast<uint32_t*>(rec + tile_off_vlist(h.nTets));
-        for (uint32_t l = 0; l < h.nLocal; ++l) {
-            const uint32_t v = vlist[l];
-            if (fillv[v] == L.vslotPtr[v]) vlist[l] = v | TILE_OWNER_BIT;     // first slot of the vertex = owner
-            L.vslot[fillv[v]++] = h.slotBase + l;
-        }
+    for (size_t s = 0; s < L.vlist.size(); ++s) {
+        const uint32_t v = L.vlist[s];
+        if (v == 0xffffffffu) continue;
+        if (fillv[v] == L.vslotPtr[v]) L.vlist[s] = v | TILE_OWNER_BIT;       // first slot of the vertex = owner
+        L.vslot[fillv[v]++] = (uint32_t)s;
     }
 }
 

@@ -21,28 +21,36 @@ constexpr uint32_t TILE_OWNER_BIT = 0x80000000u;         // vlist flag: this slo
 //   +0    TileHeader                                                          32 B
 //   +32   group table u32[12]: rowBase | nRows << 16 of each 32-vertex group (8 used)  48 B
 //   +80   tet records, 48 B each: f32 B[9] (DmInv, row-major), f32 w = |V0|*mu, u32 c01, u32 c23 --
-//         the four tile-local corner indices * 16 (byte offsets into the staged vertex array)
-//   offV  vlist u32[nLocal]: global (renumbered) vertex id of each tile-local vertex | TILE_OWNER_BIT,
-//         ordered by (in-tile incidence count descending, id ascending)     (pad 16)
+//         four 16-bit corner words: bits 4..11 = tile-local vertex index (so `word & 0xff0` is the byte offset
+//         into the staged vertex array), bits 12..14 = H-scratch column of this corner's contribution
+// The tile's vertex list lives OUTSIDE the record, in the global array Layout::vlist indexed by slot.
+// Slots are PADDED per tile: slot = tile * TILE_NLMAX + tile-local vertex, so that the local kernel needs no
+// per-tile offset to find them; entry = u32 global (renumbered) vertex id | TILE_OWNER_BIT, or 0xffffffff for
+// the unused tail; tile-local vertices ordered by (in-tile incidence count descending, id ascending).  The
+// local kernel reads it with plain coalesced loads two tiles ahead of use (it feeds the position gather,
+// which runs one tile ahead).  Unused slots of the partial-sum array are never read or written.
 // Part C (phase C, single buffered): the tile-local incidence lists, transposed per group of 32
 // vertices: row r of group g holds, for each of the 32 lanes (vertices), entries 2r and 2r+1 of that
 // vertex's list packed as two u16 in one u32.  An entry is the byte offset of one tet-corner
-// contribution in the H scratch, corner*TILE_HSTRIDE + swz(tet)*16 with swz(t) = t ^ ((t>>3)&7);
-// lists are ascending in (tet, corner) and padded with TILE_ZERO_OFF.  128 B per row.
+// contribution in the H scratch, tile_h_offset(tet, corner, column): the 8 tets of a quarter-warp share one
+// 128-byte line per corner and the column (0..7) inside it comes from an 8-colouring (layout.cpp:color_tile)
+// that makes every quarter-warp STS.128 of phase B and every quarter-warp LDS.128 of phase C conflict free.
+// Lists are ascending in (tet, corner) and padded with TILE_ZERO_OFF + 16*c (eight zero slots, one per
+// column, c = a column the pad's quarter-warp does not use).  128 B per row.
 struct TileHeader {
     uint32_t nTets, nLocal, slotBase, abBytes, cBytes, nGroups, offLo, offHi;   // off = this record's byte offset in the stream
 };
-struct TileEntry {   // per-tile entry of the device tile table
+struct TileEntry {   // per-tile entry of the device tile table (one uint4)
     uint64_t off;    // byte offset of part AB in the record stream (part C follows at off + abBytes)
     uint32_t abBytes, cBytes;
 };
 inline uint32_t rup16(uint32_t x) { return (x + 15u) & ~15u; }
 constexpr uint32_t TILE_OFF_TETS = 80u;
-inline uint32_t tile_off_vlist(uint32_t nTets) { return TILE_OFF_TETS + 48u * nTets; }
-inline uint32_t tile_ab_bytes(uint32_t nTets, uint32_t nLocal) { return tile_off_vlist(nTets) + rup16(4u * nLocal); }
-inline uint32_t tile_swz(uint32_t t) { return t ^ ((t >> 3) & 7u); }
+inline uint32_t tile_ab_bytes(uint32_t nTets) { return TILE_OFF_TETS + 48u * nTets; }
+inline uint32_t tile_h_offset(uint32_t tet, uint32_t corner, uint32_t column) { return corner * TILE_HSTRIDE + ((tet & ~7u) | column) * 16u; }
+inline uint32_t tile_corner_half(uint32_t localVertex, uint32_t column) { return (localVertex << 4) | (column << 12); }
 // TMA landing buffers (multiples of 128 B)
-constexpr uint32_t TILE_ABMAX = ((TILE_OFF_TETS + 48u * TILE_T + 4u * TILE_NLMAX) + 127u) & ~127u;
+constexpr uint32_t TILE_ABMAX = ((TILE_OFF_TETS + 48u * TILE_T) + 127u) & ~127u;
 constexpr uint32_t TILE_CMAX = 128u * TILE_ROWSMAX;
 
 struct Layout {
@@ -58,10 +66,11 @@ struct Layout {
     std::vector<uint64_t> tileRecOff;   // nTiles+1, byte offsets into `records` (16-B aligned)
     std::vector<TileEntry> tileTab;     // nTiles, what the local kernel's producer thread reads
     std::vector<uint8_t> records;       // packed tile records
-    // partial-sum slots: slot = slotBase[tile] + localVertex
-    uint32_t nSlots = 0;
+    // partial-sum slots: slot = tile * TILE_NLMAX + localVertex
+    uint32_t nSlots = 0;                // used slots (sum of the tiles' distinct-vertex counts)
     std::vector<uint32_t> vslotPtr;     // nV+1   vertex -> slots CSR (ascending slots)
     std::vector<uint32_t> vslot;        // nSlots
+    std::vector<uint32_t> vlist;        // nTiles * TILE_NLMAX   slot -> vertex id | TILE_OWNER_BIT (first slot of the vertex), 0xffffffff unused
     int maxLocal = 0;
 };
 

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -24,7 +25,7 @@ struct Engine::Impl {
     // tile stream
     uint8_t* records = nullptr;
     uint4* tileTab = nullptr;         // per tile: record offset (lo, hi), part AB bytes, part C bytes
-    uint32_t *vslotPtr = nullptr, *vslot = nullptr;
+    uint32_t *vslotPtr = nullptr, *vslot = nullptr, *vlist = nullptr;
     float4* P = nullptr;             // one partial RHS sum per (tile, tile-local vertex) slot
     // per-vertex state (renumbered, padded float4)
     float4* q[3] = {nullptr, nullptr, nullptr};
@@ -80,7 +81,8 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     d.tileTab = dalloc<uint4>(L_.tileTab.size());
     d.vslotPtr = dalloc<uint32_t>(L_.vslotPtr.size());
     d.vslot = dalloc<uint32_t>(L_.vslot.size());
-    d.P = dalloc<float4>((size_t)L_.nSlots);
+    d.vlist = dalloc<uint32_t>(L_.vlist.size());
+    d.P = dalloc<float4>((size_t)L_.nTiles * TILE_NLMAX);      // padded slots: tile * TILE_NLMAX + local vertex
     for (int k = 0; k < 3; ++k) d.q[k] = dalloc<float4>(nV_);
     d.b0 = dalloc<float4>(nV_); d.X = dalloc<float4>(nV_); d.V = dalloc<float4>(nV_);
     d.XT = dalloc<float4>(nV_); d.X0 = dalloc<float4>(nV_);
@@ -94,6 +96,7 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     CUDA_CHECK(cudaMemcpy(d.tileTab, L_.tileTab.data(), L_.tileTab.size() * sizeof(TileEntry), cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(d.vslotPtr, L_.vslotPtr.data(), L_.vslotPtr.size() * 4, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(d.vslot, L_.vslot.data(), L_.vslot.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(d.vlist, L_.vlist.data(), L_.vlist.size() * 4, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(d.oldOfNew, L_.vertOrder.data(), (size_t)nV_ * 4, cudaMemcpyHostToDevice));
     {
         std::vector<float> m(nV_), b(nV_);
@@ -137,6 +140,7 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     };
     setAttr((const void*)k_local<0, true>); setAttr((const void*)k_local<0, false>);
     setAttr((const void*)k_local<1, true>); setAttr((const void*)k_local<1, false>);
+    setAttr((const void*)k_local<2, true>); setAttr((const void*)k_local<0, true, true>); setAttr((const void*)k_local<2, true, true>);
     int perSm = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_local<0, true>, TILE_T, LOCAL_SMEM_BYTES));
     if (perSm < 1) throw std::runtime_error("local kernel does not fit on an SM");
@@ -196,12 +200,12 @@ void Engine::prepare()
     for (int ti = 0; ti < L_.nTiles; ++ti) {
         const uint8_t* rec = L_.records.data() + L_.tileRecOff[ti];
         TileHeader h; std::memcpy(&h, rec, sizeof(h));
-        const uint32_t* vlist = reinterpret_cast<const uint32_t*>(rec + tile_off_vlist(h.nTets));
+        const uint32_t* vlist = L_.vlist.data() + h.slotBase;
         for (uint32_t t = 0; t < h.nTets; ++t) {
             const float* B = reinterpret_cast<const float*>(rec + TILE_OFF_TETS + 48 * (size_t)t);
             const float w = B[9];
             uint32_t cw[2]; std::memcpy(cw, B + 10, 8);
-            const uint32_t loc[4] = {(cw[0] & 0xffffu) >> 4, cw[0] >> 20, (cw[1] & 0xffffu) >> 4, cw[1] >> 20};
+            const uint32_t loc[4] = {(cw[0] >> 4) & 0xffu, (cw[0] >> 20) & 0xffu, (cw[1] >> 4) & 0xffu, (cw[1] >> 20) & 0xffu};
             for (int i = 0; i < 4; ++i) {
                 float col[3];
                 for (int r = 0; r < 3; ++r)
@@ -217,6 +221,24 @@ void Engine::prepare()
     dt2Prepared_ = params_.dt * params_.dt;
     ready_ = true;
     graphValid_ = false;
+}
+
+void Engine::launchLocal(const float4* q, bool jacobi, unsigned long long* prof)
+{
+    Impl& d = *d_;
+#define PD_LOCAL(RM, JAC) k_local<RM, JAC><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vlist, q, d.b0, d.P, prof)
+    if (prof) {
+        if (opt_.rotMode == 2) k_local<2, true, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vlist, q, d.b0, d.P, prof);
+        else k_local<0, true, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vlist, q, d.b0, d.P, prof);
+    } else if (jacobi) {
+        if (opt_.rotMode == 0) PD_LOCAL(0, true);
+        else if (opt_.rotMode == 1) PD_LOCAL(1, true);
+        else PD_LOCAL(2, true);
+    } else {
+        if (opt_.rotMode == 1) PD_LOCAL(1, false);
+        else PD_LOCAL(0, false);
+    }
+#undef PD_LOCAL
 }
 
 // The launch sequence of one PdSolver::Update in Jacobi mode.  `timed` brackets the local /
@@ -239,16 +261,14 @@ void Engine::enqueueStep(bool timed)
         const float4* prev = d.q[(i + 2) % 3];
         float4* next = d.q[(i + 1) % 3];
         rec();
-        if (opt_.rotMode == 0)
-            k_local<0, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, cur, d.b0, d.P);
-        else
-            k_local<1, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, cur, d.b0, d.P);
+        launchLocal(cur, true);
         rec();
         // omega recurrence in float, pdSolver.cu:196-198
         if (i <= 10) omega = 1;
         else if (i == 11) omega = 2 / (2 - p.rho * p.rho);
         else omega = 4 / (4 - p.rho * p.rho * omega);
-        k_vertex_jacobi<<<vg, vb, 0, stream_>>>(nV_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega, wdbc);
+        if (opt_.rotMode == 1) k_vertex_jacobi<false><<<vg, vb, 0, stream_>>>(nV_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega, wdbc);
+        else k_vertex_jacobi<true><<<vg, vb, 0, stream_>>>(nV_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega, wdbc);
         rec();
     }
     rec();
@@ -406,10 +426,7 @@ float Engine::timeLocalKernelMs(int reps)
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     CUDA_CHECK(cudaEventRecord(a, stream_));
     for (int r = 0; r < reps; ++r) {
-        if (opt_.rotMode == 0)
-            k_local<0, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.XT, d.b0, d.P);
-        else
-            k_local<1, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.XT, d.b0, d.P);
+        launchLocal(d.XT, true);
     }
     CUDA_CHECK(cudaEventRecord(b, stream_));
     CUDA_CHECK(cudaEventSynchronize(b));
@@ -433,13 +450,28 @@ float Engine::timeVertexKernelMs(int reps)
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     CUDA_CHECK(cudaEventRecord(a, stream_));
     for (int r = 0; r < reps; ++r)
-        k_vertex_jacobi<<<vg, vb, 0, stream_>>>(nV_, d.q[0], d.q[2], d.q[1], d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, 1.0f, 1.0f);
+        k_vertex_jacobi<true><<<vg, vb, 0, stream_>>>(nV_, d.q[0], d.q[2], d.q[1], d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, 1.0f, 1.0f);
     CUDA_CHECK(cudaEventRecord(b, stream_));
     CUDA_CHECK(cudaEventSynchronize(b));
     float ms = 0;
     CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
     cudaEventDestroy(a); cudaEventDestroy(b);
     return ms / (float)reps;
+}
+
+// per-phase clock totals of the local kernel (warp 0 of every CTA): out[8 * localGrid()]
+void Engine::profileLocal(unsigned long long* out)
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    if (!ready_) prepare();
+    unsigned long long* dprof = nullptr;
+    CUDA_CHECK(cudaMalloc(&dprof, 64ull * localGrid_));
+    CUDA_CHECK(cudaMemsetAsync(dprof, 0, 64ull * localGrid_, stream_));
+    launchLocal(d_->XT, true, nullptr);            // warm
+    launchLocal(d_->XT, true, dprof);
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    CUDA_CHECK(cudaMemcpy(out, dprof, 64ull * localGrid_, cudaMemcpyDeviceToHost));
+    cudaFree(dprof);
 }
 
 void rotation_batch(int device, int rotMode, int n, const float* F, float* R, int* usedFast)

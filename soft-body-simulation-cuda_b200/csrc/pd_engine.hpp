@@ -3,6 +3,8 @@
 #pragma once
 #include <cstdint>
 #include <memory>
+
+#include <cuda_runtime.h>
 #include <string>
 #include <vector>
 
@@ -63,12 +65,14 @@ public:
     // timing of one kernel family, measured with events over `reps` launches on the engine's stream
     float timeLocalKernelMs(int reps);
     float timeVertexKernelMs(int reps);
+    void profileLocal(unsigned long long* out);     // 8 counters per CTA of the local kernel (clock64 per phase)
 
 private:
     struct Impl;
     void prepare();
     void buildGraph();
     void enqueueStep(bool timed);
+    void launchLocal(const float4* q, bool jacobi, unsigned long long* prof = nullptr);
     template <typename T> T* dalloc(size_t n);
 
     int nV_ = 0, nT_ = 0;

@@ -57,12 +57,13 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 // 16-byte asynchronous gather global -> shared (LDGSTS), no register staging
-__device__ __forceinline__ void cp_async16_hint(void* dst, const void* src, unsigned long long policy)
+__device__ __forceinline__ void cp_async16_hint(uint32_t dstShared, const void* src, unsigned long long policy)
 {
-    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "l"(policy) : "memory");
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dstShared), "l"(src), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 ldg_hint(const float4* p, unsigned long long policy)
 {
@@ -108,20 +109,20 @@ __global__ void k_predict(int nV, const float4* __restrict__ X, const float4* __
 // PdUtil::addM_h2Sn + computeLocal (pdUtil.cu:97-145,168-179), one tile of <= TILE_T tets per
 // iteration of a persistent CTA (4 CTAs per SM).  Per tile:
 //   0. two bulk asynchronous copies (TMA, cp.async.bulk + mbarrier, L2 evict_first) land the packed
-//      tile record in shared memory: part AB (tet records, vertex list; double buffered, fetched two
-//      tiles ahead) and part C (transposed incidence rows; fetched while phase B runs);
+//      tile record in shared memory: part AB (tet records; double buffered, fetched two tiles ahead)
+//      and part C (transposed incidence rows; fetched while phase B runs);
 //   A. the tile's distinct vertex positions are gathered into shared memory by 16-byte cp.async
-//      (LDGSTS), issued one tile ahead so that the gather latency hides behind phase C of the
-//      previous tile;
+//      (LDGSTS) into a DOUBLE-BUFFERED staging area, issued a whole tile ahead (before phase B of the
+//      previous tile), so the random-access latency hides behind a full phase B + phase C; the vertex
+//      ids come from the global slot-indexed vlist, read (coalesced) one more tile ahead into a register;
 //   B. one tet per thread: 3 x LDS.128 (48-byte record: DmInv, w, corner offsets; the 48-byte
 //      stride is bank-conflict free), 4 x LDS.128 positions, F = Ds*DmInv, rotation,
-//      H = w (R - F) DmInv^T G (or w R DmInv^T G), 4 x STS.128 into the (swizzled) H scratch;
-//   C. (deferred until the next tile's gather is in flight) one tile-local vertex per thread, 32
-//      vertices of similar incidence count per warp: ordered sum over the vertex's incidence list
-//      (one conflict-free LDS.32 yields two ready-made byte offsets into the H scratch) -> ONE
-//      partial sum per (tile, vertex) slot.  The vertex's first (owner) slot starts from
-//      b0 = (M/h^2) s_old, so a vertex whose tets all sit in one tile gets exactly the reference's
-//      sequential  b = c*s; b += h1; b += h2; ...  (tet order).
+//      H = w (R - F) DmInv^T G (or w R DmInv^T G), 4 x STS.128 into the H scratch;
+//   C. (deferred into the next iteration) one tile-local vertex per thread, 32 vertices of similar
+//      incidence count per warp: ordered sum over the vertex's incidence list (one conflict-free LDS.32
+//      yields two ready-made byte offsets into the H scratch) -> ONE partial sum per (tile, vertex)
+//      slot.  The vertex's first (owner) slot starts from b0 = (M/h^2) s_old, so a vertex whose tets
+//      all sit in one tile gets exactly the reference's sequential  b = c*s; b += h1; b += h2; ...
 // No atomics anywhere: the reference's 12 float atomicAdds per tet become ordered sums, so results
 // are run-to-run bit-identical.  Two __syncthreads per tile.
 // F and H are written with the fused/rounded operation pattern nvcc gives the reference's glm
@@ -129,9 +130,11 @@ __global__ void k_predict(int nV, const float4* __restrict__ X, const float4* __
 // bit-identical to the reference kernel's.
 constexpr uint32_t LOCAL_OFF_C = 2u * TILE_ABMAX;
 constexpr uint32_t LOCAL_OFF_QS = LOCAL_OFF_C + TILE_CMAX;
-constexpr uint32_t LOCAL_OFF_HS = LOCAL_OFF_QS + 16u * TILE_NLMAX;
-constexpr uint32_t LOCAL_OFF_BAR = LOCAL_OFF_HS + TILE_ZERO_OFF + 16u;
-constexpr uint32_t LOCAL_SMEM_BYTES = LOCAL_OFF_BAR + 32u;
+constexpr uint32_t LOCAL_QS_BYTES = 16u * TILE_NLMAX;
+constexpr uint32_t LOCAL_OFF_HS = LOCAL_OFF_QS + 2u * LOCAL_QS_BYTES;
+constexpr uint32_t LOCAL_OFF_BAR = LOCAL_OFF_HS + TILE_ZERO_OFF + 128u;    // eight zero slots, one per column
+constexpr uint32_t LOCAL_OFF_TE = LOCAL_OFF_BAR + 32u;      // producer: two prefetched tile-table entries (tile parity)
+constexpr uint32_t LOCAL_SMEM_BYTES = LOCAL_OFF_TE + 32u;
 static_assert(4u * (LOCAL_SMEM_BYTES + 1024u) <= 233472u, "4 CTAs of the local kernel must fit one SM's shared memory");
 static_assert(TILE_NLMAX == TILE_T, "one tile-local vertex per thread");
 
@@ -141,33 +144,70 @@ __device__ __forceinline__ float dot3_nv(float a0, float b0, float a1, float b1,
 }
 
 // phase C of one tile: `ve` = this thread's vlist entry (0xffffffff if it has no vertex), gt = this
-// warp's group-table word, slot0 = the tile's first slot
+// warp's group-table word, slot0 = the tile's first slot.
+// FAITHFUL: b = b0; b += h_1; b += h_2; ... strictly in (tet, corner) order, the vertex's first (owner) slot
+// starting from b0 = (M/h^2) s_old -- the reference's sequential sum for a vertex whose tets share a tile.
+// Otherwise (product default) the slot holds the elastic terms only (the vertex kernel adds b0), summed in
+// a different FIXED order without a long dependency chain: four rows per trip, their entries prefetched a
+// trip ahead, eight gathered LDS.128 in flight, even and odd list entries accumulated separately.  Rows
+// past the group's count read the zero slot.
+template <bool FAITHFUL>
 __device__ __forceinline__ void local_phase_c(const uint8_t* smem, uint32_t ve, uint32_t gt, uint32_t slot0, int tid,
                                               const float4* __restrict__ b0, float4* __restrict__ P)
 {
     const uint32_t* row = reinterpret_cast<const uint32_t*>(smem + LOCAL_OFF_C) + (gt & 0xffffu) * 32u + (tid & 31);
     const uint32_t nR = gt >> 16;
     const uint8_t* Hb = smem + LOCAL_OFF_HS;
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    if (ve != 0xffffffffu && (ve & TILE_OWNER_BIT)) {
-        const float4 bb = ldg_hint(&b0[ve & ~TILE_OWNER_BIT], L2_EVICT_LAST);
-        sx = bb.x; sy = bb.y; sz = bb.z;
-    }
-    for (uint32_t r = 0; r < nR; ++r) {
-        const uint32_t e2 = row[32u * r];
-        const float4 ha = *reinterpret_cast<const float4*>(Hb + (e2 & 0xffffu));
-        const float4 hb = *reinterpret_cast<const float4*>(Hb + (e2 >> 16));
-        sx = __fadd_rn(sx, ha.x); sy = __fadd_rn(sy, ha.y); sz = __fadd_rn(sz, ha.z);
-        sx = __fadd_rn(sx, hb.x); sy = __fadd_rn(sy, hb.y); sz = __fadd_rn(sz, hb.z);
+    float sx, sy, sz;
+    if (FAITHFUL) {
+        sx = sy = sz = 0.f;
+        if (ve != 0xffffffffu && (ve & TILE_OWNER_BIT)) {
+            const float4 bb = ldg_hint(&b0[ve & ~TILE_OWNER_BIT], L2_EVICT_LAST);
+            sx = bb.x; sy = bb.y; sz = bb.z;
+        }
+        for (uint32_t r = 0; r < nR; ++r) {
+            const uint32_t e2 = row[32u * r];
+            const float4 ha = *reinterpret_cast<const float4*>(Hb + (e2 & 0xffffu));
+            const float4 hb = *reinterpret_cast<const float4*>(Hb + (e2 >> 16));
+            sx = __fadd_rn(sx, ha.x); sy = __fadd_rn(sy, ha.y); sz = __fadd_rn(sz, ha.z);
+            sx = __fadd_rn(sx, hb.x); sy = __fadd_rn(sy, hb.y); sz = __fadd_rn(sz, hb.z);
+        }
+    } else {
+        constexpr uint32_t ZZ = TILE_ZERO_OFF | (TILE_ZERO_OFF << 16);
+        float ax = 0.f, ay = 0.f, az = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
+        uint32_t e0 = (0u < nR) ? row[0] : ZZ, e1 = (1u < nR) ? row[32] : ZZ, e2 = (2u < nR) ? row[64] : ZZ, e3 = (3u < nR) ? row[96] : ZZ;
+        for (uint32_t r = 0; r < nR; r += 4) {
+            const float4 h0 = *reinterpret_cast<const float4*>(Hb + (e0 & 0xffffu));
+            const float4 h1 = *reinterpret_cast<const float4*>(Hb + (e0 >> 16));
+            const float4 h2 = *reinterpret_cast<const float4*>(Hb + (e1 & 0xffffu));
+            const float4 h3 = *reinterpret_cast<const float4*>(Hb + (e1 >> 16));
+            const float4 h4 = *reinterpret_cast<const float4*>(Hb + (e2 & 0xffffu));
+            const float4 h5 = *reinterpret_cast<const float4*>(Hb + (e2 >> 16));
+            const float4 h6 = *reinterpret_cast<const float4*>(Hb + (e3 & 0xffffu));
+            const float4 h7 = *reinterpret_cast<const float4*>(Hb + (e3 >> 16));
+            const uint32_t* nx = row + 32u * (r + 4u);
+            e0 = (r + 4u < nR) ? nx[0] : ZZ; e1 = (r + 5u < nR) ? nx[32] : ZZ; e2 = (r + 6u < nR) ? nx[64] : ZZ; e3 = (r + 7u < nR) ? nx[96] : ZZ;
+            ax = __fadd_rn(ax, h0.x); ay = __fadd_rn(ay, h0.y); az = __fadd_rn(az, h0.z);
+            cx = __fadd_rn(cx, h1.x); cy = __fadd_rn(cy, h1.y); cz = __fadd_rn(cz, h1.z);
+            ax = __fadd_rn(ax, h2.x); ay = __fadd_rn(ay, h2.y); az = __fadd_rn(az, h2.z);
+            cx = __fadd_rn(cx, h3.x); cy = __fadd_rn(cy, h3.y); cz = __fadd_rn(cz, h3.z);
+            ax = __fadd_rn(ax, h4.x); ay = __fadd_rn(ay, h4.y); az = __fadd_rn(az, h4.z);
+            cx = __fadd_rn(cx, h5.x); cy = __fadd_rn(cy, h5.y); cz = __fadd_rn(cz, h5.z);
+            ax = __fadd_rn(ax, h6.x); ay = __fadd_rn(ay, h6.y); az = __fadd_rn(az, h6.z);
+            cx = __fadd_rn(cx, h7.x); cy = __fadd_rn(cy, h7.y); cz = __fadd_rn(cz, h7.z);
+        }
+        sx = __fadd_rn(ax, cx); sy = __fadd_rn(ay, cy); sz = __fadd_rn(az, cz);
     }
     if (ve != 0xffffffffu) P[slot0 + tid] = make_float4(sx, sy, sz, 0.f);
 }
 
-template <int ROT_MODE, bool JACOBI>
+template <int ROT_MODE, bool JACOBI, bool PROF = false>
 __global__ void __launch_bounds__(TILE_T, 4)
 k_local(const uint8_t* __restrict__ records, const uint4* __restrict__ tileTab, int nTiles,
-        const float4* __restrict__ q, const float4* __restrict__ b0, float4* __restrict__ P)
+        const uint32_t* __restrict__ vlist, const float4* __restrict__ q, const float4* __restrict__ b0, float4* __restrict__ P,
+        unsigned long long* __restrict__ prof)
 {
+    // prof (may be null): per-phase clock64 totals of warp 0 of every CTA, 8 counters per CTA (scripts/phase_profile.py)
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + LOCAL_OFF_BAR);   // [0],[1]: part AB buffers, [2]: part C
     const int tid = threadIdx.x;
@@ -179,72 +219,110 @@ k_local(const uint8_t* __restrict__ records, const uint4* __restrict__ tileTab, 
         mbar_init(&bar[1], 1);
         mbar_init(&bar[2], 1);
         fence_barrier_init();
-        *reinterpret_cast<float4*>(smem + LOCAL_OFF_HS + TILE_ZERO_OFF) = make_float4(0.f, 0.f, 0.f, 0.f);
         fence_proxy_async();
     }
+    if (tid < 8) *reinterpret_cast<float4*>(smem + LOCAL_OFF_HS + TILE_ZERO_OFF + 16 * tid) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
-    // producer (thread 0): part AB of tile number k of this CTA -> buffer k & 1
-    auto fetch_ab = [&](int k) {
-        const uint4 te = __ldg(&tileTab[blockIdx.x + k * gridDim.x]);
+    // producer (thread 0): part AB of the tile whose table entry is `te` -> buffer k & 1
+    auto fetch_ab = [&](int k, uint4 te) {
         mbar_expect_tx(&bar[k & 1], te.z);
         bulk_g2s_hint(smem + (k & 1) * TILE_ABMAX, records + (((unsigned long long)te.y << 32) | te.x), te.z, &bar[k & 1], L2_EVICT_FIRST);
     };
-    // all threads: wait for part AB of tile k, start the asynchronous gather of its vertex positions
-    // (thread l <-> tile-local vertex l); returns this thread's vlist entry
-    auto start_gather = [&](int k) -> uint32_t {
-        mbar_wait(&bar[k & 1], (uint32_t)((k >> 1) & 1));
-        const uint8_t* rec = smem + (k & 1) * TILE_ABMAX;
-        const uint2 h = *reinterpret_cast<const uint2*>(rec);        // nTets, nLocal
-        uint32_t ve = 0xffffffffu;
-        if ((uint32_t)tid < h.y) {
-            ve = *reinterpret_cast<const uint32_t*>(rec + TILE_OFF_TETS + 48u * h.x + 4u * tid);
-            cp_async16_hint(smem + LOCAL_OFF_QS + 16 * tid, &q[ve & ~TILE_OWNER_BIT], L2_EVICT_LAST);
-            if (ve & TILE_OWNER_BIT) prefetch_l2(&b0[ve & ~TILE_OWNER_BIT]);
+    auto tile_entry = [&](int k) -> uint4 { return __ldg(&tileTab[blockIdx.x + k * gridDim.x]); };
+    // this thread's entry of the padded, slot-indexed vertex list of tile number k of this CTA
+    auto load_ve = [&](int k) -> uint32_t { return __ldg(&vlist[(blockIdx.x + k * gridDim.x) * (unsigned)TILE_NLMAX + tid]); };
+    // asynchronous gather of this thread's vertex into the staging buffers, alternating.  The two
+    // destinations live in per-thread registers that swap every tile: when ptxas 12.9 folds a uniform-register
+    // buffer offset into an LDGSTS that also carries a cache-hint descriptor it emits an encoding the B200
+    // rejects ("illegal instruction")
+    uint32_t gdst = smem_u32(smem + LOCAL_OFF_QS + 16 * tid);
+    uint32_t gdstOther = gdst + LOCAL_QS_BYTES;
+    auto gather = [&](uint32_t ve) {
+        if (ve != 0xffffffffu) {
+            cp_async16_hint(gdst, &q[ve & ~TILE_OWNER_BIT], L2_EVICT_LAST);
+            if (ROT_MODE == 1 && (ve & TILE_OWNER_BIT)) prefetch_l2(&b0[ve & ~TILE_OWNER_BIT]);
         }
         cp_async_commit();
-        return ve;
+        const uint32_t t = gdst; gdst = gdstOther; gdstOther = t;
     };
 
-    if (tid == 0) {
-        fetch_ab(0);
-        if (nIt > 1) fetch_ab(1);
+    // the producer (TMA issue) is lane 0 of the LAST warp: the tile-local vertices are sorted by incidence
+    // count, so warp 0 carries the longest phase C and the last warp the shortest (usually none at all)
+    const bool producer = tid == TILE_T - 32;
+    // its table entries arrive by 16-byte cp.async in the same groups as the position gathers (no registers held):
+    // the entry of tile k is requested at the top of iteration k-3 and read after barrier 2 of iteration k-2
+    auto prefetch_entry = [&](int k) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem + LOCAL_OFF_TE + 16 * (k & 1))),
+                     "l"(&tileTab[blockIdx.x + k * gridDim.x]) : "memory");
+    };
+    if (producer) {
+        fetch_ab(0, tile_entry(0));
+        if (nIt > 1) fetch_ab(1, tile_entry(1));
+        if (nIt > 2) prefetch_entry(2);
     }
-    uint32_t ve = start_gather(0);
-    uint32_t vePrev = 0xffffffffu, gtPrev = 0, slotPrev = 0;
-    // H scratch address of this thread's tet (swizzled so that phase C's gathers spread over banks)
-    float4* const Hst = reinterpret_cast<float4*>(smem + LOCAL_OFF_HS) + (tid ^ ((tid >> 3) & 7));
+    uint32_t veCur = load_ve(0);                             // vlist entry of this thread: tile it
+    gather(veCur);
+    uint32_t veNext = (nIt > 1) ? load_ve(1) : 0xffffffffu;  // tile it + 1
+    uint32_t vePrev = 0xffffffffu, gtPrev = 0;
+    // H scratch line of this thread's quarter-warp (corner k adds k * TILE_HSTRIDE, the record's column adds 16 * col)
+    uint8_t* const Hline = smem + LOCAL_OFF_HS + 16 * (tid & ~7);
 
+    long long tk = 0, acc[7] = {0, 0, 0, 0, 0, 0, 0};
+#define PD_TICK(i) if (PROF) { const long long now = clock64(); acc[i] += now - tk; tk = now; }
+    if (PROF) tk = clock64();
     for (int it = 0; it < nIt; ++it) {
         const int b = it & 1;
         const uint8_t* rec = smem + b * TILE_ABMAX;
-        // deferred phase C of the previous tile: runs while this tile's position gather is in flight
+        // a whole tile ahead: start the position gather of tile it+1 (its staging buffer was last read in
+        // phase B of tile it-1) and fetch the vertex ids of tile it+2
+        if (producer && it + 3 < nIt) prefetch_entry(it + 3);
+        gather(veNext);
+        const uint32_t veNext2 = (it + 2 < nIt) ? load_ve(it + 2) : 0xffffffffu;
+        PD_TICK(0)
+        // deferred phase C of the previous tile
         if (it > 0) {
             mbar_wait(&bar[2], (uint32_t)((it - 1) & 1));
-            local_phase_c(smem, vePrev, gtPrev, slotPrev, tid, b0, P);
+            PD_TICK(1)
+            local_phase_c<ROT_MODE == 1>(smem, vePrev, gtPrev, (blockIdx.x + (it - 1) * gridDim.x) * (unsigned)TILE_NLMAX, tid, b0, P);
         }
-        cp_async_wait_all();
-        __syncthreads();   // positions staged; every warp is past phase C of the previous tile
-
+        PD_TICK(2)
+        cp_async_wait_1();     // this thread's gather of tile `it` has landed (the one just issued may be in flight)
+        __syncthreads();       // positions staged; every warp is past phase C of the previous tile
+        PD_TICK(3)
+        mbar_wait(&bar[b], (uint32_t)((it >> 1) & 1));
+        PD_TICK(4)
         const uint4 hdr = *reinterpret_cast<const uint4*>(rec);      // nTets, nLocal, slotBase, abBytes
-        if (tid == 0) {    // the part C buffer is free now: stream this tile's incidence rows in
+        if (producer) {        // the part C buffer is free now: stream this tile's incidence rows in
             const uint4 h2 = *reinterpret_cast<const uint4*>(rec + 16);      // cBytes, nGroups, offLo, offHi
             mbar_expect_tx(&bar[2], h2.x);
             bulk_g2s_hint(smem + LOCAL_OFF_C, records + ((((unsigned long long)h2.w << 32) | h2.z) + hdr.w), h2.x, &bar[2], L2_EVICT_FIRST);
         }
+        // context of this tile's (deferred) phase C
+        vePrev = veCur; veCur = veNext; veNext = veNext2;
+        gtPrev = *reinterpret_cast<const uint32_t*>(rec + 32 + 4 * (tid >> 5));
 
-        // phase B: one tet per thread
-        if ((uint32_t)tid < hdr.x) {
+        // phase B, part 1: this thread's tet record and corner positions -> registers
+        const bool active = (uint32_t)tid < hdr.x;
+        float4 r0, r1, r2;
+        if (active) {
             const float4* tr = reinterpret_cast<const float4*>(rec + TILE_OFF_TETS + 48 * tid);
-            const float4 r0 = tr[0], r1 = tr[1], r2 = tr[2];
+            r0 = tr[0]; r1 = tr[1]; r2 = tr[2];
+        }
+        __syncthreads();       // every record of this AB buffer is in registers: refill it now, two tiles ahead
+        if (producer && it + 2 < nIt) fetch_ab(it + 2, *reinterpret_cast<const uint4*>(smem + LOCAL_OFF_TE + 16 * (it & 1)));
+
+        PD_TICK(5)
+        // phase B, part 2: one tet per thread
+        if (active) {
             const float B0 = r0.x, B1 = r0.y, B2 = r0.z, B3 = r0.w, B4 = r1.x, B5 = r1.y, B6 = r1.z, B7 = r1.w, B8 = r2.x;
             const float w = r2.y;
             const uint32_t c01 = __float_as_uint(r2.z), c23 = __float_as_uint(r2.w);
-            const uint8_t* qsb = smem + LOCAL_OFF_QS;
-            const float4 p0 = *reinterpret_cast<const float4*>(qsb + (c01 & 0xffffu));
-            const float4 p1 = *reinterpret_cast<const float4*>(qsb + (c01 >> 16));
-            const float4 p2 = *reinterpret_cast<const float4*>(qsb + (c23 & 0xffffu));
-            const float4 p3 = *reinterpret_cast<const float4*>(qsb + (c23 >> 16));
+            const uint8_t* qsb = smem + LOCAL_OFF_QS + b * LOCAL_QS_BYTES;
+            const float4 p0 = *reinterpret_cast<const float4*>(qsb + (c01 & 0x0ff0u));
+            const float4 p1 = *reinterpret_cast<const float4*>(qsb + ((c01 >> 16) & 0x0ff0u));
+            const float4 p2 = *reinterpret_cast<const float4*>(qsb + (c23 & 0x0ff0u));
+            const float4 p3 = *reinterpret_cast<const float4*>(qsb + ((c23 >> 16) & 0x0ff0u));
             // Ds columns = edges; F = Ds * DmInv  (row-major F[r][c] = sum_k Ds[r][k] B[k][c])
             const float d00 = p1.x - p0.x, d01 = p2.x - p0.x, d02 = p3.x - p0.x;
             const float d10 = p1.y - p0.y, d11 = p2.y - p0.y, d12 = p3.y - p0.y;
@@ -266,21 +344,24 @@ k_local(const uint8_t* __restrict__ records, const uint4* __restrict__ tileTab, 
             h0.y = __fsub_rn(__fsub_rn(-h1.y, h2.y), h3.y);
             h0.z = __fsub_rn(__fsub_rn(-h1.z, h2.z), h3.z);
             h0.w = h1.w = h2.w = h3.w = 0.f;
-            Hst[0] = h0; Hst[TILE_T] = h1; Hst[2 * TILE_T] = h2; Hst[3 * TILE_T] = h3;
+            // conflict-free columns from the layout's 8-colouring (layout.cpp:color_tile): col * 16 = (word >> 8) & 0x70
+            *reinterpret_cast<float4*>(Hline + ((c01 >> 8) & 0x70u)) = h0;
+            *reinterpret_cast<float4*>(Hline + TILE_HSTRIDE + ((c01 >> 24) & 0x70u)) = h1;
+            *reinterpret_cast<float4*>(Hline + 2 * TILE_HSTRIDE + ((c23 >> 8) & 0x70u)) = h2;
+            *reinterpret_cast<float4*>(Hline + 3 * TILE_HSTRIDE + ((c23 >> 24) & 0x70u)) = h3;
         }
-        // context of this tile's (deferred) phase C
-        vePrev = ve;
-        gtPrev = *reinterpret_cast<const uint32_t*>(rec + 32 + 4 * (tid >> 5));
-        slotPrev = hdr.z;
-        __syncthreads();   // H scratch complete; this AB buffer and the staged positions are free
-
-        if (it + 1 < nIt) {
-            if (tid == 0 && it + 2 < nIt) fetch_ab(it + 2);     // into the buffer just freed
-            ve = start_gather(it + 1);
-        }
+        if (PROF) { const long long now = clock64(); acc[6] += now - tk; tk = now; }     // math + H stores of this warp
+        __syncthreads();   // H scratch complete; this staging buffer is free
+        if (PROF) { const long long now = clock64(); acc[0] += now - tk; tk = now; }     // barrier 3 -> counted with the loop top
     }
+    if (PROF && tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) prof[8 * blockIdx.x + i] = (unsigned long long)acc[i];
+        prof[8 * blockIdx.x + 7] = (unsigned long long)nIt;
+    }
+#undef PD_TICK
     mbar_wait(&bar[2], (uint32_t)((nIt - 1) & 1));
-    local_phase_c(smem, vePrev, gtPrev, slotPrev, tid, b0, P);
+    local_phase_c<ROT_MODE == 1>(smem, vePrev, gtPrev, (blockIdx.x + (nIt - 1) * gridDim.x) * (unsigned)TILE_NLMAX, tid, b0, P);
 }
 
 // ------------------------------------------------------------------ global step (Jacobi + Chebyshev)
@@ -288,6 +369,8 @@ k_local(const uint8_t* __restrict__ records, const uint4* __restrict__ tileTab, 
 // b = ordered sum of the vertex's partial-sum slots (the first one already carries (M/h^2) s_old).
 // Arithmetic forms follow the reference's SASS: next = fma(-c,q,b)/(c+md) + q (IEEE division);
 // under-relaxation as one DFMA (the reference's `0.9 *` literal is a double); Chebyshev as one FFMA.
+template <bool BASE>      // BASE: the slots hold the elastic terms only and b0 is added here (product default);
+                           // otherwise the vertex's first slot already starts from b0 (faithful mode)
 __global__ void k_vertex_jacobi(int nV, const float4* __restrict__ qcur, const float4* __restrict__ qprev,
                                 float4* __restrict__ qnext, const float4* __restrict__ X0, const float4* __restrict__ b0,
                                 const float2* __restrict__ cc, const uint32_t* __restrict__ vslotPtr,
@@ -303,10 +386,11 @@ __global__ void k_vertex_jacobi(int nV, const float4* __restrict__ qcur, const f
         const float4 d = X0[v];
         bx = __fmul_rn(d.x, wdbc); by = __fmul_rn(d.y, wdbc); bz = __fmul_rn(d.z, wdbc);
     } else {
-        const uint32_t e0 = vslotPtr[v], e1 = vslotPtr[v + 1];
-        const float4 p0 = (e0 < e1) ? __ldg(&P[vslot[e0]]) : b0[v];    // a vertex without tets keeps b = (M/h^2) s_old
+        uint32_t e0 = vslotPtr[v];
+        const uint32_t e1 = vslotPtr[v + 1];
+        const float4 p0 = (BASE || e0 == e1) ? b0[v] : __ldg(&P[vslot[e0++]]);    // a vertex without tets keeps b = (M/h^2) s_old
         bx = p0.x; by = p0.y; bz = p0.z;
-        for (uint32_t e = e0 + 1; e < e1; ++e) {
+        for (uint32_t e = e0; e < e1; ++e) {
             const float4 p = __ldg(&P[vslot[e]]);
             bx = __fadd_rn(bx, p.x); by = __fadd_rn(by, p.y); bz = __fadd_rn(bz, p.z);
         }
@@ -327,6 +411,7 @@ __global__ void k_vertex_jacobi(int nV, const float4* __restrict__ qcur, const f
 }
 
 // right-hand side for the direct / CG global solves: b = c*s_old + sum of partials (R, not R-F)
+template <bool BASE>
 __global__ void k_vertex_rhs(int nV, const float4* __restrict__ X0, const float4* __restrict__ b0, const float2* __restrict__ cc,
                              const uint32_t* __restrict__ vslotPtr, const uint32_t* __restrict__ vslot,
                              const float4* __restrict__ P, float wdbc, float4* __restrict__ rhs)
@@ -338,10 +423,11 @@ __global__ void k_vertex_rhs(int nV, const float4* __restrict__ X0, const float4
         const float4 d = X0[v];
         bx = __fmul_rn(d.x, wdbc); by = __fmul_rn(d.y, wdbc); bz = __fmul_rn(d.z, wdbc);
     } else {
-        const uint32_t e0 = vslotPtr[v], e1 = vslotPtr[v + 1];
-        const float4 p0 = (e0 < e1) ? __ldg(&P[vslot[e0]]) : b0[v];    // a vertex without tets keeps b = (M/h^2) s_old
+        uint32_t e0 = vslotPtr[v];
+        const uint32_t e1 = vslotPtr[v + 1];
+        const float4 p0 = (BASE || e0 == e1) ? b0[v] : __ldg(&P[vslot[e0++]]);    // a vertex without tets keeps b = (M/h^2) s_old
         bx = p0.x; by = p0.y; bz = p0.z;
-        for (uint32_t e = e0 + 1; e < e1; ++e) {
+        for (uint32_t e = e0; e < e1; ++e) {
             const float4 p = __ldg(&P[vslot[e]]);
             bx = __fadd_rn(bx, p.x); by = __fadd_rn(by, p.y); bz = __fadd_rn(bz, p.z);
         }

@@ -253,6 +253,7 @@ __device__ __forceinline__ bool rotation_newton(const Mat3& Fm, Mat3& Rm)
 template <int ROT_MODE>
 __device__ __forceinline__ void corotation(const Mat3& F, Mat3& R)
 {
+    if (ROT_MODE == 2) { R = F; return; }     // measurement only (scripts/experiments): no projection at all
     if (ROT_MODE == 0) {
         if (rotation_newton(F, R)) return;
     }

@@ -67,7 +67,7 @@ def build(X, Tet, mu, reorder=True):
     B, V0 = rest_shape(X, Tet)
     Br = B[tet_order].reshape(nT, 9); wr = (np.abs(V0) * mu.astype(np.float32))[tet_order]
     # tiles
-    tile_tet_start = [0]; tile_rec_off = [0]; recs = []; slot = 0
+    tile_tet_start = [0]; tile_rec_off = [0]; tiles = []; slot = 0; vlists = []
     vslots = [[] for _ in range(nV)]
     t0 = 0; max_local = 0
     seen_before = np.zeros(nV, bool)            # vertex already has a slot in an earlier tile
@@ -97,39 +97,29 @@ def build(X, Tet, mu, reorder=True):
         trec = np.zeros((nTets, 12), np.uint32)
         trec[:, :9] = Br[t0:t1].view(np.uint32)
         trec[:, 9] = wr[t0:t1].view(np.uint32)
-        trec[:, 10] = (cidx[:, 0] * 16) | ((cidx[:, 1] * 16) << 16)
-        trec[:, 11] = (cidx[:, 2] * 16) | ((cidx[:, 3] * 16) << 16)
-        # transposed incidence rows: entry e of local vertex l -> row g_base[l//32] + e//2, lane l%32, half e%2
-        incT = np.full((nRows, 32, 2), TILE_ZERO_OFF, np.uint16)
+        # incidence list of every tile-local vertex: ascending (tet, corner)
         owner = cidx.reshape(-1)
-        tl = np.repeat(np.arange(nTets), 4); k = np.tile(np.arange(4), nTets)
-        swz = tl ^ ((tl >> 3) & 7)
-        ent = (k * TILE_HSTRIDE + swz * 16).astype(np.uint16)
-        o = np.argsort(owner, kind="stable")     # per vertex, ascending (tet, corner)
-        ow = owner[o]
+        o = np.argsort(owner, kind="stable")
         start = np.concatenate([[0], np.cumsum(np.bincount(owner, minlength=nLocal))])
-        e = np.arange(len(o)) - start[ow]
-        incT[g_base[ow // 32] + e // 2, ow % 32, e % 2] = ent[o]
+        inc = [[(int(x) // 4, int(x) % 4) for x in o[start[l]:start[l + 1]]] for l in range(nLocal)]
         vlist = vl.astype(np.uint32)
         first = ~seen_before[vl]
         vlist = np.where(first, vlist | np.uint32(TILE_OWNER_BIT), vlist).astype(np.uint32)
         seen_before[vl] = True
-        ab_bytes = TILE_OFF_TETS + 48 * nTets + rup(4 * nLocal, 16); c_bytes = 128 * nRows
+        ab_bytes = TILE_OFF_TETS + 48 * nTets; c_bytes = 128 * nRows
         base = tile_rec_off[-1]
         gtab = np.zeros(12, np.uint32)
         for g in range(nGroups):
             gtab[g] = int(g_base[g]) | (g_rows[g] << 16)
-        rec = bytearray()
-        rec += np.array([nTets, nLocal, slot, ab_bytes, c_bytes, nGroups, base & 0xffffffff, base >> 32], np.uint32).tobytes()
-        rec += gtab.tobytes()
-        rec += trec.tobytes()
-        rec += vlist.tobytes() + b"\0" * (rup(4 * nLocal, 16) - 4 * nLocal)
-        assert len(rec) == ab_bytes
-        rec += incT.tobytes()
-        assert len(rec) == ab_bytes + c_bytes
-        recs.append(bytes(rec))
+        slot_base = len(tiles) * TILE_NLMAX       # padded slots: tile * TILE_NLMAX + tile-local vertex
+        head = np.array([nTets, nLocal, slot_base, ab_bytes, c_bytes, nGroups, base & 0xffffffff, base >> 32], np.uint32).tobytes() + gtab.tobytes()
+        # the H-scratch columns (bits 12..14 of the corner words, and the incidence entries built from them) are
+        # the builder's free choice, constrained only by the conflict-freeness the tests check -> canonical form
+        tiles.append(dict(head=head, tet40=trec[:, :10].copy(), corners=cidx.astype(np.int64), inc=inc,
+                          g_base=g_base, g_rows=g_rows, ab_bytes=ab_bytes, c_bytes=c_bytes, base=base))
+        vlists.append(np.concatenate([vlist, np.full(TILE_NLMAX - nLocal, 0xffffffff, np.uint32)]))   # slot-indexed, padded
         for l, v in enumerate(vl):
-            vslots[int(v)].append(slot + l)
+            vslots[int(v)].append(slot_base + l)
         slot += nLocal
         t0 = t1
         tile_tet_start.append(t0); tile_rec_off.append(base + ab_bytes + c_bytes)
@@ -138,9 +128,56 @@ def build(X, Tet, mu, reorder=True):
     vslot = np.array([s for ss in vslots for s in ss], np.uint32)
     return dict(tet_order=tet_order, vert_order=vert_order, tet_new=tet_new,
                 tile_tet_start=np.array(tile_tet_start, np.uint32), tile_rec_off=np.array(tile_rec_off, np.uint64),
-                records=np.frombuffer(b"".join(recs), np.uint8), vslot_ptr=vslot_ptr, vslot=vslot,
-                num_tiles=len(recs), num_slots=slot, max_local=max_local, DmInv=B, V0=V0)
+                tiles=tiles, vslot_ptr=vslot_ptr, vslot=vslot, vlist=np.concatenate(vlists).astype(np.uint32),
+                num_tiles=len(tiles), num_slots=slot, max_local=max_local, DmInv=B, V0=V0)
 
 
 def partition_vertices(nV, world):
     return np.array([(nV * r) // world for r in range(world + 1)], np.int32)
+
+
+def decode_and_check_records(records, tile_rec_off, tiles):
+    """Decode the builder's packed tile records and compare them with the canonical tiles of build():
+    header, group table, DmInv/w bits and corner indices bit for bit; the incidence rows entry by entry
+    after mapping every H-scratch offset back to its (tet, corner); plus the bank-conflict freedom of the
+    8-colouring (every quarter-warp STS.128 of phase B and LDS.128 of phase C hits 8 distinct 16-byte columns)."""
+    rec = np.asarray(records, np.uint8)
+    for ti, T in enumerate(tiles):
+        base = int(tile_rec_off[ti])
+        assert base == T["base"] and int(tile_rec_off[ti + 1]) == base + T["ab_bytes"] + T["c_bytes"]
+        assert rec[base:base + 80].tobytes() == T["head"], ti
+        nT = T["tet40"].shape[0]
+        tr = rec[base + 80:base + 80 + 48 * nT].view(np.uint32).reshape(nT, 12)
+        assert np.array_equal(tr[:, :10], T["tet40"]), ti
+        halves = np.stack([tr[:, 10] & 0xffff, tr[:, 10] >> 16, tr[:, 11] & 0xffff, tr[:, 11] >> 16], 1).astype(np.int64)
+        assert np.array_equal((halves >> 4) & 0xff, T["corners"]), ti
+        assert ((halves & 0x800f) == 0).all()
+        col = (halves >> 12) & 7
+        # stores: the 8 tets of a quarter-warp use 8 distinct columns per corner
+        for q in range(0, nT, 8):
+            for k in range(4):
+                c = col[q:q + 8, k]
+                assert len(set(c.tolist())) == len(c), (ti, q, k)
+        nRows = T["c_bytes"] // 128
+        incT = rec[base + T["ab_bytes"]:base + T["ab_bytes"] + T["c_bytes"]].view(np.uint16).reshape(nRows, 32, 2).astype(np.int64)
+        # loads: per (row, half, quarter-warp) distinct addresses fall into distinct columns
+        colsT = (incT // 16) % 8
+        for r in range(nRows):
+            for h in range(2):
+                for qw in range(4):
+                    a = incT[r, 8 * qw:8 * qw + 8, h]; c = colsT[r, 8 * qw:8 * qw + 8, h]
+                    assert len(set(zip(a.tolist(), c.tolist()))) == len(set(c.tolist())), (ti, r, h, qw)
+        assert ((incT % 16) == 0).all() and (incT < TILE_ZERO_OFF + 128).all()
+        for l, lst in enumerate(T["inc"]):
+            g, lane = l // 32, l % 32
+            rows = T["g_rows"][g]
+            ent = incT[T["g_base"][g]:T["g_base"][g] + rows, lane, :].reshape(-1)
+            assert len(lst) <= len(ent)
+            assert (ent[len(lst):] >= TILE_ZERO_OFF).all(), (ti, l)
+            for e, (t, k) in enumerate(lst):
+                assert ent[e] == k * TILE_HSTRIDE + ((t & ~7) | int(col[t, k])) * 16, (ti, l, e)
+        # lanes beyond the tile's vertices hold only pads
+        nLocal = len(T["inc"])
+        for l in range(nLocal, 32 * len(T["g_rows"])):
+            g, lane = l // 32, l % 32
+            assert (incT[T["g_base"][g]:T["g_base"][g] + T["g_rows"][g], lane, :] >= TILE_ZERO_OFF).all()

@@ -27,7 +27,11 @@ import meshes
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 TOL_FAITHFUL = 2e-5
-TOL_DEFAULT_C1 = 2e-4
+# C1 in free fall: the reference's approximate SVD (svd3_cuda.h, rsqrt-based Givens angles) drifts from exact
+# arithmetic by 1.8e-4 at step 40 (profiles/r1_noise_floor.txt, column orc64-refA); the default rotation path
+# (Newton polar, accurate to float rounding) sits on the exact side of that gap, 2.0e-4 from the reference.
+# The faithful path (rot_mode=1) is held to TOL / bit-exactness instead.
+TOL_DEFAULT_C1 = 2.5e-4
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 

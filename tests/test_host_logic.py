@@ -118,10 +118,11 @@ def _check_layout(pd, sc, reorder=True):
     a = sc.arrays()
     Lc = sc.layout(reorder)
     Lo = LO.build(a["X"], a["Tet"], a["mu"], reorder)
-    for k in ["tet_order", "vert_order", "tet_new", "tile_tet_start", "tile_rec_off", "vslot_ptr", "vslot"]:
+    for k in ["tet_order", "vert_order", "tet_new", "tile_tet_start", "tile_rec_off", "vslot_ptr", "vslot", "vlist"]:
         assert np.array_equal(getattr(Lc, k), Lo[k]), k
     assert (Lc.num_tiles, Lc.num_slots, Lc.max_local) == (Lo["num_tiles"], Lo["num_slots"], Lo["max_local"])
-    assert Lc.records.tobytes() == Lo["records"].tobytes()       # incl. DmInv/w bits and incidence CSR
+    assert Lc.record_bytes == int(Lc.tile_rec_off[-1])
+    LO.decode_and_check_records(Lc.records, Lc.tile_rec_off, Lo["tiles"])    # incl. DmInv/w bits and the incidence CSR
     return Lc
 
 
@@ -147,7 +148,9 @@ def test_layout_invariants(pd, assets):
     L = sc.layout()
     assert sorted(L.tet_order.tolist()) == list(range(nT)) and sorted(L.vert_order.tolist()) == list(range(nV))
     # every (tile, local vertex) slot appears exactly once in the vertex->slot CSR, ascending per vertex
-    assert sorted(L.vslot.tolist()) == list(range(L.num_slots))
+    used = np.flatnonzero(L.vlist != 0xffffffff)          # slots are padded per tile: tile * 256 + local vertex
+    assert sorted(L.vslot.tolist()) == used.tolist() and len(used) == L.num_slots
+    assert np.array_equal((L.vlist[L.vslot] & 0x7fffffff), np.repeat(np.arange(nV), np.diff(L.vslot_ptr.astype(np.int64))))
     for v in range(0, nV, 997):
         s = L.vslot[L.vslot_ptr[v]:L.vslot_ptr[v + 1]]
         assert (np.diff(s.astype(np.int64)) > 0).all() and len(s) >= 1
