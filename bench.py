@@ -127,6 +127,7 @@ def cpu_baseline(workload_iters, threads):
 def dist_setup(n_gpus):
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's "NCCL version ..." banner goes to stdout and would break the one-JSON-line contract
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -154,18 +155,33 @@ def run_b200(args):
     import torch
     pd = importlib.import_module("soft-body-simulation-cuda_b200")
     rank, world, local = dist_setup(args.gpus)
-    if world > 1:
-        raise SystemExit("multi-GPU partitioned PD step is not wired into bench.py yet (round 1: N=1)")
     torch.cuda.set_device(local)
     sc, p = make_scene(pd, args.workload)
     nV, nT = sc.counts()[:2]
     iters = p["num_iterations"]
-    eng = pd.PdSolver(sc, device=local, rot_mode=args.rot_mode, ctas_per_sm=args.ctas_per_sm)
+    # N > 1: the mesh is vertex-partitioned, one rank per GPU; every rank builds the same global layout and keeps
+    # the tiles that touch its vertices.  torch.distributed (NCCL) carries only the setup
+    # (window handles) and the timing reductions; the per-iteration halo goes over NVLink peer memory.
+    eng = pd.PdSolver(sc, device=local, rot_mode=args.rot_mode, ctas_per_sm=args.ctas_per_sm, rank=rank, world=world)
+    dist_info = None
+    if world > 1:
+        import torch.distributed as dist
+        h = torch.from_numpy(eng.window_handle()).cuda()
+        allh = [torch.zeros_like(h) for _ in range(world)]
+        dist.all_gather(allh, h)
+        eng.connect(torch.stack(allh).cpu().numpy())
+        di = eng.dist_info()
+        t = torch.tensor([di["num_owned"], di["num_ghosts"], di["num_tets_local"], di["num_push"]], dtype=torch.int64, device="cuda")
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        allt = torch.stack(allt).cpu().numpy()
+        dist_info = {"owned_verts_per_rank": allt[:, 0].tolist(), "ghost_verts_per_rank": allt[:, 1].tolist(),
+                     "tets_evaluated_per_rank": allt[:, 2].tolist(), "pushed_verts_per_rank": allt[:, 3].tolist(),
+                     "redundant_tet_fraction": float(allt[:, 2].sum() / nT - 1.0)}
     X0 = sc.arrays()["X"]
     V0 = initial_velocity(X0)
     eng.upload(V=V0)
     info = eng.info()
-    launches_per_step = 2 + 2 * iters
 
     # ---- device-resident timing: inputs already in HBM, K steps bracketed by sync + events
     for _ in range(args.warmup):
@@ -181,10 +197,14 @@ def run_b200(args):
     launches = eng.GetPerformanceData()[1].kernel_launches - perf0
 
     # ---- kernel-level roofline, measured live with CUDA events on the engine's stream
+    barrier(world)
     t_local_ms, t_vertex_ms = eng.time_kernels(reps=20)
     peak, peak_src = peaks()
-    bytes_local = 56.0 * nT + 24.0 * nV
-    bytes_iter = 56.0 * nT + 68.0 * nV
+    # algorithmic bytes of what THIS rank's launch processes (56 B/tet + 24 B/vertex local, 68 B/vertex global)
+    nT_launch = nT if world == 1 else eng.dist_info()["num_tets_local"]
+    nV_launch = nV if world == 1 else eng.dist_info()["num_owned"]
+    bytes_local = 56.0 * nT_launch + 24.0 * nV_launch
+    bytes_iter = 56.0 * nT_launch + 68.0 * nV_launch
     ach_local = bytes_local / (t_local_ms * 1e-3) / 1e9
     ach_iter = bytes_iter / ((t_local_ms + t_vertex_ms) * 1e-3) / 1e9
 
@@ -208,8 +228,13 @@ def run_b200(args):
     finite = bool(np.isfinite(final).all())
     for b in bufs:
         pd.lib().pd_free_pinned(b)
+    halo_ok = eng.dist_status() == 0 if world > 1 else True
+    barrier(world)
 
     if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
         return
     value = nT * iters / (ms_step * 1e-3) / 1e6
     line = {
@@ -220,21 +245,25 @@ def run_b200(args):
         "config": {"workload": args.workload, "description": WORKLOADS[args.workload][2], "num_verts": nV, "num_tets": nT,
                    "pd_iterations_per_step": iters, "global_solver": "chebyshev-jacobi", "dt": DT, "gravity": GRAVITY, "mu": MU,
                    "initial_velocity": "0.5*sin(x/7) y^", "l2": f"inputs larger than L2: tile stream {info['tile_stream_bytes'] / 1e6:.0f} MB per iteration, no flush needed",
-                   "finite": finite},
+                   "finite": finite, "parallelism": "single GPU" if world == 1 else f"vertex partition over {world} GPUs, tile-replicated boundary, NVLink peer-memory halo push + flags per PD iteration",
+                   "multi_gpu": dist_info, "halo_ok": halo_ok},
         "clocks": clocks,
         "e2e": {"value": nT * iters / (e2e_ms * 1e-3) / 1e6, "unit": "Mtet-updates/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 3 * nbytes, "d2h_bytes_per_step": 3 * nbytes, "steps": e2e_steps,
-                "api": "pd_step_host (include/pd_b200.h): pinned host X,V,XTilde in and out every step"},
+                "api": "pd_step_host (include/pd_b200.h): pinned host X,V,XTilde in and out every step (every rank moves the full arrays)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_local (local step: F, rotation, ordered RHS partials)",
+        "roofline": {"bound": "hbm", "kernel": "k_local (local step: F, rotation, ordered RHS partials)" + ("" if world == 1 else " -- rank 0's launch"),
                      "achieved": ach_local, "peak": peak, "unit": "GB/s", "frac": ach_local / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_local, "launch_ms": t_local_ms,
                      "fused_iteration": {"achieved": ach_iter, "frac": ach_iter / peak, "algorithmic_bytes": bytes_iter,
                                          "ms": t_local_ms + t_vertex_ms, "vertex_kernel_ms": t_vertex_ms},
                      "frac_of_8TBs_nominal": ach_local / 8000.0},
-        "cpu_baseline": cpu_baseline(iters, os.cpu_count() or 1) if not args.no_cpu_baseline else None,
+        "cpu_baseline": cpu_baseline(iters, os.cpu_count() or 1) if (not args.no_cpu_baseline and world == 1) else None,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 def run_reference(args):

@@ -31,6 +31,7 @@ extern "C" {
 typedef struct pd_engine pd_engine;   /* one SimulationCUDAContext::Impl<float> + PdSolver        */
 typedef struct pd_scene pd_scene;     /* host-side merged scene (DataLoader output), no GPU needed */
 typedef struct pd_layout pd_layout;   /* host-side device-layout builder output, no GPU needed     */
+typedef struct pd_rank_plan pd_rank_plan; /* host-side multi-GPU plan of one rank, no GPU needed    */
 
 enum pd_status {
     PD_OK = 0,
@@ -81,6 +82,7 @@ typedef struct {
     int reorder;              /* 1 (default) Morton tet order + first-touch vertex renumbering */
     int use_graph;            /* 1 (default) one CUDA graph per step                          */
     int ctas_per_sm;          /* 0 = occupancy query                                          */
+    int rank, world;          /* multi-GPU: this engine is rank `rank` of `world` (default 0 of 1); one process per GPU */
 } pd_engine_options;
 
 /* PdSolver::GetPerformanceData (solver.h:20, pdSolver.cu:26): the four named counters, ms */
@@ -129,6 +131,22 @@ int pd_layout_get(const pd_layout*, uint32_t* tet_order, uint32_t* vert_order, u
                   uint32_t* vslot_ptr, uint32_t* vslot, uint32_t* vlist);
 int pd_morton_keys(const float* X, const uint32_t* Tet, int num_tets, uint32_t* keys);
 int pd_partition_vertices(int num_verts, int world, int* vbeg /* world+1 */);
+/* host-side prefactorisation of the small-mesh path: sparse Cholesky A = L L^T of a symmetric CSR matrix in the given
+ * order (replaces cusolverSpXcsrcholAnalysis/Factor, cholesky.cu:152-157, and Eigen::SimplicialCholesky, pdSolver.cu:103).
+ * L is returned by rows (ascending columns, diagonal last); free the three arrays with pd_free. */
+int pd_cholesky_factor(int n, const int* rowptr, const int* col, const float* val, int* nnz_l, int** lptr, int** lcol, float** lval);
+
+/* ---- multi-GPU plan (host only) : vertex partition, tile selection, ghosts, push lists --- new work,
+ * the reference is single-GPU.  Checked bit for bit across ranks by the gloo tests. */
+pd_rank_plan* pd_rank_plan_build(const pd_layout* global_layout, int world, int rank);
+void pd_rank_plan_free(pd_rank_plan*);
+/* counts[7] = {num_owned, num_ghosts, num_tiles, num_neighbours, num_push, first_owned_vertex (renumbered id),
+ *              num_interior_tiles (they come first in `tiles`; only the tiles after them read ghost positions)} */
+int pd_rank_plan_counts(const pd_rank_plan*, int counts[7]);
+int pd_rank_plan_get(const pd_rank_plan*, uint32_t* tiles, uint32_t* ghosts, int* neighbours, int* n_loc_of /* world */,
+                     uint32_t* push_src, uint32_t* push_dst, int* push_rank);
+/* the rank's own layout (selected tiles, local vertex ids); vert_order maps local -> ORIGINAL vertex ids */
+pd_layout* pd_rank_layout(const pd_layout* global_layout, const pd_rank_plan*);
 
 /* ---- engine : PdSolver behind SimulationCUDAContext -------------------------------------- */
 /* PdSolver::PdSolver + FEMSolver ctor (pdSolver.cu:22-27, femSolver.cu:6-17) */
@@ -163,6 +181,13 @@ int pd_step_host(pd_engine*, int n_steps, const float* X_in, const float* V_in, 
 int pd_update_device(pd_engine*, int n_steps, float* dX, float* dV, float* dXTilde);
 /* setup products for parity checks (original numbering): matrix_diag, massDt_2s, DmInv(9/tet,row-major), V0 */
 int pd_get_setup(pd_engine*, float* matrix_diag, float* mass_dt2, float* DmInv, float* V0);
+/* the scalar system matrix A^ = M/h^2 + sum_t w_t S^T (DmInv^T G)^T (DmInv^T G) S that SolverPrepare assembles as COO
+ * (pdSolver.cu:62-77, pdUtil.cu:9-54), deduplicated CSR with ascending columns, in the engine's RENUMBERED vertex ids
+ * (pd_layout_get: vert_order maps renumbered -> original).  Call with NULL arrays to get nnz first. */
+int pd_get_system_matrix(pd_engine*, int* nnz, int* rowptr, int* col, float* val);
+/* direct / CG modes: computeError of the last PD iteration (pdSolver.cu:243-253) and the PD iterations the last step ran
+ * before sqrt(err) < tol (pdSolver.cu:164) */
+int pd_get_solve_stats(pd_engine*, float* err, int* pd_iterations_last_step);
 /* measurement helpers used by bench.py: average device time (ms) of one launch of the local /
  * vertex kernel over `reps` back-to-back launches, CUDA events on the engine's stream */
 int pd_time_kernels(pd_engine*, int reps, float* local_ms, float* vertex_ms);
@@ -172,6 +197,18 @@ int pd_time_kernels(pd_engine*, int reps, float* local_ms, float* vertex_ms);
 int pd_profile_local(pd_engine*, unsigned long long* out);
 int pd_engine_info(const pd_engine*, int* num_verts, int* num_tets, int* num_tiles, uint32_t* num_slots,
                    size_t* tile_stream_bytes, size_t* device_bytes, int* local_grid);
+/* ---- multi-GPU engine (options.world > 1): every rank creates its engine from the SAME scene, exchanges the
+ * 64-byte window handles (e.g. torch.distributed.all_gather) and connects; pd_step then runs the ranks in
+ * lock step through halo flags in peer memory (no host synchronisation, no NCCL on the data path).
+ * pd_download returns the rank's OWN vertices and zeros elsewhere (sum the ranks' arrays to combine). */
+int pd_dist_window_handle(pd_engine*, void* out64);                       /* cudaIpcMemHandle_t */
+int pd_dist_connect(pd_engine*, const void* handles /* world x 64 bytes, rank order */);
+int pd_dist_connect_local(pd_engine* const* engines, int n);              /* all ranks in one process (tests) */
+int pd_dist_step_lockstep(pd_engine* const* engines, int n, int n_steps); /* one process drives all ranks phase by phase */
+int pd_dist_status(pd_engine*, unsigned int* halo_wait_timed_out);
+/* info[6] = {num_owned, num_ghosts, num_neighbours, num_push, tets evaluated here, tiles evaluated here} */
+int pd_dist_info(const pd_engine*, int info[6]);
+
 /* test hook: the corotational projection (pdUtil.cu:112-122) of n row-major 3x3 matrices on
  * `device`; rot_mode as in pd_engine_options; used_fast (may be NULL) reports the path taken */
 int pd_rotation_batch(int device, int rot_mode, int n, const float* F, float* R, int* used_fast);

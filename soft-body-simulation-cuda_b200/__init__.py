@@ -48,7 +48,7 @@ class pd_scene_desc(C.Structure):
 
 class pd_engine_options(C.Structure):
     _fields_ = [("device", C.c_int), ("rot_mode", C.c_int), ("reorder", C.c_int), ("use_graph", C.c_int),
-                ("ctas_per_sm", C.c_int)]
+                ("ctas_per_sm", C.c_int), ("rank", C.c_int), ("world", C.c_int)]
 
 
 class pd_perf(C.Structure):
@@ -87,6 +87,18 @@ SYMBOLS = {
     "pd_layout_get": (_I, [_VP] * 10),
     "pd_morton_keys": (_I, [_VP, _VP, _I, _VP]),
     "pd_partition_vertices": (_I, [_I, _I, _VP]),
+    "pd_cholesky_factor": (_I, [_I, _VP, _VP, _VP, _PI, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
+    "pd_rank_plan_build": (_VP, [_VP, _I, _I]),
+    "pd_rank_plan_free": (None, [_VP]),
+    "pd_rank_plan_counts": (_I, [_VP, _VP]),
+    "pd_rank_plan_get": (_I, [_VP] * 8),
+    "pd_rank_layout": (_VP, [_VP, _VP]),
+    "pd_dist_window_handle": (_I, [_VP, _VP]),
+    "pd_dist_connect": (_I, [_VP, _VP]),
+    "pd_dist_connect_local": (_I, [_VP, _I]),
+    "pd_dist_step_lockstep": (_I, [_VP, _I, _I]),
+    "pd_dist_status": (_I, [_VP, _VP]),
+    "pd_dist_info": (_I, [_VP, _VP]),
     "pd_create": (_VP, [_VP, C.POINTER(pd_engine_options)]),
     "pd_create_from_json": (_VP, [_CP, _CP, _CP, C.POINTER(pd_engine_options)]),
     "pd_destroy": (None, [_VP]),
@@ -104,6 +116,8 @@ SYMBOLS = {
     "pd_step_host": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "pd_update_device": (_I, [_VP, _I, _VP, _VP, _VP]),
     "pd_get_setup": (_I, [_VP, _VP, _VP, _VP, _VP]),
+    "pd_get_system_matrix": (_I, [_VP, _PI, _VP, _VP, _VP]),
+    "pd_get_solve_stats": (_I, [_VP, _PF, _PI]),
     "pd_time_kernels": (_I, [_VP, _I, _PF, _PF]),
     "pd_profile_local": (_I, [_VP, _VP]),
     "pd_engine_info": (_I, [_VP, _PI, _PI, _PI, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), _PI]),
@@ -255,11 +269,11 @@ class Scene:
 class Layout:
     """Device layout (tet order, vertex renumbering, tile records, slot CSR), host only."""
 
-    def __init__(self, scene, reorder=True):
-        self._h = lib().pd_layout_build(scene._h, int(reorder))
+    def __init__(self, scene, reorder=True, handle=None, counts=None):
+        self._h = handle if handle is not None else lib().pd_layout_build(scene._h, int(reorder))
         if not self._h:
             raise PdError(_err())
-        nV, nT, _, _ = scene.counts()
+        nV, nT = counts if counts is not None else scene.counts()[:2]
         nt, ns, rb, ml = C.c_int(), C.c_uint32(), C.c_size_t(), C.c_int()
         _check(lib().pd_layout_counts(self._h, C.byref(nt), C.byref(ns), C.byref(rb), C.byref(ml)))
         self.num_tiles, self.num_slots, self.record_bytes, self.max_local = nt.value, ns.value, rb.value, ml.value
@@ -279,17 +293,82 @@ class Layout:
             self._h = None
 
 
+class RankPlan:
+    """Multi-GPU plan of one rank (host only): tiles evaluated, ghosts, neighbours, push lists."""
+
+    def __init__(self, layout, world, rank):
+        self._h = lib().pd_rank_plan_build(layout._h, world, rank)
+        if not self._h:
+            raise PdError(_err())
+        self.world, self.rank = world, rank
+        c = np.zeros(7, np.int32)
+        _check(lib().pd_rank_plan_counts(self._h, _p(c)))
+        self.num_owned, self.num_ghosts, self.num_tiles, self.num_neighbours, self.num_push, self.first_owned, self.num_interior_tiles = [int(x) for x in c]
+        self.tiles = np.zeros(self.num_tiles, np.uint32); self.ghosts = np.zeros(self.num_ghosts, np.uint32)
+        self.neighbours = np.zeros(self.num_neighbours, np.int32); self.n_loc_of = np.zeros(world, np.int32)
+        self.push_src = np.zeros(self.num_push, np.uint32); self.push_dst = np.zeros(self.num_push, np.uint32)
+        self.push_rank = np.zeros(self.num_push, np.int32)
+        _check(lib().pd_rank_plan_get(self._h, _p(self.tiles), _p(self.ghosts), _p(self.neighbours), _p(self.n_loc_of),
+                                      _p(self.push_src), _p(self.push_dst), _p(self.push_rank)))
+
+    def local_layout(self, global_layout):
+        h = lib().pd_rank_layout(global_layout._h, self._h)
+        if not h:
+            raise PdError(_err())
+        nT = int(np.diff(global_layout.tile_tet_start.astype(np.int64))[self.tiles].sum())
+        return Layout(None, handle=h, counts=(self.num_owned + self.num_ghosts, nT))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.pd_rank_plan_free(self._h)
+            self._h = None
+
+
+def dist_connect_local(engines):
+    """All ranks of a multi-GPU engine inside ONE process (tests): wire the exchange windows directly."""
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    _check(lib().pd_dist_connect_local(arr, len(engines)))
+
+
+def dist_step_lockstep(engines, n_steps=1):
+    """One host thread drives all ranks phase by phase (see pd_dist_step_lockstep)."""
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    _check(lib().pd_dist_step_lockstep(arr, len(engines), n_steps))
+
+
 class PdSolver:
     """PdSolver behind SimulationCUDAContext, on one B200 (pdSolver.h:12-44, simulationContext.h:17-84)."""
 
     SolverType = {"Jacobi": PD_JACOBI, "CuSolverCholesky": PD_CHOLESKY, "EigenCholesky": PD_CHOLESKY, "PCGJacobi": PD_PCG_JACOBI}
 
-    def __init__(self, scene, device=0, rot_mode=0, reorder=1, use_graph=1, ctas_per_sm=0):
-        o = pd_engine_options(device, rot_mode, reorder, use_graph, ctas_per_sm)
+    def __init__(self, scene, device=0, rot_mode=0, reorder=1, use_graph=1, ctas_per_sm=0, rank=0, world=1):
+        o = pd_engine_options(device, rot_mode, reorder, use_graph, ctas_per_sm, rank, world)
         self._h = lib().pd_create(scene._h, C.byref(o))
         if not self._h:
             raise PdError(_err())
-        self.num_verts, self.num_tets = scene.counts()[:2]
+        self.num_verts, self.num_tets = scene.counts()[:2]      # GLOBAL counts: host arrays always cover the whole scene
+        self.rank, self.world = rank, world
+
+    # --- multi-GPU plumbing (world > 1)
+    def window_handle(self):
+        h = np.zeros(64, np.uint8)
+        _check(lib().pd_dist_window_handle(self._h, _p(h)))
+        return h
+
+    def connect(self, handles):
+        """handles: (world, 64) uint8, rank order -- e.g. torch.distributed.all_gather of window_handle()"""
+        h = np.ascontiguousarray(handles, np.uint8).reshape(self.world, 64)
+        _check(lib().pd_dist_connect(self._h, _p(h)))
+
+    def dist_status(self):
+        s = C.c_uint()
+        _check(lib().pd_dist_status(self._h, C.byref(s)))
+        return s.value
+
+    def dist_info(self):
+        a = np.zeros(6, np.int32)
+        _check(lib().pd_dist_info(self._h, _p(a)))
+        return dict(zip(["num_owned", "num_ghosts", "num_neighbours", "num_push", "num_tets_local", "num_tiles_local"], [int(x) for x in a]))
 
     def close(self):
         if getattr(self, "_h", None) and _lib is not None:
@@ -359,6 +438,20 @@ class PdSolver:
         _check(lib().pd_get_setup(self._h, _p(md), _p(c), _p(B), _p(V0)))
         return md, c, B.reshape(-1, 3, 3), V0
 
+    def system_matrix(self):
+        """A^ as (rowptr, col, val) in the engine's renumbered vertex ids (scipy.sparse.csr_matrix-ready)."""
+        nnz = C.c_int()
+        _check(lib().pd_get_system_matrix(self._h, C.byref(nnz), None, None, None))
+        n = self.dist_info()["num_owned"] + self.dist_info()["num_ghosts"]
+        rp = np.zeros(n + 1, np.int32); col = np.zeros(nnz.value, np.int32); val = np.zeros(nnz.value, np.float32)
+        _check(lib().pd_get_system_matrix(self._h, C.byref(nnz), _p(rp), _p(col), _p(val)))
+        return rp, col, val
+
+    def solve_stats(self):
+        err, it = C.c_float(), C.c_int()
+        _check(lib().pd_get_solve_stats(self._h, C.byref(err), C.byref(it)))
+        return err.value, it.value
+
     def time_kernels(self, reps=20):
         a, b = C.c_float(), C.c_float()
         _check(lib().pd_time_kernels(self._h, reps, C.byref(a), C.byref(b)))
@@ -376,6 +469,20 @@ class PdSolver:
         _check(lib().pd_engine_info(self._h, C.byref(nv), C.byref(nt), C.byref(ntl), C.byref(ns), C.byref(sb), C.byref(db), C.byref(lg)))
         return dict(num_verts=nv.value, num_tets=nt.value, num_tiles=ntl.value, num_slots=ns.value,
                     tile_stream_bytes=sb.value, device_bytes=db.value, local_grid=lg.value)
+
+
+def cholesky_factor(rowptr, col, val):
+    """Host-side sparse Cholesky (no GPU): returns L by rows (rowptr, col, val), diagonal last in every row."""
+    rowptr = np.ascontiguousarray(rowptr, np.int32); col = np.ascontiguousarray(col, np.int32); val = np.ascontiguousarray(val, np.float32)
+    n = rowptr.shape[0] - 1
+    nnz = C.c_int(); lp, lc, lv = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    _check(lib().pd_cholesky_factor(n, _p(rowptr), _p(col), _p(val), C.byref(nnz), C.byref(lp), C.byref(lc), C.byref(lv)))
+    out = (np.ctypeslib.as_array(C.cast(lp, C.POINTER(C.c_int)), shape=(n + 1,)).copy(),
+           np.ctypeslib.as_array(C.cast(lc, C.POINTER(C.c_int)), shape=(nnz.value,)).copy(),
+           np.ctypeslib.as_array(C.cast(lv, C.POINTER(C.c_float)), shape=(nnz.value,)).copy())
+    for q in (lp, lc, lv):
+        lib().pd_free(q)
+    return out
 
 
 def rotation_batch(F, rot_mode=0, device=0):

@@ -17,6 +17,7 @@ using namespace pdb200;
 struct pd_scene { Scene s; };
 struct pd_layout { Layout L; };
 struct pd_engine { Engine* e; };
+struct pd_rank_plan { RankPlan P; };
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& m) { g_err = m; return code; }
@@ -55,7 +56,7 @@ const char* pd_last_error(void) { return g_err.c_str(); }
 const char* pd_version(void) { return "pd_b200 0.1 (sm_100a)"; }
 
 void pd_default_params(pd_params* p) { SolverParams d; to_c(d, p); }
-void pd_default_options(pd_engine_options* o) { o->device = 0; o->rot_mode = 0; o->reorder = 1; o->use_graph = 1; o->ctas_per_sm = 0; }
+void pd_default_options(pd_engine_options* o) { o->device = 0; o->rot_mode = 0; o->reorder = 1; o->use_graph = 1; o->ctas_per_sm = 0; o->rank = 0; o->world = 1; }
 
 // ------------------------------------------------------------------ scene
 pd_scene* pd_scene_load_json(const char* json_path, const char* context_name, const char* asset_root)
@@ -239,6 +240,21 @@ int pd_morton_keys(const float* X, const uint32_t* Tet, int nT, uint32_t* keys)
     return PD_OK;
     PD_CATCH_INT
 }
+int pd_cholesky_factor(int n, const int* rowptr, const int* col, const float* val, int* nnz_l, int** lptr, int** lcol, float** lval)
+{
+    PD_TRY
+    if (n <= 0 || !rowptr || !col || !val || !nnz_l || !lptr || !lcol || !lval) return fail(PD_ERR_INVALID, "bad argument");
+    CsrMatrix A; A.n = n;
+    A.rowPtr.assign(rowptr, rowptr + n + 1); A.col.assign(col, col + rowptr[n]); A.val.assign(val, val + rowptr[n]);
+    CholFactor F;
+    cholesky_factor(A, F);
+    *nnz_l = (int)F.lCol.size();
+    *lptr = (int*)std::malloc(F.lPtr.size() * sizeof(int)); *lcol = (int*)std::malloc(F.lCol.size() * sizeof(int)); *lval = (float*)std::malloc(F.lVal.size() * sizeof(float));
+    std::memcpy(*lptr, F.lPtr.data(), F.lPtr.size() * sizeof(int)); std::memcpy(*lcol, F.lCol.data(), F.lCol.size() * sizeof(int));
+    std::memcpy(*lval, F.lVal.data(), F.lVal.size() * sizeof(float));
+    return PD_OK;
+    PD_CATCH_INT
+}
 int pd_partition_vertices(int nV, int world, int* vbeg)
 {
     if (nV < 0 || world <= 0 || !vbeg) return fail(PD_ERR_INVALID, "bad argument");
@@ -248,13 +264,55 @@ int pd_partition_vertices(int nV, int world, int* vbeg)
     return PD_OK;
 }
 
+// ------------------------------------------------------------------ multi-GPU plan (host only)
+pd_rank_plan* pd_rank_plan_build(const pd_layout* g, int world, int rank)
+{
+    PD_TRY
+    if (!g) { g_err = "layout is NULL"; return nullptr; }
+    pd_rank_plan* p = new pd_rank_plan;
+    try { build_rank_plan(g->L, world, rank, p->P); } catch (...) { delete p; throw; }
+    return p;
+    PD_CATCH_PTR
+}
+void pd_rank_plan_free(pd_rank_plan* p) { delete p; }
+int pd_rank_plan_counts(const pd_rank_plan* p, int c[7])
+{
+    if (!p || !c) return fail(PD_ERR_INVALID, "NULL argument");
+    c[0] = p->P.nOwn; c[1] = p->P.nGhost; c[2] = (int)p->P.tiles.size(); c[3] = (int)p->P.neighbours.size();
+    c[4] = (int)p->P.pushSrc.size(); c[5] = p->P.vbeg[(size_t)p->P.rank]; c[6] = p->P.nInteriorTiles;
+    return PD_OK;
+}
+int pd_rank_plan_get(const pd_rank_plan* p, uint32_t* tiles, uint32_t* ghosts, int* nbr, int* nLocOf, uint32_t* ps, uint32_t* pdst, int* pr)
+{
+    if (!p) return fail(PD_ERR_INVALID, "plan is NULL");
+    const RankPlan& P = p->P;
+    if (tiles) std::memcpy(tiles, P.tiles.data(), P.tiles.size() * 4);
+    if (ghosts) std::memcpy(ghosts, P.ghosts.data(), P.ghosts.size() * 4);
+    if (nbr) std::memcpy(nbr, P.neighbours.data(), P.neighbours.size() * sizeof(int));
+    if (nLocOf) std::memcpy(nLocOf, P.nLocOf.data(), P.nLocOf.size() * sizeof(int));
+    if (ps) std::memcpy(ps, P.pushSrc.data(), P.pushSrc.size() * 4);
+    if (pdst) std::memcpy(pdst, P.pushDst.data(), P.pushDst.size() * 4);
+    if (pr) std::memcpy(pr, P.pushRank.data(), P.pushRank.size() * sizeof(int));
+    return PD_OK;
+}
+pd_layout* pd_rank_layout(const pd_layout* g, const pd_rank_plan* p)
+{
+    PD_TRY
+    if (!g || !p) { g_err = "NULL argument"; return nullptr; }
+    pd_layout* l = new pd_layout;
+    try { extract_rank_layout(g->L, p->P, l->L); } catch (...) { delete l; throw; }
+    return l;
+    PD_CATCH_PTR
+}
+
 // ------------------------------------------------------------------ engine
 pd_engine* pd_create(const pd_scene* s, const pd_engine_options* o)
 {
     PD_TRY
     if (!s) { g_err = "scene is NULL"; return nullptr; }
     EngineOptions eo;
-    if (o) { eo.device = o->device; eo.rotMode = o->rot_mode; eo.reorder = o->reorder; eo.useGraph = o->use_graph; eo.ctasPerSm = o->ctas_per_sm; }
+    if (o) { eo.device = o->device; eo.rotMode = o->rot_mode; eo.reorder = o->reorder; eo.useGraph = o->use_graph; eo.ctasPerSm = o->ctas_per_sm;
+             eo.rank = o->rank; eo.world = o->world < 1 ? 1 : o->world; }
     pd_engine* e = new pd_engine{nullptr};
     try { e->e = new Engine(s->s, eo); } catch (...) { delete e; throw; }
     return e;
@@ -306,6 +364,7 @@ int pd_set_perf(pd_engine* e, int on) { ENGINE_CALL(e->e->setPerf(on != 0)) }
 int pd_get_perf(const pd_engine* e, pd_perf* o)
 {
     if (!e || !e->e || !o) return fail(PD_ERR_INVALID, "NULL argument");
+    try { e->e->syncSolveStats(); } catch (const std::exception& ex) { return fail(PD_ERR_CUDA, ex.what()); }
     const PerfCounters& c = e->e->perf();
     o->local_step_ms = c.localStep; o->global_step_ms = c.globalStep; o->collision_fixed_ms = c.collisionFixed; o->collision_mesh_ms = c.collisionMesh;
     o->step_ms_total = c.stepMsTotal; o->steps = c.steps; o->pd_iterations = c.pdIterations; o->inner_iterations = c.innerIterations;
@@ -324,6 +383,18 @@ int pd_update_device(pd_engine* e, int n, float* dX, float* dV, float* dXT)
                 e->e->importDevice(dX, dV, dXT); e->e->step(n); e->e->exportDevice(dX, dV, dXT); e->e->synchronize())
 }
 int pd_get_setup(pd_engine* e, float* md, float* mdt2, float* DmInv, float* V0) { ENGINE_CALL(e->e->getSetup(md, mdt2, DmInv, V0)) }
+int pd_get_system_matrix(pd_engine* e, int* nnz, int* rowptr, int* col, float* val)
+{
+    ENGINE_CALL(const CsrMatrix& A = e->e->systemMatrix();
+                if (nnz) *nnz = (int)A.col.size();
+                if (rowptr) std::memcpy(rowptr, A.rowPtr.data(), A.rowPtr.size() * sizeof(int));
+                if (col) std::memcpy(col, A.col.data(), A.col.size() * sizeof(int));
+                if (val) std::memcpy(val, A.val.data(), A.val.size() * sizeof(float)))
+}
+int pd_get_solve_stats(pd_engine* e, float* err, int* pd_iters)
+{
+    ENGINE_CALL(e->e->syncSolveStats(); if (err) *err = e->e->lastError(); if (pd_iters) *pd_iters = e->e->lastPdIterations())
+}
 int pd_time_kernels(pd_engine* e, int reps, float* lms, float* vms)
 {
     ENGINE_CALL(if (reps <= 0) return fail(PD_ERR_INVALID, "reps <= 0");
@@ -340,6 +411,43 @@ int pd_engine_info(const pd_engine* e, int* nv, int* nt, int* ntiles, uint32_t* 
     if (streamBytes) *streamBytes = e->e->tileStreamBytes();
     if (devBytes) *devBytes = e->e->deviceBytes();
     if (lgrid) *lgrid = e->e->localGrid();
+    return PD_OK;
+}
+
+int pd_dist_window_handle(pd_engine* e, void* out64) { ENGINE_CALL(if (!out64) return fail(PD_ERR_INVALID, "out is NULL"); e->e->windowHandle(out64)) }
+int pd_dist_connect(pd_engine* e, const void* handles) { ENGINE_CALL(if (!handles) return fail(PD_ERR_INVALID, "handles is NULL"); e->e->connectIpc(handles)) }
+static int collect(pd_engine* const* engines, int n, std::vector<Engine*>& v)
+{
+    if (!engines || n <= 0) return fail(PD_ERR_INVALID, "no engines");
+    for (int i = 0; i < n; ++i) { if (!engines[i] || !engines[i]->e) return fail(PD_ERR_INVALID, "engine is NULL"); v.push_back(engines[i]->e); }
+    return PD_OK;
+}
+int pd_dist_connect_local(pd_engine* const* engines, int n)
+{
+    PD_TRY
+    std::vector<Engine*> v;
+    if (int rc = collect(engines, n, v)) return rc;
+    Engine::connectLocal(v.data(), n);
+    return PD_OK;
+    PD_CATCH_INT
+}
+int pd_dist_step_lockstep(pd_engine* const* engines, int n, int nSteps)
+{
+    PD_TRY
+    std::vector<Engine*> v;
+    if (int rc = collect(engines, n, v)) return rc;
+    if (nSteps < 0) return fail(PD_ERR_INVALID, "n_steps < 0");
+    Engine::stepLockstep(v.data(), n, nSteps);
+    return PD_OK;
+    PD_CATCH_INT
+}
+int pd_dist_status(pd_engine* e, unsigned int* out) { ENGINE_CALL(if (!out) return fail(PD_ERR_INVALID, "out is NULL"); *out = e->e->distStatus()) }
+int pd_dist_info(const pd_engine* e, int info[6])
+{
+    if (!e || !e->e || !info) return fail(PD_ERR_INVALID, "NULL argument");
+    const RankPlan& P = e->e->plan();
+    info[0] = e->e->numOwned(); info[1] = e->e->numVerts() - e->e->numOwned(); info[2] = (int)P.neighbours.size();
+    info[3] = (int)P.pushSrc.size(); info[4] = e->e->numTets(); info[5] = e->e->layout().nTiles;
     return PD_OK;
 }
 

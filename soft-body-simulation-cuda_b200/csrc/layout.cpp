@@ -8,6 +8,7 @@
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
+#include <string>
 
 namespace pdb200 {
 
@@ -357,10 +358,214 @@ void build_system_matrix(const Layout& L, const float*, const float* DmInv, cons
     A.rowPtr[nV] = (int)A.col.size();
 }
 
+void cholesky_factor(const CsrMatrix& A, CholFactor& F)
+{
+    const int n = A.n;
+    F = CholFactor();
+    F.n = n;
+    // elimination tree (Liu): A is symmetric, row k's entries with column < k are column k's upper part
+    std::vector<int> parent((size_t)n, -1), anc((size_t)n, -1);
+    for (int k = 0; k < n; ++k)
+        for (int e = A.rowPtr[k]; e < A.rowPtr[k + 1]; ++e) {
+            int i = A.col[e];
+            while (i != -1 && i < k) {
+                const int nx = anc[(size_t)i];
+                anc[(size_t)i] = k;
+                if (nx == -1) parent[(size_t)i] = k;
+                i = nx;
+            }
+        }
+    // columns of L grow row by row (entries arrive in ascending row order)
+    std::vector<std::vector<int>> ci((size_t)n);
+    std::vector<std::vector<double>> cx((size_t)n);
+    std::vector<double> diag((size_t)n, 0.0), x((size_t)n, 0.0);
+    std::vector<int> mark((size_t)n, -1), stack((size_t)n), path((size_t)n);
+    for (int k = 0; k < n; ++k) {
+        // pattern of row k of L = nodes reached from the entries of A(k, 0:k) up the elimination tree, topological order
+        int top = n;
+        mark[(size_t)k] = k;
+        double d = 0.0;
+        for (int e = A.rowPtr[k]; e < A.rowPtr[k + 1]; ++e) {
+            const int c = A.col[e];
+            if (c > k) continue;
+            if (c == k) { d = (double)A.val[e]; continue; }
+            x[(size_t)c] = (double)A.val[e];
+            int len = 0;
+            for (int i = c; mark[(size_t)i] != k; i = parent[(size_t)i]) { path[(size_t)len++] = i; mark[(size_t)i] = k; }
+            while (len > 0) stack[(size_t)--top] = path[(size_t)--len];
+        }
+        for (int t = top; t < n; ++t) {
+            const int j = stack[(size_t)t];
+            const double lkj = x[(size_t)j] / diag[(size_t)j];
+            x[(size_t)j] = 0.0;
+            const std::vector<int>& rj = ci[(size_t)j];
+            const std::vector<double>& vj = cx[(size_t)j];
+            for (size_t q = 0; q < rj.size(); ++q) x[(size_t)rj[q]] -= vj[q] * lkj;
+            d -= lkj * lkj;
+            ci[(size_t)j].push_back(k);
+            cx[(size_t)j].push_back(lkj);
+        }
+        if (!(d > 0.0)) throw std::runtime_error("Cholesky: system matrix is not positive definite at row " + std::to_string(k));
+        diag[(size_t)k] = std::sqrt(d);
+    }
+    // L^T by rows = L by columns: diagonal first, then ascending rows
+    F.uPtr.assign((size_t)n + 1, 0);
+    for (int j = 0; j < n; ++j) F.uPtr[(size_t)j + 1] = F.uPtr[(size_t)j] + 1 + (int)ci[(size_t)j].size();
+    F.uCol.resize((size_t)F.uPtr[(size_t)n]); F.uVal.resize((size_t)F.uPtr[(size_t)n]);
+    std::vector<int> rowCount((size_t)n, 1);
+    for (int j = 0; j < n; ++j) {
+        int o = F.uPtr[(size_t)j];
+        F.uCol[(size_t)o] = j; F.uVal[(size_t)o] = (float)diag[(size_t)j]; ++o;
+        for (size_t q = 0; q < ci[(size_t)j].size(); ++q, ++o) {
+            F.uCol[(size_t)o] = ci[(size_t)j][q]; F.uVal[(size_t)o] = (float)cx[(size_t)j][q];
+            rowCount[(size_t)ci[(size_t)j][q]]++;
+        }
+    }
+    // L by rows: ascending columns (columns are visited in ascending order), diagonal last
+    F.lPtr.assign((size_t)n + 1, 0);
+    for (int i = 0; i < n; ++i) F.lPtr[(size_t)i + 1] = F.lPtr[(size_t)i] + rowCount[(size_t)i];
+    F.lCol.resize((size_t)F.lPtr[(size_t)n]); F.lVal.resize((size_t)F.lPtr[(size_t)n]);
+    std::vector<int> fill(F.lPtr.begin(), F.lPtr.end() - 1);
+    for (int j = 0; j < n; ++j)
+        for (size_t q = 0; q < ci[(size_t)j].size(); ++q) {
+            const int i = ci[(size_t)j][q];
+            F.lCol[(size_t)fill[(size_t)i]] = j; F.lVal[(size_t)fill[(size_t)i]] = (float)cx[(size_t)j][q];
+            ++fill[(size_t)i];
+        }
+    for (int i = 0; i < n; ++i) { F.lCol[(size_t)fill[(size_t)i]] = i; F.lVal[(size_t)fill[(size_t)i]] = (float)diag[(size_t)i]; }
+}
+
 void partition_vertices(int nV, int world, std::vector<int>& vbeg)
 {
     vbeg.assign((size_t)world + 1, 0);
     for (int r = 0; r <= world; ++r) vbeg[r] = (int)(((long long)nV * r) / world);
+}
+
+static inline int owner_of(const std::vector<int>& vbeg, uint32_t v)
+{
+    return (int)(std::upper_bound(vbeg.begin(), vbeg.end(), (int)v) - vbeg.begin()) - 1;
+}
+
+void build_rank_plan(const Layout& G, int world, int rank, RankPlan& P)
+{
+    if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("rank plan: bad rank/world");
+    P = RankPlan();
+    P.rank = rank; P.world = world;
+    partition_vertices(G.nV, world, P.vbeg);
+    P.nOwn = P.vbeg[rank + 1] - P.vbeg[rank];
+    // one pass over the tiles: which ranks evaluate it, and whose ghosts its vertices become
+    std::vector<std::vector<uint32_t>> ghostsOf((size_t)world);
+    std::vector<int> ranksOfTile;
+    std::vector<uint32_t> boundaryTiles;
+    for (int t = 0; t < G.nTiles; ++t) {
+        const uint32_t* vl = G.vlist.data() + (size_t)t * TILE_NLMAX;
+        ranksOfTile.clear();
+        for (int l = 0; l < TILE_NLMAX && vl[l] != 0xffffffffu; ++l) {
+            const int o = owner_of(P.vbeg, vl[l] & ~TILE_OWNER_BIT);
+            if (std::find(ranksOfTile.begin(), ranksOfTile.end(), o) == ranksOfTile.end()) ranksOfTile.push_back(o);
+        }
+        if (std::find(ranksOfTile.begin(), ranksOfTile.end(), rank) != ranksOfTile.end())
+            (ranksOfTile.size() > 1 ? boundaryTiles : P.tiles).push_back((uint32_t)t);
+        if (ranksOfTile.size() > 1)
+            for (int l = 0; l < TILE_NLMAX && vl[l] != 0xffffffffu; ++l) {
+                const uint32_t v = vl[l] & ~TILE_OWNER_BIT;
+                const int o = owner_of(P.vbeg, v);
+                for (int r : ranksOfTile) if (r != o) ghostsOf[(size_t)r].push_back(v);
+            }
+    }
+    P.nInteriorTiles = (int)P.tiles.size();
+    P.tiles.insert(P.tiles.end(), boundaryTiles.begin(), boundaryTiles.end());
+    P.nLocOf.assign((size_t)world, 0);
+    for (int r = 0; r < world; ++r) {
+        std::vector<uint32_t>& g = ghostsOf[(size_t)r];
+        std::sort(g.begin(), g.end());
+        g.erase(std::unique(g.begin(), g.end()), g.end());
+        P.nLocOf[(size_t)r] = (P.vbeg[r + 1] - P.vbeg[r]) + (int)g.size();
+    }
+    P.ghosts = ghostsOf[(size_t)rank];
+    P.nGhost = (int)P.ghosts.size();
+    // what this rank sends: its own vertices in the other ranks' ghost lists
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        const std::vector<uint32_t>& g = ghostsOf[(size_t)r];
+        const int nOwnR = P.vbeg[r + 1] - P.vbeg[r];
+        bool any = false;
+        for (size_t i = 0; i < g.size(); ++i)
+            if ((int)g[i] >= P.vbeg[rank] && (int)g[i] < P.vbeg[rank + 1]) {
+                P.pushSrc.push_back(g[i] - (uint32_t)P.vbeg[rank]);
+                P.pushDst.push_back((uint32_t)nOwnR + (uint32_t)i);
+                P.pushRank.push_back(r);
+                any = true;
+            }
+        if (any) P.neighbours.push_back(r);
+    }
+    // the relation is symmetric (a shared tile makes ghosts on both sides); keep the union anyway
+    for (uint32_t g : P.ghosts) {
+        const int o = owner_of(P.vbeg, g);
+        if (std::find(P.neighbours.begin(), P.neighbours.end(), o) == P.neighbours.end()) P.neighbours.push_back(o);
+    }
+    std::sort(P.neighbours.begin(), P.neighbours.end());
+}
+
+void extract_rank_layout(const Layout& G, const RankPlan& P, Layout& L)
+{
+    L = Layout();
+    const int v0 = P.vbeg[P.rank];
+    L.nV = P.nOwn + P.nGhost;
+    std::vector<uint32_t> localOf((size_t)G.nV, 0xffffffffu);          // global renumbered id -> local id
+    for (int i = 0; i < P.nOwn; ++i) localOf[(size_t)(v0 + i)] = (uint32_t)i;
+    for (int i = 0; i < P.nGhost; ++i) localOf[P.ghosts[(size_t)i]] = (uint32_t)(P.nOwn + i);
+    L.vertOrder.resize((size_t)L.nV);
+    for (int g = 0; g < G.nV; ++g) if (localOf[(size_t)g] != 0xffffffffu) L.vertOrder[localOf[(size_t)g]] = G.vertOrder[(size_t)g];
+    L.vertNewOfOld.assign((size_t)G.nV, 0xffffffffu);                   // ORIGINAL id -> local id (0xffffffff: not on this rank)
+    for (int l = 0; l < L.nV; ++l) L.vertNewOfOld[L.vertOrder[(size_t)l]] = (uint32_t)l;
+    std::vector<uint32_t> localTile((size_t)G.nTiles, 0xffffffffu);
+    L.nTiles = (int)P.tiles.size();
+    L.tileTetStart.push_back(0); L.tileRecOff.push_back(0);
+    L.vlist.assign((size_t)L.nTiles * TILE_NLMAX, 0xffffffffu);
+    L.maxLocal = 0;
+    for (int lt = 0; lt < L.nTiles; ++lt) {
+        const uint32_t gt = P.tiles[(size_t)lt];
+        localTile[gt] = (uint32_t)lt;
+        const uint64_t gb = G.tileRecOff[gt], ge = G.tileRecOff[gt + 1];
+        const size_t base = L.records.size();
+        L.records.insert(L.records.end(), G.records.begin() + (ptrdiff_t)gb, G.records.begin() + (ptrdiff_t)ge);
+        TileHeader h; std::memcpy(&h, L.records.data() + base, sizeof(h));
+        h.slotBase = (uint32_t)lt * (uint32_t)TILE_NLMAX;
+        h.offLo = (uint32_t)(base & 0xffffffffu); h.offHi = (uint32_t)((uint64_t)base >> 32);
+        std::memcpy(L.records.data() + base, &h, sizeof(h));
+        L.tileTab.push_back(TileEntry{(uint64_t)base, h.abBytes, h.cBytes});
+        L.maxLocal = std::max(L.maxLocal, (int)h.nLocal);
+        const uint32_t t0 = G.tileTetStart[gt], t1 = G.tileTetStart[gt + 1];
+        for (uint32_t t = t0; t < t1; ++t) {
+            L.tetOrder.push_back(G.tetOrder[t]);
+            for (int k = 0; k < 4; ++k) L.tetNew.push_back(localOf[G.tetNew[4 * (size_t)t + k]]);
+        }
+        L.tileTetStart.push_back((uint32_t)L.tetOrder.size());
+        L.tileRecOff.push_back((uint64_t)L.records.size());
+        for (uint32_t l = 0; l < h.nLocal; ++l) {
+            const uint32_t e = G.vlist[(size_t)gt * TILE_NLMAX + l];
+            L.vlist[(size_t)lt * TILE_NLMAX + l] = localOf[e & ~TILE_OWNER_BIT] | (e & TILE_OWNER_BIT);
+        }
+    }
+    L.nT = (int)L.tetOrder.size();
+    // vertex -> slots: the global lists restricted to this rank's tiles (complete for owned vertices), same order
+    L.vslotPtr.assign((size_t)L.nV + 1, 0u);
+    std::vector<uint32_t> globalOf((size_t)L.nV);
+    for (int g = 0; g < G.nV; ++g) if (localOf[(size_t)g] != 0xffffffffu) globalOf[localOf[(size_t)g]] = (uint32_t)g;
+    for (int l = 0; l < L.nV; ++l) {
+        const uint32_t g = globalOf[(size_t)l];
+        for (uint32_t e = G.vslotPtr[g]; e < G.vslotPtr[g + 1]; ++e) {
+            const uint32_t slot = G.vslot[e], lt = localTile[slot / TILE_NLMAX];
+            if (lt == 0xffffffffu) continue;
+            if (l < P.nOwn) { /* every tile of an owned vertex is evaluated here */ }
+            L.vslot.push_back(lt * (uint32_t)TILE_NLMAX + slot % TILE_NLMAX);
+        }
+        L.vslotPtr[(size_t)l + 1] = (uint32_t)L.vslot.size();
+        if (l < P.nOwn && L.vslotPtr[(size_t)l + 1] - L.vslotPtr[(size_t)l] != G.vslotPtr[g + 1] - G.vslotPtr[g])
+            throw std::runtime_error("rank layout: an owned vertex lost a tile");
+    }
+    L.nSlots = (uint32_t)L.vslot.size();
 }
 
 }  // namespace pdb200

@@ -94,8 +94,45 @@ struct CsrMatrix {
 void build_system_matrix(const Layout& L, const float* Xnew, const float* DmInv /*reordered*/, const float* w /*reordered*/,
                          const float* c /*nV renumbered*/, CsrMatrix& A, std::vector<float>& matrixDiag);
 
+// Sparse Cholesky A^ = L L^T of the scalar system matrix in the given (Morton first-touch) vertex order, no further
+// permutation: up-looking factorisation over the elimination tree, accumulated in double, stored as float.
+// lPtr/lCol/lVal: L by rows (ascending columns, diagonal last); uPtr/uCol/uVal: L^T by rows (diagonal first).
+// This is the host-side "prefactor once" of CholeskySpLinearSolver (cholesky.cu:133-158) / SimplicialCholesky
+// (pdSolver.cu:103); throws if the matrix is not positive definite.
+struct CholFactor {
+    int n = 0;
+    std::vector<int> lPtr, lCol, uPtr, uCol;
+    std::vector<float> lVal, uVal;
+};
+void cholesky_factor(const CsrMatrix& A, CholFactor& F);
+
 // Contiguous vertex partition of the renumbered ids into `world` ranks:
 // rank r owns [vbeg[r], vbeg[r+1]).
 void partition_vertices(int nV, int world, std::vector<int>& vbeg);
+
+// Multi-GPU plan of one rank.  The partition is by VERTEX (contiguous ranges of the
+// renumbered ids, which follow the Morton order of the tets and are therefore spatially compact); a rank
+// evaluates every global TILE that touches one of its vertices, unchanged -- same record bytes, same order --
+// so the partial sums and the per-vertex slot sums of its own vertices are bit-identical to the single-GPU
+// run.  Vertices of those tiles that belong to other ranks are ghosts: their positions are pushed by their
+// owners once per PD iteration.  Local vertex numbering: [own range in global order | ghosts ascending].
+struct RankPlan {
+    int rank = 0, world = 1;
+    std::vector<int> vbeg;             // world + 1
+    int nOwn = 0, nGhost = 0;
+    std::vector<uint32_t> tiles;       // global tile ids evaluated by this rank: first the interior tiles (all vertices owned),
+                                       // then the boundary tiles (some ghost vertex), each group ascending
+    int nInteriorTiles = 0;            // the local kernel needs the neighbours' halo only from tile nInteriorTiles on
+    std::vector<uint32_t> ghosts;      // global (renumbered) ids of the ghost vertices, ascending
+    std::vector<int> nLocOf;           // world: owned + ghost vertex count of every rank (sizes of the peers' windows)
+    std::vector<int> neighbours;       // ranks exchanged with (symmetric), ascending
+    // push list, sorted by (rank, dst): owned local vertex `src` here is ghost local vertex `dst` on `rank`
+    std::vector<uint32_t> pushSrc, pushDst;
+    std::vector<int> pushRank;
+};
+void build_rank_plan(const Layout& G, int world, int rank, RankPlan& plan);
+// the rank's own Layout: selected tiles (headers re-based), local vertex ids, local slots; vertOrder maps local ->
+// ORIGINAL vertex ids so that everything downstream of a Layout works unchanged
+void extract_rank_layout(const Layout& G, const RankPlan& plan, Layout& out);
 
 }  // namespace pdb200

@@ -9,6 +9,7 @@
 #include <stdexcept>
 
 #include "pd_kernels.cuh"
+#include "pd_solvers.cuh"
 
 namespace pdb200 {
 
@@ -36,11 +37,34 @@ struct Engine::Impl {
     float* stage3 = nullptr;          // 3 x (3 nV) floats, AoS staging for import/export
     float* fbData = nullptr;
     DevFixedBodies fb{};
-    cudaGraphExec_t graphExec = nullptr;
-    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graphExec[3] = {nullptr, nullptr, nullptr};   // one per rotation base of the position buffers
     std::vector<cudaEvent_t> events;
     std::vector<void*> allocs;
     std::vector<float> hostMd;        // renumbered
+    // multi-GPU exchange window (this rank's) and the tables that point into the neighbours' windows
+    uint8_t* window = nullptr;
+    size_t windowBytes = 0;
+    unsigned long long *flags = nullptr, *epoch = nullptr;
+    unsigned int *ticket = nullptr, *status = nullptr;
+    uint32_t *pushSrc = nullptr, *pushDst = nullptr, *pushNbr = nullptr;
+    int* nbrRanks = nullptr;
+    float4** peerQ = nullptr;                  // [3 * nNbr]: buffer k of neighbour j
+    unsigned long long** peerFlag = nullptr;   // [nNbr]: this rank's entry in neighbour j's flag array
+    int nPush = 0, nNbr = 0;
+    std::vector<void*> ipcOpened;
+    cudaEvent_t lockEvent = nullptr;
+    // non-Jacobi global solvers (PCG, sparse Cholesky)
+    bool solverReady = false, cholReady = false;
+    CsrDev A{0, nullptr, nullptr, nullptr, nullptr};
+    CholDev C{0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float4 *rhs = nullptr, *cgR = nullptr, *cgP = nullptr, *cgQ = nullptr, *xprev = nullptr, *cholY = nullptr;
+    int* cholReadyFlags = nullptr;
+    int cholEpoch = 0;
+    SolveState* solveState = nullptr;
+    double* partials = nullptr;
+    int solveGrid = 0;
+    size_t nnzA = 0, nnzL = 0;
+    DistWait wait{nullptr, nullptr, nullptr, 0, 0x7fffffff, nullptr};
 };
 
 template <typename T>
@@ -56,9 +80,8 @@ T* Engine::dalloc(size_t n)
 
 Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), params_(scene.params), opt_(opt), d_(new Impl)
 {
-    nV_ = scene.numVerts;
-    nT_ = scene.numTets;
-    if (nV_ <= 0 || nT_ <= 0) throw std::runtime_error("empty scene");
+    if (scene.numVerts <= 0 || scene.numTets <= 0) throw std::runtime_error("empty scene");
+    if (opt.world < 1 || opt.rank < 0 || opt.rank >= opt.world) throw std::runtime_error("bad rank/world");
     if (params_.handleCollision)
         throw std::runtime_error("handleCollision=true (mesh-mesh BVH/CCD) is outside the PD hot path; set it to false");
     int ndev = 0;
@@ -73,7 +96,20 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     numSms_ = prop.multiProcessorCount;
     CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
 
-    build_layout(nV_, nT_, scene_.X.data(), scene_.Tet.data(), scene_.mu.data(), opt.reorder != 0, L_);
+    if (opt.world == 1) {
+        build_layout(scene_.numVerts, scene_.numTets, scene_.X.data(), scene_.Tet.data(), scene_.mu.data(), opt.reorder != 0, L_);
+        nOwn_ = L_.nV;
+    } else {
+        // every rank builds the same global layout, then keeps the tiles that touch its vertex range
+        Layout G;
+        build_layout(scene_.numVerts, scene_.numTets, scene_.X.data(), scene_.Tet.data(), scene_.mu.data(), opt.reorder != 0, G);
+        build_rank_plan(G, opt.world, opt.rank, plan_);
+        extract_rank_layout(G, plan_, L_);
+        nOwn_ = plan_.nOwn;
+    }
+    nV_ = L_.nV;
+    nT_ = L_.nT;
+    if (nV_ <= 0 || nT_ <= 0) throw std::runtime_error("rank " + std::to_string(opt.rank) + " holds no tets: fewer ranks, or a larger mesh");
 
     // ---- device buffers
     Impl& d = *d_;
@@ -83,13 +119,21 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     d.vslot = dalloc<uint32_t>(L_.vslot.size());
     d.vlist = dalloc<uint32_t>(L_.vlist.size());
     d.P = dalloc<float4>((size_t)L_.nTiles * TILE_NLMAX);      // padded slots: tile * TILE_NLMAX + local vertex
-    for (int k = 0; k < 3; ++k) d.q[k] = dalloc<float4>(nV_);
+    // the three position buffers live in the exchange window: [q0 | q1 | q2 | flags[world] | epoch | ticket | status]
+    d.windowBytes = 3 * (size_t)nV_ * 16 + 8 * (size_t)opt.world + 8 + 8;
+    d.window = dalloc<uint8_t>(d.windowBytes);
+    CUDA_CHECK(cudaMemset(d.window, 0, d.windowBytes));
+    for (int k = 0; k < 3; ++k) d.q[k] = reinterpret_cast<float4*>(d.window) + (size_t)k * nV_;
+    d.flags = reinterpret_cast<unsigned long long*>(d.window + 3 * (size_t)nV_ * 16);
+    d.epoch = d.flags + opt.world;
+    d.ticket = reinterpret_cast<unsigned int*>(d.epoch + 1);
+    d.status = d.ticket + 1;
     d.b0 = dalloc<float4>(nV_); d.X = dalloc<float4>(nV_); d.V = dalloc<float4>(nV_);
     d.XT = dalloc<float4>(nV_); d.X0 = dalloc<float4>(nV_);
     d.cc = dalloc<float2>(nV_);
     d.mass = dalloc<float>(nV_); d.dbc = dalloc<float>(nV_); d.md = dalloc<float>(nV_);
     d.oldOfNew = dalloc<uint32_t>(nV_);
-    d.stage3 = dalloc<float>(9 * (size_t)nV_);
+    d.stage3 = dalloc<float>(9 * (size_t)scene_.numVerts);
 
     CUDA_CHECK(cudaMemcpy(d.records, L_.records.data(), L_.records.size(), cudaMemcpyHostToDevice));
     static_assert(sizeof(TileEntry) == sizeof(uint4), "tile table entry layout");
@@ -155,9 +199,10 @@ Engine::~Engine()
     if (d_) {
         cudaSetDevice(opt_.device);
         if (stream_) cudaStreamSynchronize(stream_);
-        if (d_->graphExec) cudaGraphExecDestroy(d_->graphExec);
-        if (d_->graph) cudaGraphDestroy(d_->graph);
+        for (cudaGraphExec_t g : d_->graphExec) if (g) cudaGraphExecDestroy(g);
         for (cudaEvent_t ev : d_->events) cudaEventDestroy(ev);
+        if (d_->lockEvent) cudaEventDestroy(d_->lockEvent);
+        for (void* p : d_->ipcOpened) cudaIpcCloseMemHandle(p);
         for (void* p : d_->allocs) cudaFree(p);
         if (stream_) cudaStreamDestroy(stream_);
     }
@@ -197,7 +242,11 @@ void Engine::prepare()
     // matrix_diag[v] = sum over incident tets (ascending reordered order) of w_t |col_i(B^T G)|^2
     Impl& d = *d_;
     d.hostMd.assign((size_t)nV_, 0.f);
-    for (int ti = 0; ti < L_.nTiles; ++ti) {
+    // tiles in ascending GLOBAL order (a rank keeps its interior tiles first): the float sums must not depend on the world size
+    std::vector<int> tileOrder((size_t)L_.nTiles);
+    for (int i = 0; i < L_.nTiles; ++i) tileOrder[(size_t)i] = i;
+    if (opt_.world > 1) std::sort(tileOrder.begin(), tileOrder.end(), [&](int a, int b) { return plan_.tiles[(size_t)a] < plan_.tiles[(size_t)b]; });
+    for (int ti : tileOrder) {
         const uint8_t* rec = L_.records.data() + L_.tileRecOff[ti];
         TileHeader h; std::memcpy(&h, rec, sizeof(h));
         const uint32_t* vlist = L_.vlist.data() + h.slotBase;
@@ -221,15 +270,16 @@ void Engine::prepare()
     dt2Prepared_ = params_.dt * params_.dt;
     ready_ = true;
     graphValid_ = false;
+    d.solverReady = false; d.cholReady = false;      // the system matrix bakes in dt and mu
 }
 
 void Engine::launchLocal(const float4* q, bool jacobi, unsigned long long* prof)
 {
     Impl& d = *d_;
-#define PD_LOCAL(RM, JAC) k_local<RM, JAC><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vlist, q, d.b0, d.P, prof)
+#define PD_LOCAL(RM, JAC) k_local<RM, JAC><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vlist, q, d.b0, d.P, prof, d.wait)
     if (prof) {
-        if (opt_.rotMode == 2) k_local<2, true, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vlist, q, d.b0, d.P, prof);
-        else k_local<0, true, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vlist, q, d.b0, d.P, prof);
+        if (opt_.rotMode == 2) k_local<2, true, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vlist, q, d.b0, d.P, prof, d.wait);
+        else k_local<0, true, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vlist, q, d.b0, d.P, prof, d.wait);
     } else if (jacobi) {
         if (opt_.rotMode == 0) PD_LOCAL(0, true);
         else if (opt_.rotMode == 1) PD_LOCAL(1, true);
@@ -241,61 +291,112 @@ void Engine::launchLocal(const float4* q, bool jacobi, unsigned long long* prof)
 #undef PD_LOCAL
 }
 
+void Engine::enqueuePredict()
+{
+    Impl& d = *d_;
+    const SolverParams& p = params_;
+    const int vb = 256, vg = (nOwn_ + vb - 1) / vb;
+    base_ = (opt_.world > 1) ? (int)(phase_ % 3) : 0;
+    omega_ = 1.0f;
+    k_predict<<<vg, vb, 0, stream_>>>(nOwn_, d.X, d.V, d.mass, d.dbc, d.md, p.dt, dt2Prepared_, p.gravity,
+                                      d.q[base_], d.q[(base_ + 2) % 3], d.b0, d.cc);
+    enqueuePush(d.q[base_], base_);
+    ++phase_;
+}
+
+void Engine::enqueueIteration(int i, bool timed, size_t* ev)
+{
+    Impl& d = *d_;
+    const SolverParams& p = params_;
+    const int vb = 256, vg = (nOwn_ + vb - 1) / vb;
+    const float dtInv = 1.0f / p.dt;
+    const float wdbc = 1e6f * (dtInv * dtInv);
+    auto rec = [&]() { if (timed) CUDA_CHECK(cudaEventRecord(d.events[(*ev)++], stream_)); };
+    const int ic = (base_ + i) % 3, in = (base_ + i + 1) % 3, ip = (base_ + i + 2) % 3;
+    const float4* cur = d.q[ic];
+    const float4* prev = d.q[ip];
+    float4* next = d.q[in];
+    rec();
+    launchLocal(cur, true);
+    rec();
+    // omega recurrence in float, pdSolver.cu:196-198
+    if (i <= 10) omega_ = 1;
+    else if (i == 11) omega_ = 2 / (2 - p.rho * p.rho);
+    else omega_ = 4 / (4 - p.rho * p.rho * omega_);
+    if (opt_.rotMode == 1) k_vertex_jacobi<false><<<vg, vb, 0, stream_>>>(nOwn_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
+    else k_vertex_jacobi<true><<<vg, vb, 0, stream_>>>(nOwn_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
+    enqueuePush(next, in);
+    ++phase_;
+    rec();
+}
+
+void Engine::enqueueFinish()
+{
+    Impl& d = *d_;
+    const SolverParams& p = params_;
+    const int vb = 256, vg = (nOwn_ + vb - 1) / vb;
+    k_finish<<<vg, vb, 0, stream_>>>(nOwn_, d.q[(base_ + p.numIterations) % 3], 1.0f / p.dt, d.X, d.XT, d.V, d.fb, p.muT, p.muN);
+}
+
+// multi-GPU: boundary positions of buffer `bufIndex` -> the neighbours' ghost entries, then the flags
+void Engine::enqueuePush(const float4* q, int bufIndex)
+{
+    Impl& d = *d_;
+    if (opt_.world == 1) return;
+    if (!connected_) throw std::runtime_error("multi-GPU engine stepped before pd_dist_connect");
+    const int grid = std::max(1, std::min(numSms_, (d.nPush + 255) / 256));
+    k_halo_push<<<grid, 256, 0, stream_>>>(d.nPush, d.pushSrc, d.pushDst, d.pushNbr, q, d.peerQ + (size_t)bufIndex * d.nNbr, d.nNbr,
+                                           d.peerFlag, d.epoch, d.ticket);
+}
+
 // The launch sequence of one PdSolver::Update in Jacobi mode.  `timed` brackets the local /
 // global / collision parts with events (perf mode, no host sync inside the loop).
 void Engine::enqueueStep(bool timed)
 {
     Impl& d = *d_;
-    const SolverParams& p = params_;
-    const int vb = 256, vg = (nV_ + vb - 1) / vb;
-    const float dt = p.dt, dtInv = 1.0f / dt;
-    const float wdbc = 1e6f * (dtInv * dtInv);
     size_t ev = 0;
-    auto rec = [&]() { if (timed) CUDA_CHECK(cudaEventRecord(d.events[ev++], stream_)); };
-
-    k_predict<<<vg, vb, 0, stream_>>>(nV_, d.X, d.V, d.mass, d.dbc, d.md, dt, dt2Prepared_, p.gravity,
-                                      d.q[0], d.q[2], d.b0, d.cc);
-    float omega = 1.0f;
-    for (int i = 0; i < p.numIterations; ++i) {
-        const float4* cur = d.q[i % 3];
-        const float4* prev = d.q[(i + 2) % 3];
-        float4* next = d.q[(i + 1) % 3];
-        rec();
-        launchLocal(cur, true);
-        rec();
-        // omega recurrence in float, pdSolver.cu:196-198
-        if (i <= 10) omega = 1;
-        else if (i == 11) omega = 2 / (2 - p.rho * p.rho);
-        else omega = 4 / (4 - p.rho * p.rho * omega);
-        if (opt_.rotMode == 1) k_vertex_jacobi<false><<<vg, vb, 0, stream_>>>(nV_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega, wdbc);
-        else k_vertex_jacobi<true><<<vg, vb, 0, stream_>>>(nV_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega, wdbc);
-        rec();
-    }
-    rec();
-    k_finish<<<vg, vb, 0, stream_>>>(nV_, d.q[p.numIterations % 3], dtInv, d.X, d.XT, d.V, d.fb, p.muT, p.muN);
-    rec();
+    enqueuePredict();
+    for (int i = 0; i < params_.numIterations; ++i) enqueueIteration(i, timed, &ev);
+    if (timed) CUDA_CHECK(cudaEventRecord(d.events[ev++], stream_));
+    enqueueFinish();
+    if (timed) CUDA_CHECK(cudaEventRecord(d.events[ev++], stream_));
 }
 
+// One CUDA graph per step.  Multi-GPU: the position buffers rotate across steps (base = phase_ % 3), so up to
+// three graphs exist, one per base; the halo flags make the replayed kernels wait for the neighbours as usual.
 void Engine::buildGraph()
 {
     Impl& d = *d_;
-    if (d.graphExec) { cudaGraphExecDestroy(d.graphExec); d.graphExec = nullptr; }
-    if (d.graph) { cudaGraphDestroy(d.graph); d.graph = nullptr; }
+    if (!graphValid_) {
+        for (cudaGraphExec_t& g : d.graphExec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+        graphValid_ = true;
+    }
+    const int b = (opt_.world > 1) ? (int)(phase_ % 3) : 0;
+    if (d.graphExec[b]) return;
+    const long long phaseSaved = phase_;
+    cudaGraph_t graph = nullptr;
     CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
     enqueueStep(false);
-    CUDA_CHECK(cudaStreamEndCapture(stream_, &d.graph));
-    CUDA_CHECK(cudaGraphInstantiate(&d.graphExec, d.graph, 0));
-    graphValid_ = true;
+    CUDA_CHECK(cudaStreamEndCapture(stream_, &graph));
+    phase_ = phaseSaved;                  // capturing ran nothing
+    CUDA_CHECK(cudaGraphInstantiate(&d.graphExec[b], graph, 0));
+    cudaGraphDestroy(graph);
 }
 
 void Engine::step(int nSteps)
 {
     CUDA_CHECK(cudaSetDevice(opt_.device));
-    if (params_.globalSolver != 0)
-        throw std::runtime_error("global solver " + std::to_string(params_.globalSolver) + " not built into this engine instance");
     if (!ready_) prepare();
     Impl& d = *d_;
-    const int launchesPerStep = 2 + 2 * params_.numIterations;
+    if (params_.globalSolver != 0) {       // PCG-Jacobi / sparse Cholesky global step: plain launches, device-side early exit
+        prepareSolver();
+        for (int s = 0; s < nSteps; ++s) enqueueStepSolver();
+        CUDA_CHECK(cudaGetLastError());
+        perfc_.steps += nSteps;
+        perfc_.kernelLaunches += (long long)nSteps * (4 + 3 * params_.numIterations);
+        return;
+    }
+    const int launchesPerStep = 2 + 2 * params_.numIterations + (opt_.world > 1 ? 1 + params_.numIterations : 0);
     if (perf_) {
         const size_t need = 3 * (size_t)params_.numIterations + 2;
         while (d.events.size() < need) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); d.events.push_back(e); }
@@ -315,8 +416,11 @@ void Engine::step(int nSteps)
             perfc_.collisionFixed += c;
         }
     } else if (opt_.useGraph) {
-        if (!graphValid_) buildGraph();
-        for (int s = 0; s < nSteps; ++s) CUDA_CHECK(cudaGraphLaunch(d.graphExec, stream_));
+        for (int s = 0; s < nSteps; ++s) {
+            buildGraph();
+            CUDA_CHECK(cudaGraphLaunch(d.graphExec[(opt_.world > 1) ? (int)(phase_ % 3) : 0], stream_));
+            phase_ += params_.numIterations + 1;
+        }
     } else {
         for (int s = 0; s < nSteps; ++s) enqueueStep(false);
     }
@@ -330,7 +434,7 @@ float Engine::stepTimed(int nSteps)
 {
     CUDA_CHECK(cudaSetDevice(opt_.device));
     if (!ready_) prepare();
-    if (opt_.useGraph && !perf_ && !graphValid_) buildGraph();
+    if (opt_.useGraph && !perf_) buildGraph();
     cudaEvent_t a, b;
     CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
@@ -360,9 +464,10 @@ void Engine::exportDevice(float* dX, float* dV, float* dXTilde)
 {
     Impl& d = *d_;
     const int vb = 256, vg = (nV_ + vb - 1) / vb;
-    if (dX) k_export3<<<vg, vb, 0, stream_>>>(nV_, d.X, d.oldOfNew, dX);
-    if (dV) k_export3<<<vg, vb, 0, stream_>>>(nV_, d.V, d.oldOfNew, dV);
-    if (dXTilde) k_export3<<<vg, vb, 0, stream_>>>(nV_, d.XT, d.oldOfNew, dXTilde);
+    // multi-GPU: owned vertices only (the caller combines the ranks' disjoint contributions)
+    if (dX) k_export3<<<vg, vb, 0, stream_>>>(nOwn_, d.X, d.oldOfNew, dX);
+    if (dV) k_export3<<<vg, vb, 0, stream_>>>(nOwn_, d.V, d.oldOfNew, dV);
+    if (dXTilde) k_export3<<<vg, vb, 0, stream_>>>(nOwn_, d.XT, d.oldOfNew, dXTilde);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -370,8 +475,8 @@ void Engine::upload(const float* X, const float* V, const float* XTilde)
 {
     CUDA_CHECK(cudaSetDevice(opt_.device));
     Impl& d = *d_;
-    const size_t n = 3 * (size_t)nV_ * sizeof(float);
-    float *sx = d.stage3, *sv = d.stage3 + 3 * (size_t)nV_, *st = d.stage3 + 6 * (size_t)nV_;
+    const size_t nG = (size_t)scene_.numVerts, n = 3 * nG * sizeof(float);
+    float *sx = d.stage3, *sv = d.stage3 + 3 * nG, *st = d.stage3 + 6 * nG;
     if (X) CUDA_CHECK(cudaMemcpyAsync(sx, X, n, cudaMemcpyHostToDevice, stream_));
     if (V) CUDA_CHECK(cudaMemcpyAsync(sv, V, n, cudaMemcpyHostToDevice, stream_));
     if (XTilde) CUDA_CHECK(cudaMemcpyAsync(st, XTilde, n, cudaMemcpyHostToDevice, stream_));
@@ -382,8 +487,9 @@ void Engine::download(float* X, float* V, float* XTilde)
 {
     CUDA_CHECK(cudaSetDevice(opt_.device));
     Impl& d = *d_;
-    const size_t n = 3 * (size_t)nV_ * sizeof(float);
-    float *sx = d.stage3, *sv = d.stage3 + 3 * (size_t)nV_, *st = d.stage3 + 6 * (size_t)nV_;
+    const size_t nG = (size_t)scene_.numVerts, n = 3 * nG * sizeof(float);
+    float *sx = d.stage3, *sv = d.stage3 + 3 * nG, *st = d.stage3 + 6 * nG;
+    if (opt_.world > 1) CUDA_CHECK(cudaMemsetAsync(d.stage3, 0, 3 * n, stream_));     // vertices of other ranks read as 0
     exportDevice(X ? sx : nullptr, V ? sv : nullptr, XTilde ? st : nullptr);
     if (X) CUDA_CHECK(cudaMemcpyAsync(X, sx, n, cudaMemcpyDeviceToHost, stream_));
     if (V) CUDA_CHECK(cudaMemcpyAsync(V, sv, n, cudaMemcpyDeviceToHost, stream_));
@@ -408,8 +514,8 @@ void Engine::getSetup(float* matrixDiag, float* massDt2, float* DmInv, float* V0
         if (massDt2) massDt2[o] = (scene_.mass[o] + scene_.DBC[o] * 1e6f) / dt2;
     }
     if (DmInv || V0) {
-        std::vector<float> B((size_t)nT_ * 9), v0((size_t)nT_);
-        rest_shape(scene_.X.data(), scene_.Tet.data(), nT_, B.data(), v0.data());
+        std::vector<float> B((size_t)scene_.numTets * 9), v0((size_t)scene_.numTets);
+        rest_shape(scene_.X.data(), scene_.Tet.data(), scene_.numTets, B.data(), v0.data());
         if (DmInv) std::memcpy(DmInv, B.data(), B.size() * 4);
         if (V0) std::memcpy(V0, v0.data(), v0.size() * 4);
     }
@@ -441,22 +547,291 @@ float Engine::timeVertexKernelMs(int reps)
     CUDA_CHECK(cudaSetDevice(opt_.device));
     if (!ready_) prepare();
     Impl& d = *d_;
-    const int vb = 256, vg = (nV_ + vb - 1) / vb;
+    const int vb = 256, vg = (nOwn_ + vb - 1) / vb;
     cudaEvent_t a, b;
     CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
     // a valid so4/cc is needed: run the predictor once
-    k_predict<<<vg, vb, 0, stream_>>>(nV_, d.X, d.V, d.mass, d.dbc, d.md, params_.dt, dt2Prepared_, params_.gravity,
+    k_predict<<<vg, vb, 0, stream_>>>(nOwn_, d.X, d.V, d.mass, d.dbc, d.md, params_.dt, dt2Prepared_, params_.gravity,
                                       d.q[0], d.q[2], d.b0, d.cc);
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     CUDA_CHECK(cudaEventRecord(a, stream_));
     for (int r = 0; r < reps; ++r)
-        k_vertex_jacobi<true><<<vg, vb, 0, stream_>>>(nV_, d.q[0], d.q[2], d.q[1], d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, 1.0f, 1.0f);
+        k_vertex_jacobi<true><<<vg, vb, 0, stream_>>>(nOwn_, d.q[0], d.q[2], d.q[1], d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, 1.0f, 1.0f);
     CUDA_CHECK(cudaEventRecord(b, stream_));
     CUDA_CHECK(cudaEventSynchronize(b));
     float ms = 0;
     CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
     cudaEventDestroy(a); cudaEventDestroy(b);
     return ms / (float)reps;
+}
+
+// ---------------------------------------------------------------- PCG / Cholesky global step
+// A^ = diag(c) + sum_t w_t P^T (B^T G)^T (B^T G) P  (SolverPrepare's COO, pdSolver.cu:62-77, deduplicated on the host)
+void Engine::prepareSolver()
+{
+    Impl& d = *d_;
+    if (opt_.world > 1) throw std::runtime_error("PCG / Cholesky global solvers run on one GPU per mesh (replicas only): outside the PD hot path of the multi-GPU mode");
+    if (!d.solverReady) {
+        std::vector<float> Br((size_t)nT_ * 9), wr((size_t)nT_), c((size_t)nV_);
+        size_t t = 0;
+        for (int ti = 0; ti < L_.nTiles; ++ti) {
+            const uint8_t* rec = L_.records.data() + L_.tileRecOff[ti];
+            TileHeader h; std::memcpy(&h, rec, sizeof(h));
+            for (uint32_t k = 0; k < h.nTets; ++k, ++t) {
+                const float* B = reinterpret_cast<const float*>(rec + TILE_OFF_TETS + 48 * (size_t)k);
+                std::memcpy(&Br[9 * t], B, 36);
+                wr[t] = B[9];
+            }
+        }
+        const float dt2 = params_.dt * params_.dt;
+        for (int v = 0; v < nV_; ++v) {
+            const uint32_t o = L_.vertOrder[v];
+            c[(size_t)v] = (scene_.mass[o] + scene_.DBC[o] * 1e6f) / dt2;       // setMDt_2, pdUtil.cu:48
+        }
+        CsrMatrix A; std::vector<float> md;
+        build_system_matrix(L_, nullptr, Br.data(), wr.data(), c.data(), A, md);
+        hostA_ = A;
+        std::vector<float> inv((size_t)nV_);
+        for (int v = 0; v < nV_; ++v) {
+            float dg = 1.0f;
+            for (int e = A.rowPtr[v]; e < A.rowPtr[v + 1]; ++e) if (A.col[e] == v) { dg = A.val[e]; break; }
+            if (std::fabs(dg) < 1e-9f) dg = 1.0f;                               // ExtractInverseDiagonalKernel, pcgJacobi.cu:6-19
+            inv[(size_t)v] = 1.0f / dg;
+        }
+        int* rp = dalloc<int>(A.rowPtr.size()); int* cl = dalloc<int>(A.col.size()); float* vl = dalloc<float>(A.val.size()); float* iv = dalloc<float>(nV_);
+        CUDA_CHECK(cudaMemcpy(rp, A.rowPtr.data(), A.rowPtr.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(cl, A.col.data(), A.col.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(vl, A.val.data(), A.val.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(iv, inv.data(), (size_t)nV_ * 4, cudaMemcpyHostToDevice));
+        d.A = CsrDev{nV_, rp, cl, vl, iv};
+        d.nnzA = A.col.size();
+        if (!d.rhs) {
+            d.rhs = dalloc<float4>(nV_); d.cgR = dalloc<float4>(nV_); d.cgP = dalloc<float4>(nV_); d.cgQ = dalloc<float4>(nV_);
+            d.xprev = dalloc<float4>(nV_); d.cholY = dalloc<float4>(nV_);
+            d.cholReadyFlags = dalloc<int>(nV_);
+            CUDA_CHECK(cudaMemset(d.cholReadyFlags, 0, (size_t)nV_ * 4));
+            d.solveState = dalloc<SolveState>(1);
+            CUDA_CHECK(cudaMemset(d.solveState, 0, sizeof(SolveState)));
+            int perSm = 0;
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pcg_solve, SOLVE_THREADS, 0));
+            int perSm2 = 0;
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm2, k_chol_solve, SOLVE_THREADS, 0));
+            perSm = std::max(1, std::min(perSm, perSm2));
+            d.solveGrid = std::min(numSms_ * perSm, std::min(SOLVE_MAX_PARTIALS, (nV_ + SOLVE_THREADS - 1) / SOLVE_THREADS));
+            d.solveGrid = std::max(d.solveGrid, 1);
+            d.partials = dalloc<double>(3 * (size_t)SOLVE_MAX_PARTIALS);
+        }
+        d.solverReady = true;
+    }
+    if (params_.globalSolver == 1 && !d.cholReady) {
+        if (nV_ > 262144) throw std::runtime_error("the sparse Cholesky global step is the small-mesh path (<= 262144 vertices); use Jacobi or PCG");
+        CholFactor F;
+        cholesky_factor(hostA_, F);
+        int* lp = dalloc<int>(F.lPtr.size()); int* lc = dalloc<int>(F.lCol.size()); float* lv = dalloc<float>(F.lVal.size());
+        int* up = dalloc<int>(F.uPtr.size()); int* uc = dalloc<int>(F.uCol.size()); float* uv = dalloc<float>(F.uVal.size());
+        CUDA_CHECK(cudaMemcpy(lp, F.lPtr.data(), F.lPtr.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(lc, F.lCol.data(), F.lCol.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(lv, F.lVal.data(), F.lVal.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(up, F.uPtr.data(), F.uPtr.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(uc, F.uCol.data(), F.uCol.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(uv, F.uVal.data(), F.uVal.size() * 4, cudaMemcpyHostToDevice));
+        d.C = CholDev{nV_, lp, lc, lv, up, uc, uv};
+        d.nnzL = F.lCol.size();
+        d.cholReady = true;
+    }
+}
+
+// One PdSolver::Update in the direct / CG modes (pdSolver.cu:141-208 with isJacobi == false): the iterate lives in
+// q[0]; every PD iteration = local step (H = w R DmInv^T G) -> right-hand side -> ONE cooperative solve kernel that
+// also evaluates computeError and raises the device-side `done` flag; later iterations of the step then return at once.
+void Engine::enqueueStepSolver()
+{
+    Impl& d = *d_;
+    const SolverParams& p = params_;
+    const int vb = 256, vg = (nV_ + vb - 1) / vb;
+    const float dtInv = 1.0f / p.dt;
+    const float wdbc = 1e6f * (dtInv * dtInv);
+    k_predict<<<vg, vb, 0, stream_>>>(nV_, d.X, d.V, d.mass, d.dbc, d.md, p.dt, dt2Prepared_, p.gravity, d.q[0], d.q[2], d.b0, d.cc);
+    CUDA_CHECK(cudaMemsetAsync(d.xprev, 0, (size_t)nV_ * 16, stream_));        // cudaMemset(prev_x, 0, ...), pdSolver.cu:162
+    k_solve_begin<<<1, 1, 0, stream_>>>(d.solveState);
+    for (int i = 0; i < p.numIterations; ++i) {
+        launchLocal(d.q[0], false);
+        if (opt_.rotMode == 1) k_vertex_rhs<false><<<vg, vb, 0, stream_>>>(nV_, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, wdbc, d.rhs);
+        else k_vertex_rhs<true><<<vg, vb, 0, stream_>>>(nV_, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, wdbc, d.rhs);
+        if (p.globalSolver == 2) {
+            const float4* b = d.rhs; float4 *x = d.q[0], *r = d.cgR, *pp = d.cgP, *qq = d.cgQ, *xp = d.xprev;
+            int maxIter = p.pcgMaxIter; float cgTol = p.pcgTol, pdTol = p.tol;
+            SolveState* st = d.solveState; double* part = d.partials;
+            void* args[] = {&d.A, &b, &x, &r, &pp, &qq, &xp, &maxIter, &cgTol, &pdTol, &st, &part};
+            CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_pcg_solve, dim3(d.solveGrid), dim3(SOLVE_THREADS), args, 0, stream_));
+        } else {
+            const float4* b = d.rhs; float4 *x = d.q[0], *y = d.cholY, *xp = d.xprev; int* rdy = d.cholReadyFlags;
+            int tag = d.cholEpoch++; float pdTol = p.tol;
+            SolveState* st = d.solveState; double* part = d.partials;
+            void* args[] = {&d.C, &b, &x, &y, &xp, &rdy, &tag, &pdTol, &st, &part};
+            CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(d.solveGrid), dim3(SOLVE_THREADS), args, 0, stream_));
+        }
+    }
+    k_finish<<<vg, vb, 0, stream_>>>(nV_, d.q[0], dtInv, d.X, d.XT, d.V, d.fb, p.muT, p.muN);
+}
+
+const CsrMatrix& Engine::systemMatrix()
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    if (!ready_) prepare();
+    const int saved = params_.globalSolver;
+    if (saved == 0) params_.globalSolver = 2;      // build the matrix only, no factorisation
+    try { prepareSolver(); } catch (...) { params_.globalSolver = saved; throw; }
+    params_.globalSolver = saved;
+    return hostA_;
+}
+
+// PD / inner iteration counts of the non-Jacobi modes live on the device; fold them into the host counters
+void Engine::syncSolveStats()
+{
+    Impl& d = *d_;
+    if (!d.solveState) return;
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    SolveState st;
+    CUDA_CHECK(cudaMemcpy(&st, d.solveState, sizeof(st), cudaMemcpyDeviceToHost));
+    perfc_.pdIterations += st.pdItersTotal;
+    perfc_.innerIterations += st.innerIters;
+    lastErr_ = st.err; lastPdIters_ = st.pdIters;
+    st.pdItersTotal = 0; st.innerIters = 0;
+    CUDA_CHECK(cudaMemcpy(d.solveState, &st, sizeof(st), cudaMemcpyHostToDevice));
+}
+
+// ---------------------------------------------------------------- multi-GPU plumbing
+void Engine::windowHandle(void* out64)
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    cudaIpcMemHandle_t h;
+    CUDA_CHECK(cudaIpcGetMemHandle(&h, d_->window));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(out64, &h, 64);
+}
+
+// peerBase[r] = base of rank r's exchange window as seen from this device (nullptr for non-neighbours)
+void Engine::setPeers(const std::vector<uint8_t*>& peerBase)
+{
+    Impl& d = *d_;
+    const RankPlan& P = plan_;
+    d.nNbr = (int)P.neighbours.size();
+    d.nPush = (int)P.pushSrc.size();
+    std::vector<float4*> pq((size_t)3 * std::max(d.nNbr, 1));
+    std::vector<unsigned long long*> pf((size_t)std::max(d.nNbr, 1));
+    std::vector<int> nbrIndexOfRank((size_t)opt_.world, -1);
+    for (int j = 0; j < d.nNbr; ++j) {
+        const int r = P.neighbours[(size_t)j];
+        if (!peerBase[(size_t)r]) throw std::runtime_error("missing exchange window of neighbour rank " + std::to_string(r));
+        nbrIndexOfRank[(size_t)r] = j;
+        const size_t nLocR = (size_t)P.nLocOf[(size_t)r];
+        for (int k = 0; k < 3; ++k) pq[(size_t)k * d.nNbr + j] = reinterpret_cast<float4*>(peerBase[(size_t)r]) + (size_t)k * nLocR;
+        pf[(size_t)j] = reinterpret_cast<unsigned long long*>(peerBase[(size_t)r] + 3 * nLocR * 16) + opt_.rank;
+    }
+    std::vector<uint32_t> nb((size_t)std::max(d.nPush, 1));
+    for (int i = 0; i < d.nPush; ++i) nb[(size_t)i] = (uint32_t)nbrIndexOfRank[(size_t)P.pushRank[(size_t)i]];
+    d.pushSrc = dalloc<uint32_t>(d.nPush); d.pushDst = dalloc<uint32_t>(d.nPush); d.pushNbr = dalloc<uint32_t>(d.nPush);
+    d.nbrRanks = dalloc<int>(d.nNbr);
+    d.peerQ = dalloc<float4*>(3 * (size_t)d.nNbr); d.peerFlag = dalloc<unsigned long long*>(d.nNbr);
+    if (d.nPush) {
+        CUDA_CHECK(cudaMemcpy(d.pushSrc, P.pushSrc.data(), (size_t)d.nPush * 4, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(d.pushDst, P.pushDst.data(), (size_t)d.nPush * 4, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(d.pushNbr, nb.data(), (size_t)d.nPush * 4, cudaMemcpyHostToDevice));
+    }
+    if (d.nNbr) {
+        CUDA_CHECK(cudaMemcpy(d.nbrRanks, P.neighbours.data(), (size_t)d.nNbr * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(d.peerQ, pq.data(), (size_t)3 * d.nNbr * sizeof(float4*), cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(d.peerFlag, pf.data(), (size_t)d.nNbr * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
+    }
+    d.wait = DistWait{d.flags, d.epoch, d.nbrRanks, d.nNbr, plan_.nInteriorTiles, d.status};
+    connected_ = true;
+}
+
+void Engine::connectIpc(const void* handles)
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    if (opt_.world == 1) { connected_ = true; return; }
+    std::vector<uint8_t*> base((size_t)opt_.world, nullptr);
+    for (int r : plan_.neighbours) {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const uint8_t*>(handles) + 64 * (size_t)r, 64);
+        void* p = nullptr;
+        CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        d_->ipcOpened.push_back(p);
+        base[(size_t)r] = static_cast<uint8_t*>(p);
+    }
+    setPeers(base);
+}
+
+void Engine::connectLocal(Engine* const* engines, int n)
+{
+    for (int r = 0; r < n; ++r) {
+        Engine* e = engines[r];
+        if (e->opt_.world != n || e->opt_.rank != r) throw std::runtime_error("connectLocal: engines must be ranks 0..n-1 of world n, in order");
+        CUDA_CHECK(cudaSetDevice(e->opt_.device));
+        std::vector<uint8_t*> base((size_t)n, nullptr);
+        for (int q : e->plan_.neighbours) {
+            if (engines[q]->opt_.device != e->opt_.device) {
+                int can = 0;
+                CUDA_CHECK(cudaDeviceCanAccessPeer(&can, e->opt_.device, engines[q]->opt_.device));
+                if (!can) throw std::runtime_error("connectLocal: no peer access between the devices");
+                cudaError_t pe = cudaDeviceEnablePeerAccess(engines[q]->opt_.device, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CUDA_CHECK(pe);
+                cudaGetLastError();
+            }
+            base[(size_t)q] = engines[q]->d_->window;
+        }
+        e->setPeers(base);
+    }
+}
+
+// One host thread drives all ranks phase by phase (tests on one GPU, where a rank's local kernel could
+// otherwise occupy every SM while it waits for a neighbour that cannot be scheduled): after each phase every
+// stream waits for every other stream, so all halo flags are already up when a local kernel starts.
+void Engine::stepLockstep(Engine* const* engines, int n, int nSteps)
+{
+    auto crossSync = [&]() {
+        for (int r = 0; r < n; ++r) {
+            Engine* e = engines[r];
+            CUDA_CHECK(cudaSetDevice(e->opt_.device));
+            if (!e->d_->lockEvent) CUDA_CHECK(cudaEventCreateWithFlags(&e->d_->lockEvent, cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventRecord(e->d_->lockEvent, e->stream_));
+        }
+        for (int r = 0; r < n; ++r)
+            for (int q = 0; q < n; ++q)
+                if (q != r) { CUDA_CHECK(cudaSetDevice(engines[r]->opt_.device)); CUDA_CHECK(cudaStreamWaitEvent(engines[r]->stream_, engines[q]->d_->lockEvent, 0)); }
+    };
+    for (int r = 0; r < n; ++r) {
+        CUDA_CHECK(cudaSetDevice(engines[r]->opt_.device));
+        if (engines[r]->params_.globalSolver != 0) throw std::runtime_error("stepLockstep: Jacobi global solver only");
+        if (!engines[r]->ready_) engines[r]->prepare();
+    }
+    const int iters = engines[0]->params_.numIterations;
+    for (int s = 0; s < nSteps; ++s) {
+        for (int r = 0; r < n; ++r) { CUDA_CHECK(cudaSetDevice(engines[r]->opt_.device)); engines[r]->enqueuePredict(); }
+        crossSync();
+        for (int i = 0; i < iters; ++i) {
+            for (int r = 0; r < n; ++r) { CUDA_CHECK(cudaSetDevice(engines[r]->opt_.device)); engines[r]->enqueueIteration(i, false, nullptr); }
+            crossSync();
+        }
+        for (int r = 0; r < n; ++r) {
+            CUDA_CHECK(cudaSetDevice(engines[r]->opt_.device));
+            engines[r]->enqueueFinish();
+            engines[r]->perfc_.steps += 1; engines[r]->perfc_.pdIterations += iters;
+        }
+    }
+    for (int r = 0; r < n; ++r) { CUDA_CHECK(cudaSetDevice(engines[r]->opt_.device)); CUDA_CHECK(cudaGetLastError()); }
+}
+
+unsigned int Engine::distStatus()
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    unsigned int s = 0;
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    CUDA_CHECK(cudaMemcpy(&s, d_->status, 4, cudaMemcpyDeviceToHost));
+    return s;
 }
 
 // per-phase clock totals of the local kernel (warp 0 of every CTA): out[8 * localGrid()]

@@ -25,6 +25,7 @@ struct EngineOptions {
     int reorder = 1;        // Morton reordering of tets / first-touch renumbering of vertices
     int useGraph = 1;       // replay each step as one CUDA graph
     int ctasPerSm = 0;      // 0 = occupancy query
+    int rank = 0, world = 1; // multi-GPU: this engine is rank `rank` of `world` (one process per GPU)
 };
 
 class Engine {
@@ -51,10 +52,24 @@ public:
     void stepHost(int nSteps, const float* Xin, const float* Vin, const float* XTin, float* Xout, float* Vout, float* XTout);
 
     const PerfCounters& perf() const { return perfc_; }
+    void syncSolveStats();                                  // PCG / Cholesky modes: fold the device-side iteration counters in
+    float lastError() const { return lastErr_; }
+    int lastPdIterations() const { return lastPdIters_; }
+    const CsrMatrix& systemMatrix();                        // A^ in the renumbered vertex ids (builds it if needed)
     void resetPerf() { perfc_ = PerfCounters(); }
     const Layout& layout() const { return L_; }
-    int numVerts() const { return nV_; }
-    int numTets() const { return nT_; }
+    int numVerts() const { return nV_; }        // vertices held by this engine (owned + ghosts when world > 1)
+    int numTets() const { return nT_; }         // tets evaluated by this engine
+    int numOwned() const { return nOwn_; }
+    int numVertsGlobal() const { return scene_.numVerts; }
+    int numTetsGlobal() const { return scene_.numTets; }
+    // ---- multi-GPU (world > 1)
+    const RankPlan& plan() const { return plan_; }
+    void windowHandle(void* out64);                                // cudaIpcMemHandle_t of this rank's exchange window
+    void connectIpc(const void* handles);                          // world x 64 bytes in rank order (other processes)
+    static void connectLocal(Engine* const* engines, int n);       // all ranks inside one process (tests)
+    static void stepLockstep(Engine* const* engines, int n, int nSteps);   // one process driving all ranks phase by phase
+    unsigned int distStatus();                                     // nonzero: a halo wait timed out
     // setup products in the ORIGINAL numbering/order (for parity checks against the oracle)
     void getSetup(float* matrixDiag, float* massDt2, float* DmInv, float* V0);
     // launch geometry, for the bench's launch count / roofline bookkeeping
@@ -72,10 +87,25 @@ private:
     void prepare();
     void buildGraph();
     void enqueueStep(bool timed);
+    void prepareSolver();
+    void enqueueStepSolver();
+    void enqueuePredict();
+    void enqueueIteration(int i, bool timed, size_t* ev);
+    void enqueueFinish();
+    void enqueuePush(const float4* q, int bufIndex);
+    void setPeers(const std::vector<uint8_t*>& peerBase);
+    float* qbuf(int k) const;
     void launchLocal(const float4* q, bool jacobi, unsigned long long* prof = nullptr);
     template <typename T> T* dalloc(size_t n);
 
-    int nV_ = 0, nT_ = 0;
+    int nV_ = 0, nT_ = 0, nOwn_ = 0;
+    RankPlan plan_;
+    long long phase_ = 0;     // multi-GPU: phases (predictor / iteration) completed so far; buffer rotation base = phase_ % 3
+    int base_ = 0;            // position-buffer index of the current step's predictor output
+    float omega_ = 1.f;
+    CsrMatrix hostA_;         // scalar system matrix (renumbered ids), kept for the Cholesky factorisation and the parity tests
+    float lastErr_ = 1.f; int lastPdIters_ = 0;
+    bool connected_ = false;
     Scene scene_;             // host copy (original numbering)
     Layout L_;
     SolverParams params_;

@@ -73,6 +73,67 @@ __device__ __forceinline__ float4 ldg_hint(const float4* p, unsigned long long p
     return v;
 }
 
+// ------------------------------------------------------------------ multi-GPU halo exchange
+// Every rank owns an exchange window [q0 | q1 | q2 | flags[world] | epoch | ticket | status] that its
+// neighbours map (CUDA IPC, or plain pointers inside one process).  After each phase that produces new
+// positions (predictor, every PD iteration) the owner PUSHES the positions of its boundary vertices straight
+// into the neighbours' ghost entries over NVLink (k_halo_push) and then raises its flag there to its push
+// count (epoch).  The consumer is the next local kernel: before touching any position it waits until every
+// neighbour's flag has reached its own epoch -- all ranks push the same number of times in the same order.
+struct DistWait {
+    const unsigned long long* flags;   // this rank's flag array, written by the peers (indexed by rank)
+    const unsigned long long* epoch;   // this rank's own push count
+    const int* nbr;                    // neighbour ranks
+    int nNbr;                          // 0 on a single GPU: no wait at all
+    int firstTile;                     // first tile (in this rank's processing order) that reads ghost positions
+    unsigned int* status;              // set to 1 when a wait gave up (peer died); results are then invalid
+};
+constexpr long long DIST_WAIT_LIMIT_CYCLES = 20000000000ll;    // ~10 s: a hung peer must not hang this GPU
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void dist_wait(const DistWait& w, int tid)
+{
+    if (tid < w.nNbr) {
+        const unsigned long long need = ld_acquire_sys(w.epoch);
+        const unsigned long long* f = w.flags + w.nbr[tid];
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < need) {
+            if (clock64() - t0 > DIST_WAIT_LIMIT_CYCLES) { atomicExch(w.status, 1u); break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+
+// positions of this rank's boundary vertices -> the neighbours' ghost entries, then (last block) the flags
+__global__ void k_halo_push(int n, const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst, const uint32_t* __restrict__ nbrIdx,
+                            const float4* __restrict__ q, float4* const* __restrict__ peerQ, int nNbr,
+                            unsigned long long* const* __restrict__ peerFlag, unsigned long long* epoch, unsigned int* ticket)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) peerQ[nbrIdx[i]][dst[i]] = q[src[i]];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) {                      // every block's stores are fenced: publish
+            *ticket = 0u;
+            const unsigned long long e = *epoch + 1ull;
+            *epoch = e;
+            __threadfence_system();
+            for (int j = 0; j < nNbr; ++j) st_release_sys(peerFlag[j], e);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ predictor
 // gravity transform + setMDt_2MoreDBC + computeSn + the two D2D copies + addM_h2Sn
 // (pdSolver.cu:154-160, pdUtil.cu:56-95,168-179).  moreDBC == 0 (no mouse drag on the headless path).
@@ -205,7 +266,7 @@ template <int ROT_MODE, bool JACOBI, bool PROF = false>
 __global__ void __launch_bounds__(TILE_T, 4)
 k_local(const uint8_t* __restrict__ records, const uint4* __restrict__ tileTab, int nTiles,
         const uint32_t* __restrict__ vlist, const float4* __restrict__ q, const float4* __restrict__ b0, float4* __restrict__ P,
-        unsigned long long* __restrict__ prof)
+        unsigned long long* __restrict__ prof, DistWait dw)
 {
     // prof (may be null): per-phase clock64 totals of warp 0 of every CTA, 8 counters per CTA (scripts/phase_profile.py)
     extern __shared__ __align__(128) uint8_t smem[];
@@ -223,6 +284,12 @@ k_local(const uint8_t* __restrict__ records, const uint4* __restrict__ tileTab, 
     }
     if (tid < 8) *reinterpret_cast<float4*>(smem + LOCAL_OFF_HS + TILE_ZERO_OFF + 16 * tid) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
+    // multi-GPU: the rank's interior tiles come first; the neighbours' ghost positions are needed -- and waited
+    // for -- only before the position gather of the first boundary tile, so the exchange hides behind the interior
+    bool needHalo = dw.nNbr > 0;
+    auto halo_before = [&](int k) {
+        if (needHalo && (int)(blockIdx.x + k * gridDim.x) >= dw.firstTile) { dist_wait(dw, tid); needHalo = false; }
+    };
 
     // producer (thread 0): part AB of the tile whose table entry is `te` -> buffer k & 1
     auto fetch_ab = [&](int k, uint4 te) {
@@ -262,6 +329,7 @@ k_local(const uint8_t* __restrict__ records, const uint4* __restrict__ tileTab, 
         if (nIt > 2) prefetch_entry(2);
     }
     uint32_t veCur = load_ve(0);                             // vlist entry of this thread: tile it
+    halo_before(0);
     gather(veCur);
     uint32_t veNext = (nIt > 1) ? load_ve(1) : 0xffffffffu;  // tile it + 1
     uint32_t vePrev = 0xffffffffu, gtPrev = 0;
@@ -277,6 +345,7 @@ k_local(const uint8_t* __restrict__ records, const uint4* __restrict__ tileTab, 
         // a whole tile ahead: start the position gather of tile it+1 (its staging buffer was last read in
         // phase B of tile it-1) and fetch the vertex ids of tile it+2
         if (producer && it + 3 < nIt) prefetch_entry(it + 3);
+        if (it + 1 < nIt) halo_before(it + 1);
         gather(veNext);
         const uint32_t veNext2 = (it + 2 < nIt) ? load_ve(it + 2) : 0xffffffffu;
         PD_TICK(0)

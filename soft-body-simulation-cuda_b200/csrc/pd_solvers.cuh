@@ -1,0 +1,259 @@
+// Global-step back-ends other than Chebyshev-Jacobi: Jacobi-preconditioned CG and the prefactored sparse
+// Cholesky solve, both on the SCALAR system matrix A^ (nV x nV) with the three coordinate right-hand sides
+// interleaved as float4 -- the reference's 3nV x 3nV matrix is A^ (x) I3 (pdUtil.cu:26-37 writes the same K_ji to
+// the x, y and z rows), so one pass over A^ serves all three.
+//   PCG      : PCGJacobiSolver<float>::Solve, src/simulation/solver/linear/pcgJacobi.cu:88-172
+//   Cholesky : CholeskySpLinearSolver<float>, src/simulation/solver/linear/cholesky.cu:133-192 (cuSOLVER) and
+//              Eigen::SimplicialCholesky, src/simulation/solver/projective/pdSolver.cu:103,181-183
+// Both run as ONE persistent cooperative kernel per solve: no host round trips for the scalars (the reference
+// reads three of them back per CG iteration), no library calls.
+#pragma once
+#include <cstdint>
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+namespace pdb200 {
+namespace cg = cooperative_groups;
+
+// device-resident bookkeeping of the non-Jacobi modes (one per engine)
+struct SolveState {
+    float err;               // computeError (pdSolver.cu:243-253): mean squared change of the iterate
+    int done;                // sqrt(err) < tol reached: the remaining PD iterations of this step are skipped
+    int pdIters;             // PD iterations executed (this step)
+    long long innerIters;    // CG iterations executed (accumulated)
+    long long pdItersTotal;
+};
+
+struct CsrDev {
+    int n;
+    const int* rowPtr;
+    const int* col;
+    const float* val;
+    const float* invDiag;    // ExtractInverseDiagonalKernel, pcgJacobi.cu:6-19
+};
+
+constexpr int SOLVE_THREADS = 256;
+constexpr int SOLVE_MAX_PARTIALS = 2048;       // >= grid size of the cooperative kernels
+
+// Deterministic grid-wide sum of up to three doubles per thread: warp shuffle -> block -> one slot per block ->
+// grid.sync -> every block adds the slots in the same fixed order.  Returns the sums in out[0..2].
+__device__ __forceinline__ void grid_sum3(cg::grid_group& grid, double a, double b, double c, double* partials /* 3 * gridDim */,
+                                          double* sh /* 3 * 8 + 3 doubles of shared memory */, double out[3])
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        b += __shfl_down_sync(0xffffffffu, b, o);
+        c += __shfl_down_sync(0xffffffffu, c, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sh[warp] = a; sh[8 + warp] = b; sh[16 + warp] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sa = 0, sb = 0, sc = 0;
+        for (int w = 0; w < SOLVE_THREADS / 32; ++w) { sa += sh[w]; sb += sh[8 + w]; sc += sh[16 + w]; }
+        partials[3 * blockIdx.x] = sa; partials[3 * blockIdx.x + 1] = sb; partials[3 * blockIdx.x + 2] = sc;
+    }
+    grid.sync();
+    if (warp == 0) {
+        double sa = 0, sb = 0, sc = 0;
+        for (int i = lane; i < (int)gridDim.x; i += 32) { sa += partials[3 * i]; sb += partials[3 * i + 1]; sc += partials[3 * i + 2]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+            sc += __shfl_xor_sync(0xffffffffu, sc, o);
+        }
+        if (lane == 0) { sh[24] = sa; sh[25] = sb; sh[26] = sc; }
+    }
+    __syncthreads();
+    out[0] = sh[24]; out[1] = sh[25]; out[2] = sh[26];
+    grid.sync();          // the partial slots may be overwritten by the next reduction
+}
+
+// row v of y = A^ x for the three interleaved right-hand sides (CSR, ascending columns, one thread per row)
+__device__ __forceinline__ float4 spmv_row(const CsrDev& A, int v, const float4* __restrict__ x)
+{
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    const int e1 = A.rowPtr[v + 1];
+    for (int e = A.rowPtr[v]; e < e1; ++e) {
+        const float a = A.val[e];
+        const float4 xc = x[A.col[e]];
+        a0 = __fadd_rn(a0, __fmul_rn(a, xc.x)); a1 = __fadd_rn(a1, __fmul_rn(a, xc.y)); a2 = __fadd_rn(a2, __fmul_rn(a, xc.z));
+    }
+    return make_float4(a0, a1, a2, 0.f);
+}
+
+// computeError + prev = x, fused into the tail of both solve kernels (pdSolver.cu:186-192,243-253)
+__device__ __forceinline__ void finish_pd_iteration(cg::grid_group& grid, int n, const float4* x, float4* xprev, float tol, SolveState* st,
+                                                    int innerIters, double* partials, double* sh)
+{
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+    double acc = 0;
+    for (int v = gtid; v < n; v += gstride) {
+        const float4 a = xprev[v], b = x[v];
+        const double dx = (double)a.x - (double)b.x, dy = (double)a.y - (double)b.y, dz = (double)a.z - (double)b.z;
+        acc += dx * dx + dy * dy + dz * dz;
+        xprev[v] = b;
+    }
+    double s[3];
+    grid_sum3(grid, acc, 0.0, 0.0, partials, sh, s);
+    if (gtid == 0) {
+        const float err = (float)(s[0] / (3.0 * (double)n));
+        st->err = err;
+        st->pdIters += 1; st->pdItersTotal += 1; st->innerIters += innerIters;
+        if (!(sqrtf(err) >= tol)) st->done = 1;
+    }
+}
+
+// ------------------------------------------------------------------ Jacobi-preconditioned CG
+// One launch = one PCGJacobiSolver::Solve with d_guess = x (warm start), pcgJacobi.cu:88-172:
+//   r = b - A x;  loop k < max_iter: ||r||_2 < tol -> stop; z = D^-1 r; rho = r.z (|rho| < 1e-15 -> stop);
+//   p = z + (rho/rho_prev) p; q = A p; alpha = rho / (p.q); x += alpha p; r -= alpha q.
+// Dots accumulate in double and are rounded to float where the reference holds a float (cublasSdot results);
+// vector updates use the same unfused multiply-then-add as the oracle (oracle/pd_oracle.c:pcg_solve).
+// Three grid-wide synchronisations per CG iteration (p update | SpMV + p.q | x, r update + r.r, r.z).
+__global__ void __launch_bounds__(SOLVE_THREADS)
+k_pcg_solve(CsrDev A, const float4* __restrict__ b, float4* __restrict__ x, float4* __restrict__ r, float4* __restrict__ p, float4* __restrict__ q,
+            float4* __restrict__ xprev, int maxIter, float cgTol, float pdTol, SolveState* st, double* partials)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[27];
+    if (st->done) return;                       // uniform over the grid: this PD iteration is skipped
+    const int n = A.n, gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+    double s[3];
+    // r = b - A x ; rr = r.r ; rz = r.(D^-1 r)
+    double arr = 0, arz = 0;
+    for (int v = gtid; v < n; v += gstride) {
+        const float4 ax = spmv_row(A, v, x), bb = b[v];
+        const float4 rv = make_float4(__fsub_rn(bb.x, ax.x), __fsub_rn(bb.y, ax.y), __fsub_rn(bb.z, ax.z), 0.f);
+        r[v] = rv;
+        const float id = A.invDiag[v];
+        arr += (double)rv.x * rv.x + (double)rv.y * rv.y + (double)rv.z * rv.z;
+        arz += (double)rv.x * (double)__fmul_rn(rv.x, id) + (double)rv.y * (double)__fmul_rn(rv.y, id) + (double)rv.z * (double)__fmul_rn(rv.z, id);
+    }
+    grid_sum3(grid, arr, arz, 0.0, partials, sh, s);
+    float rho = (float)s[1], rhoPrev = 0.f;
+    float rn = sqrtf((float)s[0]);
+    int k = 0;
+    for (; k < maxIter; ++k) {
+        if (rn < cgTol) break;
+        if (fabsf(rho) < 1e-15f) break;
+        const float beta = (k == 0) ? 0.f : __fdiv_rn(rho, rhoPrev);
+        for (int v = gtid; v < n; v += gstride) {       // p = z + beta p   (k == 0: p = z)
+            const float4 rv = r[v];
+            const float id = A.invDiag[v];
+            const float zx = __fmul_rn(rv.x, id), zy = __fmul_rn(rv.y, id), zz = __fmul_rn(rv.z, id);
+            float4 pv = make_float4(zx, zy, zz, 0.f);
+            if (k > 0) {
+                const float4 po = p[v];
+                pv.x = __fadd_rn(__fmul_rn(beta, po.x), zx); pv.y = __fadd_rn(__fmul_rn(beta, po.y), zy); pv.z = __fadd_rn(__fmul_rn(beta, po.z), zz);
+            }
+            p[v] = pv;
+        }
+        grid.sync();
+        double apq = 0;
+        for (int v = gtid; v < n; v += gstride) {       // q = A p ; p.q
+            const float4 qv = spmv_row(A, v, p), pv = p[v];
+            q[v] = qv;
+            apq += (double)pv.x * qv.x + (double)pv.y * qv.y + (double)pv.z * qv.z;
+        }
+        grid_sum3(grid, apq, 0.0, 0.0, partials, sh, s);
+        const float alpha = __fdiv_rn(rho, (float)s[0]);
+        arr = 0; arz = 0;
+        for (int v = gtid; v < n; v += gstride) {       // x += alpha p ; r -= alpha q ; r.r ; r.z
+            const float4 pv = p[v], qv = q[v];
+            float4 xv = x[v], rv = r[v];
+            xv.x = __fadd_rn(xv.x, __fmul_rn(alpha, pv.x)); xv.y = __fadd_rn(xv.y, __fmul_rn(alpha, pv.y)); xv.z = __fadd_rn(xv.z, __fmul_rn(alpha, pv.z));
+            rv.x = __fsub_rn(rv.x, __fmul_rn(alpha, qv.x)); rv.y = __fsub_rn(rv.y, __fmul_rn(alpha, qv.y)); rv.z = __fsub_rn(rv.z, __fmul_rn(alpha, qv.z));
+            x[v] = xv; r[v] = rv;
+            const float id = A.invDiag[v];
+            arr += (double)rv.x * rv.x + (double)rv.y * rv.y + (double)rv.z * rv.z;
+            arz += (double)rv.x * (double)__fmul_rn(rv.x, id) + (double)rv.y * (double)__fmul_rn(rv.y, id) + (double)rv.z * (double)__fmul_rn(rv.z, id);
+        }
+        grid_sum3(grid, arr, arz, 0.0, partials, sh, s);
+        rhoPrev = rho;
+        rho = (float)s[1];
+        rn = sqrtf((float)s[0]);
+    }
+    finish_pd_iteration(grid, n, x, xprev, pdTol, st, k, partials, sh);
+}
+
+// ------------------------------------------------------------------ prefactored sparse Cholesky solve
+// A^ = L L^T was factored once on the host (pd_engine.cu:factorize; the reference does the same inside
+// SolverPrepare with cusolverSpXcsrcholFactor / Eigen::SimplicialCholesky).  Per PD iteration: L y = b, L^T x = y for
+// the three right-hand sides, as a "synchronisation-free" sparse triangular solve: one thread per row, every row
+// waits for the rows it depends on through a ready counter in global memory.  The kernel is launched
+// cooperatively, so every row's thread is resident and the ascending (descending for L^T) dependency order
+// guarantees progress.  L is stored by rows (CSR, diagonal last) and L^T by rows as well (CSR, diagonal first).
+struct CholDev {
+    int n;
+    const int *lPtr, *lCol; const float* lVal;        // L   by rows, ascending columns, diagonal LAST
+    const int *uPtr, *uCol; const float* uVal;        // L^T by rows, ascending columns, diagonal FIRST
+};
+
+__device__ __forceinline__ float4 ld_volatile4(const float4* p)
+{
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS)
+k_chol_solve(CholDev C, const float4* __restrict__ b, float4* x, float4* y, float4* __restrict__ xprev, int* ready /* n, zero on entry */,
+             int epochTag, float pdTol, SolveState* st, double* partials)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[27];
+    if (st->done) return;
+    const int n = C.n, gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+    // forward: row i needs y[j] for every off-diagonal L_ij.  ready[j] == tag: y[j] is final.
+    const int tagF = 2 * epochTag + 1, tagB = 2 * epochTag + 2;
+    for (int i = gtid; i < n; i += gstride) {
+        const float4 bb = b[i];
+        float a0 = bb.x, a1 = bb.y, a2 = bb.z;
+        const int e1 = C.lPtr[i + 1] - 1;
+        for (int e = C.lPtr[i]; e < e1; ++e) {
+            const int j = C.lCol[e];
+            while (*reinterpret_cast<volatile int*>(ready + j) != tagF) { }
+            __threadfence();
+            const float4 yj = ld_volatile4(y + j);
+            const float l = C.lVal[e];
+            a0 = __fmaf_rn(-l, yj.x, a0); a1 = __fmaf_rn(-l, yj.y, a1); a2 = __fmaf_rn(-l, yj.z, a2);
+        }
+        const float d = C.lVal[e1];
+        y[i] = make_float4(__fdiv_rn(a0, d), __fdiv_rn(a1, d), __fdiv_rn(a2, d), 0.f);
+        __threadfence();
+        *reinterpret_cast<volatile int*>(ready + i) = tagF;
+    }
+    grid.sync();
+    // backward: row i of L^T needs x[j], j > i; rows are taken in descending order
+    for (int t = gtid; t < n; t += gstride) {
+        const int i = n - 1 - t;
+        const float4 yy = ld_volatile4(y + i);
+        float a0 = yy.x, a1 = yy.y, a2 = yy.z;
+        const int e0 = C.uPtr[i], e1 = C.uPtr[i + 1];
+        for (int e = e1 - 1; e > e0; --e) {
+            const int j = C.uCol[e];
+            while (*reinterpret_cast<volatile int*>(ready + j) != tagB) { }
+            __threadfence();
+            const float4 xj = ld_volatile4(x + j);
+            const float l = C.uVal[e];
+            a0 = __fmaf_rn(-l, xj.x, a0); a1 = __fmaf_rn(-l, xj.y, a1); a2 = __fmaf_rn(-l, xj.z, a2);
+        }
+        const float d = C.uVal[e0];
+        x[i] = make_float4(__fdiv_rn(a0, d), __fdiv_rn(a1, d), __fdiv_rn(a2, d), 0.f);
+        __threadfence();
+        *reinterpret_cast<volatile int*>(ready + i) = tagB;
+    }
+    grid.sync();
+    finish_pd_iteration(grid, n, x, xprev, pdTol, st, 0, partials, sh);
+}
+
+// start of a step in the non-Jacobi modes: err = 1, nothing skipped (pdSolver.cu:163)
+__global__ void k_solve_begin(SolveState* st)
+{
+    st->err = 1.0f; st->done = 0; st->pdIters = 0;
+}
+
+}  // namespace pdb200

@@ -1,0 +1,107 @@
+"""Global-step back-ends other than Chebyshev-Jacobi, on the GPU, against the CPU oracle:
+Jacobi-preconditioned CG (pcgJacobi.cu:88-172) and the prefactored sparse Cholesky solve (cholesky.cu:133-192 /
+Eigen::SimplicialCholesky, pdSolver.cu:103,181-183) inside PdSolver::SolverStep's non-Jacobi branch (pdSolver.cu:174-192).
+The reference's tests pin neither; the oracle restates pcgJacobi.cu operation for operation and
+stands in a dense double Cholesky for the direct solves."""
+import numpy as np
+import pytest
+
+import meshes
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4       # BASELINE.json: max vertex-position relative error
+
+
+def _grid(pd, n=6):
+    sc = pd.Scene.kuhn_grid(n, n, n, 1.0, 0.05, 9, (0, 4, 0), 1.0, 2e5)
+    sc.add_fixed(pd.fixed_body(pd.PD_PLANE, pos=(0, 0, 0), scale=(450, 450, 450)))
+    return sc
+
+
+def _oracle_of(O, sc):
+    a = sc.arrays()
+    return O.Scene(a["X"], a["Tet"], a["mass"], a["mu"], DBC=a["DBC"], planes=[(np.zeros(3, np.float32), np.array([0, 1, 0], np.float32))])
+
+
+def _v0(X):
+    V = np.zeros_like(X); V[:, 1] = 0.4 * np.sin(X[:, 0]); V[:, 0] = 0.2 * np.cos(X[:, 2])
+    return V
+
+
+def test_system_matrix_vs_oracle(pd, O):
+    import scipy.sparse as sp
+    sc = _grid(pd)
+    sc.params = pd.SolverParams(dt=1 / 60, gravity=9.8, num_iterations=5)
+    eng = pd.PdSolver(sc)
+    rp, col, val = eng.system_matrix()
+    n = rp.shape[0] - 1
+    order = sc.layout().vert_order.astype(np.int64)              # renumbered -> original
+    A = sp.csr_matrix((val.astype(np.float64), col, rp), shape=(n, n)).tocoo()
+    A = sp.csr_matrix((A.data, (order[A.row], order[A.col])), shape=(n, n))
+    orp, ocol, oval = _oracle_of(O, sc).system_matrix(O.make_params(dt=1 / 60, gravity=9.8, num_iterations=5))
+    Ao = sp.csr_matrix((oval.astype(np.float64), ocol, orp), shape=(n, n))
+    assert (A != 0).nnz == (Ao != 0).nnz and abs(A - Ao).max() <= 2e-6 * abs(Ao).max()
+    md, c, _, _ = eng.setup()
+    assert np.allclose(A.diagonal(), (md + c).astype(np.float64), rtol=2e-6)        # diag(A^) = matrix_diag + M/h^2
+    assert abs(np.asarray((A - sp.diags(c.astype(np.float64))).sum(1)).ravel()).max() <= 1e-5 * abs(Ao).max()   # Laplacian rows sum to 0
+
+
+@pytest.mark.parametrize("solver,name", [(2, "PCG-Jacobi"), (1, "sparse Cholesky")])
+def test_solver_modes_vs_oracle(pd, O, solver, name):
+    sc = _grid(pd)
+    kw = dict(dt=1 / 60, gravity=9.8, num_iterations=8, tol=1e-6)
+    p = pd.SolverParams(global_solver=solver, pcg_max_iter=60, pcg_tol=1e-5, **kw)
+    sc.params = p
+    X0 = sc.arrays()["X"]
+    eng = pd.PdSolver(sc)
+    eng.upload(V=_v0(X0))
+    osc = _oracle_of(O, sc)
+    osc.set(V=_v0(X0))
+    op = O.make_params(global_solver=solver, pcg_max_iter=60, pcg_tol=1e-5, **kw)
+    worst = 0.0
+    for s in range(6):
+        eng.Update(1)
+        osc.step(op, 1)
+        X = eng.download()[0]
+        worst = max(worst, meshes.rel_err(X, osc.get()[0]))
+    err, it = eng.solve_stats()
+    print(f"{name}: worst rel err vs oracle over 6 steps {worst:.2e}; last step: {it} PD iterations, computeError {err:.3e}; oracle {osc.stats()}")
+    assert np.abs(X - X0).max() > 1e-3 and worst <= TOL
+    perf = eng.GetPerformanceData()[1]
+    assert 6 <= perf.pd_iterations <= 6 * 8 and (solver != 2 or 0 < perf.inner_iterations <= 6 * 8 * 60)
+
+
+def test_direct_mode_stops_on_tolerance_like_the_reference(pd, O, assets):
+    """pdSolver.cu:164,186-192: the non-Jacobi loop ends when sqrt(computeError) < tol.  The device-side flag must
+    stop after the same number of PD iterations as the oracle's host loop."""
+    sc = pd.Scene.from_json(assets["json"], "C5 house&sphere")
+    p = sc.params
+    p["global_solver"] = 1; p["num_iterations"] = 30; p["tol"] = 2e-3
+    sc.params = p
+    eng = pd.PdSolver(sc)
+    osc, _ = meshes.oracle_scene(O, assets, "C5 house&sphere")
+    op = O.make_params(dt=p["dt"], gravity=p["gravity"], muN=p["muN"], muT=p["muT"], rho=p["rho"], num_iterations=30, tol=2e-3, global_solver=1)
+    for s in range(3):
+        eng.Update(1)
+        osc.step(op, 1)
+        err, it = eng.solve_stats()
+        assert it == osc.stats()[0] and it < 30, (s, it, osc.stats())
+    assert meshes.rel_err(eng.download()[0], osc.get()[0]) <= TOL
+
+
+def test_solver_switch_and_reset(pd):
+    """SetGlobalSolver between Updates (simulationContext.cpp:104-114) and Reset re-preparing the factorisation."""
+    sc = _grid(pd, 5)
+    sc.params = pd.SolverParams(dt=1 / 60, gravity=9.8, num_iterations=6, tol=1e-6, pcg_max_iter=40)
+    eng = pd.PdSolver(sc)
+    eng.Update(1)
+    for s in ("CuSolverCholesky", "PCGJacobi", "Jacobi", "EigenCholesky"):
+        eng.SetGlobalSolver(s)
+        eng.Update(1)
+    a = eng.download()[0]
+    eng.Reset()
+    eng.SetGlobalSolver("Jacobi"); eng.Update(1)
+    for s in ("CuSolverCholesky", "PCGJacobi", "Jacobi", "EigenCholesky"):
+        eng.SetGlobalSolver(s)
+        eng.Update(1)
+    assert np.isfinite(a).all() and np.array_equal(a, eng.download()[0])

@@ -182,3 +182,21 @@ def test_partition_vertices(pd):
         assert pd.lib().pd_partition_vertices(nV, w, vb.ctypes.data) == 0
         assert np.array_equal(vb, LO.partition_vertices(nV, w))
         assert vb[0] == 0 and vb[-1] == nV and (np.diff(vb) >= 0).all()
+
+
+def test_sparse_cholesky_prefactor_host(pd, O, assets):
+    """cholesky_factor (host side of the small-mesh direct path) on the oracle's system matrix: L L^T == A^."""
+    import scipy.sparse as sp
+    osc, _ = meshes.oracle_scene(O, assets, "C5 house&sphere")
+    rp, col, val = osc.system_matrix(O.make_params(dt=1 / 60, gravity=9.8, num_iterations=1))
+    n = rp.shape[0] - 1
+    A = sp.csr_matrix((val.astype(np.float64), col, rp), shape=(n, n))
+    assert abs(A - A.T).max() <= 1e-6 * abs(A).max()          # symmetric up to summation-order rounding
+    lp, lc, lv = pd.cholesky_factor(rp, col, val)
+    L = sp.csr_matrix((lv.astype(np.float64), lc, lp), shape=(n, n))
+    assert (lc[lp[1:] - 1] == np.arange(n)).all() and (np.diff(lp) >= 1).all()      # diagonal last in every row
+    assert sp.triu(L, 1).nnz == 0 and (L.diagonal() > 0).all()
+    R = (L @ L.T - A)
+    assert abs(R).max() <= 2e-6 * abs(A).max()
+    with pytest.raises(pd.PdError):      # not positive definite -> error, nothing returned
+        pd.cholesky_factor(np.array([0, 1, 2], np.int32), np.array([0, 1], np.int32), np.array([1.0, -1.0], np.float32))
