@@ -28,7 +28,10 @@ WORKLOADS = {
     "grid139": (139, 100, "Kuhn 6-tet grid 139^3 cells (2,744,000 verts, 16,113,714 tets), float PD, Chebyshev-Jacobi 100 it/step"),
     "grid55": (55, 100, "Kuhn 6-tet grid 55^3 cells (175,616 verts, 998,250 tets), float PD, Chebyshev-Jacobi 100 it/step"),
     "grid24": (24, 100, "Kuhn 6-tet grid 24^3 cells (82,944 tets) -- CPU-sized sample"),
+    # independent (house2 + sphere) contexts, 64 per GPU, no inter-GPU communication (weak scaling)
+    "batch64": (0, 100, "64 independent contexts per GPU, each house2 (1,389 tets) + sphere (1,217 tets) over a floor and a fixed sphere, float PD, Chebyshev-Jacobi 100 it/step"),
 }
+BATCH_PER_GPU = 64
 DT, GRAVITY, MU, MASS, JITTER, SEED = 1.0 / 60.0, 9.8, 2e5, 1.0, 0.05, 12345
 
 
@@ -87,7 +90,34 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_scene(pd, workload):
+def make_batch_scene(pd, first, count):
+    """Contexts first .. first+count-1 of the 512-context batch: the "C5 house&sphere" context of the
+    fixture (tests/meshes.py, regenerated from tests/golden/meshes.npz -- nothing is read from /root/reference), pose i =
+    base pose rotated about y by 2*pi*i/512 and lifted by (i mod 8)*5, merged into ONE scene (pd_scene_merge)."""
+    import tempfile
+    import meshes
+    with tempfile.TemporaryDirectory() as tmp:
+        assets = meshes.write_assets(tmp)
+        base = pd.Scene.from_json(assets["json"], "C5 house&sphere")
+    a = base.arrays(); p = base.params
+    p["num_iterations"] = WORKLOADS["batch64"][1]
+    scenes = []
+    for i in range(first, first + count):
+        th = np.float32(2.0 * np.pi * i / 512.0)
+        c, s_ = np.cos(th, dtype=np.float32), np.sin(th, dtype=np.float32)
+        X = a["X"].copy()
+        X[:, 0] = c * a["X"][:, 0] + s_ * a["X"][:, 2]
+        X[:, 2] = -s_ * a["X"][:, 0] + c * a["X"][:, 2]
+        X[:, 1] += np.float32((i % 8) * 5)
+        scenes.append(pd.Scene.from_arrays(X, a["Tet"], a["mass"], a["mu"], fixed=a["fixed"], params=p))
+    sc = pd.Scene.merge(scenes)
+    sc.params = p
+    return sc, p
+
+
+def make_scene(pd, workload, rank=0):
+    if workload == "batch64":
+        return make_batch_scene(pd, rank * BATCH_PER_GPU, BATCH_PER_GPU)
     cells, iters, _ = WORKLOADS[workload]
     sc = pd.Scene.kuhn_grid(cells, cells, cells, 1.0, JITTER, SEED, (0.0, 10.0, 0.0), MASS, MU)
     p = pd.SolverParams(dt=DT, gravity=GRAVITY, num_iterations=iters)
@@ -156,15 +186,18 @@ def run_b200(args):
     pd = importlib.import_module("soft-body-simulation-cuda_b200")
     rank, world, local = dist_setup(args.gpus)
     torch.cuda.set_device(local)
-    sc, p = make_scene(pd, args.workload)
+    batch = args.workload == "batch64"
+    sc, p = make_scene(pd, args.workload, rank)
     nV, nT = sc.counts()[:2]
     iters = p["num_iterations"]
     # N > 1: the mesh is vertex-partitioned, one rank per GPU; every rank builds the same global layout and keeps
     # the tiles that touch its vertices.  torch.distributed (NCCL) carries only the setup
     # (window handles) and the timing reductions; the per-iteration halo goes over NVLink peer memory.
-    eng = pd.PdSolver(sc, device=local, rot_mode=args.rot_mode, ctas_per_sm=args.ctas_per_sm, rank=rank, world=world)
+    # (the batch workload shards whole contexts instead: every rank steps its own 64, no communication at all)
+    eng = pd.PdSolver(sc, device=local, rot_mode=args.rot_mode, ctas_per_sm=args.ctas_per_sm,
+                      rank=0 if batch else rank, world=1 if batch else world)
     dist_info = None
-    if world > 1:
+    if world > 1 and not batch:
         import torch.distributed as dist
         h = torch.from_numpy(eng.window_handle()).cuda()
         allh = [torch.zeros_like(h) for _ in range(world)]
@@ -179,7 +212,7 @@ def run_b200(args):
                      "tets_evaluated_per_rank": allt[:, 2].tolist(), "pushed_verts_per_rank": allt[:, 3].tolist(),
                      "redundant_tet_fraction": float(allt[:, 2].sum() / nT - 1.0)}
     X0 = sc.arrays()["X"]
-    V0 = initial_velocity(X0)
+    V0 = np.zeros_like(X0) if batch else initial_velocity(X0)
     eng.upload(V=V0)
     info = eng.info()
 
@@ -201,8 +234,8 @@ def run_b200(args):
     t_local_ms, t_vertex_ms = eng.time_kernels(reps=20)
     peak, peak_src = peaks()
     # algorithmic bytes of what THIS rank's launch processes (56 B/tet + 24 B/vertex local, 68 B/vertex global)
-    nT_launch = nT if world == 1 else eng.dist_info()["num_tets_local"]
-    nV_launch = nV if world == 1 else eng.dist_info()["num_owned"]
+    nT_launch = nT if (world == 1 or batch) else eng.dist_info()["num_tets_local"]
+    nV_launch = nV if (world == 1 or batch) else eng.dist_info()["num_owned"]
     bytes_local = 56.0 * nT_launch + 24.0 * nV_launch
     bytes_iter = 56.0 * nT_launch + 68.0 * nV_launch
     ach_local = bytes_local / (t_local_ms * 1e-3) / 1e9
@@ -228,7 +261,7 @@ def run_b200(args):
     finite = bool(np.isfinite(final).all())
     for b in bufs:
         pd.lib().pd_free_pinned(b)
-    halo_ok = eng.dist_status() == 0 if world > 1 else True
+    halo_ok = eng.dist_status() == 0 if (world > 1 and not batch) else True
     barrier(world)
 
     if rank != 0:
@@ -236,19 +269,21 @@ def run_b200(args):
             import torch.distributed as dist
             dist.destroy_process_group()
         return
-    value = nT * iters / (ms_step * 1e-3) / 1e6
+    nT_job = nT * world if batch else nT          # batch: every rank steps its own contexts (weak scaling)
+    value = nT_job * iters / (ms_step * 1e-3) / 1e6
     line = {
         "metric": "Mtet-updates/s & PD iters/s at 1/2/4/8 B200; % of HBM roofline",
         "value": value, "unit": "Mtet-updates/s", "pd_iters_per_s": iters / (ms_step * 1e-3),
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "description": WORKLOADS[args.workload][2], "num_verts": nV, "num_tets": nT,
-                   "pd_iterations_per_step": iters, "global_solver": "chebyshev-jacobi", "dt": DT, "gravity": GRAVITY, "mu": MU,
-                   "initial_velocity": "0.5*sin(x/7) y^", "l2": f"inputs larger than L2: tile stream {info['tile_stream_bytes'] / 1e6:.0f} MB per iteration, no flush needed",
-                   "finite": finite, "parallelism": "single GPU" if world == 1 else f"vertex partition over {world} GPUs, tile-replicated boundary, NVLink peer-memory halo push + flags per PD iteration",
+        "higher_is_better": True, "scaling": "weak" if batch else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "description": WORKLOADS[args.workload][2], "num_verts": nV * (world if batch else 1), "num_tets": nT_job,
+                   "pd_iterations_per_step": iters, "global_solver": "chebyshev-jacobi", "dt": p["dt"], "gravity": p["gravity"], "mu": MU,
+                   "initial_velocity": "0" if batch else "0.5*sin(x/7) y^", "l2": (f"inputs larger than L2: tile stream {info['tile_stream_bytes'] / 1e6:.0f} MB per iteration, no flush needed" if info["tile_stream_bytes"] > 2 * 126e6
+                          else f"working set smaller than L2 (tile stream {info['tile_stream_bytes'] / 1e6:.0f} MB): not flushed -- 100 iterations per step re-read the same stream, L2-resident is this workload's steady state"),
+                   "finite": finite, "parallelism": "single GPU" if world == 1 else f("contexts sharded 64 per GPU, no communication" if batch else f"vertex partition over {world} GPUs, tile-replicated boundary, NVLink peer-memory halo push + flags per PD iteration"),
                    "multi_gpu": dist_info, "halo_ok": halo_ok},
         "clocks": clocks,
-        "e2e": {"value": nT * iters / (e2e_ms * 1e-3) / 1e6, "unit": "Mtet-updates/s", "ms_per_step": e2e_ms,
+        "e2e": {"value": nT_job * iters / (e2e_ms * 1e-3) / 1e6, "unit": "Mtet-updates/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 3 * nbytes, "d2h_bytes_per_step": 3 * nbytes, "steps": e2e_steps,
                 "api": "pd_step_host (include/pd_b200.h): pinned host X,V,XTilde in and out every step (every rank moves the full arrays)"},
         "gpu_launches": int(launches),
@@ -274,6 +309,9 @@ def run_reference(args):
     if rank != 0:
         return
     import ref
+    if args.workload == "batch64":
+        print(json.dumps({"impl": "reference", "unavailable": "the reference arm replays the grid workloads only (its harness takes one floor plane)"}))
+        return
     pd = importlib.import_module("soft-body-simulation-cuda_b200")      # host-side scene generator only
     sc, p = make_scene(pd, args.workload)
     nV, nT = sc.counts()[:2]

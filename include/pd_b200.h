@@ -105,6 +105,10 @@ pd_scene* pd_scene_from_desc(const pd_scene_desc* desc, const pd_params* params)
 /* synthetic Kuhn 6-tet grid (bench configs 3/4) */
 pd_scene* pd_scene_kuhn_grid(int nx, int ny, int nz, float h, float jitter, uint32_t seed,
                              const float origin[3], float mass, float mu);
+/* batch of independent contexts (same solver parameters and fixed bodies) -> one scene; vertex/tet numbering is the
+ * concatenation in argument order.  Context::mpSimContexts holds several contexts but steps one (context.cpp:546-555);
+ * stepping many at once is the batch mode of BASELINE config 5. */
+pd_scene* pd_scene_merge(const pd_scene* const* scenes, int n);
 void pd_scene_free(pd_scene*);
 int pd_scene_counts(const pd_scene*, int* num_verts, int* num_tets, int* num_fixed, int* num_bodies);
 int pd_scene_get(const pd_scene*, float* X, uint32_t* Tet, float* mass, float* mu, float* DBC,

@@ -68,6 +68,7 @@ SYMBOLS = {
     "pd_scene_load_json": (_VP, [_CP, _CP, _CP]),
     "pd_scene_from_desc": (_VP, [C.POINTER(pd_scene_desc), C.POINTER(pd_params)]),
     "pd_scene_kuhn_grid": (_VP, [_I, _I, _I, _F, _F, C.c_uint32, _VP, _F, _F]),
+    "pd_scene_merge": (_VP, [_VP, _I]),
     "pd_scene_free": (None, [_VP]),
     "pd_scene_counts": (_I, [_VP, _PI, _PI, _PI, _PI]),
     "pd_scene_get": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
@@ -226,6 +227,12 @@ class Scene:
     def kuhn_grid(cls, nx, ny, nz, h=1.0, jitter=0.05, seed=12345, origin=(0, 0, 0), mass=1.0, mu=2e5):
         o = np.asarray(origin, np.float32)
         return cls(lib().pd_scene_kuhn_grid(nx, ny, nz, h, jitter, seed, _p(o), mass, mu))
+
+    @classmethod
+    def merge(cls, scenes):
+        """Batch of independent contexts -> one scene (same params / fixed bodies); see pd_scene_merge."""
+        arr = (C.c_void_p * len(scenes))(*[s._h for s in scenes])
+        return cls(lib().pd_scene_merge(arr, len(scenes)))
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:

@@ -107,6 +107,36 @@ pd_scene* pd_scene_kuhn_grid(int nx, int ny, int nz, float h, float jitter, uint
     PD_CATCH_PTR
 }
 
+// Batch of independent contexts -> one scene: bodies of different contexts share no tets, so the system matrix is
+// block diagonal and one step of the merged scene is one step of every context (SURVEY.md 8e "free decoupling").
+pd_scene* pd_scene_merge(const pd_scene* const* scenes, int n)
+{
+    PD_TRY
+    if (!scenes || n <= 0 || !scenes[0]) { g_err = "no scenes to merge"; return nullptr; }
+    pd_scene* out = new pd_scene;
+    Scene& m = out->s;
+    m.name = "batch"; m.params = scenes[0]->s.params; m.fixed = scenes[0]->s.fixed; m.precision = scenes[0]->s.precision;
+    for (int i = 0; i < n; ++i) {
+        if (!scenes[i]) { delete out; g_err = "scene is NULL"; return nullptr; }
+        const Scene& a = scenes[i]->s;
+        const SolverParams &p = a.params, &q = m.params;
+        if (p.dt != q.dt || p.gravity != q.gravity || p.muN != q.muN || p.muT != q.muT || p.rho != q.rho || p.numIterations != q.numIterations ||
+            a.fixed.size() != m.fixed.size()) { delete out; g_err = "contexts of a batch must share solver parameters and fixed bodies"; return nullptr; }
+        const uint32_t vOff = (uint32_t)m.numVerts;
+        for (size_t b = 0; b < a.bodyVertStart.size(); ++b) {
+            m.bodyVertStart.push_back(a.bodyVertStart[b] + m.numVerts); m.bodyTetStart.push_back(a.bodyTetStart[b] + m.numTets);
+            m.bodyNames.push_back(a.bodyNames[b] + "#" + std::to_string(i));
+        }
+        m.X.insert(m.X.end(), a.X.begin(), a.X.end());
+        for (uint32_t v : a.Tet) m.Tet.push_back(v + vOff);
+        m.mass.insert(m.mass.end(), a.mass.begin(), a.mass.end()); m.DBC.insert(m.DBC.end(), a.DBC.begin(), a.DBC.end());
+        m.mu.insert(m.mu.end(), a.mu.begin(), a.mu.end()); m.lambda.insert(m.lambda.end(), a.lambda.begin(), a.lambda.end());
+        m.numVerts += a.numVerts; m.numTets += a.numTets;
+    }
+    return out;
+    PD_CATCH_PTR
+}
+
 void pd_scene_free(pd_scene* s) { delete s; }
 
 int pd_scene_counts(const pd_scene* s, int* nv, int* nt, int* nf, int* nb)

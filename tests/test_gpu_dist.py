@@ -67,3 +67,30 @@ def test_two_processes_two_gpus(pd, tmp_path):
                           "--master-port", str(port), os.path.join(HERE, "dist_gpu_worker.py")], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "DIST_GPU_OK" in out.stdout
+
+
+def test_batch_of_contexts_equals_separate_contexts(pd, assets):
+    """BASELINE config 5: independent contexts merged into one scene (pd_scene_merge) step exactly like separate engines
+    up to the rounding of differently grouped partial sums (bodies share no tets: the system matrix is block diagonal)."""
+    base = pd.Scene.from_json(assets["json"], "C5 house&sphere")
+    a, p = base.arrays(), base.params
+    p["num_iterations"] = 40
+    scenes = []
+    for i in range(4):
+        X = a["X"].copy(); X[:, 1] += np.float32(5 * i); X[:, 0] += np.float32(3 * i)
+        scenes.append(pd.Scene.from_arrays(X, a["Tet"], a["mass"], a["mu"], fixed=a["fixed"], params=p))
+    merged = pd.Scene.merge(scenes)
+    nV = base.counts()[0]
+    assert merged.counts()[:2] == (4 * nV, 4 * base.counts()[1]) and merged.counts()[3] == 4      # from_arrays: one body per context
+    eng = pd.PdSolver(merged)
+    eng.Update(5)
+    Xm = eng.download()[0]
+    for i, sc in enumerate(scenes):
+        e = pd.PdSolver(sc)
+        e.Update(5)
+        err = meshes.rel_err(Xm[i * nV:(i + 1) * nV], e.download()[0])
+        print(f"context {i}: merged vs separate {err:.2e}")
+        assert err <= 1e-4
+    with pytest.raises(pd.PdError):
+        q = pd.SolverParams(dt=0.02, gravity=1.0, num_iterations=3)
+        pd.Scene.merge([scenes[0], pd.Scene.from_arrays(a["X"], a["Tet"], a["mass"], a["mu"], fixed=a["fixed"], params=q)])
