@@ -44,15 +44,34 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML in-process
+    every 2 ms (an `nvidia-smi -lms` child needs >100 ms to produce its first row, longer than a short multi-GPU run);
+    falls back to the nvidia-smi query loop if NVML cannot be loaded."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index=0):
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
+        self.sm, self.power, self.reasons, self.mx = [], [], set(), None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -61,11 +80,33 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                self.power.append(n.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                try:
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "power_w_max": max(self.power) if self.power else None, "samples": len(self.sm), "reasons": sorted(self.reasons), "source": "nvml, 2 ms period"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -87,7 +128,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 def make_batch_scene(pd, first, count):
@@ -241,26 +282,40 @@ def run_b200(args):
     ach_local = bytes_local / (t_local_ms * 1e-3) / 1e9
     ach_iter = bytes_iter / ((t_local_ms + t_vertex_ms) * 1e-3) / 1e9
 
-    # ---- end to end: HOST (pinned) state in -> H2D, step, D2H -> host state out, every step
+    # ---- end to end: HOST (pinned) state in -> H2D, step, D2H -> host state out, every step.
+    # N = 1 (and the batch): pd_step_host, whole arrays in the caller's numbering.  N > 1: every rank owns and moves
+    # only its shard of X / V / XTilde (pd_step_host_owned, 3 * num_owned floats per array).
     import ctypes as C
-    nbytes = X0.nbytes
-    bufs = [pd.lib().pd_alloc_pinned(nbytes) for _ in range(6)]
-    arr = [np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_float)), shape=(nV, 3)) for b in bufs]
+    sharded = world > 1 and not batch
     X, V, XT = eng.download()
+    if sharded:
+        ids = eng.owned_ids()
+        X, V, XT = X[ids], V[ids], XT[ids]
+    nbytes = X.nbytes
+    bufs = [pd.lib().pd_alloc_pinned(nbytes) for _ in range(6)]
+    arr = [np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_float)), shape=X.shape) for b in bufs]
     arr[0][:] = X; arr[1][:] = V; arr[2][:] = XT
     e2e_steps = max(1, min(args.steps, 5))
-    eng.step_host_ptr(1, bufs[0], bufs[1], bufs[2], bufs[3], bufs[4], bufs[5])       # warm-up
-    barrier(world)
+    host_step = eng.step_host_owned_ptr if sharded else eng.step_host_ptr
+    host_step(1, bufs[0], bufs[1], bufs[2], bufs[3], bufs[4], bufs[5])       # warm-up
+    eng.synchronize(); barrier(world)
     t0 = time.perf_counter()
     for s in range(e2e_steps):
-        i, o = (0, 3) if s % 2 == 0 else (3, 0)
-        eng.step_host_ptr(1, bufs[i], bufs[i + 1], bufs[i + 2], bufs[o], bufs[o + 1], bufs[o + 2])
+        i, o = (3, 0) if s % 2 == 0 else (0, 3)
+        host_step(1, bufs[i], bufs[i + 1], bufs[i + 2], bufs[o], bufs[o + 1], bufs[o + 2])
     t1 = time.perf_counter()
     e2e_ms = max_over_ranks((t1 - t0) * 1e3 / e2e_steps, world, local)
-    final = arr[3] if e2e_steps % 2 == 1 else arr[0]
+    final = arr[0] if e2e_steps % 2 == 1 else arr[3]
     finite = bool(np.isfinite(final).all())
     for b in bufs:
         pd.lib().pd_free_pinned(b)
+    if world > 1:       # bytes moved by the whole job per step
+        import torch.distributed as dist
+        tb = torch.tensor([3 * nbytes], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tb)
+        job_bytes = int(tb.item())
+    else:
+        job_bytes = 3 * nbytes
     halo_ok = eng.dist_status() == 0 if (world > 1 and not batch) else True
     barrier(world)
 
@@ -284,8 +339,9 @@ def run_b200(args):
                    "multi_gpu": dist_info, "halo_ok": halo_ok},
         "clocks": clocks,
         "e2e": {"value": nT_job * iters / (e2e_ms * 1e-3) / 1e6, "unit": "Mtet-updates/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 3 * nbytes, "d2h_bytes_per_step": 3 * nbytes, "steps": e2e_steps,
-                "api": "pd_step_host (include/pd_b200.h): pinned host X,V,XTilde in and out every step (every rank moves the full arrays)"},
+                "h2d_bytes_per_step": job_bytes, "d2h_bytes_per_step": job_bytes, "steps": e2e_steps,
+                "api": ("pd_step_host_owned (include/pd_b200.h): every rank moves its own shard of X,V,XTilde, pinned host in and out every step" if sharded
+                        else "pd_step_host (include/pd_b200.h): pinned host X,V,XTilde in and out every step")},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_local (local step: F, rotation, ordered RHS partials)" + ("" if world == 1 else " -- rank 0's launch"),
                      "achieved": ach_local, "peak": peak, "unit": "GB/s", "frac": ach_local / peak, "traffic": None,

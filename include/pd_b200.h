@@ -179,6 +179,12 @@ int pd_upload_state(pd_engine*, const float* X, const float* V, const float* XTi
 /* end to end on HOST buffers: upload state, n steps, download state (all inside the call) */
 int pd_step_host(pd_engine*, int n_steps, const float* X_in, const float* V_in, const float* XTilde_in,
                  float* X_out, float* V_out, float* XTilde_out);
+/* the same for ONE RANK'S SHARD of a multi-GPU engine: every array holds 3 * num_owned floats in the rank's local
+ * owned-vertex order; pd_dist_owned_ids gives the original vertex id of each entry (num_owned of them).  Each
+ * process keeps and moves only its part of SolverData<float>::X/V/XTilde (def.h:21-27). */
+int pd_step_host_owned(pd_engine*, int n_steps, const float* X_in, const float* V_in, const float* XTilde_in,
+                       float* X_out, float* V_out, float* XTilde_out);
+int pd_dist_owned_ids(const pd_engine*, uint32_t* original_ids /* num_owned */);
 /* adopt the reference's DEVICE arrays (SolverData<float>::X/V/XTilde, glm::vec3*, original
  * numbering): import -> n steps -> export, all on the engine's stream, then synchronise.
  * This is what B200PdSolver::Update calls (include/b200_pd_solver.h). */

@@ -115,6 +115,8 @@ SYMBOLS = {
     "pd_download": (_I, [_VP, _VP, _VP, _VP]),
     "pd_upload_state": (_I, [_VP, _VP, _VP, _VP]),
     "pd_step_host": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "pd_step_host_owned": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "pd_dist_owned_ids": (_I, [_VP, _VP]),
     "pd_update_device": (_I, [_VP, _I, _VP, _VP, _VP]),
     "pd_get_setup": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "pd_get_system_matrix": (_I, [_VP, _PI, _VP, _VP, _VP]),
@@ -435,6 +437,17 @@ class PdSolver:
     def step_host_ptr(self, n, xin, vin, xtin, xout, vout, xtout):
         """e2e step on raw host pointers (ints), e.g. pinned buffers."""
         _check(lib().pd_step_host(self._h, n, xin, vin, xtin, xout, vout, xtout))
+
+    def step_host_owned_ptr(self, n, xin, vin, xtin, xout, vout, xtout):
+        """e2e step on this rank's SHARD (3 * num_owned floats per array, local owned order; see owned_ids)."""
+        _check(lib().pd_step_host_owned(self._h, n, xin, vin, xtin, xout, vout, xtout))
+
+    def owned_ids(self):
+        """original vertex id of each owned vertex of this rank, in local order"""
+        n = self.dist_info()["num_owned"]
+        a = np.zeros(n, np.uint32)
+        _check(lib().pd_dist_owned_ids(self._h, _p(a)))
+        return a
 
     def update_device_ptr(self, n, dX, dV, dXT):
         _check(lib().pd_update_device(self._h, n, dX, dV, dXT))

@@ -407,6 +407,16 @@ int pd_step_host(pd_engine* e, int n, const float* Xi, const float* Vi, const fl
 {
     ENGINE_CALL(if (n < 0) return fail(PD_ERR_INVALID, "n_steps < 0"); e->e->stepHost(n, Xi, Vi, XTi, Xo, Vo, XTo))
 }
+int pd_step_host_owned(pd_engine* e, int n, const float* Xi, const float* Vi, const float* XTi, float* Xo, float* Vo, float* XTo)
+{
+    ENGINE_CALL(if (n < 0) return fail(PD_ERR_INVALID, "n_steps < 0"); e->e->stepHostOwned(n, Xi, Vi, XTi, Xo, Vo, XTo))
+}
+int pd_dist_owned_ids(const pd_engine* e, uint32_t* out)
+{
+    if (!e || !e->e || !out) return fail(PD_ERR_INVALID, "NULL argument");
+    e->e->ownedIds(out);
+    return PD_OK;
+}
 int pd_update_device(pd_engine* e, int n, float* dX, float* dV, float* dXT)
 {
     ENGINE_CALL(if (n < 0) return fail(PD_ERR_INVALID, "n_steps < 0");

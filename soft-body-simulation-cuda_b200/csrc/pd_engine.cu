@@ -22,6 +22,31 @@ namespace pdb200 {
                                      std::to_string(__LINE__) + ": " #call);                              \
     } while (0)
 
+// kernel launch with (optionally) the programmatic-dependent-launch attribute: the kernel may be scheduled while
+// the previous kernel of the stream drains; it calls pdl_wait() before touching anything that kernel wrote
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args&&... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
+
+// Exchange window of one rank (nLoc = owned + ghost vertices), mapped by its peers:
+//   [q0 | q1 | q2 | pcgP | flags[world] | epoch | ticket, status | pflags[world] | red[2][world][4 doubles]]
+struct WindowLayout {
+    size_t offP, offFlags, offEpoch, offTicket, offPFlags, offRed, bytes;
+    WindowLayout(size_t nLoc, int world)
+    {
+        offP = 3 * nLoc * 16; offFlags = 4 * nLoc * 16; offEpoch = offFlags + 8 * (size_t)world; offTicket = offEpoch + 8;
+        offPFlags = offEpoch + 16; offRed = offPFlags + 8 * (size_t)world; bytes = offRed + 2 * (size_t)world * 32;
+    }
+};
+
 struct Engine::Impl {
     // tile stream
     uint8_t* records = nullptr;
@@ -47,10 +72,15 @@ struct Engine::Impl {
     unsigned long long *flags = nullptr, *epoch = nullptr;
     unsigned int *ticket = nullptr, *status = nullptr;
     uint32_t *pushSrc = nullptr, *pushDst = nullptr, *pushNbr = nullptr;
+    uint32_t *pushPtrV = nullptr, *pushDstV = nullptr, *pushNbrV = nullptr;     // the same list as a CSR by owned vertex (fused push)
     int* nbrRanks = nullptr;
     float4** peerQ = nullptr;                  // [3 * nNbr]: buffer k of neighbour j
     unsigned long long** peerFlag = nullptr;   // [nNbr]: this rank's entry in neighbour j's flag array
     int nPush = 0, nNbr = 0;
+    // distributed PCG (pd_solvers.cuh: DistSolve): p lives in the window; flags / reduction slots / sequence counters
+    unsigned long long *pflags = nullptr, *solveSeq = nullptr;
+    double* red = nullptr;
+    float4** peerP = nullptr; unsigned long long** peerPFlag = nullptr; double** peerRed = nullptr;
     std::vector<void*> ipcOpened;
     cudaEvent_t lockEvent = nullptr;
     // non-Jacobi global solvers (PCG, sparse Cholesky)
@@ -94,6 +124,8 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     if (prop.major < 10)
         throw std::runtime_error("this build targets sm_100a (B200); found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor));
     numSms_ = prop.multiProcessorCount;
+    if (const char* e = std::getenv("PD_PDL")) usePdl_ = std::atoi(e) != 0;      // experiments: PD_PDL=1 turns programmatic dependent launch on
+    pdlActive_ = usePdl_;
     CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
 
     if (opt.world == 1) {
@@ -119,15 +151,21 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     d.vslot = dalloc<uint32_t>(L_.vslot.size());
     d.vlist = dalloc<uint32_t>(L_.vlist.size());
     d.P = dalloc<float4>((size_t)L_.nTiles * TILE_NLMAX);      // padded slots: tile * TILE_NLMAX + local vertex
-    // the three position buffers live in the exchange window: [q0 | q1 | q2 | flags[world] | epoch | ticket | status]
-    d.windowBytes = 3 * (size_t)nV_ * 16 + 8 * (size_t)opt.world + 8 + 8;
+    // the three position buffers (and the CG direction p) live in the exchange window, see WindowLayout
+    const WindowLayout wl((size_t)nV_, opt.world);
+    d.windowBytes = wl.bytes;
     d.window = dalloc<uint8_t>(d.windowBytes);
     CUDA_CHECK(cudaMemset(d.window, 0, d.windowBytes));
     for (int k = 0; k < 3; ++k) d.q[k] = reinterpret_cast<float4*>(d.window) + (size_t)k * nV_;
-    d.flags = reinterpret_cast<unsigned long long*>(d.window + 3 * (size_t)nV_ * 16);
-    d.epoch = d.flags + opt.world;
-    d.ticket = reinterpret_cast<unsigned int*>(d.epoch + 1);
+    d.cgP = reinterpret_cast<float4*>(d.window + wl.offP);
+    d.flags = reinterpret_cast<unsigned long long*>(d.window + wl.offFlags);
+    d.epoch = reinterpret_cast<unsigned long long*>(d.window + wl.offEpoch);
+    d.ticket = reinterpret_cast<unsigned int*>(d.window + wl.offTicket);
     d.status = d.ticket + 1;
+    d.pflags = reinterpret_cast<unsigned long long*>(d.window + wl.offPFlags);
+    d.red = reinterpret_cast<double*>(d.window + wl.offRed);
+    d.solveSeq = dalloc<unsigned long long>(2);
+    CUDA_CHECK(cudaMemset(d.solveSeq, 0, 16));
     d.b0 = dalloc<float4>(nV_); d.X = dalloc<float4>(nV_); d.V = dalloc<float4>(nV_);
     d.XT = dalloc<float4>(nV_); d.X0 = dalloc<float4>(nV_);
     d.cc = dalloc<float2>(nV_);
@@ -276,7 +314,7 @@ void Engine::prepare()
 void Engine::launchLocal(const float4* q, bool jacobi, unsigned long long* prof)
 {
     Impl& d = *d_;
-#define PD_LOCAL(RM, JAC) k_local<RM, JAC><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vlist, q, d.b0, d.P, prof, d.wait)
+#define PD_LOCAL(RM, JAC) launch_pdl(k_local<RM, JAC>, dim3(localGrid_), dim3(TILE_T), LOCAL_SMEM_BYTES, stream_, pdlActive_, d.records, d.tileTab, L_.nTiles, d.vlist, q, d.b0, d.P, prof, d.wait)
     if (prof) {
         if (opt_.rotMode == 2) k_local<2, true, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vlist, q, d.b0, d.P, prof, d.wait);
         else k_local<0, true, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vlist, q, d.b0, d.P, prof, d.wait);
@@ -323,9 +361,17 @@ void Engine::enqueueIteration(int i, bool timed, size_t* ev)
     if (i <= 10) omega_ = 1;
     else if (i == 11) omega_ = 2 / (2 - p.rho * p.rho);
     else omega_ = 4 / (4 - p.rho * p.rho * omega_);
-    if (opt_.rotMode == 1) k_vertex_jacobi<false><<<vg, vb, 0, stream_>>>(nOwn_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
-    else k_vertex_jacobi<true><<<vg, vb, 0, stream_>>>(nOwn_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
-    enqueuePush(next, in);
+    if (opt_.world > 1) {
+        // multi-GPU: the halo push of the new positions is fused into the vertex kernel (no separate launch)
+        if (!connected_) throw std::runtime_error("multi-GPU engine stepped before pd_dist_connect");
+        const DistPush dp{d.pushPtrV, d.pushDstV, d.pushNbrV, d.peerQ + (size_t)in * d.nNbr, d.peerFlag, d.nNbr, d.epoch, d.ticket};
+        if (opt_.rotMode == 1) launch_pdl(k_vertex_jacobi<false, true>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc, dp);
+        else launch_pdl(k_vertex_jacobi<true, true>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc, dp);
+    } else {
+        const DistPush dp{};
+        if (opt_.rotMode == 1) launch_pdl(k_vertex_jacobi<false, false>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc, dp);
+        else launch_pdl(k_vertex_jacobi<true, false>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc, dp);
+    }
     ++phase_;
     rec();
 }
@@ -355,11 +401,13 @@ void Engine::enqueueStep(bool timed)
 {
     Impl& d = *d_;
     size_t ev = 0;
+    pdlActive_ = usePdl_ && !timed;        // event records between the kernels (perf mode) want fully serialised launches
     enqueuePredict();
     for (int i = 0; i < params_.numIterations; ++i) enqueueIteration(i, timed, &ev);
     if (timed) CUDA_CHECK(cudaEventRecord(d.events[ev++], stream_));
     enqueueFinish();
     if (timed) CUDA_CHECK(cudaEventRecord(d.events[ev++], stream_));
+    pdlActive_ = usePdl_;
 }
 
 // One CUDA graph per step.  Multi-GPU: the position buffers rotate across steps (base = phase_ % 3), so up to
@@ -396,7 +444,7 @@ void Engine::step(int nSteps)
         perfc_.kernelLaunches += (long long)nSteps * (4 + 3 * params_.numIterations);
         return;
     }
-    const int launchesPerStep = 2 + 2 * params_.numIterations + (opt_.world > 1 ? 1 + params_.numIterations : 0);
+    const int launchesPerStep = 2 + 2 * params_.numIterations + (opt_.world > 1 ? 1 : 0);     // + the predictor's halo push
     if (perf_) {
         const size_t need = 3 * (size_t)params_.numIterations + 2;
         while (d.events.size() < need) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); d.events.push_back(e); }
@@ -504,6 +552,32 @@ void Engine::stepHost(int nSteps, const float* Xin, const float* Vin, const floa
     download(Xout, Vout, XTout);
 }
 
+// Multi-GPU end to end: every rank moves only ITS shard -- 3 * numOwned() floats per array, in the rank's local
+// owned-vertex order (ownedIds() gives the original vertex id of each entry).  On one GPU the shard is the whole
+// state in the engine's renumbered order.
+void Engine::stepHostOwned(int nSteps, const float* Xin, const float* Vin, const float* XTin, float* Xout, float* Vout, float* XTout)
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    Impl& d = *d_;
+    const size_t nO = (size_t)nOwn_, n = 3 * nO * sizeof(float);
+    float *sx = d.stage3, *sv = d.stage3 + 3 * nO, *st = d.stage3 + 6 * nO;
+    const int vb = 256, vg = (nOwn_ + vb - 1) / vb;
+    if (Xin) { CUDA_CHECK(cudaMemcpyAsync(sx, Xin, n, cudaMemcpyHostToDevice, stream_)); k_import3<<<vg, vb, 0, stream_>>>(nOwn_, sx, nullptr, d.X); }
+    if (Vin) { CUDA_CHECK(cudaMemcpyAsync(sv, Vin, n, cudaMemcpyHostToDevice, stream_)); k_import3<<<vg, vb, 0, stream_>>>(nOwn_, sv, nullptr, d.V); }
+    if (XTin) { CUDA_CHECK(cudaMemcpyAsync(st, XTin, n, cudaMemcpyHostToDevice, stream_)); k_import3<<<vg, vb, 0, stream_>>>(nOwn_, st, nullptr, d.XT); }
+    step(nSteps);
+    if (Xout) { k_export3<<<vg, vb, 0, stream_>>>(nOwn_, d.X, nullptr, sx); CUDA_CHECK(cudaMemcpyAsync(Xout, sx, n, cudaMemcpyDeviceToHost, stream_)); }
+    if (Vout) { k_export3<<<vg, vb, 0, stream_>>>(nOwn_, d.V, nullptr, sv); CUDA_CHECK(cudaMemcpyAsync(Vout, sv, n, cudaMemcpyDeviceToHost, stream_)); }
+    if (XTout) { k_export3<<<vg, vb, 0, stream_>>>(nOwn_, d.XT, nullptr, st); CUDA_CHECK(cudaMemcpyAsync(XTout, st, n, cudaMemcpyDeviceToHost, stream_)); }
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+void Engine::ownedIds(uint32_t* out) const
+{
+    std::memcpy(out, L_.vertOrder.data(), (size_t)nOwn_ * sizeof(uint32_t));
+}
+
 void Engine::getSetup(float* matrixDiag, float* massDt2, float* DmInv, float* V0)
 {
     if (!ready_) prepare();
@@ -531,9 +605,11 @@ float Engine::timeLocalKernelMs(int reps)
     CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     CUDA_CHECK(cudaEventRecord(a, stream_));
+    pdlActive_ = false;                    // isolated launches: no overlap with the neighbouring launch
     for (int r = 0; r < reps; ++r) {
         launchLocal(d.XT, true);
     }
+    pdlActive_ = usePdl_;
     CUDA_CHECK(cudaEventRecord(b, stream_));
     CUDA_CHECK(cudaEventSynchronize(b));
     float ms = 0;
@@ -556,7 +632,7 @@ float Engine::timeVertexKernelMs(int reps)
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     CUDA_CHECK(cudaEventRecord(a, stream_));
     for (int r = 0; r < reps; ++r)
-        k_vertex_jacobi<true><<<vg, vb, 0, stream_>>>(nOwn_, d.q[0], d.q[2], d.q[1], d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, 1.0f, 1.0f);
+        k_vertex_jacobi<true><<<vg, vb, 0, stream_>>>(nOwn_, d.q[0], d.q[2], d.q[1], d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, 1.0f, 1.0f, DistPush{});
     CUDA_CHECK(cudaEventRecord(b, stream_));
     CUDA_CHECK(cudaEventSynchronize(b));
     float ms = 0;
@@ -570,7 +646,9 @@ float Engine::timeVertexKernelMs(int reps)
 void Engine::prepareSolver()
 {
     Impl& d = *d_;
-    if (opt_.world > 1) throw std::runtime_error("PCG / Cholesky global solvers run on one GPU per mesh (replicas only): outside the PD hot path of the multi-GPU mode");
+    if (opt_.world > 1 && params_.globalSolver == 1)
+        throw std::runtime_error("the sparse Cholesky global step does not shard (replicas only, one mesh per GPU); use Jacobi or PCG on a partitioned mesh");
+    if (opt_.world > 1 && !connected_) throw std::runtime_error("multi-GPU engine stepped before pd_dist_connect");
     if (!d.solverReady) {
         std::vector<float> Br((size_t)nT_ * 9), wr((size_t)nT_), c((size_t)nV_);
         size_t t = 0;
@@ -590,9 +668,15 @@ void Engine::prepareSolver()
         }
         CsrMatrix A; std::vector<float> md;
         build_system_matrix(L_, nullptr, Br.data(), wr.data(), c.data(), A, md);
+        if (opt_.world > 1) {      // keep this rank's rows only (every tet of an owned vertex is here, so they are complete)
+            A.n = nOwn_;
+            A.rowPtr.resize((size_t)nOwn_ + 1);
+            A.col.resize((size_t)A.rowPtr[(size_t)nOwn_]); A.val.resize((size_t)A.rowPtr[(size_t)nOwn_]);
+        }
         hostA_ = A;
+        const int nRows = A.n;
         std::vector<float> inv((size_t)nV_);
-        for (int v = 0; v < nV_; ++v) {
+        for (int v = 0; v < nRows; ++v) {
             float dg = 1.0f;
             for (int e = A.rowPtr[v]; e < A.rowPtr[v + 1]; ++e) if (A.col[e] == v) { dg = A.val[e]; break; }
             if (std::fabs(dg) < 1e-9f) dg = 1.0f;                               // ExtractInverseDiagonalKernel, pcgJacobi.cu:6-19
@@ -603,21 +687,24 @@ void Engine::prepareSolver()
         CUDA_CHECK(cudaMemcpy(cl, A.col.data(), A.col.size() * 4, cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaMemcpy(vl, A.val.data(), A.val.size() * 4, cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaMemcpy(iv, inv.data(), (size_t)nV_ * 4, cudaMemcpyHostToDevice));
-        d.A = CsrDev{nV_, rp, cl, vl, iv};
+        d.A = CsrDev{nRows, rp, cl, vl, iv};
         d.nnzA = A.col.size();
         if (!d.rhs) {
-            d.rhs = dalloc<float4>(nV_); d.cgR = dalloc<float4>(nV_); d.cgP = dalloc<float4>(nV_); d.cgQ = dalloc<float4>(nV_);
+            d.rhs = dalloc<float4>(nV_); d.cgR = dalloc<float4>(nV_); d.cgQ = dalloc<float4>(nV_);
             d.xprev = dalloc<float4>(nV_); d.cholY = dalloc<float4>(nV_);
             d.cholReadyFlags = dalloc<int>(nV_);
             CUDA_CHECK(cudaMemset(d.cholReadyFlags, 0, (size_t)nV_ * 4));
             d.solveState = dalloc<SolveState>(1);
             CUDA_CHECK(cudaMemset(d.solveState, 0, sizeof(SolveState)));
             int perSm = 0;
-            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pcg_solve, SOLVE_THREADS, 0));
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pcg_solve<false>, SOLVE_THREADS, 0));
+            int perSmD = 0;
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmD, k_pcg_solve<true>, SOLVE_THREADS, 0));
+            perSm = std::min(perSm, perSmD);
             int perSm2 = 0;
             CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm2, k_chol_solve, SOLVE_THREADS, 0));
             perSm = std::max(1, std::min(perSm, perSm2));
-            d.solveGrid = std::min(numSms_ * perSm, std::min(SOLVE_MAX_PARTIALS, (nV_ + SOLVE_THREADS - 1) / SOLVE_THREADS));
+            d.solveGrid = std::min(numSms_ * perSm, std::min(SOLVE_MAX_PARTIALS, (nOwn_ + SOLVE_THREADS - 1) / SOLVE_THREADS));
             d.solveGrid = std::max(d.solveGrid, 1);
             d.partials = dalloc<double>(3 * (size_t)SOLVE_MAX_PARTIALS);
         }
@@ -648,22 +735,31 @@ void Engine::enqueueStepSolver()
 {
     Impl& d = *d_;
     const SolverParams& p = params_;
-    const int vb = 256, vg = (nV_ + vb - 1) / vb;
+    const int n = nOwn_;                    // multi-GPU: this rank's vertices (rows); ghosts are filled by the halo pushes
+    const int vb = 256, vg = (n + vb - 1) / vb;
     const float dtInv = 1.0f / p.dt;
     const float wdbc = 1e6f * (dtInv * dtInv);
-    k_predict<<<vg, vb, 0, stream_>>>(nV_, d.X, d.V, d.mass, d.dbc, d.md, p.dt, dt2Prepared_, p.gravity, d.q[0], d.q[2], d.b0, d.cc);
-    CUDA_CHECK(cudaMemsetAsync(d.xprev, 0, (size_t)nV_ * 16, stream_));        // cudaMemset(prev_x, 0, ...), pdSolver.cu:162
+    const bool dist = opt_.world > 1;
+    pdlActive_ = false;                     // cooperative solve kernels in between: plain, fully serialised launches
+    k_predict<<<vg, vb, 0, stream_>>>(n, d.X, d.V, d.mass, d.dbc, d.md, p.dt, dt2Prepared_, p.gravity, d.q[0], d.q[2], d.b0, d.cc);
+    enqueuePush(d.q[0], 0);
+    CUDA_CHECK(cudaMemsetAsync(d.xprev, 0, (size_t)n * 16, stream_));        // cudaMemset(prev_x, 0, ...), pdSolver.cu:162
     k_solve_begin<<<1, 1, 0, stream_>>>(d.solveState);
+    DistSolve ds{};
+    if (dist) ds = DistSolve{opt_.world, opt_.rank, d.nNbr, d.nPush, scene_.numVerts, d.nbrRanks, d.pushSrc, d.pushDst, d.pushNbr,
+                             d.peerP, d.peerPFlag, d.pflags, d.peerRed, d.red, d.solveSeq, d.status};
     for (int i = 0; i < p.numIterations; ++i) {
         launchLocal(d.q[0], false);
-        if (opt_.rotMode == 1) k_vertex_rhs<false><<<vg, vb, 0, stream_>>>(nV_, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, wdbc, d.rhs);
-        else k_vertex_rhs<true><<<vg, vb, 0, stream_>>>(nV_, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, wdbc, d.rhs);
+        if (opt_.rotMode == 1) k_vertex_rhs<false><<<vg, vb, 0, stream_>>>(n, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, wdbc, d.rhs);
+        else k_vertex_rhs<true><<<vg, vb, 0, stream_>>>(n, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, wdbc, d.rhs);
         if (p.globalSolver == 2) {
             const float4* b = d.rhs; float4 *x = d.q[0], *r = d.cgR, *pp = d.cgP, *qq = d.cgQ, *xp = d.xprev;
             int maxIter = p.pcgMaxIter; float cgTol = p.pcgTol, pdTol = p.tol;
             SolveState* st = d.solveState; double* part = d.partials;
-            void* args[] = {&d.A, &b, &x, &r, &pp, &qq, &xp, &maxIter, &cgTol, &pdTol, &st, &part};
-            CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_pcg_solve, dim3(d.solveGrid), dim3(SOLVE_THREADS), args, 0, stream_));
+            void* args[] = {&d.A, &b, &x, &r, &pp, &qq, &xp, &maxIter, &cgTol, &pdTol, &st, &part, &ds};
+            CUDA_CHECK(cudaLaunchCooperativeKernel(dist ? (const void*)k_pcg_solve<true> : (const void*)k_pcg_solve<false>,
+                                                   dim3(d.solveGrid), dim3(SOLVE_THREADS), args, 0, stream_));
+            enqueuePush(d.q[0], 0);         // multi-GPU: the new iterate's boundary entries -> the neighbours' ghosts
         } else {
             const float4* b = d.rhs; float4 *x = d.q[0], *y = d.cholY, *xp = d.xprev; int* rdy = d.cholReadyFlags;
             int tag = d.cholEpoch++; float pdTol = p.tol;
@@ -672,7 +768,8 @@ void Engine::enqueueStepSolver()
             CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(d.solveGrid), dim3(SOLVE_THREADS), args, 0, stream_));
         }
     }
-    k_finish<<<vg, vb, 0, stream_>>>(nV_, d.q[0], dtInv, d.X, d.XT, d.V, d.fb, p.muT, p.muN);
+    k_finish<<<vg, vb, 0, stream_>>>(n, d.q[0], dtInv, d.X, d.XT, d.V, d.fb, p.muT, p.muN);
+    pdlActive_ = usePdl_;
 }
 
 const CsrMatrix& Engine::systemMatrix()
@@ -727,12 +824,52 @@ void Engine::setPeers(const std::vector<uint8_t*>& peerBase)
         if (!peerBase[(size_t)r]) throw std::runtime_error("missing exchange window of neighbour rank " + std::to_string(r));
         nbrIndexOfRank[(size_t)r] = j;
         const size_t nLocR = (size_t)P.nLocOf[(size_t)r];
+        const WindowLayout wl(nLocR, opt_.world);
         for (int k = 0; k < 3; ++k) pq[(size_t)k * d.nNbr + j] = reinterpret_cast<float4*>(peerBase[(size_t)r]) + (size_t)k * nLocR;
-        pf[(size_t)j] = reinterpret_cast<unsigned long long*>(peerBase[(size_t)r] + 3 * nLocR * 16) + opt_.rank;
+        pf[(size_t)j] = reinterpret_cast<unsigned long long*>(peerBase[(size_t)r] + wl.offFlags) + opt_.rank;
+    }
+    {   // distributed PCG: the neighbours' p vectors and p-flags, and EVERY rank's reduction slots (own included)
+        std::vector<float4*> pp((size_t)std::max(d.nNbr, 1));
+        std::vector<unsigned long long*> ppf((size_t)std::max(d.nNbr, 1));
+        std::vector<double*> pr((size_t)opt_.world, nullptr);
+        for (int j = 0; j < d.nNbr; ++j) {
+            const int r = P.neighbours[(size_t)j];
+            const WindowLayout wl((size_t)P.nLocOf[(size_t)r], opt_.world);
+            pp[(size_t)j] = reinterpret_cast<float4*>(peerBase[(size_t)r] + wl.offP);
+            ppf[(size_t)j] = reinterpret_cast<unsigned long long*>(peerBase[(size_t)r] + wl.offPFlags) + opt_.rank;
+        }
+        for (int r = 0; r < opt_.world; ++r) {
+            if (r == opt_.rank) { pr[(size_t)r] = d.red; continue; }
+            if (!peerBase[(size_t)r]) throw std::runtime_error("missing exchange window of rank " + std::to_string(r));
+            const WindowLayout wl((size_t)P.nLocOf[(size_t)r], opt_.world);
+            pr[(size_t)r] = reinterpret_cast<double*>(peerBase[(size_t)r] + wl.offRed);
+        }
+        d.peerP = dalloc<float4*>((size_t)d.nNbr); d.peerPFlag = dalloc<unsigned long long*>((size_t)d.nNbr); d.peerRed = dalloc<double*>((size_t)opt_.world);
+        if (d.nNbr) {
+            CUDA_CHECK(cudaMemcpy(d.peerP, pp.data(), (size_t)d.nNbr * sizeof(float4*), cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaMemcpy(d.peerPFlag, ppf.data(), (size_t)d.nNbr * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
+        }
+        CUDA_CHECK(cudaMemcpy(d.peerRed, pr.data(), (size_t)opt_.world * sizeof(double*), cudaMemcpyHostToDevice));
     }
     std::vector<uint32_t> nb((size_t)std::max(d.nPush, 1));
     for (int i = 0; i < d.nPush; ++i) nb[(size_t)i] = (uint32_t)nbrIndexOfRank[(size_t)P.pushRank[(size_t)i]];
     d.pushSrc = dalloc<uint32_t>(d.nPush); d.pushDst = dalloc<uint32_t>(d.nPush); d.pushNbr = dalloc<uint32_t>(d.nPush);
+    {   // the same list as a CSR by owned vertex, for the push fused into the vertex kernel
+        std::vector<uint32_t> ptr((size_t)nOwn_ + 1, 0u), dstV((size_t)std::max(d.nPush, 1)), nbrV((size_t)std::max(d.nPush, 1));
+        for (int i = 0; i < d.nPush; ++i) ptr[(size_t)P.pushSrc[(size_t)i] + 1]++;
+        for (int v = 0; v < nOwn_; ++v) ptr[(size_t)v + 1] += ptr[(size_t)v];
+        std::vector<uint32_t> fill(ptr.begin(), ptr.end() - 1);
+        for (int i = 0; i < d.nPush; ++i) {
+            const uint32_t at = fill[(size_t)P.pushSrc[(size_t)i]]++;
+            dstV[at] = P.pushDst[(size_t)i]; nbrV[at] = nb[(size_t)i];
+        }
+        d.pushPtrV = dalloc<uint32_t>((size_t)nOwn_ + 1); d.pushDstV = dalloc<uint32_t>(d.nPush); d.pushNbrV = dalloc<uint32_t>(d.nPush);
+        CUDA_CHECK(cudaMemcpy(d.pushPtrV, ptr.data(), ((size_t)nOwn_ + 1) * 4, cudaMemcpyHostToDevice));
+        if (d.nPush) {
+            CUDA_CHECK(cudaMemcpy(d.pushDstV, dstV.data(), (size_t)d.nPush * 4, cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaMemcpy(d.pushNbrV, nbrV.data(), (size_t)d.nPush * 4, cudaMemcpyHostToDevice));
+        }
+    }
     d.nbrRanks = dalloc<int>(d.nNbr);
     d.peerQ = dalloc<float4*>(3 * (size_t)d.nNbr); d.peerFlag = dalloc<unsigned long long*>(d.nNbr);
     if (d.nPush) {
@@ -754,7 +891,8 @@ void Engine::connectIpc(const void* handles)
     CUDA_CHECK(cudaSetDevice(opt_.device));
     if (opt_.world == 1) { connected_ = true; return; }
     std::vector<uint8_t*> base((size_t)opt_.world, nullptr);
-    for (int r : plan_.neighbours) {
+    for (int r = 0; r < opt_.world; ++r) {      // every rank's window: the neighbours' for the halo, all of them for the CG all-reduce
+        if (r == opt_.rank) continue;
         cudaIpcMemHandle_t h;
         std::memcpy(&h, static_cast<const uint8_t*>(handles) + 64 * (size_t)r, 64);
         void* p = nullptr;
@@ -772,7 +910,8 @@ void Engine::connectLocal(Engine* const* engines, int n)
         if (e->opt_.world != n || e->opt_.rank != r) throw std::runtime_error("connectLocal: engines must be ranks 0..n-1 of world n, in order");
         CUDA_CHECK(cudaSetDevice(e->opt_.device));
         std::vector<uint8_t*> base((size_t)n, nullptr);
-        for (int q : e->plan_.neighbours) {
+        for (int q = 0; q < n; ++q) {
+            if (q == r) continue;
             if (engines[q]->opt_.device != e->opt_.device) {
                 int can = 0;
                 CUDA_CHECK(cudaDeviceCanAccessPeer(&can, e->opt_.device, engines[q]->opt_.device));

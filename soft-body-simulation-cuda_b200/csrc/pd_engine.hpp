@@ -51,6 +51,10 @@ public:
     // end-to-end step on host buffers (pinned or pageable): upload, n steps, download
     void stepHost(int nSteps, const float* Xin, const float* Vin, const float* XTin, float* Xout, float* Vout, float* XTout);
 
+    // the same on this rank's SHARD only: 3 * numOwned() floats per array in local owned order (see ownedIds)
+    void stepHostOwned(int nSteps, const float* Xin, const float* Vin, const float* XTin, float* Xout, float* Vout, float* XTout);
+    void ownedIds(uint32_t* out) const;                     // original vertex id of each owned vertex, local order
+
     const PerfCounters& perf() const { return perfc_; }
     void syncSolveStats();                                  // PCG / Cholesky modes: fold the device-side iteration counters in
     float lastError() const { return lastErr_; }
@@ -111,6 +115,9 @@ private:
     SolverParams params_;
     EngineOptions opt_;
     bool ready_ = false, perf_ = false, graphValid_ = false;
+    bool pdlActive_ = false;
+    bool usePdl_ = false;     // programmatic dependent launch of the per-iteration kernels (pd_kernels.cuh: pdl_wait); measured SLOWER
+                              // on B200 (grid139: 42.0 vs 36.9 ms/step, batch64: 2.68 vs 2.23), so it stays an opt-in experiment (PD_PDL=1)
     float dt2Prepared_ = 0.f;
     PerfCounters perfc_;
     int localGrid_ = 0, numSms_ = 0;

@@ -64,6 +64,12 @@ __device__ __forceinline__ void cp_async16_hint(uint32_t dstShared, const void* 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still draining; pdl_wait() blocks until the predecessor grid has
+// completed and its writes are visible (a no-op for a normal launch), pdl_launch_dependents() lets the successor's
+// CTAs be scheduled as soon as every CTA of this grid has got this far.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 ldg_hint(const float4* p, unsigned long long policy)
 {
@@ -329,6 +335,10 @@ k_local(const uint8_t* __restrict__ records, const uint4* __restrict__ tileTab, 
         if (nIt > 2) prefetch_entry(2);
     }
     uint32_t veCur = load_ve(0);                             // vlist entry of this thread: tile it
+    // everything above touches only the immutable tile stream; from here on the kernel reads positions written by
+    // the previous launch in the stream (and later overwrites the slots that launch reads)
+    pdl_launch_dependents();
+    pdl_wait();
     halo_before(0);
     gather(veCur);
     uint32_t veNext = (nIt > 1) ? load_ve(1) : 0xffffffffu;  // tile it + 1
@@ -438,45 +448,83 @@ k_local(const uint8_t* __restrict__ records, const uint4* __restrict__ tileTab, 
 // b = ordered sum of the vertex's partial-sum slots (the first one already carries (M/h^2) s_old).
 // Arithmetic forms follow the reference's SASS: next = fma(-c,q,b)/(c+md) + q (IEEE division);
 // under-relaxation as one DFMA (the reference's `0.9 *` literal is a double); Chebyshev as one FFMA.
-template <bool BASE>      // BASE: the slots hold the elastic terms only and b0 is added here (product default);
+// Multi-GPU (DIST): the halo exchange is FUSED into this kernel -- a boundary vertex's new position goes straight
+// from the register that holds it into the neighbours' ghost entries over NVLink (pushPtr/pushDst/pushNbr = CSR of
+// the push list by owned vertex), and the last block to finish raises this rank's flag at the neighbours
+// (fence.sys by the storing threads -> ticket -> st.release.sys, as k_halo_push).  No separate push launch.
+struct DistPush {
+    const uint32_t* pushPtr;                    // nOwn + 1
+    const uint32_t* pushDst;                    // ghost index at the neighbour
+    const uint32_t* pushNbr;                    // neighbour slot
+    float4* const* peerQ;                       // [nNbr]: the neighbours' copies of the buffer this launch writes
+    unsigned long long* const* peerFlag;        // [nNbr]: this rank's entry in the neighbours' flag arrays
+    int nNbr;
+    unsigned long long* epoch;
+    unsigned int* ticket;
+};
+
+template <bool BASE, bool DIST = false>      // BASE: the slots hold the elastic terms only and b0 is added here (product default);
                            // otherwise the vertex's first slot already starts from b0 (faithful mode)
 __global__ void k_vertex_jacobi(int nV, const float4* __restrict__ qcur, const float4* __restrict__ qprev,
                                 float4* __restrict__ qnext, const float4* __restrict__ X0, const float4* __restrict__ b0,
                                 const float2* __restrict__ cc, const uint32_t* __restrict__ vslotPtr,
                                 const uint32_t* __restrict__ vslot, const float4* __restrict__ P,
-                                float omega, float wdbc)
+                                float omega, float wdbc, DistPush dp)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= nV) return;
-    const float2 c2 = cc[v];
-    const float c = fabsf(c2.x);
-    float bx, by, bz;
-    if (c2.x < 0.f) {                 // computeDBCLocal overwrites b for pinned vertices; DBCX = X0 (pdSolver.cu:134)
-        const float4 d = X0[v];
-        bx = __fmul_rn(d.x, wdbc); by = __fmul_rn(d.y, wdbc); bz = __fmul_rn(d.z, wdbc);
-    } else {
-        uint32_t e0 = vslotPtr[v];
-        const uint32_t e1 = vslotPtr[v + 1];
-        const float4 p0 = (BASE || e0 == e1) ? b0[v] : __ldg(&P[vslot[e0++]]);    // a vertex without tets keeps b = (M/h^2) s_old
-        bx = p0.x; by = p0.y; bz = p0.z;
-        for (uint32_t e = e0; e < e1; ++e) {
-            const float4 p = __ldg(&P[vslot[e]]);
-            bx = __fadd_rn(bx, p.x); by = __fadd_rn(by, p.y); bz = __fadd_rn(bz, p.z);
+    bool pushed = false;
+    pdl_launch_dependents();
+    pdl_wait();              // the slots (and, multi-GPU, the ticket) come from the local kernel just before
+    if (v < nV) {
+        const float2 c2 = cc[v];
+        const float c = fabsf(c2.x);
+        float bx, by, bz;
+        if (c2.x < 0.f) {                 // computeDBCLocal overwrites b for pinned vertices; DBCX = X0 (pdSolver.cu:134)
+            const float4 d = X0[v];
+            bx = __fmul_rn(d.x, wdbc); by = __fmul_rn(d.y, wdbc); bz = __fmul_rn(d.z, wdbc);
+        } else {
+            uint32_t e0 = vslotPtr[v];
+            const uint32_t e1 = vslotPtr[v + 1];
+            const float4 p0 = (BASE || e0 == e1) ? b0[v] : __ldg(&P[vslot[e0++]]);    // a vertex without tets keeps b = (M/h^2) s_old
+            bx = p0.x; by = p0.y; bz = p0.z;
+            for (uint32_t e = e0; e < e1; ++e) {
+                const float4 p = __ldg(&P[vslot[e]]);
+                bx = __fadd_rn(bx, p.x); by = __fadd_rn(by, p.y); bz = __fadd_rn(bz, p.z);
+            }
+        }
+        const float4 q = qcur[v], pr = qprev[v];
+        const float den = c2.y;
+        float nx = __fadd_rn(__fdiv_rn(__fmaf_rn(-c, q.x, bx), den), q.x);
+        float ny = __fadd_rn(__fdiv_rn(__fmaf_rn(-c, q.y, by), den), q.y);
+        float nz = __fadd_rn(__fdiv_rn(__fmaf_rn(-c, q.z, bz), den), q.z);
+        // under-relaxation in double, as the reference's `0.9 *` literal (pdUtil.cu:221)
+        nx = (float)__fma_rn((double)__fsub_rn(nx, q.x), 0.9, (double)q.x);
+        ny = (float)__fma_rn((double)__fsub_rn(ny, q.y), 0.9, (double)q.y);
+        nz = (float)__fma_rn((double)__fsub_rn(nz, q.z), 0.9, (double)q.z);
+        nx = __fmaf_rn(__fsub_rn(nx, pr.x), omega, pr.x);
+        ny = __fmaf_rn(__fsub_rn(ny, pr.y), omega, pr.y);
+        nz = __fmaf_rn(__fsub_rn(nz, pr.z), omega, pr.z);
+        const float4 out = make_float4(nx, ny, nz, 0.f);
+        qnext[v] = out;
+        if (DIST) {
+            const uint32_t p1 = dp.pushPtr[v + 1];
+            for (uint32_t e = dp.pushPtr[v]; e < p1; ++e) { dp.peerQ[dp.pushNbr[e]][dp.pushDst[e]] = out; pushed = true; }
         }
     }
-    const float4 q = qcur[v], pr = qprev[v];
-    const float den = c2.y;
-    float nx = __fadd_rn(__fdiv_rn(__fmaf_rn(-c, q.x, bx), den), q.x);
-    float ny = __fadd_rn(__fdiv_rn(__fmaf_rn(-c, q.y, by), den), q.y);
-    float nz = __fadd_rn(__fdiv_rn(__fmaf_rn(-c, q.z, bz), den), q.z);
-    // under-relaxation in double, as the reference's `0.9 *` literal (pdUtil.cu:221)
-    nx = (float)__fma_rn((double)__fsub_rn(nx, q.x), 0.9, (double)q.x);
-    ny = (float)__fma_rn((double)__fsub_rn(ny, q.y), 0.9, (double)q.y);
-    nz = (float)__fma_rn((double)__fsub_rn(nz, q.z), 0.9, (double)q.z);
-    nx = __fmaf_rn(__fsub_rn(nx, pr.x), omega, pr.x);
-    ny = __fmaf_rn(__fsub_rn(ny, pr.y), omega, pr.y);
-    nz = __fmaf_rn(__fsub_rn(nz, pr.z), omega, pr.z);
-    qnext[v] = make_float4(nx, ny, nz, 0.f);
+    if (DIST) {
+        if (pushed) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int t = atomicAdd(dp.ticket, 1u);
+            if (t == gridDim.x - 1) {                      // every block's remote stores are fenced: publish
+                *dp.ticket = 0u;
+                const unsigned long long e = *dp.epoch + 1ull;
+                *dp.epoch = e;
+                __threadfence_system();
+                for (int j = 0; j < dp.nNbr; ++j) st_release_sys(dp.peerFlag[j], e);
+            }
+        }
+    }
 }
 
 // right-hand side for the direct / CG global solves: b = c*s_old + sum of partials (R, not R-F)
@@ -583,7 +631,7 @@ __global__ void k_import3(int nV, const float* __restrict__ src3, const uint32_t
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nV) return;
-    const float* s = src3 + 3ull * oldOfNew[v];
+    const float* s = src3 + 3ull * (oldOfNew ? oldOfNew[v] : (uint32_t)v);      // no map: compact shard in local order
     dst[v] = make_float4(s[0], s[1], s[2], 0.f);
 }
 __global__ void k_export3(int nV, const float4* __restrict__ src, const uint32_t* __restrict__ oldOfNew, float* __restrict__ dst3)
@@ -591,7 +639,7 @@ __global__ void k_export3(int nV, const float4* __restrict__ src, const uint32_t
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nV) return;
     const float4 s = src[v];
-    float* d = dst3 + 3ull * oldOfNew[v];
+    float* d = dst3 + 3ull * (oldOfNew ? oldOfNew[v] : (uint32_t)v);
     d[0] = s.x; d[1] = s.y; d[2] = s.z;
 }
 

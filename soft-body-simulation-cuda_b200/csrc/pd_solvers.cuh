@@ -71,8 +71,108 @@ __device__ __forceinline__ void grid_sum3(cg::grid_group& grid, double a, double
     grid.sync();          // the partial slots may be overwritten by the next reduction
 }
 
+// ------------------------------------------------------------------ multi-GPU PCG
+// The rows of A^ are partitioned like the vertices; every rank runs the same cooperative kernel on its rows.
+// Two exchanges per CG iteration go over NVLink peer memory from INSIDE the kernel (no NCCL call, no host):
+//  * the halo of p: boundary entries are stored straight into the neighbours' ghost entries of p, then a flag per
+//    neighbour (sequence number) is raised; the SpMV starts once every neighbour's flag has arrived;
+//  * the dot products (p.Ap | r.r, r.z | the PD error): an all-gather of the ranks' partial sums (three doubles +
+//    a sequence number per rank, double-buffered by sequence parity) that every rank adds up in RANK ORDER, so all
+//    ranks hold bit-identical scalars and take identical branches.
+// Slot reuse is safe with two parities: a rank can only publish reduction k+2 after it has seen every rank's
+// reduction k+1, which those ranks publish after all their blocks have consumed reduction k (grid.sync in grid_sum3).
+struct DistSolve {
+    int world, rank, nNbr, nPush, nGlobal;
+    const int* nbr;                               // neighbour ranks
+    const uint32_t *pushSrc, *pushDst, *pushNbr;  // the engine's push list (owned vertex -> ghost entry at neighbour slot)
+    float4* const* peerP;                         // [nNbr]: the neighbours' p vectors
+    unsigned long long* const* peerPFlag;         // [nNbr]: this rank's entry in the neighbours' p-flag arrays
+    const unsigned long long* pflags;             // this rank's p-flag array, written by the peers (indexed by rank)
+    double* const* peerRed;                       // [world]: every rank's reduction slots (own included)
+    const double* red;                            // this rank's reduction slots: [parity][rank][a, b, c, seq]
+    unsigned long long* seq;                      // device-resident counters: [0] p pushes, [1] reductions
+    unsigned int* status;                         // set to 1 when a wait gave up
+};
+constexpr long long SOLVE_WAIT_LIMIT_CYCLES = 20000000000ll;
+
+__device__ __forceinline__ unsigned long long solve_ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void solve_st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double solve_ld_relaxed_sys(const double* p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// in/out: the rank-local sums (identical in every thread of the grid, from grid_sum3) -> the sums over all ranks
+__device__ __forceinline__ void dist_allreduce3(const DistSolve& D, unsigned long long seq, double* sh, double v[3])
+{
+    if (blockIdx.x == 0 && (int)threadIdx.x < D.world) {
+        double* slot = D.peerRed[threadIdx.x] + ((seq & 1ull) * (unsigned)D.world + (unsigned)D.rank) * 4u;
+        slot[0] = v[0]; slot[1] = v[1]; slot[2] = v[2];
+        __threadfence_system();
+        solve_st_release_sys(reinterpret_cast<unsigned long long*>(slot + 3), seq);
+    }
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        double a = 0, b = 0, c = 0;
+        if (lane < D.world) {
+            const double* slot = D.red + ((seq & 1ull) * (unsigned)D.world + (unsigned)lane) * 4u;
+            const long long t0 = clock64();
+            while (solve_ld_acquire_sys(reinterpret_cast<const unsigned long long*>(slot + 3)) != seq) {
+                if (clock64() - t0 > SOLVE_WAIT_LIMIT_CYCLES) { atomicExch(D.status, 1u); break; }
+            }
+            a = solve_ld_relaxed_sys(slot); b = solve_ld_relaxed_sys(slot + 1); c = solve_ld_relaxed_sys(slot + 2);
+        }
+        double sa = 0, sb = 0, sc = 0;
+        for (int r = 0; r < D.world; ++r) {          // rank order: every rank gets the same bits
+            sa += __shfl_sync(0xffffffffu, a, r); sb += __shfl_sync(0xffffffffu, b, r); sc += __shfl_sync(0xffffffffu, c, r);
+        }
+        if (lane == 0) { sh[24] = sa; sh[25] = sb; sh[26] = sc; }
+    }
+    __syncthreads();
+    v[0] = sh[24]; v[1] = sh[25]; v[2] = sh[26];
+    __syncthreads();
+}
+
+template <bool DIST>
+__device__ __forceinline__ void solve_sum3(cg::grid_group& grid, const DistSolve& D, unsigned long long& rSeq, double a, double b, double c,
+                                           double* partials, double* sh, double out[3])
+{
+    grid_sum3(grid, a, b, c, partials, sh, out);
+    if (DIST) { ++rSeq; dist_allreduce3(D, rSeq, sh, out); }
+}
+
+// boundary entries of p -> the neighbours' ghost entries, flags up, wait for the neighbours' (call after a grid.sync
+// that completed p); returns with every ghost entry of p current
+__device__ __forceinline__ void dist_push_p(cg::grid_group& grid, const DistSolve& D, unsigned long long& pSeq, const float4* p)
+{
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+    for (int i = gtid; i < D.nPush; i += gstride) D.peerP[D.pushNbr[i]][D.pushDst[i]] = p[D.pushSrc[i]];
+    __threadfence_system();
+    grid.sync();
+    ++pSeq;
+    if (blockIdx.x == 0 && (int)threadIdx.x < D.nNbr) solve_st_release_sys(D.peerPFlag[threadIdx.x], pSeq);
+    if ((int)threadIdx.x < D.nNbr) {
+        const unsigned long long* f = D.pflags + D.nbr[threadIdx.x];
+        const long long t0 = clock64();
+        while (solve_ld_acquire_sys(f) < pSeq) {
+            if (clock64() - t0 > SOLVE_WAIT_LIMIT_CYCLES) { atomicExch(D.status, 1u); break; }
+        }
+    }
+    __syncthreads();
+}
+
 // row v of y = A^ x for the three interleaved right-hand sides (CSR, ascending columns, one thread per row)
-__device__ __forceinline__ float4 spmv_row(const CsrDev& A, int v, const float4* __restrict__ x)
+__device__ __forceinline__ float4 spmv_row(const CsrDev& A, int v, const float4* x)
 {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     const int e1 = A.rowPtr[v + 1];
@@ -85,8 +185,9 @@ __device__ __forceinline__ float4 spmv_row(const CsrDev& A, int v, const float4*
 }
 
 // computeError + prev = x, fused into the tail of both solve kernels (pdSolver.cu:186-192,243-253)
+template <bool DIST>
 __device__ __forceinline__ void finish_pd_iteration(cg::grid_group& grid, int n, const float4* x, float4* xprev, float tol, SolveState* st,
-                                                    int innerIters, double* partials, double* sh)
+                                                    int innerIters, double* partials, double* sh, const DistSolve& D, unsigned long long& rSeq)
 {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
     double acc = 0;
@@ -97,9 +198,9 @@ __device__ __forceinline__ void finish_pd_iteration(cg::grid_group& grid, int n,
         xprev[v] = b;
     }
     double s[3];
-    grid_sum3(grid, acc, 0.0, 0.0, partials, sh, s);
+    solve_sum3<DIST>(grid, D, rSeq, acc, 0.0, 0.0, partials, sh, s);
     if (gtid == 0) {
-        const float err = (float)(s[0] / (3.0 * (double)n));
+        const float err = (float)(s[0] / (3.0 * (double)(DIST ? D.nGlobal : n)));
         st->err = err;
         st->pdIters += 1; st->pdItersTotal += 1; st->innerIters += innerIters;
         if (!(sqrtf(err) >= tol)) st->done = 1;
@@ -113,14 +214,19 @@ __device__ __forceinline__ void finish_pd_iteration(cg::grid_group& grid, int n,
 // Dots accumulate in double and are rounded to float where the reference holds a float (cublasSdot results);
 // vector updates use the same unfused multiply-then-add as the oracle (oracle/pd_oracle.c:pcg_solve).
 // Three grid-wide synchronisations per CG iteration (p update | SpMV + p.q | x, r update + r.r, r.z).
+// DIST: A holds this rank's rows (n = owned vertices; columns index the rank's local vertex array, ghosts included);
+// x and p carry ghost entries -- x's are current on entry (the engine's position halo), p's are exchanged here.
+template <bool DIST>
 __global__ void __launch_bounds__(SOLVE_THREADS)
-k_pcg_solve(CsrDev A, const float4* __restrict__ b, float4* __restrict__ x, float4* __restrict__ r, float4* __restrict__ p, float4* __restrict__ q,
-            float4* __restrict__ xprev, int maxIter, float cgTol, float pdTol, SolveState* st, double* partials)
+k_pcg_solve(CsrDev A, const float4* __restrict__ b, float4* x, float4* __restrict__ r, float4* p, float4* __restrict__ q,
+            float4* __restrict__ xprev, int maxIter, float cgTol, float pdTol, SolveState* st, double* partials, DistSolve D)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[27];
-    if (st->done) return;                       // uniform over the grid: this PD iteration is skipped
+    if (st->done) return;                       // uniform over the grid (and over the ranks): this PD iteration is skipped
     const int n = A.n, gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+    unsigned long long pSeq = 0, rSeq = 0;
+    if (DIST) { pSeq = D.seq[0]; rSeq = D.seq[1]; }
     double s[3];
     // r = b - A x ; rr = r.r ; rz = r.(D^-1 r)
     double arr = 0, arz = 0;
@@ -132,7 +238,7 @@ k_pcg_solve(CsrDev A, const float4* __restrict__ b, float4* __restrict__ x, floa
         arr += (double)rv.x * rv.x + (double)rv.y * rv.y + (double)rv.z * rv.z;
         arz += (double)rv.x * (double)__fmul_rn(rv.x, id) + (double)rv.y * (double)__fmul_rn(rv.y, id) + (double)rv.z * (double)__fmul_rn(rv.z, id);
     }
-    grid_sum3(grid, arr, arz, 0.0, partials, sh, s);
+    solve_sum3<DIST>(grid, D, rSeq, arr, arz, 0.0, partials, sh, s);
     float rho = (float)s[1], rhoPrev = 0.f;
     float rn = sqrtf((float)s[0]);
     int k = 0;
@@ -152,13 +258,14 @@ k_pcg_solve(CsrDev A, const float4* __restrict__ b, float4* __restrict__ x, floa
             p[v] = pv;
         }
         grid.sync();
+        if (DIST) dist_push_p(grid, D, pSeq, p);
         double apq = 0;
         for (int v = gtid; v < n; v += gstride) {       // q = A p ; p.q
             const float4 qv = spmv_row(A, v, p), pv = p[v];
             q[v] = qv;
             apq += (double)pv.x * qv.x + (double)pv.y * qv.y + (double)pv.z * qv.z;
         }
-        grid_sum3(grid, apq, 0.0, 0.0, partials, sh, s);
+        solve_sum3<DIST>(grid, D, rSeq, apq, 0.0, 0.0, partials, sh, s);
         const float alpha = __fdiv_rn(rho, (float)s[0]);
         arr = 0; arz = 0;
         for (int v = gtid; v < n; v += gstride) {       // x += alpha p ; r -= alpha q ; r.r ; r.z
@@ -171,12 +278,13 @@ k_pcg_solve(CsrDev A, const float4* __restrict__ b, float4* __restrict__ x, floa
             arr += (double)rv.x * rv.x + (double)rv.y * rv.y + (double)rv.z * rv.z;
             arz += (double)rv.x * (double)__fmul_rn(rv.x, id) + (double)rv.y * (double)__fmul_rn(rv.y, id) + (double)rv.z * (double)__fmul_rn(rv.z, id);
         }
-        grid_sum3(grid, arr, arz, 0.0, partials, sh, s);
+        solve_sum3<DIST>(grid, D, rSeq, arr, arz, 0.0, partials, sh, s);
         rhoPrev = rho;
         rho = (float)s[1];
         rn = sqrtf((float)s[0]);
     }
-    finish_pd_iteration(grid, n, x, xprev, pdTol, st, k, partials, sh);
+    finish_pd_iteration<DIST>(grid, n, x, xprev, pdTol, st, k, partials, sh, D, rSeq);
+    if (DIST && gtid == 0) { D.seq[0] = pSeq; D.seq[1] = rSeq; }
 }
 
 // ------------------------------------------------------------------ prefactored sparse Cholesky solve
@@ -247,7 +355,8 @@ k_chol_solve(CholDev C, const float4* __restrict__ b, float4* x, float4* y, floa
         *reinterpret_cast<volatile int*>(ready + i) = tagB;
     }
     grid.sync();
-    finish_pd_iteration(grid, n, x, xprev, pdTol, st, 0, partials, sh);
+    unsigned long long noSeq = 0;
+    finish_pd_iteration<false>(grid, n, x, xprev, pdTol, st, 0, partials, sh, DistSolve{}, noSeq);
 }
 
 // start of a step in the non-Jacobi modes: err = 1, nothing skipped (pdSolver.cu:163)
