@@ -26,6 +26,7 @@ for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
 WORKLOADS = {
     # name: (cells per axis, PD iterations per step, description)   SURVEY.md section 8d
     "grid139": (139, 100, "Kuhn 6-tet grid 139^3 cells (2,744,000 verts, 16,113,714 tets), float PD, Chebyshev-Jacobi 100 it/step"),
+    "grid70": (70, 100, "Kuhn 6-tet grid 70^3 cells (357,911 verts, 2,058,000 tets) -- the per-GPU share of grid139 on 8 GPUs"),
     "grid55": (55, 100, "Kuhn 6-tet grid 55^3 cells (175,616 verts, 998,250 tets), float PD, Chebyshev-Jacobi 100 it/step"),
     "grid24": (24, 100, "Kuhn 6-tet grid 24^3 cells (82,944 tets) -- CPU-sized sample"),
     # independent (house2 + sphere) contexts, 64 per GPU, no inter-GPU communication (weak scaling)
