@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpd_b200.so")
+LIB_PATH = os.environ.get("PD_B200_LIB") or os.path.join(_HERE, "libpd_b200.so")     # PD_B200_LIB: kernel-variant experiments only
 
 PD_JACOBI, PD_CHOLESKY, PD_PCG_JACOBI = 0, 1, 2
 PD_PLANE, PD_SPHERE, PD_CYLINDER = 0, 1, 2

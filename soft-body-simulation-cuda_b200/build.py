@@ -9,7 +9,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libpd_b200.so")
+OUT = os.environ.get("PD_OUT", os.path.join(HERE, "libpd_b200.so"))      # PD_OUT / PD_DEFS: experiment variants only
+DEFS = os.environ.get("PD_DEFS", "").split()
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = os.environ.get("PD_HOSTCXX", "/usr/bin/g++")
 
@@ -30,12 +31,12 @@ def _newest_src():
 def build(force=False, verbose=False):
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_src():
         return OUT
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if not DEFS else "build_" + "_".join(d.strip("-D").replace("=", "") for d in DEFS))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     for s in SOURCES:
         o = os.path.join(objdir, s.rsplit(".", 1)[0] + ".o")
-        cmd = [NVCC] + ARCH + COMMON + ["-x", "cu" if s.endswith(".cu") else "c++", "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [NVCC] + ARCH + COMMON + DEFS + ["-x", "cu" if s.endswith(".cu") else "c++", "-c", os.path.join(CSRC, s), "-o", o]
         if s.endswith(".cu"):
             cmd += ["-Xptxas", "-v"] if verbose else []
         if verbose:

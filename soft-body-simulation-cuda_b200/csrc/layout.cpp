@@ -178,11 +178,11 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
             // order: in-tile incidence count descending, id ascending
             std::sort(vl.begin(), vl.end(), [&](uint32_t a, uint32_t b) { return lidx[a] != lidx[b] ? lidx[a] > lidx[b] : a < b; });
             nLocal = (uint32_t)vl.size();
-            nGroups = (nLocal + 31u) / 32u;
+            nGroups = (nLocal + (uint32_t)TILE_GROUP - 1u) / (uint32_t)TILE_GROUP;
             nRows = 0;
             for (uint32_t g = 0; g < nGroups; ++g) {
                 gRowBase[g] = nRows;
-                gRows[g] = (lidx[vl[32 * g]] + 1u) / 2u;        // the group's first vertex has its largest count
+                gRows[g] = (lidx[vl[TILE_GROUP * g]] + 2u * TILE_LPV - 1u) / (2u * TILE_LPV);        // the group's first vertex has its largest count
                 nRows += gRows[g];
             }
             if (nRows <= (uint32_t)TILE_ROWSMAX || nTets == 1) break;
@@ -214,8 +214,8 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
             for (int k = 0; k < 4; ++k) {
                 const uint32_t l = lidx[tet[4 * ((size_t)t0 + tl) + k]];
                 cl[tl][k] = l;
-                const uint32_t e = fill[l]++, g = l / 32u, lane = l % 32u;
-                epos[4 * tl + k] = ((gRowBase[g] + e / 2u) * 32u + lane) * 2u + (e & 1u);
+                const uint32_t e = fill[l]++, g = l / (uint32_t)TILE_GROUP, lane = l % (uint32_t)TILE_GROUP + (uint32_t)TILE_GROUP * ((e >> 1) % (uint32_t)TILE_LPV);
+                epos[4 * tl + k] = ((gRowBase[g] + e / (2u * TILE_LPV)) * 32u + lane) * 2u + (e & 1u);
             }
         // H-scratch column of every (tet, corner): proper 8-colouring of the bipartite multigraph
         // store groups {8 consecutive tets, corner k}  x  load groups {row, half, 8 consecutive lanes}
@@ -241,7 +241,7 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
         }
         for (uint32_t tl = 0; tl < nTets; ++tl) {
             const size_t t = (size_t)t0 + tl;
-            float* tr = reinterpret_cast<float*>(rec + TILE_OFF_TETS + 48 * (size_t)tl);
+            float tr[12];
             for (int e = 0; e < 9; ++e) tr[e] = DmInv[9 * t + e];
             tr[9] = w[t];
             uint32_t h[4];
@@ -252,6 +252,7 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
             const uint32_t c01 = h[0] | (h[1] << 16), c23 = h[2] | (h[3] << 16);
             std::memcpy(&tr[10], &c01, 4);
             std::memcpy(&tr[11], &c23, 4);
+            for (uint32_t j = 0; j < 12; ++j) std::memcpy(rec + tile_tet_word(nTets, tl, j), &tr[j], 4);      // three 16-byte planes
         }
         L.tileTab.push_back(TileEntry{(uint64_t)base, (uint32_t)abBytes, (uint32_t)cBytes});
         slot += nLocal;

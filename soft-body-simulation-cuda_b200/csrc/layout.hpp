@@ -3,6 +3,7 @@
 // All of it is integer/index work that tests check bit-for-bit against an independent numpy
 // restatement (tests/layout_oracle.py).  The specification lives in DESIGN.md section 3.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <vector>
 
@@ -10,7 +11,14 @@ namespace pdb200 {
 
 constexpr int TILE_T = 256;       // tets per tile (= threads per CTA of the local kernel)
 constexpr int TILE_NLMAX = 256;   // max distinct vertices per tile (a tile is closed early beyond); = TILE_T: one vertex per thread
-constexpr int TILE_NGROUPS = TILE_NLMAX / 32;   // tile-local vertices are handled in groups of 32 (one warp)
+#ifndef PD_TILE_GROUP
+#define PD_TILE_GROUP 32
+#endif
+constexpr int TILE_GROUP = PD_TILE_GROUP;             // tile-local vertices are summed in groups of 32 (one warp, one lane per vertex; measured
+                                                     // faster on grid139) or 16 (two lanes per vertex: half the longest list, more instructions)
+constexpr int TILE_LPV = 32 / TILE_GROUP;             // lanes per vertex in phase C
+constexpr int TILE_NGROUPS = TILE_NLMAX / TILE_GROUP;   // warp w of the local kernel sums groups w (and w + 8)
+static_assert(TILE_GROUP == 32 || TILE_GROUP == 16, "phase C group size");
 constexpr int TILE_ROWSMAX = 56;  // max incidence rows per tile (a tile is shrunk beyond)
 constexpr uint32_t TILE_HSTRIDE = TILE_T * 16;           // bytes between corner planes of the per-tile H scratch
 constexpr uint32_t TILE_ZERO_OFF = 4u * TILE_HSTRIDE;    // byte offset of the all-zero float4 padding entries point at
@@ -19,19 +27,24 @@ constexpr uint32_t TILE_OWNER_BIT = 0x80000000u;         // vlist flag: this slo
 // One packed tile record = two parts, each moved to shared memory by ONE
 // bulk copy (TMA).  Part AB (phases A and B of the local kernel, double buffered):
 //   +0    TileHeader                                                          32 B
-//   +32   group table u32[12]: rowBase | nRows << 16 of each 32-vertex group (8 used)  48 B
-//   +80   tet records, 48 B each: f32 B[9] (DmInv, row-major), f32 w = |V0|*mu, u32 c01, u32 c23 --
+//   +32   group table u32[16]: rowBase | nRows << 16 of each TILE_GROUP-vertex group     64 B
+//   +96   tet records, 48 B (12 words) each: f32 B[9] (DmInv, row-major), f32 w = |V0|*mu, u32 c01, u32 c23 --
 //         four 16-bit corner words: bits 4..11 = tile-local vertex index (so `word & 0xff0` is the byte offset
-//         into the staged vertex array), bits 12..14 = H-scratch column of this corner's contribution
+//         into the staged vertex array), bits 12..14 = H-scratch column of this corner's contribution.
+//         Stored as THREE PLANES of 16 bytes per tet (plane p holds words 4p..4p+3 of every tet of the tile,
+//         tile_tet_word()), so that thread t of the local kernel reads its record with three fully coalesced
+//         16-byte loads straight from global memory (plane stride = 16 * nTets).
 // The tile's vertex list lives OUTSIDE the record, in the global array Layout::vlist indexed by slot.
 // Slots are PADDED per tile: slot = tile * TILE_NLMAX + tile-local vertex, so that the local kernel needs no
 // per-tile offset to find them; entry = u32 global (renumbered) vertex id | TILE_OWNER_BIT, or 0xffffffff for
 // the unused tail; tile-local vertices ordered by (in-tile incidence count descending, id ascending).  The
 // local kernel reads it with plain coalesced loads two tiles ahead of use (it feeds the position gather,
 // which runs one tile ahead).  Unused slots of the partial-sum array are never read or written.
-// Part C (phase C, single buffered): the tile-local incidence lists, transposed per group of 32
-// vertices: row r of group g holds, for each of the 32 lanes (vertices), entries 2r and 2r+1 of that
-// vertex's list packed as two u16 in one u32.  An entry is the byte offset of one tet-corner
+// Part C (phase C, double buffered): the tile-local incidence lists, transposed per group of TILE_GROUP
+// vertices.  TILE_GROUP 32: row r of group g holds, for each of the 32 lanes (vertices), entries 2r and 2r+1 of
+// that vertex's list packed as two u16 in one u32.  TILE_GROUP 16: a vertex is summed by TWO lanes of a warp
+// (combined by one shuffle): row r holds, for vertex l, entries 4r and 4r+1 of its list in lane l % 16 and
+// entries 4r+2 and 4r+3 in lane l % 16 + 16.  An entry is the byte offset of one tet-corner
 // contribution in the H scratch, tile_h_offset(tet, corner, column): the 8 tets of a quarter-warp share one
 // 128-byte line per corner and the column (0..7) inside it comes from an 8-colouring (layout.cpp:color_tile)
 // that makes every quarter-warp STS.128 of phase B and every quarter-warp LDS.128 of phase C conflict free.
@@ -45,8 +58,10 @@ struct TileEntry {   // per-tile entry of the device tile table (one uint4)
     uint32_t abBytes, cBytes;
 };
 inline uint32_t rup16(uint32_t x) { return (x + 15u) & ~15u; }
-constexpr uint32_t TILE_OFF_TETS = 80u;
+constexpr uint32_t TILE_OFF_TETS = 96u;
 inline uint32_t tile_ab_bytes(uint32_t nTets) { return TILE_OFF_TETS + 48u * nTets; }
+// byte offset (inside part AB) of word j (0..11) of the record of tile-local tet tl in a tile of nTets tets
+inline size_t tile_tet_word(uint32_t nTets, uint32_t tl, uint32_t j) { return TILE_OFF_TETS + 16u * ((size_t)tl + (size_t)nTets * (j / 4u)) + 4u * (j % 4u); }
 inline uint32_t tile_h_offset(uint32_t tet, uint32_t corner, uint32_t column) { return corner * TILE_HSTRIDE + ((tet & ~7u) | column) * 16u; }
 inline uint32_t tile_corner_half(uint32_t localVertex, uint32_t column) { return (localVertex << 4) | (column << 12); }
 // TMA landing buffers (multiples of 128 B)

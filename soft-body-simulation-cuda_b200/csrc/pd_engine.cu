@@ -50,7 +50,7 @@ struct WindowLayout {
 struct Engine::Impl {
     // tile stream
     uint8_t* records = nullptr;
-    uint4* tileTab = nullptr;         // per tile: record offset (lo, hi), part AB bytes, part C bytes
+    uint32_t* tileTab = nullptr;      // per tile TILE_META_WORDS words: record offset (lo, hi), part AB bytes, part C bytes, 8 per-warp words
     uint32_t *vslotPtr = nullptr, *vslot = nullptr, *vlist = nullptr;
     float4* P = nullptr;             // one partial RHS sum per (tile, tile-local vertex) slot
     // per-vertex state (renumbered, padded float4)
@@ -146,7 +146,7 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     // ---- device buffers
     Impl& d = *d_;
     d.records = dalloc<uint8_t>(L_.records.size());
-    d.tileTab = dalloc<uint4>(L_.tileTab.size());
+    d.tileTab = dalloc<uint32_t>(L_.tileTab.size() * TILE_META_WORDS);
     d.vslotPtr = dalloc<uint32_t>(L_.vslotPtr.size());
     d.vslot = dalloc<uint32_t>(L_.vslot.size());
     d.vlist = dalloc<uint32_t>(L_.vlist.size());
@@ -175,7 +175,26 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
 
     CUDA_CHECK(cudaMemcpy(d.records, L_.records.data(), L_.records.size(), cudaMemcpyHostToDevice));
     static_assert(sizeof(TileEntry) == sizeof(uint4), "tile table entry layout");
-    CUDA_CHECK(cudaMemcpy(d.tileTab, L_.tileTab.data(), L_.tileTab.size() * sizeof(TileEntry), cudaMemcpyHostToDevice));
+    {   // device tile table (pd_kernels.cuh, TILE_META_WORDS): offset / 16, abBytes | cBytes << 16, two words per warp
+        std::vector<uint32_t> meta(L_.tileTab.size() * TILE_META_WORDS, 0u);
+        for (size_t ti = 0; ti < L_.tileTab.size(); ++ti) {
+            const uint8_t* rec = L_.records.data() + L_.tileRecOff[ti];
+            TileHeader h; std::memcpy(&h, rec, sizeof(h));
+            uint32_t* m = &meta[ti * TILE_META_WORDS];
+            if ((L_.tileTab[ti].off & 15u) || (L_.tileTab[ti].off >> 4) > 0xffffffffull || L_.tileTab[ti].abBytes > 0xffffu || L_.tileTab[ti].cBytes > 0xffffu)
+                throw std::runtime_error("tile table: record offset / size out of range");
+            m[0] = (uint32_t)(L_.tileTab[ti].off >> 4);
+            m[1] = L_.tileTab[ti].abBytes | (L_.tileTab[ti].cBytes << 16);
+            m[2] = h.nTets | (h.nLocal << 16);
+            for (uint32_t g = 0; g < (uint32_t)TILE_NGROUPS; ++g) {
+                uint32_t gt = 0;
+                if (g < h.nGroups) std::memcpy(&gt, rec + 32 + 4 * g, 4);          // rowBase | nRows << 16
+                const uint32_t nValid = (g < h.nGroups) ? std::min<uint32_t>((uint32_t)TILE_GROUP, h.nLocal - g * (uint32_t)TILE_GROUP) : 0u;
+                m[4 + g] = (gt & 63u) | ((gt >> 16) << 6) | (nValid << 12) | (g < 8u ? (h.nTets << 18) : 0u);
+            }
+        }
+        CUDA_CHECK(cudaMemcpy(d.tileTab, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
+    }
     CUDA_CHECK(cudaMemcpy(d.vslotPtr, L_.vslotPtr.data(), L_.vslotPtr.size() * 4, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(d.vslot, L_.vslot.data(), L_.vslot.size() * 4, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(d.vlist, L_.vlist.data(), L_.vlist.size() * 4, cudaMemcpyHostToDevice));
@@ -289,7 +308,8 @@ void Engine::prepare()
         TileHeader h; std::memcpy(&h, rec, sizeof(h));
         const uint32_t* vlist = L_.vlist.data() + h.slotBase;
         for (uint32_t t = 0; t < h.nTets; ++t) {
-            const float* B = reinterpret_cast<const float*>(rec + TILE_OFF_TETS + 48 * (size_t)t);
+            float B[12];
+            for (uint32_t j = 0; j < 12; ++j) std::memcpy(&B[j], rec + tile_tet_word(h.nTets, t, j), 4);
             const float w = B[9];
             uint32_t cw[2]; std::memcpy(cw, B + 10, 8);
             const uint32_t loc[4] = {(cw[0] >> 4) & 0xffu, (cw[0] >> 20) & 0xffu, (cw[1] >> 4) & 0xffu, (cw[1] >> 20) & 0xffu};
@@ -656,7 +676,8 @@ void Engine::prepareSolver()
             const uint8_t* rec = L_.records.data() + L_.tileRecOff[ti];
             TileHeader h; std::memcpy(&h, rec, sizeof(h));
             for (uint32_t k = 0; k < h.nTets; ++k, ++t) {
-                const float* B = reinterpret_cast<const float*>(rec + TILE_OFF_TETS + 48 * (size_t)k);
+                float B[12];
+                for (uint32_t j = 0; j < 12; ++j) std::memcpy(&B[j], rec + tile_tet_word(h.nTets, k, j), 4);
                 std::memcpy(&Br[9 * t], B, 36);
                 wr[t] = B[9];
             }

@@ -31,14 +31,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+{   // bounded: a bulk copy that never arrives (a bug, not a load condition) traps instead of hanging the GPU
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (spins > (1u << 24)) __trap();
+    }
 }
 // one bulk asynchronous copy global -> shared, completion counted in bytes on the mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
@@ -174,63 +175,88 @@ __global__ void k_predict(int nV, const float4* __restrict__ X, const float4* __
 
 // ------------------------------------------------------------------ local step (the hot kernel)
 // PdUtil::addM_h2Sn + computeLocal (pdUtil.cu:97-145,168-179), one tile of <= TILE_T tets per
-// iteration of a persistent CTA (4 CTAs per SM).  Per tile:
-//   0. two bulk asynchronous copies (TMA, cp.async.bulk + mbarrier, L2 evict_first) land the packed
-//      tile record in shared memory: part AB (tet records; double buffered, fetched two tiles ahead)
-//      and part C (transposed incidence rows; fetched while phase B runs);
+// iteration of a persistent CTA (4 CTAs per SM).  v7: ONE __syncthreads per tile.  Per tile:
 //   A. the tile's distinct vertex positions are gathered into shared memory by 16-byte cp.async
-//      (LDGSTS) into a DOUBLE-BUFFERED staging area, issued a whole tile ahead (before phase B of the
-//      previous tile), so the random-access latency hides behind a full phase B + phase C; the vertex
-//      ids come from the global slot-indexed vlist, read (coalesced) one more tile ahead into a register;
-//   B. one tet per thread: 3 x LDS.128 (48-byte record: DmInv, w, corner offsets; the 48-byte
-//      stride is bank-conflict free), 4 x LDS.128 positions, F = Ds*DmInv, rotation,
-//      H = w (R - F) DmInv^T G (or w R DmInv^T G), 4 x STS.128 into the H scratch;
-//   C. (deferred into the next iteration) one tile-local vertex per thread, 32 vertices of similar
-//      incidence count per warp: ordered sum over the vertex's incidence list (one conflict-free LDS.32
-//      yields two ready-made byte offsets into the H scratch) -> ONE partial sum per (tile, vertex)
-//      slot.  The vertex's first (owner) slot starts from b0 = (M/h^2) s_old, so a vertex whose tets
-//      all sit in one tile gets exactly the reference's sequential  b = c*s; b += h1; b += h2; ...
+//      (LDGSTS) into a DOUBLE-BUFFERED staging area, issued more than a whole tile ahead (right after
+//      the barrier of tile it-2); the vertex ids come from the global slot-indexed vlist, read
+//      (coalesced) one more tile ahead into a register;
+//   B. one tet per thread.  The 48-byte record (DmInv, w, corner words) is stored as three 16-byte
+//      planes per tile and comes STRAIGHT FROM GLOBAL MEMORY into registers with three fully
+//      coalesced LDG.128 (L2 evict_first), issued at the end of phase B of the previous tile so that
+//      the latency hides behind that tile's phase C; the producer thread keeps the stream two tiles
+//      ahead in L2 with one bulk prefetch per tile.  4 x LDS.128 positions, F = Ds*DmInv, rotation,
+//      H = w (R - F) DmInv^T G (or w R DmInv^T G), 4 x STS.128 into this tile's H scratch (double
+//      buffered: fast warps run ahead into the next tile while slow ones still sum the previous one);
+//   -- barrier: H scratch complete, next tile's positions staged --
+//   C. one tile-local vertex per thread, 32 vertices of similar incidence count per warp: ordered sum
+//      over the vertex's incidence list (transposed rows, moved in by ONE bulk copy per tile (TMA,
+//      cp.async.bulk + mbarrier, double buffered, requested a whole tile ahead); one conflict-free
+//      LDS.32 yields two ready-made byte offsets into the H scratch) -> ONE partial sum per (tile,
+//      vertex) slot.  Faithful mode: the vertex's first (owner) slot starts from b0 = (M/h^2) s_old, so
+//      a vertex whose tets all sit in one tile gets exactly the reference's sequential
+//      b = c*s; b += h1; b += h2; ...
 // No atomics anywhere: the reference's 12 float atomicAdds per tet become ordered sums, so results
-// are run-to-run bit-identical.  Two __syncthreads per tile.
-// F and H are written with the fused/rounded operation pattern nvcc gives the reference's glm
-// expressions (see oracle/pd_oracle.c header), so that with ROT_MODE 1 every tet contribution is
-// bit-identical to the reference kernel's.
-constexpr uint32_t LOCAL_OFF_C = 2u * TILE_ABMAX;
-constexpr uint32_t LOCAL_OFF_QS = LOCAL_OFF_C + TILE_CMAX;
+// are run-to-run bit-identical.
+// F and H of the scalar path are written with the fused/rounded operation pattern nvcc gives the
+// reference's glm expressions (see oracle/pd_oracle.c header), so that with ROT_MODE 1 every tet
+// contribution is bit-identical to the reference kernel's.
 constexpr uint32_t LOCAL_QS_BYTES = 16u * TILE_NLMAX;
+constexpr uint32_t LOCAL_HS_BYTES = TILE_ZERO_OFF + 128u;      // four corner planes + eight zero slots, one per column
+constexpr uint32_t LOCAL_OFF_QS = 0u;
 constexpr uint32_t LOCAL_OFF_HS = LOCAL_OFF_QS + 2u * LOCAL_QS_BYTES;
-constexpr uint32_t LOCAL_OFF_BAR = LOCAL_OFF_HS + TILE_ZERO_OFF + 128u;    // eight zero slots, one per column
-constexpr uint32_t LOCAL_OFF_TE = LOCAL_OFF_BAR + 32u;      // producer: two prefetched tile-table entries (tile parity)
-constexpr uint32_t LOCAL_SMEM_BYTES = LOCAL_OFF_TE + 32u;
+constexpr uint32_t LOCAL_OFF_C = LOCAL_OFF_HS + 2u * LOCAL_HS_BYTES;
+constexpr uint32_t LOCAL_OFF_BAR = LOCAL_OFF_C + 2u * TILE_CMAX;
+constexpr uint32_t LOCAL_SMEM_BYTES = LOCAL_OFF_BAR + 16u;
 static_assert(4u * (LOCAL_SMEM_BYTES + 1024u) <= 233472u, "4 CTAs of the local kernel must fit one SM's shared memory");
 static_assert(TILE_NLMAX == TILE_T, "one tile-local vertex per thread");
+// per-tile entry of the device tile table: record offset / 16, part AB bytes | part C bytes << 16, tet count | vertex
+// count << 16, spare, then one word per vertex group (warp w sums group w -- word 4 + w -- and, with 16-vertex groups,
+// w + 8): rowBase | nRows << 6 | vertices in the group << 12, and in the first eight also the tile's tet count << 18
+constexpr int TILE_META_WORDS = 4 + TILE_NGROUPS;
 
 __device__ __forceinline__ float dot3_nv(float a0, float b0, float a1, float b1, float a2, float b2)
 {   // a0*b0 + a1*b1 + a2*b2 as nvcc contracts the reference's glm products
     return __fmaf_rn(a2, b2, __fmaf_rn(a0, b0, __fmul_rn(a1, b1)));
 }
-
-// phase C of one tile: `ve` = this thread's vlist entry (0xffffffff if it has no vertex), gt = this
-// warp's group-table word, slot0 = the tile's first slot.
-// FAITHFUL: b = b0; b += h_1; b += h_2; ... strictly in (tet, corner) order, the vertex's first (owner) slot
-// starting from b0 = (M/h^2) s_old -- the reference's sequential sum for a vertex whose tets share a tile.
-// Otherwise (product default) the slot holds the elastic terms only (the vertex kernel adds b0), summed in
-// a different FIXED order without a long dependency chain: four rows per trip, their entries prefetched a
-// trip ahead, eight gathered LDS.128 in flight, even and odd list entries accumulated separately.  Rows
-// past the group's count read the zero slot.
-template <bool FAITHFUL>
-__device__ __forceinline__ void local_phase_c(const uint8_t* smem, uint32_t ve, uint32_t gt, uint32_t slot0, int tid,
-                                              const float4* __restrict__ b0, float4* __restrict__ P)
+__device__ __forceinline__ float4 ldg_stream(const void* p)
+{   // read-once stream: no L1 allocation, L2 evict_first
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(L2_EVICT_FIRST));
+    return v;
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes)
 {
-    const uint32_t* row = reinterpret_cast<const uint32_t*>(smem + LOCAL_OFF_C) + (gt & 0xffffu) * 32u + (tid & 31);
-    const uint32_t nR = gt >> 16;
-    const uint8_t* Hb = smem + LOCAL_OFF_HS;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// phase C of one vertex group of a tile, by one warp: Cb = the tile's incidence rows, Hb = its H scratch, gw = the
+// group's tile-table word, slotG = the group's first slot.  32-vertex groups: one lane per vertex.  16-vertex groups:
+// vertex i is summed by lanes i (entries 4r, 4r+1 of its list in row r) and i + 16 (entries 4r+2, 4r+3), combined by
+// one shuffle.
+// FAITHFUL: b = b0; b += h_1; b += h_2; ... strictly in (tet, corner) order (a second lane hands its entries over by
+// shuffle), the vertex's first (owner) slot starting from b0 = (M/h^2) s_old -- the reference's sequential sum for a
+// vertex whose tets share a tile.  Otherwise (product default) the slot holds the elastic terms only (the vertex
+// kernel adds b0), summed in a different FIXED order without a long dependency chain: two rows per trip, their
+// entries prefetched a trip ahead, four gathered LDS.128 in flight, the two entries of a lane accumulated separately
+// ((x, y) as one packed FADD2).  A row past the group's count reads the zero slot.
+template <bool FAITHFUL>
+__device__ __forceinline__ void local_phase_c(const uint8_t* Cb, const uint8_t* Hb, uint32_t gw, uint32_t slotG, int lane,
+                                              const uint32_t* __restrict__ vlist, const float4* __restrict__ b0, float4* __restrict__ P)
+{
+    const uint32_t nR = (gw >> 6) & 63u;
+    if (nR == 0u) return;                                     // warp-uniform: no such group in this tile
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(Cb) + (gw & 63u) * 32u + lane;
+    const bool writer = (uint32_t)lane < ((gw >> 12) & 63u);
     float sx, sy, sz;
     if (FAITHFUL) {
         sx = sy = sz = 0.f;
-        if (ve != 0xffffffffu && (ve & TILE_OWNER_BIT)) {
-            const float4 bb = ldg_hint(&b0[ve & ~TILE_OWNER_BIT], L2_EVICT_LAST);
-            sx = bb.x; sy = bb.y; sz = bb.z;
+        if (writer) {
+            const uint32_t ve = __ldg(&vlist[slotG + lane]);
+            if (ve & TILE_OWNER_BIT) {
+                const float4 bb = ldg_hint(&b0[ve & ~TILE_OWNER_BIT], L2_EVICT_LAST);
+                sx = bb.x; sy = bb.y; sz = bb.z;
+            }
         }
         for (uint32_t r = 0; r < nR; ++r) {
             const uint32_t e2 = row[32u * r];
@@ -238,171 +264,99 @@ __device__ __forceinline__ void local_phase_c(const uint8_t* smem, uint32_t ve, 
             const float4 hb = *reinterpret_cast<const float4*>(Hb + (e2 >> 16));
             sx = __fadd_rn(sx, ha.x); sy = __fadd_rn(sy, ha.y); sz = __fadd_rn(sz, ha.z);
             sx = __fadd_rn(sx, hb.x); sy = __fadd_rn(sy, hb.y); sz = __fadd_rn(sz, hb.z);
+            if (TILE_LPV == 2) {
+                sx = __fadd_rn(sx, __shfl_down_sync(0xffffffffu, ha.x, 16)); sy = __fadd_rn(sy, __shfl_down_sync(0xffffffffu, ha.y, 16)); sz = __fadd_rn(sz, __shfl_down_sync(0xffffffffu, ha.z, 16));
+                sx = __fadd_rn(sx, __shfl_down_sync(0xffffffffu, hb.x, 16)); sy = __fadd_rn(sy, __shfl_down_sync(0xffffffffu, hb.y, 16)); sz = __fadd_rn(sz, __shfl_down_sync(0xffffffffu, hb.z, 16));
+            }
         }
     } else {
         constexpr uint32_t ZZ = TILE_ZERO_OFF | (TILE_ZERO_OFF << 16);
-        float ax = 0.f, ay = 0.f, az = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
-        uint32_t e0 = (0u < nR) ? row[0] : ZZ, e1 = (1u < nR) ? row[32] : ZZ, e2 = (2u < nR) ? row[64] : ZZ, e3 = (3u < nR) ? row[96] : ZZ;
-        for (uint32_t r = 0; r < nR; r += 4) {
+        // (x, y) of every entry is added as one packed FADD2 (rotation.cuh), z as a scalar
+        float2 axy = make_float2(0.f, 0.f), cxy = make_float2(0.f, 0.f);
+        float az = 0.f, cz = 0.f;
+        uint32_t e0 = row[0], e1 = (1u < nR) ? row[32] : ZZ;
+#pragma unroll 1
+        for (uint32_t r = 0; r < nR; r += 2) {
             const float4 h0 = *reinterpret_cast<const float4*>(Hb + (e0 & 0xffffu));
             const float4 h1 = *reinterpret_cast<const float4*>(Hb + (e0 >> 16));
             const float4 h2 = *reinterpret_cast<const float4*>(Hb + (e1 & 0xffffu));
             const float4 h3 = *reinterpret_cast<const float4*>(Hb + (e1 >> 16));
-            const float4 h4 = *reinterpret_cast<const float4*>(Hb + (e2 & 0xffffu));
-            const float4 h5 = *reinterpret_cast<const float4*>(Hb + (e2 >> 16));
-            const float4 h6 = *reinterpret_cast<const float4*>(Hb + (e3 & 0xffffu));
-            const float4 h7 = *reinterpret_cast<const float4*>(Hb + (e3 >> 16));
-            const uint32_t* nx = row + 32u * (r + 4u);
-            e0 = (r + 4u < nR) ? nx[0] : ZZ; e1 = (r + 5u < nR) ? nx[32] : ZZ; e2 = (r + 6u < nR) ? nx[64] : ZZ; e3 = (r + 7u < nR) ? nx[96] : ZZ;
-            ax = __fadd_rn(ax, h0.x); ay = __fadd_rn(ay, h0.y); az = __fadd_rn(az, h0.z);
-            cx = __fadd_rn(cx, h1.x); cy = __fadd_rn(cy, h1.y); cz = __fadd_rn(cz, h1.z);
-            ax = __fadd_rn(ax, h2.x); ay = __fadd_rn(ay, h2.y); az = __fadd_rn(az, h2.z);
-            cx = __fadd_rn(cx, h3.x); cy = __fadd_rn(cy, h3.y); cz = __fadd_rn(cz, h3.z);
-            ax = __fadd_rn(ax, h4.x); ay = __fadd_rn(ay, h4.y); az = __fadd_rn(az, h4.z);
-            cx = __fadd_rn(cx, h5.x); cy = __fadd_rn(cy, h5.y); cz = __fadd_rn(cz, h5.z);
-            ax = __fadd_rn(ax, h6.x); ay = __fadd_rn(ay, h6.y); az = __fadd_rn(az, h6.z);
-            cx = __fadd_rn(cx, h7.x); cy = __fadd_rn(cy, h7.y); cz = __fadd_rn(cz, h7.z);
+            const uint32_t* nx = row + 32u * (r + 2u);
+            e0 = (r + 2u < nR) ? nx[0] : ZZ; e1 = (r + 3u < nR) ? nx[32] : ZZ;
+            axy = f2add(axy, make_float2(h0.x, h0.y)); az = __fadd_rn(az, h0.z);
+            cxy = f2add(cxy, make_float2(h1.x, h1.y)); cz = __fadd_rn(cz, h1.z);
+            axy = f2add(axy, make_float2(h2.x, h2.y)); az = __fadd_rn(az, h2.z);
+            cxy = f2add(cxy, make_float2(h3.x, h3.y)); cz = __fadd_rn(cz, h3.z);
         }
-        sx = __fadd_rn(ax, cx); sy = __fadd_rn(ay, cy); sz = __fadd_rn(az, cz);
+        const float2 sxy = f2add(axy, cxy);
+        sx = sxy.x; sy = sxy.y; sz = __fadd_rn(az, cz);
+        if (TILE_LPV == 2) {
+            sx = __fadd_rn(sx, __shfl_down_sync(0xffffffffu, sx, 16));
+            sy = __fadd_rn(sy, __shfl_down_sync(0xffffffffu, sy, 16));
+            sz = __fadd_rn(sz, __shfl_down_sync(0xffffffffu, sz, 16));
+        }
     }
-    if (ve != 0xffffffffu) P[slot0 + tid] = make_float4(sx, sy, sz, 0.f);
+    if (writer) P[slotG + lane] = make_float4(sx, sy, sz, 0.f);
 }
 
-template <int ROT_MODE, bool JACOBI, bool PROF = false>
-__global__ void __launch_bounds__(TILE_T, 4)
-k_local(const uint8_t* __restrict__ records, const uint4* __restrict__ tileTab, int nTiles,
-        const uint32_t* __restrict__ vlist, const float4* __restrict__ q, const float4* __restrict__ b0, float4* __restrict__ P,
-        unsigned long long* __restrict__ prof, DistWait dw)
+// phase B of one tet: record (r0, r1, r2) in registers, positions from the staging buffer qsb, the four corner
+// contributions into the quarter-warp's H scratch line
+template <int ROT_MODE, bool JACOBI>
+__device__ __forceinline__ void local_phase_b(const float4 r0, const float4 r1, const float4 r2, const uint8_t* qsb, uint8_t* Hline)
 {
-    // prof (may be null): per-phase clock64 totals of warp 0 of every CTA, 8 counters per CTA (scripts/phase_profile.py)
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + LOCAL_OFF_BAR);   // [0],[1]: part AB buffers, [2]: part C
-    const int tid = threadIdx.x;
-    const int nIt = ((int)blockIdx.x < nTiles) ? (nTiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    if (nIt == 0) return;
-
-    if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        mbar_init(&bar[2], 1);
-        fence_barrier_init();
-        fence_proxy_async();
-    }
-    if (tid < 8) *reinterpret_cast<float4*>(smem + LOCAL_OFF_HS + TILE_ZERO_OFF + 16 * tid) = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    // multi-GPU: the rank's interior tiles come first; the neighbours' ghost positions are needed -- and waited
-    // for -- only before the position gather of the first boundary tile, so the exchange hides behind the interior
-    bool needHalo = dw.nNbr > 0;
-    auto halo_before = [&](int k) {
-        if (needHalo && (int)(blockIdx.x + k * gridDim.x) >= dw.firstTile) { dist_wait(dw, tid); needHalo = false; }
-    };
-
-    // producer (thread 0): part AB of the tile whose table entry is `te` -> buffer k & 1
-    auto fetch_ab = [&](int k, uint4 te) {
-        mbar_expect_tx(&bar[k & 1], te.z);
-        bulk_g2s_hint(smem + (k & 1) * TILE_ABMAX, records + (((unsigned long long)te.y << 32) | te.x), te.z, &bar[k & 1], L2_EVICT_FIRST);
-    };
-    auto tile_entry = [&](int k) -> uint4 { return __ldg(&tileTab[blockIdx.x + k * gridDim.x]); };
-    // this thread's entry of the padded, slot-indexed vertex list of tile number k of this CTA
-    auto load_ve = [&](int k) -> uint32_t { return __ldg(&vlist[(blockIdx.x + k * gridDim.x) * (unsigned)TILE_NLMAX + tid]); };
-    // asynchronous gather of this thread's vertex into the staging buffers, alternating.  The two
-    // destinations live in per-thread registers that swap every tile: when ptxas 12.9 folds a uniform-register
-    // buffer offset into an LDGSTS that also carries a cache-hint descriptor it emits an encoding the B200
-    // rejects ("illegal instruction")
-    uint32_t gdst = smem_u32(smem + LOCAL_OFF_QS + 16 * tid);
-    uint32_t gdstOther = gdst + LOCAL_QS_BYTES;
-    auto gather = [&](uint32_t ve) {
-        if (ve != 0xffffffffu) {
-            cp_async16_hint(gdst, &q[ve & ~TILE_OWNER_BIT], L2_EVICT_LAST);
-            if (ROT_MODE == 1 && (ve & TILE_OWNER_BIT)) prefetch_l2(&b0[ve & ~TILE_OWNER_BIT]);
+        const float B0 = r0.x, B1 = r0.y, B2 = r0.z, B3 = r0.w, B4 = r1.x, B5 = r1.y, B6 = r1.z, B7 = r1.w, B8 = r2.x;
+        const float w = r2.y;
+        const uint32_t c01 = __float_as_uint(r2.z), c23 = __float_as_uint(r2.w);
+        const float4 p0 = *reinterpret_cast<const float4*>(qsb + (c01 & 0x0ff0u));
+        const float4 p1 = *reinterpret_cast<const float4*>(qsb + ((c01 >> 16) & 0x0ff0u));
+        const float4 p2 = *reinterpret_cast<const float4*>(qsb + (c23 & 0x0ff0u));
+        const float4 p3 = *reinterpret_cast<const float4*>(qsb + ((c23 >> 16) & 0x0ff0u));
+        float4 h0, h1, h2, h3;
+        bool done = false;
+        if (ROT_MODE == 0) {
+            // product default: packed FP32 (FFMA2) on matrix columns, rotation.cuh.  Edge k = p_{k+1} - p_0 is
+            // column k of Ds; column c of F = sum_k edge_k B[k][c]
+            const float2 p0xy = make_float2(p0.x, p0.y);
+            Col3 e0, e1, e2;
+            e0.xy = f2sub(make_float2(p1.x, p1.y), p0xy); e0.z = p1.z - p0.z;
+            e1.xy = f2sub(make_float2(p2.x, p2.y), p0xy); e1.z = p2.z - p0.z;
+            e2.xy = f2sub(make_float2(p3.x, p3.y), p0xy); e2.z = p3.z - p0.z;
+            Col3 f0, f1, f2;
+            f0.xy = f2fma(e2.xy, bc2(B6), f2fma(e0.xy, bc2(B0), f2mul(e1.xy, bc2(B3)))); f0.z = fmaf(e2.z, B6, fmaf(e0.z, B0, e1.z * B3));
+            f1.xy = f2fma(e2.xy, bc2(B7), f2fma(e0.xy, bc2(B1), f2mul(e1.xy, bc2(B4)))); f1.z = fmaf(e2.z, B7, fmaf(e0.z, B1, e1.z * B4));
+            f2.xy = f2fma(e2.xy, bc2(B8), f2fma(e0.xy, bc2(B2), f2mul(e1.xy, bc2(B5)))); f2.z = fmaf(e2.z, B8, fmaf(e0.z, B2, e1.z * B5));
+            Col3 y0, y1, y2;
+            if (rotation_newton2_packed(f0, f1, f2, y0, y1, y2)) {
+                // M = w (R - F) = (w/4) Y - w F   (or w R), column k
+                const float w4 = 0.25f * w;
+                Col3 m0, m1, m2;
+                if (JACOBI) {
+                    m0.xy = f2fma(y0.xy, bc2(w4), f2mul(f0.xy, bc2(-w))); m0.z = fmaf(y0.z, w4, f0.z * -w);
+                    m1.xy = f2fma(y1.xy, bc2(w4), f2mul(f1.xy, bc2(-w))); m1.z = fmaf(y1.z, w4, f1.z * -w);
+                    m2.xy = f2fma(y2.xy, bc2(w4), f2mul(f2.xy, bc2(-w))); m2.z = fmaf(y2.z, w4, f2.z * -w);
+                } else {
+                    m0.xy = f2mul(y0.xy, bc2(w4)); m0.z = y0.z * w4;
+                    m1.xy = f2mul(y1.xy, bc2(w4)); m1.z = y1.z * w4;
+                    m2.xy = f2mul(y2.xy, bc2(w4)); m2.z = y2.z * w4;
+                }
+                // H = M DmInv^T: column j (vertex j+1) = sum_k M_k B[j][k]; vertex 0: -(sum of the columns)
+                const float2 a1 = f2fma(m2.xy, bc2(B2), f2fma(m0.xy, bc2(B0), f2mul(m1.xy, bc2(B1))));
+                const float2 a2 = f2fma(m2.xy, bc2(B5), f2fma(m0.xy, bc2(B3), f2mul(m1.xy, bc2(B4))));
+                const float2 a3 = f2fma(m2.xy, bc2(B8), f2fma(m0.xy, bc2(B6), f2mul(m1.xy, bc2(B7))));
+                const float z1 = fmaf(m2.z, B2, fmaf(m0.z, B0, m1.z * B1));
+                const float z2 = fmaf(m2.z, B5, fmaf(m0.z, B3, m1.z * B4));
+                const float z3 = fmaf(m2.z, B8, fmaf(m0.z, B6, m1.z * B7));
+                const float2 a0 = f2sub(f2sub(make_float2(-a1.x, -a1.y), a2), a3);
+                h0 = make_float4(a0.x, a0.y, (-z1 - z2) - z3, 0.f);
+                h1 = make_float4(a1.x, a1.y, z1, 0.f);
+                h2 = make_float4(a2.x, a2.y, z2, 0.f);
+                h3 = make_float4(a3.x, a3.y, z3, 0.f);
+                done = true;
+            }
         }
-        cp_async_commit();
-        const uint32_t t = gdst; gdst = gdstOther; gdstOther = t;
-    };
-
-    // the producer (TMA issue) is lane 0 of the LAST warp: the tile-local vertices are sorted by incidence
-    // count, so warp 0 carries the longest phase C and the last warp the shortest (usually none at all)
-    const bool producer = tid == TILE_T - 32;
-    // its table entries arrive by 16-byte cp.async in the same groups as the position gathers (no registers held):
-    // the entry of tile k is requested at the top of iteration k-3 and read after barrier 2 of iteration k-2
-    auto prefetch_entry = [&](int k) {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem + LOCAL_OFF_TE + 16 * (k & 1))),
-                     "l"(&tileTab[blockIdx.x + k * gridDim.x]) : "memory");
-    };
-    if (producer) {
-        fetch_ab(0, tile_entry(0));
-        if (nIt > 1) fetch_ab(1, tile_entry(1));
-        if (nIt > 2) prefetch_entry(2);
-    }
-    uint32_t veCur = load_ve(0);                             // vlist entry of this thread: tile it
-    // everything above touches only the immutable tile stream; from here on the kernel reads positions written by
-    // the previous launch in the stream (and later overwrites the slots that launch reads)
-    pdl_launch_dependents();
-    pdl_wait();
-    halo_before(0);
-    gather(veCur);
-    uint32_t veNext = (nIt > 1) ? load_ve(1) : 0xffffffffu;  // tile it + 1
-    uint32_t vePrev = 0xffffffffu, gtPrev = 0;
-    // H scratch line of this thread's quarter-warp (corner k adds k * TILE_HSTRIDE, the record's column adds 16 * col)
-    uint8_t* const Hline = smem + LOCAL_OFF_HS + 16 * (tid & ~7);
-
-    long long tk = 0, acc[7] = {0, 0, 0, 0, 0, 0, 0};
-#define PD_TICK(i) if (PROF) { const long long now = clock64(); acc[i] += now - tk; tk = now; }
-    if (PROF) tk = clock64();
-    for (int it = 0; it < nIt; ++it) {
-        const int b = it & 1;
-        const uint8_t* rec = smem + b * TILE_ABMAX;
-        // a whole tile ahead: start the position gather of tile it+1 (its staging buffer was last read in
-        // phase B of tile it-1) and fetch the vertex ids of tile it+2
-        if (producer && it + 3 < nIt) prefetch_entry(it + 3);
-        if (it + 1 < nIt) halo_before(it + 1);
-        gather(veNext);
-        const uint32_t veNext2 = (it + 2 < nIt) ? load_ve(it + 2) : 0xffffffffu;
-        PD_TICK(0)
-        // deferred phase C of the previous tile
-        if (it > 0) {
-            mbar_wait(&bar[2], (uint32_t)((it - 1) & 1));
-            PD_TICK(1)
-            local_phase_c<ROT_MODE == 1>(smem, vePrev, gtPrev, (blockIdx.x + (it - 1) * gridDim.x) * (unsigned)TILE_NLMAX, tid, b0, P);
-        }
-        PD_TICK(2)
-        cp_async_wait_1();     // this thread's gather of tile `it` has landed (the one just issued may be in flight)
-        __syncthreads();       // positions staged; every warp is past phase C of the previous tile
-        PD_TICK(3)
-        mbar_wait(&bar[b], (uint32_t)((it >> 1) & 1));
-        PD_TICK(4)
-        const uint4 hdr = *reinterpret_cast<const uint4*>(rec);      // nTets, nLocal, slotBase, abBytes
-        if (producer) {        // the part C buffer is free now: stream this tile's incidence rows in
-            const uint4 h2 = *reinterpret_cast<const uint4*>(rec + 16);      // cBytes, nGroups, offLo, offHi
-            mbar_expect_tx(&bar[2], h2.x);
-            bulk_g2s_hint(smem + LOCAL_OFF_C, records + ((((unsigned long long)h2.w << 32) | h2.z) + hdr.w), h2.x, &bar[2], L2_EVICT_FIRST);
-        }
-        // context of this tile's (deferred) phase C
-        vePrev = veCur; veCur = veNext; veNext = veNext2;
-        gtPrev = *reinterpret_cast<const uint32_t*>(rec + 32 + 4 * (tid >> 5));
-
-        // phase B, part 1: this thread's tet record and corner positions -> registers
-        const bool active = (uint32_t)tid < hdr.x;
-        float4 r0, r1, r2;
-        if (active) {
-            const float4* tr = reinterpret_cast<const float4*>(rec + TILE_OFF_TETS + 48 * tid);
-            r0 = tr[0]; r1 = tr[1]; r2 = tr[2];
-        }
-        __syncthreads();       // every record of this AB buffer is in registers: refill it now, two tiles ahead
-        if (producer && it + 2 < nIt) fetch_ab(it + 2, *reinterpret_cast<const uint4*>(smem + LOCAL_OFF_TE + 16 * (it & 1)));
-
-        PD_TICK(5)
-        // phase B, part 2: one tet per thread
-        if (active) {
-            const float B0 = r0.x, B1 = r0.y, B2 = r0.z, B3 = r0.w, B4 = r1.x, B5 = r1.y, B6 = r1.z, B7 = r1.w, B8 = r2.x;
-            const float w = r2.y;
-            const uint32_t c01 = __float_as_uint(r2.z), c23 = __float_as_uint(r2.w);
-            const uint8_t* qsb = smem + LOCAL_OFF_QS + b * LOCAL_QS_BYTES;
-            const float4 p0 = *reinterpret_cast<const float4*>(qsb + (c01 & 0x0ff0u));
-            const float4 p1 = *reinterpret_cast<const float4*>(qsb + ((c01 >> 16) & 0x0ff0u));
-            const float4 p2 = *reinterpret_cast<const float4*>(qsb + (c23 & 0x0ff0u));
-            const float4 p3 = *reinterpret_cast<const float4*>(qsb + ((c23 >> 16) & 0x0ff0u));
-            // Ds columns = edges; F = Ds * DmInv  (row-major F[r][c] = sum_k Ds[r][k] B[k][c])
+        if (!done) {
+            // faithful mode, and the default mode's rare inverted / flat / strongly deformed tets: scalar path in
+            // the reference's operation order.  Ds columns = edges; F = Ds * DmInv  (row-major F[r][c] = sum_k Ds[r][k] B[k][c])
             const float d00 = p1.x - p0.x, d01 = p2.x - p0.x, d02 = p3.x - p0.x;
             const float d10 = p1.y - p0.y, d11 = p2.y - p0.y, d12 = p3.y - p0.y;
             const float d20 = p1.z - p0.z, d21 = p2.z - p0.z, d22 = p3.z - p0.z;
@@ -415,7 +369,6 @@ k_local(const uint8_t* __restrict__ records, const uint4* __restrict__ tileTab, 
 #pragma unroll
             for (int e = 0; e < 9; ++e) M[e] = __fmul_rn(w, JACOBI ? __fsub_rn(R.m[e], F.m[e]) : R.m[e]);
             // H = M * DmInv^T ; column j (vertex j+1): H[r][j] = sum_k M[r][k] B[j][k] ; vertex 0: -(sum of columns)
-            float4 h0, h1, h2, h3;
             h1.x = dot3_nv(M[0], B0, M[1], B1, M[2], B2); h2.x = dot3_nv(M[0], B3, M[1], B4, M[2], B5); h3.x = dot3_nv(M[0], B6, M[1], B7, M[2], B8);
             h1.y = dot3_nv(M[3], B0, M[4], B1, M[5], B2); h2.y = dot3_nv(M[3], B3, M[4], B4, M[5], B5); h3.y = dot3_nv(M[3], B6, M[4], B7, M[5], B8);
             h1.z = dot3_nv(M[6], B0, M[7], B1, M[8], B2); h2.z = dot3_nv(M[6], B3, M[7], B4, M[8], B5); h3.z = dot3_nv(M[6], B6, M[7], B7, M[8], B8);
@@ -423,15 +376,141 @@ k_local(const uint8_t* __restrict__ records, const uint4* __restrict__ tileTab, 
             h0.y = __fsub_rn(__fsub_rn(-h1.y, h2.y), h3.y);
             h0.z = __fsub_rn(__fsub_rn(-h1.z, h2.z), h3.z);
             h0.w = h1.w = h2.w = h3.w = 0.f;
-            // conflict-free columns from the layout's 8-colouring (layout.cpp:color_tile): col * 16 = (word >> 8) & 0x70
-            *reinterpret_cast<float4*>(Hline + ((c01 >> 8) & 0x70u)) = h0;
-            *reinterpret_cast<float4*>(Hline + TILE_HSTRIDE + ((c01 >> 24) & 0x70u)) = h1;
-            *reinterpret_cast<float4*>(Hline + 2 * TILE_HSTRIDE + ((c23 >> 8) & 0x70u)) = h2;
-            *reinterpret_cast<float4*>(Hline + 3 * TILE_HSTRIDE + ((c23 >> 24) & 0x70u)) = h3;
         }
-        if (PROF) { const long long now = clock64(); acc[6] += now - tk; tk = now; }     // math + H stores of this warp
-        __syncthreads();   // H scratch complete; this staging buffer is free
-        if (PROF) { const long long now = clock64(); acc[0] += now - tk; tk = now; }     // barrier 3 -> counted with the loop top
+        // conflict-free columns from the layout's 8-colouring (layout.cpp:color_tile): col * 16 = (word >> 8) & 0x70
+        *reinterpret_cast<float4*>(Hline + ((c01 >> 8) & 0x70u)) = h0;
+        *reinterpret_cast<float4*>(Hline + TILE_HSTRIDE + ((c01 >> 24) & 0x70u)) = h1;
+        *reinterpret_cast<float4*>(Hline + 2 * TILE_HSTRIDE + ((c23 >> 8) & 0x70u)) = h2;
+        *reinterpret_cast<float4*>(Hline + 3 * TILE_HSTRIDE + ((c23 >> 24) & 0x70u)) = h3;
+}
+
+template <int ROT_MODE, bool JACOBI, bool PROF = false>
+__global__ void __launch_bounds__(TILE_T, 4)
+k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMeta, int nTiles,
+        const uint32_t* __restrict__ vlist, const float4* __restrict__ q, const float4* __restrict__ b0, float4* __restrict__ P,
+        unsigned long long* __restrict__ prof, DistWait dw)
+{
+    // prof (may be null): per-phase clock64 totals of warp 0 of every CTA, 8 counters per CTA (scripts/phase_profile.py)
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* cbar = reinterpret_cast<uint64_t*>(smem + LOCAL_OFF_BAR);   // part C buffers 0, 1
+    const int tid = threadIdx.x;
+    const int nIt = ((int)blockIdx.x < nTiles) ? (nTiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    if (nIt == 0) return;
+
+    if (tid == 0) {
+        mbar_init(&cbar[0], 1);
+        mbar_init(&cbar[1], 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (tid < 16) *reinterpret_cast<float4*>(smem + LOCAL_OFF_HS + (tid >> 3) * LOCAL_HS_BYTES + TILE_ZERO_OFF + 16 * (tid & 7)) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    // multi-GPU: the rank's interior tiles come first; the neighbours' ghost positions are needed -- and waited
+    // for -- only before the position gather of the first boundary tile, so the exchange hides behind the interior
+    bool needHalo = dw.nNbr > 0;
+    auto halo_before = [&](int k) {
+        if (needHalo && (int)(blockIdx.x + k * gridDim.x) >= dw.firstTile) { dist_wait(dw, tid); needHalo = false; }
+    };
+    auto meta_of = [&](int k) -> const uint32_t* { return tileMeta + (size_t)(blockIdx.x + k * gridDim.x) * TILE_META_WORDS; };
+    const int warp = tid >> 5, lane = tid & 31;
+    // this thread's entry of the padded, slot-indexed vertex list of tile number k of this CTA
+    auto load_ve = [&](int k) -> uint32_t { return __ldg(&vlist[(blockIdx.x + k * gridDim.x) * (unsigned)TILE_NLMAX + tid]); };
+    // this thread's record (three coalesced 16-byte planes) of a tile with nTets tets whose record starts at 16 * off16
+    auto load_rec = [&](uint32_t off16, uint32_t nTets, float4& a0, float4& a1, float4& a2) {
+        const uint8_t* base = records + 16ull * off16 + TILE_OFF_TETS + 16 * tid;
+        if ((uint32_t)tid < nTets) { a0 = ldg_stream(base); a1 = ldg_stream(base + 16u * nTets); a2 = ldg_stream(base + 32u * nTets); }
+    };
+    // asynchronous gather of this thread's vertex into the staging buffers, alternating (tile k -> buffer k & 1).
+    // The two destinations live in per-thread registers that swap every call: when ptxas 12.9 folds a
+    // uniform-register buffer offset into an LDGSTS that also carries a cache-hint descriptor it emits an encoding
+    // the B200 rejects ("illegal instruction")
+    uint32_t gdst = smem_u32(smem + LOCAL_OFF_QS + 16 * tid);
+    uint32_t gdstOther = gdst + LOCAL_QS_BYTES;
+    auto gather = [&](uint32_t ve) {
+        if (ve != 0xffffffffu) {
+            cp_async16_hint(gdst, &q[ve & ~TILE_OWNER_BIT], L2_EVICT_LAST);
+            if (ROT_MODE == 1 && (ve & TILE_OWNER_BIT)) prefetch_l2(&b0[ve & ~TILE_OWNER_BIT]);
+        }
+        cp_async_commit();
+        const uint32_t t = gdst; gdst = gdstOther; gdstOther = t;
+    };
+    // producer duties: lane 0 of the last warp
+    const bool producer = tid == TILE_T - 32;
+    auto fetch_c = [&](int k) {        // part C of tile k -> buffer k & 1
+        const uint2 te = __ldg(reinterpret_cast<const uint2*>(meta_of(k)));       // off / 16, abBytes | cBytes << 16
+        const uint32_t abBytes = te.y & 0xffffu, cBytes = te.y >> 16;
+        mbar_expect_tx(&cbar[k & 1], cBytes);
+        bulk_g2s_hint(smem + LOCAL_OFF_C + (k & 1) * TILE_CMAX, records + 16ull * te.x + abBytes, cBytes, &cbar[k & 1], L2_EVICT_FIRST);
+    };
+    auto prefetch_ab = [&](int k) {    // part AB of tile k -> L2
+        const uint2 te = __ldg(reinterpret_cast<const uint2*>(meta_of(k)));
+        bulk_prefetch_l2(records + 16ull * te.x, te.y & 0xffffu);
+    };
+
+    // ---- prologue: everything here touches only the immutable tile stream
+    if (producer) {
+        fetch_c(0);
+        if (nIt > 1) { fetch_c(1); prefetch_ab(1); }
+        if (nIt > 2) prefetch_ab(2);
+    }
+    // tile-table words of the current tile: group `warp` (with the tet count) and, with 16-vertex groups, `warp + 8`
+    uint32_t mwA = __ldg(meta_of(0) + 4 + warp), mwB = (TILE_NGROUPS > 8) ? __ldg(meta_of(0) + 4 + (warp + 8) % TILE_NGROUPS) : 0u;
+    uint32_t veN = load_ve(0);
+    float4 r0, r1, r2;
+    load_rec(__ldg(meta_of(0)), mwA >> 18, r0, r1, r2);
+    // from here on the kernel reads positions written by the previous launch in the stream (and later overwrites
+    // the slots that launch reads)
+    pdl_launch_dependents();
+    pdl_wait();
+    halo_before(0);
+    gather(veN);
+    veN = (nIt > 1) ? load_ve(1) : 0xffffffffu;
+    if (nIt > 1) halo_before(1);
+    gather(veN);
+    veN = (nIt > 2) ? load_ve(2) : 0xffffffffu;                  // vlist entry of tile it+2
+    cp_async_wait_1();       // this thread's part of tile 0 has landed
+    __syncthreads();         // tile 0 staged
+
+    long long tk = 0, acc[7] = {0, 0, 0, 0, 0, 0, 0};
+#define PD_TICK(i) if (PROF) { const long long now = clock64(); acc[i] += now - tk; tk = now; }
+    if (PROF) tk = clock64();
+    for (int it = 0; it < nIt; ++it) {
+        const int b = it & 1;
+        // the next tile's table words (consumed at the end of this tile's phase B and later)
+        uint32_t off16N = 0u, mwAN = 0u, mwBN = 0u;
+        if (it + 1 < nIt) { const uint32_t* m = meta_of(it + 1); off16N = __ldg(m); mwAN = __ldg(m + 4 + warp); if (TILE_NGROUPS > 8) mwBN = __ldg(m + 4 + (warp + 8) % TILE_NGROUPS); }
+        // ---- phase B of tile it
+        if ((uint32_t)tid < (mwA >> 18))
+            local_phase_b<ROT_MODE, JACOBI>(r0, r1, r2, smem + LOCAL_OFF_QS + b * LOCAL_QS_BYTES,
+                                            smem + LOCAL_OFF_HS + b * LOCAL_HS_BYTES + 16 * (tid & ~7));
+        PD_TICK(0)
+        // the record registers are free: fetch the next tile's record (consumed after this tile's phase C)
+        if (it + 1 < nIt) load_rec(off16N, mwAN >> 18, r0, r1, r2);
+        cp_async_wait_all();   // this thread's part of tile it+1's positions has landed
+        PD_TICK(1)
+        __syncthreads();       // H scratch of tile it complete; tile it+1 staged; every warp is past phase C of tile it-1
+        PD_TICK(2)
+        // staging buffer b and part C buffer (it+1)&1 are free now
+        if (it + 2 < nIt) halo_before(it + 2);
+        gather(veN);           // tile it+2 into buffer b (an empty group when there is none)
+        if (producer) {
+            if (it >= 1 && it + 1 < nIt) fetch_c(it + 1);
+            if (it + 3 < nIt) prefetch_ab(it + 3);
+        }
+        veN = (it + 3 < nIt) ? load_ve(it + 3) : 0xffffffffu;
+        PD_TICK(3)
+        // ---- phase C of tile it: this warp sums vertex group `warp` (and `warp + 8`)
+        mbar_wait(&cbar[b], (uint32_t)((it >> 1) & 1));
+        PD_TICK(4)
+        {
+            const uint8_t* Cb = smem + LOCAL_OFF_C + b * TILE_CMAX;
+            const uint8_t* Hb = smem + LOCAL_OFF_HS + b * LOCAL_HS_BYTES;
+            const uint32_t slot0 = (blockIdx.x + it * gridDim.x) * (unsigned)TILE_NLMAX;
+            local_phase_c<ROT_MODE == 1>(Cb, Hb, mwA, slot0 + (uint32_t)(TILE_GROUP * warp), lane, vlist, b0, P);
+            if (TILE_NGROUPS > 8) local_phase_c<ROT_MODE == 1>(Cb, Hb, mwB, slot0 + (uint32_t)(TILE_GROUP * (warp + 8)), lane, vlist, b0, P);
+        }
+        PD_TICK(5)
+        mwA = mwAN; mwB = mwBN;
     }
     if (PROF && tid == 0) {
 #pragma unroll
@@ -439,8 +518,6 @@ k_local(const uint8_t* __restrict__ records, const uint4* __restrict__ tileTab, 
         prof[8 * blockIdx.x + 7] = (unsigned long long)nIt;
     }
 #undef PD_TICK
-    mbar_wait(&bar[2], (uint32_t)((nIt - 1) & 1));
-    local_phase_c<ROT_MODE == 1>(smem, vePrev, gtPrev, (blockIdx.x + (nIt - 1) * gridDim.x) * (unsigned)TILE_NLMAX, tid, b0, P);
 }
 
 // ------------------------------------------------------------------ global step (Jacobi + Chebyshev)

@@ -249,6 +249,97 @@ __device__ __forceinline__ bool rotation_newton(const Mat3& Fm, Mat3& Rm)
     return ok;
 }
 
+// ------------------------------------------------------------------ packed FP32 (Blackwell FFMA2 / FMUL2 / FADD2)
+// sm_100 executes add/mul/fma on PAIRS of floats held in an aligned 64-bit register pair as ONE instruction
+// (`fma.rn.f32x2` -> FFMA2): one issue slot for two FMAs (measured on B200, scripts/micro/ffma2_bench.cu: the FMA
+// pipe is busy two cycles, the scheduler one), each half rounded exactly like the scalar operation.  An operand
+// may be a scalar broadcast, have its halves swapped and either half negated at no cost (ptxas folds
+// make_float2(s, s), make_float2(a.y, a.x), make_float2(-a.x, a.y) into operand modifiers).  The local kernel is
+// bound by instruction issue, so its phase B works on matrix COLUMNS stored as (rows 0 and 1 packed, row 2 scalar).
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c)
+{
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\tmov.b64 rc, {%6,%7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b)
+{
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2add(float2 a, float2 b)
+{
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b)
+{
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\t"
+        "sub.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+struct Col3 {          // one matrix column: rows 0 and 1 packed, row 2 scalar
+    float2 xy;
+    float z;
+};
+// u x v: 2 packed + 2 scalar instructions
+__device__ __forceinline__ Col3 cross3(const Col3& u, const Col3& v)
+{
+    Col3 c;
+    const float2 t = f2mul(make_float2(-v.xy.y, v.xy.x), bc2(u.z));            // (-v.y u.z,  v.x u.z)
+    c.xy = f2fma(make_float2(u.xy.y, -u.xy.x), bc2(v.z), t);                   // ( u.y v.z - v.y u.z, -u.x v.z + v.x u.z)
+    c.z = fmaf(u.xy.x, v.xy.y, -(u.xy.y * v.xy.x));
+    return c;
+}
+__device__ __forceinline__ float dot3c(const Col3& a, const Col3& b)
+{
+    const float2 p = f2mul(a.xy, b.xy);
+    return fmaf(a.z, b.z, p.x) + p.y;
+}
+
+// Packed fast path of the corotational projection, the polar Newton iteration X <- (X + X^-T)/2 of
+// rotation_newton() unrolled for the two steps a PD solve needs and carried in SCALED form (Y_k = 2^k X_k, so that
+// an update is one fused multiply-add per entry:  Y1 = F + cof(F)/det(F),  Y2 = Y1 + 4 cof(Y1)/det(Y1) = 4 X2).
+// Works on the COLUMNS of F (the polar factor of F^T is R^T, and cof(X) has the cross products of X's columns as
+// its columns).  Same acceptance tests as rotation_newton(): det F > kNewtonDetMin, det X1 - 1 < kNewtonTol,
+// det X1 > 0.5.  Returns false (Y untouched or partial) when the tet needs the general path.
+__device__ __forceinline__ bool rotation_newton2_packed(const Col3& f0, const Col3& f1, const Col3& f2, Col3& y0, Col3& y1, Col3& y2)
+{
+    Col3 c0 = cross3(f1, f2), c1 = cross3(f2, f0), c2 = cross3(f0, f1);
+    const float det0 = dot3c(f0, c0);
+    if (!(det0 > kNewtonDetMin)) return false;
+    const float g0 = rcp_approx(det0);
+    y0.xy = f2fma(c0.xy, bc2(g0), f0.xy); y0.z = fmaf(c0.z, g0, f0.z);
+    y1.xy = f2fma(c1.xy, bc2(g0), f1.xy); y1.z = fmaf(c1.z, g0, f1.z);
+    y2.xy = f2fma(c2.xy, bc2(g0), f2.xy); y2.z = fmaf(c2.z, g0, f2.z);
+    c0 = cross3(y1, y2); c1 = cross3(y2, y0); c2 = cross3(y0, y1);         // = 4 cof(X1)
+    const float det1 = dot3c(y0, c0);                                        // = 8 det(X1)
+    if (!(det1 < 8.0f * (1.0f + kNewtonTol) && det1 > 4.0f)) return false;
+    const float g1 = 4.0f * rcp_approx(det1);
+    y0.xy = f2fma(c0.xy, bc2(g1), y0.xy); y0.z = fmaf(c0.z, g1, y0.z);
+    y1.xy = f2fma(c1.xy, bc2(g1), y1.xy); y1.z = fmaf(c1.z, g1, y1.z);
+    y2.xy = f2fma(c2.xy, bc2(g1), y2.xy); y2.z = fmaf(c2.z, g1, y2.z);     // = 4 X2
+    return true;
+}
+
 // ROT_MODE 0: Newton fast path with SVD fallback (product default); 1: always the SVD (faithful)
 template <int ROT_MODE>
 __device__ __forceinline__ void corotation(const Mat3& F, Mat3& R)

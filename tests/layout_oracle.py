@@ -9,7 +9,9 @@ TILE_ROWSMAX = 56
 TILE_HSTRIDE = TILE_T * 16
 TILE_ZERO_OFF = 4 * TILE_HSTRIDE
 TILE_OWNER_BIT = 0x80000000
-TILE_OFF_TETS = 80
+TILE_OFF_TETS = 96
+TILE_GROUP = 32      # vertices per phase-C group (layout.hpp PD_TILE_GROUP): 32 = one lane per vertex, 16 = two
+TILE_LPV = 32 // TILE_GROUP
 
 
 def spread3(x):
@@ -84,8 +86,8 @@ def build(X, Tet, mu, reorder=True):
             ids, counts = np.unique(tl_tets.reshape(-1), return_counts=True)
             order = np.lexsort((ids, -counts))   # in-tile incidence count descending, id ascending
             vl = ids[order]; cnt = counts[order]
-            nLocal = len(vl); nGroups = (nLocal + 31) // 32
-            g_rows = [(int(cnt[32 * g]) + 1) // 2 for g in range(nGroups)]
+            nLocal = len(vl); nGroups = (nLocal + TILE_GROUP - 1) // TILE_GROUP
+            g_rows = [(int(cnt[TILE_GROUP * g]) + 2 * TILE_LPV - 1) // (2 * TILE_LPV) for g in range(nGroups)]
             g_base = np.concatenate([[0], np.cumsum(g_rows)]).astype(np.int64)
             nRows = int(g_base[-1])
             if nRows <= TILE_ROWSMAX or nTets == 1:
@@ -108,7 +110,7 @@ def build(X, Tet, mu, reorder=True):
         seen_before[vl] = True
         ab_bytes = TILE_OFF_TETS + 48 * nTets; c_bytes = 128 * nRows
         base = tile_rec_off[-1]
-        gtab = np.zeros(12, np.uint32)
+        gtab = np.zeros(16, np.uint32)
         for g in range(nGroups):
             gtab[g] = int(g_base[g]) | (g_rows[g] << 16)
         slot_base = len(tiles) * TILE_NLMAX       # padded slots: tile * TILE_NLMAX + tile-local vertex
@@ -145,9 +147,10 @@ def decode_and_check_records(records, tile_rec_off, tiles):
     for ti, T in enumerate(tiles):
         base = int(tile_rec_off[ti])
         assert base == T["base"] and int(tile_rec_off[ti + 1]) == base + T["ab_bytes"] + T["c_bytes"]
-        assert rec[base:base + 80].tobytes() == T["head"], ti
+        assert rec[base:base + TILE_OFF_TETS].tobytes() == T["head"], ti
         nT = T["tet40"].shape[0]
-        tr = rec[base + 80:base + 80 + 48 * nT].view(np.uint32).reshape(nT, 12)
+        # three planes of 16 bytes per tet: plane p holds words 4p..4p+3 of every record
+        tr = rec[base + TILE_OFF_TETS:base + TILE_OFF_TETS + 48 * nT].view(np.uint32).reshape(3, nT, 4).transpose(1, 0, 2).reshape(nT, 12)
         assert np.array_equal(tr[:, :10], T["tet40"]), ti
         halves = np.stack([tr[:, 10] & 0xffff, tr[:, 10] >> 16, tr[:, 11] & 0xffff, tr[:, 11] >> 16], 1).astype(np.int64)
         assert np.array_equal((halves >> 4) & 0xff, T["corners"]), ti
@@ -169,15 +172,19 @@ def decode_and_check_records(records, tile_rec_off, tiles):
                     assert len(set(zip(a.tolist(), c.tolist()))) == len(set(c.tolist())), (ti, r, h, qw)
         assert ((incT % 16) == 0).all() and (incT < TILE_ZERO_OFF + 128).all()
         for l, lst in enumerate(T["inc"]):
-            g, lane = l // 32, l % 32
+            # vertex l: group l // TILE_GROUP; row r holds entries 2r, 2r+1 of its list in lane l % 32 (one lane per
+            # vertex), or entries 4r, 4r+1 in lane l % 16 and 4r+2, 4r+3 in lane l % 16 + 16 (two lanes per vertex)
+            g, lane = l // TILE_GROUP, l % TILE_GROUP
             rows = T["g_rows"][g]
-            ent = incT[T["g_base"][g]:T["g_base"][g] + rows, lane, :].reshape(-1)
+            blk = incT[T["g_base"][g]:T["g_base"][g] + rows]
+            ent = np.concatenate([blk[:, lane + TILE_GROUP * j, :] for j in range(TILE_LPV)], axis=1).reshape(-1)
             assert len(lst) <= len(ent)
             assert (ent[len(lst):] >= TILE_ZERO_OFF).all(), (ti, l)
             for e, (t, k) in enumerate(lst):
                 assert ent[e] == k * TILE_HSTRIDE + ((t & ~7) | int(col[t, k])) * 16, (ti, l, e)
         # lanes beyond the tile's vertices hold only pads
         nLocal = len(T["inc"])
-        for l in range(nLocal, 32 * len(T["g_rows"])):
-            g, lane = l // 32, l % 32
-            assert (incT[T["g_base"][g]:T["g_base"][g] + T["g_rows"][g], lane, :] >= TILE_ZERO_OFF).all()
+        for l in range(nLocal, TILE_GROUP * len(T["g_rows"])):
+            g, lane = l // TILE_GROUP, l % TILE_GROUP
+            blk = incT[T["g_base"][g]:T["g_base"][g] + T["g_rows"][g]]
+            assert all((blk[:, lane + TILE_GROUP * j, :] >= TILE_ZERO_OFF).all() for j in range(TILE_LPV))
