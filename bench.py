@@ -36,6 +36,17 @@ BATCH_PER_GPU = 64
 DT, GRAVITY, MU, MASS, JITTER, SEED = 1.0 / 60.0, 9.8, 2e5, 1.0, 0.05, 12345
 
 
+def ncu_traffic(workload, kernel="k_local"):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+    (profiles/ncu_traffic.json, written from the .ncu-rep by scripts/ncu_summary.py --traffic); None if not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)[workload][kernel]
+        return float(t["dram_read_bytes"] + t["dram_write_bytes"])
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -345,7 +356,8 @@ def run_b200(args):
                         else "pd_step_host (include/pd_b200.h): pinned host X,V,XTilde in and out every step")},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_local (local step: F, rotation, ordered RHS partials)" + ("" if world == 1 else " -- rank 0's launch"),
-                     "achieved": ach_local, "peak": peak, "unit": "GB/s", "frac": ach_local / peak, "traffic": None,
+                     "achieved": ach_local, "peak": peak, "unit": "GB/s", "frac": ach_local / peak,
+                     "traffic": ncu_traffic(args.workload) if world == 1 else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_local, "launch_ms": t_local_ms,
                      "fused_iteration": {"achieved": ach_iter, "frac": ach_iter / peak, "algorithmic_bytes": bytes_iter,
                                          "ms": t_local_ms + t_vertex_ms, "vertex_kernel_ms": t_vertex_ms},

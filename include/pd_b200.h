@@ -133,6 +133,9 @@ int pd_layout_counts(const pd_layout*, int* num_tiles, uint32_t* num_slots, size
 int pd_layout_get(const pd_layout*, uint32_t* tet_order, uint32_t* vert_order, uint32_t* tet_new,
                   uint32_t* tile_tet_start, uint64_t* tile_rec_off, uint8_t* records,
                   uint32_t* vslot_ptr, uint32_t* vslot, uint32_t* vlist);
+/* staging slot -> vertex map of every tile (num_tiles * 256 entries, 0xffffffff = empty): what the local kernel's
+   position gather reads; the corner words of the tet records hold staging slots */
+int pd_layout_get_vstage(const pd_layout*, uint32_t* vstage);
 int pd_morton_keys(const float* X, const uint32_t* Tet, int num_tets, uint32_t* keys);
 int pd_partition_vertices(int num_verts, int world, int* vbeg /* world+1 */);
 /* host-side prefactorisation of the small-mesh path: sparse Cholesky A = L L^T of a symmetric CSR matrix in the given

@@ -1,5 +1,6 @@
 """Summarise an .ncu-rep (read here, no GPU): key raw metrics + per-phase SASS execution counts.
-  python scripts/ncu_summary.py gpurun_out/x.ncu-rep [--sass]"""
+  python scripts/ncu_summary.py gpurun_out/x.ncu-rep [--sass] [--traffic WORKLOAD KERNEL]
+--traffic merges the capture's DRAM bytes per launch into profiles/ncu_traffic.json (bench.py's roofline.traffic)."""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -37,3 +38,17 @@ if '--sass' in sys.argv:
             n = sum(x[1] for x in seg); s = sum(x[2] for x in seg); w = sum(x[3] for x in seg); wi = sum(x[4] for x in seg)
             if n: print(f"  [{prev:4d}:{i + 1:4d}] -> {o[0][:34]:34s} exec {n:10d} ({100 * n / tot:5.1f}%) samples {100 * s / samp:5.1f}% smemWF {w:9d} (ideal {wi:9d})")
             prev = i + 1
+
+if '--traffic' in sys.argv:
+    import json, os
+    i = sys.argv.index('--traffic'); wl, kn = sys.argv[i + 1], sys.argv[i + 2]
+    def col(name):
+        j = next(k for k, h in enumerate(hdr) if h == name)
+        scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[units[j]]
+        return sum(float(r[j]) for r in data) / len(data) * scale
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    t = json.load(open(path)) if os.path.exists(path) else {}
+    t.setdefault(wl, {})[kn] = {"dram_read_bytes": col('dram__bytes_read.sum'), "dram_write_bytes": col('dram__bytes_write.sum'),
+                                "launches_averaged": len(data), "source": os.path.basename(rep)}
+    json.dump(t, open(path, "w"), indent=1)
+    print("wrote", path, t[wl][kn])

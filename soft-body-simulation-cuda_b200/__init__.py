@@ -86,6 +86,7 @@ SYMBOLS = {
     "pd_layout_free": (None, [_VP]),
     "pd_layout_counts": (_I, [_VP, _PI, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t), _PI]),
     "pd_layout_get": (_I, [_VP] * 10),
+    "pd_layout_get_vstage": (_I, [_VP, _VP]),
     "pd_morton_keys": (_I, [_VP, _VP, _I, _VP]),
     "pd_partition_vertices": (_I, [_I, _I, _VP]),
     "pd_cholesky_factor": (_I, [_I, _VP, _VP, _VP, _PI, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
@@ -295,6 +296,8 @@ class Layout:
         self.vlist = np.zeros(self.num_tiles * 256, np.uint32)      # padded: tile * TILE_NLMAX + local vertex
         _check(lib().pd_layout_get(self._h, _p(self.tet_order), _p(self.vert_order), _p(self.tet_new), _p(self.tile_tet_start),
                                    _p(self.tile_rec_off), _p(self.records), _p(self.vslot_ptr), _p(self.vslot), _p(self.vlist)))
+        self.vstage = np.zeros(self.num_tiles * 256, np.uint32)     # staging slot -> vlist entry of the vertex staged there
+        _check(lib().pd_layout_get_vstage(self._h, _p(self.vstage)))
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:

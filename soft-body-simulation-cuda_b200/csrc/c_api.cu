@@ -260,6 +260,12 @@ int pd_layout_get(const pd_layout* l, uint32_t* tetOrder, uint32_t* vertOrder, u
     if (vlist) std::memcpy(vlist, L.vlist.data(), L.vlist.size() * 4);
     return PD_OK;
 }
+int pd_layout_get_vstage(const pd_layout* l, uint32_t* vstage)
+{
+    if (!l || !vstage) return fail(PD_ERR_INVALID, "bad argument");
+    std::memcpy(vstage, l->L.vstage.data(), l->L.vstage.size() * 4);
+    return PD_OK;
+}
 int pd_morton_keys(const float* X, const uint32_t* Tet, int nT, uint32_t* keys)
 {
     PD_TRY

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
@@ -132,6 +133,64 @@ static void color_tile(uint32_t nTets, uint32_t nRows, const uint32_t* epos, uin
     for (uint32_t e = 0; e < nE; ++e) col[e / 4u][e % 4u] = (uint8_t)ec[e];
 }
 
+// Staging slot of every tile-local vertex (the position gather of the local kernel writes vertex l to slot sigma[l];
+// phase B reads it back with one LDS.128 per corner).  A quarter-warp (8 consecutive tets) reading corner k is conflict
+// free when its distinct vertices sit in 8 different 16-byte bank groups = slots that differ mod 8.  Greedy colouring
+// of the vertices (most constrained first) with the bank group as colour, then two improvement sweeps; at most 32
+// vertices per colour (256 slots).  Integer work only, deterministic.  PD_NO_STAGE_COLOR=1 keeps sigma = identity.
+static void stage_slots(uint32_t nTets, uint32_t nLocal, const uint32_t (*cl)[4], std::vector<uint8_t>& sigma)
+{
+    sigma.resize(nLocal);
+    static const bool off = [] { const char* e = std::getenv("PD_NO_STAGE_COLOR"); return e && e[0] == '1'; }();
+    if (off) { for (uint32_t l = 0; l < nLocal; ++l) sigma[l] = (uint8_t)l; return; }
+    const uint32_t nQ = (nTets + 7u) / 8u, nSets = nQ * 4u;
+    // sets = (quarter-warp, corner): distinct vertices; per vertex the sets it is in
+    std::vector<std::vector<uint16_t>> setsOf(nLocal);
+    for (uint32_t q = 0; q < nQ; ++q)
+        for (uint32_t k = 0; k < 4; ++k) {
+            uint32_t seen[8]; int ns = 0;
+            for (uint32_t t = 8 * q; t < std::min(nTets, 8 * q + 8); ++t) {
+                const uint32_t l = cl[t][k];
+                bool dup = false;
+                for (int i = 0; i < ns; ++i) dup |= seen[i] == l;
+                if (!dup) { seen[ns++] = l; setsOf[l].push_back((uint16_t)(q * 4u + k)); }
+            }
+        }
+    std::vector<uint8_t> cnt((size_t)nSets * 8, 0);      // vertices of colour c in set s
+    std::vector<int> colour(nLocal, -1);
+    uint32_t used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<uint32_t> order(nLocal);
+    for (uint32_t l = 0; l < nLocal; ++l) order[l] = l;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return setsOf[a].size() > setsOf[b].size(); });
+    auto best_colour = [&](uint32_t l) {
+        int best = -1; uint32_t bestCost = 0xffffffffu;
+        for (int c = 0; c < 8; ++c) {
+            if (used[c] >= 32u) continue;
+            uint32_t cost = 0;
+            for (uint16_t s_ : setsOf[l]) cost += cnt[(size_t)s_ * 8 + c];
+            cost = cost * 64u + used[c];                  // ties: the emptiest colour
+            if (cost < bestCost) { bestCost = cost; best = c; }
+        }
+        return best;
+    };
+    for (uint32_t l : order) {
+        const int c = best_colour(l);
+        colour[l] = c; used[c]++;
+        for (uint16_t s_ : setsOf[l]) cnt[(size_t)s_ * 8 + c]++;
+    }
+    for (int sweep = 0; sweep < 2; ++sweep)
+        for (uint32_t l : order) {
+            int c = colour[l];
+            used[c]--;
+            for (uint16_t s_ : setsOf[l]) cnt[(size_t)s_ * 8 + c]--;
+            c = best_colour(l);
+            colour[l] = c; used[c]++;
+            for (uint16_t s_ : setsOf[l]) cnt[(size_t)s_ * 8 + c]++;
+        }
+    uint32_t next[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t l = 0; l < nLocal; ++l) { const int c = colour[l]; sigma[l] = (uint8_t)(c + 8 * (int)next[c]++); }
+}
+
 // tiles + records + slots for a mesh whose vertex ids are final
 static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv, const float* w, Layout& L)
 {
@@ -146,6 +205,7 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
     L.tileTetStart.push_back(0);
     L.tileRecOff.push_back(0);
     std::vector<uint32_t> cnt;
+    std::vector<uint8_t> tileSigma;      // staging slot of every (tile, tile-local vertex)
     while (t0 < nT) {
         // greedy tile: up to TILE_T tets and TILE_NLMAX distinct vertices ...
         vl.clear();
@@ -217,6 +277,8 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
                 const uint32_t e = fill[l]++, g = l / (uint32_t)TILE_GROUP, lane = l % (uint32_t)TILE_GROUP + (uint32_t)TILE_GROUP * ((e >> 1) % (uint32_t)TILE_LPV);
                 epos[4 * tl + k] = ((gRowBase[g] + e / (2u * TILE_LPV)) * 32u + lane) * 2u + (e & 1u);
             }
+        std::vector<uint8_t> sigma;
+        stage_slots(nTets, nLocal, cl, sigma);
         // H-scratch column of every (tet, corner): proper 8-colouring of the bipartite multigraph
         // store groups {8 consecutive tets, corner k}  x  load groups {row, half, 8 consecutive lanes}
         uint8_t col[TILE_T][4];
@@ -246,7 +308,7 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
             tr[9] = w[t];
             uint32_t h[4];
             for (int k = 0; k < 4; ++k) {
-                h[k] = tile_corner_half(cl[tl][k], col[tl][k]);
+                h[k] = tile_corner_half(sigma[cl[tl][k]], col[tl][k]);
                 incT[epos[4 * tl + k]] = (uint16_t)tile_h_offset(tl, (uint32_t)k, col[tl][k]);
             }
             const uint32_t c01 = h[0] | (h[1] << 16), c23 = h[2] | (h[3] << 16);
@@ -255,6 +317,8 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
             for (uint32_t j = 0; j < 12; ++j) std::memcpy(rec + tile_tet_word(nTets, tl, j), &tr[j], 4);      // three 16-byte planes
         }
         L.tileTab.push_back(TileEntry{(uint64_t)base, (uint32_t)abBytes, (uint32_t)cBytes});
+        tileSigma.insert(tileSigma.end(), sigma.begin(), sigma.end());
+        tileSigma.resize((size_t)(tile + 1) * TILE_NLMAX, 0);
         slot += nLocal;
         t0 = t1;
         ++tile;
@@ -274,6 +338,9 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
         if (fillv[v] == L.vslotPtr[v]) L.vlist[s] = v | TILE_OWNER_BIT;       // first slot of the vertex = owner
         L.vslot[fillv[v]++] = (uint32_t)s;
     }
+    L.vstage.assign(L.vlist.size(), 0xffffffffu);
+    for (size_t s = 0; s < L.vlist.size(); ++s)
+        if (L.vlist[s] != 0xffffffffu) L.vstage[(s / TILE_NLMAX) * TILE_NLMAX + tileSigma[s]] = L.vlist[s];
 }
 
 void build_layout(int nV, int nT, const float* X, const uint32_t* Tet, const float* mu, bool reorder, Layout& L)
@@ -524,6 +591,7 @@ void extract_rank_layout(const Layout& G, const RankPlan& P, Layout& L)
     L.nTiles = (int)P.tiles.size();
     L.tileTetStart.push_back(0); L.tileRecOff.push_back(0);
     L.vlist.assign((size_t)L.nTiles * TILE_NLMAX, 0xffffffffu);
+    L.vstage.assign((size_t)L.nTiles * TILE_NLMAX, 0xffffffffu);
     L.maxLocal = 0;
     for (int lt = 0; lt < L.nTiles; ++lt) {
         const uint32_t gt = P.tiles[(size_t)lt];
@@ -547,6 +615,10 @@ void extract_rank_layout(const Layout& G, const RankPlan& P, Layout& L)
         for (uint32_t l = 0; l < h.nLocal; ++l) {
             const uint32_t e = G.vlist[(size_t)gt * TILE_NLMAX + l];
             L.vlist[(size_t)lt * TILE_NLMAX + l] = localOf[e & ~TILE_OWNER_BIT] | (e & TILE_OWNER_BIT);
+        }
+        for (uint32_t sl = 0; sl < (uint32_t)TILE_NLMAX; ++sl) {
+            const uint32_t e = G.vstage[(size_t)gt * TILE_NLMAX + sl];
+            if (e != 0xffffffffu) L.vstage[(size_t)lt * TILE_NLMAX + sl] = localOf[e & ~TILE_OWNER_BIT] | (e & TILE_OWNER_BIT);
         }
     }
     L.nT = (int)L.tetOrder.size();

@@ -29,8 +29,11 @@ constexpr uint32_t TILE_OWNER_BIT = 0x80000000u;         // vlist flag: this slo
 //   +0    TileHeader                                                          32 B
 //   +32   group table u32[16]: rowBase | nRows << 16 of each TILE_GROUP-vertex group     64 B
 //   +96   tet records, 48 B (12 words) each: f32 B[9] (DmInv, row-major), f32 w = |V0|*mu, u32 c01, u32 c23 --
-//         four 16-bit corner words: bits 4..11 = tile-local vertex index (so `word & 0xff0` is the byte offset
-//         into the staged vertex array), bits 12..14 = H-scratch column of this corner's contribution.
+//         four 16-bit corner words: bits 4..11 = STAGING slot of the corner's vertex (so `word & 0xff0` is the byte
+//         offset into the staged vertex array; the slot -> vertex map is Layout::vstage), bits 12..14 = H-scratch
+//         column of this corner's contribution.  Staging slots are chosen per tile (layout.cpp:stage_slots) so that
+//         the 8 tets of a quarter-warp read their corner-k positions from 8 different 16-byte bank groups wherever
+//         the mesh allows (a heuristic 8-colouring; unlike the H columns it is not always conflict free).
 //         Stored as THREE PLANES of 16 bytes per tet (plane p holds words 4p..4p+3 of every tet of the tile,
 //         tile_tet_word()), so that thread t of the local kernel reads its record with three fully coalesced
 //         16-byte loads straight from global memory (plane stride = 16 * nTets).
@@ -85,6 +88,8 @@ struct Layout {
     uint32_t nSlots = 0;                // used slots (sum of the tiles' distinct-vertex counts)
     std::vector<uint32_t> vslotPtr;     // nV+1   vertex -> slots CSR (ascending slots)
     std::vector<uint32_t> vslot;        // nSlots
+    std::vector<uint32_t> vstage;       // nTiles * TILE_NLMAX   STAGING slot -> the vlist entry of the vertex staged there (0xffffffff: none);
+                                        // what the local kernel's position gather reads (stage_slots() in layout.cpp)
     std::vector<uint32_t> vlist;        // nTiles * TILE_NLMAX   slot -> vertex id | TILE_OWNER_BIT (first slot of the vertex), 0xffffffff unused
     int maxLocal = 0;
 };

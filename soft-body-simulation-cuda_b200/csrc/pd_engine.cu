@@ -51,7 +51,7 @@ struct Engine::Impl {
     // tile stream
     uint8_t* records = nullptr;
     uint32_t* tileTab = nullptr;      // per tile TILE_META_WORDS words: record offset (lo, hi), part AB bytes, part C bytes, 8 per-warp words
-    uint32_t *vslotPtr = nullptr, *vslot = nullptr, *vlist = nullptr;
+    uint32_t *vslotPtr = nullptr, *vslot = nullptr, *vlist = nullptr, *vstage = nullptr;
     float4* P = nullptr;             // one partial RHS sum per (tile, tile-local vertex) slot
     // per-vertex state (renumbered, padded float4)
     float4* q[3] = {nullptr, nullptr, nullptr};
@@ -150,6 +150,7 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     d.vslotPtr = dalloc<uint32_t>(L_.vslotPtr.size());
     d.vslot = dalloc<uint32_t>(L_.vslot.size());
     d.vlist = dalloc<uint32_t>(L_.vlist.size());
+    d.vstage = dalloc<uint32_t>(L_.vstage.size());
     d.P = dalloc<float4>((size_t)L_.nTiles * TILE_NLMAX);      // padded slots: tile * TILE_NLMAX + local vertex
     // the three position buffers (and the CG direction p) live in the exchange window, see WindowLayout
     const WindowLayout wl((size_t)nV_, opt.world);
@@ -198,6 +199,7 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     CUDA_CHECK(cudaMemcpy(d.vslotPtr, L_.vslotPtr.data(), L_.vslotPtr.size() * 4, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(d.vslot, L_.vslot.data(), L_.vslot.size() * 4, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(d.vlist, L_.vlist.data(), L_.vlist.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(d.vstage, L_.vstage.data(), L_.vstage.size() * 4, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(d.oldOfNew, L_.vertOrder.data(), (size_t)nV_ * 4, cudaMemcpyHostToDevice));
     {
         std::vector<float> m(nV_), b(nV_);
@@ -306,7 +308,7 @@ void Engine::prepare()
     for (int ti : tileOrder) {
         const uint8_t* rec = L_.records.data() + L_.tileRecOff[ti];
         TileHeader h; std::memcpy(&h, rec, sizeof(h));
-        const uint32_t* vlist = L_.vlist.data() + h.slotBase;
+        const uint32_t* vstage = L_.vstage.data() + h.slotBase;      // the corner words hold staging slots
         for (uint32_t t = 0; t < h.nTets; ++t) {
             float B[12];
             for (uint32_t j = 0; j < 12; ++j) std::memcpy(&B[j], rec + tile_tet_word(h.nTets, t, j), 4);
@@ -319,7 +321,7 @@ void Engine::prepare()
                     col[r] = (i == 0) ? ((-B[0 * 3 + r] - B[1 * 3 + r]) - B[2 * 3 + r]) : B[(i - 1) * 3 + r];
                 // computeSiTSi as nvcc fuses it: fma(c2,c2, fma(c0,c0, c1*c1)), then * (V0*mu)
                 const float kii = std::fma(col[2], col[2], std::fma(col[0], col[0], col[1] * col[1]));
-                d.hostMd[vlist[loc[i]] & ~TILE_OWNER_BIT] += kii * w;
+                d.hostMd[vstage[loc[i]] & ~TILE_OWNER_BIT] += kii * w;
             }
         }
     }
@@ -334,10 +336,10 @@ void Engine::prepare()
 void Engine::launchLocal(const float4* q, bool jacobi, unsigned long long* prof)
 {
     Impl& d = *d_;
-#define PD_LOCAL(RM, JAC) launch_pdl(k_local<RM, JAC>, dim3(localGrid_), dim3(TILE_T), LOCAL_SMEM_BYTES, stream_, pdlActive_, d.records, d.tileTab, L_.nTiles, d.vlist, q, d.b0, d.P, prof, d.wait)
+#define PD_LOCAL(RM, JAC) launch_pdl(k_local<RM, JAC>, dim3(localGrid_), dim3(TILE_T), LOCAL_SMEM_BYTES, stream_, pdlActive_, d.records, d.tileTab, L_.nTiles, d.vstage, d.vlist, q, d.b0, d.P, prof, d.wait)
     if (prof) {
-        if (opt_.rotMode == 2) k_local<2, true, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vlist, q, d.b0, d.P, prof, d.wait);
-        else k_local<0, true, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vlist, q, d.b0, d.P, prof, d.wait);
+        if (opt_.rotMode == 2) k_local<2, true, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vstage, d.vlist, q, d.b0, d.P, prof, d.wait);
+        else k_local<0, true, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vstage, d.vlist, q, d.b0, d.P, prof, d.wait);
     } else if (jacobi) {
         if (opt_.rotMode == 0) PD_LOCAL(0, true);
         else if (opt_.rotMode == 1) PD_LOCAL(1, true);

@@ -387,7 +387,7 @@ __device__ __forceinline__ void local_phase_b(const float4 r0, const float4 r1, 
 template <int ROT_MODE, bool JACOBI, bool PROF = false>
 __global__ void __launch_bounds__(TILE_T, 4)
 k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMeta, int nTiles,
-        const uint32_t* __restrict__ vlist, const float4* __restrict__ q, const float4* __restrict__ b0, float4* __restrict__ P,
+        const uint32_t* __restrict__ vstage, const uint32_t* __restrict__ vlist, const float4* __restrict__ q, const float4* __restrict__ b0, float4* __restrict__ P,
         unsigned long long* __restrict__ prof, DistWait dw)
 {
     // prof (may be null): per-phase clock64 totals of warp 0 of every CTA, 8 counters per CTA (scripts/phase_profile.py)
@@ -413,8 +413,8 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
     };
     auto meta_of = [&](int k) -> const uint32_t* { return tileMeta + (size_t)(blockIdx.x + k * gridDim.x) * TILE_META_WORDS; };
     const int warp = tid >> 5, lane = tid & 31;
-    // this thread's entry of the padded, slot-indexed vertex list of tile number k of this CTA
-    auto load_ve = [&](int k) -> uint32_t { return __ldg(&vlist[(blockIdx.x + k * gridDim.x) * (unsigned)TILE_NLMAX + tid]); };
+    // the vertex staged in this thread's staging slot for tile number k of this CTA (Layout::vstage)
+    auto load_ve = [&](int k) -> uint32_t { return __ldg(&vstage[(blockIdx.x + k * gridDim.x) * (unsigned)TILE_NLMAX + tid]); };
     // this thread's record (three coalesced 16-byte planes) of a tile with nTets tets whose record starts at 16 * off16
     auto load_rec = [&](uint32_t off16, uint32_t nTets, float4& a0, float4& a1, float4& a2) {
         const uint8_t* base = records + 16ull * off16 + TILE_OFF_TETS + 16 * tid;
@@ -434,7 +434,10 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
         cp_async_commit();
         const uint32_t t = gdst; gdst = gdstOther; gdstOther = t;
     };
-    // producer duties: lane 0 of the last warp
+    // producer duties: lane 0 of the LAST warp (the tile-local vertices are sorted by incidence count, so warp 0
+    // carries the longest phase C and the last warp the shortest, usually none at all).  Measured and rejected:
+    // heaviest groups on the highest warp ids (+3 %), the record's table entry requested a phase earlier (+1 %),
+    // 16-vertex groups with two lanes per vertex (-50 % longest list, +10 % instructions: +6 %)
     const bool producer = tid == TILE_T - 32;
     auto fetch_c = [&](int k) {        // part C of tile k -> buffer k & 1
         const uint2 te = __ldg(reinterpret_cast<const uint2*>(meta_of(k)));       // off / 16, abBytes | cBytes << 16
@@ -471,21 +474,32 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
     cp_async_wait_1();       // this thread's part of tile 0 has landed
     __syncthreads();         // tile 0 staged
 
+    // the next tile's group words (phase C) ...
+    uint32_t mwAN = 0u, mwBN = 0u;
+    auto load_groups_next = [&](int k) {
+        if (k < nIt) { const uint32_t* m = meta_of(k); mwAN = __ldg(m + 4 + warp); if (TILE_NGROUPS > 8) mwBN = __ldg(m + 4 + (warp + 8) % TILE_NGROUPS); }
+    };
+    load_groups_next(1);
+    // ... and the record offset and tet count of the tile whose record is fetched next (raw words: any arithmetic on
+    // a loaded value here would stall the warp at the load)
+    uint32_t off16N = 0u, ntvN = 0u;
+    auto load_rec_entry = [&](int k) {
+        if (k < nIt) { const uint32_t* m = meta_of(k); off16N = __ldg(m); ntvN = __ldg(m + 2); }
+    };
+    load_rec_entry(1);
+
     long long tk = 0, acc[7] = {0, 0, 0, 0, 0, 0, 0};
 #define PD_TICK(i) if (PROF) { const long long now = clock64(); acc[i] += now - tk; tk = now; }
     if (PROF) tk = clock64();
     for (int it = 0; it < nIt; ++it) {
         const int b = it & 1;
-        // the next tile's table words (consumed at the end of this tile's phase B and later)
-        uint32_t off16N = 0u, mwAN = 0u, mwBN = 0u;
-        if (it + 1 < nIt) { const uint32_t* m = meta_of(it + 1); off16N = __ldg(m); mwAN = __ldg(m + 4 + warp); if (TILE_NGROUPS > 8) mwBN = __ldg(m + 4 + (warp + 8) % TILE_NGROUPS); }
         // ---- phase B of tile it
         if ((uint32_t)tid < (mwA >> 18))
             local_phase_b<ROT_MODE, JACOBI>(r0, r1, r2, smem + LOCAL_OFF_QS + b * LOCAL_QS_BYTES,
                                             smem + LOCAL_OFF_HS + b * LOCAL_HS_BYTES + 16 * (tid & ~7));
         PD_TICK(0)
         // the record registers are free: fetch the next tile's record (consumed after this tile's phase C)
-        if (it + 1 < nIt) load_rec(off16N, mwAN >> 18, r0, r1, r2);
+        if (it + 1 < nIt) load_rec(off16N, ntvN & 0xffffu, r0, r1, r2);
         cp_async_wait_all();   // this thread's part of tile it+1's positions has landed
         PD_TICK(1)
         __syncthreads();       // H scratch of tile it complete; tile it+1 staged; every warp is past phase C of tile it-1
@@ -511,6 +525,8 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
         }
         PD_TICK(5)
         mwA = mwAN; mwB = mwBN;
+        load_groups_next(it + 2);
+        load_rec_entry(it + 2);
     }
     if (PROF && tid == 0) {
 #pragma unroll

@@ -138,12 +138,16 @@ def partition_vertices(nV, world):
     return np.array([(nV * r) // world for r in range(world + 1)], np.int32)
 
 
-def decode_and_check_records(records, tile_rec_off, tiles):
+def decode_and_check_records(records, tile_rec_off, tiles, vlist=None, vstage=None):
     """Decode the builder's packed tile records and compare them with the canonical tiles of build():
     header, group table, DmInv/w bits and corner indices bit for bit; the incidence rows entry by entry
     after mapping every H-scratch offset back to its (tet, corner); plus the bank-conflict freedom of the
-    8-colouring (every quarter-warp STS.128 of phase B and LDS.128 of phase C hits 8 distinct 16-byte columns)."""
+    8-colouring (every quarter-warp STS.128 of phase B and LDS.128 of phase C hits 8 distinct 16-byte columns).
+    The corner words hold STAGING slots, the builder's free choice like the H columns: with vlist/vstage given, the
+    slot -> vertex map must be a bijection onto the tile's vertices and send every corner back to its vertex.
+    Returns (position-load wavefronts, ideal) of phase B over all tiles (bank conflicts of the staging choice)."""
     rec = np.asarray(records, np.uint8)
+    wf = ideal = 0
     for ti, T in enumerate(tiles):
         base = int(tile_rec_off[ti])
         assert base == T["base"] and int(tile_rec_off[ti + 1]) == base + T["ab_bytes"] + T["c_bytes"]
@@ -153,7 +157,19 @@ def decode_and_check_records(records, tile_rec_off, tiles):
         tr = rec[base + TILE_OFF_TETS:base + TILE_OFF_TETS + 48 * nT].view(np.uint32).reshape(3, nT, 4).transpose(1, 0, 2).reshape(nT, 12)
         assert np.array_equal(tr[:, :10], T["tet40"]), ti
         halves = np.stack([tr[:, 10] & 0xffff, tr[:, 10] >> 16, tr[:, 11] & 0xffff, tr[:, 11] >> 16], 1).astype(np.int64)
-        assert np.array_equal((halves >> 4) & 0xff, T["corners"]), ti
+        stage = (halves >> 4) & 0xff
+        if vstage is None:
+            assert np.array_equal(stage, T["corners"]), ti
+        else:
+            vl = np.asarray(vlist[256 * ti:256 * ti + 256]); vs = np.asarray(vstage[256 * ti:256 * ti + 256])
+            nLocal = len(T["inc"])
+            assert (vl[:nLocal] != 0xffffffff).all() and (vl[nLocal:] == 0xffffffff).all()
+            assert sorted(vs[vs != 0xffffffff].tolist()) == sorted(vl[:nLocal].tolist()), ti         # bijection, owner bits kept
+            assert np.array_equal(vs[stage], vl[T["corners"]]), ti                                  # corner -> slot -> its vertex
+            for q in range(0, nT, 8):           # conflicts of the staged position loads: distinct slots per bank group
+                for k in range(4):
+                    sl = np.unique(stage[q:q + 8, k])
+                    wf += int(np.bincount(sl % 8, minlength=8).max()); ideal += 1
         assert ((halves & 0x800f) == 0).all()
         col = (halves >> 12) & 7
         # stores: the 8 tets of a quarter-warp use 8 distinct columns per corner
@@ -188,3 +204,4 @@ def decode_and_check_records(records, tile_rec_off, tiles):
             g, lane = l // TILE_GROUP, l % TILE_GROUP
             blk = incT[T["g_base"][g]:T["g_base"][g] + T["g_rows"][g]]
             assert all((blk[:, lane + TILE_GROUP * j, :] >= TILE_ZERO_OFF).all() for j in range(TILE_LPV))
+    return wf, ideal

@@ -122,7 +122,8 @@ def _check_layout(pd, sc, reorder=True):
         assert np.array_equal(getattr(Lc, k), Lo[k]), k
     assert (Lc.num_tiles, Lc.num_slots, Lc.max_local) == (Lo["num_tiles"], Lo["num_slots"], Lo["max_local"])
     assert Lc.record_bytes == int(Lc.tile_rec_off[-1])
-    LO.decode_and_check_records(Lc.records, Lc.tile_rec_off, Lo["tiles"])    # incl. DmInv/w bits and the incidence CSR
+    wf, ideal = LO.decode_and_check_records(Lc.records, Lc.tile_rec_off, Lo["tiles"], Lc.vlist, Lc.vstage)    # incl. DmInv/w bits and the incidence CSR
+    assert wf <= 1.35 * ideal, (wf, ideal)      # staging-slot colouring: few bank conflicts left on the position loads (identity: ~1.8x)
     return Lc
 
 
