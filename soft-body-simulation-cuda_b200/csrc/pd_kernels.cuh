@@ -556,6 +556,43 @@ struct DistPush {
     unsigned int* ticket;
 };
 
+// b = (b0 or the owner slot) + the vertex's partial-sum slots in ascending slot order.  The first four slot indices
+// and then their four partial sums are requested together (two dependent load levels instead of one pair per slot:
+// this kernel is latency bound); the ordered sum itself is unchanged bit for bit.
+template <bool BASE>
+__device__ __forceinline__ void vertex_slot_sum(int v, const float4* __restrict__ b0, const uint32_t* __restrict__ vslotPtr,
+                                                const uint32_t* __restrict__ vslot, const float4* __restrict__ P,
+                                                float& bx, float& by, float& bz)
+{
+    uint32_t e0 = vslotPtr[v];
+    const uint32_t e1 = vslotPtr[v + 1];
+    float4 first;
+    if (BASE || e0 == e1) first = b0[v];                        // a vertex without tets keeps b = (M/h^2) s_old
+    uint32_t i0 = 0xffffffffu, i1 = 0xffffffffu, i2 = 0xffffffffu, i3 = 0xffffffffu;
+    if (e0 < e1) i0 = __ldg(&vslot[e0]);
+    if (e0 + 1u < e1) i1 = __ldg(&vslot[e0 + 1u]);
+    if (e0 + 2u < e1) i2 = __ldg(&vslot[e0 + 2u]);
+    if (e0 + 3u < e1) i3 = __ldg(&vslot[e0 + 3u]);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 p0 = (i0 != 0xffffffffu) ? __ldg(&P[i0]) : z;
+    const float4 p1 = (i1 != 0xffffffffu) ? __ldg(&P[i1]) : z;
+    const float4 p2 = (i2 != 0xffffffffu) ? __ldg(&P[i2]) : z;
+    const float4 p3 = (i3 != 0xffffffffu) ? __ldg(&P[i3]) : z;
+    if (BASE || e0 == e1) {
+        bx = first.x; by = first.y; bz = first.z;
+        if (i0 != 0xffffffffu) { bx = __fadd_rn(bx, p0.x); by = __fadd_rn(by, p0.y); bz = __fadd_rn(bz, p0.z); }
+    } else {
+        bx = p0.x; by = p0.y; bz = p0.z;                         // faithful mode: the owner slot already starts from b0
+    }
+    if (i1 != 0xffffffffu) { bx = __fadd_rn(bx, p1.x); by = __fadd_rn(by, p1.y); bz = __fadd_rn(bz, p1.z); }
+    if (i2 != 0xffffffffu) { bx = __fadd_rn(bx, p2.x); by = __fadd_rn(by, p2.y); bz = __fadd_rn(bz, p2.z); }
+    if (i3 != 0xffffffffu) { bx = __fadd_rn(bx, p3.x); by = __fadd_rn(by, p3.y); bz = __fadd_rn(bz, p3.z); }
+    for (uint32_t e = e0 + 4u; e < e1; ++e) {
+        const float4 p = __ldg(&P[vslot[e]]);
+        bx = __fadd_rn(bx, p.x); by = __fadd_rn(by, p.y); bz = __fadd_rn(bz, p.z);
+    }
+}
+
 template <bool BASE, bool DIST = false>      // BASE: the slots hold the elastic terms only and b0 is added here (product default);
                            // otherwise the vertex's first slot already starts from b0 (faithful mode)
 __global__ void k_vertex_jacobi(int nV, const float4* __restrict__ qcur, const float4* __restrict__ qprev,
@@ -576,14 +613,7 @@ __global__ void k_vertex_jacobi(int nV, const float4* __restrict__ qcur, const f
             const float4 d = X0[v];
             bx = __fmul_rn(d.x, wdbc); by = __fmul_rn(d.y, wdbc); bz = __fmul_rn(d.z, wdbc);
         } else {
-            uint32_t e0 = vslotPtr[v];
-            const uint32_t e1 = vslotPtr[v + 1];
-            const float4 p0 = (BASE || e0 == e1) ? b0[v] : __ldg(&P[vslot[e0++]]);    // a vertex without tets keeps b = (M/h^2) s_old
-            bx = p0.x; by = p0.y; bz = p0.z;
-            for (uint32_t e = e0; e < e1; ++e) {
-                const float4 p = __ldg(&P[vslot[e]]);
-                bx = __fadd_rn(bx, p.x); by = __fadd_rn(by, p.y); bz = __fadd_rn(bz, p.z);
-            }
+            vertex_slot_sum<BASE>(v, b0, vslotPtr, vslot, P, bx, by, bz);
         }
         const float4 q = qcur[v], pr = qprev[v];
         const float den = c2.y;
@@ -633,14 +663,7 @@ __global__ void k_vertex_rhs(int nV, const float4* __restrict__ X0, const float4
         const float4 d = X0[v];
         bx = __fmul_rn(d.x, wdbc); by = __fmul_rn(d.y, wdbc); bz = __fmul_rn(d.z, wdbc);
     } else {
-        uint32_t e0 = vslotPtr[v];
-        const uint32_t e1 = vslotPtr[v + 1];
-        const float4 p0 = (BASE || e0 == e1) ? b0[v] : __ldg(&P[vslot[e0++]]);    // a vertex without tets keeps b = (M/h^2) s_old
-        bx = p0.x; by = p0.y; bz = p0.z;
-        for (uint32_t e = e0; e < e1; ++e) {
-            const float4 p = __ldg(&P[vslot[e]]);
-            bx = __fadd_rn(bx, p.x); by = __fadd_rn(by, p.y); bz = __fadd_rn(bz, p.z);
-        }
+        vertex_slot_sum<BASE>(v, b0, vslotPtr, vslot, P, bx, by, bz);
     }
     rhs[v] = make_float4(bx, by, bz, 0.f);
 }
