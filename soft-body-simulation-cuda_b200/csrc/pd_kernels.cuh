@@ -556,6 +556,9 @@ struct DistPush {
     unsigned int* ticket;
 };
 
+#ifndef PD_VERTEX_MINBLOCKS
+#define PD_VERTEX_MINBLOCKS 8      // resident 256-thread blocks per SM (32 registers): measured 66 vs 76 us on grid139 against 6 (40 registers)
+#endif
 // b = (b0 or the owner slot) + the vertex's partial-sum slots in ascending slot order.  The first four slot indices
 // and then their four partial sums are requested together (two dependent load levels instead of one pair per slot:
 // this kernel is latency bound); the ordered sum itself is unchanged bit for bit.
@@ -595,7 +598,7 @@ __device__ __forceinline__ void vertex_slot_sum(int v, const float4* __restrict_
 
 template <bool BASE, bool DIST = false>      // BASE: the slots hold the elastic terms only and b0 is added here (product default);
                            // otherwise the vertex's first slot already starts from b0 (faithful mode)
-__global__ void k_vertex_jacobi(int nV, const float4* __restrict__ qcur, const float4* __restrict__ qprev,
+__global__ void __launch_bounds__(256, PD_VERTEX_MINBLOCKS) k_vertex_jacobi(int nV, const float4* __restrict__ qcur, const float4* __restrict__ qprev,
                                 float4* __restrict__ qnext, const float4* __restrict__ X0, const float4* __restrict__ b0,
                                 const float2* __restrict__ cc, const uint32_t* __restrict__ vslotPtr,
                                 const uint32_t* __restrict__ vslot, const float4* __restrict__ P,
