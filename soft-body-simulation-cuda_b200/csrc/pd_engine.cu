@@ -72,7 +72,6 @@ struct Engine::Impl {
     unsigned long long *flags = nullptr, *epoch = nullptr;
     unsigned int *ticket = nullptr, *status = nullptr;
     uint32_t *pushSrc = nullptr, *pushDst = nullptr, *pushNbr = nullptr;
-    uint32_t *pushPtrV = nullptr, *pushDstV = nullptr, *pushNbrV = nullptr;     // the same list as a CSR by owned vertex (fused push)
     int* nbrRanks = nullptr;
     float4** peerQ = nullptr;                  // [3 * nNbr]: buffer k of neighbour j
     unsigned long long** peerFlag = nullptr;   // [nNbr]: this rank's entry in neighbour j's flag array
@@ -333,13 +332,17 @@ void Engine::prepare()
     d.solverReady = false; d.cholReady = false;      // the system matrix bakes in dt and mu
 }
 
-void Engine::launchLocal(const float4* q, bool jacobi, unsigned long long* prof)
+// pushBuf >= 0 (multi-GPU): q is position buffer number pushBuf and the kernel first pushes its boundary entries to
+// the neighbours (DistWait in pd_kernels.cuh); -1: no push inside the kernel
+void Engine::launchLocal(const float4* q, bool jacobi, unsigned long long* prof, int pushBuf)
 {
     Impl& d = *d_;
-#define PD_LOCAL(RM, JAC) launch_pdl(k_local<RM, JAC>, dim3(localGrid_), dim3(TILE_T), LOCAL_SMEM_BYTES, stream_, pdlActive_, d.records, d.tileTab, L_.nTiles, d.vstage, d.vlist, q, d.b0, d.P, prof, d.wait)
+    DistWait w = d.wait;
+    if (pushBuf >= 0 && opt_.world > 1) { w.nPush = d.nPush; w.peerQ = d.peerQ + (size_t)pushBuf * d.nNbr; }
+#define PD_LOCAL(RM, JAC) launch_pdl(k_local<RM, JAC>, dim3(localGrid_), dim3(TILE_T), LOCAL_SMEM_BYTES, stream_, pdlActive_, d.records, d.tileTab, L_.nTiles, d.vstage, d.vlist, q, d.b0, d.P, prof, w)
     if (prof) {
-        if (opt_.rotMode == 2) k_local<2, true, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vstage, d.vlist, q, d.b0, d.P, prof, d.wait);
-        else k_local<0, true, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vstage, d.vlist, q, d.b0, d.P, prof, d.wait);
+        if (opt_.rotMode == 2) k_local<2, true, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vstage, d.vlist, q, d.b0, d.P, prof, w);
+        else k_local<0, true, true><<<localGrid_, TILE_T, LOCAL_SMEM_BYTES, stream_>>>(d.records, d.tileTab, L_.nTiles, d.vstage, d.vlist, q, d.b0, d.P, prof, w);
     } else if (jacobi) {
         if (opt_.rotMode == 0) PD_LOCAL(0, true);
         else if (opt_.rotMode == 1) PD_LOCAL(1, true);
@@ -360,7 +363,7 @@ void Engine::enqueuePredict()
     omega_ = 1.0f;
     k_predict<<<vg, vb, 0, stream_>>>(nOwn_, d.X, d.V, d.mass, d.dbc, d.md, p.dt, dt2Prepared_, p.gravity,
                                       d.q[base_], d.q[(base_ + 2) % 3], d.b0, d.cc);
-    enqueuePush(d.q[base_], base_);
+    if (lockstep_) enqueuePush(d.q[base_], base_);      // otherwise the first local kernel pushes its input itself
     ++phase_;
 }
 
@@ -377,23 +380,18 @@ void Engine::enqueueIteration(int i, bool timed, size_t* ev)
     const float4* prev = d.q[ip];
     float4* next = d.q[in];
     rec();
-    launchLocal(cur, true);
+    // multi-GPU: the local kernel first pushes the boundary entries of the buffer it reads (`cur`) to the neighbours,
+    // spread over its CTAs and in push-list order, and waits for theirs only before its first boundary tile
+    if (opt_.world > 1 && !connected_) throw std::runtime_error("multi-GPU engine stepped before pd_dist_connect");
+    launchLocal(cur, true, nullptr, (opt_.world > 1 && !lockstep_) ? ic : -1);
     rec();
     // omega recurrence in float, pdSolver.cu:196-198
     if (i <= 10) omega_ = 1;
     else if (i == 11) omega_ = 2 / (2 - p.rho * p.rho);
     else omega_ = 4 / (4 - p.rho * p.rho * omega_);
-    if (opt_.world > 1) {
-        // multi-GPU: the halo push of the new positions is fused into the vertex kernel (no separate launch)
-        if (!connected_) throw std::runtime_error("multi-GPU engine stepped before pd_dist_connect");
-        const DistPush dp{d.pushPtrV, d.pushDstV, d.pushNbrV, d.peerQ + (size_t)in * d.nNbr, d.peerFlag, d.nNbr, d.epoch, d.ticket};
-        if (opt_.rotMode == 1) launch_pdl(k_vertex_jacobi<false, true>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc, dp);
-        else launch_pdl(k_vertex_jacobi<true, true>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc, dp);
-    } else {
-        const DistPush dp{};
-        if (opt_.rotMode == 1) launch_pdl(k_vertex_jacobi<false, false>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc, dp);
-        else launch_pdl(k_vertex_jacobi<true, false>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc, dp);
-    }
+    if (opt_.rotMode == 1) launch_pdl(k_vertex_jacobi<false>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
+    else launch_pdl(k_vertex_jacobi<true>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
+    if (lockstep_) enqueuePush(next, in);
     ++phase_;
     rec();
 }
@@ -466,7 +464,7 @@ void Engine::step(int nSteps)
         perfc_.kernelLaunches += (long long)nSteps * (4 + 3 * params_.numIterations);
         return;
     }
-    const int launchesPerStep = 2 + 2 * params_.numIterations + (opt_.world > 1 ? 1 : 0);     // + the predictor's halo push
+    const int launchesPerStep = 2 + 2 * params_.numIterations;     // multi-GPU: the halo pushes ride inside the local kernels
     if (perf_) {
         const size_t need = 3 * (size_t)params_.numIterations + 2;
         while (d.events.size() < need) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); d.events.push_back(e); }
@@ -654,7 +652,7 @@ float Engine::timeVertexKernelMs(int reps)
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     CUDA_CHECK(cudaEventRecord(a, stream_));
     for (int r = 0; r < reps; ++r)
-        k_vertex_jacobi<true><<<vg, vb, 0, stream_>>>(nOwn_, d.q[0], d.q[2], d.q[1], d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, 1.0f, 1.0f, DistPush{});
+        k_vertex_jacobi<true><<<vg, vb, 0, stream_>>>(nOwn_, d.q[0], d.q[2], d.q[1], d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, 1.0f, 1.0f);
     CUDA_CHECK(cudaEventRecord(b, stream_));
     CUDA_CHECK(cudaEventSynchronize(b));
     float ms = 0;
@@ -877,22 +875,6 @@ void Engine::setPeers(const std::vector<uint8_t*>& peerBase)
     std::vector<uint32_t> nb((size_t)std::max(d.nPush, 1));
     for (int i = 0; i < d.nPush; ++i) nb[(size_t)i] = (uint32_t)nbrIndexOfRank[(size_t)P.pushRank[(size_t)i]];
     d.pushSrc = dalloc<uint32_t>(d.nPush); d.pushDst = dalloc<uint32_t>(d.nPush); d.pushNbr = dalloc<uint32_t>(d.nPush);
-    {   // the same list as a CSR by owned vertex, for the push fused into the vertex kernel
-        std::vector<uint32_t> ptr((size_t)nOwn_ + 1, 0u), dstV((size_t)std::max(d.nPush, 1)), nbrV((size_t)std::max(d.nPush, 1));
-        for (int i = 0; i < d.nPush; ++i) ptr[(size_t)P.pushSrc[(size_t)i] + 1]++;
-        for (int v = 0; v < nOwn_; ++v) ptr[(size_t)v + 1] += ptr[(size_t)v];
-        std::vector<uint32_t> fill(ptr.begin(), ptr.end() - 1);
-        for (int i = 0; i < d.nPush; ++i) {
-            const uint32_t at = fill[(size_t)P.pushSrc[(size_t)i]]++;
-            dstV[at] = P.pushDst[(size_t)i]; nbrV[at] = nb[(size_t)i];
-        }
-        d.pushPtrV = dalloc<uint32_t>((size_t)nOwn_ + 1); d.pushDstV = dalloc<uint32_t>(d.nPush); d.pushNbrV = dalloc<uint32_t>(d.nPush);
-        CUDA_CHECK(cudaMemcpy(d.pushPtrV, ptr.data(), ((size_t)nOwn_ + 1) * 4, cudaMemcpyHostToDevice));
-        if (d.nPush) {
-            CUDA_CHECK(cudaMemcpy(d.pushDstV, dstV.data(), (size_t)d.nPush * 4, cudaMemcpyHostToDevice));
-            CUDA_CHECK(cudaMemcpy(d.pushNbrV, nbrV.data(), (size_t)d.nPush * 4, cudaMemcpyHostToDevice));
-        }
-    }
     d.nbrRanks = dalloc<int>(d.nNbr);
     d.peerQ = dalloc<float4*>(3 * (size_t)d.nNbr); d.peerFlag = dalloc<unsigned long long*>(d.nNbr);
     if (d.nPush) {
@@ -905,7 +887,7 @@ void Engine::setPeers(const std::vector<uint8_t*>& peerBase)
         CUDA_CHECK(cudaMemcpy(d.peerQ, pq.data(), (size_t)3 * d.nNbr * sizeof(float4*), cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaMemcpy(d.peerFlag, pf.data(), (size_t)d.nNbr * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
     }
-    d.wait = DistWait{d.flags, d.epoch, d.nbrRanks, d.nNbr, plan_.nInteriorTiles, d.status};
+    d.wait = DistWait{d.flags, d.epoch, d.nbrRanks, d.nNbr, plan_.nInteriorTiles, d.status, 0, d.pushSrc, d.pushDst, d.pushNbr, d.peerQ, d.peerFlag, d.ticket};
     connected_ = true;
 }
 
@@ -971,6 +953,7 @@ void Engine::stepLockstep(Engine* const* engines, int n, int nSteps)
         if (!engines[r]->ready_) engines[r]->prepare();
     }
     const int iters = engines[0]->params_.numIterations;
+    for (int r = 0; r < n; ++r) engines[r]->lockstep_ = true;
     for (int s = 0; s < nSteps; ++s) {
         for (int r = 0; r < n; ++r) { CUDA_CHECK(cudaSetDevice(engines[r]->opt_.device)); engines[r]->enqueuePredict(); }
         crossSync();
@@ -984,7 +967,7 @@ void Engine::stepLockstep(Engine* const* engines, int n, int nSteps)
             engines[r]->perfc_.steps += 1; engines[r]->perfc_.pdIterations += iters;
         }
     }
-    for (int r = 0; r < n; ++r) { CUDA_CHECK(cudaSetDevice(engines[r]->opt_.device)); CUDA_CHECK(cudaGetLastError()); }
+    for (int r = 0; r < n; ++r) { engines[r]->lockstep_ = false; CUDA_CHECK(cudaSetDevice(engines[r]->opt_.device)); CUDA_CHECK(cudaGetLastError()); }
 }
 
 unsigned int Engine::distStatus()

@@ -99,7 +99,7 @@ private:
     void enqueuePush(const float4* q, int bufIndex);
     void setPeers(const std::vector<uint8_t*>& peerBase);
     float* qbuf(int k) const;
-    void launchLocal(const float4* q, bool jacobi, unsigned long long* prof = nullptr);
+    void launchLocal(const float4* q, bool jacobi, unsigned long long* prof = nullptr, int pushBuf = -1);
     template <typename T> T* dalloc(size_t n);
 
     int nV_ = 0, nT_ = 0, nOwn_ = 0;
@@ -110,6 +110,7 @@ private:
     CsrMatrix hostA_;         // scalar system matrix (renumbered ids), kept for the Cholesky factorisation and the parity tests
     float lastErr_ = 1.f; int lastPdIters_ = 0;
     bool connected_ = false;
+    bool lockstep_ = false;   // driven phase by phase by stepLockstep: halo pushes are separate launches, not in the local kernel
     Scene scene_;             // host copy (original numbering)
     Layout L_;
     SolverParams params_;

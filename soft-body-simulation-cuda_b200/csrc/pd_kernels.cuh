@@ -89,11 +89,21 @@ __device__ __forceinline__ float4 ldg_hint(const float4* p, unsigned long long p
 // neighbour's flag has reached its own epoch -- all ranks push the same number of times in the same order.
 struct DistWait {
     const unsigned long long* flags;   // this rank's flag array, written by the peers (indexed by rank)
-    const unsigned long long* epoch;   // this rank's own push count
+    unsigned long long* epoch;         // this rank's own push count
     const int* nbr;                    // neighbour ranks
     int nNbr;                          // 0 on a single GPU: no wait at all
     int firstTile;                     // first tile (in this rank's processing order) that reads ghost positions
     unsigned int* status;              // set to 1 when a wait gave up (peer died); results are then invalid
+    // push at the START of the local kernel (nPush == 0: the pushes were separate launches): the boundary entries of
+    // the position buffer this launch reads -> the neighbours' ghost entries, in push-list order (consecutive
+    // destinations: full 128-byte NVLink writes), then this rank's flag at the neighbours
+    int nPush;
+    const uint32_t* pushSrc;           // owned local vertex
+    const uint32_t* pushDst;           // ghost index at the neighbour
+    const uint32_t* pushNbr;           // neighbour slot
+    float4* const* peerQ;              // [nNbr]: the neighbours' copies of the buffer this launch reads
+    unsigned long long* const* peerFlag;   // [nNbr]: this rank's entry in the neighbours' flag arrays
+    unsigned int* ticket;
 };
 constexpr long long DIST_WAIT_LIMIT_CYCLES = 20000000000ll;    // ~10 s: a hung peer must not hang this GPU
 
@@ -107,10 +117,10 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void dist_wait(const DistWait& w, int tid)
+// wait until every neighbour's flag has reached `need` (= this rank's push count including this phase's push)
+__device__ __forceinline__ void dist_wait(const DistWait& w, int tid, unsigned long long need)
 {
     if (tid < w.nNbr) {
-        const unsigned long long need = ld_acquire_sys(w.epoch);
         const unsigned long long* f = w.flags + w.nbr[tid];
         const long long t0 = clock64();
         while (ld_acquire_sys(f) < need) {
@@ -127,9 +137,9 @@ __global__ void k_halo_push(int n, const uint32_t* __restrict__ src, const uint3
                             unsigned long long* const* __restrict__ peerFlag, unsigned long long* epoch, unsigned int* ticket)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) peerQ[nbrIdx[i]][dst[i]] = q[src[i]];
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();                        // one per block, cumulative over the block's stores (barrier above)
         const unsigned int t = atomicAdd(ticket, 1u);
         if (t == gridDim.x - 1) {                      // every block's stores are fenced: publish
             *ticket = 0u;
@@ -206,7 +216,7 @@ constexpr uint32_t LOCAL_OFF_QS = 0u;
 constexpr uint32_t LOCAL_OFF_HS = LOCAL_OFF_QS + 2u * LOCAL_QS_BYTES;
 constexpr uint32_t LOCAL_OFF_C = LOCAL_OFF_HS + 2u * LOCAL_HS_BYTES;
 constexpr uint32_t LOCAL_OFF_BAR = LOCAL_OFF_C + 2u * TILE_CMAX;
-constexpr uint32_t LOCAL_SMEM_BYTES = LOCAL_OFF_BAR + 16u;
+constexpr uint32_t LOCAL_SMEM_BYTES = LOCAL_OFF_BAR + 32u;      // two mbarriers, the halo epoch this launch waits for
 static_assert(4u * (LOCAL_SMEM_BYTES + 1024u) <= 233472u, "4 CTAs of the local kernel must fit one SM's shared memory");
 static_assert(TILE_NLMAX == TILE_T, "one tile-local vertex per thread");
 // per-tile entry of the device tile table: record offset / 16, part AB bytes | part C bytes << 16, tet count | vertex
@@ -408,8 +418,9 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
     // multi-GPU: the rank's interior tiles come first; the neighbours' ghost positions are needed -- and waited
     // for -- only before the position gather of the first boundary tile, so the exchange hides behind the interior
     bool needHalo = dw.nNbr > 0;
+    volatile unsigned long long* haloNeed = reinterpret_cast<volatile unsigned long long*>(smem + LOCAL_OFF_BAR + 16);   // (not a register: 64 regs are full)
     auto halo_before = [&](int k) {
-        if (needHalo && (int)(blockIdx.x + k * gridDim.x) >= dw.firstTile) { dist_wait(dw, tid); needHalo = false; }
+        if (needHalo && (int)(blockIdx.x + k * gridDim.x) >= dw.firstTile) { dist_wait(dw, tid, *haloNeed); needHalo = false; }
     };
     auto meta_of = [&](int k) -> const uint32_t* { return tileMeta + (size_t)(blockIdx.x + k * gridDim.x) * TILE_META_WORDS; };
     const int warp = tid >> 5, lane = tid & 31;
@@ -465,6 +476,27 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
     // the slots that launch reads)
     pdl_launch_dependents();
     pdl_wait();
+    if (dw.nNbr > 0) {
+        // this rank's push count so far (read before this CTA's ticket, hence before the last CTA bumps it), plus this
+        // launch's own push
+        if (tid == 0) *haloNeed = *reinterpret_cast<const volatile unsigned long long*>(dw.epoch) + (dw.nPush > 0 ? 1ull : 0ull);
+        // multi-GPU halo push, spread over all CTAs: the exchange overlaps the interior tiles, and the receivers
+        // wait (halo_before) only before their first boundary tile
+        for (int i = blockIdx.x * TILE_T + tid; i < dw.nPush; i += gridDim.x * TILE_T)
+            dw.peerQ[dw.pushNbr[i]][dw.pushDst[i]] = q[dw.pushSrc[i]];
+        __syncthreads();
+        if (tid == 0 && dw.nPush > 0) {
+            __threadfence_system();            // one per CTA, cumulative over the CTA's remote stores (barrier above)
+            const unsigned int t = atomicAdd(dw.ticket, 1u);
+            if (t == gridDim.x - 1) {          // every CTA's stores are fenced: publish
+                const unsigned long long e = *haloNeed;
+                *dw.ticket = 0u;
+                *dw.epoch = e;
+                __threadfence_system();
+                for (int j = 0; j < dw.nNbr; ++j) st_release_sys(dw.peerFlag[j], e);
+            }
+        }
+    }
     halo_before(0);
     gather(veN);
     veN = (nIt > 1) ? load_ve(1) : 0xffffffffu;
@@ -541,21 +573,8 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
 // b = ordered sum of the vertex's partial-sum slots (the first one already carries (M/h^2) s_old).
 // Arithmetic forms follow the reference's SASS: next = fma(-c,q,b)/(c+md) + q (IEEE division);
 // under-relaxation as one DFMA (the reference's `0.9 *` literal is a double); Chebyshev as one FFMA.
-// Multi-GPU (DIST): the halo exchange is FUSED into this kernel -- a boundary vertex's new position goes straight
-// from the register that holds it into the neighbours' ghost entries over NVLink (pushPtr/pushDst/pushNbr = CSR of
-// the push list by owned vertex), and the last block to finish raises this rank's flag at the neighbours
-// (fence.sys by the storing threads -> ticket -> st.release.sys, as k_halo_push).  No separate push launch.
-struct DistPush {
-    const uint32_t* pushPtr;                    // nOwn + 1
-    const uint32_t* pushDst;                    // ghost index at the neighbour
-    const uint32_t* pushNbr;                    // neighbour slot
-    float4* const* peerQ;                       // [nNbr]: the neighbours' copies of the buffer this launch writes
-    unsigned long long* const* peerFlag;        // [nNbr]: this rank's entry in the neighbours' flag arrays
-    int nNbr;
-    unsigned long long* epoch;
-    unsigned int* ticket;
-};
-
+// Multi-GPU: the halo push of the new positions happens at the start of the NEXT local kernel (k_local, DistWait), in
+// push-list order; this kernel is the same on one and on many GPUs.
 #ifndef PD_VERTEX_MINBLOCKS
 #define PD_VERTEX_MINBLOCKS 8      // resident 256-thread blocks per SM (32 registers): measured 66 vs 76 us on grid139 against 6 (40 registers)
 #endif
@@ -596,16 +615,15 @@ __device__ __forceinline__ void vertex_slot_sum(int v, const float4* __restrict_
     }
 }
 
-template <bool BASE, bool DIST = false>      // BASE: the slots hold the elastic terms only and b0 is added here (product default);
+template <bool BASE>       // BASE: the slots hold the elastic terms only and b0 is added here (product default);
                            // otherwise the vertex's first slot already starts from b0 (faithful mode)
 __global__ void __launch_bounds__(256, PD_VERTEX_MINBLOCKS) k_vertex_jacobi(int nV, const float4* __restrict__ qcur, const float4* __restrict__ qprev,
                                 float4* __restrict__ qnext, const float4* __restrict__ X0, const float4* __restrict__ b0,
                                 const float2* __restrict__ cc, const uint32_t* __restrict__ vslotPtr,
                                 const uint32_t* __restrict__ vslot, const float4* __restrict__ P,
-                                float omega, float wdbc, DistPush dp)
+                                float omega, float wdbc)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    bool pushed = false;
     pdl_launch_dependents();
     pdl_wait();              // the slots (and, multi-GPU, the ticket) come from the local kernel just before
     if (v < nV) {
@@ -632,24 +650,6 @@ __global__ void __launch_bounds__(256, PD_VERTEX_MINBLOCKS) k_vertex_jacobi(int 
         nz = __fmaf_rn(__fsub_rn(nz, pr.z), omega, pr.z);
         const float4 out = make_float4(nx, ny, nz, 0.f);
         qnext[v] = out;
-        if (DIST) {
-            const uint32_t p1 = dp.pushPtr[v + 1];
-            for (uint32_t e = dp.pushPtr[v]; e < p1; ++e) { dp.peerQ[dp.pushNbr[e]][dp.pushDst[e]] = out; pushed = true; }
-        }
-    }
-    if (DIST) {
-        if (pushed) __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned int t = atomicAdd(dp.ticket, 1u);
-            if (t == gridDim.x - 1) {                      // every block's remote stores are fenced: publish
-                *dp.ticket = 0u;
-                const unsigned long long e = *dp.epoch + 1ull;
-                *dp.epoch = e;
-                __threadfence_system();
-                for (int j = 0; j < dp.nNbr; ++j) st_release_sys(dp.peerFlag[j], e);
-            }
-        }
     }
 }
 

@@ -157,7 +157,8 @@ __device__ __forceinline__ void dist_push_p(cg::grid_group& grid, const DistSolv
 {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
     for (int i = gtid; i < D.nPush; i += gstride) D.peerP[D.pushNbr[i]][D.pushDst[i]] = p[D.pushSrc[i]];
-    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();      // one per block, cumulative over the block's remote stores
     grid.sync();
     ++pSeq;
     if (blockIdx.x == 0 && (int)threadIdx.x < D.nNbr) solve_st_release_sys(D.peerPFlag[threadIdx.x], pSeq);
