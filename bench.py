@@ -187,10 +187,12 @@ def initial_velocity(X):
 
 
 def cpu_baseline(workload_iters, threads):
-    """The oracle port (oracle/pd_oracle.c, OpenMP) on a bounded sample of the same workload family."""
+    """The oracle port (oracle/pd_oracle.c, OpenMP) on a bounded sample of the same workload family: the same
+    jittered Kuhn grid at 64^3 cells (1.57 M tets, far larger than the host caches, like grid139 is for the GPU),
+    one warm-up step + two timed steps of 100 iterations = about 10-20 s on 16 host threads."""
     import oracle as O
     pd = importlib.import_module("soft-body-simulation-cuda_b200")
-    cells = 24
+    cells = int(os.environ.get("PD_CPU_BASELINE_CELLS", "64"))
     sc = pd.Scene.kuhn_grid(cells, cells, cells, 1.0, JITTER, SEED, (0.0, 10.0, 0.0), MASS, MU)
     a = sc.arrays()
     osc = O.Scene(a["X"], a["Tet"], a["mass"], a["mu"], planes=[(np.zeros(3, np.float32), np.array([0, 1, 0], np.float32))])
