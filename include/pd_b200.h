@@ -136,6 +136,8 @@ int pd_layout_get(const pd_layout*, uint32_t* tet_order, uint32_t* vert_order, u
 /* staging slot -> vertex map of every tile (num_tiles * 256 entries, 0xffffffff = empty): what the local kernel's
    position gather reads; the corner words of the tet records hold staging slots */
 int pd_layout_get_vstage(const pd_layout*, uint32_t* vstage);
+/* the device tile table the local kernel reads: num_tiles * 12 words (csrc/layout.hpp, TILE_META_WORDS) */
+int pd_layout_tile_table(const pd_layout*, uint32_t* table);
 int pd_morton_keys(const float* X, const uint32_t* Tet, int num_tets, uint32_t* keys);
 int pd_partition_vertices(int num_verts, int world, int* vbeg /* world+1 */);
 /* host-side prefactorisation of the small-mesh path: sparse Cholesky A = L L^T of a symmetric CSR matrix in the given

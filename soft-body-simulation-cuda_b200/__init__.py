@@ -87,6 +87,7 @@ SYMBOLS = {
     "pd_layout_counts": (_I, [_VP, _PI, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t), _PI]),
     "pd_layout_get": (_I, [_VP] * 10),
     "pd_layout_get_vstage": (_I, [_VP, _VP]),
+    "pd_layout_tile_table": (_I, [_VP, _VP]),
     "pd_morton_keys": (_I, [_VP, _VP, _I, _VP]),
     "pd_partition_vertices": (_I, [_I, _I, _VP]),
     "pd_cholesky_factor": (_I, [_I, _VP, _VP, _VP, _PI, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
@@ -298,6 +299,8 @@ class Layout:
                                    _p(self.tile_rec_off), _p(self.records), _p(self.vslot_ptr), _p(self.vslot), _p(self.vlist)))
         self.vstage = np.zeros(self.num_tiles * 256, np.uint32)     # staging slot -> vlist entry of the vertex staged there
         _check(lib().pd_layout_get_vstage(self._h, _p(self.vstage)))
+        self.tile_table = np.zeros((self.num_tiles, 12), np.uint32)  # what the local kernel reads per tile (layout.hpp TILE_META_WORDS)
+        _check(lib().pd_layout_tile_table(self._h, _p(self.tile_table)))
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:

@@ -260,6 +260,16 @@ int pd_layout_get(const pd_layout* l, uint32_t* tetOrder, uint32_t* vertOrder, u
     if (vlist) std::memcpy(vlist, L.vlist.data(), L.vlist.size() * 4);
     return PD_OK;
 }
+int pd_layout_tile_table(const pd_layout* l, uint32_t* table)
+{
+    PD_TRY
+    if (!l || !table) return fail(PD_ERR_INVALID, "bad argument");
+    std::vector<uint32_t> m;
+    build_tile_table(l->L, m);
+    std::memcpy(table, m.data(), m.size() * 4);
+    return PD_OK;
+    PD_CATCH_INT
+}
 int pd_layout_get_vstage(const pd_layout* l, uint32_t* vstage)
 {
     if (!l || !vstage) return fail(PD_ERR_INVALID, "bad argument");

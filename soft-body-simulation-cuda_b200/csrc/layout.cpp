@@ -343,6 +343,28 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
         if (L.vlist[s] != 0xffffffffu) L.vstage[(s / TILE_NLMAX) * TILE_NLMAX + tileSigma[s]] = L.vlist[s];
 }
 
+// The device tile table the local kernel reads (TILE_META_WORDS words per tile, layout.hpp).
+void build_tile_table(const Layout& L, std::vector<uint32_t>& meta)
+{
+    meta.assign(L.tileTab.size() * TILE_META_WORDS, 0u);
+    for (size_t ti = 0; ti < L.tileTab.size(); ++ti) {
+        const uint8_t* rec = L.records.data() + L.tileRecOff[ti];
+        TileHeader h; std::memcpy(&h, rec, sizeof(h));
+        uint32_t* m = &meta[ti * TILE_META_WORDS];
+        if ((L.tileTab[ti].off & 15u) || (L.tileTab[ti].off >> 4) > 0xffffffffull || L.tileTab[ti].abBytes > 0xffffu || L.tileTab[ti].cBytes > 0xffffu)
+            throw std::runtime_error("tile table: record offset / size out of range");
+        m[0] = (uint32_t)(L.tileTab[ti].off >> 4);
+        m[1] = L.tileTab[ti].abBytes | (L.tileTab[ti].cBytes << 16);
+        m[2] = h.nTets | (h.nLocal << 16);
+        for (uint32_t g = 0; g < (uint32_t)TILE_NGROUPS; ++g) {
+            uint32_t gt = 0;
+            if (g < h.nGroups) std::memcpy(&gt, rec + 32 + 4 * g, 4);          // rowBase | nRows << 16
+            const uint32_t nValid = (g < h.nGroups) ? std::min<uint32_t>((uint32_t)TILE_GROUP, h.nLocal - g * (uint32_t)TILE_GROUP) : 0u;
+            m[4 + g] = (gt & 63u) | ((gt >> 16) << 6) | (nValid << 12) | (g < 8u ? (h.nTets << 18) : 0u);
+        }
+    }
+}
+
 void build_layout(int nV, int nT, const float* X, const uint32_t* Tet, const float* mu, bool reorder, Layout& L)
 {
     L = Layout();

@@ -94,6 +94,13 @@ struct Layout {
     int maxLocal = 0;
 };
 
+// Per-tile entry of the DEVICE tile table the local kernel reads (build_tile_table): record offset / 16, part AB bytes |
+// part C bytes << 16, tet count | vertex count << 16, spare, then one word per vertex group (warp w sums group w -- word
+// 4 + w -- and, with 16-vertex groups, w + 8): rowBase | nRows << 6 | vertices in the group << 12, and in the first
+// eight also the tile's tet count << 18
+constexpr int TILE_META_WORDS = 4 + TILE_NGROUPS;
+void build_tile_table(const Layout& L, std::vector<uint32_t>& meta);
+
 // Reordering key of a tet: 30-bit Morton code of its quantised centroid
 void morton_keys(const float* X, const uint32_t* Tet, int nT, std::vector<uint32_t>& keys);
 

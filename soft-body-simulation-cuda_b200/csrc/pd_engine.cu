@@ -175,24 +175,9 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
 
     CUDA_CHECK(cudaMemcpy(d.records, L_.records.data(), L_.records.size(), cudaMemcpyHostToDevice));
     static_assert(sizeof(TileEntry) == sizeof(uint4), "tile table entry layout");
-    {   // device tile table (pd_kernels.cuh, TILE_META_WORDS): offset / 16, abBytes | cBytes << 16, two words per warp
-        std::vector<uint32_t> meta(L_.tileTab.size() * TILE_META_WORDS, 0u);
-        for (size_t ti = 0; ti < L_.tileTab.size(); ++ti) {
-            const uint8_t* rec = L_.records.data() + L_.tileRecOff[ti];
-            TileHeader h; std::memcpy(&h, rec, sizeof(h));
-            uint32_t* m = &meta[ti * TILE_META_WORDS];
-            if ((L_.tileTab[ti].off & 15u) || (L_.tileTab[ti].off >> 4) > 0xffffffffull || L_.tileTab[ti].abBytes > 0xffffu || L_.tileTab[ti].cBytes > 0xffffu)
-                throw std::runtime_error("tile table: record offset / size out of range");
-            m[0] = (uint32_t)(L_.tileTab[ti].off >> 4);
-            m[1] = L_.tileTab[ti].abBytes | (L_.tileTab[ti].cBytes << 16);
-            m[2] = h.nTets | (h.nLocal << 16);
-            for (uint32_t g = 0; g < (uint32_t)TILE_NGROUPS; ++g) {
-                uint32_t gt = 0;
-                if (g < h.nGroups) std::memcpy(&gt, rec + 32 + 4 * g, 4);          // rowBase | nRows << 16
-                const uint32_t nValid = (g < h.nGroups) ? std::min<uint32_t>((uint32_t)TILE_GROUP, h.nLocal - g * (uint32_t)TILE_GROUP) : 0u;
-                m[4 + g] = (gt & 63u) | ((gt >> 16) << 6) | (nValid << 12) | (g < 8u ? (h.nTets << 18) : 0u);
-            }
-        }
+    {   // device tile table (layout.cpp:build_tile_table)
+        std::vector<uint32_t> meta;
+        build_tile_table(L_, meta);
         CUDA_CHECK(cudaMemcpy(d.tileTab, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
     }
     CUDA_CHECK(cudaMemcpy(d.vslotPtr, L_.vslotPtr.data(), L_.vslotPtr.size() * 4, cudaMemcpyHostToDevice));

@@ -219,10 +219,7 @@ constexpr uint32_t LOCAL_OFF_BAR = LOCAL_OFF_C + 2u * TILE_CMAX;
 constexpr uint32_t LOCAL_SMEM_BYTES = LOCAL_OFF_BAR + 32u;      // two mbarriers, the halo epoch this launch waits for
 static_assert(4u * (LOCAL_SMEM_BYTES + 1024u) <= 233472u, "4 CTAs of the local kernel must fit one SM's shared memory");
 static_assert(TILE_NLMAX == TILE_T, "one tile-local vertex per thread");
-// per-tile entry of the device tile table: record offset / 16, part AB bytes | part C bytes << 16, tet count | vertex
-// count << 16, spare, then one word per vertex group (warp w sums group w -- word 4 + w -- and, with 16-vertex groups,
-// w + 8): rowBase | nRows << 6 | vertices in the group << 12, and in the first eight also the tile's tet count << 18
-constexpr int TILE_META_WORDS = 4 + TILE_NGROUPS;
+// (the per-tile entry of the device tile table, TILE_META_WORDS words, is described in layout.hpp)
 
 __device__ __forceinline__ float dot3_nv(float a0, float b0, float a1, float b1, float a2, float b2)
 {   // a0*b0 + a1*b1 + a2*b2 as nvcc contracts the reference's glm products

@@ -205,3 +205,19 @@ def decode_and_check_records(records, tile_rec_off, tiles, vlist=None, vstage=No
             blk = incT[T["g_base"][g]:T["g_base"][g] + T["g_rows"][g]]
             assert all((blk[:, lane + TILE_GROUP * j, :] >= TILE_ZERO_OFF).all() for j in range(TILE_LPV))
     return wf, ideal
+
+
+def tile_table(tiles):
+    """layout.cpp:build_tile_table restated from the canonical tiles of build(): per tile 12 words."""
+    out = np.zeros((len(tiles), 4 + TILE_NLMAX // TILE_GROUP), np.uint32)
+    for ti, T in enumerate(tiles):
+        nTets = T["tet40"].shape[0]; nLocal = len(T["inc"])
+        assert T["base"] % 16 == 0
+        out[ti, 0] = T["base"] // 16
+        out[ti, 1] = T["ab_bytes"] | (T["c_bytes"] << 16)
+        out[ti, 2] = nTets | (nLocal << 16)
+        for g in range(len(T["g_rows"])):
+            n_valid = min(TILE_GROUP, nLocal - g * TILE_GROUP)
+            out[ti, 4 + g] = int(T["g_base"][g]) | (int(T["g_rows"][g]) << 6) | (n_valid << 12)
+        out[ti, 4:12] |= np.uint32(nTets << 18)
+    return out

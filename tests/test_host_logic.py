@@ -123,6 +123,7 @@ def _check_layout(pd, sc, reorder=True):
     assert (Lc.num_tiles, Lc.num_slots, Lc.max_local) == (Lo["num_tiles"], Lo["num_slots"], Lo["max_local"])
     assert Lc.record_bytes == int(Lc.tile_rec_off[-1])
     wf, ideal = LO.decode_and_check_records(Lc.records, Lc.tile_rec_off, Lo["tiles"], Lc.vlist, Lc.vstage)    # incl. DmInv/w bits and the incidence CSR
+    assert np.array_equal(Lc.tile_table, LO.tile_table(Lo["tiles"]))        # what the local kernel reads per tile
     assert wf <= 1.35 * ideal, (wf, ideal)      # staging-slot colouring: few bank conflicts left on the position loads (identity: ~1.8x)
     return Lc
 
