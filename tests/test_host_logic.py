@@ -202,3 +202,54 @@ def test_sparse_cholesky_prefactor_host(pd, O, assets):
     assert abs(R).max() <= 2e-6 * abs(A).max()
     with pytest.raises(pd.PdError):      # not positive definite -> error, nothing returned
         pd.cholesky_factor(np.array([0, 1, 2], np.int32), np.array([0, 1], np.int32), np.array([1.0, -1.0], np.float32))
+
+
+def _fan(n_tets, hub_first=True):
+    """n_tets tets that all share vertex 0 (a hub of valence n_tets) and, pairwise, an edge: a closed fan of thin
+    wedges around the z axis.  The hub's incidence list is far longer than one tile's row budget allows."""
+    n = n_tets
+    ang = 2 * np.pi * np.arange(n) / n
+    ring_lo = np.stack([np.cos(ang), np.sin(ang), np.zeros(n)], 1)
+    ring_hi = ring_lo + np.array([0, 0, 1.0])
+    X = np.concatenate([[[0, 0, 0.5]], ring_lo, ring_hi]).astype(np.float32)
+    lo = 1 + np.arange(n); hi = 1 + n + np.arange(n)
+    T = np.stack([np.zeros(n, np.int64), lo, np.roll(lo, -1), hi], 1).astype(np.uint32)
+    return X, T
+
+
+def test_layout_edge_cases(pd):
+    """Ragged and extreme inputs of the tile builder, each bit for bit against the numpy restatement: one tet;
+    vertices no tet touches (renumbered last, no slots, nothing staged); 256 / 257 tets (tile boundary); a hub vertex of
+    valence 700 (its list alone exceeds a tile's 56 incidence rows, so tiles must be halved until it fits)."""
+    one = pd.Scene.from_arrays(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32), np.array([[0, 1, 2, 3]], np.uint32), 1.0, 1e5)
+    L = _check_layout(pd, one)
+    assert (L.num_tiles, L.num_slots) == (1, 4)
+    # isolated vertices: ids 1 and 5 are not referenced
+    X = np.random.default_rng(5).normal(size=(7, 3)).astype(np.float32)
+    iso = pd.Scene.from_arrays(X, np.array([[0, 2, 3, 4], [2, 3, 4, 6]], np.uint32), 1.0, 1e5)
+    L = _check_layout(pd, iso)
+    assert sorted(L.vert_order[-2:].tolist()) == [1, 5]
+    assert np.diff(L.vslot_ptr.astype(np.int64))[-2:].tolist() == [0, 0] and L.num_slots == 5
+    assert int((L.vstage != 0xffffffff).sum()) == 5
+    for n in (256, 257):
+        g = pd.Scene.kuhn_grid(n, 1, 1, 1.0, 0.0, 1, (0, 0, 0), 1.0, 1e5)       # 6 n tets in a row of cells
+        Xg, Tg = g.arrays()["X"], g.arrays()["Tet"][:n]
+        sc = pd.Scene.from_arrays(Xg, Tg, 1.0, 1e5)
+        L = _check_layout(pd, sc)
+        assert L.num_tiles == (1 if n == 256 else 2)
+    X, T = _fan(700)
+    fan = pd.Scene.from_arrays(X, T, 1.0, 1e5)
+    L = _check_layout(pd, fan)
+    tt = np.diff(L.tile_tet_start.astype(np.int64))
+    assert tt.max() <= 112 and tt.sum() == 700          # 2 list entries per row, 56 rows: at most 112 tets around the hub per tile
+    hub = int(np.flatnonzero(L.vert_order == 0)[0])
+    assert int(L.vslot_ptr[hub + 1] - L.vslot_ptr[hub]) == L.num_tiles      # the hub has a slot in every tile
+
+
+def test_bad_meshes_are_rejected(pd):
+    X = np.zeros((4, 3), np.float32)
+    with pytest.raises(pd.PdError):
+        pd.Scene.from_arrays(X, np.array([[0, 1, 2, 9]], np.uint32), 1.0, 1e5).layout()      # vertex index out of range
+    for Xe, Te in [(np.zeros((3, 3), np.float32), np.zeros((0, 4), np.uint32)), (np.zeros((0, 3), np.float32), np.zeros((0, 4), np.uint32))]:
+        with pytest.raises(pd.PdError):                                                          # empty meshes: an error code, not a crash
+            pd.Scene.from_arrays(Xe, Te, 1.0, 1e5)
