@@ -93,3 +93,69 @@ def rotation(F):
     if rc:
         raise RuntimeError(f"reference harness CUDA error {rc}")
     return R.reshape(-1, 3, 3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# oracle/_ref/libpd_ref_solvers.so (oracle/ref_solvers.cu): the reference's direct / CG global-step back-ends
+SOLVERS_PATH = os.path.join(_HERE, "_ref", "libpd_ref_solvers.so")
+_slib = None
+
+
+def solvers_available():
+    return os.path.exists(SOLVERS_PATH)
+
+
+def solvers_lib():
+    global _slib
+    if _slib is None:
+        L = C.CDLL(SOLVERS_PATH)
+        L.refs_create.restype = C.c_void_p
+        L.refs_create.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_int]
+        L.refs_destroy.argtypes = [C.c_void_p]
+        L.refs_step.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]
+        L.refs_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refs_get.argtypes = [C.c_void_p] * 4
+        L.refs_set.argtypes = [C.c_void_p] * 4
+        _slib = L
+    return _slib
+
+
+class RefSolverScene:
+    """PdSolver in a direct mode as the reference runs it: solver 1 = CuSolverCholesky (CholeskySpLinearSolver<float>),
+    solver 2 = the same branch with PCGJacobiSolver<float> (warm start).  No fixed bodies."""
+
+    def __init__(self, X, Tet, mass, mu, solver, DBC=None, threads_per_block=128):
+        X = np.ascontiguousarray(X, np.float32); Tet = np.ascontiguousarray(Tet, np.uint32)
+        self.nV, self.nT = X.shape[0], Tet.shape[0]
+        mass = np.ascontiguousarray(np.broadcast_to(np.asarray(mass, np.float32), (self.nV,)))
+        mu = np.ascontiguousarray(np.broadcast_to(np.asarray(mu, np.float32), (self.nT,)))
+        dbc = None if DBC is None else np.ascontiguousarray(DBC, np.float32)
+        p = lambda a: None if a is None or a.size == 0 else a.ctypes.data
+        self._h = solvers_lib().refs_create(self.nV, self.nT, p(X), p(Tet), p(mass), p(mu), p(dbc), int(solver), threads_per_block)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            solvers_lib().refs_destroy(self._h)
+            self._h = None
+
+    def step(self, n=1, dt=1 / 60, gravity=9.8, tol=1e-4, num_iterations=10):
+        rc = solvers_lib().refs_step(self._h, np.float32(dt), gravity, tol, num_iterations, n)
+        if rc:
+            raise RuntimeError(f"reference solver harness CUDA error {rc}")
+
+    def stats(self):
+        it, err = C.c_int(), C.c_float()
+        solvers_lib().refs_stats(self._h, C.byref(it), C.byref(err))
+        return it.value, err.value
+
+    def get(self):
+        X = np.zeros((self.nV, 3), np.float32); V = np.zeros_like(X); XT = np.zeros_like(X)
+        solvers_lib().refs_get(self._h, X.ctypes.data, V.ctypes.data, XT.ctypes.data)
+        return X, V, XT
+
+    def set(self, X=None, V=None, XTilde=None):
+        c = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        X, V, XTilde = c(X), c(V), c(XTilde)
+        p = lambda a: None if a is None else a.ctypes.data
+        solvers_lib().refs_set(self._h, p(X), p(V), p(XTilde))
+        self._keep = (X, V, XTilde)
