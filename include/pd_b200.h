@@ -207,8 +207,8 @@ int pd_get_solve_stats(pd_engine*, float* err, int* pd_iterations_last_step);
  * vertex kernel over `reps` back-to-back launches, CUDA events on the engine's stream */
 int pd_time_kernels(pd_engine*, int reps, float* local_ms, float* vertex_ms);
 /* measurement helper: clock64 totals per phase of the local kernel, 8 x u64 per CTA (local_grid CTAs):
- * [loop top + barrier 3, wait part C, phase C, gather wait + barrier 1, wait part AB, record loads + barrier 2,
- *  phase B math + H stores, tiles processed] */
+ * [phase B, record fetch + gather wait, barrier, gather issue + producer + table loads, wait part C, phase C,
+ *  unused, tiles processed] */
 int pd_profile_local(pd_engine*, unsigned long long* out);
 int pd_engine_info(const pd_engine*, int* num_verts, int* num_tets, int* num_tiles, uint32_t* num_slots,
                    size_t* tile_stream_bytes, size_t* device_bytes, int* local_grid);

@@ -25,7 +25,8 @@ constexpr uint32_t TILE_ZERO_OFF = 4u * TILE_HSTRIDE;    // byte offset of the a
 constexpr uint32_t TILE_OWNER_BIT = 0x80000000u;         // vlist flag: this slot is the vertex's first (owner) slot
 
 // One packed tile record = two parts, each moved to shared memory by ONE
-// bulk copy (TMA).  Part AB (phases A and B of the local kernel, double buffered):
+// Part AB (what phase B of the local kernel reads: header and group table on the host side only, the tet records
+// straight from global memory):
 //   +0    TileHeader                                                          32 B
 //   +32   group table u32[16]: rowBase | nRows << 16 of each TILE_GROUP-vertex group     64 B
 //   +96   tet records, 48 B (12 words) each: f32 B[9] (DmInv, row-major), f32 w = |V0|*mu, u32 c01, u32 c23 --
@@ -41,8 +42,8 @@ constexpr uint32_t TILE_OWNER_BIT = 0x80000000u;         // vlist flag: this slo
 // Slots are PADDED per tile: slot = tile * TILE_NLMAX + tile-local vertex, so that the local kernel needs no
 // per-tile offset to find them; entry = u32 global (renumbered) vertex id | TILE_OWNER_BIT, or 0xffffffff for
 // the unused tail; tile-local vertices ordered by (in-tile incidence count descending, id ascending).  The
-// local kernel reads it with plain coalesced loads two tiles ahead of use (it feeds the position gather,
-// which runs one tile ahead).  Unused slots of the partial-sum array are never read or written.
+// position gather of the local kernel reads the same entries indexed by STAGING slot (Layout::vstage) with plain
+// coalesced loads three tiles ahead of use.  Unused slots of the partial-sum array are never read or written.
 // Part C (phase C, double buffered): the tile-local incidence lists, transposed per group of TILE_GROUP
 // vertices.  TILE_GROUP 32: row r of group g holds, for each of the 32 lanes (vertices), entries 2r and 2r+1 of
 // that vertex's list packed as two u16 in one u32.  TILE_GROUP 16: a vertex is summed by TWO lanes of a warp

@@ -50,7 +50,7 @@ struct WindowLayout {
 struct Engine::Impl {
     // tile stream
     uint8_t* records = nullptr;
-    uint32_t* tileTab = nullptr;      // per tile TILE_META_WORDS words: record offset (lo, hi), part AB bytes, part C bytes, 8 per-warp words
+    uint32_t* tileTab = nullptr;      // device tile table, TILE_META_WORDS words per tile (layout.hpp:build_tile_table)
     uint32_t *vslotPtr = nullptr, *vslot = nullptr, *vlist = nullptr, *vstage = nullptr;
     float4* P = nullptr;             // one partial RHS sum per (tile, tile-local vertex) slot
     // per-vertex state (renumbered, padded float4)

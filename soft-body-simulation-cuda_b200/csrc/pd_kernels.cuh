@@ -82,11 +82,13 @@ __device__ __forceinline__ float4 ldg_hint(const float4* p, unsigned long long p
 
 // ------------------------------------------------------------------ multi-GPU halo exchange
 // Every rank owns an exchange window [q0 | q1 | q2 | flags[world] | epoch | ticket | status] that its
-// neighbours map (CUDA IPC, or plain pointers inside one process).  After each phase that produces new
-// positions (predictor, every PD iteration) the owner PUSHES the positions of its boundary vertices straight
-// into the neighbours' ghost entries over NVLink (k_halo_push) and then raises its flag there to its push
-// count (epoch).  The consumer is the next local kernel: before touching any position it waits until every
-// neighbour's flag has reached its own epoch -- all ranks push the same number of times in the same order.
+// neighbours map (CUDA IPC, or plain pointers inside one process).  Every phase that produced new positions
+// (predictor, every PD iteration) is followed by a PUSH of the owner's boundary vertices straight into the
+// neighbours' ghost entries over NVLink, after which the owner raises its flag there to its push count (epoch).
+// The push rides at the start of the local kernel that consumes those positions (below; k_halo_push is the
+// stand-alone form for the PCG path and the lock-step test driver).  The consumer is that same local kernel on the
+// other side: before the gather of its first boundary tile it waits until every neighbour's flag has reached its own
+// epoch -- all ranks push the same number of times in the same order.
 struct DistWait {
     const unsigned long long* flags;   // this rank's flag array, written by the peers (indexed by rank)
     unsigned long long* epoch;         // this rank's own push count
