@@ -18,6 +18,8 @@
  *   every Update : pd_set_params (CopyUIToParams runs before every Update, simulationContext.cpp:85)
  *       -> pd_update_device(engine, 1, data.X, data.V, data.XTilde): AoS glm::vec3 import, one PD step, AoS export,
  *       all on the engine's stream, synchronised on return (the renderer and BVH read data.X next).
+ *       While data.mouseSelection.dragging: pd_set_drag_device(data.moreDBC, data.OffsetX, mouseSelection.target) first.
+ *       (data.DBCX is not written back: nothing but the PD solver itself reads it.)
  * The fixed bodies are passed as plain structs; B200_FIXED_BODY_FROM shows how to fill one from a FixedBody*.
  */
 #pragma once
@@ -87,6 +89,7 @@ public:
         Solver<float>::Reset();
         for (auto& kv : performanceData) kv.second = 0.f;
         if (engine_) { pd_destroy(engine_); engine_ = nullptr; }
+        dragSeen_ = false;
     }
 
 protected:
@@ -127,6 +130,17 @@ protected:
             p.handle_collision = 0;
         }
         pd_set_perf(engine_, perf ? 1 : 0);
+        /* mouse drag (README "PD solver supports interactive object dragging"): while MouseSelection::dragging the
+         * caller's Control_Kernel keeps SolverData::moreDBC / OffsetX up to date (simulationContext.cu:202-231) and
+         * RayIntersect the target (:196); when dragging ends main.cpp zeroes moreDBC (ResetMoreDBC(true), main.cpp:95-114).
+         * PdSolver reads all three in every SolverStep (pdSolver.cu:156-157,171,194,206). */
+        const bool drag = d.mouseSelection.dragging && d.moreDBC && d.OffsetX;
+        if (drag || dragSeen_) {
+            const int rc = drag ? pd_set_drag_device(engine_, d.moreDBC, &d.OffsetX[0].x, &d.mouseSelection.target.x)
+                                : pd_set_drag_device(engine_, nullptr, nullptr, nullptr);
+            if (rc != PD_OK) { std::fprintf(stderr, "B200PdSolver: %s\n", pd_last_error()); return false; }
+            dragSeen_ = drag;
+        }
         if (pd_set_params(engine_, &p) != PD_OK || pd_update_device(engine_, 1, &d.X[0].x, &d.V[0].x, &d.XTilde[0].x) != PD_OK) {
             std::fprintf(stderr, "B200PdSolver: %s\n", pd_last_error());
             return false;
@@ -156,4 +170,5 @@ private:
     pd_engine* engine_ = nullptr;
     int solverType_ = PD_JACOBI;
     int device_ = 0;
+    bool dragSeen_ = false;
 };

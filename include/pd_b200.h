@@ -194,6 +194,20 @@ int pd_dist_owned_ids(const pd_engine*, uint32_t* original_ids /* num_owned */);
  * numbering): import -> n steps -> export, all on the engine's stream, then synchronise.
  * This is what B200PdSolver::Update calls (include/b200_pd_solver.h). */
 int pd_update_device(pd_engine*, int n_steps, float* dX, float* dV, float* dXTilde);
+/* Mouse-drag soft constraints: SolverData<float>::moreDBC[num_verts] / OffsetX[3*num_verts] (def.h:31-32) and
+ * MouseSelection::target (def.h:14-18), written by Control_Kernel between two Updates (simulationContext.cu:202-231)
+ * and consumed by PdSolver at pdUtil.cu:56-69,80-87,159-164,187-188,201-206: a vertex with moreDBC > 0 is held at
+ * target + OffsetX for the whole step with zero velocity, and its massDt_2s becomes (m + moreDBC)/dt^2.
+ * Original vertex numbering.  more_dbc NULL (or no positive entry) ends the drag (ResetMoreDBC(true)); pd_reset clears
+ * it like SimulationCUDAContext::Reset (simulationContext.cu:240).  Single-GPU engines only (PD_ERR_UNSUPPORTED else). */
+int pd_set_drag(pd_engine*, const float* more_dbc, const float* offset_x, const float target[3]);
+/* the same from the reference's DEVICE arrays (what B200PdSolver::Update passes while mouseSelection.dragging) */
+int pd_set_drag_device(pd_engine*, const float* d_more_dbc, const float* d_offset_x, const float target[3]);
+/* Control_Kernel itself (simulationContext.cu:202-218: RADIUS_SQUARED 0.002, control_mag 10 at :229) on the engine's
+ * current X: select_v = -1 clears; for headless callers that have no SimulationCUDAContext */
+int pd_drag_select(pd_engine*, int select_v, float control_mag, const float target[3]);
+/* parity checks: the engine's moreDBC / OffsetX / DBCX (computeSn overwrites DBCX of dragged vertices, pdUtil.cu:86) */
+int pd_get_drag(pd_engine*, float* more_dbc, float* offset_x, float* dbcx, int* active);
 /* setup products for parity checks (original numbering): matrix_diag, massDt_2s, DmInv(9/tet,row-major), V0 */
 int pd_get_setup(pd_engine*, float* matrix_diag, float* mass_dt2, float* DmInv, float* V0);
 /* the scalar system matrix A^ = M/h^2 + sum_t w_t S^T (DmInv^T G)^T (DmInv^T G) S that SolverPrepare assembles as COO

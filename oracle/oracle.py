@@ -70,6 +70,9 @@ def lib():
         L.o_scene_get_setup.argtypes = [C.c_void_p, C.POINTER(Params), f32p, f32p, f32p, f32p]
         L.o_scene_system_matrix.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p]
         L.o_scene_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.o_scene_set_drag.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.o_scene_drag_select.argtypes = [C.c_void_p, C.c_int, C.c_float, f32p]
+        L.o_scene_get_drag.argtypes = [C.c_void_p, f32p, f32p, f32p]
         _LIB = L
     return _LIB
 
@@ -195,6 +198,25 @@ class Scene:
         rp = np.zeros(self.nV + 1, np.int32); col = np.zeros(nnz, np.int32); val = np.zeros(nnz, np.float32)
         lib().o_scene_system_matrix(self._h, C.byref(params), rp.ctypes.data, col.ctypes.data, val.ctypes.data)
         return rp, col, val
+
+    def set_drag(self, more_dbc=None, offset_x=None, target=(0.0, 0.0, 0.0)):
+        """SolverData::moreDBC / OffsetX / mouseSelection.target; more_dbc None clears (ResetMoreDBC(true))."""
+        if more_dbc is None:
+            lib().o_scene_set_drag(self._h, None, None, None)
+            return
+        m = np.ascontiguousarray(more_dbc, np.float32).reshape(self.nV)
+        o = np.ascontiguousarray(offset_x, np.float32).reshape(self.nV, 3)
+        t = np.ascontiguousarray(target, np.float32).reshape(3)
+        lib().o_scene_set_drag(self._h, m.ctypes.data, o.ctypes.data, t.ctypes.data)
+
+    def drag_select(self, select_v, target, control_mag=10.0):
+        """Control_Kernel (simulationContext.cu:202-218) on the current X."""
+        lib().o_scene_drag_select(self._h, int(select_v), float(control_mag), np.ascontiguousarray(target, np.float32).reshape(3))
+
+    def get_drag(self):
+        m = np.zeros(self.nV, np.float32); o = np.zeros((self.nV, 3), np.float32); d = np.zeros((self.nV, 3), np.float32)
+        lib().o_scene_get_drag(self._h, m, o.reshape(-1), d.reshape(-1))
+        return m, o, d
 
     def stats(self):
         a = C.c_int(); b = C.c_int()

@@ -464,6 +464,7 @@ struct o_scene {
     int nV, nT, numDBC;
     float *X, *X0, *XTilde, *V, *DBCX, *ExtForce;    /* 3 nV */
     float *mass, *DBC;                                 /* nV   */
+    float *moreDBC, *OffsetX; float drag_target[3];    /* mouse drag: def.h:31-32, MouseSelection::target def.h:14-18 */
     float *mu;                                         /* nT   */
     uint32_t *Tet;
     float *DmInv, *V0;                                 /* FEMSolver ctor products */
@@ -502,6 +503,7 @@ o_scene *o_scene_create(int nV, int nT, const float *X, const uint32_t *Tet, con
     s->DBCX = fdup(X, 3 * (size_t)nV);
     s->V = fdup(NULL, 3 * (size_t)nV); s->ExtForce = fdup(NULL, 3 * (size_t)nV);
     s->mass = fdup(mass, nV); s->DBC = fdup(DBC, nV); s->mu = fdup(mu, nT);
+    s->moreDBC = fdup(NULL, nV); s->OffsetX = fdup(NULL, 3 * (size_t)nV);   /* dataLoader.cu:305,316 (zero-filled) */
     for (int i = 0; i < nV; i++) if (s->DBC[i] > 0) s->numDBC++;
     s->Tet = (uint32_t *)malloc(sizeof(uint32_t) * 4 * (size_t)nT);
     memcpy(s->Tet, Tet, sizeof(uint32_t) * 4 * (size_t)nT);
@@ -546,6 +548,7 @@ void o_scene_destroy(o_scene *s)
 {
     if (!s) return;
     free(s->X); free(s->X0); free(s->XTilde); free(s->V); free(s->DBCX); free(s->ExtForce);
+    free(s->moreDBC); free(s->OffsetX);
     free(s->mass); free(s->DBC); free(s->mu); free(s->Tet); free(s->DmInv); free(s->V0);
     free(s->massDt_2s); free(s->matrix_diag); free(s->sn); free(s->sn_old); free(s->b);
     free(s->next_x); free(s->prev_x); free(s->H); free(s->inc_ptr); free(s->inc);
@@ -561,6 +564,7 @@ void o_scene_reset(o_scene *s)
     memcpy(s->X, s->X0, n * sizeof(float));
     memcpy(s->XTilde, s->X0, n * sizeof(float));
     memset(s->V, 0, n * sizeof(float));
+    memset(s->moreDBC, 0, (size_t)s->nV * sizeof(float));   /* simulationContext.cu:240 */
     for (size_t i = 0; i < n; i++) { s->Xd[i] = s->XTd[i] = s->X0[i]; s->Vd[i] = 0; }
     s->ready = 0;
 }
@@ -579,6 +583,42 @@ void o_scene_set(o_scene *s, const float *X, const float *V, const float *XTilde
     if (X) memcpy(s->X, X, n);
     if (V) memcpy(s->V, V, n);
     if (XTilde) memcpy(s->XTilde, XTilde, n);
+}
+
+/* Mouse-drag soft constraints.  The reference fills SolverData::moreDBC / OffsetX with Control_Kernel
+ * (simulationContext.cu:202-218) and MouseSelection::target in RayIntersect (:196); PdSolver consumes them at
+ * pdUtil.cu:56-69,80-87,159-164,187-188,201-206.  moreDBC == NULL clears the drag (ResetMoreDBC(true), :220-226). */
+void o_scene_set_drag(o_scene *s, const float *moreDBC, const float *OffsetX, const float target[3])
+{
+    if (!moreDBC) { memset(s->moreDBC, 0, (size_t)s->nV * sizeof(float)); return; }
+    memcpy(s->moreDBC, moreDBC, (size_t)s->nV * sizeof(float));
+    if (OffsetX) memcpy(s->OffsetX, OffsetX, 3 * (size_t)s->nV * sizeof(float));
+    if (target) memcpy(s->drag_target, target, 12);
+}
+
+/* Control_Kernel, simulationContext.cu:202-218 (RADIUS_SQUARED 0.002, :18; control_mag 10, :229), on the
+ * current X; then MouseSelection::target = `target`.  The SASS of the kernel fuses dot(diff, diff) like every
+ * other glm::dot here (FMUL y, FFMA x, FFMA z). */
+void o_scene_drag_select(o_scene *s, int select_v, float control_mag, const float target[3])
+{
+    for (int i = 0; i < s->nV; i++) {
+        float stiffness = 0.0f;
+        if (s->DBC[i] == 0 && select_v != -1) {
+            float d[3];
+            for (int k = 0; k < 3; k++) { d[k] = s->X[3 * i + k] - s->X[3 * select_v + k]; s->OffsetX[3 * i + k] = d[k]; }
+            float dist2 = DOT3_NV(d[0], d[0], d[1], d[1], d[2], d[2]);
+            if ((double)dist2 < 0.002) stiffness = control_mag;     /* RADIUS_SQUARED is a double literal: the comparison promotes dist2 */
+        }
+        s->moreDBC[i] = stiffness;
+    }
+    if (target) memcpy(s->drag_target, target, 12);
+}
+
+void o_scene_get_drag(const o_scene *s, float *moreDBC, float *OffsetX, float *DBCX)
+{
+    if (moreDBC) memcpy(moreDBC, s->moreDBC, (size_t)s->nV * sizeof(float));
+    if (OffsetX) memcpy(OffsetX, s->OffsetX, 3 * (size_t)s->nV * sizeof(float));
+    if (DBCX) memcpy(DBCX, s->DBCX, 3 * (size_t)s->nV * sizeof(float));
 }
 
 /* AiSi = transpose(DmInv) * G ; columns (pdUtil.cu:16).  col0 = -(r0+r1+r2), col k = row k-1 */
@@ -650,7 +690,8 @@ static void build_matrix(o_scene *s, const o_params *p)
                 e[base + k].c = (int)s->Tet[4 * t + j]; e[base + k].v = kji * coef; e[base + k].seq = k; k++;
             }
         }
-        e[base + k].c = v; e[base + k].v = s->massDt_2s[v]; e[base + k].seq = k; k++;
+        /* setMDt_2 at prepare time (pdUtil.cu:42-54): the assembled matrix never sees moreDBC or a later dt */
+        e[base + k].c = v; e[base + k].v = (s->mass[v] + s->DBC[v] * 1e6f) / (s->prepared_dt * s->prepared_dt); e[base + k].seq = k; k++;
         qsort(e + base, (size_t)k, sizeof(ent_t), ent_cmp);
         rowptr[v] = nnz;
         for (int a = 0; a < k;) {
@@ -741,8 +782,11 @@ static void local_step(o_scene *s, const o_params *p, int is_jacobi)
             const float *h = s->H + 3 * (size_t)s->inc[k];
             b0 += h[0]; b1 += h[1]; b2 += h[2];
         }
-        if (s->numDBC > 0 && s->DBC[v] > 0) {   /* computeDBCLocal pdUtil.cu:147-166 */
+        if (s->numDBC > 0 && s->DBC[v] > 0) {   /* computeDBCLocal pdUtil.cu:147-166 (launched only when numDBC > 0, pdSolver.cu:170) */
             b0 = s->DBCX[3 * v] * wdbc; b1 = s->DBCX[3 * v + 1] * wdbc; b2 = s->DBCX[3 * v + 2] * wdbc;
+        } else if (s->numDBC > 0 && s->moreDBC[v] > 0) {   /* pdUtil.cu:159-164: the weight is moreDBC itself, not moreDBC / h^2 */
+            float mw = s->moreDBC[v];
+            b0 = s->DBCX[3 * v] * mw; b1 = s->DBCX[3 * v + 1] * mw; b2 = s->DBCX[3 * v + 2] * mw;
         }
         s->b[3 * v] = b0; s->b[3 * v + 1] = b1; s->b[3 * v + 2] = b2;
     }
@@ -924,9 +968,16 @@ static int solver_step(o_scene *s, const o_params *p)
     for (int v = 0; v < nV; v++) {   /* gravity_force pdSolver.cu:14-18,154 */
         s->ExtForce[3 * v] = 0.0f; s->ExtForce[3 * v + 1] = -p->gravity * s->mass[v]; s->ExtForce[3 * v + 2] = 0.0f;
     }
-    for (int v = 0; v < nV; v++)     /* setMDt_2MoreDBC pdUtil.cu:56-69, moreDBC = 0 */
-        if (s->DBC[v] == 0) s->massDt_2s[v] = s->mass[v] / dt2;
+    for (int v = 0; v < nV; v++)     /* setMDt_2MoreDBC pdUtil.cu:56-69 */
+        if (s->DBC[v] == 0) {
+            float wi = s->moreDBC[v];
+            s->massDt_2s[v] = (wi > 0) ? (s->mass[v] + wi) / dt2 : s->mass[v] / dt2;
+        }
     for (int v = 0; v < nV; v++) {   /* computeSn pdUtil.cu:73-95 */
+        if (s->moreDBC[v] > 0) {     /* dragged vertex: sn = DBCX = target + OffsetX (pdUtil.cu:80-87) */
+            for (int k = 0; k < 3; k++) s->sn[3 * v + k] = s->DBCX[3 * v + k] = s->drag_target[k] + s->OffsetX[3 * v + k];
+            continue;
+        }
         float dt2_m_1 = 1.0f / s->massDt_2s[v];
         for (int k = 0; k < 3; k++)
             s->sn[3 * v + k] = fmaf(s->ExtForce[3 * v + k], dt2_m_1, fmaf(s->V[3 * v + k], dt, s->X[3 * v + k]));   /* computeSn SASS: 2 FFMA */
@@ -943,6 +994,10 @@ static int solver_step(o_scene *s, const o_params *p)
         if (jacobi) {
             for (int v = 0; v < nV; v++) {   /* getErrorKern pdUtil.cu:195-214 */
                 float c = s->massDt_2s[v], md = s->matrix_diag[v];
+                if (s->moreDBC[v] > 0) {     /* pdUtil.cu:201-206: a dragged vertex keeps sn */
+                    for (int k = 0; k < 3; k++) s->next_x[3 * v + k] = s->sn[3 * v + k];
+                    continue;
+                }
                 for (int k = 0; k < 3; k++)
                     s->next_x[3 * v + k] = fmaf(-c, s->sn[3 * v + k], s->b[3 * v + k]) / (c + md) + s->sn[3 * v + k];   /* FFMA(-c,q,b); IEEE div; FADD */
             }
@@ -972,7 +1027,7 @@ static int solver_step(o_scene *s, const o_params *p)
     for (int v = 0; v < nV; v++)   /* updateVelPos pdUtil.cu:180-193 */
         for (int k = 0; k < 3; k++) {
             float np = s->sn[3 * v + k];
-            s->V[3 * v + k] = (np - s->XTilde[3 * v + k]) * dtInv;
+            s->V[3 * v + k] = (s->moreDBC[v] > 0) ? 0.0f : (np - s->XTilde[3 * v + k]) * dtInv;   /* pdUtil.cu:187-190 */
             s->XTilde[3 * v + k] = np;
         }
     return 0;

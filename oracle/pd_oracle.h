@@ -81,6 +81,12 @@ int  o_scene_step(o_scene *, const o_params *, int n_steps);
 void o_scene_reset(o_scene *);
 void o_scene_get(const o_scene *, float *X, float *V, float *XTilde);
 void o_scene_set(o_scene *, const float *X, const float *V, const float *XTilde);
+/* mouse-drag soft constraints: SolverData::moreDBC[nV] / OffsetX[3nV] (def.h:31-32) and MouseSelection::target
+ * (def.h:14-18), consumed at pdUtil.cu:56-69,80-87,159-164,187-188,201-206.  moreDBC NULL clears the drag. */
+void o_scene_set_drag(o_scene *, const float *moreDBC, const float *OffsetX, const float target[3]);
+/* Control_Kernel (simulationContext.cu:202-218) on the current X, then target */
+void o_scene_drag_select(o_scene *, int select_v, float control_mag, const float target[3]);
+void o_scene_get_drag(const o_scene *, float *moreDBC, float *OffsetX, float *DBCX);
 /* setup products, for unit checks: matrix_diag[nV], massDt_2s[nV], DmInv[9nT], V0[nT] */
 void o_scene_get_setup(o_scene *, const o_params *, float *matrix_diag, float *massDt_2s,
                        float *DmInv, float *V0);

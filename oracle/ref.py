@@ -30,6 +30,9 @@ def lib():
         L.ref_get_setup.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 4
         L.ref_get_perf.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_rotation.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_set_drag.argtypes = [C.c_void_p] * 4
+        L.ref_drag_select.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p]
+        L.ref_get_drag.argtypes = [C.c_void_p] * 4
         _lib = L
     return _lib
 
@@ -73,6 +76,24 @@ class RefScene:
     def set(self, X=None, V=None, XTilde=None):
         a = [None if t is None else np.ascontiguousarray(t, np.float32) for t in (X, V, XTilde)]
         lib().ref_set(self._h, *[None if t is None else t.ctypes.data for t in a])
+
+    def set_drag(self, more_dbc=None, offset_x=None, target=(0.0, 0.0, 0.0)):
+        if more_dbc is None:
+            lib().ref_set_drag(self._h, None, None, None)
+            return
+        m = np.ascontiguousarray(more_dbc, np.float32).reshape(self.nV)
+        o = np.ascontiguousarray(offset_x, np.float32).reshape(self.nV, 3)
+        t = np.ascontiguousarray(target, np.float32).reshape(3)
+        lib().ref_set_drag(self._h, m.ctypes.data, o.ctypes.data, t.ctypes.data)
+
+    def drag_select(self, select_v, target, control_mag=10.0):
+        t = np.ascontiguousarray(target, np.float32).reshape(3)
+        lib().ref_drag_select(self._h, int(select_v), float(control_mag), t.ctypes.data)
+
+    def get_drag(self):
+        m = np.zeros(self.nV, np.float32); o = np.zeros((self.nV, 3), np.float32); d = np.zeros((self.nV, 3), np.float32)
+        lib().ref_get_drag(self._h, m.ctypes.data, o.ctypes.data, d.ctypes.data)
+        return m, o, d
 
     def setup(self, dt):
         md = np.zeros(self.nV, np.float32); c = np.zeros(self.nV, np.float32)

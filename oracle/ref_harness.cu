@@ -95,6 +95,23 @@ __global__ void refCylinder(glm::vec3* X, glm::vec3* V, int numVerts, const floa
     }
 }
 
+// Control_Kernel restated (simulationContext.cu:202-218; its TU needs OpenGL headers); RADIUS_SQUARED is the reference's
+// double literal (simulationContext.cu:18)
+#define RADIUS_SQUARED 0.002
+__global__ void refControl(glm::vec3* X, float* fixed, float* more_fixed, glm::vec3* offset_X, const float control_mag, const int number, const int select_v)
+{
+    int i = blockDim.x * blockIdx.x + threadIdx.x;
+    if (i >= number) return;
+    float stiffness = 0;
+    if (fixed[i] == 0 && select_v != -1) {
+        glm::vec3 diff = X[i] - X[select_v];
+        offset_X[i] = diff;
+        float dist2 = glm::dot(diff, diff);
+        if (dist2 < RADIUS_SQUARED) stiffness = control_mag;
+    }
+    more_fixed[i] = stiffness;
+}
+
 struct Ref {
     int nV = 0, nT = 0, numDBC = 0, tpb = 128;
     // SolverData<float>
@@ -105,6 +122,7 @@ struct Ref {
     // PdSolver private
     float *massDt_2s = nullptr, *sn = nullptr, *sn_old = nullptr, *b = nullptr, *matrix_diag = nullptr, *next_x = nullptr, *prev_x = nullptr;
     float omega = 1.f;
+    glm::vec3 target = glm::vec3(0.f);   // SolverData::mouseSelection.target (def.h:14-18)
     bool ready = false;
     // fixed bodies
     float *planes = nullptr, *spheres = nullptr, *cyls = nullptr;
@@ -154,7 +172,7 @@ void solver_step(Ref& r, float dt, float gravity, float rho, int numIterations, 
     thrust::transform(thrust::device_pointer_cast(r.mass), thrust::device_pointer_cast(r.mass) + r.nV,
                       thrust::device_pointer_cast(r.ExtForce), gravity_force(gravity));
     PdUtil::setMDt_2MoreDBC<<<vertBlocks, r.tpb>>>(r.nV, r.mass, dt * dt, r.massDt_2s, r.moreDBC, r.DBC);
-    PdUtil::computeSn<<<vertBlocks, r.tpb>>>(r.nV, r.sn, dt, r.massDt_2s, r.X, r.V, r.ExtForce, r.moreDBC, r.OffsetX, r.DBCX, glm::vec3(0.f));
+    PdUtil::computeSn<<<vertBlocks, r.tpb>>>(r.nV, r.sn, dt, r.massDt_2s, r.X, r.V, r.ExtForce, r.moreDBC, r.OffsetX, r.DBCX, r.target);
     cudaMemcpy(r.sn_old, r.sn, sizeof(float) * (r.nV * 3), cudaMemcpyDeviceToDevice);
     cudaMemcpy(r.prev_x, r.sn, sizeof(float) * (r.nV * 3), cudaMemcpyDeviceToDevice);
     for (int i = 0; i < numIterations; i++) {
@@ -250,6 +268,7 @@ void ref_reset(void* h)
     size_t v3 = sizeof(glm::vec3) * r.nV;
     cudaMemcpy(r.X, r.X0, v3, cudaMemcpyDeviceToDevice); cudaMemcpy(r.XTilde, r.X0, v3, cudaMemcpyDeviceToDevice);
     cudaMemset(r.V, 0, v3);
+    cudaMemset(r.moreDBC, 0, sizeof(float) * r.nV);
     r.ready = false;
     for (float& p : r.perf) p = 0;
 }
@@ -270,6 +289,31 @@ void ref_set(void* h, const float* X, const float* V, const float* XTilde)
     if (X) cudaMemcpy(r.X, X, v3, cudaMemcpyHostToDevice);
     if (V) cudaMemcpy(r.V, V, v3, cudaMemcpyHostToDevice);
     if (XTilde) cudaMemcpy(r.XTilde, XTilde, v3, cudaMemcpyHostToDevice);
+}
+
+// mouse drag: SolverData::moreDBC / OffsetX / mouseSelection.target as the caller's Control_Kernel would leave them;
+// moreDBC NULL = ResetMoreDBC(true) (simulationContext.cu:220-226)
+void ref_set_drag(void* h, const float* moreDBC, const float* OffsetX, const float* target)
+{
+    Ref& r = *(Ref*)h;
+    if (!moreDBC) { cudaMemset(r.moreDBC, 0, sizeof(float) * r.nV); return; }
+    cudaMemcpy(r.moreDBC, moreDBC, sizeof(float) * r.nV, cudaMemcpyHostToDevice);
+    if (OffsetX) cudaMemcpy(r.OffsetX, OffsetX, sizeof(glm::vec3) * r.nV, cudaMemcpyHostToDevice);
+    if (target) r.target = glm::vec3(target[0], target[1], target[2]);
+}
+// ResetMoreDBC(false) while dragging (simulationContext.cu:227-230) with the reference's launch shape, then the target
+void ref_drag_select(void* h, int select_v, float control_mag, const float* target)
+{
+    Ref& r = *(Ref*)h;
+    refControl<<<r.nV / r.tpb + 1, r.tpb>>>(r.X, r.DBC, r.moreDBC, r.OffsetX, control_mag, r.nV, select_v);
+    if (target) r.target = glm::vec3(target[0], target[1], target[2]);
+}
+void ref_get_drag(void* h, float* moreDBC, float* OffsetX, float* DBCX)
+{
+    Ref& r = *(Ref*)h;
+    if (moreDBC) cudaMemcpy(moreDBC, r.moreDBC, sizeof(float) * r.nV, cudaMemcpyDeviceToHost);
+    if (OffsetX) cudaMemcpy(OffsetX, r.OffsetX, sizeof(glm::vec3) * r.nV, cudaMemcpyDeviceToHost);
+    if (DBCX) cudaMemcpy(DBCX, r.DBCX, sizeof(glm::vec3) * r.nV, cudaMemcpyDeviceToHost);
 }
 
 void ref_get_setup(void* h, float dt, float* matrix_diag, float* massDt_2s, float* DmInv /*9/tet glm column-major*/, float* V0)

@@ -120,6 +120,10 @@ SYMBOLS = {
     "pd_step_host_owned": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "pd_dist_owned_ids": (_I, [_VP, _VP]),
     "pd_update_device": (_I, [_VP, _I, _VP, _VP, _VP]),
+    "pd_set_drag": (_I, [_VP, _VP, _VP, _VP]),
+    "pd_set_drag_device": (_I, [_VP, _VP, _VP, _VP]),
+    "pd_drag_select": (_I, [_VP, _I, _F, _VP]),
+    "pd_get_drag": (_I, [_VP, _VP, _VP, _VP, _PI]),
     "pd_get_setup": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "pd_get_system_matrix": (_I, [_VP, _PI, _VP, _VP, _VP]),
     "pd_get_solve_stats": (_I, [_VP, _PF, _PI]),
@@ -457,6 +461,32 @@ class PdSolver:
 
     def update_device_ptr(self, n, dX, dV, dXT):
         _check(lib().pd_update_device(self._h, n, dX, dV, dXT))
+
+    # --- mouse-drag soft constraints (SolverData::moreDBC / OffsetX / mouseSelection.target, def.h:14-18,31-32)
+    def set_drag(self, more_dbc=None, offset_x=None, target=(0.0, 0.0, 0.0)):
+        """more_dbc None ends the drag (SimulationCUDAContext::ResetMoreDBC(true), simulationContext.cu:220-226)."""
+        if more_dbc is None:
+            _check(lib().pd_set_drag(self._h, None, None, None))
+            return
+        m = np.ascontiguousarray(more_dbc, np.float32).reshape(self.num_verts)
+        o = np.ascontiguousarray(offset_x, np.float32).reshape(self.num_verts, 3)
+        t = np.ascontiguousarray(target, np.float32).reshape(3)
+        _check(lib().pd_set_drag(self._h, _p(m), _p(o), _p(t)))
+
+    def set_drag_device_ptr(self, d_more_dbc, d_offset_x, target):
+        t = np.ascontiguousarray(target, np.float32).reshape(3)
+        _check(lib().pd_set_drag_device(self._h, d_more_dbc, d_offset_x, _p(t)))
+
+    def drag_select(self, select_v, target, control_mag=10.0):
+        """Control_Kernel (simulationContext.cu:202-218) on the engine's current X; select_v = -1 clears."""
+        t = np.ascontiguousarray(target, np.float32).reshape(3)
+        _check(lib().pd_drag_select(self._h, int(select_v), float(control_mag), _p(t)))
+
+    def get_drag(self):
+        m = np.zeros(self.num_verts, np.float32); o = np.zeros((self.num_verts, 3), np.float32); d = np.zeros((self.num_verts, 3), np.float32)
+        a = C.c_int()
+        _check(lib().pd_get_drag(self._h, _p(m), _p(o), _p(d), C.byref(a)))
+        return m, o, d, bool(a.value)
 
     def setup(self):
         md = np.zeros(self.num_verts, np.float32); c = np.zeros(self.num_verts, np.float32)

@@ -438,6 +438,22 @@ int pd_update_device(pd_engine* e, int n, float* dX, float* dV, float* dXT)
     ENGINE_CALL(if (n < 0) return fail(PD_ERR_INVALID, "n_steps < 0");
                 e->e->importDevice(dX, dV, dXT); e->e->step(n); e->e->exportDevice(dX, dV, dXT); e->e->synchronize())
 }
+int pd_set_drag(pd_engine* e, const float* more, const float* off, const float* target)
+{
+    ENGINE_CALL(if (more && (!off || !target)) return fail(PD_ERR_INVALID, "offset_x and target are required with more_dbc"); e->e->setDrag(more, off, target))
+}
+int pd_set_drag_device(pd_engine* e, const float* dMore, const float* dOff, const float* target)
+{
+    ENGINE_CALL(if (dMore && (!dOff || !target)) return fail(PD_ERR_INVALID, "d_offset_x and target are required with d_more_dbc"); e->e->setDragDevice(dMore, dOff, target))
+}
+int pd_drag_select(pd_engine* e, int selectV, float controlMag, const float* target)
+{
+    ENGINE_CALL(if (!target) return fail(PD_ERR_INVALID, "target is NULL"); e->e->dragSelect(selectV, controlMag, target))
+}
+int pd_get_drag(pd_engine* e, float* more, float* off, float* dbcx, int* active)
+{
+    ENGINE_CALL(e->e->getDrag(more, off, dbcx); if (active) *active = e->e->dragActive() ? 1 : 0)
+}
 int pd_get_setup(pd_engine* e, float* md, float* mdt2, float* DmInv, float* V0) { ENGINE_CALL(e->e->getSetup(md, mdt2, DmInv, V0)) }
 int pd_get_system_matrix(pd_engine* e, int* nnz, int* rowptr, int* col, float* val)
 {

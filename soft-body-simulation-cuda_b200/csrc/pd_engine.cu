@@ -58,6 +58,10 @@ struct Engine::Impl {
     float4 *b0 = nullptr, *X = nullptr, *V = nullptr, *XT = nullptr, *X0 = nullptr;
     float2* cc = nullptr;
     float *mass = nullptr, *dbc = nullptr, *md = nullptr;
+    // mouse drag (allocated by the first setDrag*): moreDBC, OffsetX, a DBCX of its own (until then DBCX is X0) and the
+    // "some moreDBC > 0" flag
+    float* more = nullptr; float4* offX = nullptr; float4* dbcx = nullptr; int* dragFlag = nullptr;
+    DragArgs drag(const float t[3], int numDBC) const { return DragArgs{more, offX, dbcx, t[0], t[1], t[2], numDBC > 0 ? 1 : 0}; }
     uint32_t* oldOfNew = nullptr;
     float* stage3 = nullptr;          // 3 x (3 nV) floats, AoS staging for import/export
     float* fbData = nullptr;
@@ -172,6 +176,8 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     d.mass = dalloc<float>(nV_); d.dbc = dalloc<float>(nV_); d.md = dalloc<float>(nV_);
     d.oldOfNew = dalloc<uint32_t>(nV_);
     d.stage3 = dalloc<float>(9 * (size_t)scene_.numVerts);
+    d.dbcx = d.X0;                          // DBCX <- X0 (pdSolver.cu:134); a drag gives it storage of its own
+    for (float f : scene_.DBC) if (f > 0.f) ++numDBC_;
 
     CUDA_CHECK(cudaMemcpy(d.records, L_.records.data(), L_.records.size(), cudaMemcpyHostToDevice));
     static_assert(sizeof(TileEntry) == sizeof(uint4), "tile table entry layout");
@@ -275,6 +281,11 @@ void Engine::reset()
     CUDA_CHECK(cudaMemcpyAsync(d.X, d.X0, (size_t)nV_ * 16, cudaMemcpyDeviceToDevice, stream_));
     CUDA_CHECK(cudaMemcpyAsync(d.XT, d.X0, (size_t)nV_ * 16, cudaMemcpyDeviceToDevice, stream_));
     CUDA_CHECK(cudaMemsetAsync(d.V, 0, (size_t)nV_ * 16, stream_));
+    if (d.more) {       // cudaMemset(moreDBC, 0) (simulationContext.cu:240); the next SolverPrepare restores DBCX <- X0 (pdSolver.cu:134)
+        CUDA_CHECK(cudaMemsetAsync(d.more, 0, (size_t)nV_ * 4, stream_));
+        CUDA_CHECK(cudaMemcpyAsync(d.dbcx, d.X0, (size_t)nV_ * 16, cudaMemcpyDeviceToDevice, stream_));
+    }
+    dragActive_ = false;
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     ready_ = false;
     perfc_ = PerfCounters();
@@ -346,8 +357,12 @@ void Engine::enqueuePredict()
     const int vb = 256, vg = (nOwn_ + vb - 1) / vb;
     base_ = (opt_.world > 1) ? (int)(phase_ % 3) : 0;
     omega_ = 1.0f;
-    k_predict<<<vg, vb, 0, stream_>>>(nOwn_, d.X, d.V, d.mass, d.dbc, d.md, p.dt, dt2Prepared_, p.gravity,
-                                      d.q[base_], d.q[(base_ + 2) % 3], d.b0, d.cc);
+    if (dragActive_)
+        k_predict<true><<<vg, vb, 0, stream_>>>(nOwn_, d.X, d.V, d.mass, d.dbc, d.md, p.dt, dt2Prepared_, p.gravity,
+                                                d.q[base_], d.q[(base_ + 2) % 3], d.b0, d.cc, d.drag(dragTarget_, numDBC_));
+    else
+        k_predict<false><<<vg, vb, 0, stream_>>>(nOwn_, d.X, d.V, d.mass, d.dbc, d.md, p.dt, dt2Prepared_, p.gravity,
+                                                 d.q[base_], d.q[(base_ + 2) % 3], d.b0, d.cc, DragArgs{});
     if (lockstep_) enqueuePush(d.q[base_], base_);      // otherwise the first local kernel pushes its input itself
     ++phase_;
 }
@@ -374,8 +389,13 @@ void Engine::enqueueIteration(int i, bool timed, size_t* ev)
     if (i <= 10) omega_ = 1;
     else if (i == 11) omega_ = 2 / (2 - p.rho * p.rho);
     else omega_ = 4 / (4 - p.rho * p.rho * omega_);
-    if (opt_.rotMode == 1) launch_pdl(k_vertex_jacobi<false>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
-    else launch_pdl(k_vertex_jacobi<true>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
+    const float4* dbcx = d.dbcx;
+    if (dragActive_) {      // dragged vertices (cc.y < 0) keep their position (getErrorKern, pdUtil.cu:201-206)
+        if (opt_.rotMode == 1) k_vertex_jacobi<false, true><<<vg, vb, 0, stream_>>>(nOwn_, cur, prev, next, dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
+        else k_vertex_jacobi<true, true><<<vg, vb, 0, stream_>>>(nOwn_, cur, prev, next, dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
+    }
+    else if (opt_.rotMode == 1) launch_pdl(k_vertex_jacobi<false>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
+    else launch_pdl(k_vertex_jacobi<true>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
     if (lockstep_) enqueuePush(next, in);
     ++phase_;
     rec();
@@ -386,7 +406,8 @@ void Engine::enqueueFinish()
     Impl& d = *d_;
     const SolverParams& p = params_;
     const int vb = 256, vg = (nOwn_ + vb - 1) / vb;
-    k_finish<<<vg, vb, 0, stream_>>>(nOwn_, d.q[(base_ + p.numIterations) % 3], 1.0f / p.dt, d.X, d.XT, d.V, d.fb, p.muT, p.muN);
+    if (dragActive_) k_finish<true><<<vg, vb, 0, stream_>>>(nOwn_, d.q[(base_ + p.numIterations) % 3], 1.0f / p.dt, d.X, d.XT, d.V, d.fb, p.muT, p.muN, d.more);
+    else k_finish<false><<<vg, vb, 0, stream_>>>(nOwn_, d.q[(base_ + p.numIterations) % 3], 1.0f / p.dt, d.X, d.XT, d.V, d.fb, p.muT, p.muN, nullptr);
 }
 
 // multi-GPU: boundary positions of buffer `bufIndex` -> the neighbours' ghost entries, then the flags
@@ -406,7 +427,7 @@ void Engine::enqueueStep(bool timed)
 {
     Impl& d = *d_;
     size_t ev = 0;
-    pdlActive_ = usePdl_ && !timed;        // event records between the kernels (perf mode) want fully serialised launches
+    pdlActive_ = usePdl_ && !timed && !dragActive_;        // event records between the kernels (perf mode) want fully serialised launches
     enqueuePredict();
     for (int i = 0; i < params_.numIterations; ++i) enqueueIteration(i, timed, &ev);
     if (timed) CUDA_CHECK(cudaEventRecord(d.events[ev++], stream_));
@@ -468,7 +489,7 @@ void Engine::step(int nSteps)
             CUDA_CHECK(cudaEventElapsedTime(&c, d.events[ev], d.events[ev + 1]));
             perfc_.collisionFixed += c;
         }
-    } else if (opt_.useGraph) {
+    } else if (opt_.useGraph && !dragActive_) {     // (a drag moves its target every frame: plain launches)
         for (int s = 0; s < nSteps; ++s) {
             buildGraph();
             CUDA_CHECK(cudaGraphLaunch(d.graphExec[(opt_.world > 1) ? (int)(phase_ % 3) : 0], stream_));
@@ -487,7 +508,7 @@ float Engine::stepTimed(int nSteps)
 {
     CUDA_CHECK(cudaSetDevice(opt_.device));
     if (!ready_) prepare();
-    if (opt_.useGraph && !perf_) buildGraph();
+    if (opt_.useGraph && !perf_ && !dragActive_ && params_.globalSolver == 0) buildGraph();
     cudaEvent_t a, b;
     CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
@@ -600,6 +621,103 @@ void Engine::getSetup(float* matrixDiag, float* massDt2, float* DmInv, float* V0
     }
 }
 
+// ---------------------------------------------------------------- mouse-drag soft constraints
+// SolverData<float>::moreDBC / OffsetX / mouseSelection.target (def.h:14-18,31-32).  The reference fills them with
+// Control_Kernel (simulationContext.cu:202-218) between two Updates; PdSolver reads them at pdUtil.cu:56-69,80-87,
+// 159-164,187-188,201-206.  While some moreDBC is positive the step runs the DRAG instantiations of the per-vertex
+// kernels as plain launches; the local kernel does not change.
+void Engine::ensureDragBuffers()
+{
+    Impl& d = *d_;
+    if (opt_.world > 1) throw std::runtime_error("mouse-drag constraints on a partitioned mesh are outside the PD hot path (single-GPU engines only)");
+    if (d.more) return;
+    d.more = dalloc<float>(nV_); d.offX = dalloc<float4>(nV_); d.dbcx = dalloc<float4>(nV_); d.dragFlag = dalloc<int>(1);
+    graphValid_ = false;                    // the captured launches hold the old DBCX pointer (X0)
+    CUDA_CHECK(cudaMemsetAsync(d.more, 0, (size_t)nV_ * 4, stream_));
+    CUDA_CHECK(cudaMemsetAsync(d.offX, 0, (size_t)nV_ * 16, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(d.dbcx, d.X0, (size_t)nV_ * 16, cudaMemcpyDeviceToDevice, stream_));
+}
+
+void Engine::finishDragUpdate(const float target[3])
+{   // the stream has just written `more` and or-ed the flag
+    int any = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&any, d_->dragFlag, 4, cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    CUDA_CHECK(cudaGetLastError());
+    dragActive_ = any != 0;
+    if (target) std::memcpy(dragTarget_, target, 12);
+}
+
+void Engine::setDrag(const float* more, const float* offsetX, const float target[3])
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    Impl& d = *d_;
+    if (!more) {                              // ResetMoreDBC(true)
+        if (d.more) CUDA_CHECK(cudaMemsetAsync(d.more, 0, (size_t)nV_ * 4, stream_));
+        dragActive_ = false;
+        return;
+    }
+    ensureDragBuffers();
+    const size_t nG = (size_t)scene_.numVerts;
+    const int vb = 256, vg = (nV_ + vb - 1) / vb;
+    float *so = d.stage3, *sm = d.stage3 + 3 * nG;
+    CUDA_CHECK(cudaMemsetAsync(d.dragFlag, 0, 4, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(sm, more, nG * 4, cudaMemcpyHostToDevice, stream_));
+    k_import1<<<vg, vb, 0, stream_>>>(nV_, sm, d.oldOfNew, d.more, d.dragFlag);
+    if (offsetX) {
+        CUDA_CHECK(cudaMemcpyAsync(so, offsetX, nG * 12, cudaMemcpyHostToDevice, stream_));
+        k_import3<<<vg, vb, 0, stream_>>>(nV_, so, d.oldOfNew, d.offX);
+    }
+    finishDragUpdate(target);
+}
+
+void Engine::setDragDevice(const float* dMore, const float* dOffsetX, const float target[3])
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    Impl& d = *d_;
+    if (!dMore) { setDrag(nullptr, nullptr, nullptr); return; }
+    ensureDragBuffers();
+    const int vb = 256, vg = (nV_ + vb - 1) / vb;
+    CUDA_CHECK(cudaMemsetAsync(d.dragFlag, 0, 4, stream_));
+    k_import1<<<vg, vb, 0, stream_>>>(nV_, dMore, d.oldOfNew, d.more, d.dragFlag);
+    if (dOffsetX) k_import3<<<vg, vb, 0, stream_>>>(nV_, dOffsetX, d.oldOfNew, d.offX);
+    finishDragUpdate(target);
+}
+
+void Engine::dragSelect(int selectV, float controlMag, const float target[3])
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    Impl& d = *d_;
+    if (selectV < -1 || selectV >= scene_.numVerts) throw std::runtime_error("dragSelect: vertex index out of range");
+    ensureDragBuffers();
+    int sel = -1;
+    if (selectV >= 0) sel = (int)L_.vertNewOfOld[(size_t)selectV];
+    const int vb = 256, vg = (nV_ + vb - 1) / vb;
+    CUDA_CHECK(cudaMemsetAsync(d.dragFlag, 0, 4, stream_));
+    k_drag_select<<<vg, vb, 0, stream_>>>(nV_, d.X, d.dbc, sel, controlMag, d.more, d.offX, d.dragFlag);
+    finishDragUpdate(target);
+}
+
+void Engine::getDrag(float* more, float* offsetX, float* dbcx)
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    Impl& d = *d_;
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    std::vector<float> m((size_t)nV_, 0.f);
+    std::vector<float4> o((size_t)nV_, make_float4(0.f, 0.f, 0.f, 0.f)), x((size_t)nV_);
+    if (d.more) {
+        CUDA_CHECK(cudaMemcpy(m.data(), d.more, (size_t)nV_ * 4, cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(o.data(), d.offX, (size_t)nV_ * 16, cudaMemcpyDeviceToHost));
+    }
+    CUDA_CHECK(cudaMemcpy(x.data(), d.dbcx, (size_t)nV_ * 16, cudaMemcpyDeviceToHost));
+    for (int v = 0; v < nV_; ++v) {
+        const size_t g = L_.vertOrder[(size_t)v];
+        if (more) more[g] = m[(size_t)v];
+        if (offsetX) { offsetX[3 * g] = o[(size_t)v].x; offsetX[3 * g + 1] = o[(size_t)v].y; offsetX[3 * g + 2] = o[(size_t)v].z; }
+        if (dbcx) { dbcx[3 * g] = x[(size_t)v].x; dbcx[3 * g + 1] = x[(size_t)v].y; dbcx[3 * g + 2] = x[(size_t)v].z; }
+    }
+}
+
 // ---------------------------------------------------------------- kernel timing helpers (bench)
 float Engine::timeLocalKernelMs(int reps)
 {
@@ -632,12 +750,12 @@ float Engine::timeVertexKernelMs(int reps)
     cudaEvent_t a, b;
     CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
     // a valid so4/cc is needed: run the predictor once
-    k_predict<<<vg, vb, 0, stream_>>>(nOwn_, d.X, d.V, d.mass, d.dbc, d.md, params_.dt, dt2Prepared_, params_.gravity,
-                                      d.q[0], d.q[2], d.b0, d.cc);
+    k_predict<false><<<vg, vb, 0, stream_>>>(nOwn_, d.X, d.V, d.mass, d.dbc, d.md, params_.dt, dt2Prepared_, params_.gravity,
+                                             d.q[0], d.q[2], d.b0, d.cc, DragArgs{});
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     CUDA_CHECK(cudaEventRecord(a, stream_));
     for (int r = 0; r < reps; ++r)
-        k_vertex_jacobi<true><<<vg, vb, 0, stream_>>>(nOwn_, d.q[0], d.q[2], d.q[1], d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, 1.0f, 1.0f);
+        k_vertex_jacobi<true><<<vg, vb, 0, stream_>>>(nOwn_, d.q[0], d.q[2], d.q[1], d.dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, 1.0f, 1.0f);
     CUDA_CHECK(cudaEventRecord(b, stream_));
     CUDA_CHECK(cudaEventSynchronize(b));
     float ms = 0;
@@ -747,7 +865,9 @@ void Engine::enqueueStepSolver()
     const float wdbc = 1e6f * (dtInv * dtInv);
     const bool dist = opt_.world > 1;
     pdlActive_ = false;                     // cooperative solve kernels in between: plain, fully serialised launches
-    k_predict<<<vg, vb, 0, stream_>>>(n, d.X, d.V, d.mass, d.dbc, d.md, p.dt, dt2Prepared_, p.gravity, d.q[0], d.q[2], d.b0, d.cc);
+    const DragArgs dr = dragActive_ ? d.drag(dragTarget_, numDBC_) : DragArgs{};
+    if (dragActive_) k_predict<true><<<vg, vb, 0, stream_>>>(n, d.X, d.V, d.mass, d.dbc, d.md, p.dt, dt2Prepared_, p.gravity, d.q[0], d.q[2], d.b0, d.cc, dr);
+    else k_predict<false><<<vg, vb, 0, stream_>>>(n, d.X, d.V, d.mass, d.dbc, d.md, p.dt, dt2Prepared_, p.gravity, d.q[0], d.q[2], d.b0, d.cc, dr);
     enqueuePush(d.q[0], 0);
     CUDA_CHECK(cudaMemsetAsync(d.xprev, 0, (size_t)n * 16, stream_));        // cudaMemset(prev_x, 0, ...), pdSolver.cu:162
     k_solve_begin<<<1, 1, 0, stream_>>>(d.solveState);
@@ -756,8 +876,12 @@ void Engine::enqueueStepSolver()
                              d.peerP, d.peerPFlag, d.pflags, d.peerRed, d.red, d.solveSeq, d.status};
     for (int i = 0; i < p.numIterations; ++i) {
         launchLocal(d.q[0], false);
-        if (opt_.rotMode == 1) k_vertex_rhs<false><<<vg, vb, 0, stream_>>>(n, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, wdbc, d.rhs);
-        else k_vertex_rhs<true><<<vg, vb, 0, stream_>>>(n, d.X0, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, wdbc, d.rhs);
+        if (dragActive_) {
+            if (opt_.rotMode == 1) k_vertex_rhs<false, true><<<vg, vb, 0, stream_>>>(n, d.dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, wdbc, d.rhs, dr);
+            else k_vertex_rhs<true, true><<<vg, vb, 0, stream_>>>(n, d.dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, wdbc, d.rhs, dr);
+        }
+        else if (opt_.rotMode == 1) k_vertex_rhs<false><<<vg, vb, 0, stream_>>>(n, d.dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, wdbc, d.rhs, dr);
+        else k_vertex_rhs<true><<<vg, vb, 0, stream_>>>(n, d.dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, wdbc, d.rhs, dr);
         if (p.globalSolver == 2) {
             const float4* b = d.rhs; float4 *x = d.q[0], *r = d.cgR, *pp = d.cgP, *qq = d.cgQ, *xp = d.xprev;
             int maxIter = p.pcgMaxIter; float cgTol = p.pcgTol, pdTol = p.tol;
@@ -774,7 +898,8 @@ void Engine::enqueueStepSolver()
             CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(d.solveGrid), dim3(SOLVE_THREADS), args, 0, stream_));
         }
     }
-    k_finish<<<vg, vb, 0, stream_>>>(n, d.q[0], dtInv, d.X, d.XT, d.V, d.fb, p.muT, p.muN);
+    if (dragActive_) k_finish<true><<<vg, vb, 0, stream_>>>(n, d.q[0], dtInv, d.X, d.XT, d.V, d.fb, p.muT, p.muN, d.more);
+    else k_finish<false><<<vg, vb, 0, stream_>>>(n, d.q[0], dtInv, d.X, d.XT, d.V, d.fb, p.muT, p.muN, nullptr);
     pdlActive_ = usePdl_;
 }
 

@@ -55,6 +55,15 @@ public:
     void stepHostOwned(int nSteps, const float* Xin, const float* Vin, const float* XTin, float* Xout, float* Vout, float* XTout);
     void ownedIds(uint32_t* out) const;                     // original vertex id of each owned vertex, local order
 
+    // ---- mouse-drag soft constraints: SolverData<float>::moreDBC / OffsetX / mouseSelection.target (def.h:14-18,31-32),
+    // consumed at pdUtil.cu:56-69,80-87,159-164,187-188,201-206.  Arrays in the reference's layout and ORIGINAL vertex
+    // numbering; more == nullptr (or no positive entry) ends the drag (ResetMoreDBC(true), simulationContext.cu:220-226).
+    void setDrag(const float* more, const float* offsetX, const float target[3]);                 // host arrays
+    void setDragDevice(const float* dMore, const float* dOffsetX, const float target[3]);         // the reference's device arrays
+    void dragSelect(int selectV, float controlMag, const float target[3]);                        // Control_Kernel on the engine's X (simulationContext.cu:202-218)
+    void getDrag(float* more, float* offsetX, float* dbcx);                                       // host, original numbering (parity checks)
+    bool dragActive() const { return dragActive_; }
+
     const PerfCounters& perf() const { return perfc_; }
     void syncSolveStats();                                  // PCG / Cholesky modes: fold the device-side iteration counters in
     float lastError() const { return lastErr_; }
@@ -99,6 +108,8 @@ private:
     void enqueuePush(const float4* q, int bufIndex);
     void setPeers(const std::vector<uint8_t*>& peerBase);
     float* qbuf(int k) const;
+    void ensureDragBuffers();
+    void finishDragUpdate(const float target[3]);
     void launchLocal(const float4* q, bool jacobi, unsigned long long* prof = nullptr, int pushBuf = -1);
     template <typename T> T* dalloc(size_t n);
 
@@ -120,6 +131,9 @@ private:
     bool usePdl_ = false;     // programmatic dependent launch of the per-iteration kernels (pd_kernels.cuh: pdl_wait); measured SLOWER
                               // on B200 (grid139: 42.0 vs 36.9 ms/step, batch64: 2.68 vs 2.23), so it stays an opt-in experiment (PD_PDL=1)
     float dt2Prepared_ = 0.f;
+    bool dragActive_ = false;             // some vertex has moreDBC > 0: the DRAG kernel variants run, as plain launches (the target moves every frame)
+    float dragTarget_[3] = {0.f, 0.f, 0.f};
+    int numDBC_ = 0;                      // SolverData::numDBC
     PerfCounters perfc_;
     int localGrid_ = 0, numSms_ = 0;
     size_t devBytes_ = 0;

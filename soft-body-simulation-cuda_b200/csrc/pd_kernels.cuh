@@ -153,36 +153,62 @@ __global__ void k_halo_push(int n, const uint32_t* __restrict__ src, const uint3
     }
 }
 
+// ------------------------------------------------------------------ mouse-drag soft constraints
+// SolverData<float>::moreDBC / OffsetX and MouseSelection::target (def.h:14-18,31-32), filled by Control_Kernel
+// (simulationContext.cu:202-218) and consumed by five PdUtil kernels (pdUtil.cu:56-69,80-87,159-164,187-188,201-206).
+// The per-vertex kernels below exist in two instantiations: DRAG = false is the headless path (moreDBC == 0
+// everywhere, no extra loads), DRAG = true restates the reference's branches.  A dragged vertex is marked for the
+// vertex kernel by a NEGATIVE cc.y (c + matrix_diag is positive otherwise).
+struct DragArgs {
+    const float* more;      // moreDBC per vertex (renumbered ids)
+    const float4* offX;     // OffsetX
+    float4* dbcx;           // DBCX: computeSn overwrites it with the drag target of every dragged vertex (pdUtil.cu:86)
+    float tx, ty, tz;       // MouseSelection::target
+    int hasDBC;             // SolverData::numDBC > 0: computeDBCLocal is launched at all (pdSolver.cu:170)
+};
+
 // ------------------------------------------------------------------ predictor
 // gravity transform + setMDt_2MoreDBC + computeSn + the two D2D copies + addM_h2Sn
-// (pdSolver.cu:154-160, pdUtil.cu:56-95,168-179).  moreDBC == 0 (no mouse drag on the headless path).
+// (pdSolver.cu:154-160, pdUtil.cu:56-95,168-179).
 // Writes q0 = prev = s, b0 = c * s_old (what addM_h2Sn recomputes every iteration; constant over
 // a step), cc = (+-c, c + matrix_diag) with a NEGATIVE c marking a pinned (DBC) vertex.
 // Arithmetic forms follow the reference's SASS: s = fma(f, 1/c, fma(v, dt, x)).
+template <bool DRAG>
 __global__ void k_predict(int nV, const float4* __restrict__ X, const float4* __restrict__ V,
                           const float* __restrict__ mass, const float* __restrict__ dbc,
                           const float* __restrict__ md, float dt, float dt2Prepared, float gravity,
                           float4* __restrict__ q0, float4* __restrict__ qprev, float4* __restrict__ b0,
-                          float2* __restrict__ cc)
+                          float2* __restrict__ cc, DragArgs dr)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nV) return;
     const float m = mass[v], isDbc = dbc[v];
     const float dt2 = __fmul_rn(dt, dt);
-    // DBC vertices keep the massDt_2s computed by setMDt_2 at prepare time (pdUtil.cu:48,59)
-    const float c = (isDbc == 0.f) ? __fdiv_rn(m, dt2) : __fdiv_rn(__fadd_rn(m, __fmul_rn(isDbc, 1e6f)), dt2Prepared);
-    const float4 x = X[v], vel = V[v];
-    const float fy = __fmul_rn(-gravity, m);
-    const float dt2_m_1 = __fdiv_rn(1.0f, c);
+    const float wi = DRAG ? dr.more[v] : 0.f;
+    // DBC vertices keep the massDt_2s computed by setMDt_2 at prepare time (pdUtil.cu:48,59); the others get
+    // (m + moreDBC) / dt^2 while they are dragged (pdUtil.cu:61-67)
+    const float c = (isDbc == 0.f) ? __fdiv_rn((DRAG && wi > 0.f) ? __fadd_rn(m, wi) : m, dt2)
+                                   : __fdiv_rn(__fadd_rn(m, __fmul_rn(isDbc, 1e6f)), dt2Prepared);
     float4 s;
-    s.x = __fmaf_rn(0.0f, dt2_m_1, __fmaf_rn(vel.x, dt, x.x));
-    s.y = __fmaf_rn(fy, dt2_m_1, __fmaf_rn(vel.y, dt, x.y));
-    s.z = __fmaf_rn(0.0f, dt2_m_1, __fmaf_rn(vel.z, dt, x.z));
-    s.w = 0.f;
+    if (DRAG && wi > 0.f) {
+        // computeSn, pdUtil.cu:80-87: sn = DBCX = target + OffsetX (whatever DBC says)
+        const float4 o = dr.offX[v];
+        s = make_float4(__fadd_rn(dr.tx, o.x), __fadd_rn(dr.ty, o.y), __fadd_rn(dr.tz, o.z), 0.f);
+        dr.dbcx[v] = s;
+    } else {
+        const float4 x = X[v], vel = V[v];
+        const float fy = __fmul_rn(-gravity, m);
+        const float dt2_m_1 = __fdiv_rn(1.0f, c);
+        s.x = __fmaf_rn(0.0f, dt2_m_1, __fmaf_rn(vel.x, dt, x.x));
+        s.y = __fmaf_rn(fy, dt2_m_1, __fmaf_rn(vel.y, dt, x.y));
+        s.z = __fmaf_rn(0.0f, dt2_m_1, __fmaf_rn(vel.z, dt, x.z));
+        s.w = 0.f;
+    }
     q0[v] = s;
     qprev[v] = s;
     b0[v] = make_float4(__fmul_rn(c, s.x), __fmul_rn(c, s.y), __fmul_rn(c, s.z), 0.f);
-    cc[v] = make_float2(isDbc > 0.f ? -c : c, __fadd_rn(c, md[v]));
+    const float den = __fadd_rn(c, md[v]);
+    cc[v] = make_float2(isDbc > 0.f ? -c : c, (DRAG && wi > 0.f) ? -den : den);
 }
 
 // ------------------------------------------------------------------ local step (the hot kernel)
@@ -614,10 +640,11 @@ __device__ __forceinline__ void vertex_slot_sum(int v, const float4* __restrict_
     }
 }
 
-template <bool BASE>       // BASE: the slots hold the elastic terms only and b0 is added here (product default);
-                           // otherwise the vertex's first slot already starts from b0 (faithful mode)
+template <bool BASE, bool DRAG = false>    // BASE: the slots hold the elastic terms only and b0 is added here (product default);
+                           // otherwise the vertex's first slot already starts from b0 (faithful mode).
+                           // DRAG: a vertex with cc.y < 0 is being dragged and keeps its position (getErrorKern, pdUtil.cu:201-206)
 __global__ void __launch_bounds__(256, PD_VERTEX_MINBLOCKS) k_vertex_jacobi(int nV, const float4* __restrict__ qcur, const float4* __restrict__ qprev,
-                                float4* __restrict__ qnext, const float4* __restrict__ X0, const float4* __restrict__ b0,
+                                float4* __restrict__ qnext, const float4* __restrict__ X0 /* DBCX */, const float4* __restrict__ b0,
                                 const float2* __restrict__ cc, const uint32_t* __restrict__ vslotPtr,
                                 const uint32_t* __restrict__ vslot, const float4* __restrict__ P,
                                 float omega, float wdbc)
@@ -636,10 +663,11 @@ __global__ void __launch_bounds__(256, PD_VERTEX_MINBLOCKS) k_vertex_jacobi(int 
             vertex_slot_sum<BASE>(v, b0, vslotPtr, vslot, P, bx, by, bz);
         }
         const float4 q = qcur[v], pr = qprev[v];
-        const float den = c2.y;
+        const float den = DRAG ? fabsf(c2.y) : c2.y;
         float nx = __fadd_rn(__fdiv_rn(__fmaf_rn(-c, q.x, bx), den), q.x);
         float ny = __fadd_rn(__fdiv_rn(__fmaf_rn(-c, q.y, by), den), q.y);
         float nz = __fadd_rn(__fdiv_rn(__fmaf_rn(-c, q.z, bz), den), q.z);
+        if (DRAG && c2.y < 0.f) { nx = q.x; ny = q.y; nz = q.z; }      // next_x = sn for a dragged vertex, then chebyshevKern as usual
         // under-relaxation in double, as the reference's `0.9 *` literal (pdUtil.cu:221)
         nx = (float)__fma_rn((double)__fsub_rn(nx, q.x), 0.9, (double)q.x);
         ny = (float)__fma_rn((double)__fsub_rn(ny, q.y), 0.9, (double)q.y);
@@ -653,17 +681,23 @@ __global__ void __launch_bounds__(256, PD_VERTEX_MINBLOCKS) k_vertex_jacobi(int 
 }
 
 // right-hand side for the direct / CG global solves: b = c*s_old + sum of partials (R, not R-F)
-template <bool BASE>
-__global__ void k_vertex_rhs(int nV, const float4* __restrict__ X0, const float4* __restrict__ b0, const float2* __restrict__ cc,
+template <bool BASE, bool DRAG = false>
+__global__ void k_vertex_rhs(int nV, const float4* __restrict__ X0 /* DBCX */, const float4* __restrict__ b0, const float2* __restrict__ cc,
                              const uint32_t* __restrict__ vslotPtr, const uint32_t* __restrict__ vslot,
-                             const float4* __restrict__ P, float wdbc, float4* __restrict__ rhs)
+                             const float4* __restrict__ P, float wdbc, float4* __restrict__ rhs, DragArgs dr)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nV) return;
     float bx, by, bz;
-    if (cc[v].x < 0.f) {
+    const float2 c2 = cc[v];
+    if (c2.x < 0.f) {
         const float4 d = X0[v];
         bx = __fmul_rn(d.x, wdbc); by = __fmul_rn(d.y, wdbc); bz = __fmul_rn(d.z, wdbc);
+    } else if (DRAG && c2.y < 0.f && dr.hasDBC) {
+        // computeDBCLocal's second branch (pdUtil.cu:159-164; the kernel runs only when numDBC > 0): b = DBCX * moreDBC
+        const float4 d = X0[v];
+        const float mw = dr.more[v];
+        bx = __fmul_rn(d.x, mw); by = __fmul_rn(d.y, mw); bz = __fmul_rn(d.z, mw);
     } else {
         vertex_slot_sum<BASE>(v, b0, vslotPtr, vslot, P, bx, by, bz);
     }
@@ -690,13 +724,16 @@ __device__ __forceinline__ void fb_respond(float3& vel, const float3 n, float kf
     vel.z = __fmaf_rn(vT.z, a, -__fmul_rn(vN.z, muN));
 }
 
+template <bool DRAG>
 __global__ void k_finish(int nV, const float4* __restrict__ qfinal, float dtInv, float4* __restrict__ X,
-                         float4* __restrict__ XTilde, float4* __restrict__ V, DevFixedBodies fb, float muT, float muN)
+                         float4* __restrict__ XTilde, float4* __restrict__ V, DevFixedBodies fb, float muT, float muN,
+                         const float* __restrict__ more)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nV) return;
     const float4 q = qfinal[v], xt = XTilde[v];
     float3 vel = make_float3(__fmul_rn(__fsub_rn(q.x, xt.x), dtInv), __fmul_rn(__fsub_rn(q.y, xt.y), dtInv), __fmul_rn(__fsub_rn(q.z, xt.z), dtInv));
+    if (DRAG && more[v] > 0.f) vel = make_float3(0.f, 0.f, 0.f);      // updateVelPos, pdUtil.cu:187-188
     float3 x = make_float3(q.x, q.y, q.z);
     X[v] = make_float4(x.x, x.y, x.z, 0.f);      // X keeps the un-projected position
     const float kf = __fmul_rn(__fadd_rn(muN, 1.f), muT);
@@ -759,6 +796,33 @@ __global__ void k_export3(int nV, const float4* __restrict__ src, const uint32_t
     const float4 s = src[v];
     float* d = dst3 + 3ull * (oldOfNew ? oldOfNew[v] : (uint32_t)v);
     d[0] = s.x; d[1] = s.y; d[2] = s.z;
+}
+
+// scalar per-vertex array (reference numbering) -> renumbered; *anyPositive |= (value > 0)
+__global__ void k_import1(int nV, const float* __restrict__ src, const uint32_t* __restrict__ oldOfNew, float* __restrict__ dst, int* __restrict__ anyPositive)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nV) return;
+    const float a = src[oldOfNew ? oldOfNew[v] : (uint32_t)v];
+    dst[v] = a;
+    if (a > 0.f) atomicOr(anyPositive, 1);
+}
+// Control_Kernel (simulationContext.cu:202-218; RADIUS_SQUARED 0.002 is a double literal, :18): vertices within the
+// radius of the selected one (sel, renumbered id) get stiffness controlMag, and every free vertex its offset
+__global__ void k_drag_select(int nV, const float4* __restrict__ X, const float* __restrict__ dbc, int sel, float controlMag,
+                              float* __restrict__ more, float4* __restrict__ offX, int* __restrict__ anyPositive)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nV) return;
+    float stiffness = 0.f;
+    if (dbc[v] == 0.f && sel >= 0) {
+        const float4 a = X[v], b = X[sel];
+        const float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
+        offX[v] = make_float4(dx, dy, dz, 0.f);
+        if ((double)dot3_nv(dx, dx, dy, dy, dz, dz) < 0.002) stiffness = controlMag;
+    }
+    more[v] = stiffness;
+    if (stiffness > 0.f) atomicOr(anyPositive, 1);
 }
 
 // ------------------------------------------------------------------ test hook

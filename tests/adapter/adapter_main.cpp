@@ -43,6 +43,18 @@ int main(int argc, char** argv)
     if (!eng) { std::fprintf(stderr, "%s\n", pd_last_error()); return 2; }
     std::vector<float> X1(X.size()), V1(X.size()), T1(X.size());
     if (pd_step(eng, steps) || pd_download(eng, X1.data(), V1.data(), T1.data())) { std::fprintf(stderr, "%s\n", pd_last_error()); return 2; }
+    // ... then two more steps with a mouse drag (a handful of vertices held at target + offset), through pd_set_drag
+    std::vector<float> more(nV, 0.f), off(3 * (size_t)nV, 0.f);
+    const int pick = nV / 2;
+    const float target[3] = {X1[3 * pick] + 0.4f, X1[3 * pick + 1] + 0.3f, X1[3 * pick + 2]};
+    int nDrag = 0;
+    for (int i = 0; i < nV; ++i) {
+        float d2 = 0;
+        for (int k = 0; k < 3; ++k) { off[3 * i + k] = X1[3 * i + k] - X1[3 * pick + k]; d2 += off[3 * i + k] * off[3 * i + k]; }
+        if (d2 < 1.5f) { more[i] = 10.f; ++nDrag; }
+    }
+    std::vector<float> X1d(X.size()), V1d(X.size()), T1d(X.size());
+    if (pd_set_drag(eng, more.data(), off.data(), target) || pd_step(eng, 2) || pd_download(eng, X1d.data(), V1d.data(), T1d.data())) { std::fprintf(stderr, "%s\n", pd_last_error()); return 2; }
     pd_destroy(eng);
     pd_scene_free(sc);
 
@@ -76,6 +88,33 @@ int main(int argc, char** argv)
         worst = std::fmax(worst, std::fabs((double)T1[i] - T2[i]));
         moved = std::fmax(moved, std::fabs((double)X2[i] - X[i]));
     }
+    // the same drag through SolverData (what Control_Kernel / RayIntersect leave there, simulationContext.cu:177-231)
+    CK(cudaMalloc((void**)&d.moreDBC, 4 * (size_t)nV)); CK(cudaMalloc((void**)&d.OffsetX, 12 * (size_t)nV));
+    CK(cudaMemcpy(d.moreDBC, more.data(), 4 * (size_t)nV, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d.OffsetX, off.data(), 12 * (size_t)nV, cudaMemcpyHostToDevice));
+    d.mouseSelection.dragging = true; d.mouseSelection.select_v = pick; d.mouseSelection.target = glm::vec3(target[0], target[1], target[2]);
+    for (int s = 0; s < 2; ++s) solver->Update(d, params);
+    CK(cudaMemcpy(X2.data(), d.X, 12 * (size_t)nV, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(V2.data(), d.V, 12 * (size_t)nV, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(T2.data(), d.XTilde, 12 * (size_t)nV, cudaMemcpyDeviceToHost));
+    double worstDrag = 0, held = 0;
+    for (size_t i = 0; i < X.size(); ++i) {
+        worstDrag = std::fmax(worstDrag, std::fabs((double)X1d[i] - X2[i]));
+        worstDrag = std::fmax(worstDrag, std::fabs((double)V1d[i] - V2[i]));
+        worstDrag = std::fmax(worstDrag, std::fabs((double)T1d[i] - T2[i]));
+    }
+    for (int i = 0; i < nV; ++i)
+        if (more[i] > 0.f)
+            for (int k = 0; k < 3; ++k) held = std::fmax(held, std::fabs((double)X2[3 * i + k] - (double)(target[k] + off[3 * i + k])) + std::fabs((double)V2[3 * i + k]));
+    std::printf("drag: %d vertices held, max_abs_diff %.9g, distance of the held vertices from target+offset %.9g\n", nDrag, worstDrag, held);
+    // release (main.cpp:95-99: SetDragging(false) + ResetMoreDBC(true)) and one more Update: must run, nothing held any more
+    d.mouseSelection.dragging = false;
+    CK(cudaMemset(d.moreDBC, 0, 4 * (size_t)nV));
+    solver->Update(d, params);
+    CK(cudaMemcpy(V2.data(), d.V, 12 * (size_t)nV, cudaMemcpyDeviceToHost));
+    double vfree = 0;
+    for (int i = 0; i < nV; ++i) if (more[i] > 0.f) vfree = std::fmax(vfree, std::fabs((double)V2[3 * i + 1]));
+    std::printf("release: |V.y| of a formerly held vertex %.4f\n", vfree);
+    worst = std::fmax(worst, worstDrag);
+    if (held != 0.0 || nDrag == 0 || !(vfree > 0.0)) worst = std::fmax(worst, 1.0);
     const auto& perf = solver->GetPerformanceData();
     std::printf("nV %d nT %d steps %d moved %.4f perf[%s]=%.3f ms perf[%s]=%.3f ms\n", nV, nT, steps, moved, perf[0].first.c_str(), perf[0].second,
                 perf[1].first.c_str(), perf[1].second);

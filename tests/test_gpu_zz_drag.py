@@ -1,0 +1,209 @@
+"""GPU parity of the mouse-drag soft constraints (SolverData::moreDBC / OffsetX / mouseSelection.target, def.h:14-18,31-32;
+pdUtil.cu:56-69,80-87,159-164,187-188,201-206; Control_Kernel simulationContext.cu:202-218) through the C ABI
+(pd_set_drag / pd_drag_select / pd_get_drag) against the CPU oracle and, when the prebuilt harness travelled with the
+snapshot, against the reference's own kernels (oracle/_ref).  Also runs the reference-side adapter binary
+(include/b200_pd_solver.h compiled against the reference's def.h / solver.h, tests/adapter/adapter_main.cpp).
+
+This file sorts after the other GPU suites on purpose: it was written in a session without GPU time, so its first run is
+the round-end driver's; `-x` then cannot hide the established suites behind it.
+
+Bars: the held vertices are BIT-EXACT (position = target + OffsetX as one float add, velocity = 0); everything else
+max relative vertex error <= 1e-4 in faithful mode (rot_mode=1) and <= 1e-3 in the default mode vs the oracle (the default
+mode's bound is uncalibrated for the strongly sheared tets next to a dragged patch; the measured value is printed)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import meshes
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _oracle_params(O, p, **kw):
+    d = dict(dt=p["dt"], gravity=p["gravity"], muN=p["muN"], muT=p["muT"], rho=p["rho"], tol=p["tol"],
+             num_iterations=p["num_iterations"], threads=8)
+    d.update(kw)
+    return O.make_params(**d)
+
+
+def _ball(X, v, r):
+    off = (X - X[v]).astype(np.float32)
+    more = np.where((off.astype(np.float64) ** 2).sum(1) < r * r, np.float32(10.0), np.float32(0.0)).astype(np.float32)
+    return more, off
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("rot_mode,tol", [(1, 1e-4), (0, 1e-3)])
+def test_drag_hold_move_release_vs_oracle(pd, O, assets, rot_mode, tol):
+    """house + sphere in free fall: 2 free steps, 6 steps with a ball of vertices dragged along a moving target, 3 steps
+    after the release."""
+    name = "C5 house&sphere"
+    sc = pd.Scene.from_json(assets["json"], name)
+    p = sc.params
+    p["num_iterations"] = 50
+    sc.params = p
+    osc, _ = meshes.oracle_scene(O, assets, name)
+    op = _oracle_params(O, p)
+    eng = pd.PdSolver(sc, rot_mode=rot_mode)
+    scale = float(np.linalg.norm(osc.X0.max(0) - osc.X0.min(0)))
+    eng.Update(2); osc.step(op, 2)
+    X = osc.get()[0]
+    pick = 17
+    more, off = _ball(X, pick, 8.0)
+    held = more > 0
+    assert 1 < held.sum() < sc.counts()[0] // 2
+    worst = 0.0
+    for k in range(6):
+        target = (X[pick] + np.float32([0.4 * (k + 1), 0.2 * (k + 1), 0.0])).astype(np.float32)
+        eng.set_drag(more, off, target); osc.set_drag(more, off, target)
+        eng.Update(1); osc.step(op, 1)
+        Xe, Ve, XTe = eng.download()
+        Xo, Vo, XTo = osc.get()
+        want = (target[None, :] + off[held]).astype(np.float32)
+        assert np.array_equal(_bits(XTe[held]), _bits(want)) and np.array_equal(_bits(Xe[held]), _bits(want)), f"drag step {k}"
+        assert not Ve[held].any()
+        m, o, dbcx, active = eng.get_drag()
+        assert active and np.array_equal(m, more) and np.array_equal(_bits(o), _bits(off))
+        assert np.array_equal(_bits(dbcx[held]), _bits(want))                    # computeSn overwrites DBCX (pdUtil.cu:86)
+        assert np.array_equal(_bits(dbcx[~held]), _bits(sc.arrays()["X"][~held]))
+        worst = max(worst, meshes.rel_err(Xe, Xo, scale), meshes.rel_err(XTe, XTo, scale))
+    eng.set_drag(None); osc.set_drag(None)
+    assert not eng.get_drag()[3]
+    eng.Update(3); osc.step(op, 3)
+    Xe, Ve, XTe = eng.download()
+    Xo, Vo, XTo = osc.get()
+    worst = max(worst, meshes.rel_err(Xe, Xo, scale), meshes.rel_err(XTe, XTo, scale))
+    print(f"drag on {name} rot_mode={rot_mode}: worst rel err vs oracle {worst:.3e} ({int(held.sum())} held vertices)")
+    assert np.isfinite(Xe).all() and np.abs(Ve[held, 1]).min() > 0                # falling again
+    assert worst <= tol, worst
+
+
+def test_zero_more_dbc_is_the_plain_step_bit_for_bit(pd, assets):
+    """moreDBC == 0 everywhere must take the headless kernels: same bits as an engine that never heard of a drag."""
+    sc = pd.Scene.from_json(assets["json"], "C5 house&sphere")
+    a, b = pd.PdSolver(sc), pd.PdSolver(sc)
+    n = sc.counts()[0]
+    b.set_drag(np.zeros(n, np.float32), np.ones((n, 3), np.float32), (1.0, 2.0, 3.0))
+    assert not b.get_drag()[3]
+    a.Update(3); b.Update(3)
+    for x, y in zip(a.download(), b.download()):
+        assert np.array_equal(_bits(x), _bits(y))
+
+
+def test_control_kernel_and_reset_vs_oracle(pd, O, assets):
+    """pd_drag_select = Control_Kernel on the engine's X.  Faithful mode on the cube is bit-exact vs the oracle, so the
+    offsets are too; then one held step, and Reset clears the drag (simulationContext.cu:240)."""
+    sc = pd.Scene.from_json(assets["json"], "C1 cube")
+    p = sc.params
+    p["dt"] = 1 / 60
+    sc.params = p
+    osc, _ = meshes.oracle_scene(O, assets, "C1 cube")
+    op = _oracle_params(O, p)
+    eng = pd.PdSolver(sc, rot_mode=1, reorder=0)
+    eng.Update(2); osc.step(op, 2)
+    target = np.float32([0.5, 31.0, 0.25])
+    eng.drag_select(3, target); osc.drag_select(3, target)
+    me, oe, _, active = eng.get_drag()
+    mo, oo, _ = osc.get_drag()
+    assert active and np.array_equal(me, mo) and np.array_equal(_bits(oe), _bits(oo)) and me[3] == np.float32(10.0)
+    eng.Update(2); osc.step(op, 2)
+    for x, y in zip(eng.download(), osc.get()):
+        assert np.array_equal(_bits(x), _bits(y))
+    assert np.array_equal(eng.download()[2][3], target)
+    eng.drag_select(-1, target)
+    assert not eng.get_drag()[3] and not eng.get_drag()[0].any()
+    eng.drag_select(3, target)
+    eng.Reset(); osc.reset()
+    assert not eng.get_drag()[3] and not eng.get_drag()[0].any()
+    eng.Update(2); osc.step(op, 2)
+    for x, y in zip(eng.download(), osc.get()):
+        assert np.array_equal(_bits(x), _bits(y))
+
+
+def test_drag_in_the_pcg_branch_vs_oracle(pd, O):
+    """Direct / CG modes: the drag enters b0 = (m + w)/h^2 s and zeroes the held velocities; the prefactored matrix does not
+    change (pdSolver.cu:62-77 runs once), so the vertices are pulled, not pinned.  Same grid and solver parameters as
+    tests/test_gpu_solvers.py::test_solver_modes_vs_oracle."""
+    from test_gpu_solvers import _grid, _oracle_of
+    sc = _grid(pd)
+    kw = dict(dt=1 / 60, gravity=9.8, num_iterations=8, tol=1e-6)
+    sc.params = pd.SolverParams(global_solver=2, pcg_max_iter=60, pcg_tol=1e-5, **kw)
+    eng = pd.PdSolver(sc)
+    osc = _oracle_of(O, sc)
+    op = O.make_params(global_solver=2, pcg_max_iter=60, pcg_tol=1e-5, **kw)
+    eng.Update(1); osc.step(op, 1)
+    X = osc.get()[0]
+    pick = X.shape[0] // 2
+    more, off = _ball(X, pick, 1.2)
+    held = more > 0
+    assert 1 < held.sum() < 40
+    target = (X[pick] + np.float32([0.2, 0.1, 0.0])).astype(np.float32)
+    eng.set_drag(more, off, target); osc.set_drag(more, off, target)
+    worst = 0.0
+    for s in range(3):
+        eng.Update(1); osc.step(op, 1)
+        Xe, Ve, _ = eng.download()
+        worst = max(worst, meshes.rel_err(Xe, osc.get()[0]))
+        assert not Ve[held].any()
+    print(f"drag, PCG branch: worst rel err vs oracle over 3 steps {worst:.3e} ({int(held.sum())} held vertices)")
+    assert worst <= 1e-4, worst
+
+
+def test_drag_vs_reference_kernels(pd, O, assets):
+    """The same drag through the reference's own kernels (setMDt_2MoreDBC, computeSn, getErrorKern, updateVelPos compiled
+    verbatim, oracle/_ref): held vertices identical, the rest within 10x the reference's own run-to-run spread or 1e-4."""
+    import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libpd_ref.so was not built (no /root/reference at build time)")
+    name = "C5 house&sphere"
+    sc = pd.Scene.from_json(assets["json"], name)
+    p = sc.params
+    p["num_iterations"] = 50
+    sc.params = p
+    from test_gpu_parity import _ref_scene, _ref_kw
+    kw = _ref_kw(p)
+    refs = [_ref_scene(pd, sc) for _ in range(2)]
+    X0 = sc.arrays()["X"]
+    eng = pd.PdSolver(sc, rot_mode=1)
+    scale = float(np.linalg.norm(X0.max(0) - X0.min(0)))
+    eng.Update(2)
+    for r in refs:
+        r.step(2, **kw)
+    X = refs[0].get()[0]
+    more, off = _ball(X, 17, 8.0)
+    held = more > 0
+    worst = spread = 0.0
+    for k in range(6):
+        target = (X[17] + np.float32([0.4 * (k + 1), 0.2 * (k + 1), 0.0])).astype(np.float32)
+        eng.set_drag(more, off, target); eng.Update(1)
+        for r in refs:
+            r.set_drag(more, off, target); r.step(1, **kw)
+        Xe, Ve, XTe = eng.download()
+        Xr, Vr, XTr = refs[0].get()
+        assert np.array_equal(_bits(XTe[held]), _bits(XTr[held])) and not Vr[held].any() and not Ve[held].any()
+        assert np.array_equal(_bits(eng.get_drag()[2][held]), _bits(refs[0].get_drag()[2][held]))     # DBCX
+        worst = max(worst, meshes.rel_err(XTe, XTr, scale))
+        spread = max(spread, meshes.rel_err(refs[1].get()[2], XTr, scale))
+    print(f"drag vs reference kernels: worst rel err {worst:.3e}, reference run-to-run spread {spread:.3e}")
+    assert worst <= max(1e-4, 10 * spread), (worst, spread)
+
+
+def test_reference_side_adapter_binary(pd):
+    """include/b200_pd_solver.h compiled against the reference's own def.h / solver.h (make -C oracle adapter) and driven
+    like SimulationCUDAContext drives PdSolver, mouse drag included: identical (max_abs_diff 0) to the plain C ABI."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "adapter_test")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/adapter_test was not built (no /root/reference at build time)")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = env.get("LD_LIBRARY_PATH", "") + ":/usr/local/cuda/lib64"
+    r = subprocess.run([exe, "6", "3"], capture_output=True, text=True, timeout=300, env=env)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "max_abs_diff 0" in r.stdout
