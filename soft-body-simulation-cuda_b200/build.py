@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.environ.get("PD_OUT", os.path.join(HERE, "libpd_b200.so"))      # PD_OUT / PD_DEFS: experiment variants only
 DEFS = os.environ.get("PD_DEFS", "").split()
+RUNNER = os.path.join(HERE, "pd_run")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = os.environ.get("PD_HOSTCXX", "/usr/bin/g++")
 
@@ -29,7 +30,7 @@ def _newest_src():
 
 
 def build(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_src():
+    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_src() and (DEFS or os.path.exists(RUNNER)):
         return OUT
     objdir = os.path.join(HERE, "build" if not DEFS else "build_" + "_".join(d.strip("-D").replace("=", "") for d in DEFS))
     os.makedirs(objdir, exist_ok=True)
@@ -47,6 +48,13 @@ def build(force=False, verbose=False):
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    if not DEFS:
+        # the headless C++ host driver over the C ABI (csrc/pd_run.cpp): plain g++, no CUDA headers, finds the library next to itself
+        cmd = [HOSTCXX, "-std=c++17", "-O2", "-Wall", os.path.join(CSRC, "pd_run.cpp"), "-o", RUNNER, "-L" + os.path.dirname(OUT),
+               "-l:" + os.path.basename(OUT), "-Wl,-rpath,$ORIGIN"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
     return OUT
 
 
