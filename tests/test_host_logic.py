@@ -253,3 +253,29 @@ def test_bad_meshes_are_rejected(pd):
     for Xe, Te in [(np.zeros((3, 3), np.float32), np.zeros((0, 4), np.uint32)), (np.zeros((0, 3), np.float32), np.zeros((0, 4), np.uint32))]:
         with pytest.raises(pd.PdError):                                                          # empty meshes: an error code, not a crash
             pd.Scene.from_arrays(Xe, Te, 1.0, 1e5)
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(tmp_path, pd):
+    """The drop-in boundary is a C ABI: include/pd_b200.h must compile as C99 (no C++, no torch, no CUDA types), and a C
+    program must link against the library and reach the host-only entry points (no GPU needed)."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "pd_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '  pd_params p; pd_default_params(&p);\n'
+                   '  const float o[3] = {0.f, 1.f, 0.f};\n'
+                   '  pd_scene* s = pd_scene_kuhn_grid(2, 2, 2, 1.0f, 0.0f, 1u, o, 1.0f, 1000.0f);\n'
+                   '  int nv = 0, nt = 0; if (!s || pd_scene_counts(s, &nv, &nt, 0, 0) != PD_OK) return 1;\n'
+                   '  pd_engine* e = pd_create(s, 0);            /* no GPU here: must fail loudly, not fall back */\n'
+                   '  printf("%d %d %d %s|%s\\n", nv, nt, p.num_iterations, pd_version(), e ? "engine" : pd_last_error());\n'
+                   '  if (e) pd_destroy(e);\n'
+                   '  pd_scene_free(s); return 0; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(pd.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe),
+                           "-L", libdir, "-l:" + os.path.basename(pd.LIB_PATH), "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    nv, nt, its = out.split()[:3]
+    assert (int(nv), int(nt)) == (27, 48) and int(its) >= 1
+    assert out.strip().endswith("|engine") or "CUDA" in out          # on a box without a GPU: "no CUDA device: ... no CPU fallback"
