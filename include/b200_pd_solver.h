@@ -71,6 +71,13 @@ public:
     B200PdSolver& operator=(const B200PdSolver&) = delete;
 
     void SetGlobalSolver(SolverType val) { solverType_ = static_cast<int>(val); }
+    /* Call after SimulationCUDAContext::UpdateSoftBodyAttr has refilled SolverData::mu (simulationContext.cu:165-176): PdSolver
+     * reads data.mu inside computeLocal every iteration, the engine keeps |V0|*mu in its tile stream.  Like the reference,
+     * matrix_diag and the assembled matrix follow only after Reset(). */
+    void MuChanged(const SolverData<float>& solverData)
+    {
+        if (engine_ && solverData.mu && pd_update_mu_device(engine_, solverData.mu) != PD_OK) std::fprintf(stderr, "B200PdSolver: %s\n", pd_last_error());
+    }
     /* number of PD iterations per Update; the reference keeps it in SolverParams::numIterations */
 
     void Update(SolverData<float>& solverData, const SolverParams<float>& solverParams) override

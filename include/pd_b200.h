@@ -208,6 +208,12 @@ int pd_set_drag_device(pd_engine*, const float* d_more_dbc, const float* d_offse
 int pd_drag_select(pd_engine*, int select_v, float control_mag, const float target[3]);
 /* parity checks: the engine's moreDBC / OffsetX / DBCX (computeSn overwrites DBCX of dragged vertices, pdUtil.cu:86) */
 int pd_get_drag(pd_engine*, float* more_dbc, float* offset_x, float* dbcx, int* active);
+/* Live stiffness edit: SolverData<float>::mu[num_tets] changed (SimulationCUDAContext::UpdateSoftBodyAttr -> FillData,
+ * simulationContext.cu:165-176; original tet order).  As in the reference the new mu acts from the next Update on
+ * (computeLocal reads it every iteration, pdUtil.cu:97,124) while matrix_diag and the assembled system matrix stay
+ * SolverPrepare products: they follow only after pd_reset (pdSolver.cu:212-216). */
+int pd_update_mu(pd_engine*, const float* mu);
+int pd_update_mu_device(pd_engine*, const float* d_mu);
 /* setup products for parity checks (original numbering): matrix_diag, massDt_2s, DmInv(9/tet,row-major), V0 */
 int pd_get_setup(pd_engine*, float* matrix_diag, float* mass_dt2, float* DmInv, float* V0);
 /* the scalar system matrix A^ = M/h^2 + sum_t w_t S^T (DmInv^T G)^T (DmInv^T G) S that SolverPrepare assembles as COO

@@ -73,6 +73,7 @@ def lib():
         L.o_scene_set_drag.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.o_scene_drag_select.argtypes = [C.c_void_p, C.c_int, C.c_float, f32p]
         L.o_scene_get_drag.argtypes = [C.c_void_p, f32p, f32p, f32p]
+        L.o_scene_set_mu.argtypes = [C.c_void_p, f32p]
         _LIB = L
     return _LIB
 
@@ -212,6 +213,9 @@ class Scene:
     def drag_select(self, select_v, target, control_mag=10.0):
         """Control_Kernel (simulationContext.cu:202-218) on the current X."""
         lib().o_scene_drag_select(self._h, int(select_v), float(control_mag), np.ascontiguousarray(target, np.float32).reshape(3))
+
+    def set_mu(self, mu):
+        lib().o_scene_set_mu(self._h, np.ascontiguousarray(mu, np.float32).reshape(self.nT))
 
     def get_drag(self):
         m = np.zeros(self.nV, np.float32); o = np.zeros((self.nV, 3), np.float32); d = np.zeros((self.nV, 3), np.float32)

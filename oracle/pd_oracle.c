@@ -614,6 +614,11 @@ void o_scene_drag_select(o_scene *s, int select_v, float control_mag, const floa
     if (target) memcpy(s->drag_target, target, 12);
 }
 
+/* SimulationCUDAContext::UpdateSoftBodyAttr -> DataLoader::FillData (simulationContext.cu:165-176, dataLoader.cu:381-384):
+ * SolverData::mu is overwritten; computeLocal reads it live, matrix_diag / the assembled matrix wait for the next
+ * SolverPrepare (after Reset). */
+void o_scene_set_mu(o_scene *s, const float *mu) { memcpy(s->mu, mu, (size_t)s->nT * sizeof(float)); }
+
 void o_scene_get_drag(const o_scene *s, float *moreDBC, float *OffsetX, float *DBCX)
 {
     if (moreDBC) memcpy(moreDBC, s->moreDBC, (size_t)s->nV * sizeof(float));

@@ -87,6 +87,8 @@ void o_scene_set_drag(o_scene *, const float *moreDBC, const float *OffsetX, con
 /* Control_Kernel (simulationContext.cu:202-218) on the current X, then target */
 void o_scene_drag_select(o_scene *, int select_v, float control_mag, const float target[3]);
 void o_scene_get_drag(const o_scene *, float *moreDBC, float *OffsetX, float *DBCX);
+/* live stiffness edit (UpdateSoftBodyAttr, simulationContext.cu:165-176): mu[nT]; setup products follow only after reset */
+void o_scene_set_mu(o_scene *, const float *mu);
 /* setup products, for unit checks: matrix_diag[nV], massDt_2s[nV], DmInv[9nT], V0[nT] */
 void o_scene_get_setup(o_scene *, const o_params *, float *matrix_diag, float *massDt_2s,
                        float *DmInv, float *V0);

@@ -124,6 +124,8 @@ SYMBOLS = {
     "pd_set_drag_device": (_I, [_VP, _VP, _VP, _VP]),
     "pd_drag_select": (_I, [_VP, _I, _F, _VP]),
     "pd_get_drag": (_I, [_VP, _VP, _VP, _VP, _PI]),
+    "pd_update_mu": (_I, [_VP, _VP]),
+    "pd_update_mu_device": (_I, [_VP, _VP]),
     "pd_get_setup": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "pd_get_system_matrix": (_I, [_VP, _PI, _VP, _VP, _VP]),
     "pd_get_solve_stats": (_I, [_VP, _PF, _PI]),
@@ -487,6 +489,11 @@ class PdSolver:
         a = C.c_int()
         _check(lib().pd_get_drag(self._h, _p(m), _p(o), _p(d), C.byref(a)))
         return m, o, d, bool(a.value)
+
+    def update_mu(self, mu):
+        """SimulationCUDAContext::UpdateSoftBodyAttr (simulationContext.cu:165-176): new per-tet mu, original tet order."""
+        m = np.ascontiguousarray(mu, np.float32).reshape(self.num_tets)
+        _check(lib().pd_update_mu(self._h, _p(m)))
 
     def setup(self):
         md = np.zeros(self.num_verts, np.float32); c = np.zeros(self.num_verts, np.float32)

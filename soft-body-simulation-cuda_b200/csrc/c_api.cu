@@ -454,6 +454,8 @@ int pd_get_drag(pd_engine* e, float* more, float* off, float* dbcx, int* active)
 {
     ENGINE_CALL(e->e->getDrag(more, off, dbcx); if (active) *active = e->e->dragActive() ? 1 : 0)
 }
+int pd_update_mu(pd_engine* e, const float* mu) { ENGINE_CALL(e->e->updateMu(mu)) }
+int pd_update_mu_device(pd_engine* e, const float* dMu) { ENGINE_CALL(e->e->updateMuDevice(dMu)) }
 int pd_get_setup(pd_engine* e, float* md, float* mdt2, float* DmInv, float* V0) { ENGINE_CALL(e->e->getSetup(md, mdt2, DmInv, V0)) }
 int pd_get_system_matrix(pd_engine* e, int* nnz, int* rowptr, int* col, float* val)
 {

@@ -70,6 +70,8 @@ struct Engine::Impl {
     std::vector<cudaEvent_t> events;
     std::vector<void*> allocs;
     std::vector<float> hostMd;        // renumbered
+    std::vector<float> hostWPrepared; // w = |V0| mu of every tet (tile order) as SolverPrepare saw it: the system matrix of the
+                                      // direct / CG modes is assembled from THESE even if mu was edited since (pd_update_mu)
     // multi-GPU exchange window (this rank's) and the tables that point into the neighbours' windows
     uint8_t* window = nullptr;
     size_t windowBytes = 0;
@@ -296,6 +298,12 @@ void Engine::prepare()
     // matrix_diag[v] = sum over incident tets (ascending reordered order) of w_t |col_i(B^T G)|^2
     Impl& d = *d_;
     d.hostMd.assign((size_t)nV_, 0.f);
+    d.hostWPrepared.clear(); d.hostWPrepared.reserve((size_t)nT_);
+    for (int ti = 0; ti < L_.nTiles; ++ti) {
+        const uint8_t* rec = L_.records.data() + L_.tileRecOff[ti];
+        TileHeader h; std::memcpy(&h, rec, sizeof(h));
+        for (uint32_t t = 0; t < h.nTets; ++t) { float w; std::memcpy(&w, rec + tile_tet_word(h.nTets, t, 9), 4); d.hostWPrepared.push_back(w); }
+    }
     // tiles in ascending GLOBAL order (a rank keeps its interior tiles first): the float sums must not depend on the world size
     std::vector<int> tileOrder((size_t)L_.nTiles);
     for (int i = 0; i < L_.nTiles; ++i) tileOrder[(size_t)i] = i;
@@ -718,6 +726,41 @@ void Engine::getDrag(float* more, float* offsetX, float* dbcx)
     }
 }
 
+// ---------------------------------------------------------------- live stiffness edit
+// The tile stream carries w = |V0| * mu per tet (what computeLocal multiplies by, pdUtil.cu:124): rewrite that word of
+// every record on the host copy and upload the stream again.  matrix_diag (hostMd) and the assembled system matrix are
+// deliberately left alone -- the reference rebuilds them only in SolverPrepare, i.e. after Reset() (pdSolver.cu:212-216).
+void Engine::updateMu(const float* mu)
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    if (!mu) throw std::runtime_error("updateMu: mu is NULL");
+    Impl& d = *d_;
+    std::vector<float> B((size_t)scene_.numTets * 9), v0((size_t)scene_.numTets);
+    rest_shape(scene_.X.data(), scene_.Tet.data(), scene_.numTets, B.data(), v0.data());
+    std::copy(mu, mu + scene_.numTets, scene_.mu.begin());
+    CUDA_CHECK(cudaStreamSynchronize(stream_));        // no launch may still be reading the stream
+    for (int ti = 0; ti < L_.nTiles; ++ti) {
+        uint8_t* rec = L_.records.data() + L_.tileRecOff[(size_t)ti];
+        TileHeader h; std::memcpy(&h, rec, sizeof(h));
+        const uint32_t t0 = L_.tileTetStart[(size_t)ti];
+        for (uint32_t tl = 0; tl < h.nTets; ++tl) {
+            const size_t o = L_.tetOrder[(size_t)t0 + tl];                      // original tet id (also in a rank's layout)
+            const float w = std::fabs(v0[o]) * scene_.mu[o];                    // as build_layout computes it
+            std::memcpy(rec + tile_tet_word(h.nTets, tl, 9), &w, 4);
+        }
+    }
+    CUDA_CHECK(cudaMemcpy(d.records, L_.records.data(), L_.records.size(), cudaMemcpyHostToDevice));
+}
+
+void Engine::updateMuDevice(const float* dMu)
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    if (!dMu) throw std::runtime_error("updateMuDevice: mu is NULL");
+    std::vector<float> mu((size_t)scene_.numTets);
+    CUDA_CHECK(cudaMemcpy(mu.data(), dMu, mu.size() * 4, cudaMemcpyDeviceToHost));
+    updateMu(mu.data());
+}
+
 // ---------------------------------------------------------------- kernel timing helpers (bench)
 float Engine::timeLocalKernelMs(int reps)
 {
@@ -782,7 +825,7 @@ void Engine::prepareSolver()
                 float B[12];
                 for (uint32_t j = 0; j < 12; ++j) std::memcpy(&B[j], rec + tile_tet_word(h.nTets, k, j), 4);
                 std::memcpy(&Br[9 * t], B, 36);
-                wr[t] = B[9];
+                wr[t] = d.hostWPrepared[t];             // setup-time stiffness (computeSiTSi runs in SolverPrepare only, pdSolver.cu:62-70)
             }
         }
         const float dt2 = params_.dt * params_.dt;

@@ -63,6 +63,11 @@ public:
     void dragSelect(int selectV, float controlMag, const float target[3]);                        // Control_Kernel on the engine's X (simulationContext.cu:202-218)
     void getDrag(float* more, float* offsetX, float* dbcx);                                       // host, original numbering (parity checks)
     bool dragActive() const { return dragActive_; }
+    // live stiffness edit: SolverData<float>::mu[numTets] changed (SimulationCUDAContext::UpdateSoftBodyAttr -> FillData,
+    // simulationContext.cu:165-176).  computeLocal reads mu in every iteration (pdUtil.cu:97,124), so the new value acts at
+    // once; matrix_diag and the assembled system matrix are SolverPrepare products and stay as they are until Reset().
+    void updateMu(const float* mu);                    // host array, original tet order
+    void updateMuDevice(const float* dMu);             // the reference's device array
 
     const PerfCounters& perf() const { return perfc_; }
     void syncSolveStats();                                  // PCG / Cholesky modes: fold the device-side iteration counters in

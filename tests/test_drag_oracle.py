@@ -84,3 +84,23 @@ def test_dragged_mass_term_enters_the_direct_modes_right_hand_side_only(O, asset
     Xn, Vn, _ = sc.get()
     assert not Vn[5].any() and np.isfinite(Xn).all()
     assert np.abs(Xn[5] - target).max() > 1e-4          # pulled towards the target, not pinned to it
+
+
+def test_live_mu_edit_acts_at_once_but_setup_products_wait_for_reset(O, assets):
+    """UpdateSoftBodyAttr (simulationContext.cu:165-176) overwrites SolverData::mu; computeLocal reads it in every iteration
+    while matrix_diag was computed by SolverPrepare: stale until Reset, exactly like the reference."""
+    a, op = _scene(O, assets)
+    b, _ = _scene(O, assets)
+    a.step(op, 2); b.step(op, 2)
+    md0 = b.setup(op)[0].copy()
+    # a SOFTER material: with the stale (larger) diagonal the Jacobi sweeps stay stable.  Raising mu instead makes them
+    # diverge within a step -- the reference's latent bug (SURVEY.md section 8f row 3), restated as it is.
+    mu2 = np.full(b.nT, 1.0e5, np.float32)
+    b.set_mu(mu2)
+    assert np.array_equal(b.setup(op)[0], md0)                       # stale on purpose
+    a.step(op, 2); b.step(op, 2)
+    assert np.isfinite(b.get()[0]).all() and np.abs(a.get()[0] - b.get()[0]).max() > 1e-6     # acts at once
+    b.reset()
+    assert not np.array_equal(b.setup(op)[0], md0)                   # re-prepared with the new mu
+    c = O.Scene(b.X0, b.Tet, 10.0, mu2, planes=[])                    # same mesh built with the new mu from the start
+    assert np.allclose(b.setup(op)[0], c.setup(op)[0], rtol=0, atol=0)

@@ -207,3 +207,35 @@ def test_reference_side_adapter_binary(pd):
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "max_abs_diff 0" in r.stdout
+
+
+def test_live_mu_edit_vs_oracle(pd, O, assets):
+    """pd_update_mu = SimulationCUDAContext::UpdateSoftBodyAttr (simulationContext.cu:165-176): the new stiffness acts from the
+    next Update on, matrix_diag stays the SolverPrepare product until Reset -- both as in the reference (oracle)."""
+    name = "C5 house&sphere"
+    sc = pd.Scene.from_json(assets["json"], name)
+    p = sc.params
+    p["num_iterations"] = 50
+    sc.params = p
+    osc, _ = meshes.oracle_scene(O, assets, name)
+    op = _oracle_params(O, p)
+    eng = pd.PdSolver(sc, rot_mode=1)
+    scale = float(np.linalg.norm(osc.X0.max(0) - osc.X0.min(0)))
+    V0 = (0.3 * np.sin(osc.X0[:, [1, 2, 0]])).astype(np.float32)          # some deformation, so that the stiffness matters
+    eng.upload(V=V0); osc.set(V=V0)
+    eng.Update(2); osc.step(op, 2)
+    md0 = eng.setup()[0].copy()
+    mu2 = (sc.arrays()["mu"] * np.float32(0.5)).astype(np.float32)         # softer: stable with the stale diagonal
+    eng.update_mu(mu2); osc.set_mu(mu2)
+    assert np.array_equal(eng.setup()[0], md0)
+    eng.Update(4); osc.step(op, 4)
+    e1 = meshes.rel_err(eng.download()[0], osc.get()[0], scale)
+    eng.Reset(); osc.reset()
+    eng.upload(V=V0); osc.set(V=V0)
+    md1 = eng.setup()[0]
+    assert np.allclose(md1, 0.5 * md0, rtol=1e-5)                          # re-prepared with the new mu
+    assert np.allclose(md1, osc.setup(op)[0], rtol=2e-6)
+    eng.Update(3); osc.step(op, 3)
+    e2 = meshes.rel_err(eng.download()[0], osc.get()[0], scale)
+    print(f"live mu edit: rel err vs oracle {e1:.3e} (stale matrix_diag), {e2:.3e} (after Reset)")
+    assert e1 <= 1e-4 and e2 <= 1e-4, (e1, e2)
