@@ -94,41 +94,43 @@ static inline size_t rup(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // Deterministic: edges in (tet, corner) order, smallest free colours, alternating-path recolouring.
 static void color_tile(uint32_t nTets, uint32_t nRows, const uint32_t* epos, uint8_t (*col)[4])
 {
-    const uint32_t nE = 4u * nTets, nR = nRows * 8u;
-    int16_t atL[128][8];
-    std::vector<int16_t> atR((size_t)nR * 8, -1);
-    for (auto& a : atL) for (auto& x : a) x = -1;
+    // NC colours; store group of edge (tl, k) and load group of its incidence entry at position p = (row * 32 + lane) * 2 + half:
+    //   default     NC = 8 : 8 consecutive tets x corner (one quarter-warp STS.128) / (row, half, lane / 8)
+    //   PD_H_PLANES NC = 32: 32 consecutive tets x corner (one warp STS.32)        / (row, half)
+    constexpr uint32_t NC = TILE_HCOLOURS, NL = 4u * (uint32_t)TILE_T / NC, LG = 32u / NC;      // left nodes; load groups per (row, half)
+    const uint32_t nE = 4u * nTets, nR = nRows * 2u * LG;
+    std::vector<int16_t> atL((size_t)NL * NC, -1), atR((size_t)nR * NC, -1);
     std::vector<uint16_t> eu(nE), ev(nE);
     std::vector<int8_t> ec(nE, -1);
     std::vector<uint16_t> path;
     for (uint32_t e = 0; e < nE; ++e) {
         const uint32_t tl = e / 4u, k = e % 4u, p = epos[e];
-        const uint32_t u = k * 32u + tl / 8u, v = ((p / 64u) * 2u + (p & 1u)) * 4u + ((p / 2u) % 32u) / 8u;
+        const uint32_t u = k * ((uint32_t)TILE_T / NC) + tl / NC, v = ((p / 64u) * 2u + (p & 1u)) * LG + ((p / 2u) % 32u) / NC;
         eu[e] = (uint16_t)u; ev[e] = (uint16_t)v;
-        int a = 0, b = 0;
-        while (a < 8 && atL[u][a] >= 0) ++a;
-        while (b < 8 && atR[(size_t)v * 8 + b] >= 0) ++b;
-        if (a >= 8 || b >= 8) throw std::runtime_error("tile colouring: degree above 8");
-        if (atR[(size_t)v * 8 + a] >= 0) {
+        uint32_t a = 0, b = 0;
+        while (a < NC && atL[(size_t)u * NC + a] >= 0) ++a;
+        while (b < NC && atR[(size_t)v * NC + b] >= 0) ++b;
+        if (a >= NC || b >= NC) throw std::runtime_error("tile colouring: degree above the colour count");
+        if (atR[(size_t)v * NC + a] >= 0) {
             // free colour a at v: swap a <-> b along the alternating path that leaves v by colour a
             path.clear();
-            uint32_t node = v; bool right = true; int c = a;
+            uint32_t node = v; bool right = true; uint32_t c = a;
             for (;;) {
-                const int16_t f = right ? atR[(size_t)node * 8 + c] : atL[node][c];
+                const int16_t f = right ? atR[(size_t)node * NC + c] : atL[(size_t)node * NC + c];
                 if (f < 0) break;
                 path.push_back((uint16_t)f);
                 node = right ? eu[f] : ev[f];
                 right = !right;
                 c = (c == a) ? b : a;
             }
-            for (uint16_t f : path) { atL[eu[f]][ec[f]] = -1; atR[(size_t)ev[f] * 8 + ec[f]] = -1; }
+            for (uint16_t f : path) { atL[(size_t)eu[f] * NC + ec[f]] = -1; atR[(size_t)ev[f] * NC + ec[f]] = -1; }
             for (uint16_t f : path) {
-                ec[f] = (int8_t)(ec[f] == a ? b : a);
-                atL[eu[f]][ec[f]] = (int16_t)f; atR[(size_t)ev[f] * 8 + ec[f]] = (int16_t)f;
+                ec[f] = (int8_t)((uint32_t)ec[f] == a ? b : a);
+                atL[(size_t)eu[f] * NC + ec[f]] = (int16_t)f; atR[(size_t)ev[f] * NC + ec[f]] = (int16_t)f;
             }
         }
         ec[e] = (int8_t)a;
-        atL[u][a] = (int16_t)e; atR[(size_t)v * 8 + a] = (int16_t)e;
+        atL[(size_t)u * NC + a] = (int16_t)e; atR[(size_t)v * NC + a] = (int16_t)e;
     }
     for (uint32_t e = 0; e < nE; ++e) col[e / 4u][e % 4u] = (uint8_t)ec[e];
 }
@@ -285,20 +287,21 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
         color_tile(nTets, nRows, epos.data(), col);
         // pads point at the zero slot of a column no real entry of their load group uses
         {
-            const size_t nLg = (size_t)nRows * 8;          // load group = (row, half, lane / 8)
-            std::vector<uint8_t> used(nLg, 0);
+            constexpr uint32_t NC = TILE_HCOLOURS, LG = 32u / NC, ESZ = PD_H_PLANES ? 4u : 16u;      // load groups per (row, half); entry bytes
+            const size_t nLg = (size_t)nRows * 2 * LG;     // load group = (row, half, lane / NC)
+            std::vector<uint32_t> used(nLg, 0);
             for (uint32_t tl = 0; tl < nTets; ++tl)
                 for (int k = 0; k < 4; ++k) {
                     const uint32_t p = epos[4 * tl + k], row = p / 64u, lane = (p / 2u) % 32u, half = p & 1u;
-                    used[(row * 2u + half) * 4u + lane / 8u] |= (uint8_t)(1u << col[tl][k]);
+                    used[(row * 2u + half) * LG + lane / NC] |= 1u << col[tl][k];
                 }
             for (uint32_t row = 0; row < nRows; ++row)
                 for (uint32_t lane = 0; lane < 32; ++lane)
                     for (uint32_t half = 0; half < 2; ++half) {
-                        const uint8_t u = used[(row * 2u + half) * 4u + lane / 8u];
+                        const uint32_t u = used[(row * 2u + half) * LG + lane / NC];
                         uint32_t c = 0;
-                        while (c < 7 && (u >> c & 1u)) ++c;          // a full group (u == 0xff) has no pad
-                        incT[(row * 32u + lane) * 2u + half] = (uint16_t)(TILE_ZERO_OFF + 16u * c);
+                        while (c < NC - 1u && (u >> c & 1u)) ++c;    // a full group (every colour used) has no pad
+                        incT[(row * 32u + lane) * 2u + half] = (uint16_t)(TILE_ZERO_OFF + ESZ * c);
                     }
         }
         for (uint32_t tl = 0; tl < nTets; ++tl) {
