@@ -307,6 +307,8 @@ class Layout:
         _check(lib().pd_layout_get_vstage(self._h, _p(self.vstage)))
         self.tile_table = np.zeros((self.num_tiles, 12), np.uint32)  # what the local kernel reads per tile (layout.hpp TILE_META_WORDS)
         _check(lib().pd_layout_tile_table(self._h, _p(self.tile_table)))
+        self.num_tets = int(self.tile_tet_start[-1])                 # (a trimmed rank layout holds fewer tets than its plan's tiles)
+        self.tet_order, self.tet_new = self.tet_order[:self.num_tets], self.tet_new[:self.num_tets]
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:

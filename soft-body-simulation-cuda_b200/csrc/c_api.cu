@@ -346,7 +346,7 @@ pd_layout* pd_rank_layout(const pd_layout* g, const pd_rank_plan* p)
     PD_TRY
     if (!g || !p) { g_err = "NULL argument"; return nullptr; }
     pd_layout* l = new pd_layout;
-    try { extract_rank_layout(g->L, p->P, l->L); } catch (...) { delete l; throw; }
+    try { extract_rank_layout(g->L, p->P, l->L, dist_trim_from_env()); } catch (...) { delete l; throw; }
     return l;
     PD_CATCH_PTR
 }

@@ -600,7 +600,13 @@ void build_rank_plan(const Layout& G, int world, int rank, RankPlan& P)
     std::sort(P.neighbours.begin(), P.neighbours.end());
 }
 
-void extract_rank_layout(const Layout& G, const RankPlan& P, Layout& L)
+bool dist_trim_from_env()
+{
+    const char* e = std::getenv("PD_DIST_TRIM");
+    return e && e[0] == '1';
+}
+
+void extract_rank_layout(const Layout& G, const RankPlan& P, Layout& L, bool trim)
 {
     L = Layout();
     const int v0 = P.vbeg[P.rank];
@@ -612,14 +618,23 @@ void extract_rank_layout(const Layout& G, const RankPlan& P, Layout& L)
     for (int g = 0; g < G.nV; ++g) if (localOf[(size_t)g] != 0xffffffffu) L.vertOrder[localOf[(size_t)g]] = G.vertOrder[(size_t)g];
     L.vertNewOfOld.assign((size_t)G.nV, 0xffffffffu);                   // ORIGINAL id -> local id (0xffffffff: not on this rank)
     for (int l = 0; l < L.nV; ++l) L.vertNewOfOld[L.vertOrder[(size_t)l]] = (uint32_t)l;
-    std::vector<uint32_t> localTile((size_t)G.nTiles, 0xffffffffu);
-    L.nTiles = (int)P.tiles.size();
+    std::vector<uint32_t> localTile((size_t)G.nTiles, 0xffffffffu);     // global tile -> local tile, for the tiles copied unchanged
     L.tileTetStart.push_back(0); L.tileRecOff.push_back(0);
-    L.vlist.assign((size_t)L.nTiles * TILE_NLMAX, 0xffffffffu);
-    L.vstage.assign((size_t)L.nTiles * TILE_NLMAX, 0xffffffffu);
     L.maxLocal = 0;
-    for (int lt = 0; lt < L.nTiles; ++lt) {
-        const uint32_t gt = P.tiles[(size_t)lt];
+    L.nTiles = 0;
+    auto open_tile = [&]() {
+        L.vlist.resize((size_t)(L.nTiles + 1) * TILE_NLMAX, 0xffffffffu);
+        L.vstage.resize((size_t)(L.nTiles + 1) * TILE_NLMAX, 0xffffffffu);
+    };
+    auto close_tile = [&]() {
+        L.tileTetStart.push_back((uint32_t)L.tetOrder.size());
+        L.tileRecOff.push_back((uint64_t)L.records.size());
+        ++L.nTiles;
+    };
+    // a global tile exactly as it is: same record bytes, same slots
+    auto copy_tile = [&](uint32_t gt) {
+        const int lt = L.nTiles;
+        open_tile();
         localTile[gt] = (uint32_t)lt;
         const uint64_t gb = G.tileRecOff[gt], ge = G.tileRecOff[gt + 1];
         const size_t base = L.records.size();
@@ -633,10 +648,9 @@ void extract_rank_layout(const Layout& G, const RankPlan& P, Layout& L)
         const uint32_t t0 = G.tileTetStart[gt], t1 = G.tileTetStart[gt + 1];
         for (uint32_t t = t0; t < t1; ++t) {
             L.tetOrder.push_back(G.tetOrder[t]);
+            L.tetGlobal.push_back(t);
             for (int k = 0; k < 4; ++k) L.tetNew.push_back(localOf[G.tetNew[4 * (size_t)t + k]]);
         }
-        L.tileTetStart.push_back((uint32_t)L.tetOrder.size());
-        L.tileRecOff.push_back((uint64_t)L.records.size());
         for (uint32_t l = 0; l < h.nLocal; ++l) {
             const uint32_t e = G.vlist[(size_t)gt * TILE_NLMAX + l];
             L.vlist[(size_t)lt * TILE_NLMAX + l] = localOf[e & ~TILE_OWNER_BIT] | (e & TILE_OWNER_BIT);
@@ -645,6 +659,123 @@ void extract_rank_layout(const Layout& G, const RankPlan& P, Layout& L)
             const uint32_t e = G.vstage[(size_t)gt * TILE_NLMAX + sl];
             if (e != 0xffffffffu) L.vstage[(size_t)lt * TILE_NLMAX + sl] = localOf[e & ~TILE_OWNER_BIT] | (e & TILE_OWNER_BIT);
         }
+        close_tile();
+    };
+    // ---- trimmed boundary tiles (experiment, see layout.hpp): slots of the (global tile, vertex) pairs they keep
+    struct Part {               // one boundary tile cut down to the tets that touch an owned vertex
+        uint32_t gt;
+        std::vector<uint32_t> tets;                 // global reordered tet indices, ascending
+        std::vector<uint32_t> verts;                // their distinct vertices: global id | owner bit of this tile's slot
+    };
+    std::vector<std::pair<uint64_t, uint32_t>> packedSlot;      // ((gt << 32) | global vertex, local slot), sorted below
+    auto make_part = [&](uint32_t gt, Part& part) {
+        part.gt = gt; part.tets.clear(); part.verts.clear();
+        for (uint32_t t = G.tileTetStart[gt]; t < G.tileTetStart[gt + 1]; ++t) {
+            bool owned = false;
+            for (int k = 0; k < 4; ++k) owned = owned || localOf[G.tetNew[4 * (size_t)t + k]] < (uint32_t)P.nOwn;
+            if (owned) part.tets.push_back(t);
+        }
+        // distinct vertices in the tile's own slot order, with the owner flag of that slot
+        const uint32_t* vl = G.vlist.data() + (size_t)gt * TILE_NLMAX;
+        std::vector<uint8_t> seen((size_t)TILE_NLMAX, 0);
+        std::vector<uint32_t> ids;
+        for (int l = 0; l < TILE_NLMAX && vl[l] != 0xffffffffu; ++l) ids.push_back(vl[l] & ~TILE_OWNER_BIT);
+        for (uint32_t t : part.tets)
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t v = G.tetNew[4 * (size_t)t + k];
+                const size_t l = (size_t)(std::find(ids.begin(), ids.end(), v) - ids.begin());
+                if (l >= ids.size()) throw std::runtime_error("rank layout: a tet's vertex is missing from its tile's list");
+                seen[l] = 1;
+            }
+        for (size_t l = 0; l < ids.size(); ++l) if (seen[l]) part.verts.push_back(vl[l]);
+    };
+    // several consecutive parts -> ONE physical tile through the ordinary tile builder, on a small mesh whose vertex ids
+    // are the (part, vertex) pairs; false if the builder needed more than one tile (the incidence row budget)
+    auto emit_parts = [&](const Part* parts, size_t nParts) -> bool {
+        std::vector<uint32_t> keyVert;              // key -> global id | owner bit
+        std::vector<uint32_t> keyPart;
+        std::vector<uint32_t> tet4;
+        std::vector<float> B, w;
+        std::vector<uint32_t> tetIdx;
+        for (size_t pi = 0; pi < nParts; ++pi) {
+            const Part& part = parts[pi];
+            const uint32_t key0 = (uint32_t)keyVert.size();
+            for (uint32_t e : part.verts) { keyVert.push_back(e); keyPart.push_back((uint32_t)pi); }
+            const uint8_t* rec = G.records.data() + G.tileRecOff[part.gt];
+            TileHeader h; std::memcpy(&h, rec, sizeof(h));
+            for (uint32_t t : part.tets) {
+                const uint32_t tl = t - G.tileTetStart[part.gt];
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t v = G.tetNew[4 * (size_t)t + k];
+                    uint32_t key = key0;
+                    while ((keyVert[key] & ~TILE_OWNER_BIT) != v) ++key;        // present by construction (make_part)
+                    tet4.push_back(key);
+                }
+                for (uint32_t j = 0; j < 9; ++j) { float f; std::memcpy(&f, rec + tile_tet_word(h.nTets, tl, j), 4); B.push_back(f); }
+                float wt; std::memcpy(&wt, rec + tile_tet_word(h.nTets, tl, 9), 4); w.push_back(wt);
+                tetIdx.push_back(t);
+            }
+        }
+        Layout T;
+        T.nV = (int)keyVert.size(); T.nT = (int)tetIdx.size();
+        build_tiles(T.nV, T.nT, tet4.data(), B.data(), w.data(), T);
+        if (T.nTiles != 1) return false;
+        const int lt = L.nTiles;
+        open_tile();
+        const size_t base = L.records.size();
+        L.records.insert(L.records.end(), T.records.begin(), T.records.end());
+        TileHeader h; std::memcpy(&h, L.records.data() + base, sizeof(h));
+        h.slotBase = (uint32_t)lt * (uint32_t)TILE_NLMAX;
+        h.offLo = (uint32_t)(base & 0xffffffffu); h.offHi = (uint32_t)((uint64_t)base >> 32);
+        std::memcpy(L.records.data() + base, &h, sizeof(h));
+        L.tileTab.push_back(TileEntry{(uint64_t)base, h.abBytes, h.cBytes});
+        L.maxLocal = std::max(L.maxLocal, (int)h.nLocal);
+        for (uint32_t t : tetIdx) {
+            L.tetOrder.push_back(G.tetOrder[t]);
+            L.tetGlobal.push_back(t);
+            for (int k = 0; k < 4; ++k) L.tetNew.push_back(localOf[G.tetNew[4 * (size_t)t + k]]);
+        }
+        auto translate = [&](uint32_t e) -> uint32_t {      // the builder's entry (key | its own owner bit) -> local vertex | the global slot's owner bit
+            const uint32_t kv = keyVert[e & ~TILE_OWNER_BIT];
+            return localOf[kv & ~TILE_OWNER_BIT] | (kv & TILE_OWNER_BIT);
+        };
+        for (uint32_t l = 0; l < h.nLocal; ++l) {
+            const uint32_t e = T.vlist[l];
+            L.vlist[(size_t)lt * TILE_NLMAX + l] = translate(e);
+            const uint32_t key = e & ~TILE_OWNER_BIT;
+            packedSlot.push_back({((uint64_t)parts[keyPart[key]].gt << 32) | (keyVert[key] & ~TILE_OWNER_BIT), (uint32_t)lt * (uint32_t)TILE_NLMAX + l});
+        }
+        for (uint32_t sl = 0; sl < (uint32_t)TILE_NLMAX; ++sl)
+            if (T.vstage[sl] != 0xffffffffu) L.vstage[(size_t)lt * TILE_NLMAX + sl] = translate(T.vstage[sl]);
+        close_tile();
+        return true;
+    };
+
+    for (int i = 0; i < P.nInteriorTiles; ++i) copy_tile(P.tiles[(size_t)i]);
+    if (!trim) {
+        for (size_t i = (size_t)P.nInteriorTiles; i < P.tiles.size(); ++i) copy_tile(P.tiles[i]);
+    } else {
+        std::vector<Part> group;
+        size_t gTets = 0, gVerts = 0;
+        auto flush = [&]() {
+            if (group.empty()) return;
+            if (!emit_parts(group.data(), group.size())) {
+                if (group.size() == 1) throw std::runtime_error("rank layout: a trimmed tile does not fit one tile");
+                for (const Part& part : group)
+                    if (!emit_parts(&part, 1)) throw std::runtime_error("rank layout: a trimmed tile does not fit one tile");
+            }
+            group.clear(); gTets = gVerts = 0;
+        };
+        for (size_t i = (size_t)P.nInteriorTiles; i < P.tiles.size(); ++i) {
+            Part part;
+            make_part(P.tiles[i], part);
+            if (part.tets.empty()) continue;            // (cannot happen: the tile is here because it holds an owned vertex)
+            if (gTets + part.tets.size() > (size_t)TILE_T || gVerts + part.verts.size() > (size_t)TILE_NLMAX) flush();
+            gTets += part.tets.size(); gVerts += part.verts.size();
+            group.push_back(std::move(part));
+        }
+        flush();
+        std::sort(packedSlot.begin(), packedSlot.end());
     }
     L.nT = (int)L.tetOrder.size();
     // vertex -> slots: the global lists restricted to this rank's tiles (complete for owned vertices), same order
@@ -654,10 +785,11 @@ void extract_rank_layout(const Layout& G, const RankPlan& P, Layout& L)
     for (int l = 0; l < L.nV; ++l) {
         const uint32_t g = globalOf[(size_t)l];
         for (uint32_t e = G.vslotPtr[g]; e < G.vslotPtr[g + 1]; ++e) {
-            const uint32_t slot = G.vslot[e], lt = localTile[slot / TILE_NLMAX];
-            if (lt == 0xffffffffu) continue;
-            if (l < P.nOwn) { /* every tile of an owned vertex is evaluated here */ }
-            L.vslot.push_back(lt * (uint32_t)TILE_NLMAX + slot % TILE_NLMAX);
+            const uint32_t slot = G.vslot[e], gt = slot / TILE_NLMAX, lt = localTile[gt];
+            if (lt != 0xffffffffu) { L.vslot.push_back(lt * (uint32_t)TILE_NLMAX + slot % TILE_NLMAX); continue; }
+            const uint64_t key = ((uint64_t)gt << 32) | g;
+            const auto it = std::lower_bound(packedSlot.begin(), packedSlot.end(), std::make_pair(key, 0u));
+            if (it != packedSlot.end() && it->first == key) L.vslot.push_back(it->second);
         }
         L.vslotPtr[(size_t)l + 1] = (uint32_t)L.vslot.size();
         if (l < P.nOwn && L.vslotPtr[(size_t)l + 1] - L.vslotPtr[(size_t)l] != G.vslotPtr[g + 1] - G.vslotPtr[g])

@@ -120,6 +120,9 @@ struct Layout {
                                         // what the local kernel's position gather reads (stage_slots() in layout.cpp)
     std::vector<uint32_t> vlist;        // nTiles * TILE_NLMAX   slot -> vertex id | TILE_OWNER_BIT (first slot of the vertex), 0xffffffff unused
     int maxLocal = 0;
+    // a rank's layout only (extract_rank_layout): position of every local tet in the GLOBAL reordered tet list, so that
+    // float sums over a vertex's tets (matrix_diag) can be taken in the same order on every world size
+    std::vector<uint32_t> tetGlobal;    // nT, empty for a single-GPU layout
 };
 
 // Per-tile entry of the DEVICE tile table the local kernel reads (build_tile_table): record offset / 16, part AB bytes |
@@ -188,6 +191,13 @@ struct RankPlan {
 void build_rank_plan(const Layout& G, int world, int rank, RankPlan& plan);
 // the rank's own Layout: selected tiles (headers re-based), local vertex ids, local slots; vertOrder maps local ->
 // ORIGINAL vertex ids so that everything downstream of a Layout works unchanged
-void extract_rank_layout(const Layout& G, const RankPlan& plan, Layout& out);
+// EXPERIMENT (trim = true; the engine and pd_rank_layout take it from the environment, PD_DIST_TRIM=1; default off): a boundary
+// tile is cut down to the tets that touch a vertex this rank OWNS (the others only feed ghost vertices, whose sums are never
+// read), and consecutive trimmed tiles are packed into physical tiles of up to TILE_T tets.  Every (global tile, vertex)
+// pair keeps a slot of its own with its incidence list in the original order, so the partial sums -- and the vertex sums
+// over the slots in ascending global tile order -- stay bit-identical to the single-GPU run.  Redundant tets on the 139^3
+// grid at N = 8: 13 % -> about 4 %.
+void extract_rank_layout(const Layout& G, const RankPlan& plan, Layout& out, bool trim = false);
+bool dist_trim_from_env();
 
 }  // namespace pdb200
