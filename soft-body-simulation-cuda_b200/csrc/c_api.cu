@@ -316,7 +316,7 @@ pd_rank_plan* pd_rank_plan_build(const pd_layout* g, int world, int rank)
     PD_TRY
     if (!g) { g_err = "layout is NULL"; return nullptr; }
     pd_rank_plan* p = new pd_rank_plan;
-    try { build_rank_plan(g->L, world, rank, p->P); } catch (...) { delete p; throw; }
+    try { build_rank_plan(g->L, world, rank, p->P, dist_trim_from_env()); } catch (...) { delete p; throw; }
     return p;
     PD_CATCH_PTR
 }
@@ -346,7 +346,7 @@ pd_layout* pd_rank_layout(const pd_layout* g, const pd_rank_plan* p)
     PD_TRY
     if (!g || !p) { g_err = "NULL argument"; return nullptr; }
     pd_layout* l = new pd_layout;
-    try { extract_rank_layout(g->L, p->P, l->L, dist_trim_from_env()); } catch (...) { delete l; throw; }
+    try { extract_rank_layout(g->L, p->P, l->L); } catch (...) { delete l; throw; }
     return l;
     PD_CATCH_PTR
 }

@@ -539,11 +539,11 @@ static inline int owner_of(const std::vector<int>& vbeg, uint32_t v)
     return (int)(std::upper_bound(vbeg.begin(), vbeg.end(), (int)v) - vbeg.begin()) - 1;
 }
 
-void build_rank_plan(const Layout& G, int world, int rank, RankPlan& P)
+void build_rank_plan(const Layout& G, int world, int rank, RankPlan& P, bool trim)
 {
     if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("rank plan: bad rank/world");
     P = RankPlan();
-    P.rank = rank; P.world = world;
+    P.rank = rank; P.world = world; P.trim = trim;
     partition_vertices(G.nV, world, P.vbeg);
     P.nOwn = P.vbeg[rank + 1] - P.vbeg[rank];
     // one pass over the tiles: which ranks evaluate it, and whose ghosts its vertices become
@@ -559,11 +559,22 @@ void build_rank_plan(const Layout& G, int world, int rank, RankPlan& P)
         }
         if (std::find(ranksOfTile.begin(), ranksOfTile.end(), rank) != ranksOfTile.end())
             (ranksOfTile.size() > 1 ? boundaryTiles : P.tiles).push_back((uint32_t)t);
-        if (ranksOfTile.size() > 1)
+        if (ranksOfTile.size() > 1 && !trim)
             for (int l = 0; l < TILE_NLMAX && vl[l] != 0xffffffffu; ++l) {
                 const uint32_t v = vl[l] & ~TILE_OWNER_BIT;
                 const int o = owner_of(P.vbeg, v);
                 for (int r : ranksOfTile) if (r != o) ghostsOf[(size_t)r].push_back(v);
+            }
+        if (ranksOfTile.size() > 1 && trim)          // a rank keeps a tet iff it owns one of its vertices; the others are its ghosts
+            for (uint32_t tt = G.tileTetStart[(size_t)t]; tt < G.tileTetStart[(size_t)t + 1]; ++tt) {
+                int o[4];
+                for (int k = 0; k < 4; ++k) o[k] = owner_of(P.vbeg, G.tetNew[4 * (size_t)tt + k]);
+                for (int k = 0; k < 4; ++k) {
+                    bool first = true;
+                    for (int j = 0; j < k; ++j) first = first && o[j] != o[k];
+                    if (!first) continue;                                    // rank o[k] handled already for this tet
+                    for (int j = 0; j < 4; ++j) if (o[j] != o[k]) ghostsOf[(size_t)o[k]].push_back(G.tetNew[4 * (size_t)tt + j]);
+                }
             }
     }
     P.nInteriorTiles = (int)P.tiles.size();
@@ -606,8 +617,9 @@ bool dist_trim_from_env()
     return e && e[0] == '1';
 }
 
-void extract_rank_layout(const Layout& G, const RankPlan& P, Layout& L, bool trim)
+void extract_rank_layout(const Layout& G, const RankPlan& P, Layout& L)
 {
+    const bool trim = P.trim;
     L = Layout();
     const int v0 = P.vbeg[P.rank];
     L.nV = P.nOwn + P.nGhost;

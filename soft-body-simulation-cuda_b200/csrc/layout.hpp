@@ -176,6 +176,7 @@ void partition_vertices(int nV, int world, std::vector<int>& vbeg);
 // owners once per PD iteration.  Local vertex numbering: [own range in global order | ghosts ascending].
 struct RankPlan {
     int rank = 0, world = 1;
+    bool trim = false;                 // PD_DIST_TRIM experiment: trimmed ghosts here, trimmed + re-packed boundary tiles in extract_rank_layout
     std::vector<int> vbeg;             // world + 1
     int nOwn = 0, nGhost = 0;
     std::vector<uint32_t> tiles;       // global tile ids evaluated by this rank: first the interior tiles (all vertices owned),
@@ -188,16 +189,18 @@ struct RankPlan {
     std::vector<uint32_t> pushSrc, pushDst;
     std::vector<int> pushRank;
 };
-void build_rank_plan(const Layout& G, int world, int rank, RankPlan& plan);
+// trim (PD_DIST_TRIM=1, experiment): the ghosts of a rank are only the vertices of the tets it keeps (the tets that touch a
+// vertex it owns), not every vertex of its boundary tiles -- the halo pushes shrink accordingly.  Same tiles either way.
+void build_rank_plan(const Layout& G, int world, int rank, RankPlan& plan, bool trim = false);
 // the rank's own Layout: selected tiles (headers re-based), local vertex ids, local slots; vertOrder maps local ->
 // ORIGINAL vertex ids so that everything downstream of a Layout works unchanged
-// EXPERIMENT (trim = true; the engine and pd_rank_layout take it from the environment, PD_DIST_TRIM=1; default off): a boundary
+// EXPERIMENT (plan.trim; the engine and pd_rank_plan_build take it from the environment, PD_DIST_TRIM=1; default off): a boundary
 // tile is cut down to the tets that touch a vertex this rank OWNS (the others only feed ghost vertices, whose sums are never
 // read), and consecutive trimmed tiles are packed into physical tiles of up to TILE_T tets.  Every (global tile, vertex)
 // pair keeps a slot of its own with its incidence list in the original order, so the partial sums -- and the vertex sums
 // over the slots in ascending global tile order -- stay bit-identical to the single-GPU run.  Redundant tets on the 139^3
 // grid at N = 8: 13 % -> about 4 %.
-void extract_rank_layout(const Layout& G, const RankPlan& plan, Layout& out, bool trim = false);
+void extract_rank_layout(const Layout& G, const RankPlan& plan, Layout& out);      // trims iff plan.trim
 bool dist_trim_from_env();
 
 }  // namespace pdb200

@@ -140,8 +140,8 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
         // every rank builds the same global layout, then keeps the tiles that touch its vertex range
         Layout G;
         build_layout(scene_.numVerts, scene_.numTets, scene_.X.data(), scene_.Tet.data(), scene_.mu.data(), opt.reorder != 0, G);
-        build_rank_plan(G, opt.world, opt.rank, plan_);
-        extract_rank_layout(G, plan_, L_, dist_trim_from_env());      // PD_DIST_TRIM=1: trimmed + packed boundary tiles (experiment, layout.hpp)
+        build_rank_plan(G, opt.world, opt.rank, plan_, dist_trim_from_env());
+        extract_rank_layout(G, plan_, L_);      // plan_.trim (PD_DIST_TRIM=1): trimmed + packed boundary tiles (experiment, layout.hpp)
         nOwn_ = plan_.nOwn;
     }
     nV_ = L_.nV;

@@ -121,13 +121,15 @@ def test_world_one_is_the_single_gpu_layout(pd):
         assert np.array_equal(getattr(L, k), getattr(G, k)), k
 
 
-def test_halo_exchange_world2_gloo(tmp_path):
+@pytest.mark.parametrize("trim", ["0", "1"])
+def test_halo_exchange_world2_gloo(tmp_path, trim):
     """Two processes (gloo): each builds its own plan, they exchange one halo with the real push lists and
-    check every ghost entry against the owner's value bit for bit."""
-    port = 29500 + os.getpid() % 2000
+    check every ghost entry against the owner's value bit for bit.  trim = 1: the PD_DIST_TRIM experiment's shorter
+    ghost / push lists (csrc/layout.hpp)."""
+    port = 29500 + (os.getpid() + 7 * int(trim)) % 2000
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(HERE, "dist_gloo_worker.py")]
-    env = dict(os.environ, OMP_NUM_THREADS="1")
+    env = dict(os.environ, OMP_NUM_THREADS="1", PD_DIST_TRIM=trim)
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("HALO_OK") == 2, out.stdout[-2000:]

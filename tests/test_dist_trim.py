@@ -62,18 +62,35 @@ def test_trimmed_rank_layouts_keep_every_owned_slot(pd, assets, scene_name, worl
     G = sc.layout()
     glists = _slot_lists(G)
     full = trimmed = 0
+    monkeypatch.setenv("PD_DIST_TRIM", "1")
+    plans = [pd.RankPlan(G, world, r) for r in range(world)]              # the plan carries the switch to its layout
+    monkeypatch.delenv("PD_DIST_TRIM", raising=False)
+    plans0 = [pd.RankPlan(G, world, r) for r in range(world)]
+    # push lists of the trimmed plans: the same vertex on both sides, every ghost fed exactly once by its owner
+    for n, Pn in enumerate(plans):
+        fed = np.zeros(Pn.num_ghosts, np.int32)
+        for r, Pr in enumerate(plans):
+            m = Pr.push_rank == n
+            gid = Pr.first_owned + Pr.push_src[m].astype(np.int64)
+            slot = Pr.push_dst[m].astype(np.int64) - Pn.num_owned
+            assert (slot >= 0).all() and np.array_equal(Pn.ghosts[slot].astype(np.int64), gid) and (Pr.push_src[m] < Pr.num_owned).all()
+            np.add.at(fed, slot, 1)
+        assert (fed == 1).all()
+        assert Pn.n_loc_of.tolist() == [q.num_owned + q.num_ghosts for q in plans]
+        assert set(Pn.ghosts.tolist()) <= set(plans0[n].ghosts.tolist()) and Pn.tiles.tolist() == plans0[n].tiles.tolist()
+    print(f"{scene_name} world {world}: ghosts {sum(q.num_ghosts for q in plans0)} -> {sum(q.num_ghosts for q in plans)}")
     for rank in range(world):
-        P = pd.RankPlan(G, world, rank)
-        monkeypatch.delenv("PD_DIST_TRIM", raising=False)
-        L0 = P.local_layout(G)
-        monkeypatch.setenv("PD_DIST_TRIM", "1")
+        P = plans[rank]
+        L0 = plans0[rank].local_layout(G)
         L = P.local_layout(G)
-        monkeypatch.delenv("PD_DIST_TRIM", raising=False)
         full += L0.num_tets; trimmed += L.num_tets
         assert L.num_tiles <= L0.num_tiles and L.num_tets <= L0.num_tets
         # interior tiles are untouched and come first
         n_int = P.num_interior_tiles
         assert np.array_equal(L.tile_table[:n_int, 1:], L0.tile_table[:n_int, 1:])
+        # the ghosts are exactly the foreign vertices of the kept tets
+        used = np.unique(L.tet_new)
+        assert used.max() < P.num_owned + P.num_ghosts and set(range(P.num_owned, P.num_owned + P.num_ghosts)) <= set(used.tolist())
         # exactly the tets that touch an owned vertex, once each
         first, n_own = P.first_owned, P.num_owned
         own_orig = set(G.vert_order[first:first + n_own].tolist())
