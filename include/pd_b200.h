@@ -138,6 +138,9 @@ int pd_layout_get(const pd_layout*, uint32_t* tet_order, uint32_t* vert_order, u
 int pd_layout_get_vstage(const pd_layout*, uint32_t* vstage);
 /* the device tile table the local kernel reads: num_tiles * 12 words (csrc/layout.hpp, TILE_META_WORDS) */
 int pd_layout_tile_table(const pd_layout*, uint32_t* table);
+/* matrix_diag of SolverPrepare (computeSiTSi, pdUtil.cu:16-24) as the engine computes it on the host, per LAYOUT vertex
+ * (renumbered ids of a global layout, local ids of a rank's layout): sums in ascending global tet order on every world size */
+int pd_layout_matrix_diag(const pd_layout*, float* matrix_diag /* layout's vertex count */);
 int pd_morton_keys(const float* X, const uint32_t* Tet, int num_tets, uint32_t* keys);
 int pd_partition_vertices(int num_verts, int world, int* vbeg /* world+1 */);
 /* host-side prefactorisation of the small-mesh path: sparse Cholesky A = L L^T of a symmetric CSR matrix in the given

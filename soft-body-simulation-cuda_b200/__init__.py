@@ -88,6 +88,7 @@ SYMBOLS = {
     "pd_layout_get": (_I, [_VP] * 10),
     "pd_layout_get_vstage": (_I, [_VP, _VP]),
     "pd_layout_tile_table": (_I, [_VP, _VP]),
+    "pd_layout_matrix_diag": (_I, [_VP, _VP]),
     "pd_morton_keys": (_I, [_VP, _VP, _I, _VP]),
     "pd_partition_vertices": (_I, [_I, _I, _VP]),
     "pd_cholesky_factor": (_I, [_I, _VP, _VP, _VP, _PI, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
@@ -309,6 +310,12 @@ class Layout:
         _check(lib().pd_layout_tile_table(self._h, _p(self.tile_table)))
         self.num_tets = int(self.tile_tet_start[-1])                 # (a trimmed rank layout holds fewer tets than its plan's tiles)
         self.tet_order, self.tet_new = self.tet_order[:self.num_tets], self.tet_new[:self.num_tets]
+
+    def matrix_diag(self):
+        """SolverPrepare's matrix_diag per layout vertex, as Engine::prepare computes it (host only)."""
+        md = np.zeros(len(self.vert_order), np.float32)
+        _check(lib().pd_layout_matrix_diag(self._h, _p(md)))
+        return md
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:

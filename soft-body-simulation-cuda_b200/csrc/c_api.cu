@@ -276,6 +276,16 @@ int pd_layout_get_vstage(const pd_layout* l, uint32_t* vstage)
     std::memcpy(vstage, l->L.vstage.data(), l->L.vstage.size() * 4);
     return PD_OK;
 }
+int pd_layout_matrix_diag(const pd_layout* l, float* md)
+{
+    PD_TRY
+    if (!l || !md) return fail(PD_ERR_INVALID, "NULL argument");
+    std::vector<float> v;
+    matrix_diag_host(l->L, v);
+    std::memcpy(md, v.data(), v.size() * sizeof(float));
+    return PD_OK;
+    PD_CATCH_INT
+}
 int pd_morton_keys(const float* X, const uint32_t* Tet, int nT, uint32_t* keys)
 {
     PD_TRY

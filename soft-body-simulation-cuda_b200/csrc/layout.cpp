@@ -405,6 +405,45 @@ void build_layout(int nV, int nT, const float* X, const uint32_t* Tet, const flo
     build_tiles(nV, nT, L.tetNew.data(), Br.data(), wr.data(), L);
 }
 
+// matrix_diag[v] = sum over the tets incident to v of w_t |col_i(B^T G)|^2 (PdUtil::computeSiTSi, pdUtil.cu:16-24), read back
+// from the tile records, in ascending GLOBAL tet order: a rank keeps its interior tiles first and may have re-packed its
+// boundary tiles (Layout::tetGlobal), and the float sums must not depend on the world size.
+void matrix_diag_host(const Layout& L, std::vector<float>& md)
+{
+    md.assign((size_t)L.nV, 0.f);
+    struct TetRef { uint32_t global; uint32_t tile, tl; };
+    std::vector<TetRef> order; order.reserve((size_t)L.nT);
+    size_t t = 0;
+    for (int ti = 0; ti < L.nTiles; ++ti) {
+        const uint32_t n = L.tileTetStart[(size_t)ti + 1] - L.tileTetStart[(size_t)ti];
+        for (uint32_t tl = 0; tl < n; ++tl, ++t) order.push_back(TetRef{L.tetGlobal.empty() ? (uint32_t)t : L.tetGlobal[t], (uint32_t)ti, tl});
+    }
+    if (!L.tetGlobal.empty()) std::sort(order.begin(), order.end(), [](const TetRef& a, const TetRef& b) { return a.global < b.global; });
+    int curTile = -1;
+    const uint8_t* rec = nullptr; TileHeader h{}; const uint32_t* vstage = nullptr;
+    for (const TetRef& r : order) {
+        if ((int)r.tile != curTile) {
+            curTile = (int)r.tile;
+            rec = L.records.data() + L.tileRecOff[r.tile];
+            std::memcpy(&h, rec, sizeof(h));
+            vstage = L.vstage.data() + h.slotBase;      // the corner words hold staging slots
+        }
+        float B[12];
+        for (uint32_t j = 0; j < 12; ++j) std::memcpy(&B[j], rec + tile_tet_word(h.nTets, r.tl, j), 4);
+        const float w = B[9];
+        uint32_t cw[2]; std::memcpy(cw, B + 10, 8);
+        const uint32_t loc[4] = {(cw[0] >> 4) & 0xffu, (cw[0] >> 20) & 0xffu, (cw[1] >> 4) & 0xffu, (cw[1] >> 20) & 0xffu};
+        for (int i = 0; i < 4; ++i) {
+            float col[3];
+            for (int c = 0; c < 3; ++c)
+                col[c] = (i == 0) ? ((-B[0 * 3 + c] - B[1 * 3 + c]) - B[2 * 3 + c]) : B[(i - 1) * 3 + c];
+            // computeSiTSi as nvcc fuses it: fma(c2,c2, fma(c0,c0, c1*c1)), then * (V0*mu)
+            const float kii = std::fma(col[2], col[2], std::fma(col[0], col[0], col[1] * col[1]));
+            md[vstage[loc[i]] & ~TILE_OWNER_BIT] += kii * w;
+        }
+    }
+}
+
 void build_system_matrix(const Layout& L, const float*, const float* DmInv, const float* w, const float* c,
                          CsrMatrix& A, std::vector<float>& matrixDiag)
 {

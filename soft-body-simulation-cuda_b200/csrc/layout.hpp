@@ -149,6 +149,8 @@ struct CsrMatrix {
     std::vector<int> rowPtr, col;
     std::vector<float> val;
 };
+// matrix_diag of PdSolver::SolverPrepare (pdUtil.cu:16-24) from the tile records, per layout-local vertex
+void matrix_diag_host(const Layout& L, std::vector<float>& md);
 void build_system_matrix(const Layout& L, const float* Xnew, const float* DmInv /*reordered*/, const float* w /*reordered*/,
                          const float* c /*nV renumbered*/, CsrMatrix& A, std::vector<float>& matrixDiag);
 

@@ -297,51 +297,13 @@ void Engine::prepare()
 {   // PdSolver::SolverPrepare (pdSolver.cu:40-139): matrix_diag and the dt baked into DBC rows.
     // matrix_diag[v] = sum over incident tets (ascending reordered order) of w_t |col_i(B^T G)|^2
     Impl& d = *d_;
-    d.hostMd.assign((size_t)nV_, 0.f);
     d.hostWPrepared.clear(); d.hostWPrepared.reserve((size_t)nT_);
     for (int ti = 0; ti < L_.nTiles; ++ti) {
         const uint8_t* rec = L_.records.data() + L_.tileRecOff[ti];
         TileHeader h; std::memcpy(&h, rec, sizeof(h));
         for (uint32_t t = 0; t < h.nTets; ++t) { float w; std::memcpy(&w, rec + tile_tet_word(h.nTets, t, 9), 4); d.hostWPrepared.push_back(w); }
     }
-    // tets in ascending GLOBAL order (a rank keeps its interior tiles first, and may have re-packed its boundary tiles):
-    // the float sums must not depend on the world size
-    struct TetRef { uint32_t global; uint32_t tile, tl; };
-    std::vector<TetRef> order; order.reserve((size_t)nT_);
-    {
-        size_t t = 0;
-        for (int ti = 0; ti < L_.nTiles; ++ti) {
-            const uint32_t n = L_.tileTetStart[(size_t)ti + 1] - L_.tileTetStart[(size_t)ti];
-            for (uint32_t tl = 0; tl < n; ++tl, ++t) order.push_back(TetRef{L_.tetGlobal.empty() ? (uint32_t)t : L_.tetGlobal[t], (uint32_t)ti, tl});
-        }
-        if (!L_.tetGlobal.empty()) std::sort(order.begin(), order.end(), [](const TetRef& a, const TetRef& b) { return a.global < b.global; });
-    }
-    {
-        int curTile = -1;
-        const uint8_t* rec = nullptr; TileHeader h{}; const uint32_t* vstage = nullptr;
-        for (const TetRef& r : order) {
-            if ((int)r.tile != curTile) {
-                curTile = (int)r.tile;
-                rec = L_.records.data() + L_.tileRecOff[r.tile];
-                std::memcpy(&h, rec, sizeof(h));
-                vstage = L_.vstage.data() + h.slotBase;      // the corner words hold staging slots
-            }
-            const uint32_t t = r.tl;
-            float B[12];
-            for (uint32_t j = 0; j < 12; ++j) std::memcpy(&B[j], rec + tile_tet_word(h.nTets, t, j), 4);
-            const float w = B[9];
-            uint32_t cw[2]; std::memcpy(cw, B + 10, 8);
-            const uint32_t loc[4] = {(cw[0] >> 4) & 0xffu, (cw[0] >> 20) & 0xffu, (cw[1] >> 4) & 0xffu, (cw[1] >> 20) & 0xffu};
-            for (int i = 0; i < 4; ++i) {
-                float col[3];
-                for (int c = 0; c < 3; ++c)
-                    col[c] = (i == 0) ? ((-B[0 * 3 + c] - B[1 * 3 + c]) - B[2 * 3 + c]) : B[(i - 1) * 3 + c];
-                // computeSiTSi as nvcc fuses it: fma(c2,c2, fma(c0,c0, c1*c1)), then * (V0*mu)
-                const float kii = std::fma(col[2], col[2], std::fma(col[0], col[0], col[1] * col[1]));
-                d.hostMd[vstage[loc[i]] & ~TILE_OWNER_BIT] += kii * w;
-            }
-        }
-    }
+    matrix_diag_host(L_, d.hostMd);        // layout.cpp: ascending GLOBAL tet order, so the float sums do not depend on the world size
     CUDA_CHECK(cudaMemcpyAsync(d.md, d.hostMd.data(), (size_t)nV_ * 4, cudaMemcpyHostToDevice, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     dt2Prepared_ = params_.dt * params_.dt;

@@ -112,3 +112,26 @@ def test_trimmed_rank_layouts_keep_every_owned_slot(pd, assets, scene_name, worl
                 assert (int(L.vlist[a]) & OWNER) == (int(G.vlist[b]) & OWNER)
     print(f"{scene_name} world {world}: tets evaluated over all ranks {full} -> {trimmed} (mesh {nT}): redundant {full / nT - 1:.3f} -> {trimmed / nT - 1:.3f}")
     assert trimmed < full
+
+
+def test_matrix_diag_host_vs_oracle_and_across_world_sizes(pd, O, assets, monkeypatch):
+    """SolverPrepare's matrix_diag (computeSiTSi, pdUtil.cu:16-24) as Engine::prepare computes it from the tile records:
+    equal to the oracle's up to the summation order (the reordered tets), and BIT-identical for every owned vertex of every
+    rank layout, trimmed or not -- the sums run in ascending global tet order on every world size."""
+    import meshes
+    sc = pd.Scene.from_json(assets["json"], "C5 house&sphere")
+    osc, p = meshes.oracle_scene(O, assets, "C5 house&sphere")
+    mdo = osc.setup(O.make_params(dt=p["dt"], gravity=p["gravity"], num_iterations=5))[0]
+    G = sc.layout()
+    md = G.matrix_diag()
+    assert np.allclose(md, mdo[G.vert_order], rtol=2e-6, atol=0)
+    for trim in ("0", "1"):
+        for world in (2, 3):
+            for rank in range(world):
+                monkeypatch.setenv("PD_DIST_TRIM", trim)
+                P = pd.RankPlan(G, world, rank)
+                L = P.local_layout(G)
+                monkeypatch.delenv("PD_DIST_TRIM", raising=False)
+                mdl = L.matrix_diag()
+                own = md[P.first_owned:P.first_owned + P.num_owned]
+                assert np.array_equal(mdl[:P.num_owned].view(np.uint32), own.view(np.uint32)), (trim, world, rank)
