@@ -350,7 +350,8 @@ def run_b200(args):
                    "initial_velocity": "0" if batch else "0.5*sin(x/7) y^", "l2": (f"inputs larger than L2: tile stream {info['tile_stream_bytes'] / 1e6:.0f} MB per iteration, no flush needed" if info["tile_stream_bytes"] > 2 * 126e6
                           else f"working set smaller than L2 (tile stream {info['tile_stream_bytes'] / 1e6:.0f} MB): not flushed -- 100 iterations per step re-read the same stream, L2-resident is this workload's steady state"),
                    "finite": finite, "parallelism": "single GPU" if world == 1 else ("contexts sharded 64 per GPU, no communication" if batch else f"vertex partition over {world} GPUs, tile-replicated boundary, NVLink peer-memory halo push + flags per PD iteration"),
-                   "multi_gpu": dist_info, "halo_ok": halo_ok},
+                   "multi_gpu": dist_info, "halo_ok": halo_ok,
+                   "experiments": {k: os.environ[k] for k in ("PD_DIST_TRIM", "PD_B200_LIB", "PD_PDL", "PD_NO_STAGE_COLOR") if os.environ.get(k)} or None},
         "clocks": clocks,
         "e2e": {"value": nT_job * iters / (e2e_ms * 1e-3) / 1e6, "unit": "Mtet-updates/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": job_bytes, "d2h_bytes_per_step": job_bytes, "steps": e2e_steps,
