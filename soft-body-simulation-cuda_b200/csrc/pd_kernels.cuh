@@ -3,7 +3,14 @@
 // the roofline of each.
 #pragma once
 #include <cstdint>
+#ifdef PD_HOST_EMU
+#include "host_emu.hpp"      // tests/emu: the kernels' source compiled for the host by the CPU test suite (TEST ONLY, see there);
+                             // every PTX helper below has a host branch next to its asm
+#define PD_DYN_SMEM(name) PD_EMU_DYN_SMEM(name)
+#else
 #include <cuda_runtime.h>
+#define PD_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
+#endif
 
 #include "layout.hpp"
 #include "rotation.cuh"
@@ -19,6 +26,19 @@ struct DevFixedBodies {
 };
 
 // ------------------------------------------------------------------ mbarrier / bulk-copy (TMA) PTX
+#ifdef PD_HOST_EMU
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)(static_cast<const uint8_t*>(p) - pd_emu::cta->smem); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t) { pd_emu::mbar_init(bar); }
+__device__ __forceinline__ void fence_barrier_init() {}
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { pd_emu::mbar_expect(bar, bytes); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { while (!pd_emu::mbar_test(bar, parity)) std::this_thread::yield(); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    std::memcpy(dst, src, bytes);
+    pd_emu::mbar_complete(bar, bytes);
+}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
@@ -47,11 +67,23 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+#endif
 
 // L2 cache policies (the encodings CUTLASS uses for createpolicy.fractional.L2::evict_*): the tile
 // stream is read once per iteration and is far larger than L2 -> evict_first; the per-vertex arrays the
 // gathers hit (positions, b0) are re-read every iteration and fit in L2 -> evict_last.
 constexpr unsigned long long L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
+#ifdef PD_HOST_EMU
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, unsigned long long) { bulk_g2s(dst, src, bytes, bar); }
+__device__ __forceinline__ void cp_async16_hint(uint32_t dstShared, const void* src, unsigned long long) { std::memcpy(pd_emu::cta->smem + dstShared, src, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+__device__ __forceinline__ void cp_async_wait_all() {}
+__device__ __forceinline__ void cp_async_wait_1() {}
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_launch_dependents() {}
+__device__ __forceinline__ void prefetch_l2(const void*) {}
+__device__ __forceinline__ float4 ldg_hint(const float4* p, unsigned long long) { return *p; }
+#else
 __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, unsigned long long policy)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
@@ -79,6 +111,7 @@ __device__ __forceinline__ float4 ldg_hint(const float4* p, unsigned long long p
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
     return v;
 }
+#endif
 
 // ------------------------------------------------------------------ multi-GPU halo exchange
 // Every rank owns an exchange window [q0 | q1 | q2 | flags[world] | epoch | ticket | status] that its
@@ -109,6 +142,10 @@ struct DistWait {
 };
 constexpr long long DIST_WAIT_LIMIT_CYCLES = 20000000000ll;    // ~10 s: a hung peer must not hang this GPU
 
+#ifdef PD_HOST_EMU
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+#else
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
 {
     unsigned long long v;
@@ -119,6 +156,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+#endif
 // wait until every neighbour's flag has reached `need` (= this rank's push count including this phase's push)
 __device__ __forceinline__ void dist_wait(const DistWait& w, int tid, unsigned long long need)
 {
@@ -254,6 +292,10 @@ __device__ __forceinline__ float dot3_nv(float a0, float b0, float a1, float b1,
 {   // a0*b0 + a1*b1 + a2*b2 as nvcc contracts the reference's glm products
     return __fmaf_rn(a2, b2, __fmaf_rn(a0, b0, __fmul_rn(a1, b1)));
 }
+#ifdef PD_HOST_EMU
+__device__ __forceinline__ float4 ldg_stream(const void* p) { return *static_cast<const float4*>(p); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void*, uint32_t) {}
+#else
 __device__ __forceinline__ float4 ldg_stream(const void* p)
 {   // read-once stream: no L1 allocation, L2 evict_first
     float4 v;
@@ -265,6 +307,7 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+#endif
 
 // one H-scratch entry (x, y, z) at byte offset `off` of the tile's scratch Hb
 __device__ __forceinline__ float4 h_load(const uint8_t* Hb, uint32_t off)
@@ -451,7 +494,7 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
         unsigned long long* __restrict__ prof, DistWait dw)
 {
     // prof (may be null): per-phase clock64 totals of warp 0 of every CTA, 8 counters per CTA (scripts/phase_profile.py)
-    extern __shared__ __align__(128) uint8_t smem[];
+    PD_DYN_SMEM(smem);
     uint64_t* cbar = reinterpret_cast<uint64_t*>(smem + LOCAL_OFF_BAR);   // part C buffers 0, 1
     const int tid = threadIdx.x;
     const int nIt = ((int)blockIdx.x < nTiles) ? (nTiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;

@@ -14,7 +14,11 @@
 //    reference uses -- written with explicit single-rounding intrinsics so that it returns the
 //    same bits as the CPU oracle (oracle/pd_oracle.c:o_svd3).
 #pragma once
+#ifdef PD_HOST_EMU
+#include "host_emu.hpp"      // tests/emu (TEST ONLY): the packed operations below have host branches, one rounding per half
+#else
 #include <cuda_runtime.h>
+#endif
 
 namespace pdb200 {
 
@@ -256,6 +260,13 @@ __device__ __forceinline__ bool rotation_newton(const Mat3& Fm, Mat3& Rm)
 // may be a scalar broadcast, have its halves swapped and either half negated at no cost (ptxas folds
 // make_float2(s, s), make_float2(a.y, a.x), make_float2(-a.x, a.y) into operand modifiers).  The local kernel is
 // bound by instruction issue, so its phase B works on matrix COLUMNS stored as (rows 0 and 1 packed, row 2 scalar).
+#ifdef PD_HOST_EMU
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return make_float2(std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float rcp_approx(float x) { return 1.0f / x; }
+#else
 __device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c)
 {
     float2 d;
@@ -288,13 +299,14 @@ __device__ __forceinline__ float2 f2sub(float2 a, float2 b)
         : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
     return d;
 }
-__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
 __device__ __forceinline__ float rcp_approx(float x)
 {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+#endif
+__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
 
 struct Col3 {          // one matrix column: rows 0 and 1 packed, row 2 scalar
     float2 xy;

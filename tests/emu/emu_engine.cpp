@@ -1,0 +1,225 @@
+// TEST INFRASTRUCTURE ONLY.  The product's kernels (csrc/pd_kernels.cuh, rotation.cuh) compiled for the HOST with
+// -DPD_HOST_EMU (tests/emu/host_emu.hpp) and driven the way Engine::enqueuePredict / enqueueIteration / enqueueFinish
+// (csrc/pd_engine.cu) drive them on the GPU, on the device layout built by the product's own layout.cpp.  One or several
+// ranks in lock step (the halo push is a host copy along the plan's push lists, as k_halo_push does it).  Used by
+// tests/test_kernel_emulation.py to check the kernels' logic against the oracle without a GPU, including the
+// experiments (PD_H_PLANES at compile time, PD_DIST_TRIM at run time).  Nothing here is linked into libpd_b200.so.
+#include <cstdio>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../soft-body-simulation-cuda_b200/csrc/pd_kernels.cuh"
+
+using namespace pdb200;
+
+namespace {
+
+struct Rank {
+    Layout L;
+    RankPlan P;
+    int nV = 0, nOwn = 0;
+    std::vector<uint32_t> tileTab;
+    std::vector<float4> Pslots, q[3], b0, X, V, XT, X0, dbcx, offX;
+    std::vector<float2> cc;
+    std::vector<float> mass, dbc, md, more;
+};
+
+struct Emu {
+    int nVg = 0, world = 1, rotMode = 0, grid = 3, numDBC = 0;
+    bool drag = false;
+    float target[3] = {0, 0, 0};
+    float dt2Prepared = 0.f;
+    bool ready = false;
+    std::vector<float> fb;
+    DevFixedBodies dfb{};
+    std::vector<std::unique_ptr<Rank>> ranks;
+    std::string err;
+};
+
+void push(Emu& e, int buf)
+{   // k_halo_push: q_peer[dst] = q[src]
+    if (e.world == 1) return;
+    for (auto& r : e.ranks)
+        for (size_t i = 0; i < r->P.pushSrc.size(); ++i)
+            e.ranks[(size_t)r->P.pushRank[i]]->q[buf][r->P.pushDst[i]] = r->q[buf][r->P.pushSrc[i]];
+}
+
+template <int RM, bool BASE>
+void step_once(Emu& e, float dt, float gravity, float rho, float muN, float muT, int iters)
+{
+    const float dtInv = 1.0f / dt, wdbc = 1e6f * (dtInv * dtInv);
+    const int vb = 256;
+    for (auto& rp : e.ranks) {
+        Rank& r = *rp;
+        const unsigned vg = (unsigned)((r.nOwn + vb - 1) / vb);
+        const DragArgs dr{r.more.data(), r.offX.data(), r.dbcx.data(), e.target[0], e.target[1], e.target[2], e.numDBC > 0 ? 1 : 0};
+        if (e.drag) pd_emu::launch_flat(vg, vb, k_predict<true>, r.nOwn, r.X.data(), r.V.data(), r.mass.data(), r.dbc.data(), r.md.data(), dt, e.dt2Prepared,
+                                        gravity, r.q[0].data(), r.q[2].data(), r.b0.data(), r.cc.data(), dr);
+        else pd_emu::launch_flat(vg, vb, k_predict<false>, r.nOwn, r.X.data(), r.V.data(), r.mass.data(), r.dbc.data(), r.md.data(), dt, e.dt2Prepared,
+                                 gravity, r.q[0].data(), r.q[2].data(), r.b0.data(), r.cc.data(), DragArgs{});
+    }
+    push(e, 0); push(e, 2);
+    float omega = 1.0f;
+    for (int i = 0; i < iters; ++i) {
+        const int ic = i % 3, in = (i + 1) % 3, ip = (i + 2) % 3;
+        if (i <= 10) omega = 1;
+        else if (i == 11) omega = 2 / (2 - rho * rho);
+        else omega = 4 / (4 - rho * rho * omega);
+        for (auto& rp : e.ranks) {
+            Rank& r = *rp;
+            const unsigned vg = (unsigned)((r.nOwn + vb - 1) / vb);
+            const unsigned grid = (unsigned)std::min(r.L.nTiles, e.grid);
+            DistWait dw{};                  // lock step: the pushes are host copies between the launches, nobody waits
+            dw.firstTile = 0x7fffffff;
+            pd_emu::launch(grid, (unsigned)TILE_T, LOCAL_SMEM_BYTES, k_local<RM, true, false>, (const uint8_t*)r.L.records.data(), (const uint32_t*)r.tileTab.data(),
+                           r.L.nTiles, (const uint32_t*)r.L.vstage.data(), (const uint32_t*)r.L.vlist.data(), (const float4*)r.q[ic].data(),
+                           (const float4*)r.b0.data(), r.Pslots.data(), (unsigned long long*)nullptr, dw);
+            if (e.drag) pd_emu::launch_flat(vg, vb, k_vertex_jacobi<BASE, true>, r.nOwn, (const float4*)r.q[ic].data(), (const float4*)r.q[ip].data(), r.q[in].data(),
+                                            (const float4*)r.dbcx.data(), (const float4*)r.b0.data(), (const float2*)r.cc.data(), (const uint32_t*)r.L.vslotPtr.data(),
+                                            (const uint32_t*)r.L.vslot.data(), (const float4*)r.Pslots.data(), omega, wdbc);
+            else pd_emu::launch_flat(vg, vb, k_vertex_jacobi<BASE, false>, r.nOwn, (const float4*)r.q[ic].data(), (const float4*)r.q[ip].data(), r.q[in].data(),
+                                     (const float4*)r.dbcx.data(), (const float4*)r.b0.data(), (const float2*)r.cc.data(), (const uint32_t*)r.L.vslotPtr.data(),
+                                     (const uint32_t*)r.L.vslot.data(), (const float4*)r.Pslots.data(), omega, wdbc);
+        }
+        push(e, in);
+    }
+    for (auto& rp : e.ranks) {
+        Rank& r = *rp;
+        const unsigned vg = (unsigned)((r.nOwn + vb - 1) / vb);
+        if (e.drag) pd_emu::launch_flat(vg, vb, k_finish<true>, r.nOwn, (const float4*)r.q[iters % 3].data(), dtInv, r.X.data(), r.XT.data(), r.V.data(), e.dfb, muT, muN,
+                                        (const float*)r.more.data());
+        else pd_emu::launch_flat(vg, vb, k_finish<false>, r.nOwn, (const float4*)r.q[iters % 3].data(), dtInv, r.X.data(), r.XT.data(), r.V.data(), e.dfb, muT, muN,
+                                 (const float*)nullptr);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* emu_variant(void) { return PD_H_PLANES ? "planes" : "default"; }
+
+// planes: 6 floats each (p0, up); spheres: 4 (c, r); cylinders: 7 (c, axis, r) -- the arrays the collision kernels consume
+void* emu_create(int nV, int nT, const float* X, const uint32_t* Tet, const float* mass, const float* mu, const float* DBC,
+                 int nPlanes, const float* planes, int nSpheres, const float* spheres, int nCyls, const float* cyls,
+                 int rotMode, int reorder, int world, int trim, int grid)
+{
+    auto e = std::make_unique<Emu>();
+    try {
+        e->nVg = nV; e->world = world; e->rotMode = rotMode; e->grid = grid > 0 ? grid : 3;
+        for (int i = 0; i < nV; ++i) if (DBC && DBC[i] > 0.f) e->numDBC++;
+        e->fb.insert(e->fb.end(), planes, planes + 6 * (size_t)nPlanes);
+        e->fb.insert(e->fb.end(), spheres, spheres + 4 * (size_t)nSpheres);
+        e->fb.insert(e->fb.end(), cyls, cyls + 7 * (size_t)nCyls);
+        e->fb.push_back(0.f);
+        e->dfb.nPlanes = nPlanes; e->dfb.nSpheres = nSpheres; e->dfb.nCyls = nCyls;
+        e->dfb.planes = e->fb.data(); e->dfb.spheres = e->fb.data() + 6 * (size_t)nPlanes; e->dfb.cyls = e->dfb.spheres + 4 * (size_t)nSpheres;
+        Layout G;
+        build_layout(nV, nT, X, Tet, mu, reorder != 0, G);
+        for (int rk = 0; rk < world; ++rk) {
+            auto r = std::make_unique<Rank>();
+            if (world == 1) { r->L = G; r->nOwn = G.nV; }
+            else {
+                build_rank_plan(G, world, rk, r->P, trim != 0);
+                extract_rank_layout(G, r->P, r->L);
+                r->nOwn = r->P.nOwn;
+            }
+            const int n = r->nV = r->L.nV;
+            build_tile_table(r->L, r->tileTab);
+            r->Pslots.assign((size_t)r->L.nTiles * TILE_NLMAX, make_float4(0, 0, 0, 0));
+            for (auto& qb : r->q) qb.assign((size_t)n, make_float4(0, 0, 0, 0));
+            r->b0.assign((size_t)n, make_float4(0, 0, 0, 0)); r->V = r->b0; r->offX = r->b0;
+            r->X.resize((size_t)n); r->cc.assign((size_t)n, float2{0, 0});
+            r->mass.resize((size_t)n); r->dbc.resize((size_t)n); r->more.assign((size_t)n, 0.f);
+            for (int v = 0; v < n; ++v) {
+                const uint32_t o = r->L.vertOrder[(size_t)v];
+                r->mass[(size_t)v] = mass[o]; r->dbc[(size_t)v] = DBC ? DBC[o] : 0.f;
+                r->X[(size_t)v] = make_float4(X[3 * (size_t)o], X[3 * (size_t)o + 1], X[3 * (size_t)o + 2], 0.f);
+            }
+            r->XT = r->X; r->X0 = r->X; r->dbcx = r->X;
+            e->ranks.push_back(std::move(r));
+        }
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, "emu_create: %s\n", ex.what());
+        return nullptr;
+    }
+    return e.release();
+}
+
+void emu_destroy(void* h) { delete static_cast<Emu*>(h); }
+
+int emu_step(void* h, float dt, float gravity, float rho, float muN, float muT, int iters, int nSteps)
+{
+    Emu& e = *static_cast<Emu*>(h);
+    try {
+        if (!e.ready) {     // Engine::prepare
+            for (auto& r : e.ranks) matrix_diag_host(r->L, r->md);
+            e.dt2Prepared = dt * dt;
+            e.ready = true;
+        }
+        for (int s = 0; s < nSteps; ++s) {
+            if (e.rotMode == 1) step_once<1, false>(e, dt, gravity, rho, muN, muT, iters);
+            else step_once<0, true>(e, dt, gravity, rho, muN, muT, iters);
+        }
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, "emu_step: %s\n", ex.what());
+        return 1;
+    }
+    return 0;
+}
+
+static void gather3(const Emu& e, const std::vector<float4> Rank::*field, float* out)
+{
+    if (!out) return;
+    for (const auto& r : e.ranks)
+        for (int v = 0; v < r->nOwn; ++v) {
+            const size_t o = r->L.vertOrder[(size_t)v];
+            const float4 a = ((*r).*field)[(size_t)v];
+            out[3 * o] = a.x; out[3 * o + 1] = a.y; out[3 * o + 2] = a.z;
+        }
+}
+void emu_get(void* h, float* X, float* V, float* XT)
+{
+    const Emu& e = *static_cast<Emu*>(h);
+    gather3(e, &Rank::X, X); gather3(e, &Rank::V, V); gather3(e, &Rank::XT, XT);
+}
+void emu_set(void* h, const float* X, const float* V, const float* XT)
+{
+    Emu& e = *static_cast<Emu*>(h);
+    for (auto& r : e.ranks)
+        for (int v = 0; v < r->nV; ++v) {
+            const size_t o = r->L.vertOrder[(size_t)v];
+            if (X) r->X[(size_t)v] = make_float4(X[3 * o], X[3 * o + 1], X[3 * o + 2], 0.f);
+            if (V) r->V[(size_t)v] = make_float4(V[3 * o], V[3 * o + 1], V[3 * o + 2], 0.f);
+            if (XT) r->XT[(size_t)v] = make_float4(XT[3 * o], XT[3 * o + 1], XT[3 * o + 2], 0.f);
+        }
+}
+// mouse drag, single rank only (like the engine); more == NULL clears
+int emu_set_drag(void* h, const float* more, const float* off, const float* target)
+{
+    Emu& e = *static_cast<Emu*>(h);
+    if (e.world != 1) return 1;
+    Rank& r = *e.ranks[0];
+    e.drag = false;
+    for (int v = 0; v < r.nV; ++v) {
+        const size_t o = r.L.vertOrder[(size_t)v];
+        r.more[(size_t)v] = more ? more[o] : 0.f;
+        if (more && off) r.offX[(size_t)v] = make_float4(off[3 * o], off[3 * o + 1], off[3 * o + 2], 0.f);
+        e.drag = e.drag || r.more[(size_t)v] > 0.f;
+    }
+    if (target) for (int k = 0; k < 3; ++k) e.target[k] = target[k];
+    return 0;
+}
+void emu_info(void* h, long long* tetsEvaluated, long long* tiles, long long* ghosts)
+{
+    const Emu& e = *static_cast<Emu*>(h);
+    long long t = 0, ti = 0, g = 0;
+    for (const auto& r : e.ranks) { t += r->L.nT; ti += r->L.nTiles; g += r->nV - r->nOwn; }
+    if (tetsEvaluated) *tetsEvaluated = t;
+    if (tiles) *tiles = ti;
+    if (ghosts) *ghosts = g;
+}
+
+}  // extern "C"
