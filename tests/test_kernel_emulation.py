@@ -14,6 +14,7 @@ import pytest
 
 import meshes
 
+pytestmark = pytest.mark.timeout(1200)        # 256 OS threads per emulated CTA: a scheduling problem must not hang the suite
 HERE = os.path.dirname(os.path.abspath(__file__))
 EMU = os.path.join(HERE, "emu")
 _libs = {}
@@ -171,6 +172,28 @@ def test_drag_kernels_vs_oracle(pd, O, rot_mode):
     worst = max(worst, meshes.rel_err(emu.get()[0], osc.get()[0], scale))
     print(f"emulated drag kernels, rot_mode {rot_mode}: worst rel err vs oracle {worst:.2e}")
     assert worst <= 2e-5 and np.abs(emu.get()[1][held, 1]).min() > 0
+
+
+def test_cube_corner_dragged_faithful_kernels_bit_exact_vs_oracle(pd, O, assets):
+    """What tests/test_gpu_zz_drag.py::test_control_kernel_and_reset_vs_oracle expects of the GPU: with a corner of the cube
+    held by Control_Kernel's arrays, the faithful kernels still match the oracle bit for bit."""
+    sc, p = _scene(pd, assets, "C1 cube", 100, dt=1 / 60)
+    osc, _ = meshes.oracle_scene(O, assets, "C1 cube")
+    op = _oparams(O, p)
+    emu = Emu(pd, sc, rot_mode=1, reorder=0)
+    emu.step(2); osc.step(op, 2)
+    target = np.float32([0.5, 31.0, 0.25])
+    osc.drag_select(3, target)
+    more, off, _ = osc.get_drag()
+    emu.set_drag(more, off, target)
+    emu.step(2); osc.step(op, 2)
+    for a, b in zip(emu.get(), osc.get()):
+        assert np.array_equal(_bits(a), _bits(b))
+    assert np.array_equal(emu.get()[2][3], target)
+    emu.set_drag(None); osc.set_drag(None)
+    emu.step(2); osc.step(op, 2)
+    for a, b in zip(emu.get(), osc.get()):
+        assert np.array_equal(_bits(a), _bits(b))
 
 
 @pytest.mark.parametrize("world,trim", [(2, 0), (3, 0), (3, 1), (8, 1)])
