@@ -15,6 +15,10 @@
 #include "layout.hpp"
 #include "rotation.cuh"
 
+#ifndef PD_PHASEC_PRED
+#define PD_PHASEC_PRED 0
+#endif
+
 namespace pdb200 {
 
 // ------------------------------------------------------------------ device-side fixed bodies
@@ -381,10 +385,21 @@ __device__ __forceinline__ void local_phase_c(const uint8_t* Cb, const uint8_t* 
         uint32_t e0 = row[0], e1 = (1u < nR) ? row[32] : ZZ;
 #pragma unroll 1
         for (uint32_t r = 0; r < nR; r += 2) {
+#if PD_PHASEC_PRED
+            // EXPERIMENT (-DPD_PHASEC_PRED=1, variant library only): a pad is not loaded at all.  The lists of a group are
+            // sorted by length, so in its last rows whole quarter-warps hold nothing but pads, and a quarter-warp without an
+            // active lane costs the shared-memory pipe no wavefront (the rows are 70 % full on the grid)
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 h0 = ((e0 & 0xffffu) < TILE_ZERO_OFF) ? h_load(Hb, e0 & 0xffffu) : zero4;
+            const float4 h1 = ((e0 >> 16) < TILE_ZERO_OFF) ? h_load(Hb, e0 >> 16) : zero4;
+            const float4 h2 = ((e1 & 0xffffu) < TILE_ZERO_OFF) ? h_load(Hb, e1 & 0xffffu) : zero4;
+            const float4 h3 = ((e1 >> 16) < TILE_ZERO_OFF) ? h_load(Hb, e1 >> 16) : zero4;
+#else
             const float4 h0 = h_load(Hb, e0 & 0xffffu);
             const float4 h1 = h_load(Hb, e0 >> 16);
             const float4 h2 = h_load(Hb, e1 & 0xffffu);
             const float4 h3 = h_load(Hb, e1 >> 16);
+#endif
             const uint32_t* nx = row + 32u * (r + 2u);
             e0 = (r + 2u < nR) ? nx[0] : ZZ; e1 = (r + 3u < nR) ? nx[32] : ZZ;
             axy = f2add(axy, make_float2(h0.x, h0.y)); az = __fadd_rn(az, h0.z);

@@ -99,7 +99,7 @@ void step_once(Emu& e, float dt, float gravity, float rho, float muN, float muT,
 
 extern "C" {
 
-const char* emu_variant(void) { return PD_H_PLANES ? "planes" : "default"; }
+const char* emu_variant(void) { return PD_H_PLANES ? "planes" : (PD_PHASEC_PRED ? "pred" : "default"); }
 
 // planes: 6 floats each (p0, up); spheres: 4 (c, r); cylinders: 7 (c, axis, r) -- the arrays the collision kernels consume
 void* emu_create(int nV, int nT, const float* X, const uint32_t* Tet, const float* mass, const float* mu, const float* DBC,

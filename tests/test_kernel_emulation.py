@@ -121,7 +121,7 @@ def test_c1_cube_faithful_kernels_are_bit_exact_vs_oracle(pd, O, assets, variant
     assert emu.get()[2][:, 1].min() > -1e-3                        # came to rest on the plane
 
 
-@pytest.mark.parametrize("variant,rot_mode,tol", [("default", 1, 1e-4), ("default", 0, 1e-4), ("planes", 0, 1e-4)])
+@pytest.mark.parametrize("variant,rot_mode,tol", [("default", 1, 1e-4), ("default", 0, 1e-4), ("planes", 0, 1e-4), ("pred", 0, 1e-4)])
 def test_house_and_sphere_kernels_vs_oracle(pd, O, assets, variant, rot_mode, tol):
     """11 tiles over 3 emulated CTAs (several tiles per CTA: prologue, steady state and tail of the software pipeline),
     two bodies, fixed sphere + planes.  Faithful mode differs from the oracle only by the order of the per-tile partial
