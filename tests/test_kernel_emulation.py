@@ -174,6 +174,20 @@ def test_drag_kernels_vs_oracle(pd, O, rot_mode):
     assert worst <= 2e-5 and np.abs(emu.get()[1][held, 1]).min() > 0
 
 
+@pytest.mark.parametrize("variant", ["planes", "pred"])
+def test_experimental_variants_change_no_bit(pd, assets, variant):
+    """The k_local experiments only change HOW the H scratch is laid out / read: same contributions,
+    same summation order, so every state must equal the default kernels' bit for bit."""
+    sc, p = _scene(pd, assets, "C5 house&sphere", 20)
+    V0 = (0.3 * np.sin(sc.arrays()["X"][:, [1, 2, 0]])).astype(np.float32)
+    a, b = Emu(pd, sc, variant="default"), Emu(pd, sc, variant=variant)
+    a.set(V=V0); b.set(V=V0)
+    a.step(2); b.step(2)
+    for x, y in zip(a.get(), b.get()):
+        assert np.array_equal(_bits(x), _bits(y))
+    assert np.abs(a.get()[0] - sc.arrays()["X"]).max() > 1e-2
+
+
 def test_cube_corner_dragged_faithful_kernels_bit_exact_vs_oracle(pd, O, assets):
     """What tests/test_gpu_zz_drag.py::test_control_kernel_and_reset_vs_oracle expects of the GPU: with a corner of the cube
     held by Control_Kernel's arrays, the faithful kernels still match the oracle bit for bit."""
