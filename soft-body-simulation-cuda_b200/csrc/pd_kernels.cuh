@@ -418,19 +418,14 @@ __device__ __forceinline__ void local_phase_c(const uint8_t* Cb, const uint8_t* 
     if (writer) P[slotG + lane] = make_float4(sx, sy, sz, 0.f);
 }
 
-// phase B of one tet: record (r0, r1, r2) in registers, positions from the staging buffer qsb, the four corner
-// contributions into the quarter-warp's H scratch line
+// the contributions of ONE tet to the right-hand sides of its four vertices (PdUtil::computeLocal, pdUtil.cu:107-143):
+// F = Ds DmInv, rotation, H = w (R - F) DmInv^T G (Jacobi mode) or w R DmInv^T G (direct / CG modes).  B0..B8 = DmInv
+// (row-major), p0..p3 = the corner positions; shared by the tile kernel below and the per-body kernel (pd_body_kernel.cuh)
 template <int ROT_MODE, bool JACOBI>
-__device__ __forceinline__ void local_phase_b(const float4 r0, const float4 r1, const float4 r2, const uint8_t* qsb, uint8_t* Hline)
+__device__ __forceinline__ void tet_contrib(const float B0, const float B1, const float B2, const float B3, const float B4, const float B5, const float B6,
+                                            const float B7, const float B8, const float w, const float4 p0, const float4 p1, const float4 p2, const float4 p3,
+                                            float4& h0, float4& h1, float4& h2, float4& h3)
 {
-        const float B0 = r0.x, B1 = r0.y, B2 = r0.z, B3 = r0.w, B4 = r1.x, B5 = r1.y, B6 = r1.z, B7 = r1.w, B8 = r2.x;
-        const float w = r2.y;
-        const uint32_t c01 = __float_as_uint(r2.z), c23 = __float_as_uint(r2.w);
-        const float4 p0 = *reinterpret_cast<const float4*>(qsb + (c01 & 0x0ff0u));
-        const float4 p1 = *reinterpret_cast<const float4*>(qsb + ((c01 >> 16) & 0x0ff0u));
-        const float4 p2 = *reinterpret_cast<const float4*>(qsb + (c23 & 0x0ff0u));
-        const float4 p3 = *reinterpret_cast<const float4*>(qsb + ((c23 >> 16) & 0x0ff0u));
-        float4 h0, h1, h2, h3;
         bool done = false;
         if (ROT_MODE == 0) {
             // product default: packed FP32 (FFMA2) on matrix columns, rotation.cuh.  Edge k = p_{k+1} - p_0 is
@@ -496,6 +491,20 @@ __device__ __forceinline__ void local_phase_b(const float4 r0, const float4 r1, 
             h0.z = __fsub_rn(__fsub_rn(-h1.z, h2.z), h3.z);
             h0.w = h1.w = h2.w = h3.w = 0.f;
         }
+}
+
+// phase B of one tet: record (r0, r1, r2) in registers, positions from the staging buffer qsb, the four corner
+// contributions into the quarter-warp's H scratch line
+template <int ROT_MODE, bool JACOBI>
+__device__ __forceinline__ void local_phase_b(const float4 r0, const float4 r1, const float4 r2, const uint8_t* qsb, uint8_t* Hline)
+{
+        const uint32_t c01 = __float_as_uint(r2.z), c23 = __float_as_uint(r2.w);
+        const float4 p0 = *reinterpret_cast<const float4*>(qsb + (c01 & 0x0ff0u));
+        const float4 p1 = *reinterpret_cast<const float4*>(qsb + ((c01 >> 16) & 0x0ff0u));
+        const float4 p2 = *reinterpret_cast<const float4*>(qsb + (c23 & 0x0ff0u));
+        const float4 p3 = *reinterpret_cast<const float4*>(qsb + ((c23 >> 16) & 0x0ff0u));
+        float4 h0, h1, h2, h3;
+        tet_contrib<ROT_MODE, JACOBI>(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, p0, p1, p2, p3, h0, h1, h2, h3);
         h_store(Hline, 0u, c01 & 0xffffu, h0);
         h_store(Hline, 1u, c01 >> 16, h1);
         h_store(Hline, 2u, c23 & 0xffffu, h2);
