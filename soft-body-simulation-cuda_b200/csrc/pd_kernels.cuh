@@ -821,18 +821,14 @@ __device__ __forceinline__ void fb_respond(float3& vel, const float3 n, float kf
     vel.z = __fmaf_rn(vT.z, a, -__fmul_rn(vN.z, muN));
 }
 
-template <bool DRAG>
-__global__ void k_finish(int nV, const float4* __restrict__ qfinal, float dtInv, float4* __restrict__ X,
-                         float4* __restrict__ XTilde, float4* __restrict__ V, DevFixedBodies fb, float muT, float muN,
-                         const float* __restrict__ more)
+// one vertex of the end of step: q = the final iterate, xt = XTilde of the previous step
+__device__ __forceinline__ void finish_vertex(const float4 q, const float4 xt, float dtInv, bool dragged, const DevFixedBodies& fb, float muT, float muN,
+                                              float4* __restrict__ Xout, float4* __restrict__ XTout, float4* __restrict__ Vout)
 {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= nV) return;
-    const float4 q = qfinal[v], xt = XTilde[v];
     float3 vel = make_float3(__fmul_rn(__fsub_rn(q.x, xt.x), dtInv), __fmul_rn(__fsub_rn(q.y, xt.y), dtInv), __fmul_rn(__fsub_rn(q.z, xt.z), dtInv));
-    if (DRAG && more[v] > 0.f) vel = make_float3(0.f, 0.f, 0.f);      // updateVelPos, pdUtil.cu:187-188
+    if (dragged) vel = make_float3(0.f, 0.f, 0.f);      // updateVelPos, pdUtil.cu:187-188
     float3 x = make_float3(q.x, q.y, q.z);
-    X[v] = make_float4(x.x, x.y, x.z, 0.f);      // X keeps the un-projected position
+    *Xout = make_float4(x.x, x.y, x.z, 0.f);      // X keeps the un-projected position
     const float kf = __fmul_rn(__fadd_rn(muN, 1.f), muT);
     for (int j = 0; j < fb.nSpheres; ++j) {
         const float* s = fb.spheres + 4 * j;
@@ -873,8 +869,18 @@ __global__ void k_finish(int nV, const float4* __restrict__ qfinal, float dtInv,
             fb_respond(vel, n, kf, muN);
         }
     }
-    XTilde[v] = make_float4(x.x, x.y, x.z, 0.f);
-    V[v] = make_float4(vel.x, vel.y, vel.z, 0.f);
+    *XTout = make_float4(x.x, x.y, x.z, 0.f);
+    *Vout = make_float4(vel.x, vel.y, vel.z, 0.f);
+}
+
+template <bool DRAG>
+__global__ void k_finish(int nV, const float4* __restrict__ qfinal, float dtInv, float4* __restrict__ X,
+                         float4* __restrict__ XTilde, float4* __restrict__ V, DevFixedBodies fb, float muT, float muN,
+                         const float* __restrict__ more)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nV) return;
+    finish_vertex(qfinal[v], XTilde[v], dtInv, DRAG && more[v] > 0.f, fb, muT, muN, &X[v], &XTilde[v], &V[v]);
 }
 
 // ------------------------------------------------------------------ layout conversion
