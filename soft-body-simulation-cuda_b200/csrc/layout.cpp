@@ -567,6 +567,68 @@ void cholesky_factor(const CsrMatrix& A, CholFactor& F)
     for (int i = 0; i < n; ++i) { F.lCol[(size_t)fill[(size_t)i]] = i; F.lVal[(size_t)fill[(size_t)i]] = (float)diag[(size_t)i]; }
 }
 
+void build_body_batch(int nV, int nT, const float* X, const uint32_t* Tet, const float* mu, const std::vector<int>& bodyVertStart,
+                      const uint32_t* vertNewOfOld, BodyBatch& out)
+{
+    out = BodyBatch();
+    const size_t nB = bodyVertStart.size();
+    if (nB == 0) throw std::runtime_error("body batch: the scene names no bodies");
+    std::vector<float> B((size_t)nT * 9), V0((size_t)nT);
+    rest_shape(X, Tet, nT, B.data(), V0.data());
+    int t = 0;
+    for (size_t b = 0; b < nB; ++b) {
+        const int vb = bodyVertStart[b], ve = (b + 1 < nB) ? bodyVertStart[b + 1] : nV;
+        if (vb < 0 || ve <= vb || ve > nV) throw std::runtime_error("body batch: bad vertex range");
+        const int tb = t;
+        while (t < nT && (int)Tet[4 * (size_t)t] >= vb && (int)Tet[4 * (size_t)t] < ve) {
+            for (int k = 1; k < 4; ++k)
+                if ((int)Tet[4 * (size_t)t + k] < vb || (int)Tet[4 * (size_t)t + k] >= ve) throw std::runtime_error("body batch: a tet spans two bodies");
+            ++t;
+        }
+        const uint32_t nVb = (uint32_t)(ve - vb), nTb = (uint32_t)(t - tb);
+        if (nTb == 0) throw std::runtime_error("body batch: a body without tets");
+        if (nVb > 65535u || nTb > 16383u) throw std::runtime_error("body batch: body too large for the per-body kernel");
+        BodyDesc d{};
+        d.v0 = (uint32_t)out.verts.size(); d.nV = nVb; d.ptr0 = (uint32_t)out.incPtr.size(); d.nT = nTb;
+        d.inc0 = (uint32_t)out.inc.size(); d.recOff16 = (uint32_t)(out.rec.size() / 16);
+        for (int v = vb; v < ve; ++v) out.verts.push_back(vertNewOfOld ? vertNewOfOld[v] : (uint32_t)v);
+        // records: three planes of 16 bytes per tet
+        const size_t base = out.rec.size();
+        out.rec.resize(base + 48 * (size_t)nTb, 0);
+        std::vector<uint32_t> cnt((size_t)nVb + 1, 0);
+        std::vector<float> md((size_t)nVb, 0.f);
+        for (uint32_t tl = 0; tl < nTb; ++tl) {
+            const size_t tt = (size_t)tb + tl;
+            float tr[12];
+            for (int e = 0; e < 9; ++e) tr[e] = B[9 * tt + e];
+            const float w = std::fabs(V0[tt]) * mu[tt];
+            tr[9] = w;
+            uint32_t loc[4];
+            for (int k = 0; k < 4; ++k) { loc[k] = Tet[4 * tt + k] - (uint32_t)vb; cnt[loc[k] + 1]++; }
+            const uint32_t c01 = loc[0] | (loc[1] << 16), c23 = loc[2] | (loc[3] << 16);
+            std::memcpy(&tr[10], &c01, 4); std::memcpy(&tr[11], &c23, 4);
+            for (uint32_t j = 0; j < 12; ++j) std::memcpy(out.rec.data() + base + 16 * ((size_t)(j / 4) * nTb + tl) + 4 * (j % 4), &tr[j], 4);
+            for (int i = 0; i < 4; ++i) {       // computeSiTSi, as matrix_diag_host does it
+                float col[3];
+                for (int c = 0; c < 3; ++c) col[c] = (i == 0) ? ((-tr[0 * 3 + c] - tr[1 * 3 + c]) - tr[2 * 3 + c]) : tr[(i - 1) * 3 + c];
+                const float kii = std::fma(col[2], col[2], std::fma(col[0], col[0], col[1] * col[1]));
+                md[loc[i]] += kii * w;
+            }
+        }
+        for (uint32_t l = 0; l < nVb; ++l) cnt[l + 1] += cnt[l];
+        out.incPtr.insert(out.incPtr.end(), cnt.begin(), cnt.end());
+        std::vector<uint32_t> fill(cnt.begin(), cnt.end() - 1);
+        out.inc.resize(d.inc0 + 4 * (size_t)nTb);
+        for (uint32_t tl = 0; tl < nTb; ++tl)
+            for (uint32_t k = 0; k < 4; ++k) out.inc[d.inc0 + fill[Tet[4 * ((size_t)tb + tl) + k] - (uint32_t)vb]++] = (uint16_t)(tl * 4 + k);
+        out.md.insert(out.md.end(), md.begin(), md.end());
+        out.bodies.push_back(d);
+        out.nVmax = std::max(out.nVmax, (nVb + 31u) & ~31u);
+        out.nTmax = std::max(out.nTmax, (nTb + 31u) & ~31u);
+    }
+    if (t != nT) throw std::runtime_error("body batch: tets outside every body (bodies must own contiguous, ascending tet ranges)");
+}
+
 void partition_vertices(int nV, int world, std::vector<int>& vbeg)
 {
     vbeg.assign((size_t)world + 1, 0);

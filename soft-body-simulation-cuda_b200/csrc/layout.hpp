@@ -166,6 +166,29 @@ struct CholFactor {
 };
 void cholesky_factor(const CsrMatrix& A, CholFactor& F);
 
+// EXPERIMENT (PD_BODY_KERNEL=1, pd_body_kernel.cuh): per-body data of a scene made of many small soft bodies, one CTA per body.
+struct BodyDesc {           // device-visible POD, one per body
+    uint32_t v0, nV;        // its vertices: entries [v0, v0 + nV) of BodyBatch::verts / md; body-local id = position
+    uint32_t ptr0;          // its incidence pointers: incPtr[ptr0 .. ptr0 + nV], relative to inc0
+    uint32_t nT;            // its tets
+    uint32_t inc0;          // its incidence entries start at inc[inc0]; entry = body-local tet * 4 + corner
+    uint32_t recOff16;      // byte offset / 16 of its record planes in BodyBatch::rec (plane p of tet t: 16 * (p * nT + t))
+    uint32_t pad0, pad1;
+};
+struct BodyBatch {
+    std::vector<BodyDesc> bodies;
+    std::vector<uint32_t> verts;        // engine (renumbered) vertex id of every body-local vertex
+    std::vector<uint8_t> rec;           // per tet 48 B in three planes: DmInv[9] (row-major), w = |V0| mu, four u16 body-local vertex ids
+    std::vector<uint32_t> incPtr;
+    std::vector<uint16_t> inc;          // ascending (tet, corner) in the ORIGINAL tet order: the reference's sequential scatter order
+    std::vector<float> md;              // matrix_diag per body-local vertex, summed in that same order
+    uint32_t nVmax = 0, nTmax = 0;      // capacities the kernel's shared-memory carve-up is sized for (multiples of 32)
+};
+// bodyVertStart: first ORIGINAL vertex id of every body (ascending; bodies own contiguous vertex and tet ranges, as
+// DataLoader::AllocData lays them out).  Throws if a tet spans two bodies or a body exceeds the u16 index ranges.
+void build_body_batch(int nV, int nT, const float* X, const uint32_t* Tet, const float* mu, const std::vector<int>& bodyVertStart,
+                      const uint32_t* vertNewOfOld, BodyBatch& out);
+
 // Contiguous vertex partition of the renumbered ids into `world` ranks:
 // rank r owns [vbeg[r], vbeg[r+1]).
 void partition_vertices(int nV, int world, std::vector<int>& vbeg);

@@ -9,6 +9,7 @@
 #include <stdexcept>
 
 #include "pd_kernels.cuh"
+#include "pd_body_kernel.cuh"
 #include "pd_solvers.cuh"
 
 namespace pdb200 {
@@ -61,6 +62,9 @@ struct Engine::Impl {
     // mouse drag (allocated by the first setDrag*): moreDBC, OffsetX, a DBCX of its own (until then DBCX is X0) and the
     // "some moreDBC > 0" flag
     float* more = nullptr; float4* offX = nullptr; float4* dbcx = nullptr; int* dragFlag = nullptr;
+    // EXPERIMENT PD_BODY_KERNEL=1 (pd_body_kernel.cuh): one CTA per small body, one launch per step
+    BodyDesc* bBodies = nullptr; uint32_t* bVerts = nullptr; uint8_t* bRec = nullptr; uint32_t* bIncPtr = nullptr; uint16_t* bInc = nullptr; float* bMd = nullptr;
+    int nBodies = 0; uint32_t bNVmax = 0, bNTmax = 0; size_t bSmem = 0;
     DragArgs drag(const float t[3], int numDBC) const { return DragArgs{more, offX, dbcx, t[0], t[1], t[2], numDBC > 0 ? 1 : 0}; }
     uint32_t* oldOfNew = nullptr;
     float* stage3 = nullptr;          // 3 x (3 nV) floats, AoS staging for import/export
@@ -241,6 +245,33 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     if (perSm < 1) throw std::runtime_error("local kernel does not fit on an SM");
     if (opt.ctasPerSm > 0) perSm = std::min(perSm, opt.ctasPerSm);
     localGrid_ = std::min(L_.nTiles, numSms_ * perSm);
+
+    // EXPERIMENT (opt-in): scenes made of many small bodies step with one CTA per body and one launch per step
+    if (const char* e = std::getenv("PD_BODY_KERNEL")) bodyKernel_ = std::atoi(e) != 0 && opt.world == 1 && opt.rotMode != 2 && !scene_.bodyVertStart.empty();
+    if (bodyKernel_) {
+        try {
+            BodyBatch bb;
+            build_body_batch(scene_.numVerts, scene_.numTets, scene_.X.data(), scene_.Tet.data(), scene_.mu.data(), scene_.bodyVertStart, L_.vertNewOfOld.data(), bb);
+            int maxOptin = 0;
+            CUDA_CHECK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, opt.device));
+            d.bSmem = body_smem_bytes(bb.nVmax, bb.nTmax);
+            if (d.bSmem > (size_t)maxOptin) throw std::runtime_error("a body needs " + std::to_string(d.bSmem) + " bytes of shared memory");
+            d.nBodies = (int)bb.bodies.size(); d.bNVmax = bb.nVmax; d.bNTmax = bb.nTmax;
+            d.bBodies = dalloc<BodyDesc>(bb.bodies.size()); d.bVerts = dalloc<uint32_t>(bb.verts.size()); d.bRec = dalloc<uint8_t>(bb.rec.size());
+            d.bIncPtr = dalloc<uint32_t>(bb.incPtr.size()); d.bInc = dalloc<uint16_t>(bb.inc.size()); d.bMd = dalloc<float>(bb.md.size());
+            CUDA_CHECK(cudaMemcpy(d.bBodies, bb.bodies.data(), bb.bodies.size() * sizeof(BodyDesc), cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaMemcpy(d.bVerts, bb.verts.data(), bb.verts.size() * 4, cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaMemcpy(d.bRec, bb.rec.data(), bb.rec.size(), cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaMemcpy(d.bIncPtr, bb.incPtr.data(), bb.incPtr.size() * 4, cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaMemcpy(d.bInc, bb.inc.data(), bb.inc.size() * 2, cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaMemcpy(d.bMd, bb.md.data(), bb.md.size() * 4, cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaFuncSetAttribute((const void*)k_body_step<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.bSmem));
+            CUDA_CHECK(cudaFuncSetAttribute((const void*)k_body_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.bSmem));
+        } catch (const std::exception& ex) {
+            std::fprintf(stderr, "pd_b200: PD_BODY_KERNEL ignored for this scene (%s); the tile path runs\n", ex.what());
+            bodyKernel_ = false;
+        }
+    }
 
     reset();
 }
@@ -452,6 +483,23 @@ void Engine::step(int nSteps)
         CUDA_CHECK(cudaGetLastError());
         perfc_.steps += nSteps;
         perfc_.kernelLaunches += (long long)nSteps * (4 + 3 * params_.numIterations);
+        return;
+    }
+    if (bodyKernel_ && !perf_ && !dragActive_) {      // EXPERIMENT: one CTA per body, the whole step in one launch (pd_body_kernel.cuh)
+        const SolverParams& p = params_;
+        const float dtInv = 1.0f / p.dt, wdbc = 1e6f * (dtInv * dtInv);
+        for (int s = 0; s < nSteps; ++s) {
+            if (opt_.rotMode == 1)
+                k_body_step<1><<<d.nBodies, 512, d.bSmem, stream_>>>(d.bBodies, d.bVerts, d.bRec, d.bIncPtr, d.bInc, d.bMd, d.bNVmax, d.bNTmax, d.X, d.V, d.XT, d.mass,
+                                                                     d.dbc, d.dbcx, p.dt, dt2Prepared_, p.gravity, p.numIterations, p.rho, wdbc, d.fb, p.muT, p.muN);
+            else
+                k_body_step<0><<<d.nBodies, 512, d.bSmem, stream_>>>(d.bBodies, d.bVerts, d.bRec, d.bIncPtr, d.bInc, d.bMd, d.bNVmax, d.bNTmax, d.X, d.V, d.XT, d.mass,
+                                                                     d.dbc, d.dbcx, p.dt, dt2Prepared_, p.gravity, p.numIterations, p.rho, wdbc, d.fb, p.muT, p.muN);
+        }
+        CUDA_CHECK(cudaGetLastError());
+        perfc_.steps += nSteps;
+        perfc_.pdIterations += (long long)nSteps * p.numIterations;
+        perfc_.kernelLaunches += nSteps;
         return;
     }
     const int launchesPerStep = 2 + 2 * params_.numIterations;     // multi-GPU: the halo pushes ride inside the local kernels
@@ -714,6 +762,7 @@ void Engine::updateMu(const float* mu)
     std::vector<float> B((size_t)scene_.numTets * 9), v0((size_t)scene_.numTets);
     rest_shape(scene_.X.data(), scene_.Tet.data(), scene_.numTets, B.data(), v0.data());
     std::copy(mu, mu + scene_.numTets, scene_.mu.begin());
+    bodyKernel_ = false;                               // (the per-body experiment keeps its own records: back to the tile path)
     CUDA_CHECK(cudaStreamSynchronize(stream_));        // no launch may still be reading the stream
     for (int ti = 0; ti < L_.nTiles; ++ti) {
         uint8_t* rec = L_.records.data() + L_.tileRecOff[(size_t)ti];

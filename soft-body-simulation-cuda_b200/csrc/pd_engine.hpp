@@ -136,6 +136,7 @@ private:
     bool usePdl_ = false;     // programmatic dependent launch of the per-iteration kernels (pd_kernels.cuh: pdl_wait); measured SLOWER
                               // on B200 (grid139: 42.0 vs 36.9 ms/step, batch64: 2.68 vs 2.23), so it stays an opt-in experiment (PD_PDL=1)
     float dt2Prepared_ = 0.f;
+    bool bodyKernel_ = false;             // EXPERIMENT PD_BODY_KERNEL=1: one CTA per small body, one launch per step (pd_body_kernel.cuh)
     bool dragActive_ = false;             // some vertex has moreDBC > 0: the DRAG kernel variants run, as plain launches (the target moves every frame)
     float dragTarget_[3] = {0.f, 0.f, 0.f};
     int numDBC_ = 0;                      // SolverData::numDBC

@@ -10,7 +10,7 @@
 #include <string>
 #include <vector>
 
-#include "../../soft-body-simulation-cuda_b200/csrc/pd_kernels.cuh"
+#include "../../soft-body-simulation-cuda_b200/csrc/pd_body_kernel.cuh"
 
 using namespace pdb200;
 
@@ -36,6 +36,8 @@ struct Emu {
     DevFixedBodies dfb{};
     std::vector<std::unique_ptr<Rank>> ranks;
     std::string err;
+    bool bodyMode = false;          // PD_BODY_KERNEL experiment: one emulated CTA per body, the whole step in one launch
+    BodyBatch bb;
 };
 
 void push(Emu& e, int buf)
@@ -148,6 +150,21 @@ void* emu_create(int nV, int nT, const float* X, const uint32_t* Tet, const floa
     return e.release();
 }
 
+// PD_BODY_KERNEL experiment: bodyVertStart[nBodies] = first ORIGINAL vertex id of every body (single rank only)
+int emu_enable_body_kernel(void* h, int nV, int nT, const float* X, const uint32_t* Tet, const float* mu, int nBodies, const int* bodyVertStart)
+{
+    Emu& e = *static_cast<Emu*>(h);
+    if (e.world != 1) return 1;
+    try {
+        build_body_batch(nV, nT, X, Tet, mu, std::vector<int>(bodyVertStart, bodyVertStart + nBodies), e.ranks[0]->L.vertNewOfOld.data(), e.bb);
+        e.bodyMode = true;
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, "emu_enable_body_kernel: %s\n", ex.what());
+        return 2;
+    }
+    return 0;
+}
+
 void emu_destroy(void* h) { delete static_cast<Emu*>(h); }
 
 int emu_step(void* h, float dt, float gravity, float rho, float muN, float muT, int iters, int nSteps)
@@ -159,7 +176,19 @@ int emu_step(void* h, float dt, float gravity, float rho, float muN, float muT, 
             e.dt2Prepared = dt * dt;
             e.ready = true;
         }
-        for (int s = 0; s < nSteps; ++s) {
+        for (int s = 0; s < nSteps && e.bodyMode; ++s) {
+            Rank& r = *e.ranks[0];
+            const float dtInv = 1.0f / dt, wdbc = 1e6f * (dtInv * dtInv);
+            const size_t smem = body_smem_bytes(e.bb.nVmax, e.bb.nTmax);
+            auto run = [&](auto kernel) {
+                pd_emu::launch((unsigned)e.bb.bodies.size(), 512u, smem, kernel, (const BodyDesc*)e.bb.bodies.data(), (const uint32_t*)e.bb.verts.data(),
+                               (const uint8_t*)e.bb.rec.data(), (const uint32_t*)e.bb.incPtr.data(), (const uint16_t*)e.bb.inc.data(), (const float*)e.bb.md.data(),
+                               e.bb.nVmax, e.bb.nTmax, r.X.data(), r.V.data(), r.XT.data(), (const float*)r.mass.data(), (const float*)r.dbc.data(),
+                               (const float4*)r.dbcx.data(), dt, e.dt2Prepared, gravity, iters, rho, wdbc, e.dfb, muT, muN);
+            };
+            if (e.rotMode == 1) run(k_body_step<1>); else run(k_body_step<0>);
+        }
+        for (int s = 0; s < nSteps && !e.bodyMode; ++s) {
             if (e.rotMode == 1) step_once<1, false>(e, dt, gravity, rho, muN, muT, iters);
             else step_once<0, true>(e, dt, gravity, rho, muN, muT, iters);
         }

@@ -239,3 +239,40 @@ def test_live_mu_edit_vs_oracle(pd, O):
     e2 = meshes.rel_err(eng.download()[0], osc.get()[0], scale)
     print(f"live mu edit: rel err vs oracle {e1:.3e} (stale matrix_diag), {e2:.3e} (after Reset)")
     assert e1 <= 1e-4 and e2 <= 1e-4, (e1, e2)
+
+
+@pytest.mark.skipif(os.environ.get("PD_EXPERIMENTAL_GPU_TESTS") != "1", reason="experiment, not yet run on a GPU: set PD_EXPERIMENTAL_GPU_TESTS=1 (scripts/gpu_body_ab.sh)")
+def test_per_body_kernel_experiment(pd, O, assets, monkeypatch):
+    """PD_BODY_KERNEL=1 (csrc/pd_body_kernel.cuh): one CTA per body, one launch per step.  Faithful mode bit-exact vs the oracle
+    on the two-body house + sphere context (as the host emulation of the kernel is, tests/test_kernel_emulation.py); default
+    mode within 1e-4 of the tile path on a batch of well-conditioned grids."""
+    monkeypatch.setenv("PD_BODY_KERNEL", "1")
+    sc = pd.Scene.from_json(assets["json"], "C5 house&sphere")
+    p = sc.params
+    p["num_iterations"] = 25
+    sc.params = p
+    osc, _ = meshes.oracle_scene(O, assets, "C5 house&sphere")
+    op = _oracle_params(O, p)
+    eng = pd.PdSolver(sc, rot_mode=1)
+    for n in range(3):
+        eng.Update(1); osc.step(op, 1)
+        for a, b in zip(eng.download(), osc.get()):
+            assert np.array_equal(_bits(a), _bits(b)), f"step {n + 1}"
+    assert eng.GetPerformanceData()[1].kernel_launches == 3                     # one launch per step
+    grids = []
+    for i in range(3):
+        g = pd.Scene.kuhn_grid(4 + i, 4, 3, 1.0, 0.05, 11 + i, (6.0 * i, 0.4, 0.0), 1.0, 2e5)
+        g.params = pd.SolverParams(dt=1 / 60, gravity=9.8, num_iterations=30)
+        g.add_fixed(pd.fixed_body(pd.PD_PLANE, pos=(0, 0, 0), scale=(450, 450, 450)))
+        grids.append(g)
+    merged = pd.Scene.merge(grids)
+    body = pd.PdSolver(merged)
+    monkeypatch.setenv("PD_BODY_KERNEL", "0")
+    tiles = pd.PdSolver(merged)
+    X0 = merged.arrays()["X"]
+    V0 = np.zeros_like(X0); V0[:, 1] = 0.3 * np.sin(X0[:, 0])
+    body.upload(V=V0); tiles.upload(V=V0)
+    body.Update(6); tiles.Update(6)
+    err = meshes.rel_err(body.download()[0], tiles.download()[0])
+    print(f"per-body kernel vs tile path: {err:.2e}")
+    assert err <= 1e-4 and body.GetPerformanceData()[1].kernel_launches == 6

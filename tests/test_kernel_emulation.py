@@ -33,6 +33,7 @@ def emu_lib(variant="default"):
         L.emu_set.argtypes = [C.c_void_p] * 4
         L.emu_set_drag.argtypes = [C.c_void_p] * 4
         L.emu_info.argtypes = [C.c_void_p] * 4
+        L.emu_enable_body_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.emu_variant.restype = C.c_char_p
         assert L.emu_variant().decode() == variant
         _libs[variant] = L
@@ -59,6 +60,13 @@ class Emu:
         if getattr(self, "h", None):
             self.lib.emu_destroy(self.h)
             self.h = None
+
+    def enable_body_kernel(self):
+        """PD_BODY_KERNEL experiment: one emulated CTA per soft body, the whole step in one launch."""
+        a = self._keep[0]
+        bvs = np.ascontiguousarray(a["body_vert_start"], np.int32)
+        assert self.lib.emu_enable_body_kernel(self.h, self.nV, a["Tet"].shape[0], a["X"].ctypes.data, a["Tet"].ctypes.data, a["mu"].ctypes.data,
+                                               len(bvs), bvs.ctypes.data) == 0
 
     def step(self, n=1):
         p = self.p
@@ -228,3 +236,40 @@ def test_partitioned_mesh_is_bit_identical_to_one_rank(pd, world, trim):
         assert np.array_equal(_bits(a), _bits(b))
     print(f"world {world} trim {trim}: {many.info()} (one rank: {one.info()})")
     assert np.abs(one.get()[0] - X0).max() > 1e-3
+
+
+def test_per_body_kernel_faithful_is_bit_exact_vs_oracle(pd, O, assets):
+    """PD_BODY_KERNEL experiment (csrc/pd_body_kernel.cuh): one CTA per body, predictor + all iterations + end of step in one
+    launch.  Its sums run in the reference's sequential (tet, corner) order, so with the SVD rotation (rot_mode 1) it matches
+    the oracle BIT FOR BIT on a two-body scene with several hundred vertices each -- which the tiled path only does on
+    single-tile meshes."""
+    sc, p = _scene(pd, assets, "C5 house&sphere", 25)
+    osc, _ = meshes.oracle_scene(O, assets, "C5 house&sphere")
+    op = _oparams(O, p)
+    emu = Emu(pd, sc, rot_mode=1)
+    emu.enable_body_kernel()
+    for n in range(3):
+        emu.step(1); osc.step(op, 1)
+        for a, b in zip(emu.get(), osc.get()):
+            assert np.array_equal(_bits(a), _bits(b)), f"step {n + 1}"
+
+
+def test_per_body_kernel_default_mode_vs_tile_kernels(pd, assets):
+    """... and in the default mode (Newton polar rotation) it differs from the tile kernels only by the order of the sums."""
+    grids = []
+    for i in range(3):
+        g = pd.Scene.kuhn_grid(4 + i, 4, 3, 1.0, 0.05, 11 + i, (6.0 * i, 0.4, 0.0), 1.0, 2e5)
+        g.params = pd.SolverParams(dt=1 / 60, gravity=9.8, num_iterations=30)
+        g.add_fixed(pd.fixed_body(pd.PD_PLANE, pos=(0, 0, 0), scale=(450, 450, 450)))
+        grids.append(g)
+    sc = pd.Scene.merge(grids)
+    X0 = sc.arrays()["X"]
+    V0 = np.zeros_like(X0); V0[:, 1] = 0.3 * np.sin(X0[:, 0])
+    a, b = Emu(pd, sc), Emu(pd, sc)
+    b.enable_body_kernel()
+    a.set(V=V0); b.set(V=V0)
+    a.step(6); b.step(6)                                           # the grids reach the floor within these steps
+    scale = float(np.linalg.norm(X0.max(0) - X0.min(0)))
+    err = max(meshes.rel_err(x, y, scale) for x, y in zip(a.get()[::2], b.get()[::2]))
+    print(f"per-body kernel vs tile kernels, three grids, 6 steps: {err:.2e}")
+    assert err <= 2e-5 and np.abs(a.get()[0] - X0).max() > 1e-3
