@@ -540,7 +540,7 @@ float Engine::stepTimed(int nSteps)
 {
     CUDA_CHECK(cudaSetDevice(opt_.device));
     if (!ready_) prepare();
-    if (opt_.useGraph && !perf_ && !dragActive_ && params_.globalSolver == 0) buildGraph();
+    if (opt_.useGraph && !perf_ && !dragActive_ && !bodyKernel_ && params_.globalSolver == 0) buildGraph();
     cudaEvent_t a, b;
     CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
