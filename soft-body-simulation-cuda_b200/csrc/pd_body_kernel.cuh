@@ -20,8 +20,9 @@ namespace pdb200 {
 
 // BodyDesc / BodyBatch: layout.hpp (built on the host by layout.cpp:build_body_batch)
 
-// shared-memory carve-up for capacities (nVmax, nTmax): q[3] | b0 | cc | H (four corner planes)
-__host__ __device__ inline size_t body_smem_bytes(uint32_t nVmax, uint32_t nTmax) { return 16ull * nVmax * 4 + 8ull * nVmax + 16ull * 4 * nTmax; }
+// shared-memory carve-up for capacities (nVmax, nTmax, multiples of 32): q[3] | b0 | cc | H (four corner planes) | incidence
+// pointers (nVmax + 32 words) | incidence entries (4 nTmax u16)
+__host__ __device__ inline size_t body_smem_bytes(uint32_t nVmax, uint32_t nTmax) { return 72ull * nVmax + 64ull * nTmax + 4ull * (nVmax + 32u) + 8ull * nTmax; }
 
 template <int ROT_MODE>
 __global__ void __launch_bounds__(512, 1)
@@ -36,9 +37,14 @@ k_body_step(const BodyDesc* __restrict__ bodies, const uint32_t* __restrict__ bv
     float4* b0s = reinterpret_cast<float4*>(smem) + 3 * nVmax;
     float2* ccs = reinterpret_cast<float2*>(smem + 64ull * nVmax);
     float4* Hs = reinterpret_cast<float4*>(smem + 72ull * nVmax);
+    uint32_t* ptrS = reinterpret_cast<uint32_t*>(smem + 72ull * nVmax + 64ull * nTmax);
+    uint16_t* incS = reinterpret_cast<uint16_t*>(smem + 72ull * nVmax + 64ull * nTmax + 4ull * (nVmax + 32u));
     const BodyDesc bd = bodies[blockIdx.x];
     const uint32_t tid = threadIdx.x, nth = blockDim.x;
 
+    // the body's incidence lists stay in shared memory for the whole step (the gather below walks them every iteration)
+    for (uint32_t l = tid; l <= bd.nV; l += nth) ptrS[l] = bincPtr[bd.ptr0 + l];
+    for (uint32_t e = tid; e < 4u * bd.nT; e += nth) incS[e] = binc[bd.inc0 + e];
     // ---- predictor: gravity, setMDt_2MoreDBC (moreDBC = 0), computeSn, addM_h2Sn (k_predict<false>)
     const float dt2 = __fmul_rn(dt, dt);
     for (uint32_t l = tid; l < bd.nV; l += nth) {
@@ -94,10 +100,18 @@ k_body_step(const BodyDesc* __restrict__ bodies, const uint32_t* __restrict__ bv
             } else {
                 const float4 bb = b0s[l];
                 bx = bb.x; by = bb.y; bz = bb.z;
-                const uint32_t e0 = bincPtr[bd.ptr0 + l], e1 = bincPtr[bd.ptr0 + l + 1];
-                for (uint32_t e = e0; e < e1; ++e) {
-                    const uint32_t code = binc[bd.inc0 + e];                   // tet * 4 + corner
-                    const float4 h = Hs[(code & 3u) * nTmax + (code >> 2)];
+                uint32_t e = ptrS[l];
+                const uint32_t e1 = ptrS[l + 1];
+                auto hs = [&](uint32_t code) -> float4 { return Hs[(code & 3u) * nTmax + (code >> 2)]; };       // code = tet * 4 + corner
+                for (; e + 4u <= e1; e += 4u) {      // four gathers in flight, added strictly in list order
+                    const float4 h0 = hs(incS[e]), h1 = hs(incS[e + 1u]), h2 = hs(incS[e + 2u]), h3 = hs(incS[e + 3u]);
+                    bx = __fadd_rn(bx, h0.x); by = __fadd_rn(by, h0.y); bz = __fadd_rn(bz, h0.z);
+                    bx = __fadd_rn(bx, h1.x); by = __fadd_rn(by, h1.y); bz = __fadd_rn(bz, h1.z);
+                    bx = __fadd_rn(bx, h2.x); by = __fadd_rn(by, h2.y); bz = __fadd_rn(bz, h2.z);
+                    bx = __fadd_rn(bx, h3.x); by = __fadd_rn(by, h3.y); bz = __fadd_rn(bz, h3.z);
+                }
+                for (; e < e1; ++e) {
+                    const float4 h = hs(incS[e]);
                     bx = __fadd_rn(bx, h.x); by = __fadd_rn(by, h.y); bz = __fadd_rn(bz, h.z);
                 }
             }

@@ -78,6 +78,10 @@ def test_trimmed_rank_layouts_keep_every_owned_slot(pd, assets, scene_name, worl
         assert (fed == 1).all()
         assert Pn.n_loc_of.tolist() == [q.num_owned + q.num_ghosts for q in plans]
         assert set(Pn.ghosts.tolist()) <= set(plans0[n].ghosts.tolist()) and Pn.tiles.tolist() == plans0[n].tiles.tolist()
+        # the neighbour relation stays symmetric (a rank waits for the flag of every neighbour: an asymmetry would be a deadlock)
+        for r in Pn.neighbours.tolist():
+            assert n in plans[r].neighbours.tolist()
+        assert sorted(Pn.neighbours.tolist()) == sorted(set(np.unique(Pn.push_rank).tolist()))
     print(f"{scene_name} world {world}: ghosts {sum(q.num_ghosts for q in plans0)} -> {sum(q.num_ghosts for q in plans)}")
     for rank in range(world):
         P = plans[rank]
