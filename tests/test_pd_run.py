@@ -14,6 +14,9 @@ EXE = os.path.join(ROOT, "soft-body-simulation-cuda_b200", "pd_run")
 
 
 def _run(*args):
+    if not os.path.exists(EXE):           # built next to the library by soft-body-simulation-cuda_b200/build.py
+        import importlib
+        importlib.import_module("soft-body-simulation-cuda_b200.build").build(force=True)
     return subprocess.run([EXE] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
 
 
