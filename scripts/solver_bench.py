@@ -60,6 +60,29 @@ def case(cells, solver, steps, inner, pcg_tol, outer=10):
     return out
 
 
+def reference_case(cells, solver, steps, outer=10):
+    """The reference's own back-end on one B200 (oracle/_ref/libpd_ref_solvers.so: PdSolver's non-Jacobi branch replayed around
+    CholeskySpLinearSolver<float> / PCGJacobiSolver<float>, default max_iter 2000, tolerance 1e-5), wall clock around synchronised
+    steps.  None when the prebuilt harness did not travel with the snapshot."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import time
+    import ref
+    if not ref.solvers_available():
+        return None
+    sc = pd.Scene.kuhn_grid(cells, cells, cells, 1.0, 0.05, 12345, (0.0, 10.0, 0.0), 1.0, 2e5)
+    a = sc.arrays()
+    rs = ref.RefSolverScene(a["X"], a["Tet"], a["mass"], a["mu"], solver)
+    V0 = np.zeros_like(a["X"]); V0[:, 1] = 0.5 * np.sin(a["X"][:, 0] / 7.0)
+    rs.set(V=V0)
+    kw = dict(dt=1 / 60, gravity=9.8, tol=1e-6, num_iterations=outer)
+    rs.step(2, **kw); rs.get()
+    t0 = time.perf_counter()
+    rs.step(steps, **kw); X = rs.get()[0]                    # the D2H read synchronises
+    ms = (time.perf_counter() - t0) * 1e3
+    return {"workload": f"grid{cells}", "impl": "reference", "solver": {1: "CholeskySpLinearSolver<float> (cuSOLVER)", 2: "PCGJacobiSolver<float> (cuSPARSE/cuBLAS)"}[solver],
+            "steps": steps, "ms_per_step": ms / steps, "pd_iterations_last_step": rs.stats()[0], "finite": bool(np.isfinite(X).all())}
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cells", type=int, default=55)
@@ -69,3 +92,8 @@ if __name__ == "__main__":
     print(json.dumps(case(a.cells, 2, a.steps, a.inner, 0.0)), flush=True)          # fixed inner count (pcg_tol 0 never triggers)
     print(json.dumps(case(a.cells, 2, a.steps, 2000, 1e-5)), flush=True)            # the reference's stopping rule
     print(json.dumps(case(min(a.cells, 24), 1, a.steps, 0, 0.0)), flush=True)       # small-mesh path (<= 262,144 vertices)
+    for cells, solver in ((a.cells, 2), (min(a.cells, 24), 1)):                     # the reference's own back-ends beside them
+        try:
+            print(json.dumps(reference_case(cells, solver, a.steps)), flush=True)
+        except Exception as ex:                                                     # e.g. cuSOLVER out of memory on the large grid
+            print(json.dumps({"impl": "reference", "solver": solver, "error": str(ex)}), flush=True)
