@@ -281,12 +281,12 @@ def test_header_is_plain_c_and_the_library_links_from_c(tmp_path, pd):
     assert out.strip().endswith("|engine") or "CUDA" in out          # on a box without a GPU: "no CUDA device: ... no CPU fallback"
 
 
-def test_gpu_scripts_parse():
+def test_gpu_scripts_parse(tmp_path):
     """scripts/*.py and scripts/*.sh only ever run on the GPU box: a syntax error there costs a gpurun call."""
     import glob
     import py_compile
     import subprocess
     for f in glob.glob(os.path.join(ROOT, "scripts", "*.py")) + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]:
-        py_compile.compile(f, doraise=True, cfile=os.devnull)
+        py_compile.compile(f, doraise=True, cfile=str(tmp_path / (os.path.basename(f) + "c")))
     for f in glob.glob(os.path.join(ROOT, "scripts", "*.sh")):
         subprocess.check_call(["bash", "-n", f])
