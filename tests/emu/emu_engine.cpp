@@ -194,7 +194,7 @@ int emu_step(void* h, float dt, float gravity, float rho, float muN, float muT, 
         }
     } catch (const std::exception& ex) {
         std::fprintf(stderr, "emu_step: %s\n", ex.what());
-        return 1;
+        return std::string(ex.what()).find("cannot create") != std::string::npos ? 77 : 1;      // 77: the host cannot run the emulation (skip)
     }
     return 0;
 }

@@ -17,6 +17,9 @@
 #include <cstring>
 #include <functional>
 #include <mutex>
+#include <stdexcept>
+#include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -89,7 +92,11 @@ struct Pool {
     void run(unsigned n, std::function<void(unsigned)> f)
     {
         std::unique_lock<std::mutex> lk(m);
-        while (th.size() < n) { const unsigned i = (unsigned)th.size(); th.emplace_back([this, i] { worker(i); }); }
+        while (th.size() < n) {
+            const unsigned i = (unsigned)th.size();
+            try { th.emplace_back([this, i] { worker(i); }); }
+            catch (const std::system_error&) { throw std::runtime_error("host emulation: cannot create " + std::to_string(n) + " threads on this machine"); }
+        }
         job = std::move(f); active = n; remaining = n; ++gen;
         cv.notify_all();
         doneCv.wait(lk, [&] { return remaining == 0; });

@@ -70,7 +70,10 @@ class Emu:
 
     def step(self, n=1):
         p = self.p
-        assert self.lib.emu_step(self.h, p["dt"], p["gravity"], p["rho"], p["muN"], p["muT"], p["num_iterations"], n) == 0
+        rc = self.lib.emu_step(self.h, p["dt"], p["gravity"], p["rho"], p["muN"], p["muT"], p["num_iterations"], n)
+        if rc == 77:
+            pytest.skip("this machine cannot create the OS threads the emulation needs (one per CUDA thread of a CTA)")
+        assert rc == 0
 
     def get(self):
         X = np.zeros((self.nV, 3), np.float32); V = np.zeros_like(X); XT = np.zeros_like(X)
