@@ -241,6 +241,30 @@ int emu_set_drag(void* h, const float* more, const float* off, const float* targ
     if (target) for (int k = 0; k < 3; ++k) e.target[k] = target[k];
     return 0;
 }
+// Control_Kernel (k_drag_select) on the current X; selectV = original vertex id or -1; single rank only
+int emu_drag_select(void* h, int selectV, float controlMag, const float* target)
+{
+    Emu& e = *static_cast<Emu*>(h);
+    if (e.world != 1) return 1;
+    Rank& r = *e.ranks[0];
+    int flag = 0;
+    const int sel = selectV >= 0 ? (int)r.L.vertNewOfOld[(size_t)selectV] : -1;
+    pd_emu::launch_flat((unsigned)((r.nV + 255) / 256), 256u, k_drag_select, r.nV, (const float4*)r.X.data(), (const float*)r.dbc.data(), sel, controlMag,
+                        r.more.data(), r.offX.data(), &flag);
+    e.drag = flag != 0;
+    if (target) for (int k = 0; k < 3; ++k) e.target[k] = target[k];
+    return 0;
+}
+void emu_get_drag(void* h, float* more, float* off)
+{
+    const Emu& e = *static_cast<Emu*>(h);
+    const Rank& r = *e.ranks[0];
+    for (int v = 0; v < r.nV; ++v) {
+        const size_t o = r.L.vertOrder[(size_t)v];
+        if (more) more[o] = r.more[(size_t)v];
+        if (off) { off[3 * o] = r.offX[(size_t)v].x; off[3 * o + 1] = r.offX[(size_t)v].y; off[3 * o + 2] = r.offX[(size_t)v].z; }
+    }
+}
 void emu_info(void* h, long long* tetsEvaluated, long long* tiles, long long* ghosts)
 {
     const Emu& e = *static_cast<Emu*>(h);

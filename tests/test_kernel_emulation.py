@@ -33,6 +33,8 @@ def emu_lib(variant="default"):
         L.emu_set.argtypes = [C.c_void_p] * 4
         L.emu_set_drag.argtypes = [C.c_void_p] * 4
         L.emu_info.argtypes = [C.c_void_p] * 4
+        L.emu_drag_select.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p]
+        L.emu_get_drag.argtypes = [C.c_void_p] * 3
         L.emu_enable_body_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.emu_variant.restype = C.c_char_p
         assert L.emu_variant().decode() == variant
@@ -90,6 +92,15 @@ class Emu:
             return
         m = np.ascontiguousarray(more, np.float32); o = np.ascontiguousarray(off, np.float32); t = np.ascontiguousarray(target, np.float32)
         assert self.lib.emu_set_drag(self.h, m.ctypes.data, o.ctypes.data, t.ctypes.data) == 0
+
+    def drag_select(self, v, target, mag=10.0):
+        t = np.ascontiguousarray(target, np.float32)
+        assert self.lib.emu_drag_select(self.h, int(v), float(mag), t.ctypes.data) == 0
+
+    def get_drag(self):
+        m = np.zeros(self.nV, np.float32); o = np.zeros((self.nV, 3), np.float32)
+        self.lib.emu_get_drag(self.h, m.ctypes.data, o.ctypes.data)
+        return m, o
 
     def info(self):
         a, b, c = C.c_longlong(), C.c_longlong(), C.c_longlong()
@@ -212,7 +223,9 @@ def test_cube_corner_dragged_faithful_kernels_bit_exact_vs_oracle(pd, O, assets)
     target = np.float32([0.5, 31.0, 0.25])
     osc.drag_select(3, target)
     more, off, _ = osc.get_drag()
-    emu.set_drag(more, off, target)
+    emu.drag_select(3, target)                                       # k_drag_select = Control_Kernel on the kernels' own X
+    me, oe = emu.get_drag()
+    assert np.array_equal(me, more) and np.array_equal(_bits(oe), _bits(off)) and me[3] == np.float32(10)
     emu.step(2); osc.step(op, 2)
     for a, b in zip(emu.get(), osc.get()):
         assert np.array_equal(_bits(a), _bits(b))
