@@ -8,6 +8,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../soft-body-simulation-cuda_b200/csrc/pd_body_kernel.cuh"
@@ -24,6 +25,14 @@ struct Rank {
     std::vector<float4> Pslots, q[3], b0, X, V, XT, X0, dbcx, offX;
     std::vector<float2> cc;
     std::vector<float> mass, dbc, md, more;
+    // exchange state of the in-kernel halo push (concurrent mode): what Engine::setPeers builds in the ranks' windows
+    std::vector<unsigned long long> flags;        // written by the peers, indexed by rank
+    unsigned long long epoch = 0;
+    unsigned int ticket = 0, status = 0;
+    std::vector<uint32_t> pushNbr;                // neighbour slot of every push-list entry
+    std::vector<float4*> peerQ;                   // [3 * nNbr]: buffer k of neighbour j
+    std::vector<unsigned long long*> peerFlag;    // [nNbr]: this rank's entry in neighbour j's flag array
+    long long phase = 0;
 };
 
 struct Emu {
@@ -99,6 +108,43 @@ void step_once(Emu& e, float dt, float gravity, float rho, float muN, float muT,
 
 }  // namespace
 
+// One rank's whole step with the halo push INSIDE the local kernel (DistWait: push-list slices by all CTAs, ticket, epoch,
+// flags, wait before the first boundary tile), as Engine::step drives it on one GPU per process.  The ranks run
+// concurrently, one driving thread each, all CTAs of a launch resident at once.
+template <int RM, bool BASE>
+void rank_step_concurrent(Emu& e, Rank& r, float dt, float gravity, float rho, float muN, float muT, int iters)
+{
+    const float dtInv = 1.0f / dt, wdbc = 1e6f * (dtInv * dtInv);
+    const int vb = 256;
+    const unsigned vg = (unsigned)((r.nOwn + vb - 1) / vb);
+    const int base = (int)(r.phase % 3);
+    pd_emu::launch_flat(vg, vb, k_predict<false>, r.nOwn, r.X.data(), r.V.data(), r.mass.data(), r.dbc.data(), r.md.data(), dt, e.dt2Prepared,
+                        gravity, r.q[base].data(), r.q[(base + 2) % 3].data(), r.b0.data(), r.cc.data(), DragArgs{});
+    ++r.phase;
+    float omega = 1.0f;
+    const int nNbr = (int)r.P.neighbours.size();
+    for (int i = 0; i < iters; ++i) {
+        const int ic = (base + i) % 3, in = (base + i + 1) % 3, ip = (base + i + 2) % 3;
+        if (i <= 10) omega = 1;
+        else if (i == 11) omega = 2 / (2 - rho * rho);
+        else omega = 4 / (4 - rho * rho * omega);
+        DistWait dw{};
+        dw.flags = r.flags.data(); dw.epoch = &r.epoch; dw.nbr = r.P.neighbours.data(); dw.nNbr = nNbr; dw.firstTile = r.P.nInteriorTiles;
+        dw.status = &r.status; dw.nPush = (int)r.P.pushSrc.size(); dw.pushSrc = r.P.pushSrc.data(); dw.pushDst = r.P.pushDst.data();
+        dw.pushNbr = r.pushNbr.data(); dw.peerQ = r.peerQ.data() + (size_t)ic * nNbr; dw.peerFlag = r.peerFlag.data(); dw.ticket = &r.ticket;
+        const unsigned grid = (unsigned)std::min(r.L.nTiles, e.grid);
+        pd_emu::launch_resident(grid, (unsigned)TILE_T, LOCAL_SMEM_BYTES, k_local<RM, true, false>, (const uint8_t*)r.L.records.data(), (const uint32_t*)r.tileTab.data(),
+                                r.L.nTiles, (const uint32_t*)r.L.vstage.data(), (const uint32_t*)r.L.vlist.data(), (const float4*)r.q[ic].data(),
+                                (const float4*)r.b0.data(), r.Pslots.data(), (unsigned long long*)nullptr, dw);
+        pd_emu::launch_flat(vg, vb, k_vertex_jacobi<BASE, false>, r.nOwn, (const float4*)r.q[ic].data(), (const float4*)r.q[ip].data(), r.q[in].data(),
+                            (const float4*)r.dbcx.data(), (const float4*)r.b0.data(), (const float2*)r.cc.data(), (const uint32_t*)r.L.vslotPtr.data(),
+                            (const uint32_t*)r.L.vslot.data(), (const float4*)r.Pslots.data(), omega, wdbc);
+        ++r.phase;
+    }
+    pd_emu::launch_flat(vg, vb, k_finish<false>, r.nOwn, (const float4*)r.q[(base + iters) % 3].data(), dtInv, r.X.data(), r.XT.data(), r.V.data(), e.dfb, muT, muN,
+                        (const float*)nullptr);
+}
+
 extern "C" {
 
 const char* emu_variant(void) { return PD_H_PLANES ? "planes" : (PD_PHASEC_PRED ? "pred" : "default"); }
@@ -148,6 +194,57 @@ void* emu_create(int nV, int nT, const float* X, const uint32_t* Tet, const floa
         return nullptr;
     }
     return e.release();
+}
+
+// world > 1: every rank steps on its own thread with the in-kernel halo exchange (instead of emu_step's lock step)
+int emu_step_concurrent(void* h, float dt, float gravity, float rho, float muN, float muT, int iters, int nSteps)
+{
+    Emu& e = *static_cast<Emu*>(h);
+    if (e.world < 2 || e.drag || e.bodyMode) return 1;
+    if (!e.ready) {
+        for (auto& r : e.ranks) matrix_diag_host(r->L, r->md);
+        e.dt2Prepared = dt * dt;
+        e.ready = true;
+    }
+    for (auto& rp : e.ranks) {          // Engine::setPeers
+        Rank& r = *rp;
+        if (!r.flags.empty()) continue;
+        r.flags.assign((size_t)e.world, 0ull);
+        const int nNbr = (int)r.P.neighbours.size();
+        std::vector<int> slotOfRank((size_t)e.world, -1);
+        for (int j = 0; j < nNbr; ++j) slotOfRank[(size_t)r.P.neighbours[(size_t)j]] = j;
+        r.pushNbr.resize(r.P.pushSrc.size());
+        for (size_t i = 0; i < r.P.pushSrc.size(); ++i) r.pushNbr[i] = (uint32_t)slotOfRank[(size_t)r.P.pushRank[i]];
+        r.peerQ.assign((size_t)3 * std::max(nNbr, 1), nullptr);
+        r.peerFlag.assign((size_t)std::max(nNbr, 1), nullptr);
+    }
+    for (auto& rp : e.ranks) {          // (second pass: every rank's flag array exists now)
+        Rank& r = *rp;
+        const int nNbr = (int)r.P.neighbours.size();
+        for (int j = 0; j < nNbr; ++j) {
+            Rank& peer = *e.ranks[(size_t)r.P.neighbours[(size_t)j]];
+            for (int k = 0; k < 3; ++k) r.peerQ[(size_t)k * nNbr + j] = peer.q[k].data();
+            r.peerFlag[(size_t)j] = &peer.flags[(size_t)r.P.rank];
+        }
+    }
+    std::vector<std::thread> drivers;
+    std::vector<int> rc((size_t)e.world, 0);
+    for (int rk = 0; rk < e.world; ++rk)
+        drivers.emplace_back([&, rk] {
+            try {
+                for (int s = 0; s < nSteps; ++s) {
+                    if (e.rotMode == 1) rank_step_concurrent<1, false>(e, *e.ranks[(size_t)rk], dt, gravity, rho, muN, muT, iters);
+                    else rank_step_concurrent<0, true>(e, *e.ranks[(size_t)rk], dt, gravity, rho, muN, muT, iters);
+                }
+            } catch (const std::exception& ex) {
+                std::fprintf(stderr, "emu_step_concurrent: %s\n", ex.what());
+                rc[(size_t)rk] = std::string(ex.what()).find("cannot create") != std::string::npos ? 77 : 1;
+            }
+        });
+    for (auto& t : drivers) t.join();
+    for (int v : rc) if (v) return v;
+    for (auto& r : e.ranks) if (r->status) return 2;      // a halo wait gave up
+    return 0;
 }
 
 // PD_BODY_KERNEL experiment: bodyVertStart[nBodies] = first ORIGINAL vertex id of every body (single rank only)

@@ -10,6 +10,7 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdint>
@@ -108,7 +109,7 @@ struct Pool {
         for (auto& t : th) t.join();
     }
 };
-inline Pool& pool() { static Pool p; return p; }
+inline Pool& pool() { static thread_local Pool p; return p; }      // one per driving thread (ranks may be driven concurrently)
 
 // kernel<<<grid, block, smemBytes>>>(args...): CTAs sequentially, the threads of a CTA concurrently
 template <typename K, typename... Args>
@@ -125,6 +126,22 @@ void launch(unsigned grid, unsigned block, size_t smemBytes, K kernel, Args... a
             kernel(args...);
         });
     }
+}
+// the same with ALL CTAs of the grid resident at once (a persistent grid whose CTAs wait for each other or for other ranks)
+template <typename K, typename... Args>
+void launch_resident(unsigned grid, unsigned block, size_t smemBytes, K kernel, Args... args)
+{
+    std::vector<std::vector<uint8_t>> raw(grid, std::vector<uint8_t>(smemBytes + 256));
+    std::vector<Cta> ctas(grid);
+    for (unsigned b = 0; b < grid; ++b) {
+        ctas[b].smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw[b].data()) + 127) & ~uintptr_t(127));
+        std::memset(ctas[b].smem, 0xcd, smemBytes);
+        ctas[b].bar.n = block;
+    }
+    pool().run(grid * block, [&](unsigned i) {
+        tIdx = uint3_emu{i % block, 0, 0}; bIdx = uint3_emu{i / block, 0, 0}; bDim = dim3(block); gDim = dim3(grid); cta = &ctas[i / block];
+        kernel(args...);
+    });
 }
 // kernels without __syncthreads / shared memory (one thread per vertex): plain loops
 template <typename K, typename... Args>
@@ -147,7 +164,10 @@ void launch_flat(unsigned grid, unsigned block, K kernel, Args... args)
 
 inline void __syncthreads() { pd_emu::cta->bar.arrive_and_wait(); }
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
-inline long long clock64() { return 0; }
+inline long long clock64()        // nanoseconds: the kernels' bounded waits (DIST_WAIT_LIMIT_CYCLES ~ 2e10) give up after 20 s instead of hanging a test
+{
+    return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 inline void __trap() { std::abort(); }
 

@@ -29,6 +29,7 @@ def emu_lib(variant="default"):
         L.emu_create.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 5
         L.emu_destroy.argtypes = [C.c_void_p]
         L.emu_step.argtypes = [C.c_void_p] + [C.c_float] * 5 + [C.c_int, C.c_int]
+        L.emu_step_concurrent.argtypes = [C.c_void_p] + [C.c_float] * 5 + [C.c_int, C.c_int]
         L.emu_get.argtypes = [C.c_void_p] * 4
         L.emu_set.argtypes = [C.c_void_p] * 4
         L.emu_set_drag.argtypes = [C.c_void_p] * 4
@@ -76,6 +77,14 @@ class Emu:
         if rc == 77:
             pytest.skip("this machine cannot create the OS threads the emulation needs (one per CUDA thread of a CTA)")
         assert rc == 0
+
+    def step_concurrent(self, n=1):
+        """world > 1: every rank on its own thread, the halo exchange inside the local kernel (flags, epochs, tickets)."""
+        p = self.p
+        rc = self.lib.emu_step_concurrent(self.h, p["dt"], p["gravity"], p["rho"], p["muN"], p["muT"], p["num_iterations"], n)
+        if rc == 77:
+            pytest.skip("this machine cannot create the OS threads the emulation needs")
+        assert rc == 0, "a halo wait gave up" if rc == 2 else rc
 
     def get(self):
         X = np.zeros((self.nV, 3), np.float32); V = np.zeros_like(X); XT = np.zeros_like(X)
@@ -291,3 +300,22 @@ def test_per_body_kernel_default_mode_vs_tile_kernels(pd, assets):
     err = max(meshes.rel_err(x, y, scale) for x, y in zip(a.get()[::2], b.get()[::2]))
     print(f"per-body kernel vs tile kernels, three grids, 6 steps: {err:.2e}")
     assert err <= 2e-5 and np.abs(a.get()[0] - X0).max() > 1e-3
+
+
+@pytest.mark.parametrize("world,trim", [(2, 0), (3, 1)])
+def test_in_kernel_halo_exchange_is_bit_identical_to_one_rank(pd, world, trim):
+    """The exchange as the multi-GPU engine runs it: every rank on its own thread, the boundary
+    positions pushed into the neighbours' buffers by the CTAs of the local kernel itself, ticket, epoch, flags, and the wait
+    only before the first boundary tile -- with the triple-buffered positions rotating across steps.  All CTAs of a launch
+    are resident at once here, as on the GPU.  (Logic only: the host's memory model is stronger than the GPU's.)"""
+    sc = pd.Scene.kuhn_grid(7, 6, 5, 1.0, 0.05, 5, (0, 3, 0), 1.0, 2e5)
+    sc.add_fixed(pd.fixed_body(pd.PD_PLANE, pos=(0, 0, 0), scale=(450, 450, 450)))
+    sc.params = pd.SolverParams(dt=1 / 60, gravity=9.8, num_iterations=10)
+    X0 = sc.arrays()["X"]
+    V0 = np.zeros_like(X0); V0[:, 1] = 0.3 * np.sin(X0[:, 0])
+    one = Emu(pd, sc)
+    many = Emu(pd, sc, world=world, trim=trim, grid=2)
+    one.set(V=V0); many.set(V=V0)
+    one.step(4); many.step_concurrent(4)            # 4 steps x 11 phases: the buffer rotation base visits 0, 2, 1, 0
+    for a, b in zip(one.get(), many.get()):
+        assert np.array_equal(_bits(a), _bits(b))
