@@ -179,6 +179,11 @@ def make_scene(pd, workload, rank=0):
     return sc, p
 
 
+def meshes_rel_err(x, r):
+    import meshes
+    return meshes.rel_err(x, r)
+
+
 def initial_velocity(X):
     """v = 0.5 sin(x/7) y^   so that F is non-trivial from the first iteration."""
     V = np.zeros_like(X)
@@ -209,14 +214,55 @@ def cpu_baseline(workload_iters, threads):
             "sample": f"oracle/pd_oracle.c (OpenMP, {threads} threads): {nsteps} steps x {workload_iters} it of the {cells}^3-cell Kuhn grid ({nT} tets), {dt:.1f} s"}
 
 
+def workload_config(workload, nV, nT, iters, p, batch, world):
+    """The `config` object of the JSON line: identical in both arms (--impl b200 / reference) for the same workload."""
+    stream_mb = 60.0 * nT / 1e6         # ~60 B/tet of tile stream (DESIGN.md 3.3) read once per PD iteration
+    return {"workload": workload, "description": WORKLOADS[workload][2], "num_verts": nV, "num_tets": nT,
+            "pd_iterations_per_step": iters, "global_solver": "chebyshev-jacobi", "dt": p["dt"], "gravity": p["gravity"], "mu": MU,
+            "rho": p["rho"], "muN": p["muN"], "muT": p["muT"],
+            "initial_velocity": "0" if batch else "0.5*sin(x/7) y^",
+            "l2": (f"inputs larger than L2: ~{stream_mb:.0f} MB of per-tet data are streamed per PD iteration, no flush needed" if stream_mb > 2 * 126
+                   else f"working set smaller than L2 (~{stream_mb:.0f} MB per PD iteration): not flushed -- 100 iterations per step re-read the same data, L2-resident is this workload's steady state"),
+            "parallelism": "single GPU" if world == 1 else ("contexts sharded 64 per GPU, no communication" if batch else f"vertex partition over {world} GPUs, tile-replicated boundary, NVLink peer-memory halo push + flags per PD iteration")}
+
+
+PARITY_STEPS = 10
+
+
+def reference_positions(a, p, iters, steps, runs=2):
+    """X after `steps` steps of the reference's own CUDA kernels (oracle/_ref, the CHECKER -- never timed here) on the scene
+    arrays `a`, `runs` times from the same start (the reference sums with float atomics: the runs differ)."""
+    import ref
+    rs = ref.RefScene(a["X"], a["Tet"], a["mass"], a["mu"], planes=[(np.zeros(3, np.float32), np.array([0, 1, 0], np.float32))])
+    kw = dict(dt=DT, gravity=GRAVITY, rho=p["rho"], muN=p["muN"], muT=p["muT"], num_iterations=iters)
+    out = []
+    for _ in range(runs):
+        rs.reset(); rs.set(V=initial_velocity(a["X"]))
+        rs.step(steps, **kw); rs.sync()
+        out.append(rs.get()[0].copy())
+    del rs
+    return out
+
+
+def engine_positions(eng, X0, steps):
+    eng.Reset(); eng.upload(V=initial_velocity(X0))
+    eng.Update(steps)
+    return eng.download()[0]
+
+
 def dist_setup(n_gpus):
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's "NCCL version ..." banner goes to stdout and would break the one-JSON-line contract
+        # (NCCL_DEBUG is left as the driver set it: its init lines carry the rank census the driver checks; the JSON line is
+        # the LAST line rank 0 prints)
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # rank census on stderr (one line per rank): the data plane is CUDA-IPC peer memory, not NCCL, so NCCL's own
+        # log shows only the setup collectives
+        print(f"[bench] rank {rank}/{world} local_rank {local} device cuda:{local} {torch.cuda.get_device_name(local)} "
+              f"uuid {torch.cuda.get_device_properties(local).uuid}", file=sys.stderr, flush=True)
     return rank, world, local
 
 
@@ -263,6 +309,8 @@ def run_b200(args):
         allt = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allt, t)
         allt = torch.stack(allt).cpu().numpy()
+        print(f"[bench] rank {rank}: owns {di['num_owned']} vertices, {di['num_ghosts']} ghosts, pushes {di['num_push']} positions per PD iteration "
+              f"to peer windows over NVLink (CUDA IPC)", file=sys.stderr, flush=True)
         dist_info = {"owned_verts_per_rank": allt[:, 0].tolist(), "ghost_verts_per_rank": allt[:, 1].tolist(),
                      "tets_evaluated_per_rank": allt[:, 2].tolist(), "pushed_verts_per_rank": allt[:, 3].tolist(),
                      "redundant_tet_fraction": float(allt[:, 2].sum() / nT - 1.0)}
@@ -333,6 +381,62 @@ def run_b200(args):
     halo_ok = eng.dist_status() == 0 if (world > 1 and not batch) else True
     barrier(world)
 
+    # ---- parity of what was just timed (outside every timed region; oracle/_ref is the CHECKER here, never the product)
+    parity = None
+    Xa = None
+    if not args.no_parity and not batch:
+        a = sc.arrays()
+        if world == 1:
+            import ref
+            Xe = engine_positions(eng, X0, PARITY_STEPS)
+            parity = {"workload": args.workload, "steps": PARITY_STEPS, "rot_mode": args.rot_mode,
+                      "definition": "max_v |x_v - ref_v| / max(|ref_v|, bounding-box diagonal) after `steps` steps from the benchmark's initial state"}
+            if ref.available():
+                Xa, Xb = reference_positions(a, p, iters, PARITY_STEPS)
+                parity.update({"reference": "oracle/_ref: the reference's CUDA kernels compiled verbatim (pdUtil.cu, svd3_cuda.h) replayed by oracle/ref_harness.cu",
+                               "rel_err": meshes_rel_err(Xe, Xa), "reference_vs_reference": meshes_rel_err(Xb, Xa)})
+            else:
+                parity.update({"reference": "unavailable (oracle/_ref/libpd_ref.so not built)", "rel_err": None})
+        else:
+            # N > 1: the partitioned run must be BIT-identical to one GPU.  Every rank contributes its owned
+            # vertices after 3 steps from the benchmark's initial state; rank 0 steps a single-GPU engine on the same mesh.
+            import torch.distributed as dist
+            steps_bi = 3
+            Xd = engine_positions(eng, X0, steps_bi)            # owned rows filled, others 0
+            own = np.zeros(nV, np.uint8); own[eng.owned_ids()] = 1
+            t = torch.from_numpy(np.ascontiguousarray(Xd * own[:, None])).cuda()
+            dist.all_reduce(t)                                  # disjoint owners: the sum is the assembled state, bit for bit
+            cnt = torch.from_numpy(own.astype(np.int32)).cuda(); dist.all_reduce(cnt)
+            Xall = t.cpu().numpy()
+            if rank == 0:
+                one = pd.PdSolver(sc, device=local, rot_mode=args.rot_mode)
+                X1 = engine_positions(one, X0, steps_bi)
+                one.close()
+                same = bool(np.array_equal(Xall, X1)) and bool(np.isfinite(X1).all()) and bool((cnt.cpu().numpy() == 1).all())
+                import hashlib
+                parity = {"workload": args.workload, "steps": steps_bi, "bit_identical_to_n1": same,
+                          "max_abs_diff_to_n1": float(np.abs(Xall.astype(np.float64) - X1).max()),
+                          "sha256_n": hashlib.sha256(Xall.tobytes()).hexdigest()[:16], "sha256_1": hashlib.sha256(X1.tobytes()).hexdigest()[:16],
+                          "every_vertex_owned_once": bool((cnt.cpu().numpy() == 1).all())}
+            barrier(world)
+
+    # ---- the bit-faithful mode (rot_mode 1: the reference's SVD operation for operation, reference summation order),
+    # second driver-visible value: its own timing and its own parity record (N = 1 only)
+    faithful = None
+    if world == 1 and not batch and not args.no_faithful and args.rot_mode == 0:
+        import ref
+        fe = pd.PdSolver(sc, device=local, rot_mode=1)
+        fe.upload(V=V0)
+        fe.Update(3)
+        fe.synchronize()
+        f_steps = max(1, min(args.steps, 2))
+        f_ms = fe.step_timed(f_steps) / f_steps
+        faithful = {"rot_mode": 1, "steps": f_steps, "ms_per_step": f_ms, "value": nT * iters / (f_ms * 1e-3) / 1e6, "unit": "Mtet-updates/s"}
+        if Xa is not None:
+            Xf = engine_positions(fe, X0, PARITY_STEPS)
+            faithful["parity_rel_err"] = meshes_rel_err(Xf, Xa)
+        fe.close()
+
     if rank != 0:
         if world > 1:
             import torch.distributed as dist
@@ -345,13 +449,11 @@ def run_b200(args):
         "value": value, "unit": "Mtet-updates/s", "pd_iters_per_s": iters / (ms_step * 1e-3),
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak" if batch else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "description": WORKLOADS[args.workload][2], "num_verts": nV * (world if batch else 1), "num_tets": nT_job,
-                   "pd_iterations_per_step": iters, "global_solver": "chebyshev-jacobi", "dt": p["dt"], "gravity": p["gravity"], "mu": MU,
-                   "initial_velocity": "0" if batch else "0.5*sin(x/7) y^", "l2": (f"inputs larger than L2: tile stream {info['tile_stream_bytes'] / 1e6:.0f} MB per iteration, no flush needed" if info["tile_stream_bytes"] > 2 * 126e6
-                          else f"working set smaller than L2 (tile stream {info['tile_stream_bytes'] / 1e6:.0f} MB): not flushed -- 100 iterations per step re-read the same stream, L2-resident is this workload's steady state"),
-                   "finite": finite, "parallelism": "single GPU" if world == 1 else ("contexts sharded 64 per GPU, no communication" if batch else f"vertex partition over {world} GPUs, tile-replicated boundary, NVLink peer-memory halo push + flags per PD iteration"),
-                   "multi_gpu": dist_info, "halo_ok": halo_ok,
-                   "experiments": {k: os.environ[k] for k in ("PD_DIST_TRIM", "PD_B200_LIB", "PD_PDL", "PD_NO_STAGE_COLOR") if os.environ.get(k)} or None},
+        "config": workload_config(args.workload, nV * (world if batch else 1), nT_job, iters, p, batch, world),
+        "run": {"finite": finite, "multi_gpu": dist_info, "halo_ok": halo_ok, "tile_stream_bytes": info["tile_stream_bytes"], "rot_mode": args.rot_mode,
+                "experiments": {k: os.environ[k] for k in ("PD_DIST_TRIM", "PD_B200_LIB", "PD_PDL", "PD_NO_STAGE_COLOR") if os.environ.get(k)} or None},
+        "parity": parity,
+        "faithful": faithful,
         "clocks": clocks,
         "e2e": {"value": nT_job * iters / (e2e_ms * 1e-3) / 1e6, "unit": "Mtet-updates/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": job_bytes, "d2h_bytes_per_step": job_bytes, "steps": e2e_steps,
@@ -393,25 +495,32 @@ def run_reference(args):
     base = {"metric": "Mtet-updates/s & PD iters/s at 1/2/4/8 B200; % of HBM roofline", "unit": "Mtet-updates/s",
             "impl": "reference", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": WORKLOADS[args.workload][2], "num_verts": nV, "num_tets": nT,
-                       "pd_iterations_per_step": iters}}
+            "config": workload_config(args.workload, nV, nT, iters, p, False, 1)}
     cpu = cpu_baseline(iters, cores)
     if ref.available():
         rs = ref.RefScene(a["X"], a["Tet"], a["mass"], a["mu"], planes=[(np.zeros(3, np.float32), np.array([0, 1, 0], np.float32))])
         rs.set(V=initial_velocity(a["X"]))
         kw = dict(dt=DT, gravity=GRAVITY, rho=p["rho"], muN=p["muN"], muT=p["muT"], num_iterations=iters)
         rs.step(args.warmup, **kw); rs.sync()
+        # same clock as the other arm: CUDA events on the stream the kernels run on (the harness launches on the legacy
+        # default stream, which is torch's current stream); the host clock around the same region is kept as a cross-check
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
         sampler = ClockSampler(0); sampler.start()
         t0 = time.perf_counter()
-        rs.step(args.steps, perf=False, **kw); rs.sync()
+        e0.record()
+        rs.step(args.steps, perf=False, **kw)
+        e1.record(); e1.synchronize(); rs.sync()
         t1 = time.perf_counter()
         clocks = sampler.stop()
-        ms = (t1 - t0) * 1e3 / args.steps
+        ms = e0.elapsed_time(e1) / args.steps
+        ms_host_clock = (t1 - t0) * 1e3 / args.steps
         t0 = time.perf_counter()
         rs.step(max(1, args.steps // 2), perf=True, **kw); rs.sync()     # as shipped: SetPerf(true), 2 event syncs per iteration
         ms_perf = (time.perf_counter() - t0) * 1e3 / max(1, args.steps // 2)
         val = nT * iters / (ms * 1e-3) / 1e6
-        base.update({"value": val, "ms_per_step": ms, "pd_iters_per_s": iters / (ms * 1e-3), "clocks": clocks,
+        base.update({"value": val, "ms_per_step": ms, "ms_per_step_host_clock": ms_host_clock, "pd_iters_per_s": iters / (ms * 1e-3), "clocks": clocks,
                      "reference_kind": "the reference's CUDA kernels (pdUtil.cu, svd3_cuda.h, computeInvDmV0) compiled verbatim for sm_100a, replayed by oracle/ref_harness.cu on one B200",
                      "value_perf_true": nT * iters / (ms_perf * 1e-3) / 1e6, "ms_per_step_perf_true": ms_perf,
                      "gpu_launches": int(args.steps * (5 + 4 * iters + 1)),
@@ -432,6 +541,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="grid139", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity record (experiments: saves the reference replay)")
+    ap.add_argument("--no-faithful", action="store_true", help="skip the rot_mode=1 record")
     ap.add_argument("--rot-mode", type=int, default=0, help="experiments only: 0 product default, 1 faithful SVD, 2 no projection (timing probe)")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="experiments only: cap the local kernel's resident CTAs per SM")
     args = ap.parse_args()

@@ -118,6 +118,7 @@ protected:
         desc.X = X.data(); desc.Tet = tet.data(); desc.mass = mass.data(); desc.mu = mu.data(); desc.DBC = dbc.data();
         desc.num_fixed = (int)fixed_.size(); desc.fixed = fixed_.data();
         pd_params p; toParams(sp, &p);
+        noteCollision(p);
         pd_scene* scene = pd_scene_from_desc(&desc, &p);
         if (!scene) { std::fprintf(stderr, "B200PdSolver: %s\n", pd_last_error()); return; }
         pd_engine_options opt; pd_default_options(&opt);
@@ -131,11 +132,7 @@ protected:
     bool SolverStep(SolverData<float>& d, const SolverParams<float>& sp) override
     {
         pd_params p; toParams(sp, &p);
-        if (p.handle_collision) {
-            /* mesh-mesh BVH/CCD stays in the reference (pdSolver.cu:218-225): step with it off, then the
-             * caller's DetectCollision/CCDKernel pair can run on the exported X/XTilde/V. */
-            p.handle_collision = 0;
-        }
+        noteCollision(p);
         pd_set_perf(engine_, perf ? 1 : 0);
         /* mouse drag (README "PD solver supports interactive object dragging"): while MouseSelection::dragging the
          * caller's Control_Kernel keeps SolverData::moreDBC / OffsetX up to date (simulationContext.cu:202-231) and
@@ -163,6 +160,20 @@ protected:
     }
 
 private:
+    /* SolverParams::handleCollision (the GUI default, context.h:44) asks for the mesh-mesh BVH/CCD pass of
+     * PdSolver::Update (pdSolver.cu:218-225).  An engine built without surface triangles cannot run it: say so ONCE
+     * and step with the flag off -- X is then already XTilde on return (pdSolver.cu:227), so the caller cannot run
+     * DetectCollision/CCDKernel between the old X and XTilde afterwards. */
+    void noteCollision(pd_params& p)
+    {
+        if (!p.handle_collision || collisionOk_) return;
+        if (!collisionNoted_) {
+            std::fprintf(stderr, "B200PdSolver: handleCollision=true but no surface triangles were given to the engine; "
+                                 "mesh-mesh collision is OFF for this solver (fixed bodies still respond)\n");
+            collisionNoted_ = true;
+        }
+        p.handle_collision = 0;
+    }
     void toParams(const SolverParams<float>& sp, pd_params* p) const
     {
         pd_default_params(p);
@@ -178,4 +189,5 @@ private:
     int solverType_ = PD_JACOBI;
     int device_ = 0;
     bool dragSeen_ = false;
+    bool collisionOk_ = false, collisionNoted_ = false;
 };

@@ -76,13 +76,20 @@ typedef struct {
     const pd_fixed_body* fixed;
 } pd_scene_desc;
 
+#define PD_ROT_AUTO (-1)
 typedef struct {
     int device;               /* CUDA device ordinal                                          */
-    int rot_mode;             /* 0 Newton polar + SVD fallback (default), 1 always Jacobi SVD  */
+    int rot_mode;             /* PD_ROT_AUTO (default): the bit-faithful mode (1, input tet order) on a mesh that fits one
+                               * tile (<= 256 tets: one warp-sized launch of the reference is deterministic and the mode
+                               * costs nothing there), else 0;  0 Newton polar + SVD fallback;  1 always the reference's
+                               * Jacobi SVD, sums in the reference's order (bit-exact parity mode, ~4x slower local step) */
     int reorder;              /* 1 (default) Morton tet order + first-touch vertex renumbering */
     int use_graph;            /* 1 (default) one CUDA graph per step                          */
     int ctas_per_sm;          /* 0 = occupancy query                                          */
     int rank, world;          /* multi-GPU: this engine is rank `rank` of `world` (default 0 of 1); one process per GPU */
+    int body_kernel;          /* -1 (default) auto: a scene whose connected components all fit one CTA's shared memory (the
+                               * batches of small bodies of BASELINE config 5) steps with one CTA per body and ONE launch per
+                               * step; 0: always the tile kernels */
 } pd_engine_options;
 
 /* PdSolver::GetPerformanceData (solver.h:20, pdSolver.cu:26): the four named counters, ms */
@@ -235,6 +242,8 @@ int pd_time_kernels(pd_engine*, int reps, float* local_ms, float* vertex_ms);
 int pd_profile_local(pd_engine*, unsigned long long* out);
 int pd_engine_info(const pd_engine*, int* num_verts, int* num_tets, int* num_tiles, uint32_t* num_slots,
                    size_t* tile_stream_bytes, size_t* device_bytes, int* local_grid);
+/* the rotation mode the engine runs (PD_ROT_AUTO resolved): 0 or 1 */
+int pd_engine_rot_mode(const pd_engine*);
 /* ---- multi-GPU engine (options.world > 1): every rank creates its engine from the SAME scene, exchanges the
  * 64-byte window handles (e.g. torch.distributed.all_gather) and connects; pd_step then runs the ranks in
  * lock step through halo flags in peer memory (no host synchronisation, no NCCL on the data path).

@@ -8,6 +8,6 @@ timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 python - <<PY
 import json
 d=[json.loads(l) for l in open("gpurun_out/dist_bench_n${N}_$W.json") if l.startswith("{")][-1]; r=d["roofline"]
-print("$W N=$N ms/step %.3f value %.0f e2e %.0f local %.1f us vertex %.1f us halo_ok %s"%(d["ms_per_step"], d["value"], d["e2e"]["value"], r["launch_ms"]*1e3, r["fused_iteration"]["vertex_kernel_ms"]*1e3, d["config"]["halo_ok"]), d["clocks"]["sm_mhz"])
-print(d["config"]["multi_gpu"])
+print("$W N=$N ms/step %.3f value %.0f e2e %.0f local %.1f us vertex %.1f us halo_ok %s"%(d["ms_per_step"], d["value"], d["e2e"]["value"], r["launch_ms"]*1e3, r["fused_iteration"]["vertex_kernel_ms"]*1e3, d["run"]["halo_ok"]), d["clocks"]["sm_mhz"])
+print(d["run"]["multi_gpu"])
 PY

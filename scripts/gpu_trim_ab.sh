@@ -14,7 +14,7 @@ import json
 for rep in (1, 2):
     for t in (0, 1):
         try:
-            d=[json.loads(l) for l in open(f"gpurun_out/trim{t}_n${N}_${W}_{rep}.json") if l.startswith("{")][-1]; r=d["roofline"]; m=d["config"]["multi_gpu"]
-            print("trim", t, "rep", rep, "$W N=$N ms/step %.3f value %.0f local %.1f us vertex %.1f us halo_ok %s redundant %.3f"%(d["ms_per_step"], d["value"], r["launch_ms"]*1e3, r["fused_iteration"]["vertex_kernel_ms"]*1e3, d["config"]["halo_ok"], m["redundant_tet_fraction"]), max(m["tets_evaluated_per_rank"]))
+            d=[json.loads(l) for l in open(f"gpurun_out/trim{t}_n${N}_${W}_{rep}.json") if l.startswith("{")][-1]; r=d["roofline"]; m=d["run"]["multi_gpu"]
+            print("trim", t, "rep", rep, "$W N=$N ms/step %.3f value %.0f local %.1f us vertex %.1f us halo_ok %s redundant %.3f"%(d["ms_per_step"], d["value"], r["launch_ms"]*1e3, r["fused_iteration"]["vertex_kernel_ms"]*1e3, d["run"]["halo_ok"], m["redundant_tet_fraction"]), max(m["tets_evaluated_per_rank"]))
         except Exception as e: print("trim", t, rep, "failed", e)
 PY

@@ -48,7 +48,7 @@ class pd_scene_desc(C.Structure):
 
 class pd_engine_options(C.Structure):
     _fields_ = [("device", C.c_int), ("rot_mode", C.c_int), ("reorder", C.c_int), ("use_graph", C.c_int),
-                ("ctas_per_sm", C.c_int), ("rank", C.c_int), ("world", C.c_int)]
+                ("ctas_per_sm", C.c_int), ("rank", C.c_int), ("world", C.c_int), ("body_kernel", C.c_int)]
 
 
 class pd_perf(C.Structure):
@@ -132,6 +132,7 @@ SYMBOLS = {
     "pd_get_solve_stats": (_I, [_VP, _PF, _PI]),
     "pd_time_kernels": (_I, [_VP, _I, _PF, _PF]),
     "pd_profile_local": (_I, [_VP, _VP]),
+    "pd_engine_rot_mode": (_I, [_VP]),
     "pd_engine_info": (_I, [_VP, _PI, _PI, _PI, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), _PI]),
     "pd_rotation_batch": (_I, [_I, _I, _I, _VP, _VP, _VP]),
     "pd_alloc_pinned": (_VP, [C.c_size_t]),
@@ -371,8 +372,8 @@ class PdSolver:
 
     SolverType = {"Jacobi": PD_JACOBI, "CuSolverCholesky": PD_CHOLESKY, "EigenCholesky": PD_CHOLESKY, "PCGJacobi": PD_PCG_JACOBI}
 
-    def __init__(self, scene, device=0, rot_mode=0, reorder=1, use_graph=1, ctas_per_sm=0, rank=0, world=1):
-        o = pd_engine_options(device, rot_mode, reorder, use_graph, ctas_per_sm, rank, world)
+    def __init__(self, scene, device=0, rot_mode=-1, reorder=1, use_graph=1, ctas_per_sm=0, rank=0, world=1, body_kernel=-1):
+        o = pd_engine_options(device, rot_mode, reorder, use_graph, ctas_per_sm, rank, world, body_kernel)
         self._h = lib().pd_create(scene._h, C.byref(o))
         if not self._h:
             raise PdError(_err())
@@ -540,7 +541,7 @@ class PdSolver:
         ns = C.c_uint32(); sb, db = C.c_size_t(), C.c_size_t()
         _check(lib().pd_engine_info(self._h, C.byref(nv), C.byref(nt), C.byref(ntl), C.byref(ns), C.byref(sb), C.byref(db), C.byref(lg)))
         return dict(num_verts=nv.value, num_tets=nt.value, num_tiles=ntl.value, num_slots=ns.value,
-                    tile_stream_bytes=sb.value, device_bytes=db.value, local_grid=lg.value)
+                    tile_stream_bytes=sb.value, device_bytes=db.value, local_grid=lg.value, rot_mode=lib().pd_engine_rot_mode(self._h))
 
 
 def cholesky_factor(rowptr, col, val):

@@ -56,7 +56,7 @@ const char* pd_last_error(void) { return g_err.c_str(); }
 const char* pd_version(void) { return "pd_b200 0.1 (sm_100a)"; }
 
 void pd_default_params(pd_params* p) { SolverParams d; to_c(d, p); }
-void pd_default_options(pd_engine_options* o) { o->device = 0; o->rot_mode = 0; o->reorder = 1; o->use_graph = 1; o->ctas_per_sm = 0; o->rank = 0; o->world = 1; }
+void pd_default_options(pd_engine_options* o) { o->device = 0; o->rot_mode = PD_ROT_AUTO; o->reorder = 1; o->use_graph = 1; o->ctas_per_sm = 0; o->rank = 0; o->world = 1; o->body_kernel = -1; }
 
 // ------------------------------------------------------------------ scene
 pd_scene* pd_scene_load_json(const char* json_path, const char* context_name, const char* asset_root)
@@ -368,7 +368,7 @@ pd_engine* pd_create(const pd_scene* s, const pd_engine_options* o)
     if (!s) { g_err = "scene is NULL"; return nullptr; }
     EngineOptions eo;
     if (o) { eo.device = o->device; eo.rotMode = o->rot_mode; eo.reorder = o->reorder; eo.useGraph = o->use_graph; eo.ctasPerSm = o->ctas_per_sm;
-             eo.rank = o->rank; eo.world = o->world < 1 ? 1 : o->world; }
+             eo.rank = o->rank; eo.world = o->world < 1 ? 1 : o->world; eo.bodyKernel = o->body_kernel; }
     pd_engine* e = new pd_engine{nullptr};
     try { e->e = new Engine(s->s, eo); } catch (...) { delete e; throw; }
     return e;
@@ -497,6 +497,8 @@ int pd_engine_info(const pd_engine* e, int* nv, int* nt, int* ntiles, uint32_t* 
     if (lgrid) *lgrid = e->e->localGrid();
     return PD_OK;
 }
+
+int pd_engine_rot_mode(const pd_engine* e) { return (e && e->e) ? e->e->rotMode() : PD_ERR_INVALID; }
 
 int pd_dist_window_handle(pd_engine* e, void* out64) { ENGINE_CALL(if (!out64) return fail(PD_ERR_INVALID, "out is NULL"); e->e->windowHandle(out64)) }
 int pd_dist_connect(pd_engine* e, const void* handles) { ENGINE_CALL(if (!handles) return fail(PD_ERR_INVALID, "handles is NULL"); e->e->connectIpc(handles)) }

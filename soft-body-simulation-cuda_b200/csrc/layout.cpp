@@ -567,6 +567,29 @@ void cholesky_factor(const CsrMatrix& A, CholFactor& F)
     for (int i = 0; i < n; ++i) { F.lCol[(size_t)fill[(size_t)i]] = i; F.lVal[(size_t)fill[(size_t)i]] = (float)diag[(size_t)i]; }
 }
 
+bool connected_body_ranges(int nV, int nT, const uint32_t* Tet, std::vector<int>& starts)
+{
+    starts.clear();
+    std::vector<int> parent((size_t)nV);
+    for (int v = 0; v < nV; ++v) parent[(size_t)v] = v;
+    auto find = [&](int v) { while (parent[(size_t)v] != v) { parent[(size_t)v] = parent[(size_t)parent[(size_t)v]]; v = parent[(size_t)v]; } return v; };
+    for (int t = 0; t < nT; ++t) {
+        const int a = find((int)Tet[4 * (size_t)t]);
+        for (int k = 1; k < 4; ++k) {
+            const int b = find((int)Tet[4 * (size_t)t + k]);
+            if (b != a) parent[(size_t)std::max(a, b)] = std::min(a, b);      // the root of a component is its smallest vertex
+        }
+    }
+    // contiguous ranges <=> walking the vertices in order, the root changes only to the current vertex itself
+    int cur = -1;
+    for (int v = 0; v < nV; ++v) {
+        const int r = find(v);
+        if (r == v) { starts.push_back(v); cur = v; }
+        else if (r != cur) { starts.clear(); return false; }
+    }
+    return !starts.empty();
+}
+
 void build_body_batch(int nV, int nT, const float* X, const uint32_t* Tet, const float* mu, const std::vector<int>& bodyVertStart,
                       const uint32_t* vertNewOfOld, BodyBatch& out)
 {

@@ -184,6 +184,10 @@ struct BodyBatch {
     std::vector<float> md;              // matrix_diag per body-local vertex, summed in that same order
     uint32_t nVmax = 0, nTmax = 0;      // capacities the kernel's shared-memory carve-up is sized for (multiples of 32)
 };
+// The soft bodies of a scene as its CONNECTED COMPONENTS (tets sharing a vertex): without mesh-mesh collision the PD system
+// is block diagonal per component whatever the scene file calls a body.  Returns false when a component is not a contiguous
+// vertex range (then the per-body kernel does not apply); starts = first vertex id of every component, ascending.
+bool connected_body_ranges(int nV, int nT, const uint32_t* Tet, std::vector<int>& starts);
 // bodyVertStart: first ORIGINAL vertex id of every body (ascending; bodies own contiguous vertex and tet ranges, as
 // DataLoader::AllocData lays them out).  Throws if a tet spans two bodies or a body exceeds the u16 index ranges.
 void build_body_batch(int nV, int nT, const float* X, const uint32_t* Tet, const float* mu, const std::vector<int>& bodyVertStart,

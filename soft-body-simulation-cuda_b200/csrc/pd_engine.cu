@@ -91,7 +91,7 @@ struct Engine::Impl {
     double* red = nullptr;
     float4** peerP = nullptr; unsigned long long** peerPFlag = nullptr; double** peerRed = nullptr;
     std::vector<void*> ipcOpened;
-    cudaEvent_t lockEvent = nullptr;
+    cudaEvent_t lockEvent = nullptr, callerEvent = nullptr;
     // non-Jacobi global solvers (PCG, sparse Cholesky)
     bool solverReady = false, cholReady = false;
     CsrDev A{0, nullptr, nullptr, nullptr, nullptr};
@@ -105,6 +105,17 @@ struct Engine::Impl {
     size_t nnzA = 0, nnzL = 0;
     DistWait wait{nullptr, nullptr, nullptr, 0, 0x7fffffff, nullptr};
 };
+
+// give a dalloc'ed buffer back (re-prepared system matrix / factor after Reset)
+void Engine::dfree(const void* p, size_t bytes)
+{
+    if (!p) return;
+    auto& a = d_->allocs;
+    auto it = std::find(a.begin(), a.end(), const_cast<void*>(p));
+    if (it != a.end()) a.erase(it);
+    cudaFree(const_cast<void*>(p));
+    devBytes_ -= std::min(devBytes_, bytes);
+}
 
 template <typename T>
 T* Engine::dalloc(size_t n)
@@ -137,13 +148,20 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     pdlActive_ = usePdl_;
     CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
 
+    if (opt_.rotMode < 0) {
+        // auto: a mesh that fits one tile is launch-latency bound whatever the rotation costs, and the reference's
+        // float atomics are deterministic at that size -- reproduce it bit for bit (faithful SVD, input tet order)
+        const bool oneTile = opt_.world == 1 && scene_.numTets <= TILE_T && scene_.numVerts <= TILE_NLMAX;
+        opt_.rotMode = oneTile ? 1 : 0;
+        if (oneTile) opt_.reorder = 0;
+    }
     if (opt.world == 1) {
-        build_layout(scene_.numVerts, scene_.numTets, scene_.X.data(), scene_.Tet.data(), scene_.mu.data(), opt.reorder != 0, L_);
+        build_layout(scene_.numVerts, scene_.numTets, scene_.X.data(), scene_.Tet.data(), scene_.mu.data(), opt_.reorder != 0, L_);
         nOwn_ = L_.nV;
     } else {
         // every rank builds the same global layout, then keeps the tiles that touch its vertex range
         Layout G;
-        build_layout(scene_.numVerts, scene_.numTets, scene_.X.data(), scene_.Tet.data(), scene_.mu.data(), opt.reorder != 0, G);
+        build_layout(scene_.numVerts, scene_.numTets, scene_.X.data(), scene_.Tet.data(), scene_.mu.data(), opt_.reorder != 0, G);
         build_rank_plan(G, opt.world, opt.rank, plan_, dist_trim_from_env());
         extract_rank_layout(G, plan_, L_);      // plan_.trim (PD_DIST_TRIM=1): trimmed + packed boundary tiles (experiment, layout.hpp)
         nOwn_ = plan_.nOwn;
@@ -246,12 +264,30 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     if (opt.ctasPerSm > 0) perSm = std::min(perSm, opt.ctasPerSm);
     localGrid_ = std::min(L_.nTiles, numSms_ * perSm);
 
-    // EXPERIMENT (opt-in): scenes made of many small bodies step with one CTA per body and one launch per step
-    if (const char* e = std::getenv("PD_BODY_KERNEL")) bodyKernel_ = std::atoi(e) != 0 && opt.world == 1 && opt.rotMode != 2 && !scene_.bodyVertStart.empty();
+    // Scenes made of SMALL bodies (every connected component fits one CTA's shared memory: BASELINE config 5, the cube, house +
+    // sphere) step with one CTA per body and ONE launch per step (pd_body_kernel.cuh) instead of 2 + 2 * iterations launches
+    // that cannot fill the GPU: measured 8x on batch64 (profiles/r2_*).  PD_BODY_KERNEL=0 keeps the tile path (A/B runs).
+    bodyKernel_ = opt.world == 1 && opt_.rotMode != 2 && opt_.bodyKernel != 0;
+    if (const char* e = std::getenv("PD_BODY_KERNEL")) bodyKernel_ = bodyKernel_ && std::atoi(e) != 0;
+    std::vector<int> bodyStarts;
+    if (bodyKernel_) {
+        int maxOptin = 0;
+        CUDA_CHECK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, opt.device));
+        bodyKernel_ = connected_body_ranges(scene_.numVerts, scene_.numTets, scene_.Tet.data(), bodyStarts);
+        if (bodyKernel_) {      // cheap size check before anything is built: the largest component must fit
+            std::vector<int> tetsOf(bodyStarts.size(), 0);
+            for (int t = 0; t < scene_.numTets; ++t)
+                ++tetsOf[(size_t)(std::upper_bound(bodyStarts.begin(), bodyStarts.end(), (int)scene_.Tet[4 * (size_t)t]) - bodyStarts.begin()) - 1];
+            for (size_t b = 0; b < bodyStarts.size() && bodyKernel_; ++b) {
+                const int nVb = ((b + 1 < bodyStarts.size()) ? bodyStarts[b + 1] : scene_.numVerts) - bodyStarts[b];
+                bodyKernel_ = body_smem_bytes(((uint32_t)nVb + 31u) & ~31u, ((uint32_t)tetsOf[b] + 31u) & ~31u) <= (size_t)maxOptin;
+            }
+        }
+    }
     if (bodyKernel_) {
         try {
             BodyBatch bb;
-            build_body_batch(scene_.numVerts, scene_.numTets, scene_.X.data(), scene_.Tet.data(), scene_.mu.data(), scene_.bodyVertStart, L_.vertNewOfOld.data(), bb);
+            build_body_batch(scene_.numVerts, scene_.numTets, scene_.X.data(), scene_.Tet.data(), scene_.mu.data(), bodyStarts, L_.vertNewOfOld.data(), bb);
             int maxOptin = 0;
             CUDA_CHECK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, opt.device));
             d.bSmem = body_smem_bytes(bb.nVmax, bb.nTmax);
@@ -268,7 +304,7 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
             CUDA_CHECK(cudaFuncSetAttribute((const void*)k_body_step<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.bSmem));
             CUDA_CHECK(cudaFuncSetAttribute((const void*)k_body_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.bSmem));
         } catch (const std::exception& ex) {
-            std::fprintf(stderr, "pd_b200: PD_BODY_KERNEL ignored for this scene (%s); the tile path runs\n", ex.what());
+            if (std::getenv("PD_BODY_KERNEL")) std::fprintf(stderr, "pd_b200: per-body kernel not used for this scene (%s); the tile path runs\n", ex.what());
             bodyKernel_ = false;
         }
     }
@@ -284,6 +320,7 @@ Engine::~Engine()
         for (cudaGraphExec_t g : d_->graphExec) if (g) cudaGraphExecDestroy(g);
         for (cudaEvent_t ev : d_->events) cudaEventDestroy(ev);
         if (d_->lockEvent) cudaEventDestroy(d_->lockEvent);
+        if (d_->callerEvent) cudaEventDestroy(d_->callerEvent);
         for (void* p : d_->ipcOpened) cudaIpcCloseMemHandle(p);
         for (void* p : d_->allocs) cudaFree(p);
         if (stream_) cudaStreamDestroy(stream_);
@@ -464,8 +501,17 @@ void Engine::buildGraph()
     if (d.graphExec[b]) return;
     const long long phaseSaved = phase_;
     cudaGraph_t graph = nullptr;
+    if (opt_.world > 1 && !connected_) throw std::runtime_error("multi-GPU engine stepped before pd_dist_connect");
     CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
-    enqueueStep(false);
+    try {
+        enqueueStep(false);
+    } catch (...) {                       // never leave the stream in capture mode
+        cudaStreamEndCapture(stream_, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        phase_ = phaseSaved;
+        throw;
+    }
     CUDA_CHECK(cudaStreamEndCapture(stream_, &graph));
     phase_ = phaseSaved;                  // capturing ran nothing
     CUDA_CHECK(cudaGraphInstantiate(&d.graphExec[b], graph, 0));
@@ -556,8 +602,22 @@ float Engine::stepTimed(int nSteps)
 }
 
 // ---------------------------------------------------------------- state transfer
+// The engine's stream is non-blocking, i.e. NOT ordered against the caller's legacy default stream, on which the
+// reference writes the SolverData arrays asynchronously (Control_Kernel in ResetMoreDBC, the D2D copies of Reset, the
+// BVH / CCD kernels): every entry point that reads CALLER DEVICE memory first makes the stream wait for whatever the
+// legacy stream has been given so far.
+void Engine::waitCallerStream()
+{
+    Impl& d = *d_;
+    if (!d.callerEvent) CUDA_CHECK(cudaEventCreateWithFlags(&d.callerEvent, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventRecord(d.callerEvent, cudaStreamLegacy));
+    CUDA_CHECK(cudaStreamWaitEvent(stream_, d.callerEvent, 0));
+}
+
 void Engine::importDevice(const float* dX, const float* dV, const float* dXTilde)
 {
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    waitCallerStream();
     Impl& d = *d_;
     const int vb = 256, vg = (nV_ + vb - 1) / vb;
     if (dX) k_import3<<<vg, vb, 0, stream_>>>(nV_, dX, d.oldOfNew, d.X);
@@ -568,6 +628,7 @@ void Engine::importDevice(const float* dX, const float* dV, const float* dXTilde
 
 void Engine::exportDevice(float* dX, float* dV, float* dXTilde)
 {
+    CUDA_CHECK(cudaSetDevice(opt_.device));
     Impl& d = *d_;
     const int vb = 256, vg = (nV_ + vb - 1) / vb;
     // multi-GPU: owned vertices only (the caller combines the ranks' disjoint contributions)
@@ -709,6 +770,7 @@ void Engine::setDragDevice(const float* dMore, const float* dOffsetX, const floa
     Impl& d = *d_;
     if (!dMore) { setDrag(nullptr, nullptr, nullptr); return; }
     ensureDragBuffers();
+    waitCallerStream();
     const int vb = 256, vg = (nV_ + vb - 1) / vb;
     CUDA_CHECK(cudaMemsetAsync(d.dragFlag, 0, 4, stream_));
     k_import1<<<vg, vb, 0, stream_>>>(nV_, dMore, d.oldOfNew, d.more, d.dragFlag);
@@ -874,6 +936,11 @@ void Engine::prepareSolver()
             if (std::fabs(dg) < 1e-9f) dg = 1.0f;                               // ExtractInverseDiagonalKernel, pcgJacobi.cu:6-19
             inv[(size_t)v] = 1.0f / dg;
         }
+        if (d.A.rowPtr) {       // re-prepare after Reset: the previous matrix goes back first (same pattern, new values)
+            CUDA_CHECK(cudaStreamSynchronize(stream_));
+            dfree(d.A.rowPtr, ((size_t)d.A.n + 1) * 4); dfree(d.A.col, d.nnzA * 4); dfree(d.A.val, d.nnzA * 4); dfree(d.A.invDiag, (size_t)nV_ * 4);
+            d.A = CsrDev{0, nullptr, nullptr, nullptr, nullptr};
+        }
         int* rp = dalloc<int>(A.rowPtr.size()); int* cl = dalloc<int>(A.col.size()); float* vl = dalloc<float>(A.val.size()); float* iv = dalloc<float>(nV_);
         CUDA_CHECK(cudaMemcpy(rp, A.rowPtr.data(), A.rowPtr.size() * 4, cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaMemcpy(cl, A.col.data(), A.col.size() * 4, cudaMemcpyHostToDevice));
@@ -906,6 +973,12 @@ void Engine::prepareSolver()
         if (nV_ > 262144) throw std::runtime_error("the sparse Cholesky global step is the small-mesh path (<= 262144 vertices); use Jacobi or PCG");
         CholFactor F;
         cholesky_factor(hostA_, F);
+        if (d.C.lPtr) {
+            CUDA_CHECK(cudaStreamSynchronize(stream_));
+            dfree(d.C.lPtr, ((size_t)d.C.n + 1) * 4); dfree(d.C.lCol, d.nnzL * 4); dfree(d.C.lVal, d.nnzL * 4);
+            dfree(d.C.uPtr, ((size_t)d.C.n + 1) * 4); dfree(d.C.uCol, d.nnzL * 4); dfree(d.C.uVal, d.nnzL * 4);
+            d.C = CholDev{0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        }
         int* lp = dalloc<int>(F.lPtr.size()); int* lc = dalloc<int>(F.lCol.size()); float* lv = dalloc<float>(F.lVal.size());
         int* up = dalloc<int>(F.uPtr.size()); int* uc = dalloc<int>(F.uCol.size()); float* uv = dalloc<float>(F.uVal.size());
         CUDA_CHECK(cudaMemcpy(lp, F.lPtr.data(), F.lPtr.size() * 4, cudaMemcpyHostToDevice));

@@ -21,7 +21,10 @@ struct PerfCounters {      // PdSolver::performanceData, pdSolver.cu:26 (millise
 
 struct EngineOptions {
     int device = 0;
-    int rotMode = 0;        // 0 Newton polar + SVD fallback (default), 1 always the Jacobi SVD
+    int rotMode = -1;       // -1 auto (default): 1 with reorder 0 on a mesh that fits ONE tile (where the reference is deterministic and the
+                            // mode costs nothing: bit-exact reproduction), else 0;  0 Newton polar + SVD fallback;  1 always the Jacobi SVD
+    int bodyKernel = -1;    // -1 auto: scenes whose connected components all fit one CTA's shared memory step with one CTA per body and one
+                            // launch per step (pd_body_kernel.cuh); 0 never (the tile path)
     int reorder = 1;        // Morton reordering of tets / first-touch renumbering of vertices
     int useGraph = 1;       // replay each step as one CUDA graph
     int ctasPerSm = 0;      // 0 = occupancy query
@@ -92,6 +95,7 @@ public:
     void getSetup(float* matrixDiag, float* massDt2, float* DmInv, float* V0);
     // launch geometry, for the bench's launch count / roofline bookkeeping
     int localGrid() const { return localGrid_; }
+    int rotMode() const { return opt_.rotMode; }      // the effective mode (options.rotMode < 0 = auto is resolved in the ctor)
     size_t deviceBytes() const { return devBytes_; }
     size_t tileStreamBytes() const { return L_.records.size(); }
     cudaStream_t stream() const { return stream_; }
@@ -117,6 +121,8 @@ private:
     void finishDragUpdate(const float target[3]);
     void launchLocal(const float4* q, bool jacobi, unsigned long long* prof = nullptr, int pushBuf = -1);
     template <typename T> T* dalloc(size_t n);
+    void dfree(const void* p, size_t bytes);
+    void waitCallerStream();
 
     int nV_ = 0, nT_ = 0, nOwn_ = 0;
     RankPlan plan_;

@@ -13,10 +13,13 @@ Tolerances (DESIGN.md section 8 has the measured noise floor these come from):
     spread exceeds 1e-4 the bound is 10x the spread measured in the same test (two reference runs;
     the spread of two samples is itself noisy), plus a 1e-3 bound on every body's centroid, which the
     high-frequency noise does not move.
-  * DEFAULT mode (Newton polar rotation, exact to float rounding) on the 6-tet cube, where the
-    reference IS deterministic: 2e-4.  The reference's 4-sweep approximate SVD puts it 1.33e-4 away
-    from the exact-arithmetic trajectory (oracle f64 twin), so anything that does not replicate
-    that SVD's rounding lands at the same distance; the faithful mode shows the rest is identical."""
+  * The 6-tet cube (C1) is the one scene where the reference IS deterministic (one warp).  The engine's default there
+    (rot_mode auto -> the bit-faithful mode on a mesh that fits one tile) is held to 1e-4 against the reference at every
+    checked step (measured: bit-identical through the free fall, <= 1e-5 after the impact).  The Newton-polar rotation
+    (rot_mode=0, what large meshes run) is exact to float rounding, and the REFERENCE is not: its 4-sweep approximate SVD
+    returns rotations with a small systematic bias that makes the free-falling rigid cube tumble, 1.8e-4 away from the
+    exact-arithmetic trajectory at step 40 (oracle f64 twin).  rot_mode=0 is therefore held to 1e-4 against the f64
+    oracle, and to "no farther from the reference than exact arithmetic is, plus 1e-4".  No tolerance above 1e-4."""
 import os
 
 import numpy as np
@@ -27,11 +30,6 @@ import meshes
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 TOL_FAITHFUL = 2e-5
-# C1 in free fall: the reference's approximate SVD (svd3_cuda.h, rsqrt-based Givens angles) drifts from exact
-# arithmetic by 1.8e-4 at step 40 (profiles/r1_noise_floor.txt, column orc64-refA); the default rotation path
-# (Newton polar, accurate to float rounding) sits on the exact side of that gap, 2.0e-4 from the reference.
-# The faithful path (rot_mode=1) is held to TOL / bit-exactness instead.
-TOL_DEFAULT_C1 = 2.5e-4
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -70,18 +68,22 @@ def test_c1_cube_faithful_mode_is_bit_exact_vs_oracle(pd, O, assets):
     assert XT[:, 1].min() > -1e-3 and np.abs(eng.download()[1]).max() < 5.0     # resting on the floor plane
 
 
-@pytest.mark.parametrize("rot_mode,reorder,tol", [(0, 1, TOL_DEFAULT_C1), (1, 1, TOL)])
-def test_c1_cube_100_steps_vs_oracle(pd, O, assets, rot_mode, reorder, tol):
+@pytest.mark.parametrize("rot_mode,reorder,f64", [(-1, 1, False), (1, 1, False), (0, 1, True)])
+def test_c1_cube_100_steps_vs_oracle(pd, O, assets, rot_mode, reorder, f64):
+    """auto (= faithful on this one-tile mesh) and faithful with Morton order: vs the float oracle (the reference's
+    arithmetic); Newton polar (rot_mode 0, exact to rounding): vs the oracle's double-precision twin."""
+    tol = TOL
     sc = pd.Scene.from_json(assets["json"], "C1 cube")
     p = _params(pd, sc, dt=1 / 60)
     osc, _ = meshes.oracle_scene(O, assets, "C1 cube")
     op = _oracle_params(O, p)
     eng = pd.PdSolver(sc, rot_mode=rot_mode, reorder=reorder)
+    assert eng.info()["rot_mode"] == (1 if rot_mode != 0 else 0)
     scale = _rest_scale(osc.X0)
     worst = 0.0
     for n in range(10):
         eng.Update(10)
-        osc.step(op, 10)
+        osc.step(op, 10, f64=f64)
         X, V, XT = eng.download()
         Xo, Vo, XTo = osc.get()
         worst = max(worst, meshes.rel_err(X, Xo, scale), meshes.rel_err(XT, XTo, scale))
@@ -316,22 +318,34 @@ def _ref_kw(p):
 def test_c1_cube_vs_reference_cuda_kernels(pd, assets):
     """The pin on the one scene where the reference is deterministic (one warp): faithful mode is
     bit-identical to the reference's CUDA build through the free fall (40 steps) and within 1e-5
-    after the impact (the reference's atomics order under contact); default mode within 2e-4."""
+    after the impact (the reference's atomics order under contact).  The engine's DEFAULT options (rot_mode auto) must
+    meet the same bar here.  The Newton-polar rotation (rot_mode=0) is checked against exact arithmetic (the oracle's
+    f64 twin, <= 1e-4) and must be no farther from the reference than exact arithmetic is (+ 1e-4): the reference's
+    approximate SVD, not the engine, is what separates the two (module docstring)."""
+    import oracle as O
     sc = pd.Scene.from_json(assets["json"], "C1 cube")
     p = _params(pd, sc, dt=1 / 60)
     rs = _ref_scene(pd, sc)
-    fa = pd.PdSolver(sc, rot_mode=1, reorder=0); de = pd.PdSolver(sc)
+    fa = pd.PdSolver(sc, rot_mode=1, reorder=0); de = pd.PdSolver(sc); nw = pd.PdSolver(sc, rot_mode=0)
+    assert de.info()["rot_mode"] == 1 and nw.info()["rot_mode"] == 0
+    o64, _ = meshes.oracle_scene(O, assets, "C1 cube")
+    op = _oracle_params(O, p)
     scale = _rest_scale(sc.arrays()["X"])
     for n in range(10):
-        fa.Update(10); de.Update(10); rs.step(10, **_ref_kw(p))
+        fa.Update(10); de.Update(10); nw.Update(10); rs.step(10, **_ref_kw(p)); o64.step(op, 10, f64=True)
         Xr, Vr, XTr = rs.get()
         Xf, Vf, XTf = fa.download()
         if n < 4:
             assert np.array_equal(Xf.view(np.uint32), Xr.view(np.uint32)) and np.array_equal(Vf.view(np.uint32), Vr.view(np.uint32)), f"step {10 * (n + 1)}"
         ef = max(meshes.rel_err(Xf, Xr, scale), meshes.rel_err(XTf, XTr, scale))
         ed = max(meshes.rel_err(a, b, scale) for a, b in zip(de.download()[::2], (Xr, XTr)))
-        print(f"C1 step {10 * (n + 1)}: faithful {ef:.2e} default {ed:.2e}")
-        assert ef <= TOL_FAITHFUL and ed <= TOL_DEFAULT_C1
+        X6, _, XT6 = o64.get()
+        en_ref = max(meshes.rel_err(a, b, scale) for a, b in zip(nw.download()[::2], (Xr, XTr)))
+        en_64 = max(meshes.rel_err(a, b, scale) for a, b in zip(nw.download()[::2], (X6, XT6)))
+        e64_ref = max(meshes.rel_err(X6, Xr, scale), meshes.rel_err(XT6, XTr, scale))
+        print(f"C1 step {10 * (n + 1)}: vs reference: faithful {ef:.2e} default(auto) {ed:.2e} newton {en_ref:.2e} exact-arithmetic(f64 oracle) {e64_ref:.2e}; newton vs f64 oracle {en_64:.2e}")
+        assert ef <= TOL_FAITHFUL and ed <= TOL_FAITHFUL
+        assert en_64 <= TOL and en_ref <= e64_ref + TOL
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="reference harness not built")
@@ -401,6 +415,81 @@ def test_rotation_and_setup_vs_reference_cuda_kernels(pd, O, assets):
     assert np.allclose(md, mdr, rtol=2e-6, atol=0)
 
 
+def _grid_scene(pd, cells, iters=100):
+    """The benchmark's own family (bench.py: C3 / C4 of SURVEY.md 8d): jittered Kuhn grid over a floor plane,
+    dt 1/60, gravity 9.8, mu 2e5, initial velocity 0.5 sin(x/7) y^."""
+    sc = pd.Scene.kuhn_grid(cells, cells, cells, 1.0, 0.05, 12345, (0.0, 10.0, 0.0), 1.0, 2e5)
+    sc.add_fixed(pd.fixed_body(pd.PD_PLANE, pos=(0, 0, 0), scale=(450, 450, 450)))
+    sc.params = pd.SolverParams(dt=1 / 60, gravity=9.8, num_iterations=iters)
+    X0 = sc.arrays()["X"]
+    V0 = np.zeros_like(X0); V0[:, 1] = 0.5 * np.sin(X0[:, 0] / 7.0)
+    return sc, X0, V0
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference harness not built")
+@pytest.mark.parametrize("cells", [12, 24])
+def test_grid_family_vs_reference_cuda_kernels(pd, cells):
+    """C3 / C4 family (what bench.py times), 100 steps (free flight with the shear velocity field, impact on the floor
+    at step ~85), default AND faithful mode against three runs of the reference's own CUDA kernels.  The bar is 1e-4
+    flat: the well-conditioned grid keeps the reference's own run-to-run spread (printed) orders of magnitude below."""
+    sc, X0, V0 = _grid_scene(pd, cells)
+    p = sc.params
+    refs = [_ref_scene(pd, sc) for _ in range(3)]
+    engs = {"default": pd.PdSolver(sc), "faithful": pd.PdSolver(sc, rot_mode=1, reorder=0)}
+    assert engs["default"].info()["rot_mode"] == 0
+    for e in engs.values():
+        e.upload(V=V0)
+    for r in refs:
+        r.set(V=V0)
+    scale = _rest_scale(X0)
+    worst = {k: 0.0 for k in engs}; worst_spread = 0.0
+    for n in range(4):
+        for e in engs.values():
+            e.Update(25)
+        for r in refs:
+            r.step(25, **_ref_kw(p))
+        got = [r.get() for r in refs]
+        dist = lambda g, h: max(meshes.rel_err(g[0], h[0], scale), meshes.rel_err(g[2], h[2], scale))
+        spread = max(dist(got[i], got[j]) for i in range(3) for j in range(i))
+        worst_spread = max(worst_spread, spread)
+        line = f"grid{cells} step {25 * (n + 1)}: reference vs reference {spread:.2e}"
+        for k, e in engs.items():
+            err = min(dist(e.download(), g) for g in got)
+            worst[k] = max(worst[k], err)
+            line += f"; {k} vs reference {err:.2e}"
+        print(line + f"; min y {got[0][2][:, 1].min():.3f}")
+    assert got[0][2][:, 1].min() < 0.01                 # the run reached the floor
+    assert worst["default"] <= TOL and worst["faithful"] <= TOL, (worst, worst_spread)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference harness not built")
+def test_grid_family_pcg_vs_reference_solver(pd):
+    """Config 3 as specified (PD + Jacobi-PCG global step) on the grid family with the velocity field, default and
+    faithful local step, against the reference's own PCGJacobiSolver<float> in PdSolver's direct branch
+    (oracle/ref_solvers.cu), 20 steps of 10 outer iterations, free flight."""
+    import ref
+    if not ref.solvers_available():
+        pytest.skip("reference solver harness not built")
+    cells = 12
+    sc = pd.Scene.kuhn_grid(cells, cells, cells, 1.0, 0.05, 12345, (0.0, 40.0, 0.0), 1.0, 2e5)      # no fixed body in that harness
+    kw = dict(dt=1 / 60, gravity=9.8, num_iterations=10, tol=1e-6)
+    sc.params = pd.SolverParams(global_solver=2, pcg_max_iter=2000, pcg_tol=1e-5, **kw)
+    a = sc.arrays()
+    V0 = np.zeros_like(a["X"]); V0[:, 1] = 0.5 * np.sin(a["X"][:, 0] / 7.0)
+    scale = _rest_scale(a["X"])
+    for name, ekw in (("default", {}), ("faithful", dict(rot_mode=1, reorder=0))):
+        eng = pd.PdSolver(sc, **ekw)
+        eng.upload(V=V0)
+        rs = ref.RefSolverScene(a["X"], a["Tet"], a["mass"], a["mu"], 2)
+        rs.set(V=V0)
+        worst = 0.0
+        for s in range(4):
+            eng.Update(5); rs.step(5, **kw)
+            worst = max(worst, meshes.rel_err(eng.download()[0], rs.get()[0], scale))
+        print(f"grid{cells} PD + PCG-Jacobi, {name}: worst rel err vs the reference's PCGJacobiSolver over 20 steps {worst:.2e}")
+        assert worst <= TOL
+
+
 def _fixed_arrays(pd, fixed):
     planes, spheres, cyls = [], [], []
     for f in fixed:
@@ -427,7 +516,7 @@ def test_golden_fixtures(pd, assets):
     sc = pd.Scene.from_json(assets["json"], "C1 cube")
     _params(pd, sc, dt=1 / 60)
     scale = _rest_scale(sc.arrays()["X"])
-    for kw, tol in ((dict(rot_mode=1, reorder=0), TOL_FAITHFUL), (dict(), TOL_DEFAULT_C1)):
+    for kw, tol in ((dict(rot_mode=1, reorder=0), TOL_FAITHFUL), (dict(), TOL_FAITHFUL)):
         eng = pd.PdSolver(sc, **kw)
         eng.Update(int(z["C1_steps"]))
         X, V, XT = eng.download()

@@ -241,12 +241,12 @@ def test_live_mu_edit_vs_oracle(pd, O):
     assert e1 <= 1e-4 and e2 <= 1e-4, (e1, e2)
 
 
-@pytest.mark.skipif(os.environ.get("PD_EXPERIMENTAL_GPU_TESTS") != "1", reason="experiment, not yet run on a GPU: set PD_EXPERIMENTAL_GPU_TESTS=1 (scripts/gpu_body_ab.sh)")
-def test_per_body_kernel_experiment(pd, O, assets, monkeypatch):
-    """PD_BODY_KERNEL=1 (csrc/pd_body_kernel.cuh): one CTA per body, one launch per step.  Faithful mode bit-exact vs the oracle
-    on the two-body house + sphere context (as the host emulation of the kernel is, tests/test_kernel_emulation.py); default
-    mode within 1e-4 of the tile path on a batch of well-conditioned grids."""
-    monkeypatch.setenv("PD_BODY_KERNEL", "1")
+def test_per_body_kernel(pd, O, assets, monkeypatch):
+    """csrc/pd_body_kernel.cuh, the default for scenes whose connected components all fit one CTA: one CTA per body, one
+    launch per step.  Faithful mode bit-exact vs the oracle on the two-body house + sphere context (as the host emulation of
+    the kernel is, tests/test_kernel_emulation.py); default mode within 1e-4 of the tile path (body_kernel=0) on a batch of
+    well-conditioned grids; bodies are found by connectivity, whatever the scene calls a body."""
+    monkeypatch.delenv("PD_BODY_KERNEL", raising=False)
     sc = pd.Scene.from_json(assets["json"], "C5 house&sphere")
     p = sc.params
     p["num_iterations"] = 25
@@ -266,13 +266,14 @@ def test_per_body_kernel_experiment(pd, O, assets, monkeypatch):
         g.add_fixed(pd.fixed_body(pd.PD_PLANE, pos=(0, 0, 0), scale=(450, 450, 450)))
         grids.append(g)
     merged = pd.Scene.merge(grids)
+    am = merged.arrays()
+    merged = pd.Scene.from_arrays(am["X"], am["Tet"], am["mass"], am["mu"], fixed=am["fixed"], params=merged.params)   # ONE named body, three components
     body = pd.PdSolver(merged)
-    monkeypatch.setenv("PD_BODY_KERNEL", "0")
-    tiles = pd.PdSolver(merged)
+    tiles = pd.PdSolver(merged, body_kernel=0)
     X0 = merged.arrays()["X"]
     V0 = np.zeros_like(X0); V0[:, 1] = 0.3 * np.sin(X0[:, 0])
     body.upload(V=V0); tiles.upload(V=V0)
     body.Update(6); tiles.Update(6)
     err = meshes.rel_err(body.download()[0], tiles.download()[0])
     print(f"per-body kernel vs tile path: {err:.2e}")
-    assert err <= 1e-4 and body.GetPerformanceData()[1].kernel_launches == 6
+    assert err <= 1e-4 and body.GetPerformanceData()[1].kernel_launches == 6 and tiles.GetPerformanceData()[1].kernel_launches == 6 * (2 + 2 * 30)
