@@ -7,7 +7,7 @@ section 7 quotes 707 per tile for grid139, which also contains the asynchronous 
 are the prediction the experiments of DESIGN.md section 9 are to be measured against.
 
     python scripts/wavefront_model.py [cells=40]                         # default layout, also evaluated with pads predicated off
-    PD_B200_LIB=.../variants/libpd_planes.so python scripts/wavefront_model.py   # -DPD_H_PLANES=1 layout"""
+"""
 import importlib
 import os
 import sys
@@ -17,7 +17,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pd = importlib.import_module("soft-body-simulation-cuda_b200")
-PLANES = "planes" in os.path.basename(pd.LIB_PATH)
+PLANES = False      # (the x|y|z-plane H scratch was measured on a B200 in round 2 and removed: no gain, profiles/r2_ab_planes_pred.txt)
 ZERO_OFF = 4 * 256 * (4 if PLANES else 16)
 
 
@@ -73,7 +73,7 @@ if __name__ == "__main__":
     m, nt = model(L, sample=max(1, L.num_tiles // 400))
     shared = m["positions_lds"] + m["h_sts"] + m["rows_lds"] + m["gather_lds"] + m["stage_ldgsts_ideal"] + m["partc_landing"]
     glob = m["records_ldg"] + m["slots_stg"] + m["misc_ldg"]
-    name = "PD_H_PLANES layout" if PLANES else "default layout"
+    name = "default layout"
     print(f"{name}, grid {n}^3, {nt} tiles sampled: wavefronts per tile")
     for k, v in m.items():
         print(f"  {k:22s} {v:8.1f}")

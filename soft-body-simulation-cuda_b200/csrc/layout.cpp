@@ -94,9 +94,8 @@ static inline size_t rup(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // Deterministic: edges in (tet, corner) order, smallest free colours, alternating-path recolouring.
 static void color_tile(uint32_t nTets, uint32_t nRows, const uint32_t* epos, uint8_t (*col)[4])
 {
-    // NC colours; store group of edge (tl, k) and load group of its incidence entry at position p = (row * 32 + lane) * 2 + half:
-    //   default     NC = 8 : 8 consecutive tets x corner (one quarter-warp STS.128) / (row, half, lane / 8)
-    //   PD_H_PLANES NC = 32: 32 consecutive tets x corner (one warp STS.32)        / (row, half)
+    // NC = 8 colours; store group of edge (tl, k) and load group of its incidence entry at position p = (row * 32 + lane) * 2 + half:
+    //   8 consecutive tets x corner (one quarter-warp STS.128) / (row, half, lane / 8)
     constexpr uint32_t NC = TILE_HCOLOURS, NL = 4u * (uint32_t)TILE_T / NC, LG = 32u / NC;      // left nodes; load groups per (row, half)
     const uint32_t nE = 4u * nTets, nR = nRows * 2u * LG;
     std::vector<int16_t> atL((size_t)NL * NC, -1), atR((size_t)nR * NC, -1);
@@ -287,7 +286,7 @@ static void build_tiles(int nV, int nT, const uint32_t* tet, const float* DmInv,
         color_tile(nTets, nRows, epos.data(), col);
         // pads point at the zero slot of a column no real entry of their load group uses
         {
-            constexpr uint32_t NC = TILE_HCOLOURS, LG = 32u / NC, ESZ = PD_H_PLANES ? 4u : 16u;      // load groups per (row, half); entry bytes
+            constexpr uint32_t NC = TILE_HCOLOURS, LG = 32u / NC, ESZ = 16u;      // load groups per (row, half); entry bytes
             const size_t nLg = (size_t)nRows * 2 * LG;     // load group = (row, half, lane / NC)
             std::vector<uint32_t> used(nLg, 0);
             for (uint32_t tl = 0; tl < nTets; ++tl)
@@ -488,6 +487,90 @@ void build_system_matrix(const Layout& L, const float*, const float* DmInv, cons
         }
     }
     A.rowPtr[nV] = (int)A.col.size();
+}
+
+void nested_dissection_order(const CsrMatrix& A, const float* xyz, std::vector<int>& perm)
+{
+    const int n = A.n;
+    perm.clear(); perm.reserve((size_t)n);
+    if (!xyz) { for (int i = 0; i < n; ++i) perm.push_back(i); return; }
+    // side[v]: id of the sub-domain v currently belongs to (-1 once numbered / moved to a separator)
+    std::vector<int> side((size_t)n, 0), work((size_t)n);
+    for (int i = 0; i < n; ++i) work[(size_t)i] = i;
+    struct Job { int lo, hi, id; bool emit; };          // work[lo, hi) is a sub-domain, or (emit) a separator to be numbered now
+    std::vector<Job> stack{{0, n, 0, false}};
+    int nextId = 1;
+    std::vector<int> sepL, sepR;
+    while (!stack.empty()) {
+        const Job j = stack.back(); stack.pop_back();
+        const int m = j.hi - j.lo;
+        if (j.emit || m <= 48) {
+            if (!j.emit) std::sort(work.begin() + j.lo, work.begin() + j.hi);      // leaves keep the matrix order
+            for (int k = j.lo; k < j.hi; ++k) { perm.push_back(work[(size_t)k]); side[(size_t)work[(size_t)k]] = -1; }
+            continue;
+        }
+        float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+        for (int k = j.lo; k < j.hi; ++k)
+            for (int c = 0; c < 3; ++c) { const float x = xyz[3 * (size_t)work[(size_t)k] + c]; mn[c] = std::min(mn[c], x); mx[c] = std::max(mx[c], x); }
+        int ax = 0;
+        for (int c = 1; c < 3; ++c) if (mx[c] - mn[c] > mx[ax] - mn[ax]) ax = c;
+        const int mid = j.lo + m / 2;
+        std::nth_element(work.begin() + j.lo, work.begin() + mid, work.begin() + j.hi, [&](int a, int b) {
+            const float xa = xyz[3 * (size_t)a + ax], xb = xyz[3 * (size_t)b + ax];
+            return xa < xb || (xa == xb && a < b);
+        });
+        const int idL = nextId++, idR = nextId++;
+        for (int k = j.lo; k < mid; ++k) side[(size_t)work[(size_t)k]] = idL;
+        for (int k = mid; k < j.hi; ++k) side[(size_t)work[(size_t)k]] = idR;
+        // the two boundary layers; the smaller one is the separator
+        sepL.clear(); sepR.clear();
+        for (int k = j.lo; k < j.hi; ++k) {
+            const int v = work[(size_t)k], other = (k < mid) ? idR : idL;
+            for (int e = A.rowPtr[v]; e < A.rowPtr[v + 1]; ++e)
+                if (side[(size_t)A.col[e]] == other) { (k < mid ? sepL : sepR).push_back(v); break; }
+        }
+        const bool takeL = sepL.size() <= sepR.size();
+        const std::vector<int>& sep = takeL ? sepL : sepR;
+        if (sep.empty()) {          // disconnected halves: no separator at all
+            stack.push_back({mid, j.hi, idR, false}); stack.push_back({j.lo, mid, idL, false});
+            continue;
+        }
+        const int idS = nextId++;
+        for (int v : sep) side[(size_t)v] = idS;
+        // regroup work[lo, hi) as [left | right | separator]
+        std::vector<int> tmp(work.begin() + j.lo, work.begin() + j.hi);
+        int o = j.lo;
+        for (int v : tmp) if (side[(size_t)v] == idL) work[(size_t)o++] = v;
+        const int endL = o;
+        for (int v : tmp) if (side[(size_t)v] == idR) work[(size_t)o++] = v;
+        const int endR = o;
+        for (int v : tmp) if (side[(size_t)v] == idS) work[(size_t)o++] = v;
+        // numbered in the order left, right, separator: the stack pops in reverse
+        stack.push_back({endR, j.hi, idS, true});
+        stack.push_back({endL, endR, idR, false});
+        stack.push_back({j.lo, endL, idL, false});
+    }
+    if ((int)perm.size() != n) throw std::runtime_error("nested dissection: internal error (not a permutation)");
+}
+
+void permute_symmetric(const CsrMatrix& A, const std::vector<int>& perm, CsrMatrix& B)
+{
+    const int n = A.n;
+    std::vector<int> inv((size_t)n);
+    for (int i = 0; i < n; ++i) inv[(size_t)perm[(size_t)i]] = i;
+    B = CsrMatrix(); B.n = n;
+    B.rowPtr.assign((size_t)n + 1, 0);
+    for (int i = 0; i < n; ++i) B.rowPtr[(size_t)i + 1] = B.rowPtr[(size_t)i] + (A.rowPtr[perm[(size_t)i] + 1] - A.rowPtr[perm[(size_t)i]]);
+    B.col.resize(A.col.size()); B.val.resize(A.val.size());
+    std::vector<std::pair<int, float>> row;
+    for (int i = 0; i < n; ++i) {
+        const int o = perm[(size_t)i];
+        row.clear();
+        for (int e = A.rowPtr[o]; e < A.rowPtr[o + 1]; ++e) row.emplace_back(inv[(size_t)A.col[e]], A.val[e]);
+        std::sort(row.begin(), row.end(), [](const std::pair<int, float>& a, const std::pair<int, float>& b) { return a.first < b.first; });
+        int p = B.rowPtr[(size_t)i];
+        for (const auto& cv : row) { B.col[(size_t)p] = cv.first; B.val[(size_t)p] = cv.second; ++p; }
+    }
 }
 
 void cholesky_factor(const CsrMatrix& A, CholFactor& F)

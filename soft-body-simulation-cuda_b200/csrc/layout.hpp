@@ -20,27 +20,10 @@ constexpr int TILE_LPV = 32 / TILE_GROUP;             // lanes per vertex in pha
 constexpr int TILE_NGROUPS = TILE_NLMAX / TILE_GROUP;   // warp w of the local kernel sums groups w (and w + 8)
 static_assert(TILE_GROUP == 32 || TILE_GROUP == 16, "phase C group size");
 constexpr int TILE_ROWSMAX = 56;  // max incidence rows per tile (a tile is shrunk beyond)
-// EXPERIMENT (PD_DEFS=-DPD_H_PLANES=1, variant library only; DESIGN.md section 7 "What actually bounds k_local"): the H
-// scratch as three 4-byte planes (x | y | z) instead of float4 entries.  The local kernel is bound by the shared-memory
-// data pipe and a quarter of the H bytes it moves are the unused w lane: 12 x STS.32 / 3 x LDS.32 per entry are 3
-// wavefronts per 32 entries instead of 4.  An entry is then an INDEX corner * 256 + (tet & ~31) + colour with a 32-colouring
-// over warp-wide store / load groups (bank = index mod 32 in every plane), followed by 32 zero entries.
-#ifndef PD_H_PLANES
-#define PD_H_PLANES 0
-#endif
-#if PD_H_PLANES
-static_assert(PD_TILE_GROUP == 32, "the plane layout of the H scratch is written for 32-vertex groups");
-constexpr uint32_t TILE_HCOLOURS = 32;
-constexpr uint32_t TILE_HPLANE = 4u * (4u * TILE_T + TILE_HCOLOURS);   // bytes of one plane: 1024 entries + 32 zero entries (33 x 128 B: every plane starts at bank 0)
-constexpr uint32_t TILE_HSTRIDE = TILE_T * 4;            // bytes between the corner blocks inside a plane
-constexpr uint32_t TILE_ZERO_OFF = 4u * TILE_HSTRIDE;    // byte offset (inside a plane) of the first all-zero entry
-constexpr uint32_t TILE_HS_BYTES = 3u * TILE_HPLANE;
-#else
 constexpr uint32_t TILE_HCOLOURS = 8;
 constexpr uint32_t TILE_HSTRIDE = TILE_T * 16;           // bytes between corner planes of the per-tile H scratch
 constexpr uint32_t TILE_ZERO_OFF = 4u * TILE_HSTRIDE;    // byte offset of the all-zero float4 padding entries point at
 constexpr uint32_t TILE_HS_BYTES = TILE_ZERO_OFF + 128u; // four corner planes + eight zero slots, one per column
-#endif
 constexpr uint32_t TILE_OWNER_BIT = 0x80000000u;         // vlist flag: this slot is the vertex's first (owner) slot
 
 // One packed tile record = two parts, each moved to shared memory by ONE
@@ -85,16 +68,9 @@ constexpr uint32_t TILE_OFF_TETS = 96u;
 inline uint32_t tile_ab_bytes(uint32_t nTets) { return TILE_OFF_TETS + 48u * nTets; }
 // byte offset (inside part AB) of word j (0..11) of the record of tile-local tet tl in a tile of nTets tets
 inline size_t tile_tet_word(uint32_t nTets, uint32_t tl, uint32_t j) { return TILE_OFF_TETS + 16u * ((size_t)tl + (size_t)nTets * (j / 4u)) + 4u * (j % 4u); }
-#if PD_H_PLANES
-inline uint32_t tile_h_offset(uint32_t tet, uint32_t corner, uint32_t column) { return corner * TILE_HSTRIDE + ((tet & ~31u) + column) * 4u; }
-// 5-bit colour: low four bits in bits 12..15 of the corner word, the fifth in bit 0 (bits 4..11 stay the staging slot)
-inline uint32_t tile_corner_half(uint32_t localVertex, uint32_t column) { return (localVertex << 4) | ((column & 15u) << 12) | (column >> 4); }
-inline uint32_t tile_corner_colour(uint32_t half) { return ((half >> 12) & 15u) | ((half & 1u) << 4); }
-#else
 inline uint32_t tile_h_offset(uint32_t tet, uint32_t corner, uint32_t column) { return corner * TILE_HSTRIDE + ((tet & ~7u) | column) * 16u; }
 inline uint32_t tile_corner_half(uint32_t localVertex, uint32_t column) { return (localVertex << 4) | (column << 12); }
 inline uint32_t tile_corner_colour(uint32_t half) { return (half >> 12) & 7u; }
-#endif
 // TMA landing buffers (multiples of 128 B)
 constexpr uint32_t TILE_ABMAX = ((TILE_OFF_TETS + 48u * TILE_T) + 127u) & ~127u;
 constexpr uint32_t TILE_CMAX = 128u * TILE_ROWSMAX;
@@ -165,6 +141,15 @@ struct CholFactor {
     std::vector<float> lVal, uVal;
 };
 void cholesky_factor(const CsrMatrix& A, CholFactor& F);
+// Fill-reducing ordering for the factorisation (the reference orders with AMD inside cusolverSpXcsrcholAnalysis /
+// Eigen::SimplicialCholesky, cholesky.cu:72-131, pdSolver.cu:103): GEOMETRIC nested dissection -- the vertex set is cut at
+// the median of its longest coordinate axis, the vertices of the smaller boundary layer between the halves become the
+// separator and are numbered LAST, recursively (leaves of <= 48 vertices keep their order).  xyz: n x 3 rest positions of
+// the matrix's rows.  perm[new] = old.  Deterministic; a mesh graph needs nothing cleverer (nnz(L) on a 24^3-cell grid:
+// 11.9 M in Morton order, 2.4 M here).
+void nested_dissection_order(const CsrMatrix& A, const float* xyz, std::vector<int>& perm);
+// B = P A P^T for perm[new] = old (rows of B sorted by column)
+void permute_symmetric(const CsrMatrix& A, const std::vector<int>& perm, CsrMatrix& B);
 
 // EXPERIMENT (PD_BODY_KERNEL=1, pd_body_kernel.cuh): per-body data of a scene made of many small soft bodies, one CTA per body.
 struct BodyDesc {           // device-visible POD, one per body

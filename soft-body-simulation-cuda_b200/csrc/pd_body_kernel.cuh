@@ -30,8 +30,20 @@ k_body_step(const BodyDesc* __restrict__ bodies, const uint32_t* __restrict__ bv
             const uint32_t* __restrict__ bincPtr, const uint16_t* __restrict__ binc, const float* __restrict__ bmd,
             uint32_t nVmax, uint32_t nTmax, float4* __restrict__ X, float4* __restrict__ V, float4* __restrict__ XT,
             const float* __restrict__ mass, const float* __restrict__ dbc, const float4* __restrict__ dbcx,
-            float dt, float dt2Prepared, float gravity, int iterations, float rho, float wdbc, DevFixedBodies fb, float muT, float muN)
+            float dt, float dt2Prepared, float gravity, int iterations, float rho, float wdbc, DevFixedBodies fb, float muT, float muN,
+            unsigned long long* __restrict__ perfNs)
 {
+    // perfNs (perf mode, else null): nanoseconds body 0 spent in {local step, global step, end of step}, added up over launches
+    // -- the split PdSolver reports through GetPerformanceData (pdSolver.cu:26,165-203,228-231)
+    const bool timed = perfNs != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    unsigned long long tLocal = 0, tGlobal = 0, tMark = 0;
+    auto now = [&]() -> unsigned long long {
+#ifdef PD_HOST_EMU
+        return 0ull;
+#else
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+#endif
+    };
     PD_DYN_SMEM(smem);
     float4* const qb = reinterpret_cast<float4*>(smem);          // iterate buffer k at qb + k * nVmax
     float4* b0s = reinterpret_cast<float4*>(smem) + 3 * nVmax;
@@ -68,6 +80,7 @@ k_body_step(const BodyDesc* __restrict__ bodies, const uint32_t* __restrict__ bv
 
     const uint8_t* rec = brec + 16ull * bd.recOff16;
     float omega = 1.0f;
+    if (timed) tMark = now();
     for (int i = 0; i < iterations; ++i) {
         const float4* cur = qb + (uint32_t)(i % 3) * nVmax;
         const float4* prev = qb + (uint32_t)((i + 2) % 3) * nVmax;
@@ -84,6 +97,7 @@ k_body_step(const BodyDesc* __restrict__ bodies, const uint32_t* __restrict__ bv
             Hs[t] = h0; Hs[nTmax + t] = h1; Hs[2 * nTmax + t] = h2; Hs[3 * nTmax + t] = h3;
         }
         __syncthreads();
+        if (timed) { const unsigned long long t = now(); tLocal += t - tMark; tMark = t; }
         // omega recurrence in float, pdSolver.cu:196-198 (the same operations Engine::enqueueIteration performs on the host)
         if (i <= 10) omega = 1.0f;
         else if (i == 11) omega = __fdiv_rn(2.0f, __fsub_rn(2.0f, __fmul_rn(rho, rho)));
@@ -129,6 +143,7 @@ k_body_step(const BodyDesc* __restrict__ bodies, const uint32_t* __restrict__ bv
             next[l] = make_float4(nx, ny, nz, 0.f);
         }
         __syncthreads();
+        if (timed) { const unsigned long long t = now(); tGlobal += t - tMark; tMark = t; }
     }
     // ---- end of step: updateVelPos, X <- XTilde, fixed bodies (k_finish<false>)
     const float dtInv = __fdiv_rn(1.0f, dt);
@@ -136,6 +151,10 @@ k_body_step(const BodyDesc* __restrict__ bodies, const uint32_t* __restrict__ bv
     for (uint32_t l = tid; l < bd.nV; l += nth) {
         const uint32_t v = bverts[bd.v0 + l];
         finish_vertex(qf[l], XT[v], dtInv, false, fb, muT, muN, &X[v], &XT[v], &V[v]);
+    }
+    if (timed) {
+        __syncthreads();
+        perfNs[0] += tLocal; perfNs[1] += tGlobal; perfNs[2] += now() - tMark;
     }
 }
 

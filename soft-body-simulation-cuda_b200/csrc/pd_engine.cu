@@ -65,6 +65,7 @@ struct Engine::Impl {
     // EXPERIMENT PD_BODY_KERNEL=1 (pd_body_kernel.cuh): one CTA per small body, one launch per step
     BodyDesc* bBodies = nullptr; uint32_t* bVerts = nullptr; uint8_t* bRec = nullptr; uint32_t* bIncPtr = nullptr; uint16_t* bInc = nullptr; float* bMd = nullptr;
     int nBodies = 0; uint32_t bNVmax = 0, bNTmax = 0; size_t bSmem = 0;
+    unsigned long long* bPerfNs = nullptr;
     DragArgs drag(const float t[3], int numDBC) const { return DragArgs{more, offX, dbcx, t[0], t[1], t[2], numDBC > 0 ? 1 : 0}; }
     uint32_t* oldOfNew = nullptr;
     float* stage3 = nullptr;          // 3 x (3 nV) floats, AoS staging for import/export
@@ -531,18 +532,30 @@ void Engine::step(int nSteps)
         perfc_.kernelLaunches += (long long)nSteps * (4 + 3 * params_.numIterations);
         return;
     }
-    if (bodyKernel_ && !perf_ && !dragActive_) {      // EXPERIMENT: one CTA per body, the whole step in one launch (pd_body_kernel.cuh)
+    if (bodyKernel_ && !dragActive_) {      // small bodies: one CTA per body, the whole step in one launch (pd_body_kernel.cuh)
         const SolverParams& p = params_;
         const float dtInv = 1.0f / p.dt, wdbc = 1e6f * (dtInv * dtInv);
+        unsigned long long* perfNs = nullptr;
+        if (perf_) {       // the four counters come from body 0's own clock (nothing else can split a single launch)
+            if (!d.bPerfNs) { d.bPerfNs = dalloc<unsigned long long>(4); CUDA_CHECK(cudaMemsetAsync(d.bPerfNs, 0, 32, stream_)); }
+            perfNs = d.bPerfNs;
+        }
         for (int s = 0; s < nSteps; ++s) {
             if (opt_.rotMode == 1)
                 k_body_step<1><<<d.nBodies, 512, d.bSmem, stream_>>>(d.bBodies, d.bVerts, d.bRec, d.bIncPtr, d.bInc, d.bMd, d.bNVmax, d.bNTmax, d.X, d.V, d.XT, d.mass,
-                                                                     d.dbc, d.dbcx, p.dt, dt2Prepared_, p.gravity, p.numIterations, p.rho, wdbc, d.fb, p.muT, p.muN);
+                                                                     d.dbc, d.dbcx, p.dt, dt2Prepared_, p.gravity, p.numIterations, p.rho, wdbc, d.fb, p.muT, p.muN, perfNs);
             else
                 k_body_step<0><<<d.nBodies, 512, d.bSmem, stream_>>>(d.bBodies, d.bVerts, d.bRec, d.bIncPtr, d.bInc, d.bMd, d.bNVmax, d.bNTmax, d.X, d.V, d.XT, d.mass,
-                                                                     d.dbc, d.dbcx, p.dt, dt2Prepared_, p.gravity, p.numIterations, p.rho, wdbc, d.fb, p.muT, p.muN);
+                                                                     d.dbc, d.dbcx, p.dt, dt2Prepared_, p.gravity, p.numIterations, p.rho, wdbc, d.fb, p.muT, p.muN, perfNs);
         }
         CUDA_CHECK(cudaGetLastError());
+        if (perf_) {
+            unsigned long long ns[4];
+            CUDA_CHECK(cudaMemcpyAsync(ns, d.bPerfNs, 32, cudaMemcpyDeviceToHost, stream_));
+            CUDA_CHECK(cudaMemsetAsync(d.bPerfNs, 0, 32, stream_));
+            CUDA_CHECK(cudaStreamSynchronize(stream_));
+            perfc_.localStep += (float)(ns[0] * 1e-6); perfc_.globalStep += (float)(ns[1] * 1e-6); perfc_.collisionFixed += (float)(ns[2] * 1e-6);
+        }
         perfc_.steps += nSteps;
         perfc_.pdIterations += (long long)nSteps * p.numIterations;
         perfc_.kernelLaunches += nSteps;

@@ -15,10 +15,6 @@
 #include "layout.hpp"
 #include "rotation.cuh"
 
-#ifndef PD_PHASEC_PRED
-#define PD_PHASEC_PRED 0
-#endif
-
 namespace pdb200 {
 
 // ------------------------------------------------------------------ device-side fixed bodies
@@ -281,8 +277,7 @@ __global__ void k_predict(int nV, const float4* __restrict__ X, const float4* __
 // reference's glm expressions (see oracle/pd_oracle.c header), so that with ROT_MODE 1 every tet
 // contribution is bit-identical to the reference kernel's.
 constexpr uint32_t LOCAL_QS_BYTES = 16u * TILE_NLMAX;
-constexpr uint32_t LOCAL_HS_BYTES = TILE_HS_BYTES;             // default: four corner planes of float4 + eight zero slots, one per column;
-                                                               // PD_H_PLANES: x | y | z planes of 1024 + 32 floats (layout.hpp)
+constexpr uint32_t LOCAL_HS_BYTES = TILE_HS_BYTES;             // four corner planes of float4 + eight zero slots, one per column
 constexpr uint32_t LOCAL_OFF_QS = 0u;
 constexpr uint32_t LOCAL_OFF_HS = LOCAL_OFF_QS + 2u * LOCAL_QS_BYTES;
 constexpr uint32_t LOCAL_OFF_C = LOCAL_OFF_HS + 2u * LOCAL_HS_BYTES;
@@ -316,26 +311,13 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes)
 // one H-scratch entry (x, y, z) at byte offset `off` of the tile's scratch Hb
 __device__ __forceinline__ float4 h_load(const uint8_t* Hb, uint32_t off)
 {
-#if PD_H_PLANES
-    return make_float4(*reinterpret_cast<const float*>(Hb + off), *reinterpret_cast<const float*>(Hb + TILE_HPLANE + off),
-                       *reinterpret_cast<const float*>(Hb + 2u * TILE_HPLANE + off), 0.f);
-#else
     return *reinterpret_cast<const float4*>(Hb + off);
-#endif
 }
-// ... and the store of phase B: Hblk = the scratch position of the thread's store group (default: the 128-byte line of its
-// quarter-warp in corner plane 0; PD_H_PLANES: entry (tid & ~31) of corner block 0 in the x plane), half = the corner word
+// ... and the store of phase B: Hblk = the 128-byte line of the thread's quarter-warp in corner plane 0, half = the corner word
 __device__ __forceinline__ void h_store(uint8_t* Hblk, uint32_t corner, uint32_t half, const float4 h)
 {
-#if PD_H_PLANES
-    uint8_t* p = Hblk + corner * TILE_HSTRIDE + 4u * (((half >> 12) & 15u) | ((half & 1u) << 4));      // layout.hpp:tile_corner_colour
-    *reinterpret_cast<float*>(p) = h.x;
-    *reinterpret_cast<float*>(p + TILE_HPLANE) = h.y;
-    *reinterpret_cast<float*>(p + 2u * TILE_HPLANE) = h.z;
-#else
     // conflict-free columns from the layout's 8-colouring (layout.cpp:color_tile): col * 16 = (half >> 8) & 0x70
     *reinterpret_cast<float4*>(Hblk + corner * TILE_HSTRIDE + ((half >> 8) & 0x70u)) = h;
-#endif
 }
 
 // phase C of one vertex group of a tile, by one warp: Cb = the tile's incidence rows, Hb = its H scratch, gw = the
@@ -385,21 +367,10 @@ __device__ __forceinline__ void local_phase_c(const uint8_t* Cb, const uint8_t* 
         uint32_t e0 = row[0], e1 = (1u < nR) ? row[32] : ZZ;
 #pragma unroll 1
         for (uint32_t r = 0; r < nR; r += 2) {
-#if PD_PHASEC_PRED
-            // EXPERIMENT (-DPD_PHASEC_PRED=1, variant library only): a pad is not loaded at all.  The lists of a group are
-            // sorted by length, so in its last rows whole quarter-warps hold nothing but pads, and a quarter-warp without an
-            // active lane costs the shared-memory pipe no wavefront (the rows are 70 % full on the grid)
-            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 h0 = ((e0 & 0xffffu) < TILE_ZERO_OFF) ? h_load(Hb, e0 & 0xffffu) : zero4;
-            const float4 h1 = ((e0 >> 16) < TILE_ZERO_OFF) ? h_load(Hb, e0 >> 16) : zero4;
-            const float4 h2 = ((e1 & 0xffffu) < TILE_ZERO_OFF) ? h_load(Hb, e1 & 0xffffu) : zero4;
-            const float4 h3 = ((e1 >> 16) < TILE_ZERO_OFF) ? h_load(Hb, e1 >> 16) : zero4;
-#else
             const float4 h0 = h_load(Hb, e0 & 0xffffu);
             const float4 h1 = h_load(Hb, e0 >> 16);
             const float4 h2 = h_load(Hb, e1 & 0xffffu);
             const float4 h3 = h_load(Hb, e1 >> 16);
-#endif
             const uint32_t* nx = row + 32u * (r + 2u);
             e0 = (r + 2u < nR) ? nx[0] : ZZ; e1 = (r + 3u < nR) ? nx[32] : ZZ;
             axy = f2add(axy, make_float2(h0.x, h0.y)); az = __fadd_rn(az, h0.z);
@@ -530,12 +501,7 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
         fence_barrier_init();
         fence_proxy_async();
     }
-#if PD_H_PLANES
-    if (tid < 192)      // 32 zero entries behind each of the three planes of both scratch buffers
-        *reinterpret_cast<float*>(smem + LOCAL_OFF_HS + (tid / 96) * LOCAL_HS_BYTES + ((tid % 96) / 32) * TILE_HPLANE + TILE_ZERO_OFF + 4 * (tid % 32)) = 0.f;
-#else
     if (tid < 16) *reinterpret_cast<float4*>(smem + LOCAL_OFF_HS + (tid >> 3) * LOCAL_HS_BYTES + TILE_ZERO_OFF + 16 * (tid & 7)) = make_float4(0.f, 0.f, 0.f, 0.f);
-#endif
     __syncthreads();
     // multi-GPU: the rank's interior tiles come first; the neighbours' ghost positions are needed -- and waited
     // for -- only before the position gather of the first boundary tile, so the exchange hides behind the interior
@@ -650,7 +616,7 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
         // ---- phase B of tile it
         if ((uint32_t)tid < (mwA >> 18))
             local_phase_b<ROT_MODE, JACOBI>(r0, r1, r2, smem + LOCAL_OFF_QS + b * LOCAL_QS_BYTES,
-                                            smem + LOCAL_OFF_HS + b * LOCAL_HS_BYTES + (PD_H_PLANES ? 4 : 16) * (tid & ~(PD_H_PLANES ? 31 : 7)));
+                                            smem + LOCAL_OFF_HS + b * LOCAL_HS_BYTES + 16 * (tid & ~7));
         PD_TICK(0)
         // the record registers are free: fetch the next tile's record (consumed after this tile's phase C)
         if (it + 1 < nIt) load_rec(off16N, ntvN & 0xffffu, r0, r1, r2);

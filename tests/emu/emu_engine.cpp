@@ -147,7 +147,7 @@ void rank_step_concurrent(Emu& e, Rank& r, float dt, float gravity, float rho, f
 
 extern "C" {
 
-const char* emu_variant(void) { return PD_H_PLANES ? "planes" : (PD_PHASEC_PRED ? "pred" : "default"); }
+const char* emu_variant(void) { return "default"; }
 
 // planes: 6 floats each (p0, up); spheres: 4 (c, r); cylinders: 7 (c, axis, r) -- the arrays the collision kernels consume
 void* emu_create(int nV, int nT, const float* X, const uint32_t* Tet, const float* mass, const float* mu, const float* DBC,
@@ -281,7 +281,7 @@ int emu_step(void* h, float dt, float gravity, float rho, float muN, float muT, 
                 pd_emu::launch((unsigned)e.bb.bodies.size(), 512u, smem, kernel, (const BodyDesc*)e.bb.bodies.data(), (const uint32_t*)e.bb.verts.data(),
                                (const uint8_t*)e.bb.rec.data(), (const uint32_t*)e.bb.incPtr.data(), (const uint16_t*)e.bb.inc.data(), (const float*)e.bb.md.data(),
                                e.bb.nVmax, e.bb.nTmax, r.X.data(), r.V.data(), r.XT.data(), (const float*)r.mass.data(), (const float*)r.dbc.data(),
-                               (const float4*)r.dbcx.data(), dt, e.dt2Prepared, gravity, iters, rho, wdbc, e.dfb, muT, muN);
+                               (const float4*)r.dbcx.data(), dt, e.dt2Prepared, gravity, iters, rho, wdbc, e.dfb, muT, muN, (unsigned long long*)nullptr);
             };
             if (e.rotMode == 1) run(k_body_step<1>); else run(k_body_step<0>);
         }

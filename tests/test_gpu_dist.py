@@ -15,7 +15,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _single(pd, sc, steps, **kw):
-    eng = pd.PdSolver(sc, **kw)
+    # (body_kernel=0: a partitioned mesh runs the tile kernels, and it is THEIR single-GPU run that the ranks must reproduce
+    # bit for bit; the per-body kernel small-body scenes default to on one GPU sums in another order)
+    eng = pd.PdSolver(sc, body_kernel=0, **kw)
     V0 = np.zeros((sc.counts()[0], 3), np.float32); V0[:, 1] = 0.3 * np.sin(sc.arrays()["X"][:, 0])
     eng.upload(V=V0)
     eng.Update(steps)
