@@ -32,6 +32,13 @@ WORKLOADS = {
     # independent (house2 + sphere) contexts, 64 per GPU, no inter-GPU communication (weak scaling)
     "batch64": (0, 100, "64 independent contexts per GPU, each house2 (1,389 tets) + sphere (1,217 tets) over a floor and a fixed sphere, float PD, Chebyshev-Jacobi 100 it/step"),
 }
+# SURVEY C3 as specified: PD + Jacobi-PCG global step, 10 outer PD iterations per step; (inner max, ||r|| tolerance)
+SOLVER_WORKLOADS = {
+    "grid55-pcg": (55, 10, 50, 0.0, "Kuhn 6-tet grid 55^3 cells (175,616 verts, 998,250 tets), float PD, 10 outer iterations x Jacobi-PCG with a FIXED 50 inner iterations (throughput variant)"),
+    "grid55-pcg-tol": (55, 10, 2000, 1e-5, "Kuhn 6-tet grid 55^3 cells (175,616 verts, 998,250 tets), float PD, 10 outer iterations x Jacobi-PCG to the reference's stopping rule (||r|| < 1e-5, at most 2000)"),
+}
+for _k, _v in SOLVER_WORKLOADS.items():
+    WORKLOADS[_k] = (_v[0], _v[1], _v[4])
 BATCH_PER_GPU = 64
 DT, GRAVITY, MU, MASS, JITTER, SEED = 1.0 / 60.0, 9.8, 2e5, 1.0, 0.05, 12345
 
@@ -173,7 +180,11 @@ def make_scene(pd, workload, rank=0):
         return make_batch_scene(pd, rank * BATCH_PER_GPU, BATCH_PER_GPU)
     cells, iters, _ = WORKLOADS[workload]
     sc = pd.Scene.kuhn_grid(cells, cells, cells, 1.0, JITTER, SEED, (0.0, 10.0, 0.0), MASS, MU)
-    p = pd.SolverParams(dt=DT, gravity=GRAVITY, num_iterations=iters)
+    if workload in SOLVER_WORKLOADS:
+        _, _, inner, cg_tol, _ = SOLVER_WORKLOADS[workload]
+        p = pd.SolverParams(dt=DT, gravity=GRAVITY, num_iterations=iters, global_solver=2, tol=1e-6, pcg_max_iter=inner, pcg_tol=cg_tol)
+    else:
+        p = pd.SolverParams(dt=DT, gravity=GRAVITY, num_iterations=iters)
     sc.params = p
     sc.add_fixed(pd.fixed_body(pd.PD_PLANE, pos=(0, 0, 0), scale=(450, 450, 450)))
     return sc, p
@@ -218,7 +229,9 @@ def workload_config(workload, nV, nT, iters, p, batch, world):
     """The `config` object of the JSON line: identical in both arms (--impl b200 / reference) for the same workload."""
     stream_mb = 60.0 * nT / 1e6         # ~60 B/tet of tile stream (DESIGN.md 3.3) read once per PD iteration
     return {"workload": workload, "description": WORKLOADS[workload][2], "num_verts": nV, "num_tets": nT,
-            "pd_iterations_per_step": iters, "global_solver": "chebyshev-jacobi", "dt": p["dt"], "gravity": p["gravity"], "mu": MU,
+            "pd_iterations_per_step": iters,
+            "global_solver": (f"pcg-jacobi (max {SOLVER_WORKLOADS[workload][2]} inner iterations, ||r|| < {SOLVER_WORKLOADS[workload][3]:g}; PD stops at sqrt(err) < 1e-6)"
+                              if workload in SOLVER_WORKLOADS else "chebyshev-jacobi"), "dt": p["dt"], "gravity": p["gravity"], "mu": MU,
             "rho": p["rho"], "muN": p["muN"], "muT": p["muT"],
             "initial_velocity": "0" if batch else "0.5*sin(x/7) y^",
             "l2": (f"inputs larger than L2: ~{stream_mb:.0f} MB of per-tet data are streamed per PD iteration, no flush needed" if stream_mb > 2 * 126
@@ -475,6 +488,145 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_b200_solver(args):
+    """BASELINE config 3 as specified: PD with the Jacobi-PCG global step (pcgJacobi.cu:88-172 inside PdSolver's direct branch,
+    pdSolver.cu:174-192) on ONE GPU.  value = tets x PD iterations actually executed / s (the PD loop may stop on its
+    tolerance); the roofline is k_pcg_solve's: B_cg = 8 nnz(A^) + 4 (nV + 1) + 144 nV bytes per CG iteration."""
+    import torch
+    import ctypes as C
+    pd = importlib.import_module("soft-body-simulation-cuda_b200")
+    torch.cuda.set_device(0)
+    sc, p = make_scene(pd, args.workload)
+    nV, nT = sc.counts()[:2]
+    iters = p["num_iterations"]
+    X0 = sc.arrays()["X"]
+    V0 = initial_velocity(X0)
+    eng = pd.PdSolver(sc, device=0, rot_mode=args.rot_mode)
+    eng.upload(V=V0)
+    for _ in range(args.warmup):
+        eng.Update(1)
+    eng.synchronize(); torch.cuda.synchronize()
+    c0 = eng.GetPerformanceData()[1]
+    sampler = ClockSampler(0); sampler.start()
+    dev_ms = eng.step_timed(args.steps)
+    clocks = sampler.stop()
+    c1 = eng.GetPerformanceData()[1]
+    pd_it, inner = c1.pd_iterations - c0.pd_iterations, c1.inner_iterations - c0.inner_iterations
+    ms_step = dev_ms / args.steps
+    # the global-solve share, from events around every launch (perf mode: one host sync per step), on further steps
+    eng.SetPerf(True)
+    n0, r0 = eng.GetPerformanceData()
+    eng.Update(args.steps)
+    n1, r1 = eng.GetPerformanceData()
+    eng.SetPerf(False)
+    local_ms, solve_ms = n1[0][1] - n0[0][1], n1[1][1] - n0[1][1]
+    inner_perf = r1.inner_iterations - r0.inner_iterations
+    sizes = eng.solver_sizes()
+    b_cg = 8.0 * sizes["nnz_A"] + 4.0 * (nV + 1) + 144.0 * nV
+    peak, peak_src = peaks()
+    ach = b_cg * inner_perf / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
+    # end to end through pd_step_host
+    X, V, XT = eng.download()
+    nbytes = X.nbytes
+    bufs = [pd.lib().pd_alloc_pinned(nbytes) for _ in range(6)]
+    arr = [np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_float)), shape=X.shape) for b in bufs]
+    arr[0][:] = X; arr[1][:] = V; arr[2][:] = XT
+    e2e_steps = max(1, min(args.steps, 5))
+    eng.step_host_ptr(1, bufs[0], bufs[1], bufs[2], bufs[3], bufs[4], bufs[5])
+    eng.synchronize()
+    e0 = eng.GetPerformanceData()[1].pd_iterations
+    t0 = time.perf_counter()
+    for s_ in range(e2e_steps):
+        i, o = (3, 0) if s_ % 2 == 0 else (0, 3)
+        eng.step_host_ptr(1, bufs[i], bufs[i + 1], bufs[i + 2], bufs[o], bufs[o + 1], bufs[o + 2])
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    e2e_it = eng.GetPerformanceData()[1].pd_iterations - e0
+    finite = bool(np.isfinite(arr[0] if e2e_steps % 2 == 1 else arr[3]).all())
+    for b in bufs:
+        pd.lib().pd_free_pinned(b)
+    # parity: the reference's own PCGJacobiSolver<float> in PdSolver's direct branch (oracle/ref_solvers.cu; that harness
+    # has no fixed bodies: 5 steps of free flight from the benchmark's initial state, its default max 2000 / 1e-5)
+    parity = None
+    if not args.no_parity:
+        import ref
+        parity = {"workload": args.workload, "steps": 5, "definition": "max_v |x_v - ref_v| / max(|ref_v|, bounding-box diagonal)"}
+        if ref.solvers_available():
+            a = sc.arrays()
+            kw = dict(dt=DT, gravity=GRAVITY, tol=1e-6, num_iterations=iters)
+            outs = []
+            for _ in range(2):
+                rs = ref.RefSolverScene(a["X"], a["Tet"], a["mass"], a["mu"], 2); rs.set(V=V0)
+                rs.step(5, **kw); outs.append(rs.get()[0].copy()); del rs
+            q = sc.params; q["pcg_max_iter"] = 2000; q["pcg_tol"] = 1e-5; sc.params = q
+            pe = pd.PdSolver(sc, device=0, rot_mode=args.rot_mode); pe.upload(V=V0); pe.Update(5)
+            parity.update({"reference": "oracle/_ref: PdSolver's direct branch around the reference's PCGJacobiSolver<float> (cuSPARSE / cuBLAS)",
+                           "rel_err": meshes_rel_err(pe.download()[0], outs[0]), "reference_vs_reference": meshes_rel_err(outs[1], outs[0])})
+            pe.close()
+        else:
+            parity.update({"reference": "unavailable (oracle/_ref/libpd_ref_solvers.so not built)", "rel_err": None})
+    value = nT * (pd_it / args.steps) / (ms_step * 1e-3) / 1e6
+    line = {
+        "metric": "Mtet-updates/s & PD iters/s at 1/2/4/8 B200; % of HBM roofline",
+        "value": value, "unit": "Mtet-updates/s", "pd_iters_per_s": (pd_it / args.steps) / (ms_step * 1e-3), "inner_iters_per_s": (inner / args.steps) / (ms_step * 1e-3),
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, nV, nT, iters, p, False, 1),
+        "run": {"finite": finite, "pd_iterations_per_step_executed": pd_it / args.steps, "inner_iterations_per_step": inner / args.steps,
+                "nnz_A": sizes["nnz_A"], "rot_mode": args.rot_mode},
+        "parity": parity, "clocks": clocks,
+        "e2e": {"value": nT * (e2e_it / e2e_steps) / (e2e_ms * 1e-3) / 1e6, "unit": "Mtet-updates/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 3 * nbytes,
+                "d2h_bytes_per_step": 3 * nbytes, "steps": e2e_steps, "api": "pd_step_host (include/pd_b200.h): pinned host X,V,XTilde in and out every step"},
+        "gpu_launches": int(c1.kernel_launches - c0.kernel_launches),
+        "roofline": {"bound": "hbm", "kernel": "k_pcg_solve (one cooperative launch per PD iteration = one whole PCG solve: fused SpMV + direction update + dots)",
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic(args.workload, "k_pcg_solve"), "peak_source": peak_src,
+                     "algorithmic_bytes_per_cg_iteration": b_cg, "cg_iterations_timed": int(inner_perf), "solve_kernels_ms": solve_ms, "local_and_rhs_kernels_ms": local_ms,
+                     "us_per_cg_iteration": solve_ms * 1e3 / max(inner_perf, 1),
+                     "note": "the working set (A^ and six vectors, ~46 MB) is L2 resident: the HBM roofline is the contract's yardstick, the kernel's own bound is the grid-wide synchronisations (two per CG iteration) and L2 latency"},
+        "cpu_baseline": cpu_baseline(100, os.cpu_count() or 1) if not args.no_cpu_baseline else None,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_reference_solver(args):
+    """Reference arm of the PCG workloads: the reference's own PCGJacobiSolver<float> inside PdSolver's direct branch (oracle/_ref,
+    compiled from its sources: cuSPARSE SpMV + cuBLAS dots, host loop with three scalar read-backs per CG iteration) on one B200."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import ref
+    import torch
+    pd = importlib.import_module("soft-body-simulation-cuda_b200")      # host-side scene generator only
+    sc, p = make_scene(pd, args.workload)
+    nV, nT = sc.counts()[:2]
+    iters = p["num_iterations"]
+    a = sc.arrays()
+    base = {"metric": "Mtet-updates/s & PD iters/s at 1/2/4/8 B200; % of HBM roofline", "unit": "Mtet-updates/s", "impl": "reference", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, nV, nT, iters, p, False, 1)}
+    if not ref.solvers_available():
+        print(json.dumps({**base, "unavailable": "oracle/_ref/libpd_ref_solvers.so not built"}))
+        return
+    rs = ref.RefSolverScene(a["X"], a["Tet"], a["mass"], a["mu"], 2)
+    rs.set(V=initial_velocity(a["X"]))
+    kw = dict(dt=DT, gravity=GRAVITY, tol=1e-6, num_iterations=iters)
+    rs.step(args.warmup, **kw); rs.get()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0); sampler.start()
+    e0.record()
+    rs.step(args.steps, **kw)
+    e1.record(); e1.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    it_last = rs.stats()[0]
+    val = nT * it_last / (ms * 1e-3) / 1e6
+    base.update({"value": val, "ms_per_step": ms, "pd_iters_per_s": it_last / (ms * 1e-3), "clocks": clocks,
+                 "reference_kind": "PdSolver's direct branch around the reference's PCGJacobiSolver<float> (its defaults: at most 2000 inner iterations, ||r|| < 1e-5), oracle/ref_solvers.cu on one B200",
+                 "run": {"pd_iterations_last_step": it_last, "finite": bool(np.isfinite(rs.get()[0]).all())},
+                 "cpu_baseline": None,
+                 "e2e": {"value": val, "unit": "Mtet-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(base))
+
+
 def run_reference(args):
     """Reference arm: the reference's own CUDA kernels (oracle/_ref, compiled verbatim from
     /root/reference) replayed launch for launch on ONE B200, same workload/metric.  If the prebuilt
@@ -547,7 +699,11 @@ if __name__ == "__main__":
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="experiments only: cap the local kernel's resident CTAs per SM")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
+    if args.workload in SOLVER_WORKLOADS:
+        if args.gpus > 1:
+            sys.exit("the PCG workloads are single-GPU bench lines (the partitioned PCG path is covered by tests/dist_gpu_worker.py)")
+        (run_reference_solver if args.impl == "reference" else run_b200_solver)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

@@ -16,8 +16,10 @@
  *   first Update after construction/Reset : D2H of the rest data (X0, Tet, mass, mu, DBC) -> pd_scene_from_desc ->
  *       pd_create (device layout is built once), DBCX <- X0 like SolverPrepare (pdSolver.cu:134)
  *   every Update : pd_set_params (CopyUIToParams runs before every Update, simulationContext.cpp:85)
- *       -> pd_update_device(engine, 1, data.X, data.V, data.XTilde): AoS glm::vec3 import, one PD step, AoS export,
- *       all on the engine's stream, synchronised on return (the renderer and BVH read data.X next).
+ *       -> pd_update_device(engine, 1, data.X, data.V, data.XTilde): AoS glm::vec3 import, one PD step (with
+ *       SolverParams::handleCollision: the mesh-mesh collision pass of pdSolver.cu:218-225 on data.Tri / dev_TriFathers, inside
+ *       the engine, before the fixed bodies -- as in PdSolver::Update), AoS export, all on the engine's stream, synchronised on
+ *       return (the renderer reads data.X next).
  *       While data.mouseSelection.dragging: pd_set_drag_device(data.moreDBC, data.OffsetX, mouseSelection.target) first.
  *       (data.DBCX is not written back: nothing but the PD solver itself reads it.)
  * The fixed bodies are passed as plain structs; B200_FIXED_BODY_FROM shows how to fill one from a FixedBody*.
@@ -117,6 +119,17 @@ protected:
         desc.num_verts = d.numVerts; desc.num_tets = d.numTets;
         desc.X = X.data(); desc.Tet = tet.data(); desc.mass = mass.data(); desc.mu = mu.data(); desc.DBC = dbc.data();
         desc.num_fixed = (int)fixed_.size(); desc.fixed = fixed_.data();
+        /* surface triangles and their father bodies for the mesh-mesh collision pass (SolverData::Tri / dev_TriFathers,
+         * dataLoader.cu:343-369): with them the engine runs DetectCollision + CCDKernel itself (pdSolver.cu:218-225) */
+        std::vector<uint32_t> tri, father;
+        collisionOk_ = false;
+        if (d.numTris > 0 && d.Tri) {
+            tri.resize(3 * (size_t)d.numTris); father.assign((size_t)d.numTris, 0u);
+            bool okT = cudaMemcpy(tri.data(), d.Tri, 12 * (size_t)d.numTris, cudaMemcpyDeviceToHost) == cudaSuccess;
+            if (okT && d.dev_TriFathers) okT = cudaMemcpy(father.data(), d.dev_TriFathers, 4 * (size_t)d.numTris, cudaMemcpyDeviceToHost) == cudaSuccess;
+            if (okT) { desc.num_tris = d.numTris; desc.Tri = tri.data(); desc.TriFathers = father.data(); collisionOk_ = true; }
+            else cudaGetLastError();
+        }
         pd_params p; toParams(sp, &p);
         noteCollision(p);
         pd_scene* scene = pd_scene_from_desc(&desc, &p);
@@ -160,10 +173,10 @@ protected:
     }
 
 private:
-    /* SolverParams::handleCollision (the GUI default, context.h:44) asks for the mesh-mesh BVH/CCD pass of
-     * PdSolver::Update (pdSolver.cu:218-225).  An engine built without surface triangles cannot run it: say so ONCE
-     * and step with the flag off -- X is then already XTilde on return (pdSolver.cu:227), so the caller cannot run
-     * DetectCollision/CCDKernel between the old X and XTilde afterwards. */
+    /* SolverParams::handleCollision (the GUI default, context.h:44) asks for the mesh-mesh collision pass of
+     * PdSolver::Update (pdSolver.cu:218-225); the engine runs it on SolverData::Tri / dev_TriFathers (SolverPrepare above).
+     * Only a SolverData WITHOUT surface triangles cannot: say so ONCE and step with the flag off -- X is then already
+     * XTilde on return (pdSolver.cu:227), so the caller cannot run DetectCollision / CCDKernel afterwards either. */
     void noteCollision(pd_params& p)
     {
         if (!p.handle_collision || collisionOk_) return;

@@ -74,6 +74,11 @@ typedef struct {
     const float* DBC;         /* num_verts, 1 = pinned (may be NULL = none)                   */
     int num_fixed;
     const pd_fixed_body* fixed;
+    /* surface triangles for the mesh-mesh collision pass (SolverData::numTris / Tri / dev_TriFathers, dataLoader.cu:343-369):
+     * num_tris = 0 or Tri = NULL: the boundary faces of the tets, ONE father body; TriFathers NULL: father 0 everywhere */
+    int num_tris;
+    const uint32_t* Tri;          /* 3*num_tris */
+    const uint32_t* TriFathers;   /* num_tris: soft body of each triangle (pairs of the same father are skipped) */
 } pd_scene_desc;
 
 #define PD_ROT_AUTO (-1)
@@ -109,6 +114,8 @@ void pd_default_options(pd_engine_options* o);
  * asset_root NULL = resolve "../assets/..." like the reference does from its build dir.    */
 pd_scene* pd_scene_load_json(const char* json_path, const char* context_name, const char* asset_root);
 pd_scene* pd_scene_from_desc(const pd_scene_desc* desc, const pd_params* params);
+/* the surface the collision pass would use: *num_tris is always set; tri (3 per triangle) / father are filled when not NULL */
+int pd_scene_get_surface(const pd_scene*, int* num_tris, uint32_t* tri, uint32_t* father);
 /* synthetic Kuhn 6-tet grid (bench configs 3/4) */
 pd_scene* pd_scene_kuhn_grid(int nx, int ny, int nz, float h, float jitter, uint32_t seed,
                              const float origin[3], float mass, float mu);
@@ -154,6 +161,10 @@ int pd_partition_vertices(int num_verts, int world, int* vbeg /* world+1 */);
  * order (replaces cusolverSpXcsrcholAnalysis/Factor, cholesky.cu:152-157, and Eigen::SimplicialCholesky, pdSolver.cu:103).
  * L is returned by rows (ascending columns, diagonal last); free the three arrays with pd_free. */
 int pd_cholesky_factor(int n, const int* rowptr, const int* col, const float* val, int* nnz_l, int** lptr, int** lcol, float** lval);
+/* the fill-reducing order the engine factors in (the reference: AMD inside cusolverSpXcsrcholAnalysis / SimplicialCholesky,
+ * cholesky.cu:72-131): geometric nested dissection of the matrix graph on the rows' rest positions xyz (n x 3).
+ * perm[new] = old.  nnz_l_natural / nnz_l_ordered (may be NULL): non-zeros of L without and with the order (symbolic). */
+int pd_nested_dissection(int n, const int* rowptr, const int* col, const float* xyz, int* perm, int* nnz_l_natural, int* nnz_l_ordered);
 
 /* ---- multi-GPU plan (host only) : vertex partition, tile selection, ghosts, push lists --- new work,
  * the reference is single-GPU.  Checked bit for bit across ranks by the gloo tests. */
@@ -233,6 +244,16 @@ int pd_get_system_matrix(pd_engine*, int* nnz, int* rowptr, int* col, float* val
 /* direct / CG modes: computeError of the last PD iteration (pdSolver.cu:243-253) and the PD iterations the last step ran
  * before sqrt(err) < tol (pdSolver.cu:164) */
 int pd_get_solve_stats(pd_engine*, float* err, int* pd_iterations_last_step);
+/* Mesh-mesh collision (pd_params.handle_collision = 1; PdSolver::Update, pdSolver.cu:218-225: DetectCollision + CCDKernel between
+ * SolverStep and the fixed-body response).  The pass runs inside pd_step / pd_update_device on the scene's surface triangles
+ * (pd_scene_desc.Tri or the tets' boundary faces; pairs of the same father body are skipped, as PdSolver asks for).  This
+ * reads back what the LAST pass left in SolverData::dev_tIs / dev_Normals: tI[v] = 1 (free) or 0.5 (in a detected contact: the
+ * vertex kept its position and got V = -(n . dx) n), the contact normals (3 per vertex), and the number of triangle pairs
+ * whose swept boxes overlapped.  Any pointer may be NULL.  Single-GPU engines only. */
+int pd_get_collision(pd_engine*, float* tI, float* normals, long long* num_pairs);
+/* sizes of the direct / CG modes' setup products (0 until the mode has been prepared): non-zeros of the scalar system matrix A^
+ * and of its Cholesky factor L in the nested-dissection order */
+int pd_get_solver_sizes(pd_engine*, long long* nnz_A, long long* nnz_L);
 /* measurement helpers used by bench.py: average device time (ms) of one launch of the local /
  * vertex kernel over `reps` back-to-back launches, CUDA events on the engine's stream */
 int pd_time_kernels(pd_engine*, int reps, float* local_ms, float* vertex_ms);
@@ -259,6 +280,10 @@ int pd_dist_info(const pd_engine*, int info[6]);
 /* test hook: the corotational projection (pdUtil.cu:112-122) of n row-major 3x3 matrices on
  * `device`; rot_mode as in pd_engine_options; used_fast (may be NULL) reports the path taken */
 int pd_rotation_batch(int device, int rot_mode, int n, const float* F, float* R, int* used_fast);
+/* test hook: the collision pass's continuous-collision test (ccdCollisionTest<float>, intersections.cu:312-355) on n queries of
+ * host arrays: type[i] = 1 vertex-face / 2 edge-edge, verts = 4 vertex ids per query, X / XTilde = 3 per vertex;
+ * toi[i] in [0, 1] (1 = no hit), normals = 3 per query */
+int pd_ccd_batch(int device, int n, const int* type, const uint32_t* verts, int num_verts, const float* X, const float* XTilde, float* toi, float* normals);
 /* pinned host memory for the e2e path */
 void* pd_alloc_pinned(size_t bytes);
 void pd_free_pinned(void*);

@@ -74,6 +74,10 @@ def lib():
         L.o_scene_drag_select.argtypes = [C.c_void_p, C.c_int, C.c_float, f32p]
         L.o_scene_get_drag.argtypes = [C.c_void_p, f32p, f32p, f32p]
         L.o_scene_set_mu.argtypes = [C.c_void_p, f32p]
+        L.o_scene_set_collision.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.o_scene_get_collision.argtypes = [C.c_void_p, f32p, f32p, C.POINTER(C.c_longlong)]
+        L.o_ccd_test.restype = C.c_float
+        L.o_ccd_test.argtypes = [C.c_int, u32p, f32p, f32p, f32p]
         _LIB = L
     return _LIB
 
@@ -83,6 +87,15 @@ def svd3(A):
     U = np.zeros(9, np.float32); S = np.zeros(3, np.float32); V = np.zeros(9, np.float32)
     lib().o_svd3(A, U, S, V)
     return U.reshape(3, 3), S, V.reshape(3, 3)
+
+
+def ccd_test(ee, q, X, XTilde):
+    """ccdCollisionTest<float> (intersections.cu:312-355) on one query -> (toi, normal)."""
+    q = np.ascontiguousarray(q, np.uint32).reshape(4)
+    X = np.ascontiguousarray(X, np.float32).reshape(-1); XT = np.ascontiguousarray(XTilde, np.float32).reshape(-1)
+    n = np.zeros(3, np.float32)
+    t = lib().o_ccd_test(int(bool(ee)), q, X, XT, n)
+    return float(t), n
 
 
 def rotation(F):
@@ -216,6 +229,21 @@ class Scene:
 
     def set_mu(self, mu):
         lib().o_scene_set_mu(self._h, np.ascontiguousarray(mu, np.float32).reshape(self.nT))
+
+    def set_collision(self, enable, Tri=None, TriFathers=None):
+        """SolverParams::handleCollision + SolverData::Tri / dev_TriFathers (pdSolver.cu:218-225)."""
+        if Tri is None:
+            lib().o_scene_set_collision(self._h, int(bool(enable)), 0, None, None)
+            return
+        t = np.ascontiguousarray(Tri, np.uint32).reshape(-1, 3)
+        f = None if TriFathers is None else np.ascontiguousarray(TriFathers, np.uint32).reshape(t.shape[0])
+        lib().o_scene_set_collision(self._h, int(bool(enable)), t.shape[0], t.ctypes.data, None if f is None else f.ctypes.data)
+
+    def collision(self):
+        """(tI, normals, ordered overlapping triangle pairs) of the last collision pass."""
+        t = np.ones(self.nV, np.float32); n = np.zeros((self.nV, 3), np.float32); p = C.c_longlong()
+        lib().o_scene_get_collision(self._h, t, n.reshape(-1), C.byref(p))
+        return t, n, p.value
 
     def get_drag(self):
         m = np.zeros(self.nV, np.float32); o = np.zeros((self.nV, 3), np.float32); d = np.zeros((self.nV, 3), np.float32)

@@ -14,6 +14,7 @@
  */
 #include "pd_oracle.h"
 
+#include <float.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -482,6 +483,8 @@ struct o_scene {
     o_fixed_bodies fb;
     float *fbbuf;
     int last_pd_iters, last_inner_iters;
+    /* mesh-mesh collision (SolverData::Tri / dev_TriFathers / dev_tIs / dev_Normals, def.h:22,40-41,44) */
+    int col_on, nTris; uint32_t *Tri, *TriFathers; float *tI, *Normals; long long col_pairs;
     /* f64 twin state */
     double *Xd, *Vd, *XTd;
 };
@@ -546,6 +549,7 @@ o_scene *o_scene_create(int nV, int nT, const float *X, const uint32_t *Tet, con
 
 void o_scene_destroy(o_scene *s)
 {
+    if (s) { free(s->Tri); free(s->TriFathers); free(s->tI); free(s->Normals); }
     if (!s) return;
     free(s->X); free(s->X0); free(s->XTilde); free(s->V); free(s->DBCX); free(s->ExtForce);
     free(s->moreDBC); free(s->OffsetX);
@@ -1038,13 +1042,16 @@ static int solver_step(o_scene *s, const o_params *p)
     return 0;
 }
 
+static void mesh_collision(o_scene *s);
+
 int o_scene_step(o_scene *s, const o_params *p, int n_steps)
 {
     for (int n = 0; n < n_steps; n++) {   /* PdSolver::Update pdSolver.cu:210-232 */
         if (!s->ready) prepare(s, p);
         int rc = solver_step(s, p);
         if (rc) return rc;
-        memcpy(s->X, s->XTilde, sizeof(float) * 3 * (size_t)s->nV);   /* handleCollision == false */
+        if (s->col_on) mesh_collision(s);                                  /* handleCollision: DetectCollision + CCDKernel, :218-225 */
+        else memcpy(s->X, s->XTilde, sizeof(float) * 3 * (size_t)s->nV);   /* handleCollision == false, :227 */
         fixed_bodies(s, p->muT, p->muN);
     }
     return 0;
@@ -1216,4 +1223,268 @@ int o_scene_step_f64(o_scene *s, const o_params *p, int n_steps)
     for (size_t i = 0; i < N; i++) { s->X[i] = (float)s->Xd[i]; s->V[i] = (float)s->Vd[i]; s->XTilde[i] = (float)s->XTd[i]; }
     free(c); free(md); free(Bd); free(w); free(sn); free(so); free(prev); free(b);
     return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * mesh-mesh collision of the PD path: CollisionDetection::DetectCollision + CCDKernel
+ * (pdSolver.cu:218-225).  Restated step by step, WITHOUT the reference's LBVH: the set of
+ * triangle pairs whose swept boxes overlap does not depend on the tree, so all pairs are tried
+ * (the oracle is for small cases).  Where the reference is racy / unstable the oracle takes
+ * "threads run in index order, sorts are stable over the previous order".
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { float x, y, z; } cv3;
+static cv3 c_mk(float x, float y, float z) { cv3 r = {x, y, z}; return r; }
+static cv3 c_ld(const float *a, uint32_t i) { return c_mk(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
+static cv3 c_sub(cv3 a, cv3 b) { return c_mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+static cv3 c_add(cv3 a, cv3 b) { return c_mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+static cv3 c_mul(cv3 a, float s) { return c_mk(a.x * s, a.y * s, a.z * s); }
+static cv3 c_smul(float s, cv3 a) { return c_mk(s * a.x, s * a.y, s * a.z); }
+static cv3 c_neg(cv3 a) { return c_mk(-a.x, -a.y, -a.z); }
+static float c_dot(cv3 a, cv3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }                 /* glm func_geometric.inl:65-72 */
+static cv3 c_cross(cv3 x, cv3 y) { return c_mk(x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y); }
+static float c_len(cv3 a) { return sqrtf(c_dot(a, a)); }
+static cv3 c_norm(cv3 a) { return c_mul(a, 1.0f / sqrtf(c_dot(a, a))); }                        /* x * inversesqrt(dot(x, x)) */
+static float c_stp(cv3 u, cv3 v, cv3 w) { return c_dot(u, c_cross(v, w)); }                     /* intersections.cu:27 */
+
+static float c_newton(float a, float b, float c, float d, float x0, int init_dir)
+{   /* intersections.cu:95-114 */
+    if (init_dir != 0) {
+        float y0 = d + x0 * (c + x0 * (b + x0 * a)), ddy0 = 2 * b + x0 * (6 * a);
+        if (ddy0 != 0) x0 += init_dir * sqrtf(fabsf(2 * y0 / ddy0));
+    }
+    for (int iter = 0; iter < 100; iter++) {
+        float y = d + x0 * (c + x0 * (b + x0 * a));
+        float dy = c + x0 * (2 * b + x0 * 3 * a);
+        if (dy == 0) return x0;
+        float x1 = x0 - y / dy;
+        if ((double)fabsf(x0 - x1) < 1e-6) return x0;
+        x0 = x1;
+    }
+    return x0;
+}
+static int c_quadratic(float a, float b, float c, float *x)
+{   /* intersections.cu:74-92 */
+    float d = b * b - 4 * a * c;
+    if (d < 0) { x[0] = -b / (2 * a); return 0; }
+    float sgn = (float)(0.0f < b) - (float)(b < 0.0f);
+    float q = -(b + sgn * sqrtf(d)) / 2;
+    int i = 0;
+    if ((double)fabsf(a) > 1e-12 * (double)fabsf(q)) x[i++] = q / a;
+    if ((double)fabsf(q) > 1e-12 * (double)fabsf(c)) x[i++] = c / q;
+    if (i == 2 && x[0] > x[1]) { float t = x[0]; x[0] = x[1]; x[1] = t; }
+    return i;
+}
+static int c_cubic(float a, float b, float c, float d, float *x)
+{   /* intersections.cu:46-72 */
+    float xc[2];
+    int ncrit = c_quadratic(3 * a, 2 * b, c, xc);
+    if (ncrit == 0) { x[0] = c_newton(a, b, c, d, xc[0], 0); return 1; }
+    if (ncrit == 1) return c_quadratic(b, c, d, x);
+    float yc[2] = {d + xc[0] * (c + xc[0] * (b + xc[0] * a)), d + xc[1] * (c + xc[1] * (b + xc[1] * a))};
+    int i = 0;
+    if (yc[0] * a >= 0) x[i++] = c_newton(a, b, c, d, xc[0], -1);
+    if (yc[0] * yc[1] <= 0) {
+        int closer = fabsf(yc[0]) < fabsf(yc[1]) ? 0 : 1;
+        x[i++] = c_newton(a, b, c, d, xc[closer], closer == 0 ? 1 : -1);
+    }
+    if (yc[1] * a <= 0) x[i++] = c_newton(a, b, c, d, xc[1], 1);
+    return i;
+}
+static float c_vf_distance(cv3 x, cv3 y0, cv3 y1, cv3 y2, cv3 *n, float w[4])
+{   /* intersections.cu:115-134 */
+    *n = c_cross(c_norm(c_sub(y1, y0)), c_norm(c_sub(y2, y0)));
+    if ((double)c_dot(*n, *n) < 1e-6) return FLT_MAX;
+    *n = c_norm(*n);
+    float h = c_dot(c_sub(x, y0), *n);
+    float b0 = c_stp(c_sub(y1, x), c_sub(y2, x), *n), b1 = c_stp(c_sub(y2, x), c_sub(y0, x), *n), b2 = c_stp(c_sub(y0, x), c_sub(y1, x), *n);
+    w[0] = 1; w[1] = -b0 / (b0 + b1 + b2); w[2] = -b1 / (b0 + b1 + b2); w[3] = -b2 / (b0 + b1 + b2);
+    return h;
+}
+static float c_ee_distance(cv3 x0, cv3 x1, cv3 y0, cv3 y1, cv3 *n, float w[4])
+{   /* intersections.cu:157-174 */
+    *n = c_cross(c_norm(c_sub(x1, x0)), c_norm(c_sub(y1, y0)));
+    if ((double)c_dot(*n, *n) < 1e-6) return FLT_MAX;
+    *n = c_norm(*n);
+    float h = c_dot(c_sub(x0, y0), *n);
+    float a0 = c_stp(c_sub(y1, x1), c_sub(y0, x1), *n), a1 = c_stp(c_sub(y0, x0), c_sub(y1, x0), *n);
+    float b0 = c_stp(c_sub(x0, y1), c_sub(x1, y1), *n), b1 = c_stp(c_sub(x1, y0), c_sub(x0, y0), *n);
+    w[0] = a0 / (a0 + a1); w[1] = a1 / (a0 + a1); w[2] = -b0 / (b0 + b1); w[3] = -b1 / (b0 + b1);
+    return h;
+}
+/* ccdCollisionTest<float>, intersections.cu:312-355; ee: edge-edge query */
+float o_ccd_test(int ee, const uint32_t q[4], const float *X, const float *XT, float nout[3])
+{
+    cv3 x0 = c_ld(X, q[0]), x1 = c_ld(X, q[1]), x2 = c_ld(X, q[2]), x3 = c_ld(X, q[3]);
+    cv3 v0 = c_sub(c_ld(XT, q[0]), x0), v1 = c_sub(c_ld(XT, q[1]), x1), v2 = c_sub(c_ld(XT, q[2]), x2), v3 = c_sub(c_ld(XT, q[3]), x3);
+    cv3 x01 = c_sub(x1, x0), x02 = c_sub(x2, x0), x03 = c_sub(x3, x0), v01 = c_sub(v1, v0), v02 = c_sub(v2, v0), v03 = c_sub(v3, v0);
+    float a0 = c_stp(x01, x02, x03);
+    float a1 = c_stp(v01, x02, x03) + c_stp(x01, v02, x03) + c_stp(x01, x02, v03);
+    float a2 = c_stp(x01, v02, v03) + c_stp(v01, x02, v03) + c_stp(v01, v02, x03);
+    float a3 = c_stp(v01, v02, v03);
+    cv3 n = c_mk(0, 0, 0);
+    float res = 1.0f;
+    if (!((double)fabsf(a0) < 1e-12 * (double)c_len(x01) * (double)c_len(x02) * (double)c_len(x03))) {
+        float t[3];
+        int nsol = c_cubic(a3, a2, a1, a0, t);
+        for (int i = 0; i < nsol; i++) {
+            if ((double)t[i] < -1e-12 || t[i] > 1) continue;
+            cv3 xt0 = c_add(x0, c_smul(t[i], v0)), xt1 = c_add(x1, c_smul(t[i], v1)), xt2 = c_add(x2, c_smul(t[i], v2)), xt3 = c_add(x3, c_smul(t[i], v3));
+            float w[4] = {0, 0, 0, 0}, d;
+            int inside;
+            if (!ee) {
+                d = c_vf_distance(xt0, xt1, xt2, xt3, &n, w);
+                inside = (double)fminf(-w[1], fminf(-w[2], -w[3])) >= -1e-3;
+            } else {
+                d = c_ee_distance(xt0, xt1, xt2, xt3, &n, w);
+                inside = (double)fminf(w[0], fminf(w[1], fminf(-w[2], -w[3]))) >= -1e-3;
+            }
+            if (c_dot(n, c_add(c_add(c_smul(w[1], v1), c_smul(w[2], v2)), c_smul(w[3], v3))) > 0) n = c_neg(n);
+            if ((double)fabsf(d) < 1e-6 && inside) { res = t[i]; break; }
+        }
+    }
+    nout[0] = n.x; nout[1] = n.y; nout[2] = n.z;
+    return res;
+}
+
+typedef struct { int type; uint32_t v[4]; float toi; float n[3]; } o_query;   /* type 1 = VF, 2 = EE (QueryType, aabb.h:54-58) */
+static void swap_u(uint32_t *a, uint32_t *b) { uint32_t t = *a; *a = *b; *b = t; }
+static int q_cmp_ids(const void *pa, const void *pb)
+{   /* QueryComparator, broadphase.cu:213-223 */
+    const o_query *a = (const o_query *)pa, *b = (const o_query *)pb;
+    if (a->type != b->type) return a->type < b->type ? -1 : 1;
+    for (int k = 0; k < 4; k++) if (a->v[k] != b->v[k]) return a->v[k] < b->v[k] ? -1 : 1;
+    return 0;
+}
+static int q_cmp_toi(const void *pa, const void *pb)
+{   /* CompareQuery, narrowphase.cu:9-41; ties fall back to the id order (the reference's sort is unstable there) */
+    const o_query *a = (const o_query *)pa, *b = (const o_query *)pb;
+    if (a->type != b->type) return a->type < b->type ? -1 : 1;
+    if (a->v[0] != b->v[0]) return a->v[0] < b->v[0] ? -1 : 1;
+    if (a->type == 2 && a->v[1] != b->v[1]) return a->v[1] < b->v[1] ? -1 : 1;
+    if (a->toi != b->toi) return a->toi < b->toi ? -1 : 1;
+    return q_cmp_ids(pa, pb);
+}
+static int q_same_group(const o_query *a, const o_query *b)
+{   /* EqualQuery, narrowphase.cu:43-61 */
+    if (a->type != b->type) return 0;
+    return a->type == 1 ? a->v[0] == b->v[0] : (a->v[0] == b->v[0] && a->v[1] == b->v[1]);
+}
+
+static void mesh_collision(o_scene *s)
+{
+    const int nV = s->nV, nT = s->nTris;
+    const uint32_t *tri = s->Tri, *fa = s->TriFathers;
+    for (int v = 0; v < nV; v++) s->tI[v] = 1.0f;                        /* thrust::fill(tI, 1.0f), bvh.cu:173-174 */
+    /* swept boxes: computeTriTrajBBoxCCD, ccd.cu:53-66 */
+    float *bmin = (float *)malloc(sizeof(float) * 3 * (size_t)(nT > 0 ? nT : 1)), *bmax = (float *)malloc(sizeof(float) * 3 * (size_t)(nT > 0 ? nT : 1));
+    for (int t = 0; t < nT; t++)
+        for (int c = 0; c < 3; c++) {
+            float mn = FLT_MAX, mx = -FLT_MAX;
+            const float *src[2] = {s->X, s->XTilde};
+            float p[6];
+            for (int h = 0; h < 2; h++) for (int k = 0; k < 3; k++) p[3 * h + k] = src[h][3 * (size_t)tri[3 * t + k] + c];
+            mn = fminf(fminf(fminf(fminf(fminf(p[0], p[1]), p[2]), p[3]), p[4]), p[5]);
+            mx = fmaxf(fmaxf(fmaxf(fmaxf(fmaxf(p[0], p[1]), p[2]), p[3]), p[4]), p[5]);
+            bmin[3 * t + c] = mn - 0.01f; bmax[3 * t + c] = mx + 0.01f;
+        }
+    /* traverseTree + fillQuery (broadphase.cu:267-400): every ORDERED pair of overlapping, non-adjacent triangles of different fathers */
+    size_t cap = 1024, nq = 0;
+    o_query *Q = (o_query *)malloc(cap * sizeof(o_query));
+    long long pairs = 0;
+    static const int ET[6] = {0, 1, 0, 2, 1, 2};                          /* edgeIndicesTable */
+    for (int i = 0; i < nT; i++)
+        for (int j = 0; j < nT; j++) {
+            if (i == j || fa[i] == fa[j]) continue;                       /* PdSolver passes ignoreSelfCollision = true */
+            int adj = 0;
+            for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) adj |= tri[3 * i + a] == tri[3 * j + b];
+            if (adj) continue;
+            int hit = 1;
+            for (int c = 0; c < 3; c++) if (bmax[3 * i + c] < bmin[3 * j + c] || bmin[3 * i + c] > bmax[3 * j + c]) hit = 0;
+            if (!hit) continue;
+            pairs++;
+            if (nq + 12 > cap) { cap *= 2; Q = (o_query *)realloc(Q, cap * sizeof(o_query)); }
+            for (int k = 0; k < 3; k++) {
+                o_query q = {1, {tri[3 * i + k], tri[3 * j], tri[3 * j + 1], tri[3 * j + 2]}, 0.f, {0, 0, 0}};
+                Q[nq++] = q;
+            }
+            for (int e = 0; e < 3; e++) {
+                uint32_t v0 = tri[3 * i + ET[2 * e]], v1 = tri[3 * i + ET[2 * e + 1]];
+                const uint32_t w[3][2] = {{tri[3 * j], tri[3 * j + 1]}, {tri[3 * j], tri[3 * j + 2]}, {tri[3 * j + 1], tri[3 * j + 2]}};
+                for (int f = 0; f < 3; f++) { o_query q = {2, {v0, v1, w[f][0], w[f][1]}, 0.f, {0, 0, 0}}; Q[nq++] = q; }
+            }
+        }
+    s->col_pairs = pairs;
+    /* sortEachQuery (broadphase.cu:453-478), removeDuplicates (:488-498) */
+    size_t m = 0;
+    for (size_t k = 0; k < nq; k++) {
+        o_query q = Q[k];
+        if (q.type == 1) {
+            if (q.v[0] == q.v[1] || q.v[0] == q.v[2] || q.v[0] == q.v[3]) continue;
+            if (q.v[1] > q.v[2]) swap_u(&q.v[1], &q.v[2]);
+            if (q.v[2] > q.v[3]) swap_u(&q.v[2], &q.v[3]);
+            if (q.v[1] > q.v[2]) swap_u(&q.v[1], &q.v[2]);
+        } else {
+            if (q.v[0] > q.v[1]) swap_u(&q.v[0], &q.v[1]);
+            if (q.v[2] > q.v[3]) swap_u(&q.v[2], &q.v[3]);
+            if (q.v[0] == q.v[2] && q.v[1] == q.v[3]) continue;
+        }
+        Q[m++] = q;
+    }
+    nq = m;
+    qsort(Q, nq, sizeof(o_query), q_cmp_ids);
+    m = 0;
+    for (size_t k = 0; k < nq; k++) if (m == 0 || q_cmp_ids(&Q[m - 1], &Q[k]) != 0) Q[m++] = Q[k];
+    nq = m;
+    if (nq > 0) {                                                         /* BroadPhaseCCD returned true: NarrowPhase, narrowphase.cu:122-134 */
+        for (size_t k = 0; k < nq; k++) Q[k].toi = o_ccd_test(Q[k].type == 2, Q[k].v, s->X, s->XTilde, Q[k].n);
+        qsort(Q, nq, sizeof(o_query), q_cmp_toi);
+        m = 0;
+        for (size_t k = 0; k < nq; k++) if (m == 0 || !q_same_group(&Q[m - 1], &Q[k])) Q[m++] = Q[k];
+        nq = m;
+        for (size_t k = 0; k < nq; k++) {                                 /* storeTi, narrowphase.cu:74-119, threads in index order */
+            const o_query *q = &Q[k];
+            if (!(q->toi < 1.0f)) continue;
+            int nw = q->type == 2 ? 2 : 4;
+            for (int u = 0; u < nw; u++) {
+                float sgn = (q->type == 1 && u > 0) ? -1.0f : 1.0f;
+                s->tI[q->v[u]] = 0.5f;
+                for (int c = 0; c < 3; c++) s->Normals[3 * (size_t)q->v[u] + c] = sgn * q->n[c];
+            }
+        }
+    }
+    free(Q); free(bmin); free(bmax);
+    /* CCDKernel, collisionUtil.cu:49-70 */
+    for (int v = 0; v < nV; v++) {
+        if (s->tI[v] < 1.0f) {
+            cv3 n = c_ld(s->Normals, (uint32_t)v), vel = c_sub(c_ld(s->XTilde, (uint32_t)v), c_ld(s->X, (uint32_t)v));
+            cv3 vn = c_smul(c_dot(vel, n), n);
+            s->V[3 * v] = -vn.x; s->V[3 * v + 1] = -vn.y; s->V[3 * v + 2] = -vn.z;
+        } else {
+            for (int c = 0; c < 3; c++) s->X[3 * v + c] = s->XTilde[3 * v + c];
+        }
+    }
+}
+
+void o_scene_set_collision(o_scene *s, int enable, int nTris, const uint32_t *Tri, const uint32_t *TriFathers)
+{
+    s->col_on = enable;
+    if (Tri) {
+        free(s->Tri); free(s->TriFathers);
+        s->nTris = nTris;
+        s->Tri = (uint32_t *)malloc(sizeof(uint32_t) * 3 * (size_t)(nTris > 0 ? nTris : 1));
+        s->TriFathers = (uint32_t *)calloc((size_t)(nTris > 0 ? nTris : 1), sizeof(uint32_t));
+        memcpy(s->Tri, Tri, sizeof(uint32_t) * 3 * (size_t)nTris);
+        if (TriFathers) memcpy(s->TriFathers, TriFathers, sizeof(uint32_t) * (size_t)nTris);
+    }
+    if (!s->tI) {
+        s->tI = (float *)malloc(sizeof(float) * (size_t)s->nV);
+        s->Normals = (float *)calloc(3 * (size_t)s->nV, sizeof(float));
+        for (int v = 0; v < s->nV; v++) s->tI[v] = 1.0f;
+    }
+}
+void o_scene_get_collision(const o_scene *s, float *tI, float *normals, long long *pairs)
+{
+    if (tI) for (int v = 0; v < s->nV; v++) tI[v] = s->tI ? s->tI[v] : 1.0f;
+    if (normals) { if (s->Normals) memcpy(normals, s->Normals, sizeof(float) * 3 * (size_t)s->nV); else memset(normals, 0, sizeof(float) * 3 * (size_t)s->nV); }
+    if (pairs) *pairs = s->col_pairs;
 }

@@ -98,6 +98,16 @@ int  o_scene_system_matrix(o_scene *, const o_params *, int *rowptr, int *col, f
 /* statistics of the last step: total PCG iterations, PD iterations executed */
 void o_scene_stats(const o_scene *, int *pd_iters, int *inner_iters);
 
+/* mesh-mesh collision of PdSolver::Update (pdSolver.cu:218-225: DetectCollision with ignoreSelfCollision = true, then
+ * CCDKernel): enable / disable (SolverParams::handleCollision) and, when Tri is not NULL, the surface triangles
+ * (SolverData::Tri, 3 per triangle) with their father bodies (dev_TriFathers; NULL = all 0).  All triangle pairs are tried
+ * instead of the reference's LBVH (same set of overlapping pairs). */
+void o_scene_set_collision(o_scene *, int enable, int nTris, const uint32_t *Tri, const uint32_t *TriFathers);
+/* SolverData::dev_tIs / dev_Normals after the last pass, and the number of (ordered) overlapping triangle pairs */
+void o_scene_get_collision(const o_scene *, float *tI, float *normals, long long *pairs);
+/* ccdCollisionTest<float> (intersections.cu:312-355) on one query: ee = edge-edge, q = its four vertex ids */
+float o_ccd_test(int ee, const uint32_t q[4], const float *X, const float *XTilde, float normal[3]);
+
 /* ---- double-precision twin of the Jacobi step (separates algorithmic from rounding
  * differences) ---- */
 int  o_scene_step_f64(o_scene *, const o_params *, int n_steps);

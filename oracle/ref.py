@@ -180,3 +180,45 @@ class RefSolverScene:
         p = lambda a: None if a is None else a.ctypes.data
         solvers_lib().refs_set(self._h, p(X), p(V), p(XTilde))
         self._keep = (X, V, XTilde)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# oracle/_ref/libpd_ref_collision.so (oracle/ref_collision.cu): the reference's CCD arithmetic, verbatim
+COLLISION_PATH = os.path.join(_HERE, "_ref", "libpd_ref_collision.so")
+_clib = None
+
+
+def collision_available():
+    return os.path.exists(COLLISION_PATH)
+
+
+def collision_lib():
+    global _clib
+    if _clib is None:
+        L = C.CDLL(COLLISION_PATH)
+        L.refc_ccd_queries.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refc_ccd_kernel.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int]
+        _clib = L
+    return _clib
+
+
+def ccd_queries(types, verts, X, XTilde):
+    """ccdCollisionTest<float> of the reference (intersections.cu:312-355) on n queries: types [n] (1 = VF, 2 = EE), verts [n, 4]
+    vertex ids, X / XTilde [nV, 3] -> (toi [n], normals [n, 3])."""
+    t = np.ascontiguousarray(types, np.int32); v = np.ascontiguousarray(verts, np.uint32).reshape(-1, 4)
+    X = np.ascontiguousarray(X, np.float32); XT = np.ascontiguousarray(XTilde, np.float32)
+    toi = np.zeros(t.shape[0], np.float32); nor = np.zeros((t.shape[0], 3), np.float32)
+    rc = collision_lib().refc_ccd_queries(t.shape[0], t.ctypes.data, v.ctypes.data, X.shape[0], X.ctypes.data, XT.ctypes.data, toi.ctypes.data, nor.ctypes.data)
+    if rc:
+        raise RuntimeError(f"reference collision harness CUDA error {rc}")
+    return toi, nor
+
+
+def ccd_kernel(X, XTilde, V, tI, normals, dt=1 / 60, muT=0.5, muN=0.5, threads_per_block=128):
+    """CCDKernel<float> of the reference (collisionUtil.cu:49-70) -> (X, V) after the kernel."""
+    X = np.ascontiguousarray(X, np.float32).copy(); V = np.ascontiguousarray(V, np.float32).copy()
+    XT = np.ascontiguousarray(XTilde, np.float32); tI = np.ascontiguousarray(tI, np.float32); n = np.ascontiguousarray(normals, np.float32)
+    rc = collision_lib().refc_ccd_kernel(X.shape[0], X.ctypes.data, XT.ctypes.data, V.ctypes.data, tI.ctypes.data, n.ctypes.data, muT, muN, np.float32(dt), threads_per_block)
+    if rc:
+        raise RuntimeError(f"reference collision harness CUDA error {rc}")
+    return X, V

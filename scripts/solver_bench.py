@@ -46,7 +46,7 @@ def case(cells, solver, steps, inner, pcg_tol, outer=10):
     p1 = eng.GetPerformanceData()[1]
     pdi, inn = p1.pd_iterations - pd0, p1.inner_iterations - in0
     X = eng.download()[0]
-    out = {"workload": f"grid{cells}", "num_verts": nV, "num_tets": nT, "nnz_A": nnz, "solver": {1: "sparse Cholesky", 2: "PCG-Jacobi"}[solver],
+    out = {"workload": f"grid{cells}", "num_verts": nV, "num_tets": nT, "nnz_A": nnz, "nnz_L": eng.solver_sizes()["nnz_L"], "solver": {1: "sparse Cholesky", 2: "PCG-Jacobi"}[solver],
            "steps": steps, "ms_per_step": ms / steps, "pd_iterations": int(pdi), "inner_iterations": int(inn),
            "pd_iters_per_s": pdi / (ms * 1e-3), "mtet_updates_per_s": nT * pdi / (ms * 1e-3) / 1e6, "finite": bool(np.isfinite(X).all())}
     if solver == 2 and inn > 0:

@@ -43,7 +43,8 @@ class pd_params(C.Structure):
 class pd_scene_desc(C.Structure):
     _fields_ = [("num_verts", C.c_int), ("num_tets", C.c_int), ("X", C.c_void_p), ("Tet", C.c_void_p),
                 ("mass", C.c_void_p), ("mu", C.c_void_p), ("DBC", C.c_void_p),
-                ("num_fixed", C.c_int), ("fixed", C.POINTER(pd_fixed_body))]
+                ("num_fixed", C.c_int), ("fixed", C.POINTER(pd_fixed_body)),
+                ("num_tris", C.c_int), ("Tri", C.c_void_p), ("TriFathers", C.c_void_p)]
 
 
 class pd_engine_options(C.Structure):
@@ -91,6 +92,8 @@ SYMBOLS = {
     "pd_layout_matrix_diag": (_I, [_VP, _VP]),
     "pd_morton_keys": (_I, [_VP, _VP, _I, _VP]),
     "pd_partition_vertices": (_I, [_I, _I, _VP]),
+    "pd_nested_dissection": (_I, [_I, _VP, _VP, _VP, _VP, _PI, _PI]),
+    "pd_scene_get_surface": (_I, [_VP, _PI, _VP, _VP]),
     "pd_cholesky_factor": (_I, [_I, _VP, _VP, _VP, _PI, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
     "pd_rank_plan_build": (_VP, [_VP, _I, _I]),
     "pd_rank_plan_free": (None, [_VP]),
@@ -130,6 +133,9 @@ SYMBOLS = {
     "pd_get_setup": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "pd_get_system_matrix": (_I, [_VP, _PI, _VP, _VP, _VP]),
     "pd_get_solve_stats": (_I, [_VP, _PF, _PI]),
+    "pd_ccd_batch": (_I, [_I, _I, _VP, _VP, _I, _VP, _VP, _VP, _VP]),
+    "pd_get_collision": (_I, [_VP, _VP, _VP, C.POINTER(C.c_longlong)]),
+    "pd_get_solver_sizes": (_I, [_VP, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "pd_time_kernels": (_I, [_VP, _I, _PF, _PF]),
     "pd_profile_local": (_I, [_VP, _VP]),
     "pd_engine_rot_mode": (_I, [_VP]),
@@ -225,14 +231,16 @@ class Scene:
         return cls(lib().pd_scene_load_json(enc(json_path), enc(context_name), enc(asset_root)))
 
     @classmethod
-    def from_arrays(cls, X, Tet, mass, mu, DBC=None, fixed=(), params=None):
+    def from_arrays(cls, X, Tet, mass, mu, DBC=None, fixed=(), params=None, Tri=None, TriFathers=None):
         X = np.ascontiguousarray(X, np.float32); Tet = np.ascontiguousarray(Tet, np.uint32)
         nV, nT = X.shape[0], Tet.shape[0]
         mass = np.ascontiguousarray(np.broadcast_to(np.asarray(mass, np.float32), (nV,)))
         mu = np.ascontiguousarray(np.broadcast_to(np.asarray(mu, np.float32), (nT,)))
         dbc = None if DBC is None else np.ascontiguousarray(DBC, np.float32)
         arr = (pd_fixed_body * max(len(fixed), 1))(*fixed)
-        d = pd_scene_desc(nV, nT, _p(X), _p(Tet), _p(mass), _p(mu), _p(dbc), len(fixed), arr)
+        tri = None if Tri is None else np.ascontiguousarray(Tri, np.uint32).reshape(-1, 3)
+        fa = None if (Tri is None or TriFathers is None) else np.ascontiguousarray(TriFathers, np.uint32)
+        d = pd_scene_desc(nV, nT, _p(X), _p(Tet), _p(mass), _p(mu), _p(dbc), len(fixed), arr, 0 if tri is None else tri.shape[0], _p(tri), _p(fa))
         return cls(lib().pd_scene_from_desc(C.byref(d), C.byref(params.c) if params else None))
 
     @classmethod
@@ -274,6 +282,15 @@ class Scene:
     @params.setter
     def params(self, p):
         _check(lib().pd_scene_set_params(self._h, C.byref(p.c)))
+
+    def surface(self):
+        """(Tri [n, 3], TriFathers [n]): the surface triangles the mesh-mesh collision pass uses (explicit .face / caller-given
+        ones, else the boundary faces of every body's tets)."""
+        n = C.c_int()
+        _check(lib().pd_scene_get_surface(self._h, C.byref(n), None, None))
+        tri = np.zeros((n.value, 3), np.uint32); fa = np.zeros(n.value, np.uint32)
+        _check(lib().pd_scene_get_surface(self._h, C.byref(n), _p(tri), _p(fa)))
+        return tri, fa
 
     def add_fixed(self, fb):
         _check(lib().pd_scene_add_fixed(self._h, C.byref(fb)))
@@ -520,6 +537,18 @@ class PdSolver:
         _check(lib().pd_get_system_matrix(self._h, C.byref(nnz), _p(rp), _p(col), _p(val)))
         return rp, col, val
 
+    def collision(self):
+        """(tI [nV], normals [nV, 3], overlapping triangle pairs) of the last mesh-mesh collision pass."""
+        nV = self.num_verts
+        tI = np.ones(nV, np.float32); nor = np.zeros((nV, 3), np.float32); n = C.c_longlong()
+        _check(lib().pd_get_collision(self._h, _p(tI), _p(nor), C.byref(n)))
+        return tI, nor, n.value
+
+    def solver_sizes(self):
+        a, l = C.c_longlong(), C.c_longlong()
+        _check(lib().pd_get_solver_sizes(self._h, C.byref(a), C.byref(l)))
+        return dict(nnz_A=a.value, nnz_L=l.value)
+
     def solve_stats(self):
         err, it = C.c_float(), C.c_int()
         _check(lib().pd_get_solve_stats(self._h, C.byref(err), C.byref(it)))
@@ -544,6 +573,15 @@ class PdSolver:
                     tile_stream_bytes=sb.value, device_bytes=db.value, local_grid=lg.value, rot_mode=lib().pd_engine_rot_mode(self._h))
 
 
+def nested_dissection(rowptr, col, xyz, count_fill=True):
+    """Host-side fill-reducing order of the Cholesky path: (perm[new] = old, nnz(L) in the given order, nnz(L) reordered)."""
+    rowptr = np.ascontiguousarray(rowptr, np.int32); col = np.ascontiguousarray(col, np.int32); xyz = np.ascontiguousarray(xyz, np.float32)
+    n = rowptr.shape[0] - 1
+    perm = np.zeros(n, np.int32); a, b = C.c_int(-1), C.c_int(-1)
+    _check(lib().pd_nested_dissection(n, _p(rowptr), _p(col), _p(xyz), _p(perm), C.byref(a) if count_fill else None, C.byref(b) if count_fill else None))
+    return perm, a.value, b.value
+
+
 def cholesky_factor(rowptr, col, val):
     """Host-side sparse Cholesky (no GPU): returns L by rows (rowptr, col, val), diagonal last in every row."""
     rowptr = np.ascontiguousarray(rowptr, np.int32); col = np.ascontiguousarray(col, np.int32); val = np.ascontiguousarray(val, np.float32)
@@ -556,6 +594,15 @@ def cholesky_factor(rowptr, col, val):
     for q in (lp, lc, lv):
         lib().pd_free(q)
     return out
+
+
+def ccd_batch(types, verts, X, XTilde, device=0):
+    """The collision pass's continuous-collision test on n queries -> (toi [n], normals [n, 3])."""
+    t = np.ascontiguousarray(types, np.int32); v = np.ascontiguousarray(verts, np.uint32).reshape(-1, 4)
+    X = np.ascontiguousarray(X, np.float32); XT = np.ascontiguousarray(XTilde, np.float32)
+    toi = np.zeros(t.shape[0], np.float32); nor = np.zeros((t.shape[0], 3), np.float32)
+    _check(lib().pd_ccd_batch(device, t.shape[0], _p(t), _p(v), X.shape[0], _p(X), _p(XT), _p(toi), _p(nor)))
+    return toi, nor
 
 
 def rotation_batch(F, rot_mode=0, device=0):

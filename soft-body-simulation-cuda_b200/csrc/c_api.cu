@@ -10,6 +10,7 @@
 
 #include "layout.hpp"
 #include "pd_engine.hpp"
+#include "collision.hpp"
 #include "scene.hpp"
 
 using namespace pdb200;
@@ -86,7 +87,12 @@ pd_scene* pd_scene_from_desc(const pd_scene_desc* d, const pd_params* params)
     sc.mu.assign(d->mu, d->mu + d->num_tets);
     sc.lambda.assign((size_t)d->num_tets, 0.f);
     if (d->DBC) sc.DBC.assign(d->DBC, d->DBC + d->num_verts); else sc.DBC.assign((size_t)d->num_verts, 0.f);
-    sc.bodyVertStart = {0}; sc.bodyTetStart = {0}; sc.bodyNames = {"desc"};
+    sc.bodyVertStart = {0}; sc.bodyTetStart = {0}; sc.bodyNames = {"desc"}; sc.bodyHasTri = {0};
+    if (d->num_tris > 0 && d->Tri) {      // SolverData::Tri / dev_TriFathers as the caller holds them (dataLoader.cu:343-369)
+        sc.Tri.assign(d->Tri, d->Tri + 3 * (size_t)d->num_tris);
+        if (d->TriFathers) sc.triFather.assign(d->TriFathers, d->TriFathers + d->num_tris); else sc.triFather.assign((size_t)d->num_tris, 0u);
+        sc.triWholeScene = true;
+    }
     for (int i = 0; i < d->num_fixed; ++i) {
         FixedBody f; f.type = d->fixed[i].type; std::memcpy(f.model, d->fixed[i].model, 64); f.radius = d->fixed[i].radius;
         sc.fixed.push_back(f);
@@ -123,9 +129,19 @@ pd_scene* pd_scene_merge(const pd_scene* const* scenes, int n)
         if (p.dt != q.dt || p.gravity != q.gravity || p.muN != q.muN || p.muT != q.muT || p.rho != q.rho || p.numIterations != q.numIterations ||
             a.fixed.size() != m.fixed.size()) { delete out; g_err = "contexts of a batch must share solver parameters and fixed bodies"; return nullptr; }
         const uint32_t vOff = (uint32_t)m.numVerts;
+        const uint32_t bOff = (uint32_t)m.bodyVertStart.size();
+        if (a.triWholeScene) {       // a caller-given surface: keep it, under the merged numbering, as explicit triangles of its bodies
+            if (a.bodyVertStart.size() != 1) { delete out; g_err = "cannot merge a multi-body scene that carries caller-given surface triangles"; return nullptr; }
+            for (uint32_t v : a.Tri) m.Tri.push_back(v + vOff);
+            m.triFather.insert(m.triFather.end(), a.triFather.size(), bOff);
+        } else {
+            for (uint32_t v : a.Tri) m.Tri.push_back(v + vOff);
+            for (uint32_t f : a.triFather) m.triFather.push_back(f + bOff);
+        }
         for (size_t b = 0; b < a.bodyVertStart.size(); ++b) {
             m.bodyVertStart.push_back(a.bodyVertStart[b] + m.numVerts); m.bodyTetStart.push_back(a.bodyTetStart[b] + m.numTets);
             m.bodyNames.push_back(a.bodyNames[b] + "#" + std::to_string(i));
+            m.bodyHasTri.push_back(a.triWholeScene ? 1 : (b < a.bodyHasTri.size() ? a.bodyHasTri[b] : 0));
         }
         m.X.insert(m.X.end(), a.X.begin(), a.X.end());
         for (uint32_t v : a.Tet) m.Tet.push_back(v + vOff);
@@ -164,6 +180,19 @@ int pd_scene_get(const pd_scene* s, float* X, uint32_t* Tet, float* mass, float*
         }
     if (bvs) for (size_t i = 0; i < sc.bodyVertStart.size(); ++i) bvs[i] = sc.bodyVertStart[i];
     return PD_OK;
+}
+
+int pd_scene_get_surface(const pd_scene* s, int* num_tris, uint32_t* tri, uint32_t* father)
+{
+    PD_TRY
+    if (!s || !num_tris) return fail(PD_ERR_INVALID, "NULL argument");
+    std::vector<uint32_t> t, f;
+    scene_surface(s->s, t, f);
+    *num_tris = (int)f.size();
+    if (tri) std::memcpy(tri, t.data(), t.size() * 4);
+    if (father) std::memcpy(father, f.data(), f.size() * 4);
+    return PD_OK;
+    PD_CATCH_INT
 }
 
 int pd_scene_get_params(const pd_scene* s, pd_params* out)
@@ -308,6 +337,26 @@ int pd_cholesky_factor(int n, const int* rowptr, const int* col, const float* va
     *lptr = (int*)std::malloc(F.lPtr.size() * sizeof(int)); *lcol = (int*)std::malloc(F.lCol.size() * sizeof(int)); *lval = (float*)std::malloc(F.lVal.size() * sizeof(float));
     std::memcpy(*lptr, F.lPtr.data(), F.lPtr.size() * sizeof(int)); std::memcpy(*lcol, F.lCol.data(), F.lCol.size() * sizeof(int));
     std::memcpy(*lval, F.lVal.data(), F.lVal.size() * sizeof(float));
+    return PD_OK;
+    PD_CATCH_INT
+}
+int pd_nested_dissection(int n, const int* rowptr, const int* col, const float* xyz, int* perm, int* nnz_l_natural, int* nnz_l_ordered)
+{
+    PD_TRY
+    if (n <= 0 || !rowptr || !col || !xyz || !perm) return fail(PD_ERR_INVALID, "bad argument");
+    CsrMatrix A; A.n = n;
+    A.rowPtr.assign(rowptr, rowptr + n + 1); A.col.assign(col, col + rowptr[n]); A.val.assign((size_t)rowptr[n], 0.f);
+    std::vector<int> p;
+    nested_dissection_order(A, xyz, p);
+    std::memcpy(perm, p.data(), (size_t)n * sizeof(int));
+    if (nnz_l_natural || nnz_l_ordered) {
+        // symbolic only: a diagonally dominant stand-in with the same pattern
+        for (int i = 0; i < n; ++i)
+            for (int e = A.rowPtr[i]; e < A.rowPtr[i + 1]; ++e) A.val[(size_t)e] = (A.col[(size_t)e] == i) ? (float)(A.rowPtr[i + 1] - A.rowPtr[i] + 1) : -1.f;
+        CholFactor F;
+        if (nnz_l_natural) { cholesky_factor(A, F); *nnz_l_natural = (int)F.lCol.size(); }
+        if (nnz_l_ordered) { CsrMatrix B; permute_symmetric(A, p, B); cholesky_factor(B, F); *nnz_l_ordered = (int)F.lCol.size(); }
+    }
     return PD_OK;
     PD_CATCH_INT
 }
@@ -475,6 +524,16 @@ int pd_get_system_matrix(pd_engine* e, int* nnz, int* rowptr, int* col, float* v
                 if (col) std::memcpy(col, A.col.data(), A.col.size() * sizeof(int));
                 if (val) std::memcpy(val, A.val.data(), A.val.size() * sizeof(float)))
 }
+int pd_get_collision(pd_engine* e, float* tI, float* normals, long long* num_pairs) { ENGINE_CALL(e->e->getCollision(tI, normals, num_pairs)) }
+int pd_get_solver_sizes(pd_engine* e, long long* nnzA, long long* nnzL)
+{
+    if (!e || !e->e) return fail(PD_ERR_INVALID, "engine is NULL");
+    size_t a = 0, l = 0;
+    e->e->solverSizes(a, l);
+    if (nnzA) *nnzA = (long long)a;
+    if (nnzL) *nnzL = (long long)l;
+    return PD_OK;
+}
 int pd_get_solve_stats(pd_engine* e, float* err, int* pd_iters)
 {
     ENGINE_CALL(e->e->syncSolveStats(); if (err) *err = e->e->lastError(); if (pd_iters) *pd_iters = e->e->lastPdIterations())
@@ -537,6 +596,15 @@ int pd_dist_info(const pd_engine* e, int info[6])
     return PD_OK;
 }
 
+int pd_ccd_batch(int device, int n, const int* type, const uint32_t* verts, int num_verts, const float* X, const float* XTilde, float* toi, float* normals)
+{
+    PD_TRY
+    if (n <= 0 || num_verts <= 0 || !type || !verts || !X || !XTilde || !toi || !normals) return fail(PD_ERR_INVALID, "bad argument");
+    for (int i = 0; i < 4 * n; ++i) if (verts[i] >= (uint32_t)num_verts) return fail(PD_ERR_INVALID, "query names a vertex outside the arrays");
+    ccd_batch(device, n, type, verts, num_verts, X, XTilde, toi, normals);
+    return PD_OK;
+    PD_CATCH_INT
+}
 int pd_rotation_batch(int device, int rot_mode, int n, const float* F, float* R, int* used_fast)
 {
     PD_TRY

@@ -820,8 +820,10 @@ void build_rank_plan(const Layout& G, int world, int rank, RankPlan& P, bool tri
 
 bool dist_trim_from_env()
 {
+    // default ON since round 2 (same-box A/B on 2 GPUs: 3.21 -> 3.09-3.15 ms/step on grid70, redundant tets 6.0 % -> 1.5 %;
+    // profiles/r2_trim_ab_n2_grid70.txt); PD_DIST_TRIM=0 keeps whole boundary tiles (A/B runs, the plan tests' specification)
     const char* e = std::getenv("PD_DIST_TRIM");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
 }
 
 void extract_rank_layout(const Layout& G, const RankPlan& P, Layout& L)

@@ -8,8 +8,10 @@
 #include <cstring>
 #include <stdexcept>
 
+#include "collision.hpp"
 #include "pd_kernels.cuh"
 #include "pd_body_kernel.cuh"
+#include "pd_collision.cuh"
 #include "pd_solvers.cuh"
 
 namespace pdb200 {
@@ -96,15 +98,22 @@ struct Engine::Impl {
     // non-Jacobi global solvers (PCG, sparse Cholesky)
     bool solverReady = false, cholReady = false;
     CsrDev A{0, nullptr, nullptr, nullptr, nullptr};
-    CholDev C{0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    float4 *rhs = nullptr, *cgR = nullptr, *cgP = nullptr, *cgQ = nullptr, *xprev = nullptr, *cholY = nullptr;
-    int* cholReadyFlags = nullptr;
+    CholDev C{0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float4 *rhs = nullptr, *cgR = nullptr, *cgP = nullptr, *cgQ = nullptr, *xprev = nullptr, *cholY = nullptr, *cholZ = nullptr;
     int cholEpoch = 0;
     SolveState* solveState = nullptr;
     double* partials = nullptr;
-    int solveGrid = 0;
+    int solveGrid = 0, cholGrid = 0;
     size_t nnzA = 0, nnzL = 0;
     DistWait wait{nullptr, nullptr, nullptr, 0, 0x7fffffff, nullptr};
+    // mesh-mesh collision pass (pd_collision.cuh), built by the first step that asks for it
+    bool colReady = false;
+    ColMeshDev cm{};
+    uint2* colPairs = nullptr; unsigned int* colCount = nullptr; unsigned int colMaxPairs = 0;
+    unsigned long long *colVf = nullptr, *colEe = nullptr;
+    int* colWriter = nullptr; float* colTI = nullptr; float4* colNors = nullptr;
+    cudaEvent_t colEv[2] = {nullptr, nullptr};
+    long long colPairsLast = 0, colHitsLast = 0;
 };
 
 // give a dalloc'ed buffer back (re-prepared system matrix / factor after Reset)
@@ -133,8 +142,8 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
 {
     if (scene.numVerts <= 0 || scene.numTets <= 0) throw std::runtime_error("empty scene");
     if (opt.world < 1 || opt.rank < 0 || opt.rank >= opt.world) throw std::runtime_error("bad rank/world");
-    if (params_.handleCollision)
-        throw std::runtime_error("handleCollision=true (mesh-mesh BVH/CCD) is outside the PD hot path; set it to false");
+    if (params_.handleCollision && opt.world > 1)
+        throw std::runtime_error("handleCollision=true (mesh-mesh collision) needs the whole surface on one GPU: single-GPU engines only");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -145,7 +154,7 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     if (prop.major < 10)
         throw std::runtime_error("this build targets sm_100a (B200); found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor));
     numSms_ = prop.multiProcessorCount;
-    if (const char* e = std::getenv("PD_PDL")) usePdl_ = std::atoi(e) != 0;      // experiments: PD_PDL=1 turns programmatic dependent launch on
+    if (const char* e = std::getenv("PD_PDL")) { usePdl_ = std::atoi(e) != 0; pdlLate_ = std::atoi(e) == 2 ? 1 : 0; }      // experiments: PD_PDL=1 / 2
     pdlActive_ = usePdl_;
     CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
 
@@ -321,6 +330,7 @@ Engine::~Engine()
         for (cudaGraphExec_t g : d_->graphExec) if (g) cudaGraphExecDestroy(g);
         for (cudaEvent_t ev : d_->events) cudaEventDestroy(ev);
         if (d_->lockEvent) cudaEventDestroy(d_->lockEvent);
+        for (cudaEvent_t ev : d_->colEv) if (ev) cudaEventDestroy(ev);
         if (d_->callerEvent) cudaEventDestroy(d_->callerEvent);
         for (void* p : d_->ipcOpened) cudaIpcCloseMemHandle(p);
         for (void* p : d_->allocs) cudaFree(p);
@@ -336,9 +346,9 @@ void Engine::synchronize()
 
 void Engine::setParams(const SolverParams& p)
 {
-    if (p.handleCollision) throw std::runtime_error("handleCollision=true is outside the PD hot path");
+    if (p.handleCollision && opt_.world > 1) throw std::runtime_error("handleCollision=true (mesh-mesh collision) is for single-GPU engines");
     const SolverParams& o = params_;
-    const bool same = o.dt == p.dt && o.gravity == p.gravity && o.muN == p.muN && o.muT == p.muT && o.rho == p.rho &&
+    const bool same = o.handleCollision == p.handleCollision && o.dt == p.dt && o.gravity == p.gravity && o.muN == p.muN && o.muT == p.muT && o.rho == p.rho &&
                       o.tol == p.tol && o.numIterations == p.numIterations && o.globalSolver == p.globalSolver &&
                       o.pcgMaxIter == p.pcgMaxIter && o.pcgTol == p.pcgTol;
     params_ = p;
@@ -387,6 +397,7 @@ void Engine::launchLocal(const float4* q, bool jacobi, unsigned long long* prof,
 {
     Impl& d = *d_;
     DistWait w = d.wait;
+    w.pdlLate = pdlLate_;
     if (pushBuf >= 0 && opt_.world > 1) { w.nPush = d.nPush; w.peerQ = d.peerQ + (size_t)pushBuf * d.nNbr; }
 #define PD_LOCAL(RM, JAC) launch_pdl(k_local<RM, JAC>, dim3(localGrid_), dim3(TILE_T), LOCAL_SMEM_BYTES, stream_, pdlActive_, d.records, d.tileTab, L_.nTiles, d.vstage, d.vlist, q, d.b0, d.P, prof, w)
     if (prof) {
@@ -447,20 +458,135 @@ void Engine::enqueueIteration(int i, bool timed, size_t* ev)
         if (opt_.rotMode == 1) k_vertex_jacobi<false, true><<<vg, vb, 0, stream_>>>(nOwn_, cur, prev, next, dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
         else k_vertex_jacobi<true, true><<<vg, vb, 0, stream_>>>(nOwn_, cur, prev, next, dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
     }
-    else if (opt_.rotMode == 1) launch_pdl(k_vertex_jacobi<false>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
-    else launch_pdl(k_vertex_jacobi<true>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
+    else if (opt_.rotMode == 1) launch_pdl(k_vertex_jacobi<false>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc, pdlLate_);
+    else launch_pdl(k_vertex_jacobi<true>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc, pdlLate_);
     if (lockstep_) enqueuePush(next, in);
     ++phase_;
     rec();
 }
 
-void Engine::enqueueFinish()
+void Engine::enqueueFinish() { enqueueEnd(d_->q[(base_ + params_.numIterations) % 3]); }
+
+// updateVelPos, [mesh-mesh collision], X <- XTilde, fixed bodies (pdSolver.cu:206, 218-231)
+void Engine::enqueueEnd(const float4* qfinal)
 {
     Impl& d = *d_;
     const SolverParams& p = params_;
     const int vb = 256, vg = (nOwn_ + vb - 1) / vb;
-    if (dragActive_) k_finish<true><<<vg, vb, 0, stream_>>>(nOwn_, d.q[(base_ + p.numIterations) % 3], 1.0f / p.dt, d.X, d.XT, d.V, d.fb, p.muT, p.muN, d.more);
-    else k_finish<false><<<vg, vb, 0, stream_>>>(nOwn_, d.q[(base_ + p.numIterations) % 3], 1.0f / p.dt, d.X, d.XT, d.V, d.fb, p.muT, p.muN, nullptr);
+    const float dtInv = 1.0f / p.dt;
+    if (!p.handleCollision) {
+        if (dragActive_) k_finish<true><<<vg, vb, 0, stream_>>>(nOwn_, qfinal, dtInv, d.X, d.XT, d.V, d.fb, p.muT, p.muN, d.more);
+        else k_finish<false><<<vg, vb, 0, stream_>>>(nOwn_, qfinal, dtInv, d.X, d.XT, d.V, d.fb, p.muT, p.muN, nullptr);
+        return;
+    }
+    if (dragActive_) k_finish_velocity<true><<<vg, vb, 0, stream_>>>(nOwn_, qfinal, dtInv, d.XT, d.V, d.more);
+    else k_finish_velocity<false><<<vg, vb, 0, stream_>>>(nOwn_, qfinal, dtInv, d.XT, d.V, nullptr);
+    collisionPass();
+    k_fixed_bodies<<<vg, vb, 0, stream_>>>(nOwn_, d.XT, d.V, d.fb, p.muT, p.muN);
+}
+
+// ---------------------------------------------------------------- mesh-mesh collision (pd_collision.cuh)
+__global__ void k_col_reset(int nV, int nEdges, int nInternal, float* tI, int* writer, unsigned long long* vf, unsigned long long* ee, int* visit, unsigned int* count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nV) { tI[i] = 1.0f; writer[i] = 0; vf[i] = COL_EMPTY; }       // thrust::fill(tI, 1.0f), bvh.cu:173-174
+    if (i < nEdges) ee[i] = COL_EMPTY;
+    if (i < nInternal) visit[i] = 0;
+    if (i == 0) *count = 0u;
+}
+
+void Engine::prepareCollision()
+{
+    Impl& d = *d_;
+    if (d.colReady) return;
+    CollisionMesh M;
+    build_collision_mesh(scene_, M);
+    ColMeshDev& c = d.cm;
+    c.nTris = M.nTris; c.nEdges = M.nEdges; c.nInternal = M.nInternal; c.nBodies = M.nBodies; c.nV = nV_;
+    auto up = [&](const auto& v) {
+        using T = typename std::decay<decltype(v)>::type::value_type;
+        T* p = dalloc<T>(v.size());
+        if (!v.empty()) CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return p;
+    };
+    c.tri = up(M.tri); c.father = up(M.father); c.edge = up(M.edge); c.triEdge = up(M.triEdge);
+    c.left = up(M.left); c.right = up(M.right); c.parent = up(M.parent); c.bodyRoot = up(M.bodyRoot);
+    c.newOfOld = up(L_.vertNewOfOld);
+    c.boxMin = dalloc<float4>((size_t)M.nInternal + M.nTris); c.boxMax = dalloc<float4>((size_t)M.nInternal + M.nTris);
+    c.visit = dalloc<int>((size_t)M.nInternal);
+    d.colCount = dalloc<unsigned int>(1);
+    d.colMaxPairs = (unsigned int)std::max<size_t>(1u << 12, 4 * (size_t)M.nTris);      // (the reference starts its query buffer at 2^15 and doubles it)
+    d.colPairs = dalloc<uint2>(d.colMaxPairs);
+    d.colVf = dalloc<unsigned long long>((size_t)nV_); d.colEe = dalloc<unsigned long long>((size_t)M.nEdges);
+    d.colWriter = dalloc<int>((size_t)nV_); d.colTI = dalloc<float>((size_t)nV_); d.colNors = dalloc<float4>((size_t)nV_);
+    CUDA_CHECK(cudaMemset(d.colNors, 0, (size_t)nV_ * 16));
+    for (cudaEvent_t& ev : d.colEv) CUDA_CHECK(cudaEventCreate(&ev));
+    d.colReady = true;
+}
+
+// DetectCollision + CCDKernel (pdSolver.cu:218-225) on (X = the step's start, XTilde = its end, V).  One host
+// synchronisation per step (the pair count; the reference reads its query count back the same way, broadphase.cu:415-429).
+void Engine::collisionPass()
+{
+    Impl& d = *d_;
+    prepareCollision();
+    const ColMeshDev& c = d.cm;
+    const int tb = 128;
+    if (perf_) CUDA_CHECK(cudaEventRecord(d.colEv[0], stream_));
+    const int nReset = std::max(std::max(nV_, c.nEdges), std::max(c.nInternal, 1));
+    k_col_reset<<<(nReset + 255) / 256, 256, 0, stream_>>>(nV_, c.nEdges, c.nInternal, d.colTI, d.colWriter, d.colVf, d.colEe, c.visit, d.colCount);
+    unsigned int nPairs = 0;
+    if (c.nTris > 0) {
+        k_col_refit<<<(c.nTris + tb - 1) / tb, tb, 0, stream_>>>(c, d.X, d.XT);
+        for (;;) {
+            k_col_traverse<<<(c.nTris + tb - 1) / tb, tb, 0, stream_>>>(c, /*ignoreSelfCollision=*/1, d.colPairs, d.colCount, d.colMaxPairs);
+            CUDA_CHECK(cudaMemcpyAsync(&nPairs, d.colCount, 4, cudaMemcpyDeviceToHost, stream_));
+            CUDA_CHECK(cudaStreamSynchronize(stream_));
+            if (nPairs <= d.colMaxPairs) break;
+            // more overlapping pairs than the buffer holds: grow it and list them again (nothing has been modified yet)
+            dfree(d.colPairs, (size_t)d.colMaxPairs * sizeof(uint2));
+            while (d.colMaxPairs < nPairs) d.colMaxPairs *= 2;
+            d.colPairs = dalloc<uint2>(d.colMaxPairs);
+            CUDA_CHECK(cudaMemsetAsync(d.colCount, 0, 4, stream_));
+        }
+    }
+    d.colPairsLast = nPairs;
+    if (nPairs > 0) {       // BroadPhaseCCD returned queries: NarrowPhase + storeTi (bvh.cu:175-178)
+        const int grid = (int)std::min<size_t>((12 * (size_t)nPairs + tb - 1) / tb, (size_t)numSms_ * 16);
+        k_col_narrow<<<grid, tb, 0, stream_>>>(c, d.X, d.XT, d.colPairs, d.colCount, d.colMaxPairs, d.colVf, d.colEe);
+        const int nG = nV_ + c.nEdges;
+        k_col_rank<<<(nG + tb - 1) / tb, tb, 0, stream_>>>(c, d.colVf, d.colEe, d.colWriter);
+        k_col_store<<<(nG + tb - 1) / tb, tb, 0, stream_>>>(c, d.X, d.XT, d.colVf, d.colEe, d.colWriter, d.colTI, d.colNors);
+    }
+    k_col_apply<<<(nV_ + 255) / 256, 256, 0, stream_>>>(nV_, d.X, d.XT, d.V, d.colTI, d.colNors);
+    CUDA_CHECK(cudaGetLastError());
+    if (perf_) {
+        CUDA_CHECK(cudaEventRecord(d.colEv[1], stream_));
+        CUDA_CHECK(cudaEventSynchronize(d.colEv[1]));
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, d.colEv[0], d.colEv[1]));
+        perfc_.collisionMesh += ms;
+    }
+}
+
+// tI (1 = free, 0.5 = in a detected contact) and the contact normals of the last collision pass, caller's numbering
+void Engine::getCollision(float* tI, float* normals, long long* numPairs)
+{
+    CUDA_CHECK(cudaSetDevice(opt_.device));
+    Impl& d = *d_;
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    if (numPairs) *numPairs = d.colPairsLast;
+    std::vector<float> t((size_t)nV_, 1.0f);
+    std::vector<float4> n((size_t)nV_, make_float4(0.f, 0.f, 0.f, 0.f));
+    if (d.colReady) {
+        CUDA_CHECK(cudaMemcpy(t.data(), d.colTI, (size_t)nV_ * 4, cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(n.data(), d.colNors, (size_t)nV_ * 16, cudaMemcpyDeviceToHost));
+    }
+    for (int v = 0; v < nV_; ++v) {
+        const size_t g = L_.vertOrder[(size_t)v];
+        if (tI) tI[g] = t[(size_t)v];
+        if (normals) { normals[3 * g] = n[(size_t)v].x; normals[3 * g + 1] = n[(size_t)v].y; normals[3 * g + 2] = n[(size_t)v].z; }
+    }
 }
 
 // multi-GPU: boundary positions of buffer `bufIndex` -> the neighbours' ghost entries, then the flags
@@ -526,13 +652,31 @@ void Engine::step(int nSteps)
     Impl& d = *d_;
     if (params_.globalSolver != 0) {       // PCG-Jacobi / sparse Cholesky global step: plain launches, device-side early exit
         prepareSolver();
-        for (int s = 0; s < nSteps; ++s) enqueueStepSolver();
+        if (perf_) {        // local step (+ right-hand side) | global solve, bracketed by events; one host sync per step
+            const size_t need = 3 * (size_t)params_.numIterations + 2;
+            while (d.events.size() < need) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); d.events.push_back(e); }
+        }
+        for (int s = 0; s < nSteps; ++s) {
+            enqueueStepSolver(perf_);
+            if (perf_) {
+                CUDA_CHECK(cudaStreamSynchronize(stream_));
+                for (int i = 0; i < params_.numIterations; ++i) {
+                    float a = 0, b = 0;
+                    CUDA_CHECK(cudaEventElapsedTime(&a, d.events[3 * (size_t)i], d.events[3 * (size_t)i + 1]));
+                    CUDA_CHECK(cudaEventElapsedTime(&b, d.events[3 * (size_t)i + 1], d.events[3 * (size_t)i + 2]));
+                    perfc_.localStep += a; perfc_.globalStep += b;
+                }
+                float c = 0;
+                CUDA_CHECK(cudaEventElapsedTime(&c, d.events[3 * (size_t)params_.numIterations], d.events[3 * (size_t)params_.numIterations + 1]));
+                perfc_.collisionFixed += c;
+            }
+        }
         CUDA_CHECK(cudaGetLastError());
         perfc_.steps += nSteps;
         perfc_.kernelLaunches += (long long)nSteps * (4 + 3 * params_.numIterations);
         return;
     }
-    if (bodyKernel_ && !dragActive_) {      // small bodies: one CTA per body, the whole step in one launch (pd_body_kernel.cuh)
+    if (bodyKernel_ && !dragActive_ && !params_.handleCollision) {      // small bodies: one CTA per body, the whole step in one launch (pd_body_kernel.cuh)
         const SolverParams& p = params_;
         const float dtInv = 1.0f / p.dt, wdbc = 1e6f * (dtInv * dtInv);
         unsigned long long* perfNs = nullptr;
@@ -566,6 +710,7 @@ void Engine::step(int nSteps)
         const size_t need = 3 * (size_t)params_.numIterations + 2;
         while (d.events.size() < need) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); d.events.push_back(e); }
         for (int s = 0; s < nSteps; ++s) {
+            const float meshBefore = perfc_.collisionMesh;
             enqueueStep(true);
             CUDA_CHECK(cudaStreamSynchronize(stream_));
             size_t ev = 0;
@@ -578,9 +723,10 @@ void Engine::step(int nSteps)
             }
             float c = 0;
             CUDA_CHECK(cudaEventElapsedTime(&c, d.events[ev], d.events[ev + 1]));
-            perfc_.collisionFixed += c;
+            perfc_.collisionFixed += std::max(0.f, c - (perfc_.collisionMesh - meshBefore));      // (the bracket holds the mesh pass too)
         }
-    } else if (opt_.useGraph && !dragActive_) {     // (a drag moves its target every frame: plain launches)
+    } else if (opt_.useGraph && !dragActive_ && !params_.handleCollision) {     // (a drag moves its target every frame, the collision pass
+                                                                                 // reads its pair count back: plain launches)
         for (int s = 0; s < nSteps; ++s) {
             buildGraph();
             CUDA_CHECK(cudaGraphLaunch(d.graphExec[(opt_.world > 1) ? (int)(phase_ % 3) : 0], stream_));
@@ -599,7 +745,7 @@ float Engine::stepTimed(int nSteps)
 {
     CUDA_CHECK(cudaSetDevice(opt_.device));
     if (!ready_) prepare();
-    if (opt_.useGraph && !perf_ && !dragActive_ && !bodyKernel_ && params_.globalSolver == 0) buildGraph();
+    if (opt_.useGraph && !perf_ && !dragActive_ && !bodyKernel_ && !params_.handleCollision && params_.globalSolver == 0) buildGraph();
     cudaEvent_t a, b;
     CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
@@ -963,9 +1109,9 @@ void Engine::prepareSolver()
         d.nnzA = A.col.size();
         if (!d.rhs) {
             d.rhs = dalloc<float4>(nV_); d.cgR = dalloc<float4>(nV_); d.cgQ = dalloc<float4>(nV_);
-            d.xprev = dalloc<float4>(nV_); d.cholY = dalloc<float4>(nV_);
-            d.cholReadyFlags = dalloc<int>(nV_);
-            CUDA_CHECK(cudaMemset(d.cholReadyFlags, 0, (size_t)nV_ * 4));
+            d.xprev = dalloc<float4>(nV_); d.cholY = dalloc<float4>(nV_); d.cholZ = dalloc<float4>(nV_);
+            CUDA_CHECK(cudaMemset(d.cholY, 0, (size_t)nV_ * 16));        // tag 0 in every entry: nothing solved yet
+            CUDA_CHECK(cudaMemset(d.cholZ, 0, (size_t)nV_ * 16));
             d.solveState = dalloc<SolveState>(1);
             CUDA_CHECK(cudaMemset(d.solveState, 0, sizeof(SolveState)));
             int perSm = 0;
@@ -975,22 +1121,36 @@ void Engine::prepareSolver()
             perSm = std::min(perSm, perSmD);
             int perSm2 = 0;
             CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm2, k_chol_solve, SOLVE_THREADS, 0));
-            perSm = std::max(1, std::min(perSm, perSm2));
+            perSm = std::max(1, perSm);
             d.solveGrid = std::min(numSms_ * perSm, std::min(SOLVE_MAX_PARTIALS, (nOwn_ + SOLVE_THREADS - 1) / SOLVE_THREADS));
             d.solveGrid = std::max(d.solveGrid, 1);
-            d.partials = dalloc<double>(3 * (size_t)SOLVE_MAX_PARTIALS);
+            // the triangular solves run one WARP per row: as many resident warps as rows, up to the whole GPU
+            // (not more than 4 blocks per SM: warps beyond the rows that can make progress only poll)
+            d.cholGrid = std::max(1, std::min(numSms_ * std::min(4, std::max(1, perSm2)), std::min(SOLVE_MAX_PARTIALS, (nOwn_ + SOLVE_THREADS / 32 - 1) / (SOLVE_THREADS / 32))));
+            if (const char* e = std::getenv("PD_CHOL_BLOCKS_PER_SM")) d.cholGrid = std::max(1, std::min(numSms_ * std::max(1, std::atoi(e)), SOLVE_MAX_PARTIALS));
+            d.partials = dalloc<double>(2 * 3 * (size_t)SOLVE_MAX_PARTIALS);      // two alternating sets of slots (grid_sum3)
         }
         d.solverReady = true;
     }
     if (params_.globalSolver == 1 && !d.cholReady) {
         if (nV_ > 262144) throw std::runtime_error("the sparse Cholesky global step is the small-mesh path (<= 262144 vertices); use Jacobi or PCG");
+        // fill-reducing order first (geometric nested dissection on the rest positions, layout.cpp), then the factorisation
         CholFactor F;
-        cholesky_factor(hostA_, F);
+        std::vector<int> perm;
+        {
+            std::vector<float> xyz(3 * (size_t)nV_);
+            for (int v = 0; v < nV_; ++v)
+                for (int c = 0; c < 3; ++c) xyz[3 * (size_t)v + c] = scene_.X[3 * (size_t)L_.vertOrder[(size_t)v] + c];
+            nested_dissection_order(hostA_, xyz.data(), perm);
+            CsrMatrix Ap;
+            permute_symmetric(hostA_, perm, Ap);
+            cholesky_factor(Ap, F);
+        }
         if (d.C.lPtr) {
             CUDA_CHECK(cudaStreamSynchronize(stream_));
             dfree(d.C.lPtr, ((size_t)d.C.n + 1) * 4); dfree(d.C.lCol, d.nnzL * 4); dfree(d.C.lVal, d.nnzL * 4);
-            dfree(d.C.uPtr, ((size_t)d.C.n + 1) * 4); dfree(d.C.uCol, d.nnzL * 4); dfree(d.C.uVal, d.nnzL * 4);
-            d.C = CholDev{0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+            dfree(d.C.uPtr, ((size_t)d.C.n + 1) * 4); dfree(d.C.uCol, d.nnzL * 4); dfree(d.C.uVal, d.nnzL * 4); dfree(d.C.perm, (size_t)d.C.n * 4);
+            d.C = CholDev{0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         }
         int* lp = dalloc<int>(F.lPtr.size()); int* lc = dalloc<int>(F.lCol.size()); float* lv = dalloc<float>(F.lVal.size());
         int* up = dalloc<int>(F.uPtr.size()); int* uc = dalloc<int>(F.uCol.size()); float* uv = dalloc<float>(F.uVal.size());
@@ -1000,7 +1160,9 @@ void Engine::prepareSolver()
         CUDA_CHECK(cudaMemcpy(up, F.uPtr.data(), F.uPtr.size() * 4, cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaMemcpy(uc, F.uCol.data(), F.uCol.size() * 4, cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaMemcpy(uv, F.uVal.data(), F.uVal.size() * 4, cudaMemcpyHostToDevice));
-        d.C = CholDev{nV_, lp, lc, lv, up, uc, uv};
+        int* pm = dalloc<int>(perm.size());
+        CUDA_CHECK(cudaMemcpy(pm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice));
+        d.C = CholDev{nV_, lp, lc, lv, up, uc, uv, pm};
         d.nnzL = F.lCol.size();
         d.cholReady = true;
     }
@@ -1009,7 +1171,7 @@ void Engine::prepareSolver()
 // One PdSolver::Update in the direct / CG modes (pdSolver.cu:141-208 with isJacobi == false): the iterate lives in
 // q[0]; every PD iteration = local step (H = w R DmInv^T G) -> right-hand side -> ONE cooperative solve kernel that
 // also evaluates computeError and raises the device-side `done` flag; later iterations of the step then return at once.
-void Engine::enqueueStepSolver()
+void Engine::enqueueStepSolver(bool timed)
 {
     Impl& d = *d_;
     const SolverParams& p = params_;
@@ -1028,7 +1190,9 @@ void Engine::enqueueStepSolver()
     DistSolve ds{};
     if (dist) ds = DistSolve{opt_.world, opt_.rank, d.nNbr, d.nPush, scene_.numVerts, d.nbrRanks, d.pushSrc, d.pushDst, d.pushNbr,
                              d.peerP, d.peerPFlag, d.pflags, d.peerRed, d.red, d.solveSeq, d.status};
+    auto rec = [&](size_t k) { if (timed) CUDA_CHECK(cudaEventRecord(d.events[k], stream_)); };
     for (int i = 0; i < p.numIterations; ++i) {
+        rec(3 * (size_t)i);
         launchLocal(d.q[0], false);
         if (dragActive_) {
             if (opt_.rotMode == 1) k_vertex_rhs<false, true><<<vg, vb, 0, stream_>>>(n, d.dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, wdbc, d.rhs, dr);
@@ -1036,6 +1200,7 @@ void Engine::enqueueStepSolver()
         }
         else if (opt_.rotMode == 1) k_vertex_rhs<false><<<vg, vb, 0, stream_>>>(n, d.dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, wdbc, d.rhs, dr);
         else k_vertex_rhs<true><<<vg, vb, 0, stream_>>>(n, d.dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, wdbc, d.rhs, dr);
+        rec(3 * (size_t)i + 1);
         if (p.globalSolver == 2) {
             const float4* b = d.rhs; float4 *x = d.q[0], *r = d.cgR, *pp = d.cgP, *qq = d.cgQ, *xp = d.xprev;
             int maxIter = p.pcgMaxIter; float cgTol = p.pcgTol, pdTol = p.tol;
@@ -1045,17 +1210,21 @@ void Engine::enqueueStepSolver()
                                                    dim3(d.solveGrid), dim3(SOLVE_THREADS), args, 0, stream_));
             enqueuePush(d.q[0], 0);         // multi-GPU: the new iterate's boundary entries -> the neighbours' ghosts
         } else {
-            const float4* b = d.rhs; float4 *x = d.q[0], *y = d.cholY, *xp = d.xprev; int* rdy = d.cholReadyFlags;
-            int tag = d.cholEpoch++; float pdTol = p.tol;
+            const float4* b = d.rhs; float4 *x = d.q[0], *y = d.cholY, *z = d.cholZ, *xp = d.xprev;
+            int tag = d.cholEpoch; d.cholEpoch = (d.cholEpoch + 1) % 0x3fffffff; float pdTol = p.tol;
             SolveState* st = d.solveState; double* part = d.partials;
-            void* args[] = {&d.C, &b, &x, &y, &xp, &rdy, &tag, &pdTol, &st, &part};
-            CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(d.solveGrid), dim3(SOLVE_THREADS), args, 0, stream_));
+            void* args[] = {&d.C, &b, &x, &y, &z, &xp, &tag, &pdTol, &st, &part};
+            CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(d.cholGrid), dim3(SOLVE_THREADS), args, 0, stream_));
         }
+        rec(3 * (size_t)i + 2);
     }
-    if (dragActive_) k_finish<true><<<vg, vb, 0, stream_>>>(n, d.q[0], dtInv, d.X, d.XT, d.V, d.fb, p.muT, p.muN, d.more);
-    else k_finish<false><<<vg, vb, 0, stream_>>>(n, d.q[0], dtInv, d.X, d.XT, d.V, d.fb, p.muT, p.muN, nullptr);
+    rec(3 * (size_t)p.numIterations);
+    enqueueEnd(d.q[0]);
+    rec(3 * (size_t)p.numIterations + 1);
     pdlActive_ = usePdl_;
 }
+
+void Engine::solverSizes(size_t& nnzA, size_t& nnzL) const { nnzA = d_->nnzA; nnzL = d_->nnzL; }
 
 const CsrMatrix& Engine::systemMatrix()
 {
@@ -1256,6 +1425,35 @@ void Engine::profileLocal(unsigned long long* out)
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     CUDA_CHECK(cudaMemcpy(out, dprof, 64ull * localGrid_, cudaMemcpyDeviceToHost));
     cudaFree(dprof);
+}
+
+// test hook: the collision pass's continuous-collision test on a batch of queries (host pointers)
+__global__ void k_ccd_batch(int n, const int* __restrict__ type, const uint32_t* __restrict__ v, const float4* __restrict__ X, const float4* __restrict__ XT,
+                            float* __restrict__ toi, float* __restrict__ nor)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ccd::V3 nn;
+    toi[i] = ccd::collision_test(type[i] == 2, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], X, XT, nn);
+    nor[3 * i] = nn.x; nor[3 * i + 1] = nn.y; nor[3 * i + 2] = nn.z;
+}
+void ccd_batch(int device, int n, const int* type, const uint32_t* verts, int nV, const float* X, const float* XT, float* toi, float* normals)
+{
+    CUDA_CHECK(cudaSetDevice(device));
+    std::vector<float4> x4((size_t)nV), t4((size_t)nV);
+    for (int v = 0; v < nV; ++v) {
+        x4[(size_t)v] = make_float4(X[3 * v], X[3 * v + 1], X[3 * v + 2], 0.f);
+        t4[(size_t)v] = make_float4(XT[3 * v], XT[3 * v + 1], XT[3 * v + 2], 0.f);
+    }
+    int* dT; uint32_t* dV; float4 *dX, *dXT; float *dToi, *dN;
+    CUDA_CHECK(cudaMalloc(&dT, 4ull * n)); CUDA_CHECK(cudaMalloc(&dV, 16ull * n)); CUDA_CHECK(cudaMalloc(&dX, 16ull * nV)); CUDA_CHECK(cudaMalloc(&dXT, 16ull * nV));
+    CUDA_CHECK(cudaMalloc(&dToi, 4ull * n)); CUDA_CHECK(cudaMalloc(&dN, 12ull * n));
+    CUDA_CHECK(cudaMemcpy(dT, type, 4ull * n, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(dV, verts, 16ull * n, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(dX, x4.data(), 16ull * nV, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(dXT, t4.data(), 16ull * nV, cudaMemcpyHostToDevice));
+    k_ccd_batch<<<(n + 127) / 128, 128>>>(n, dT, dV, dX, dXT, dToi, dN);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpy(toi, dToi, 4ull * n, cudaMemcpyDeviceToHost)); CUDA_CHECK(cudaMemcpy(normals, dN, 12ull * n, cudaMemcpyDeviceToHost));
+    cudaFree(dT); cudaFree(dV); cudaFree(dX); cudaFree(dXT); cudaFree(dToi); cudaFree(dN);
 }
 
 void rotation_batch(int device, int rotMode, int n, const float* F, float* R, int* usedFast)

@@ -95,7 +95,9 @@ public:
     void getSetup(float* matrixDiag, float* massDt2, float* DmInv, float* V0);
     // launch geometry, for the bench's launch count / roofline bookkeeping
     int localGrid() const { return localGrid_; }
-    int rotMode() const { return opt_.rotMode; }      // the effective mode (options.rotMode < 0 = auto is resolved in the ctor)
+    int rotMode() const { return opt_.rotMode; }
+    void solverSizes(size_t& nnzA, size_t& nnzL) const;
+    void getCollision(float* tI, float* normals, long long* numPairs);      // last mesh-mesh collision pass (host arrays, caller numbering)      // the effective mode (options.rotMode < 0 = auto is resolved in the ctor)
     size_t deviceBytes() const { return devBytes_; }
     size_t tileStreamBytes() const { return L_.records.size(); }
     cudaStream_t stream() const { return stream_; }
@@ -110,10 +112,13 @@ private:
     void buildGraph();
     void enqueueStep(bool timed);
     void prepareSolver();
-    void enqueueStepSolver();
+    void enqueueStepSolver(bool timed = false);
     void enqueuePredict();
     void enqueueIteration(int i, bool timed, size_t* ev);
     void enqueueFinish();
+    void enqueueEnd(const float4* qfinal);
+    void prepareCollision();
+    void collisionPass();
     void enqueuePush(const float4* q, int bufIndex);
     void setPeers(const std::vector<uint8_t*>& peerBase);
     float* qbuf(int k) const;
@@ -139,6 +144,7 @@ private:
     EngineOptions opt_;
     bool ready_ = false, perf_ = false, graphValid_ = false;
     bool pdlActive_ = false;
+    int pdlLate_ = 0;         // PD_PDL=2: the dependents are released at the END of every CTA's work instead of at its start
     bool usePdl_ = false;     // programmatic dependent launch of the per-iteration kernels (pd_kernels.cuh: pdl_wait); measured SLOWER
                               // on B200 (grid139: 42.0 vs 36.9 ms/step, batch64: 2.68 vs 2.23), so it stays an opt-in experiment (PD_PDL=1)
     float dt2Prepared_ = 0.f;
@@ -155,5 +161,7 @@ private:
 
 // test hook: corotation() of n row-major 3x3 matrices on `device` (host pointers)
 void rotation_batch(int device, int rotMode, int n, const float* F, float* R, int* usedFast);
+// test hook: ccd::collision_test (pd_collision.cuh) on n queries; type 1 = vertex-face, 2 = edge-edge; verts 4 ids per query
+void ccd_batch(int device, int n, const int* type, const uint32_t* verts, int nV, const float* X, const float* XT, float* toi, float* normals);
 
 }  // namespace pdb200

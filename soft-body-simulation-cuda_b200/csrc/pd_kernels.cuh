@@ -139,6 +139,9 @@ struct DistWait {
     float4* const* peerQ;              // [nNbr]: the neighbours' copies of the buffer this launch reads
     unsigned long long* const* peerFlag;   // [nNbr]: this rank's entry in the neighbours' flag arrays
     unsigned int* ticket;
+    // programmatic dependent launch (PD_PDL): 0 / 1 = the successor may be scheduled as soon as every CTA has STARTED (measured
+    // slower: its CTAs take SM slots from this kernel's), 2 = only once every CTA has finished its tiles (hides the launch latency)
+    int pdlLate;
 };
 constexpr long long DIST_WAIT_LIMIT_CYCLES = 20000000000ll;    // ~10 s: a hung peer must not hang this GPU
 
@@ -562,7 +565,7 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
     load_rec(__ldg(meta_of(0)), mwA >> 18, r0, r1, r2);
     // from here on the kernel reads positions written by the previous launch in the stream (and later overwrites
     // the slots that launch reads)
-    pdl_launch_dependents();
+    if (dw.pdlLate == 0) pdl_launch_dependents();
     pdl_wait();
     if (dw.nNbr > 0) {
         // this rank's push count so far (read before this CTA's ticket, hence before the last CTA bumps it), plus this
@@ -648,6 +651,7 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
         load_groups_next(it + 2);
         load_rec_entry(it + 2);
     }
+    if (dw.pdlLate) pdl_launch_dependents();
     if (PROF && tid == 0) {
 #pragma unroll
         for (int i = 0; i < 7; ++i) prof[8 * blockIdx.x + i] = (unsigned long long)acc[i];
@@ -710,10 +714,10 @@ __global__ void __launch_bounds__(256, PD_VERTEX_MINBLOCKS) k_vertex_jacobi(int 
                                 float4* __restrict__ qnext, const float4* __restrict__ X0 /* DBCX */, const float4* __restrict__ b0,
                                 const float2* __restrict__ cc, const uint32_t* __restrict__ vslotPtr,
                                 const uint32_t* __restrict__ vslot, const float4* __restrict__ P,
-                                float omega, float wdbc)
+                                float omega, float wdbc, int pdlLate = 0)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    pdl_launch_dependents();
+    if (pdlLate == 0) pdl_launch_dependents();
     pdl_wait();              // the slots (and, multi-GPU, the ticket) come from the local kernel just before
     if (v < nV) {
         const float2 c2 = cc[v];
@@ -741,6 +745,7 @@ __global__ void __launch_bounds__(256, PD_VERTEX_MINBLOCKS) k_vertex_jacobi(int 
         const float4 out = make_float4(nx, ny, nz, 0.f);
         qnext[v] = out;
     }
+    if (pdlLate) pdl_launch_dependents();
 }
 
 // right-hand side for the direct / CG global solves: b = c*s_old + sum of partials (R, not R-F)
@@ -787,14 +792,15 @@ __device__ __forceinline__ void fb_respond(float3& vel, const float3 n, float kf
     vel.z = __fmaf_rn(vT.z, a, -__fmul_rn(vN.z, muN));
 }
 
-// one vertex of the end of step: q = the final iterate, xt = XTilde of the previous step
-__device__ __forceinline__ void finish_vertex(const float4 q, const float4 xt, float dtInv, bool dragged, const DevFixedBodies& fb, float muT, float muN,
-                                              float4* __restrict__ Xout, float4* __restrict__ XTout, float4* __restrict__ Vout)
+// updateVelPos (pdUtil.cu:180-193): q = the final iterate, xt = XTilde of the previous step
+__device__ __forceinline__ float3 finish_velocity(const float4 q, const float4 xt, float dtInv, bool dragged)
 {
-    float3 vel = make_float3(__fmul_rn(__fsub_rn(q.x, xt.x), dtInv), __fmul_rn(__fsub_rn(q.y, xt.y), dtInv), __fmul_rn(__fsub_rn(q.z, xt.z), dtInv));
-    if (dragged) vel = make_float3(0.f, 0.f, 0.f);      // updateVelPos, pdUtil.cu:187-188
-    float3 x = make_float3(q.x, q.y, q.z);
-    *Xout = make_float4(x.x, x.y, x.z, 0.f);      // X keeps the un-projected position
+    if (dragged) return make_float3(0.f, 0.f, 0.f);      // pdUtil.cu:187-188
+    return make_float3(__fmul_rn(__fsub_rn(q.x, xt.x), dtInv), __fmul_rn(__fsub_rn(q.y, xt.y), dtInv), __fmul_rn(__fsub_rn(q.z, xt.z), dtInv));
+}
+// FixedBodyData::HandleCollisions on one vertex (fixedBodyData.cu:67-148): spheres, planes, cylinders in that order
+__device__ __forceinline__ void fixed_body_response(float3& x, float3& vel, const DevFixedBodies& fb, float muT, float muN)
+{
     const float kf = __fmul_rn(__fadd_rn(muN, 1.f), muT);
     for (int j = 0; j < fb.nSpheres; ++j) {
         const float* s = fb.spheres + 4 * j;
@@ -835,6 +841,16 @@ __device__ __forceinline__ void finish_vertex(const float4 q, const float4 xt, f
             fb_respond(vel, n, kf, muN);
         }
     }
+}
+// one vertex of the end of step without mesh-mesh collision: velocity, X <- XTilde (pdSolver.cu:227; X keeps the un-projected
+// position), fixed bodies on (XTilde, V)
+__device__ __forceinline__ void finish_vertex(const float4 q, const float4 xt, float dtInv, bool dragged, const DevFixedBodies& fb, float muT, float muN,
+                                              float4* __restrict__ Xout, float4* __restrict__ XTout, float4* __restrict__ Vout)
+{
+    float3 vel = finish_velocity(q, xt, dtInv, dragged);
+    float3 x = make_float3(q.x, q.y, q.z);
+    *Xout = make_float4(x.x, x.y, x.z, 0.f);
+    fixed_body_response(x, vel, fb, muT, muN);
     *XTout = make_float4(x.x, x.y, x.z, 0.f);
     *Vout = make_float4(vel.x, vel.y, vel.z, 0.f);
 }
@@ -847,6 +863,31 @@ __global__ void k_finish(int nV, const float4* __restrict__ qfinal, float dtInv,
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nV) return;
     finish_vertex(qfinal[v], XTilde[v], dtInv, DRAG && more[v] > 0.f, fb, muT, muN, &X[v], &XTilde[v], &V[v]);
+}
+
+// The same end of step around the mesh-mesh collision pass (SolverParams::handleCollision, pdSolver.cu:218-231):
+// k_finish_velocity (updateVelPos: V, XTilde <- q; X still holds the step's start), the pass of pd_collision.cuh on
+// (X, XTilde, V), then k_fixed_bodies.
+template <bool DRAG>
+__global__ void k_finish_velocity(int nV, const float4* __restrict__ qfinal, float dtInv, float4* __restrict__ XTilde, float4* __restrict__ V,
+                                  const float* __restrict__ more)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nV) return;
+    const float4 q = qfinal[v];
+    const float3 vel = finish_velocity(q, XTilde[v], dtInv, DRAG && more[v] > 0.f);
+    XTilde[v] = make_float4(q.x, q.y, q.z, 0.f);
+    V[v] = make_float4(vel.x, vel.y, vel.z, 0.f);
+}
+__global__ void k_fixed_bodies(int nV, float4* __restrict__ XTilde, float4* __restrict__ V, DevFixedBodies fb, float muT, float muN)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nV) return;
+    const float4 xt = XTilde[v], vv = V[v];
+    float3 x = make_float3(xt.x, xt.y, xt.z), vel = make_float3(vv.x, vv.y, vv.z);
+    fixed_body_response(x, vel, fb, muT, muN);
+    XTilde[v] = make_float4(x.x, x.y, x.z, 0.f);
+    V[v] = make_float4(vel.x, vel.y, vel.z, 0.f);
 }
 
 // ------------------------------------------------------------------ layout conversion

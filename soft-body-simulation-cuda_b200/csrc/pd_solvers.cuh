@@ -37,9 +37,13 @@ constexpr int SOLVE_MAX_PARTIALS = 2048;       // >= grid size of the cooperativ
 
 // Deterministic grid-wide sum of up to three doubles per thread: warp shuffle -> block -> one slot per block ->
 // grid.sync -> every block adds the slots in the same fixed order.  Returns the sums in out[0..2].
-__device__ __forceinline__ void grid_sum3(cg::grid_group& grid, double a, double b, double c, double* partials /* 3 * gridDim */,
-                                          double* sh /* 3 * 8 + 3 doubles of shared memory */, double out[3])
+// ONE grid-wide synchronisation per reduction: consecutive reductions alternate between two sets of slots (`flip`, a
+// per-thread counter every thread of the grid advances alike), and a block can only reach the synchronisation of reduction
+// k + 1 after it has read the slots of reduction k, so set k & 1 is free again when reduction k + 2 writes it.
+__device__ __forceinline__ void grid_sum3(cg::grid_group& grid, double a, double b, double c, double* partials /* 2 x 3 * SOLVE_MAX_PARTIALS */,
+                                          double* sh /* 3 * 8 + 3 doubles of shared memory */, double out[3], unsigned& flip)
 {
+    partials += (flip++ & 1u) * 3u * (unsigned)SOLVE_MAX_PARTIALS;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a += __shfl_down_sync(0xffffffffu, a, o);
@@ -68,7 +72,7 @@ __device__ __forceinline__ void grid_sum3(cg::grid_group& grid, double a, double
     }
     __syncthreads();
     out[0] = sh[24]; out[1] = sh[25]; out[2] = sh[26];
-    grid.sync();          // the partial slots may be overwritten by the next reduction
+    __syncthreads();      // sh is reused by the next reduction
 }
 
 // ------------------------------------------------------------------ multi-GPU PCG
@@ -145,9 +149,9 @@ __device__ __forceinline__ void dist_allreduce3(const DistSolve& D, unsigned lon
 
 template <bool DIST>
 __device__ __forceinline__ void solve_sum3(cg::grid_group& grid, const DistSolve& D, unsigned long long& rSeq, double a, double b, double c,
-                                           double* partials, double* sh, double out[3])
+                                           double* partials, double* sh, double out[3], unsigned& flip)
 {
-    grid_sum3(grid, a, b, c, partials, sh, out);
+    grid_sum3(grid, a, b, c, partials, sh, out, flip);
     if (DIST) { ++rSeq; dist_allreduce3(D, rSeq, sh, out); }
 }
 
@@ -177,7 +181,17 @@ __device__ __forceinline__ float4 spmv_row(const CsrDev& A, int v, const float4*
 {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     const int e1 = A.rowPtr[v + 1];
-    for (int e = A.rowPtr[v]; e < e1; ++e) {
+    int e = A.rowPtr[v];
+    for (; e + 4 <= e1; e += 4) {       // four gathers in flight; the sum keeps its ascending-column order
+        const int c0 = A.col[e], c1 = A.col[e + 1], c2 = A.col[e + 2], c3 = A.col[e + 3];
+        const float4 x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
+        const float v0 = A.val[e], v1 = A.val[e + 1], v2 = A.val[e + 2], v3 = A.val[e + 3];
+        a0 = __fadd_rn(a0, __fmul_rn(v0, x0.x)); a1 = __fadd_rn(a1, __fmul_rn(v0, x0.y)); a2 = __fadd_rn(a2, __fmul_rn(v0, x0.z));
+        a0 = __fadd_rn(a0, __fmul_rn(v1, x1.x)); a1 = __fadd_rn(a1, __fmul_rn(v1, x1.y)); a2 = __fadd_rn(a2, __fmul_rn(v1, x1.z));
+        a0 = __fadd_rn(a0, __fmul_rn(v2, x2.x)); a1 = __fadd_rn(a1, __fmul_rn(v2, x2.y)); a2 = __fadd_rn(a2, __fmul_rn(v2, x2.z));
+        a0 = __fadd_rn(a0, __fmul_rn(v3, x3.x)); a1 = __fadd_rn(a1, __fmul_rn(v3, x3.y)); a2 = __fadd_rn(a2, __fmul_rn(v3, x3.z));
+    }
+    for (; e < e1; ++e) {
         const float a = A.val[e];
         const float4 xc = x[A.col[e]];
         a0 = __fadd_rn(a0, __fmul_rn(a, xc.x)); a1 = __fadd_rn(a1, __fmul_rn(a, xc.y)); a2 = __fadd_rn(a2, __fmul_rn(a, xc.z));
@@ -188,7 +202,7 @@ __device__ __forceinline__ float4 spmv_row(const CsrDev& A, int v, const float4*
 // computeError + prev = x, fused into the tail of both solve kernels (pdSolver.cu:186-192,243-253)
 template <bool DIST>
 __device__ __forceinline__ void finish_pd_iteration(cg::grid_group& grid, int n, const float4* x, float4* xprev, float tol, SolveState* st,
-                                                    int innerIters, double* partials, double* sh, const DistSolve& D, unsigned long long& rSeq)
+                                                    int innerIters, double* partials, double* sh, const DistSolve& D, unsigned long long& rSeq, unsigned& flip)
 {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
     double acc = 0;
@@ -199,7 +213,7 @@ __device__ __forceinline__ void finish_pd_iteration(cg::grid_group& grid, int n,
         xprev[v] = b;
     }
     double s[3];
-    solve_sum3<DIST>(grid, D, rSeq, acc, 0.0, 0.0, partials, sh, s);
+    solve_sum3<DIST>(grid, D, rSeq, acc, 0.0, 0.0, partials, sh, s, flip);
     if (gtid == 0) {
         const float err = (float)(s[0] / (3.0 * (double)(DIST ? D.nGlobal : n)));
         st->err = err;
@@ -214,7 +228,10 @@ __device__ __forceinline__ void finish_pd_iteration(cg::grid_group& grid, int n,
 //   p = z + (rho/rho_prev) p; q = A p; alpha = rho / (p.q); x += alpha p; r -= alpha q.
 // Dots accumulate in double and are rounded to float where the reference holds a float (cublasSdot results);
 // vector updates use the same unfused multiply-then-add as the oracle (oracle/pd_oracle.c:pcg_solve).
-// Three grid-wide synchronisations per CG iteration (p update | SpMV + p.q | x, r update + r.r, r.z).
+// Three grid-wide synchronisations per CG iteration (p update | SpMV + p.q | x, r update + r.r, r.z): one per reduction
+// (alternating partial slots) and one between the direction update and the product.  Measured and rejected on a B200:
+// recomputing p = z + beta p_old inside the product (one synchronisation fewer, three gathers per non-zero instead of one:
+// 30.0 vs 30.4 us per CG iteration on the 55^3 grid -- the gathers' L2 traffic is what bounds the product).
 // DIST: A holds this rank's rows (n = owned vertices; columns index the rank's local vertex array, ghosts included);
 // x and p carry ghost entries -- x's are current on entry (the engine's position halo), p's are exchanged here.
 template <bool DIST>
@@ -228,6 +245,7 @@ k_pcg_solve(CsrDev A, const float4* __restrict__ b, float4* x, float4* __restric
     const int n = A.n, gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
     unsigned long long pSeq = 0, rSeq = 0;
     if (DIST) { pSeq = D.seq[0]; rSeq = D.seq[1]; }
+    unsigned flip = 0;
     double s[3];
     // r = b - A x ; rr = r.r ; rz = r.(D^-1 r)
     double arr = 0, arz = 0;
@@ -239,7 +257,7 @@ k_pcg_solve(CsrDev A, const float4* __restrict__ b, float4* x, float4* __restric
         arr += (double)rv.x * rv.x + (double)rv.y * rv.y + (double)rv.z * rv.z;
         arz += (double)rv.x * (double)__fmul_rn(rv.x, id) + (double)rv.y * (double)__fmul_rn(rv.y, id) + (double)rv.z * (double)__fmul_rn(rv.z, id);
     }
-    solve_sum3<DIST>(grid, D, rSeq, arr, arz, 0.0, partials, sh, s);
+    solve_sum3<DIST>(grid, D, rSeq, arr, arz, 0.0, partials, sh, s, flip);
     float rho = (float)s[1], rhoPrev = 0.f;
     float rn = sqrtf((float)s[0]);
     int k = 0;
@@ -247,30 +265,33 @@ k_pcg_solve(CsrDev A, const float4* __restrict__ b, float4* x, float4* __restric
         if (rn < cgTol) break;
         if (fabsf(rho) < 1e-15f) break;
         const float beta = (k == 0) ? 0.f : __fdiv_rn(rho, rhoPrev);
-        for (int v = gtid; v < n; v += gstride) {       // p = z + beta p   (k == 0: p = z)
-            const float4 rv = r[v];
-            const float id = A.invDiag[v];
-            const float zx = __fmul_rn(rv.x, id), zy = __fmul_rn(rv.y, id), zz = __fmul_rn(rv.z, id);
-            float4 pv = make_float4(zx, zy, zz, 0.f);
-            if (k > 0) {
-                const float4 po = p[v];
-                pv.x = __fadd_rn(__fmul_rn(beta, po.x), zx); pv.y = __fadd_rn(__fmul_rn(beta, po.y), zy); pv.z = __fadd_rn(__fmul_rn(beta, po.z), zz);
-            }
-            p[v] = pv;
-        }
-        grid.sync();
-        if (DIST) dist_push_p(grid, D, pSeq, p);
         double apq = 0;
-        for (int v = gtid; v < n; v += gstride) {       // q = A p ; p.q
-            const float4 qv = spmv_row(A, v, p), pv = p[v];
-            q[v] = qv;
-            apq += (double)pv.x * qv.x + (double)pv.y * qv.y + (double)pv.z * qv.z;
+        {
+            for (int v = gtid; v < n; v += gstride) {       // p = z + beta p   (k == 0: p = z)
+                const float4 rv = r[v];
+                const float id = A.invDiag[v];
+                const float zx = __fmul_rn(rv.x, id), zy = __fmul_rn(rv.y, id), zz = __fmul_rn(rv.z, id);
+                float4 pv = make_float4(zx, zy, zz, 0.f);
+                if (k > 0) {
+                    const float4 po = p[v];
+                    pv.x = __fadd_rn(__fmul_rn(beta, po.x), zx); pv.y = __fadd_rn(__fmul_rn(beta, po.y), zy); pv.z = __fadd_rn(__fmul_rn(beta, po.z), zz);
+                }
+                p[v] = pv;
+            }
+            grid.sync();
+            if (DIST) dist_push_p(grid, D, pSeq, p);
+            for (int v = gtid; v < n; v += gstride) {       // q = A p ; p.q
+                const float4 qv = spmv_row(A, v, p), pv = p[v];
+                q[v] = qv;
+                apq += (double)pv.x * qv.x + (double)pv.y * qv.y + (double)pv.z * qv.z;
+            }
         }
-        solve_sum3<DIST>(grid, D, rSeq, apq, 0.0, 0.0, partials, sh, s);
+        solve_sum3<DIST>(grid, D, rSeq, apq, 0.0, 0.0, partials, sh, s, flip);
         const float alpha = __fdiv_rn(rho, (float)s[0]);
         arr = 0; arz = 0;
+        const float4* pCur = p;
         for (int v = gtid; v < n; v += gstride) {       // x += alpha p ; r -= alpha q ; r.r ; r.z
-            const float4 pv = p[v], qv = q[v];
+            const float4 pv = pCur[v], qv = q[v];
             float4 xv = x[v], rv = r[v];
             xv.x = __fadd_rn(xv.x, __fmul_rn(alpha, pv.x)); xv.y = __fadd_rn(xv.y, __fmul_rn(alpha, pv.y)); xv.z = __fadd_rn(xv.z, __fmul_rn(alpha, pv.z));
             rv.x = __fsub_rn(rv.x, __fmul_rn(alpha, qv.x)); rv.y = __fsub_rn(rv.y, __fmul_rn(alpha, qv.y)); rv.z = __fsub_rn(rv.z, __fmul_rn(alpha, qv.z));
@@ -279,85 +300,133 @@ k_pcg_solve(CsrDev A, const float4* __restrict__ b, float4* x, float4* __restric
             arr += (double)rv.x * rv.x + (double)rv.y * rv.y + (double)rv.z * rv.z;
             arz += (double)rv.x * (double)__fmul_rn(rv.x, id) + (double)rv.y * (double)__fmul_rn(rv.y, id) + (double)rv.z * (double)__fmul_rn(rv.z, id);
         }
-        solve_sum3<DIST>(grid, D, rSeq, arr, arz, 0.0, partials, sh, s);
+        solve_sum3<DIST>(grid, D, rSeq, arr, arz, 0.0, partials, sh, s, flip);
         rhoPrev = rho;
         rho = (float)s[1];
         rn = sqrtf((float)s[0]);
     }
-    finish_pd_iteration<DIST>(grid, n, x, xprev, pdTol, st, k, partials, sh, D, rSeq);
+    finish_pd_iteration<DIST>(grid, n, x, xprev, pdTol, st, k, partials, sh, D, rSeq, flip);
     if (DIST && gtid == 0) { D.seq[0] = pSeq; D.seq[1] = rSeq; }
 }
 
 // ------------------------------------------------------------------ prefactored sparse Cholesky solve
-// A^ = L L^T was factored once on the host (pd_engine.cu:factorize; the reference does the same inside
-// SolverPrepare with cusolverSpXcsrcholFactor / Eigen::SimplicialCholesky).  Per PD iteration: L y = b, L^T x = y for
-// the three right-hand sides, as a "synchronisation-free" sparse triangular solve: one thread per row, every row
-// waits for the rows it depends on through a ready counter in global memory.  The kernel is launched
-// cooperatively, so every row's thread is resident and the ascending (descending for L^T) dependency order
-// guarantees progress.  L is stored by rows (CSR, diagonal last) and L^T by rows as well (CSR, diagonal first).
+// P A^ P^T = L L^T was factored once on the host (pd_engine.cu:prepareSolver: geometric nested-dissection ordering, then
+// layout.cpp:cholesky_factor; the reference does the same inside SolverPrepare with cusolverSpXcsrcholAnalysis / Factor or
+// Eigen::SimplicialCholesky, cholesky.cu:72-158, pdSolver.cu:103).  Per PD iteration: L y = P b, L^T z = y, x = P^T z for the
+// three right-hand sides, as a "synchronisation-free" sparse triangular solve: ONE WARP PER ROW -- the lanes split the row's
+// off-diagonal entries (the separator rows of the dissection hold hundreds), each lane waits for ITS dependencies (a tag in the
+// fourth component of every solved entry, read and written with the value as one 128-bit word: no fences, one L2 round trip
+// per hand-over), the partial sums are combined by a fixed shuffle tree.  Warp w takes rows w, w + W, ... in
+// ascending (descending for L^T) order and the kernel is launched cooperatively (every warp resident), so the smallest
+// unfinished row always has all its dependencies done and its warp working on it: progress is guaranteed.
+// L is stored by rows (CSR, diagonal last) and L^T by rows as well (CSR, diagonal first).
 struct CholDev {
     int n;
     const int *lPtr, *lCol; const float* lVal;        // L   by rows, ascending columns, diagonal LAST
     const int *uPtr, *uCol; const float* uVal;        // L^T by rows, ascending columns, diagonal FIRST
+    const int* perm;                                  // perm[row of the factor] = vertex (engine numbering)
 };
 
-__device__ __forceinline__ float4 ld_volatile4(const float4* p)
+// A solved entry and its "final" tag travel in ONE 128-bit word (x, y, z, tag): b128 accesses are single-copy atomic, so
+// value and flag need no fence between them and a consumer gets both with one L2 round trip.
+__device__ __forceinline__ float4 ld_relaxed128(const float4* p)
 {
     float4 v;
-    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    asm volatile("{\n\t.reg .b128 t;\n\tld.relaxed.gpu.global.b128 t, [%4];\n\tmov.b128 {%0, %1, %2, %3}, t;\n\t}"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void st_relaxed128(float4* p, float4 v)
+{
+    asm volatile("{\n\t.reg .b128 t;\n\tmov.b128 t, {%1, %2, %3, %4};\n\tst.relaxed.gpu.global.b128 [%0], t;\n\t}"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// sum over the off-diagonal entries [e0, e1) of one factor row of -l_e * v[col_e], lanes striding the entries; v[j] is final
+// once its fourth component carries `tag`
+__device__ __forceinline__ void chol_row_dot(const int* __restrict__ col, const float* __restrict__ val, int e0, int e1, int lane,
+                                             const float4* v, int tag, float& a0, float& a1, float& a2)
+{
+    a0 = a1 = a2 = 0.f;
+    // eight gathers in flight per lane (a separator row of the dissection holds thousands of entries; one L2 round trip per
+    // entry and lane, taken one after the other, was 6 us per row on the critical path); only an entry that is not final
+    // yet is polled again.  The sum keeps its order: ascending entries per lane.
+    constexpr int D = 8;
+    for (int e = e0 + lane; e < e1; e += 32 * D) {
+        int j[D]; float l[D]; float4 vj[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const int ek = e + 32 * k;
+            j[k] = (ek < e1) ? col[ek] : -1;
+            l[k] = (ek < e1) ? val[ek] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) if (j[k] >= 0) vj[k] = ld_relaxed128(v + j[k]);
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            if (j[k] < 0) continue;
+            for (unsigned spins = 0; __float_as_int(vj[k].w) != tag; ++spins) {
+                if (spins > 4) __nanosleep(40);          // thousands of lanes polling back to back would congest L2 for the one load that matters
+                vj[k] = ld_relaxed128(v + j[k]);
+            }
+            a0 = __fmaf_rn(-l[k], vj[k].x, a0); a1 = __fmaf_rn(-l[k], vj[k].y, a1); a2 = __fmaf_rn(-l[k], vj[k].z, a2);
+        }
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS)
-k_chol_solve(CholDev C, const float4* __restrict__ b, float4* x, float4* y, float4* __restrict__ xprev, int* ready /* n, zero on entry */,
+k_chol_solve(CholDev C, const float4* __restrict__ b, float4* x, float4* y, float4* z, float4* __restrict__ xprev,
              int epochTag, float pdTol, SolveState* st, double* partials)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[27];
     if (st->done) return;
-    const int n = C.n, gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
-    // forward: row i needs y[j] for every off-diagonal L_ij.  ready[j] == tag: y[j] is final.
-    const int tagF = 2 * epochTag + 1, tagB = 2 * epochTag + 2;
-    for (int i = gtid; i < n; i += gstride) {
-        const float4 bb = b[i];
-        float a0 = bb.x, a1 = bb.y, a2 = bb.z;
-        const int e1 = C.lPtr[i + 1] - 1;
-        for (int e = C.lPtr[i]; e < e1; ++e) {
-            const int j = C.lCol[e];
-            while (*reinterpret_cast<volatile int*>(ready + j) != tagF) { }
-            __threadfence();
-            const float4 yj = ld_volatile4(y + j);
-            const float l = C.lVal[e];
-            a0 = __fmaf_rn(-l, yj.x, a0); a1 = __fmaf_rn(-l, yj.y, a1); a2 = __fmaf_rn(-l, yj.z, a2);
+    const int n = C.n, lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
+    const int tag = epochTag + 1;          // never 0 (the buffers start zeroed), one value per launch
+    // forward: row i needs y[j] for every off-diagonal L_ij
+    for (int i = warp; i < n; i += nWarps) {
+        const int e0 = C.lPtr[i], e1 = C.lPtr[i + 1] - 1;
+        // (everything the row's last instructions need is fetched BEFORE the dependencies are waited for: the hand-over from
+        // row to row is the critical path of the whole solve)
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        float d = 1.f;
+        if (lane == 0) { bb = b[C.perm[i]]; d = C.lVal[e1]; }
+        float a0, a1, a2;
+        chol_row_dot(C.lCol, C.lVal, e0, e1, lane, y, tag, a0, a1, a2);
+        if (lane == 0) {
+            st_relaxed128(y + i, make_float4(__fdiv_rn(__fadd_rn(bb.x, a0), d), __fdiv_rn(__fadd_rn(bb.y, a1), d), __fdiv_rn(__fadd_rn(bb.z, a2), d), __int_as_float(tag)));
         }
-        const float d = C.lVal[e1];
-        y[i] = make_float4(__fdiv_rn(a0, d), __fdiv_rn(a1, d), __fdiv_rn(a2, d), 0.f);
-        __threadfence();
-        *reinterpret_cast<volatile int*>(ready + i) = tagF;
     }
-    grid.sync();
-    // backward: row i of L^T needs x[j], j > i; rows are taken in descending order
-    for (int t = gtid; t < n; t += gstride) {
+    // (no grid-wide synchronisation here: the backward rows wait for y[i] through its tag like for any other dependency)
+    // backward: row i of L^T needs z[j], j > i; rows are taken in descending order
+    for (int t = warp; t < n; t += nWarps) {
         const int i = n - 1 - t;
-        const float4 yy = ld_volatile4(y + i);
-        float a0 = yy.x, a1 = yy.y, a2 = yy.z;
         const int e0 = C.uPtr[i], e1 = C.uPtr[i + 1];
-        for (int e = e1 - 1; e > e0; --e) {
-            const int j = C.uCol[e];
-            while (*reinterpret_cast<volatile int*>(ready + j) != tagB) { }
-            __threadfence();
-            const float4 xj = ld_volatile4(x + j);
-            const float l = C.uVal[e];
-            a0 = __fmaf_rn(-l, xj.x, a0); a1 = __fmaf_rn(-l, xj.y, a1); a2 = __fmaf_rn(-l, xj.z, a2);
+        float4 yy = make_float4(0.f, 0.f, 0.f, 0.f);
+        float d = 1.f; int pi = 0;
+        if (lane == 0) {
+            d = C.uVal[e0]; pi = C.perm[i];
+            do { yy = ld_relaxed128(y + i); } while (__float_as_int(yy.w) != tag);
         }
-        const float d = C.uVal[e0];
-        x[i] = make_float4(__fdiv_rn(a0, d), __fdiv_rn(a1, d), __fdiv_rn(a2, d), 0.f);
-        __threadfence();
-        *reinterpret_cast<volatile int*>(ready + i) = tagB;
+        float a0, a1, a2;
+        chol_row_dot(C.uCol, C.uVal, e0 + 1, e1, lane, z, tag, a0, a1, a2);
+        if (lane == 0) {
+            const float4 r = make_float4(__fdiv_rn(__fadd_rn(yy.x, a0), d), __fdiv_rn(__fadd_rn(yy.y, a1), d), __fdiv_rn(__fadd_rn(yy.z, a2), d), __int_as_float(tag));
+            st_relaxed128(z + i, r);
+            x[pi] = make_float4(r.x, r.y, r.z, 0.f);
+        }
     }
     grid.sync();
     unsigned long long noSeq = 0;
-    finish_pd_iteration<false>(grid, n, x, xprev, pdTol, st, 0, partials, sh, DistSolve{}, noSeq);
+    unsigned flip = 0;
+    finish_pd_iteration<false>(grid, n, x, xprev, pdTol, st, 0, partials, sh, DistSolve{}, noSeq, flip);
 }
 
 // start of a step in the non-Jacobi modes: err = 1, nothing skipped (pdSolver.cu:163)

@@ -68,6 +68,26 @@ std::vector<uint32_t> load_ele_file(const std::string& path, int startIndex)
     return T;
 }
 
+std::vector<uint32_t> load_face_file(const std::string& path, int startIndex)
+{
+    std::vector<uint32_t> F;
+    std::ifstream f(path);
+    if (!f.is_open()) return F;                        // the reference falls back to the tets' boundary faces (dataLoader.cu:73,92)
+    std::string line;
+    std::getline(f, line);
+    int n = 0;
+    { std::istringstream is(line); is >> n; }
+    if (n <= 0) return F;
+    F.assign((size_t)n * 3, 0u);
+    for (int t = 0; t < n && std::getline(f, line); ++t) {
+        std::istringstream is(line);
+        int a = 0, b = 0, c = 0, d = 0, e = 0;         // index, three vertices, boundary marker
+        is >> a >> b >> c >> d >> e;
+        F[3 * t + 0] = (uint32_t)(b - startIndex); F[3 * t + 1] = (uint32_t)(c - startIndex); F[3 * t + 2] = (uint32_t)(d - startIndex);
+    }
+    return F;
+}
+
 // ---------------------------------------------------------------- glm-equivalent transforms
 namespace {
 void m4_identity(float M[16]) { std::memset(M, 0, 64); M[0] = M[5] = M[10] = M[15] = 1.f; }
@@ -140,10 +160,16 @@ void cylinder_axis(const float M[16], float axis[3])
 
 // ---------------------------------------------------------------- merge
 void scene_add_body(Scene& s, const std::string& name, const std::vector<float>& X, const std::vector<uint32_t>& Tet,
-                    float mass, float mu, float lambda, const std::vector<uint32_t>& dbc)
+                    float mass, float mu, float lambda, const std::vector<uint32_t>& dbc, const std::vector<uint32_t>* faces)
 {
     const int nv = (int)(X.size() / 3), nt = (int)(Tet.size() / 4);
     const uint32_t vOff = (uint32_t)s.numVerts;
+    const bool hasTri = faces && !faces->empty();
+    s.bodyHasTri.push_back(hasTri ? 1 : 0);
+    if (hasTri) {
+        for (uint32_t v : *faces) s.Tri.push_back(v + vOff);
+        s.triFather.insert(s.triFather.end(), faces->size() / 3, (uint32_t)s.bodyVertStart.size());
+    }
     s.bodyVertStart.push_back(s.numVerts);
     s.bodyTetStart.push_back(s.numTets);
     s.bodyNames.push_back(name);
@@ -295,7 +321,14 @@ Scene load_context_json(const std::string& jsonPath, const std::string& contextN
             transform_vertices(X.data(), (int)(X.size() / 3), M);
             std::vector<uint32_t> T = load_ele_file(resolve_asset(eleFile, jsonDir, assetRoot), startIndex);
             std::string base = nodeFile.substr(nodeFile.find_last_of('/') + 1);
-            scene_add_body(sc, base, X, T, mass, mu, lambda, dbc);
+            const std::string faceFile = def.value("faceFile", "");
+            std::vector<uint32_t> Fc;
+            if (!faceFile.empty()) {
+                std::string fp;
+                try { fp = resolve_asset(faceFile, jsonDir, assetRoot); } catch (...) { fp.clear(); }
+                if (!fp.empty()) Fc = load_face_file(fp, startIndex);
+            }
+            scene_add_body(sc, base, X, T, mass, mu, lambda, dbc, &Fc);
         }
     }
     if (ctx->contains("fixedBodies")) {

@@ -38,6 +38,13 @@ struct Scene {
     std::vector<float> mu, lambda; // numTets
     std::vector<int> bodyVertStart, bodyTetStart;   // per soft body (startIndices in the reference)
     std::vector<std::string> bodyNames;
+    // surface triangles for the mesh-mesh collision pass (SolverData::Tri / dev_TriFathers, dataLoader.cu:68-127,343-369):
+    // explicit ones (a body's .face file, or the caller's arrays for the whole scene); bodies without explicit triangles get
+    // the boundary faces of their tets when a collision mesh is built (collision.cpp:scene_surface) -- never before, a 16 M-tet
+    // grid should not pay for it
+    std::vector<uint32_t> Tri, triFather;      // 3 per triangle (merged numbering); body of each triangle
+    std::vector<uint8_t> bodyHasTri;           // per body: its triangles are in Tri
+    bool triWholeScene = false;                // Tri / triFather ARE the scene's surface as given by the caller
     std::vector<FixedBody> fixed;
     SolverParams params;
 };
@@ -45,6 +52,7 @@ struct Scene {
 // TetGen readers, dataLoader.cu:131-173 and :38-66
 std::vector<float> load_node_file(const std::string& path, bool centralize);
 std::vector<uint32_t> load_ele_file(const std::string& path, int startIndex);
+std::vector<uint32_t> load_face_file(const std::string& path, int startIndex);      // dataLoader.cu:69-90 (empty when the file cannot be opened)
 
 // utilities.cpp:141-150 (fixed bodies: T*Rx*Ry*Rz*S) / dataLoader.cu:214-220 (soft: T*S*Rx*Ry*Rz)
 void model_matrix(const float pos[3], const float rot[3], const float scale[3], bool softBodyOrder, float M[16]);
@@ -54,7 +62,7 @@ void cylinder_axis(const float M[16], float axis[3]); // fixedBodyData.cu:116
 
 // Append one soft body (already transformed) to a scene: DataLoader::AllocData merge rules
 void scene_add_body(Scene& s, const std::string& name, const std::vector<float>& X, const std::vector<uint32_t>& Tet,
-                    float mass, float mu, float lambda, const std::vector<uint32_t>& dbc);
+                    float mass, float mu, float lambda, const std::vector<uint32_t>& dbc, const std::vector<uint32_t>* faces = nullptr);
 
 // context.json -> Scene.  contextName empty = first context with "load" != false.
 // assetRoot empty = resolve asset paths like the reference (relative to the json's build dir).

@@ -115,6 +115,44 @@ int main(int argc, char** argv)
     std::printf("release: |V.y| of a formerly held vertex %.4f\n", vfree);
     worst = std::fmax(worst, worstDrag);
     if (held != 0.0 || nDrag == 0 || !(vfree > 0.0)) worst = std::fmax(worst, 1.0);
+    // --- SolverParams::handleCollision = true, the reference's default (context.h:44, def.h:79): the adapter hands SolverData::Tri /
+    // dev_TriFathers to the engine, which runs the mesh-mesh pass itself; it must step (it used to leave the engine
+    // null) and give exactly what pd_step gives with pd_params.handle_collision = 1
+    {
+        pd_scene* sc2 = pd_scene_kuhn_grid(cells, cells, cells, 1.0f, 0.05f, 7u, origin, 1.0f, 2e5f);
+        pd_scene_add_fixed(sc2, &floor);
+        pd_params pc = p; pc.handle_collision = 1;
+        pd_scene_set_params(sc2, &pc);
+        int nTri = 0;
+        pd_scene_get_surface(sc2, &nTri, nullptr, nullptr);
+        std::vector<uint32_t> tri(3 * (size_t)nTri), father((size_t)nTri);
+        pd_scene_get_surface(sc2, &nTri, tri.data(), father.data());
+        pd_engine* e2 = pd_create(sc2, nullptr);
+        if (!e2) { std::fprintf(stderr, "%s\n", pd_last_error()); return 2; }
+        std::vector<float> Xc(X.size()), Vc(X.size()), Tc(X.size());
+        if (pd_step(e2, 2) || pd_download(e2, Xc.data(), Vc.data(), Tc.data())) { std::fprintf(stderr, "%s\n", pd_last_error()); return 2; }
+        pd_destroy(e2); pd_scene_free(sc2);
+        SolverData<float> dc = d;
+        dc.moreDBC = nullptr; dc.OffsetX = nullptr; dc.mouseSelection.dragging = false;
+        dc.numTris = nTri;
+        CK(cudaMalloc((void**)&dc.Tri, 12 * (size_t)nTri)); CK(cudaMalloc((void**)&dc.dev_TriFathers, 4 * (size_t)nTri));
+        CK(cudaMemcpy(dc.Tri, tri.data(), 12 * (size_t)nTri, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dc.dev_TriFathers, father.data(), 4 * (size_t)nTri, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dc.X, X.data(), 12 * (size_t)nV, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dc.XTilde, X.data(), 12 * (size_t)nV, cudaMemcpyHostToDevice));
+        CK(cudaMemset(dc.V, 0, 12 * (size_t)nV));
+        SolverParams<float> pcol = params; pcol.handleCollision = true;
+        std::unique_ptr<Solver<float>> sc3 = std::make_unique<B200PdSolver>(128, dc, std::vector<pd_fixed_body>{floor});
+        for (int s = 0; s < 2; ++s) sc3->Update(dc, pcol);
+        CK(cudaMemcpy(X2.data(), dc.X, 12 * (size_t)nV, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(V2.data(), dc.V, 12 * (size_t)nV, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(T2.data(), dc.XTilde, 12 * (size_t)nV, cudaMemcpyDeviceToHost));
+        double wc = 0, mv = 0;
+        for (size_t i = 0; i < X.size(); ++i) {
+            wc = std::fmax(wc, std::fabs((double)Xc[i] - X2[i])); wc = std::fmax(wc, std::fabs((double)Vc[i] - V2[i])); wc = std::fmax(wc, std::fabs((double)Tc[i] - T2[i]));
+            mv = std::fmax(mv, std::fabs((double)X2[i] - X[i]));
+        }
+        std::printf("handleCollision=true: %d surface triangles, moved %.4f, max_abs_diff %.9g\n", nTri, mv, wc);
+        if (!(mv > 0.0)) wc = std::fmax(wc, 1.0);
+        worst = std::fmax(worst, wc);
+    }
     const auto& perf = solver->GetPerformanceData();
     std::printf("nV %d nT %d steps %d moved %.4f perf[%s]=%.3f ms perf[%s]=%.3f ms\n", nV, nT, steps, moved, perf[0].first.c_str(), perf[0].second,
                 perf[1].first.c_str(), perf[1].second);

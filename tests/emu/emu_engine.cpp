@@ -89,10 +89,10 @@ void step_once(Emu& e, float dt, float gravity, float rho, float muN, float muT,
                            (const float4*)r.b0.data(), r.Pslots.data(), (unsigned long long*)nullptr, dw);
             if (e.drag) pd_emu::launch_flat(vg, vb, k_vertex_jacobi<BASE, true>, r.nOwn, (const float4*)r.q[ic].data(), (const float4*)r.q[ip].data(), r.q[in].data(),
                                             (const float4*)r.dbcx.data(), (const float4*)r.b0.data(), (const float2*)r.cc.data(), (const uint32_t*)r.L.vslotPtr.data(),
-                                            (const uint32_t*)r.L.vslot.data(), (const float4*)r.Pslots.data(), omega, wdbc);
+                                            (const uint32_t*)r.L.vslot.data(), (const float4*)r.Pslots.data(), omega, wdbc, 0);
             else pd_emu::launch_flat(vg, vb, k_vertex_jacobi<BASE, false>, r.nOwn, (const float4*)r.q[ic].data(), (const float4*)r.q[ip].data(), r.q[in].data(),
                                      (const float4*)r.dbcx.data(), (const float4*)r.b0.data(), (const float2*)r.cc.data(), (const uint32_t*)r.L.vslotPtr.data(),
-                                     (const uint32_t*)r.L.vslot.data(), (const float4*)r.Pslots.data(), omega, wdbc);
+                                     (const uint32_t*)r.L.vslot.data(), (const float4*)r.Pslots.data(), omega, wdbc, 0);
         }
         push(e, in);
     }
@@ -138,7 +138,7 @@ void rank_step_concurrent(Emu& e, Rank& r, float dt, float gravity, float rho, f
                                 (const float4*)r.b0.data(), r.Pslots.data(), (unsigned long long*)nullptr, dw);
         pd_emu::launch_flat(vg, vb, k_vertex_jacobi<BASE, false>, r.nOwn, (const float4*)r.q[ic].data(), (const float4*)r.q[ip].data(), r.q[in].data(),
                             (const float4*)r.dbcx.data(), (const float4*)r.b0.data(), (const float2*)r.cc.data(), (const uint32_t*)r.L.vslotPtr.data(),
-                            (const uint32_t*)r.L.vslot.data(), (const float4*)r.Pslots.data(), omega, wdbc);
+                            (const uint32_t*)r.L.vslot.data(), (const float4*)r.Pslots.data(), omega, wdbc, 0);
         ++r.phase;
     }
     pd_emu::launch_flat(vg, vb, k_finish<false>, r.nOwn, (const float4*)r.q[(base + iters) % 3].data(), dtInv, r.X.data(), r.XT.data(), r.V.data(), e.dfb, muT, muN,

@@ -16,6 +16,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
+@pytest.fixture(autouse=True)
+def _whole_boundary_tiles(monkeypatch):
+    """The plan tests below state the SPECIFICATION: a rank evaluates every global tile that touches one of its vertices,
+    unchanged.  The engine's default since round 2 trims and re-packs the boundary tiles (PD_DIST_TRIM, on unless set to 0);
+    tests/test_dist_trim.py checks the trimmed plans against these."""
+    monkeypatch.setenv("PD_DIST_TRIM", "0")
+
+
 def _plans(pd, scene, world):
     G = scene.layout()
     return G, [pd.RankPlan(G, world, r) for r in range(world)]

@@ -64,7 +64,7 @@ def test_trimmed_rank_layouts_keep_every_owned_slot(pd, assets, scene_name, worl
     full = trimmed = 0
     monkeypatch.setenv("PD_DIST_TRIM", "1")
     plans = [pd.RankPlan(G, world, r) for r in range(world)]              # the plan carries the switch to its layout
-    monkeypatch.delenv("PD_DIST_TRIM", raising=False)
+    monkeypatch.setenv("PD_DIST_TRIM", "0")
     plans0 = [pd.RankPlan(G, world, r) for r in range(world)]
     # push lists of the trimmed plans: the same vertex on both sides, every ghost fed exactly once by its owner
     for n, Pn in enumerate(plans):
@@ -135,7 +135,7 @@ def test_matrix_diag_host_vs_oracle_and_across_world_sizes(pd, O, assets, monkey
                 monkeypatch.setenv("PD_DIST_TRIM", trim)
                 P = pd.RankPlan(G, world, rank)
                 L = P.local_layout(G)
-                monkeypatch.delenv("PD_DIST_TRIM", raising=False)
+                monkeypatch.setenv("PD_DIST_TRIM", "0")
                 mdl = L.matrix_diag()
                 own = md[P.first_owned:P.first_owned + P.num_owned]
                 assert np.array_equal(mdl[:P.num_owned].view(np.uint32), own.view(np.uint32)), (trim, world, rank)

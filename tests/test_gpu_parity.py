@@ -257,10 +257,11 @@ def test_params_and_perf_interface(pd, assets):
     assert names_t[0][1] > 0 and names_t[1][1] > 0 and names_t[2][1] > 0 and raw_t.kernel_launches == 2 * (2 + 14)
     for u, v in zip(eng.download(), tiles.download()):
         assert np.array_equal(u.view(np.uint32), v.view(np.uint32))        # faithful mode (auto on the cube): both paths sum in the reference's order
-    # handleCollision=true (mesh-mesh BVH/CCD) is outside the hot path and must be refused loudly
+    # handleCollision = true (mesh-mesh collision, tests/test_gpu_collision.py) is accepted: one body, nothing to collide with
     p["handle_collision"] = 1
-    with pytest.raises(pd.PdError):
-        eng.set_params(p)
+    eng.set_params(p)
+    eng.Update(1)
+    assert eng.collision()[2] == 0
 
 
 def test_dbc_pinned_vertices_vs_oracle(pd, O, assets):
