@@ -280,6 +280,25 @@ int pd_dist_info(const pd_engine*, int info[6]);
 /* test hook: the corotational projection (pdUtil.cu:112-122) of n row-major 3x3 matrices on
  * `device`; rot_mode as in pd_engine_options; used_fast (may be NULL) reports the path taken */
 int pd_rotation_batch(int device, int rot_mode, int n, const float* F, float* R, int* used_fast);
+/* ---- linear back-ends of the reference's IPC (double) solver, on the engine's fused CSR / CG kernels ---------------------------
+ * LinearSolver<double>::Solve(N, d_b, d_x, A, nz, rowIdx, colIdx, d_guess) (src/simulation/solver/linear/linear.h:55-71) as
+ * IPCSolver::SearchDirection calls it on the 3 nV x 3 nV Hessian in COO form with duplicates (IPC/ipc.cu:233-241):
+ *   PD_LS_PCG_JACOBI  PCGJacobiSolver<double> (linear/pcgJacobi.cu:88-172; defaults max_iter 2000, ||r|| < 1e-5)
+ *   PD_LS_CG_IC0      CGSolver<double>        (linear/cg.cu:81-247: IC(0)-preconditioned CG; defaults max_iter 100, ||r|| < 1e-6)
+ * COO -> CSR (duplicates summed), the preconditioner and the whole CG loop run on the device in one cooperative kernel; no
+ * cuSPARSE / cuBLAS / thrust.  max_iter / tolerance <= 0 select the reference's defaults.  The PD path does not use these. */
+typedef struct pd_linsolver pd_linsolver;
+#define PD_LS_CG_IC0 1
+#define PD_LS_PCG_JACOBI 2
+pd_linsolver* pd_linsolver_create(int kind, int n, int max_iter, double tolerance, int device);
+void pd_linsolver_destroy(pd_linsolver*);
+/* device pointers, as the reference passes them; the matrix arrays are not modified (the reference sorts them in place);
+ * d_guess may be NULL (x0 = 0).  Synchronises before returning: d_x is complete. */
+int pd_linsolver_solve_device(pd_linsolver*, int n, const double* d_b, double* d_x, const double* d_A, int nz, const int* d_row_idx, const int* d_col_idx, const double* d_guess);
+int pd_linsolver_solve_host(pd_linsolver*, int n, const double* b, double* x, const double* A, int nz, const int* row_idx, const int* col_idx, const double* guess);
+/* of the last solve: CG iterations, final ||r||_2, non-zeros of the assembled CSR */
+int pd_linsolver_stats(const pd_linsolver*, int* iterations, double* residual, int* nnz);
+
 /* test hook: the collision pass's continuous-collision test (ccdCollisionTest<float>, intersections.cu:312-355) on n queries of
  * host arrays: type[i] = 1 vertex-face / 2 edge-edge, verts = 4 vertex ids per query, X / XTilde = 3 per vertex;
  * toi[i] in [0, 1] (1 = no hit), normals = 3 per query */

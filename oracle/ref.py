@@ -137,6 +137,7 @@ def solvers_lib():
         L.refs_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.refs_get.argtypes = [C.c_void_p] * 4
         L.refs_set.argtypes = [C.c_void_p] * 4
+        L.refs_linear_solve.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double]
         _slib = L
     return _slib
 
@@ -222,3 +223,15 @@ def ccd_kernel(X, XTilde, V, tI, normals, dt=1 / 60, muT=0.5, muN=0.5, threads_p
     if rc:
         raise RuntimeError(f"reference collision harness CUDA error {rc}")
     return X, V
+
+
+def linear_solve(kind, A, row, col, b, guess=None, max_iter=0, tol=0.0):
+    """LinearSolver<double>::Solve of the reference (kind 1 = CGSolver, IC(0); 2 = PCGJacobiSolver) on a host COO with duplicates -> x."""
+    A = np.ascontiguousarray(A, np.float64); row = np.ascontiguousarray(row, np.int32); col = np.ascontiguousarray(col, np.int32)
+    b = np.ascontiguousarray(b, np.float64); g = None if guess is None else np.ascontiguousarray(guess, np.float64)
+    x = np.zeros(b.shape[0], np.float64)
+    rc = solvers_lib().refs_linear_solve(kind, b.shape[0], A.shape[0], row.ctypes.data, col.ctypes.data, A.ctypes.data, b.ctypes.data,
+                                         None if g is None else g.ctypes.data, x.ctypes.data, max_iter, tol)
+    if rc:
+        raise RuntimeError(f"reference solver harness CUDA error {rc}")
+    return x

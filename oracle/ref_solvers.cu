@@ -29,6 +29,7 @@
 #include <simulation/solver/solverUtil.cuh>
 #include <linear/cholesky.h>
 #include <linear/pcgJacobi.h>
+#include <linear/cg.h>
 
 namespace {
 
@@ -184,6 +185,29 @@ void refs_set(void* h, const float* X, const float* V, const float* XTilde)
     if (X) cudaMemcpy(r.X, X, v3, cudaMemcpyHostToDevice);
     if (V) cudaMemcpy(r.V, V, v3, cudaMemcpyHostToDevice);
     if (XTilde) cudaMemcpy(r.XTilde, XTilde, v3, cudaMemcpyHostToDevice);
+}
+
+// The IPC solver's linear back-ends on their own: LinearSolver<double>::Solve as IPCSolver::SearchDirection calls it
+// (IPC/ipc.cu:233-241), kind 1 = CGSolver<double> (linear/cg.cu), kind 2 = PCGJacobiSolver<double> (linear/pcgJacobi.cu); host arrays
+// in and out, the COO may hold duplicates.  maxIter / tol <= 0: the classes' defaults.
+int refs_linear_solve(int kind, int N, int nz, const int* row, const int* col, const double* val, const double* b, const double* guess, double* x,
+                      int maxIter, double tol)
+{
+    double *dA, *db, *dx, *dg = nullptr; int *dr, *dc;
+    cudaMalloc(&dA, 8ull * nz); cudaMalloc(&dr, 4ull * nz); cudaMalloc(&dc, 4ull * nz); cudaMalloc(&db, 8ull * N); cudaMalloc(&dx, 8ull * N);
+    cudaMemcpy(dA, val, 8ull * nz, cudaMemcpyHostToDevice); cudaMemcpy(dr, row, 4ull * nz, cudaMemcpyHostToDevice); cudaMemcpy(dc, col, 4ull * nz, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, b, 8ull * N, cudaMemcpyHostToDevice); cudaMemset(dx, 0, 8ull * N);
+    if (guess) { cudaMalloc(&dg, 8ull * N); cudaMemcpy(dg, guess, 8ull * N, cudaMemcpyHostToDevice); }
+    {
+        std::unique_ptr<LinearSolver<double>> ls;
+        if (kind == 1) ls = (maxIter > 0) ? std::make_unique<CGSolver<double>>(N, maxIter, tol) : std::make_unique<CGSolver<double>>(N);
+        else ls = (maxIter > 0) ? std::make_unique<PCGJacobiSolver<double>>(N, maxIter, tol) : std::make_unique<PCGJacobiSolver<double>>(N);
+        ls->Solve(N, db, dx, dA, nz, dr, dc, dg);
+        cudaDeviceSynchronize();
+    }
+    cudaMemcpy(x, dx, 8ull * N, cudaMemcpyDeviceToHost);
+    cudaFree(dA); cudaFree(dr); cudaFree(dc); cudaFree(db); cudaFree(dx); if (dg) cudaFree(dg);
+    return (int)cudaGetLastError();
 }
 
 }  // extern "C"

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 W=${W:-grid139}
 for rep in 1 2; do for v in ${V:-default}; do
   if [ $v = default ]; then unset PD_B200_LIB; else export PD_B200_LIB=$PWD/soft-body-simulation-cuda_b200/variants/libpd_$v.so; fi
-  timeout 300 python bench.py --workload $W --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ab_${W}_${v}_$rep.json 2> gpurun_out/ab_${W}_${v}_$rep.err; tail -2 gpurun_out/ab_${W}_${v}_$rep.err
+  timeout 300 python bench.py --workload $W --steps 3 --warmup 3 --no-cpu-baseline --no-parity --no-faithful > gpurun_out/ab_${W}_${v}_$rep.json 2> gpurun_out/ab_${W}_${v}_$rep.err; tail -2 gpurun_out/ab_${W}_${v}_$rep.err
 done; done
 unset PD_B200_LIB
 python - <<PY

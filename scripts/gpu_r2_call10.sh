@@ -17,3 +17,6 @@ d=[json.loads(l) for l in open("gpurun_out/${T}_pdl${v}_$rep.json") if l.startsw
 print("PD_PDL=$v rep $rep ms/step %.3f value %.0f"%(d["ms_per_step"], d["value"]), d["clocks"]["sm_mhz"])
 PY
 done; done
+# split phase C (default library) vs -DPD_SPLIT_C=0 (variants/libpd_nosplit.so), same box
+V="default nosplit" bash scripts/gpu_ab.sh 2>&1 | tee gpurun_out/${T}_ab_split.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_local -s 210 -c 1 -o gpurun_out/${T}_k_local_grid139_split python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity --no-faithful > gpurun_out/${T}_ncu.log 2>&1; tail -2 gpurun_out/${T}_ncu.log

@@ -133,6 +133,11 @@ SYMBOLS = {
     "pd_get_setup": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "pd_get_system_matrix": (_I, [_VP, _PI, _VP, _VP, _VP]),
     "pd_get_solve_stats": (_I, [_VP, _PF, _PI]),
+    "pd_linsolver_create": (_VP, [_I, _I, _I, C.c_double, _I]),
+    "pd_linsolver_destroy": (None, [_VP]),
+    "pd_linsolver_solve_device": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
+    "pd_linsolver_solve_host": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
+    "pd_linsolver_stats": (_I, [_VP, _PI, C.POINTER(C.c_double), _PI]),
     "pd_ccd_batch": (_I, [_I, _I, _VP, _VP, _I, _VP, _VP, _VP, _VP]),
     "pd_get_collision": (_I, [_VP, _VP, _VP, C.POINTER(C.c_longlong)]),
     "pd_get_solver_sizes": (_I, [_VP, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
@@ -594,6 +599,40 @@ def cholesky_factor(rowptr, col, val):
     for q in (lp, lc, lv):
         lib().pd_free(q)
     return out
+
+
+PD_LS_CG_IC0, PD_LS_PCG_JACOBI = 1, 2
+
+
+class LinearSolver:
+    """LinearSolver<double> of the reference's IPC solver (linear.h:55-71): kind PD_LS_PCG_JACOBI or PD_LS_CG_IC0."""
+
+    def __init__(self, kind, n, max_iter=0, tolerance=0.0, device=0):
+        self.n = n
+        self._h = lib().pd_linsolver_create(kind, n, max_iter, tolerance, device)
+        if not self._h:
+            raise PdError(_err())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().pd_linsolver_destroy(self._h)
+            self._h = None
+
+    def solve(self, A, row, col, b, guess=None):
+        """host COO (duplicates allowed) -> x"""
+        A = np.ascontiguousarray(A, np.float64); row = np.ascontiguousarray(row, np.int32); col = np.ascontiguousarray(col, np.int32)
+        b = np.ascontiguousarray(b, np.float64); g = None if guess is None else np.ascontiguousarray(guess, np.float64)
+        x = np.zeros(self.n, np.float64)
+        _check(lib().pd_linsolver_solve_host(self._h, self.n, _p(b), _p(x), _p(A), A.shape[0], _p(row), _p(col), _p(g)))
+        return x
+
+    def solve_device_ptr(self, d_b, d_x, d_A, nz, d_row, d_col, d_guess=None):
+        _check(lib().pd_linsolver_solve_device(self._h, self.n, d_b, d_x, d_A, nz, d_row, d_col, d_guess))
+
+    def stats(self):
+        it, nnz, res = C.c_int(), C.c_int(), C.c_double()
+        _check(lib().pd_linsolver_stats(self._h, C.byref(it), C.byref(res), C.byref(nnz)))
+        return dict(iterations=it.value, residual=res.value, nnz=nnz.value)
 
 
 def ccd_batch(types, verts, X, XTilde, device=0):

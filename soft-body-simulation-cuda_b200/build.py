@@ -15,7 +15,7 @@ RUNNER = os.path.join(HERE, "pd_run")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = os.environ.get("PD_HOSTCXX", "/usr/bin/g++")
 
-SOURCES = ["scene.cpp", "layout.cpp", "collision.cpp", "pd_engine.cu", "c_api.cu"]
+SOURCES = ["scene.cpp", "layout.cpp", "collision.cpp", "pd_engine.cu", "pd_linear.cu", "c_api.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-ffp-contract=off,-mfma,-Wall"]
 

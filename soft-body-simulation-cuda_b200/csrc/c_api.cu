@@ -11,6 +11,7 @@
 #include "layout.hpp"
 #include "pd_engine.hpp"
 #include "collision.hpp"
+#include "pd_linear.hpp"
 #include "scene.hpp"
 
 using namespace pdb200;
@@ -593,6 +594,41 @@ int pd_dist_info(const pd_engine* e, int info[6])
     const RankPlan& P = e->e->plan();
     info[0] = e->e->numOwned(); info[1] = e->e->numVerts() - e->e->numOwned(); info[2] = (int)P.neighbours.size();
     info[3] = (int)P.pushSrc.size(); info[4] = e->e->numTets(); info[5] = e->e->layout().nTiles;
+    return PD_OK;
+}
+
+// ------------------------------------------------------------------ IPC (double) linear back-ends
+struct pd_linsolver { LinearSolver* s; };
+pd_linsolver* pd_linsolver_create(int kind, int n, int max_iter, double tolerance, int device)
+{
+    PD_TRY
+    pd_linsolver* h = new pd_linsolver{nullptr};
+    try { h->s = new LinearSolver(kind, n, max_iter, tolerance, device); } catch (...) { delete h; throw; }
+    return h;
+    PD_CATCH_PTR
+}
+void pd_linsolver_destroy(pd_linsolver* h) { if (h) { delete h->s; delete h; } }
+int pd_linsolver_solve_device(pd_linsolver* h, int n, const double* d_b, double* d_x, const double* d_A, int nz, const int* d_row, const int* d_col, const double* d_guess)
+{
+    PD_TRY
+    if (!h || !h->s) return fail(PD_ERR_INVALID, "solver is NULL");
+    h->s->solveDevice(n, d_b, d_x, d_A, nz, d_row, d_col, d_guess);
+    return PD_OK;
+    PD_CATCH_INT
+}
+int pd_linsolver_solve_host(pd_linsolver* h, int n, const double* b, double* x, const double* A, int nz, const int* row, const int* col, const double* guess)
+{
+    PD_TRY
+    if (!h || !h->s) return fail(PD_ERR_INVALID, "solver is NULL");
+    if (!b || !x || !A || !row || !col || nz <= 0) return fail(PD_ERR_INVALID, "NULL argument or empty matrix");
+    h->s->solveHost(n, b, x, A, nz, row, col, guess);
+    return PD_OK;
+    PD_CATCH_INT
+}
+int pd_linsolver_stats(const pd_linsolver* h, int* iterations, double* residual, int* nnz)
+{
+    if (!h || !h->s) return fail(PD_ERR_INVALID, "solver is NULL");
+    h->s->stats(iterations, residual, nnz);
     return PD_OK;
 }
 

@@ -1127,7 +1127,8 @@ void Engine::prepareSolver()
             // the triangular solves run one WARP per row: as many resident warps as rows, up to the whole GPU
             // (not more than 4 blocks per SM: warps beyond the rows that can make progress only poll)
             d.cholGrid = std::max(1, std::min(numSms_ * std::min(4, std::max(1, perSm2)), std::min(SOLVE_MAX_PARTIALS, (nOwn_ + SOLVE_THREADS / 32 - 1) / (SOLVE_THREADS / 32))));
-            if (const char* e = std::getenv("PD_CHOL_BLOCKS_PER_SM")) d.cholGrid = std::max(1, std::min(numSms_ * std::max(1, std::atoi(e)), SOLVE_MAX_PARTIALS));
+            if (const char* e = std::getenv("PD_CHOL_BLOCKS_PER_SM"))       // (experiments)
+                d.cholGrid = std::max(1, std::min(numSms_ * std::min(std::max(1, perSm2), std::max(1, std::atoi(e))), SOLVE_MAX_PARTIALS));
             d.partials = dalloc<double>(2 * 3 * (size_t)SOLVE_MAX_PARTIALS);      // two alternating sets of slots (grid_sum3)
         }
         d.solverReady = true;

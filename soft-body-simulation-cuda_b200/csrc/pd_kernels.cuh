@@ -539,7 +539,11 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
     // producer duties: lane 0 of the LAST warp (the tile-local vertices are sorted by incidence count, so warp 0
     // carries the longest phase C and the last warp the shortest, usually none at all).  Measured and rejected:
     // heaviest groups on the highest warp ids (+3 %), the record's table entry requested a phase earlier (+1 %),
-    // 16-vertex groups with two lanes per vertex (-50 % longest list, +10 % instructions: +6 %)
+    // 16-vertex groups with two lanes per vertex (-50 % longest list, +10 % instructions: +6 %); round 2: warps 7 / 6 / 5
+    // summing the odd rows of groups 0 / 1 / 2 and handing them over through shared memory and a named barrier
+    // (bar.arrive / bar.sync on 64 threads): +19 % instructions, barrier stall 3.3 -> 4.0 per issue, +25 % time
+    // (profiles/r2_k_local_split_c_ncu_summary.txt); x | y | z planes for the H scratch and predicated pad loads: no gain
+    // (profiles/r2_ab_planes_pred.txt)
     const bool producer = tid == TILE_T - 32;
     auto fetch_c = [&](int k) {        // part C of tile k -> buffer k & 1
         const uint2 te = __ldg(reinterpret_cast<const uint2*>(meta_of(k)));       // off / 16, abBytes | cBytes << 16

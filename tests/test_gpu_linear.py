@@ -1,0 +1,81 @@
+"""Linear back-ends of the reference's IPC (double) solver on the engine's kernels (csrc/pd_linear.cu):
+LinearSolver<double>::Solve (linear.h:55-71) with PCGJacobiSolver<double> (linear/pcgJacobi.cu) and CGSolver<double> (IC(0),
+linear/cg.cu) behind it, on a 3 nV x 3 nV SPD matrix handed over as an unsorted COO with duplicates -- against a direct solve
+in double (scipy) and against the reference's own two classes compiled from its sources (oracle/_ref/libpd_ref_solvers.so)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _hessian_like(pd, O, cells, rng):
+    """K (x) I3 + a block-diagonal SPD perturbation, as an unsorted COO whose entries are split into duplicates"""
+    import scipy.sparse as sp
+    sc = pd.Scene.kuhn_grid(cells, cells, cells, 1.0, 0.05, 3, (0, 0, 0), 1.0, 2e5)
+    a = sc.arrays()
+    osc = O.Scene(a["X"], a["Tet"], a["mass"], a["mu"])
+    rp, col, val = osc.system_matrix(O.make_params(dt=1 / 60, gravity=9.8, num_iterations=1))
+    n = rp.shape[0] - 1
+    K = sp.csr_matrix((val.astype(np.float64), col, rp), shape=(n, n))
+    K = 0.5 * (K + K.T)
+    H = sp.kron(K, sp.identity(3), format="coo")
+    blocks = []
+    for v in range(n):                                   # couple x, y, z of every vertex (a general, non-Kronecker Hessian)
+        B = rng.normal(size=(3, 3)); blocks.append(B @ B.T * 50.0)
+    H = (H + sp.block_diag(blocks, format="coo")).tocoo()
+    parts = 3
+    w = rng.dirichlet(np.ones(parts), size=H.nnz)         # every entry arrives as three duplicates
+    row = np.repeat(H.row, parts).astype(np.int32); colv = np.repeat(H.col, parts).astype(np.int32)
+    vals = (H.data[:, None] * w).reshape(-1)
+    perm = rng.permutation(row.shape[0])
+    return H.tocsr(), row[perm], colv[perm], vals[perm]
+
+
+@pytest.mark.parametrize("kind,name", [(2, "PCG-Jacobi"), (1, "CG + IC(0)")])
+def test_linear_backends_vs_direct_and_reference(pd, O, kind, name):
+    import scipy.sparse.linalg as spla
+    rng = np.random.default_rng(3)
+    H, row, col, val = _hessian_like(pd, O, 8, rng)
+    N = H.shape[0]
+    b = rng.normal(size=N) * 100.0
+    exact = spla.spsolve(H.tocsc(), b)
+    ls = pd.LinearSolver(kind, N)
+    x = ls.solve(val, row, col, b)
+    st = ls.stats()
+    res = np.linalg.norm(b - H @ x)
+    err = np.abs(x - exact).max() / np.abs(exact).max()
+    print(f"{name}: N {N}, COO {val.shape[0]} -> nnz {st['nnz']} (matrix {H.nnz}), {st['iterations']} iterations, ||r|| {st['residual']:.2e} (recomputed {res:.2e}), "
+          f"rel err vs direct solve {err:.2e}")
+    assert st["nnz"] == H.nnz
+    tol = 1e-5 if kind == 2 else 1e-6
+    assert st["residual"] < tol and res < 10 * tol and err < 1e-8
+    # bit-reproducible: the duplicates are summed in input order, whatever order the scatter's atomics run in
+    x2 = pd.LinearSolver(kind, N).solve(val, row, col, b)
+    assert np.array_equal(x, x2)
+    # warm start from the answer: no iteration needed
+    x3 = ls.solve(val, row, col, b, guess=x)
+    assert ls.stats()["iterations"] == 0 and np.array_equal(x3, x)
+    import ref
+    if ref.solvers_available():
+        xr = ref.linear_solve(kind, val.copy(), row.copy(), col.copy(), b)
+        d = np.abs(x - xr).max() / np.abs(exact).max()
+        print(f"   vs the reference's {'PCGJacobiSolver' if kind == 2 else 'CGSolver'}<double>: rel diff {d:.2e}; reference vs direct {np.abs(xr - exact).max() / np.abs(exact).max():.2e}")
+        assert d < 1e-8
+
+
+def test_linear_backend_argument_checks(pd):
+    ls = pd.LinearSolver(2, 4)
+    A = np.array([2.0, 2.0, 2.0, 2.0]); r = np.array([0, 1, 2, 3], np.int32)
+    assert np.allclose(ls.solve(A, r, r, np.ones(4)), 0.5)
+    with pytest.raises(pd.PdError):
+        ls.solve(A, np.array([0, 1, 2, 9], np.int32), r, np.ones(4))                 # index outside [0, N)
+    with pytest.raises(pd.PdError):
+        ls.solve(A[:3], r[:3], r[:3], np.ones(4))                                     # a row without a diagonal entry
+    with pytest.raises(pd.PdError):
+        pd.LinearSolver(7, 4)
+    ic = pd.LinearSolver(1, 2)
+    with pytest.raises(pd.PdError):                                                   # not positive definite: IC(0) meets a non-positive pivot
+        ic.solve(np.array([1.0, 2.0, 2.0, 1.0]), np.array([0, 0, 1, 1], np.int32), np.array([0, 1, 0, 1], np.int32), np.ones(2))
