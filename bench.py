@@ -120,6 +120,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def mark(self):
+        """Start of the timed region: drop what was sampled before it.  (start() runs BEFORE the warm-up: loading NVML takes
+        tens of milliseconds that differ from rank to rank, and a rank that enters the timed region late makes its neighbours
+        wait for its halo inside their kernels -- seen once as a 7x outlier at N=2.)"""
+        self.sm, self.power, self.reasons, self.rows = [], [], set(), []
+
     def stop(self):
         if self.nvml:
             self.stop_flag = True
@@ -333,10 +339,11 @@ def run_b200(args):
     info = eng.info()
 
     # ---- device-resident timing: inputs already in HBM, K steps bracketed by sync + events
+    sampler = ClockSampler(local); sampler.start()
     for _ in range(args.warmup):
         eng.Update(1)
     eng.synchronize(); torch.cuda.synchronize(); barrier(world)
-    sampler = ClockSampler(local); sampler.start()
+    sampler.mark()
     perf0 = eng.GetPerformanceData()[1].kernel_launches
     # the engine launches on its own stream, so the CUDA events are recorded there (pd_step_timed)
     dev_ms = eng.step_timed(args.steps)

@@ -485,6 +485,12 @@ __device__ __forceinline__ void local_phase_b(const float4 r0, const float4 r1, 
         h_store(Hline, 3u, c23 >> 16, h3);
 }
 
+// the thread of a CTA that publishes the CTA's part of the halo push: lane 0 of the last warp (the producer; that warp
+// carries the least phase C work).  PD_PUSH_PUBLISH_EARLY=1 (experiments): publish in the prologue, before the first gather
+#ifndef PD_PUSH_PUBLISH_EARLY
+#define PD_PUSH_PUBLISH_EARLY 0
+#endif
+#define PD_PUSH_PUBLISH_TID(tid) ((tid) == TILE_T - 32)
 template <int ROT_MODE, bool JACOBI, bool PROF = false>
 __global__ void __launch_bounds__(TILE_T, 4)
 k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMeta, int nTiles,
@@ -510,8 +516,27 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
     // for -- only before the position gather of the first boundary tile, so the exchange hides behind the interior
     bool needHalo = dw.nNbr > 0;
     volatile unsigned long long* haloNeed = reinterpret_cast<volatile unsigned long long*>(smem + LOCAL_OFF_BAR + 16);   // (not a register: 64 regs are full)
+    // this CTA's part of the halo push is PUBLISHED (system fence over its remote stores, ticket, and -- by the last CTA --
+    // the flags at the neighbours) by one thread, off the critical path: after the barrier of the CTA's first tile, when
+    // the stores issued in the prologue have long completed, or before the CTA's first wait for the neighbours if that
+    // comes earlier (a CTA must never wait for a peer before it has published: the peer's CTAs wait for this rank's flag)
+    bool pushPending = false;
+    auto publish = [&]() {
+        if (pushPending) {
+            pushPending = false;
+            __threadfence_system();            // one per CTA, cumulative over the CTA's remote stores (a block barrier lies between)
+            const unsigned int t = atomicAdd(dw.ticket, 1u);
+            if (t == gridDim.x - 1) {          // every CTA's stores are fenced: publish
+                const unsigned long long e = *haloNeed;
+                *dw.ticket = 0u;
+                *dw.epoch = e;
+                __threadfence_system();
+                for (int j = 0; j < dw.nNbr; ++j) st_release_sys(dw.peerFlag[j], e);
+            }
+        }
+    };
     auto halo_before = [&](int k) {
-        if (needHalo && (int)(blockIdx.x + k * gridDim.x) >= dw.firstTile) { dist_wait(dw, tid, *haloNeed); needHalo = false; }
+        if (needHalo && (int)(blockIdx.x + k * gridDim.x) >= dw.firstTile) { publish(); dist_wait(dw, tid, *haloNeed); needHalo = false; }
     };
     auto meta_of = [&](int k) -> const uint32_t* { return tileMeta + (size_t)(blockIdx.x + k * gridDim.x) * TILE_META_WORDS; };
     const int warp = tid >> 5, lane = tid & 31;
@@ -580,17 +605,10 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
         for (int i = blockIdx.x * TILE_T + tid; i < dw.nPush; i += gridDim.x * TILE_T)
             dw.peerQ[dw.pushNbr[i]][dw.pushDst[i]] = q[dw.pushSrc[i]];
         __syncthreads();
-        if (tid == 0 && dw.nPush > 0) {
-            __threadfence_system();            // one per CTA, cumulative over the CTA's remote stores (barrier above)
-            const unsigned int t = atomicAdd(dw.ticket, 1u);
-            if (t == gridDim.x - 1) {          // every CTA's stores are fenced: publish
-                const unsigned long long e = *haloNeed;
-                *dw.ticket = 0u;
-                *dw.epoch = e;
-                __threadfence_system();
-                for (int j = 0; j < dw.nNbr; ++j) st_release_sys(dw.peerFlag[j], e);
-            }
-        }
+        pushPending = PD_PUSH_PUBLISH_TID(tid) && dw.nPush > 0;
+#if PD_PUSH_PUBLISH_EARLY
+        publish();
+#endif
     }
     halo_before(0);
     gather(veN);
@@ -631,6 +649,7 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
         PD_TICK(1)
         __syncthreads();       // H scratch of tile it complete; tile it+1 staged; every warp is past phase C of tile it-1
         PD_TICK(2)
+        publish();             // (multi-GPU, first tile only)
         // staging buffer b and part C buffer (it+1)&1 are free now
         if (it + 2 < nIt) halo_before(it + 2);
         gather(veN);           // tile it+2 into buffer b (an empty group when there is none)
