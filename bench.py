@@ -305,6 +305,12 @@ def run_b200(args):
     import torch
     pd = importlib.import_module("soft-body-simulation-cuda_b200")
     rank, world, local = dist_setup(args.gpus)
+    _t0 = time.perf_counter()
+
+    def trace(what):        # PD_BENCH_TRACE=1: wall-clock milestones per rank on stderr (diagnosis of multi-GPU stalls)
+        if os.environ.get("PD_BENCH_TRACE"):
+            st = eng.dist_status() if (world > 1 and not batch) else 0
+            print(f"[trace] rank {rank} +{time.perf_counter() - _t0:8.3f} s {what} (halo status {st})", file=sys.stderr, flush=True)
     torch.cuda.set_device(local)
     batch = args.workload == "batch64"
     sc, p = make_scene(pd, args.workload, rank)
@@ -337,12 +343,13 @@ def run_b200(args):
     V0 = np.zeros_like(X0) if batch else initial_velocity(X0)
     eng.upload(V=V0)
     info = eng.info()
+    trace("engine ready")
 
     # ---- device-resident timing: inputs already in HBM, K steps bracketed by sync + events
     sampler = ClockSampler(local); sampler.start()
     for _ in range(args.warmup):
         eng.Update(1)
-    eng.synchronize(); torch.cuda.synchronize(); barrier(world)
+    eng.synchronize(); torch.cuda.synchronize(); trace("warm-up done"); barrier(world)
     sampler.mark()
     perf0 = eng.GetPerformanceData()[1].kernel_launches
     # the engine launches on its own stream, so the CUDA events are recorded there (pd_step_timed)
@@ -351,10 +358,12 @@ def run_b200(args):
     barrier(world)
     ms_step = max_over_ranks(dev_ms / args.steps, world, local)
     launches = eng.GetPerformanceData()[1].kernel_launches - perf0
+    trace("timed steps done")
 
     # ---- kernel-level roofline, measured live with CUDA events on the engine's stream
     barrier(world)
     t_local_ms, t_vertex_ms = eng.time_kernels(reps=20)
+    trace("time_kernels done")
     peak, peak_src = peaks()
     # algorithmic bytes of what THIS rank's launch processes (56 B/tet + 24 B/vertex local, 68 B/vertex global)
     nT_launch = nT if (world == 1 or batch) else eng.dist_info()["num_tets_local"]
@@ -399,6 +408,7 @@ def run_b200(args):
     else:
         job_bytes = 3 * nbytes
     halo_ok = eng.dist_status() == 0 if (world > 1 and not batch) else True
+    trace("e2e done")
     barrier(world)
 
     # ---- parity of what was just timed (outside every timed region; oracle/_ref is the CHECKER here, never the product)
@@ -423,6 +433,7 @@ def run_b200(args):
             import torch.distributed as dist
             steps_bi = 3
             Xd = engine_positions(eng, X0, steps_bi)            # owned rows filled, others 0
+            trace("parity steps done")
             own = np.zeros(nV, np.uint8); own[eng.owned_ids()] = 1
             t = torch.from_numpy(np.ascontiguousarray(Xd * own[:, None])).cuda()
             dist.all_reduce(t)                                  # disjoint owners: the sum is the assembled state, bit for bit

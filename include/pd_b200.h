@@ -60,7 +60,9 @@ typedef struct {
     int global_solver;        /* pd_global_solver                                             */
     int pcg_max_iter;         /* PCGJacobiSolver max_iter (pcgJacobi.h)                       */
     float pcg_tol;            /* PCGJacobiSolver tolerance on ||r||_2                         */
-    int handle_collision;     /* must be 0: mesh-mesh BVH/CCD is outside the hot path         */
+    int handle_collision;     /* SolverParams::handleCollision: 1 = the mesh-mesh collision pass of PdSolver::Update
+                               * (DetectCollision + CCDKernel, pdSolver.cu:218-225) between the velocity update and the
+                               * fixed bodies; single-GPU engines */
     int threads_per_block;    /* accepted for interface parity, ignored                       */
 } pd_params;
 

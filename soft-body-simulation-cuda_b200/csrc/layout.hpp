@@ -151,7 +151,7 @@ void nested_dissection_order(const CsrMatrix& A, const float* xyz, std::vector<i
 // B = P A P^T for perm[new] = old (rows of B sorted by column)
 void permute_symmetric(const CsrMatrix& A, const std::vector<int>& perm, CsrMatrix& B);
 
-// EXPERIMENT (PD_BODY_KERNEL=1, pd_body_kernel.cuh): per-body data of a scene made of many small soft bodies, one CTA per body.
+// Per-body data of a scene made of many small soft bodies, one CTA per body (pd_body_kernel.cuh).
 struct BodyDesc {           // device-visible POD, one per body
     uint32_t v0, nV;        // its vertices: entries [v0, v0 + nV) of BodyBatch::verts / md; body-local id = position
     uint32_t ptr0;          // its incidence pointers: incPtr[ptr0 .. ptr0 + nV], relative to inc0
@@ -203,17 +203,17 @@ struct RankPlan {
     std::vector<uint32_t> pushSrc, pushDst;
     std::vector<int> pushRank;
 };
-// trim (PD_DIST_TRIM=1, experiment): the ghosts of a rank are only the vertices of the tets it keeps (the tets that touch a
+// trim (the engine's default, dist_trim_from_env): the ghosts of a rank are only the vertices of the tets it keeps (the tets that touch a
 // vertex it owns), not every vertex of its boundary tiles -- the halo pushes shrink accordingly.  Same tiles either way.
 void build_rank_plan(const Layout& G, int world, int rank, RankPlan& plan, bool trim = false);
 // the rank's own Layout: selected tiles (headers re-based), local vertex ids, local slots; vertOrder maps local ->
 // ORIGINAL vertex ids so that everything downstream of a Layout works unchanged
-// EXPERIMENT (plan.trim; the engine and pd_rank_plan_build take it from the environment, PD_DIST_TRIM=1; default off): a boundary
+// plan.trim (the engine and pd_rank_plan_build take it from dist_trim_from_env: ON unless PD_DIST_TRIM=0): a boundary
 // tile is cut down to the tets that touch a vertex this rank OWNS (the others only feed ghost vertices, whose sums are never
 // read), and consecutive trimmed tiles are packed into physical tiles of up to TILE_T tets.  Every (global tile, vertex)
 // pair keeps a slot of its own with its incidence list in the original order, so the partial sums -- and the vertex sums
 // over the slots in ascending global tile order -- stay bit-identical to the single-GPU run.  Redundant tets on the 139^3
-// grid at N = 8: 13 % -> about 4 %.
+// grid at N = 8: 13 % -> 2.7 % (measured).
 void extract_rank_layout(const Layout& G, const RankPlan& plan, Layout& out);      // trims iff plan.trim
 bool dist_trim_from_env();
 

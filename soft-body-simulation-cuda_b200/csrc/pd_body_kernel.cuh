@@ -1,13 +1,14 @@
-// EXPERIMENT (PD_BODY_KERNEL=1, default off): one whole PdSolver::Update per launch for scenes
-// made of many SMALL bodies -- BASELINE config 5, batches of independent house + sphere contexts.
+// One whole PdSolver::Update per launch for scenes made of many SMALL bodies -- BASELINE config 5, batches of independent
+// house + sphere contexts.  Selected automatically (pd_engine_options::body_kernel, Engine ctor) when every connected body fits
+// one CTA's shared memory; PD_BODY_KERNEL=0 keeps the tile kernels (A/B runs).  DESIGN.md section 4.
 //
 // Without mesh-mesh collision the soft bodies of a scene share no tet, so the PD system is block diagonal per body
 //  and a body of a few thousand tets fits one SM: ONE CTA per body keeps the iterate, its
 // predecessor, the right-hand-side base term and the per-corner contributions H in shared memory and runs predictor,
 // `iterations` x (local step, Jacobi-Chebyshev sweep) and the end of step with two __syncthreads per iteration and no
 // global traffic except the (L2-resident) tet records and incidence lists.  The tile path needs 2 + 2 * iterations
-// launches per step, each far too small to fill the GPU (batch64: 166 k tets, 2.36 ms per step = 14 % of the large-mesh
-// throughput); this is one launch per step.
+// launches per step, each far too small to fill the GPU (batch64: 166 k tets, 2.31 ms per step); this is one launch per step
+// (1.43 ms, same-box A/B, profiles/r2_body_kernel_ab_batch64.txt).
 //
 // Arithmetic: the same device functions as the tile path (tet_contrib, finish_vertex) and the same forms as k_predict /
 // k_vertex_jacobi.  The sum over a vertex's contributions runs sequentially over its incidence list in ascending

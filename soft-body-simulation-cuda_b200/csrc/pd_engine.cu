@@ -105,7 +105,7 @@ struct Engine::Impl {
     double* partials = nullptr;
     int solveGrid = 0, cholGrid = 0;
     size_t nnzA = 0, nnzL = 0;
-    DistWait wait{nullptr, nullptr, nullptr, 0, 0x7fffffff, nullptr};
+    DistWait wait{nullptr, 0, 0, 0x7fffffff, nullptr};
     // mesh-mesh collision pass (pd_collision.cuh), built by the first step that asks for it
     bool colReady = false;
     ColMeshDev cm{};
@@ -156,6 +156,7 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     numSms_ = prop.multiProcessorCount;
     if (const char* e = std::getenv("PD_PDL")) { usePdl_ = std::atoi(e) != 0; pdlLate_ = std::atoi(e) == 2 ? 1 : 0; }      // experiments: PD_PDL=1 / 2
     pdlActive_ = usePdl_;
+    if (const char* e = std::getenv("PD_VERTEX_REVERSE")) vertexFlags_ = std::atoi(e) != 0 ? 2 : 0;      // (A/B runs; default on)
     CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
 
     if (opt_.rotMode < 0) {
@@ -276,7 +277,7 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
 
     // Scenes made of SMALL bodies (every connected component fits one CTA's shared memory: BASELINE config 5, the cube, house +
     // sphere) step with one CTA per body and ONE launch per step (pd_body_kernel.cuh) instead of 2 + 2 * iterations launches
-    // that cannot fill the GPU: measured 8x on batch64 (profiles/r2_*).  PD_BODY_KERNEL=0 keeps the tile path (A/B runs).
+    // that cannot fill the GPU: batch64 2.31 -> 1.43 ms per step (profiles/r2_body_kernel_ab_batch64.txt).  PD_BODY_KERNEL=0 keeps the tile path (A/B runs).
     bodyKernel_ = opt.world == 1 && opt_.rotMode != 2 && opt_.bodyKernel != 0;
     if (const char* e = std::getenv("PD_BODY_KERNEL")) bodyKernel_ = bodyKernel_ && std::atoi(e) != 0;
     std::vector<int> bodyStarts;
@@ -393,10 +394,11 @@ void Engine::prepare()
 
 // pushBuf >= 0 (multi-GPU): q is position buffer number pushBuf and the kernel first pushes its boundary entries to
 // the neighbours (DistWait in pd_kernels.cuh); -1: no push inside the kernel
-void Engine::launchLocal(const float4* q, bool jacobi, unsigned long long* prof, int pushBuf)
+void Engine::launchLocal(const float4* q, bool jacobi, unsigned long long* prof, int pushBuf, bool checkHalo)
 {
     Impl& d = *d_;
     DistWait w = d.wait;
+    if (!checkHalo) w.nNbr = 0;          // stand-alone timing launches on a buffer nobody pushed into: no tag to look for
     w.pdlLate = pdlLate_;
     if (pushBuf >= 0 && opt_.world > 1) { w.nPush = d.nPush; w.peerQ = d.peerQ + (size_t)pushBuf * d.nNbr; }
 #define PD_LOCAL(RM, JAC) launch_pdl(k_local<RM, JAC>, dim3(localGrid_), dim3(TILE_T), LOCAL_SMEM_BYTES, stream_, pdlActive_, d.records, d.tileTab, L_.nTiles, d.vstage, d.vlist, q, d.b0, d.P, prof, w)
@@ -421,12 +423,15 @@ void Engine::enqueuePredict()
     const int vb = 256, vg = (nOwn_ + vb - 1) / vb;
     base_ = (opt_.world > 1) ? (int)(phase_ % 3) : 0;
     omega_ = 1.0f;
+    // multi-GPU: every kernel that produces new positions counts one phase (the tag of the halo push, DistWait); in the
+    // lock-step test mode k_halo_push does that itself
+    unsigned long long* bump = (opt_.world > 1 && !lockstep_) ? d.epoch : nullptr;
     if (dragActive_)
         k_predict<true><<<vg, vb, 0, stream_>>>(nOwn_, d.X, d.V, d.mass, d.dbc, d.md, p.dt, dt2Prepared_, p.gravity,
-                                                d.q[base_], d.q[(base_ + 2) % 3], d.b0, d.cc, d.drag(dragTarget_, numDBC_));
+                                                d.q[base_], d.q[(base_ + 2) % 3], d.b0, d.cc, d.drag(dragTarget_, numDBC_), bump);
     else
         k_predict<false><<<vg, vb, 0, stream_>>>(nOwn_, d.X, d.V, d.mass, d.dbc, d.md, p.dt, dt2Prepared_, p.gravity,
-                                                 d.q[base_], d.q[(base_ + 2) % 3], d.b0, d.cc, DragArgs{});
+                                                 d.q[base_], d.q[(base_ + 2) % 3], d.b0, d.cc, DragArgs{}, bump);
     if (lockstep_) enqueuePush(d.q[base_], base_);      // otherwise the first local kernel pushes its input itself
     ++phase_;
 }
@@ -454,12 +459,13 @@ void Engine::enqueueIteration(int i, bool timed, size_t* ev)
     else if (i == 11) omega_ = 2 / (2 - p.rho * p.rho);
     else omega_ = 4 / (4 - p.rho * p.rho * omega_);
     const float4* dbcx = d.dbcx;
+    unsigned long long* bump = (opt_.world > 1 && !lockstep_) ? d.epoch : nullptr;      // one more phase (see enqueuePredict)
     if (dragActive_) {      // dragged vertices (cc.y < 0) keep their position (getErrorKern, pdUtil.cu:201-206)
         if (opt_.rotMode == 1) k_vertex_jacobi<false, true><<<vg, vb, 0, stream_>>>(nOwn_, cur, prev, next, dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
         else k_vertex_jacobi<true, true><<<vg, vb, 0, stream_>>>(nOwn_, cur, prev, next, dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc);
     }
-    else if (opt_.rotMode == 1) launch_pdl(k_vertex_jacobi<false>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc, pdlLate_);
-    else launch_pdl(k_vertex_jacobi<true>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc, pdlLate_);
+    else if (opt_.rotMode == 1) launch_pdl(k_vertex_jacobi<false>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc, pdlLate_ | vertexFlags_, bump);
+    else launch_pdl(k_vertex_jacobi<true>, dim3(vg), dim3(vb), 0, stream_, pdlActive_, nOwn_, cur, prev, next, dbcx, d.b0, d.cc, d.vslotPtr, d.vslot, d.P, omega_, wdbc, pdlLate_ | vertexFlags_, bump);
     if (lockstep_) enqueuePush(next, in);
     ++phase_;
     rec();
@@ -596,8 +602,7 @@ void Engine::enqueuePush(const float4* q, int bufIndex)
     if (opt_.world == 1) return;
     if (!connected_) throw std::runtime_error("multi-GPU engine stepped before pd_dist_connect");
     const int grid = std::max(1, std::min(numSms_, (d.nPush + 255) / 256));
-    k_halo_push<<<grid, 256, 0, stream_>>>(d.nPush, d.pushSrc, d.pushDst, d.pushNbr, q, d.peerQ + (size_t)bufIndex * d.nNbr, d.nNbr,
-                                           d.peerFlag, d.epoch, d.ticket);
+    k_halo_push<<<grid, 256, 0, stream_>>>(d.nPush, d.pushSrc, d.pushDst, d.pushNbr, q, d.peerQ + (size_t)bufIndex * d.nNbr, d.epoch, d.ticket);
 }
 
 // The launch sequence of one PdSolver::Update in Jacobi mode.  `timed` brackets the local /
@@ -1019,7 +1024,7 @@ float Engine::timeLocalKernelMs(int reps)
     CUDA_CHECK(cudaEventRecord(a, stream_));
     pdlActive_ = false;                    // isolated launches: no overlap with the neighbouring launch
     for (int r = 0; r < reps; ++r) {
-        launchLocal(d.XT, true);
+        launchLocal(d.XT, true, nullptr, -1, false);
     }
     pdlActive_ = usePdl_;
     CUDA_CHECK(cudaEventRecord(b, stream_));
@@ -1321,7 +1326,7 @@ void Engine::setPeers(const std::vector<uint8_t*>& peerBase)
         CUDA_CHECK(cudaMemcpy(d.peerQ, pq.data(), (size_t)3 * d.nNbr * sizeof(float4*), cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaMemcpy(d.peerFlag, pf.data(), (size_t)d.nNbr * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
     }
-    d.wait = DistWait{d.flags, d.epoch, d.nbrRanks, d.nNbr, plan_.nInteriorTiles, d.status, 0, d.pushSrc, d.pushDst, d.pushNbr, d.peerQ, d.peerFlag, d.ticket};
+    d.wait = DistWait{d.epoch, d.nNbr, nOwn_, plan_.nInteriorTiles, d.status, 0, d.pushSrc, d.pushDst, d.pushNbr, d.peerQ};
     connected_ = true;
 }
 
@@ -1421,8 +1426,8 @@ void Engine::profileLocal(unsigned long long* out)
     unsigned long long* dprof = nullptr;
     CUDA_CHECK(cudaMalloc(&dprof, 64ull * localGrid_));
     CUDA_CHECK(cudaMemsetAsync(dprof, 0, 64ull * localGrid_, stream_));
-    launchLocal(d_->XT, true, nullptr);            // warm
-    launchLocal(d_->XT, true, dprof);
+    launchLocal(d_->XT, true, nullptr, -1, false);            // warm
+    launchLocal(d_->XT, true, dprof, -1, false);
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     CUDA_CHECK(cudaMemcpy(out, dprof, 64ull * localGrid_, cudaMemcpyDeviceToHost));
     cudaFree(dprof);

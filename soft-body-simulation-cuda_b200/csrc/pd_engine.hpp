@@ -124,7 +124,7 @@ private:
     float* qbuf(int k) const;
     void ensureDragBuffers();
     void finishDragUpdate(const float target[3]);
-    void launchLocal(const float4* q, bool jacobi, unsigned long long* prof = nullptr, int pushBuf = -1);
+    void launchLocal(const float4* q, bool jacobi, unsigned long long* prof = nullptr, int pushBuf = -1, bool checkHalo = true);
     template <typename T> T* dalloc(size_t n);
     void dfree(const void* p, size_t bytes);
     void waitCallerStream();
@@ -144,6 +144,8 @@ private:
     EngineOptions opt_;
     bool ready_ = false, perf_ = false, graphValid_ = false;
     bool pdlActive_ = false;
+    int vertexFlags_ = 2;     // k_vertex_jacobi flag bit 1: its blocks walk the vertices from the END of the array (-0.4 % per step on grid139,
+                              // profiles/r2_vertex_fold_reverse_ab_grid139.txt); PD_VERTEX_REVERSE=0 for A/B runs
     int pdlLate_ = 0;         // PD_PDL=2: the dependents are released at the END of every CTA's work instead of at its start
     bool usePdl_ = false;     // programmatic dependent launch of the per-iteration kernels (pd_kernels.cuh: pdl_wait); measured SLOWER
                               // on B200 (grid139: 42.0 vs 36.9 ms/step, batch64: 2.68 vs 2.23), so it stays an opt-in experiment (PD_PDL=1)

@@ -75,7 +75,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 constexpr unsigned long long L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
 #ifdef PD_HOST_EMU
 __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, unsigned long long) { bulk_g2s(dst, src, bytes, bar); }
-__device__ __forceinline__ void cp_async16_hint(uint32_t dstShared, const void* src, unsigned long long) { std::memcpy(pd_emu::cta->smem + dstShared, src, 16); }
+__device__ __forceinline__ void cp_async16_hint(uint32_t dstShared, const void* src, unsigned long long)
+{   // (a ghost position may be arriving from another rank's thread right now: fourth lane -- the tag -- first, with acquire, so
+    // that a fresh tag is never paired with a stale payload; see st_tagged_sys)
+    uint32_t w = __atomic_load_n(static_cast<const uint32_t*>(src) + 3, __ATOMIC_ACQUIRE);
+    std::memcpy(pd_emu::cta->smem + dstShared, src, 12);
+    std::memcpy(pd_emu::cta->smem + dstShared + 12, &w, 4);
+}
 __device__ __forceinline__ void cp_async_commit() {}
 __device__ __forceinline__ void cp_async_wait_all() {}
 __device__ __forceinline__ void cp_async_wait_1() {}
@@ -114,83 +120,101 @@ __device__ __forceinline__ float4 ldg_hint(const float4* p, unsigned long long p
 #endif
 
 // ------------------------------------------------------------------ multi-GPU halo exchange
-// Every rank owns an exchange window [q0 | q1 | q2 | flags[world] | epoch | ticket | status] that its
-// neighbours map (CUDA IPC, or plain pointers inside one process).  Every phase that produced new positions
-// (predictor, every PD iteration) is followed by a PUSH of the owner's boundary vertices straight into the
-// neighbours' ghost entries over NVLink, after which the owner raises its flag there to its push count (epoch).
-// The push rides at the start of the local kernel that consumes those positions (below; k_halo_push is the
-// stand-alone form for the PCG path and the lock-step test driver).  The consumer is that same local kernel on the
-// other side: before the gather of its first boundary tile it waits until every neighbour's flag has reached its own
-// epoch -- all ranks push the same number of times in the same order.
+// Every rank owns an exchange window [q0 | q1 | q2 | ...] that its neighbours map (CUDA IPC, or plain pointers inside one
+// process).  Every phase that produced new positions (predictor, every PD iteration) is followed by a PUSH of the owner's
+// boundary vertices straight into the neighbours' ghost entries over NVLink.  The push rides at the start of the local kernel
+// that consumes those positions (below; k_halo_push is the stand-alone form for the PCG path and the lock-step test driver).
+// FLAG IN THE DATA: a pushed position travels as ONE 16-byte store (x, y, z, tag), tag = the rank's phase count (`epoch`, the
+// same number on every rank for the same phase), and a 16-byte aligned store is delivered whole.  The producer therefore
+// needs NO fence, ticket or flag -- it fires its stores and goes on (a system-scope fence after remote stores costs an NVLink
+// round trip, ~5 us per CTA and iteration when every CTA of the persistent grid had to publish its slice: measured,
+// profiles/r2_dist_probes_n2_grid70.txt) -- and the consumer is the same launch on the other side: a thread that staged a ghost
+// position for a boundary tile looks at the tag before the block barrier that hands the staging buffer to phase B and, only if
+// it is stale, polls the entry itself.  A ghost entry of buffer k is rewritten every third phase (the buffers rotate), so a stale
+// tag is the phase count minus three; the skew bound that makes the rotation safe is in pd_engine.cu:enqueueIteration.
 struct DistWait {
-    const unsigned long long* flags;   // this rank's flag array, written by the peers (indexed by rank)
-    unsigned long long* epoch;         // this rank's own push count
-    const int* nbr;                    // neighbour ranks
-    int nNbr;                          // 0 on a single GPU: no wait at all
+    const unsigned long long* epoch;   // this rank's phase count = the tag of the positions this launch reads (bumped by k_predict /
+                                       // k_vertex_jacobi / k_halo_push, never inside the local kernel)
+    int nNbr;                          // 0 on a single GPU: no push, no check
+    int nOwn;                          // local vertex ids >= nOwn are ghosts
     int firstTile;                     // first tile (in this rank's processing order) that reads ghost positions
     unsigned int* status;              // set to 1 when a wait gave up (peer died); results are then invalid
     // push at the START of the local kernel (nPush == 0: the pushes were separate launches): the boundary entries of
     // the position buffer this launch reads -> the neighbours' ghost entries, in push-list order (consecutive
-    // destinations: full 128-byte NVLink writes), then this rank's flag at the neighbours
+    // destinations: full 128-byte NVLink writes)
     int nPush;
     const uint32_t* pushSrc;           // owned local vertex
     const uint32_t* pushDst;           // ghost index at the neighbour
     const uint32_t* pushNbr;           // neighbour slot
     float4* const* peerQ;              // [nNbr]: the neighbours' copies of the buffer this launch reads
-    unsigned long long* const* peerFlag;   // [nNbr]: this rank's entry in the neighbours' flag arrays
-    unsigned int* ticket;
     // programmatic dependent launch (PD_PDL): 0 / 1 = the successor may be scheduled as soon as every CTA has STARTED (measured
     // slower: its CTAs take SM slots from this kernel's), 2 = only once every CTA has finished its tiles (hides the launch latency)
     int pdlLate;
 };
-constexpr long long DIST_WAIT_LIMIT_CYCLES = 20000000000ll;    // ~10 s: a hung peer must not hang this GPU
+constexpr long long DIST_WAIT_LIMIT_CYCLES = 20000000000ll;    // ~10 s (ranks may enter their first step seconds apart): a hung peer must not hang this GPU
 
+// one position + tag as a single 128-bit access at system scope (single-copy atomic: value and tag arrive together)
 #ifdef PD_HOST_EMU
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
-#else
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+__device__ __forceinline__ void st_tagged_sys(float4* p, float4 v)
+{   // the host has no 16-byte store that other threads see whole: payload first, then the tag with release
+    p->x = v.x; p->y = v.y; p->z = v.z;
+    __atomic_store_n(reinterpret_cast<uint32_t*>(&p->w), __float_as_uint(v.w), __ATOMIC_RELEASE);
+}
+__device__ __forceinline__ float4 ld_tagged_sys(const float4* p)
+{   // ... and the tag first, with acquire
+    float4 v;
+    v.w = __uint_as_float(__atomic_load_n(reinterpret_cast<const uint32_t*>(&p->w), __ATOMIC_ACQUIRE));
+    v.x = p->x; v.y = p->y; v.z = p->z;
     return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+#else
+__device__ __forceinline__ void st_tagged_sys(float4* p, float4 v)
 {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("{\n\t.reg .b128 t;\n\tmov.b128 t, {%1, %2, %3, %4};\n\tst.relaxed.sys.global.b128 [%0], t;\n\t}"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld_tagged_sys(const float4* p)
+{
+    float4 v;
+    asm volatile("{\n\t.reg .b128 t;\n\tld.relaxed.sys.global.b128 t, [%4];\n\tmov.b128 {%0, %1, %2, %3}, t;\n\t}"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
 }
 #endif
-// wait until every neighbour's flag has reached `need` (= this rank's push count including this phase's push)
-__device__ __forceinline__ void dist_wait(const DistWait& w, int tid, unsigned long long need)
+// the tag of phase count e (never the 0 of a fresh buffer: the count starts at 1 before anything is consumed)
+__device__ __forceinline__ float halo_tag(unsigned long long e) { return __uint_as_float((uint32_t)e); }
+
+// ghost position `g` of the buffer this launch reads, staged at `slot` (shared memory) by the asynchronous gather: make sure it
+// carries this phase's tag; poll the entry itself while it does not (bounded: a dead peer sets the status word instead of
+// hanging this GPU)
+__device__ __forceinline__ void halo_check_staged(float4* slot, const float4* g, uint32_t tag, unsigned int* status)
 {
-    if (tid < w.nNbr) {
-        const unsigned long long* f = w.flags + w.nbr[tid];
-        const long long t0 = clock64();
-        while (ld_acquire_sys(f) < need) {
-            if (clock64() - t0 > DIST_WAIT_LIMIT_CYCLES) { atomicExch(w.status, 1u); break; }
-            __nanosleep(64);
-        }
+    if (__float_as_uint(slot->w) == tag) return;
+    const long long t0 = clock64();
+    for (;;) {
+        const float4 v = ld_tagged_sys(g);
+        if (__float_as_uint(v.w) == tag) { *slot = v; return; }
+        if (clock64() - t0 > DIST_WAIT_LIMIT_CYCLES) { atomicExch(status, 1u); return; }
+        __nanosleep(64);
     }
-    __syncthreads();
 }
 
-// positions of this rank's boundary vertices -> the neighbours' ghost entries, then (last block) the flags
+// stand-alone push (PCG path, lock-step test driver): positions of this rank's boundary vertices -> the neighbours' ghost
+// entries, tagged with the NEW phase count, which the last block then makes current
 __global__ void k_halo_push(int n, const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst, const uint32_t* __restrict__ nbrIdx,
-                            const float4* __restrict__ q, float4* const* __restrict__ peerQ, int nNbr,
-                            unsigned long long* const* __restrict__ peerFlag, unsigned long long* epoch, unsigned int* ticket)
+                            const float4* __restrict__ q, float4* const* __restrict__ peerQ, unsigned long long* epoch, unsigned int* ticket)
 {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) peerQ[nbrIdx[i]][dst[i]] = q[src[i]];
+    const unsigned long long e = *epoch + 1ull;            // (read before this block's ticket, hence before the last block bumps it)
+    const float tag = halo_tag(e);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 v = q[src[i]];
+        v.w = tag;
+        st_tagged_sys(&peerQ[nbrIdx[i]][dst[i]], v);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();                        // one per block, cumulative over the block's stores (barrier above)
         const unsigned int t = atomicAdd(ticket, 1u);
-        if (t == gridDim.x - 1) {                      // every block's stores are fenced: publish
-            *ticket = 0u;
-            const unsigned long long e = *epoch + 1ull;
-            *epoch = e;
-            __threadfence_system();
-            for (int j = 0; j < nNbr; ++j) st_release_sys(peerFlag[j], e);
-        }
+        if (t == gridDim.x - 1) { *ticket = 0u; *epoch = e; }
     }
 }
 
@@ -219,9 +243,11 @@ __global__ void k_predict(int nV, const float4* __restrict__ X, const float4* __
                           const float* __restrict__ mass, const float* __restrict__ dbc,
                           const float* __restrict__ md, float dt, float dt2Prepared, float gravity,
                           float4* __restrict__ q0, float4* __restrict__ qprev, float4* __restrict__ b0,
-                          float2* __restrict__ cc, DragArgs dr)
+                          float2* __restrict__ cc, DragArgs dr, unsigned long long* epochBump = nullptr)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    // multi-GPU: this kernel produced new positions -- one more phase (DistWait; the next local kernel pushes them with this tag)
+    if (epochBump && v == 0) *epochBump += 1ull;
     if (v >= nV) return;
     const float m = mass[v], isDbc = dbc[v];
     const float dt2 = __fmul_rn(dt, dt);
@@ -245,11 +271,15 @@ __global__ void k_predict(int nV, const float4* __restrict__ X, const float4* __
         s.z = __fmaf_rn(0.0f, dt2_m_1, __fmaf_rn(vel.z, dt, x.z));
         s.w = 0.f;
     }
+    const float den = __fadd_rn(c, md[v]);
+    const float2 c2 = make_float2(isDbc > 0.f ? -c : c, (DRAG && wi > 0.f) ? -den : den);
+    cc[v] = c2;
+    // the same two scalars ride in the unused w lanes of the arrays the Jacobi sweep reads anyway (b0.w = +-c; q.w = +-(c + md),
+    // handed from iterate to iterate), so that sweep does not read cc at all: 8 bytes per vertex and iteration less
+    s.w = c2.y;
     q0[v] = s;
     qprev[v] = s;
-    b0[v] = make_float4(__fmul_rn(c, s.x), __fmul_rn(c, s.y), __fmul_rn(c, s.z), 0.f);
-    const float den = __fadd_rn(c, md[v]);
-    cc[v] = make_float2(isDbc > 0.f ? -c : c, (DRAG && wi > 0.f) ? -den : den);
+    b0[v] = make_float4(__fmul_rn(c, s.x), __fmul_rn(c, s.y), __fmul_rn(c, s.z), c2.x);
 }
 
 // ------------------------------------------------------------------ local step (the hot kernel)
@@ -285,7 +315,7 @@ constexpr uint32_t LOCAL_OFF_QS = 0u;
 constexpr uint32_t LOCAL_OFF_HS = LOCAL_OFF_QS + 2u * LOCAL_QS_BYTES;
 constexpr uint32_t LOCAL_OFF_C = LOCAL_OFF_HS + 2u * LOCAL_HS_BYTES;
 constexpr uint32_t LOCAL_OFF_BAR = LOCAL_OFF_C + 2u * TILE_CMAX;
-constexpr uint32_t LOCAL_SMEM_BYTES = LOCAL_OFF_BAR + 32u;      // two mbarriers, the halo epoch this launch waits for
+constexpr uint32_t LOCAL_SMEM_BYTES = LOCAL_OFF_BAR + 32u;      // two mbarriers
 static_assert(4u * (LOCAL_SMEM_BYTES + 1024u) <= 233472u, "4 CTAs of the local kernel must fit one SM's shared memory");
 static_assert(TILE_NLMAX == TILE_T, "one tile-local vertex per thread");
 // (the per-tile entry of the device tile table, TILE_META_WORDS words, is described in layout.hpp)
@@ -485,12 +515,6 @@ __device__ __forceinline__ void local_phase_b(const float4 r0, const float4 r1, 
         h_store(Hline, 3u, c23 >> 16, h3);
 }
 
-// the thread of a CTA that publishes the CTA's part of the halo push: lane 0 of the last warp (the producer; that warp
-// carries the least phase C work).  PD_PUSH_PUBLISH_EARLY=1 (experiments): publish in the prologue, before the first gather
-#ifndef PD_PUSH_PUBLISH_EARLY
-#define PD_PUSH_PUBLISH_EARLY 0
-#endif
-#define PD_PUSH_PUBLISH_TID(tid) ((tid) == TILE_T - 32)
 template <int ROT_MODE, bool JACOBI, bool PROF = false>
 __global__ void __launch_bounds__(TILE_T, 4)
 k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMeta, int nTiles,
@@ -512,36 +536,22 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
     }
     if (tid < 16) *reinterpret_cast<float4*>(smem + LOCAL_OFF_HS + (tid >> 3) * LOCAL_HS_BYTES + TILE_ZERO_OFF + 16 * (tid & 7)) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    // multi-GPU: the rank's interior tiles come first; the neighbours' ghost positions are needed -- and waited
-    // for -- only before the position gather of the first boundary tile, so the exchange hides behind the interior
-    bool needHalo = dw.nNbr > 0;
-    volatile unsigned long long* haloNeed = reinterpret_cast<volatile unsigned long long*>(smem + LOCAL_OFF_BAR + 16);   // (not a register: 64 regs are full)
-    // this CTA's part of the halo push is PUBLISHED (system fence over its remote stores, ticket, and -- by the last CTA --
-    // the flags at the neighbours) by one thread, off the critical path: after the barrier of the CTA's first tile, when
-    // the stores issued in the prologue have long completed, or before the CTA's first wait for the neighbours if that
-    // comes earlier (a CTA must never wait for a peer before it has published: the peer's CTAs wait for this rank's flag)
-    bool pushPending = false;
-    auto publish = [&]() {
-        if (pushPending) {
-            pushPending = false;
-            __threadfence_system();            // one per CTA, cumulative over the CTA's remote stores (a block barrier lies between)
-            const unsigned int t = atomicAdd(dw.ticket, 1u);
-            if (t == gridDim.x - 1) {          // every CTA's stores are fenced: publish
-                const unsigned long long e = *haloNeed;
-                *dw.ticket = 0u;
-                *dw.epoch = e;
-                __threadfence_system();
-                for (int j = 0; j < dw.nNbr; ++j) st_release_sys(dw.peerFlag[j], e);
-            }
-        }
-    };
-    auto halo_before = [&](int k) {
-        if (needHalo && (int)(blockIdx.x + k * gridDim.x) >= dw.firstTile) { publish(); dist_wait(dw, tid, *haloNeed); needHalo = false; }
-    };
     auto meta_of = [&](int k) -> const uint32_t* { return tileMeta + (size_t)(blockIdx.x + k * gridDim.x) * TILE_META_WORDS; };
     const int warp = tid >> 5, lane = tid & 31;
     // the vertex staged in this thread's staging slot for tile number k of this CTA (Layout::vstage)
     auto load_ve = [&](int k) -> uint32_t { return __ldg(&vstage[(blockIdx.x + k * gridDim.x) * (unsigned)TILE_NLMAX + tid]); };
+    // multi-GPU: the rank's interior tiles come first; only its boundary tiles (>= firstTile) read ghost positions.  After this
+    // thread's asynchronous copy for tile k has landed and BEFORE the barrier that hands the staging buffer to phase B, a thread
+    // that staged a ghost checks its tag (DistWait) -- normally one shared-memory load and a compare: the neighbours pushed at the
+    // start of their launch and the boundary tiles come last
+    auto halo_check = [&](int k) {
+        if (dw.nNbr > 0 && (int)(blockIdx.x + k * gridDim.x) >= dw.firstTile) {
+            const uint32_t ve = load_ve(k) & ~TILE_OWNER_BIT;         // (0xffffffff = empty slot: not < anything below)
+            if (ve != (0xffffffffu & ~TILE_OWNER_BIT) && (int)ve >= dw.nOwn)
+                halo_check_staged(reinterpret_cast<float4*>(smem + LOCAL_OFF_QS + (k & 1) * LOCAL_QS_BYTES + 16 * tid), &q[ve],
+                                  (uint32_t)*dw.epoch, dw.status);
+        }
+    };
     // this thread's record (three coalesced 16-byte planes) of a tile with nTets tets whose record starts at 16 * off16
     auto load_rec = [&](uint32_t off16, uint32_t nTets, float4& a0, float4& a1, float4& a2) {
         const uint8_t* base = records + 16ull * off16 + TILE_OFF_TETS + 16 * tid;
@@ -554,6 +564,9 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
     uint32_t gdst = smem_u32(smem + LOCAL_OFF_QS + 16 * tid);
     uint32_t gdstOther = gdst + LOCAL_QS_BYTES;
     auto gather = [&](uint32_t ve) {
+#ifndef PD_HOST_EMU
+        asm volatile("" : "+r"(gdst));      // (opaque to the optimiser: the destination stays a plain per-thread register, see above)
+#endif
         if (ve != 0xffffffffu) {
             cp_async16_hint(gdst, &q[ve & ~TILE_OWNER_BIT], L2_EVICT_LAST);
             if (ROT_MODE == 1 && (ve & TILE_OWNER_BIT)) prefetch_l2(&b0[ve & ~TILE_OWNER_BIT]);
@@ -596,27 +609,22 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
     // the slots that launch reads)
     if (dw.pdlLate == 0) pdl_launch_dependents();
     pdl_wait();
-    if (dw.nNbr > 0) {
-        // this rank's push count so far (read before this CTA's ticket, hence before the last CTA bumps it), plus this
-        // launch's own push
-        if (tid == 0) *haloNeed = *reinterpret_cast<const volatile unsigned long long*>(dw.epoch) + (dw.nPush > 0 ? 1ull : 0ull);
-        // multi-GPU halo push, spread over all CTAs: the exchange overlaps the interior tiles, and the receivers
-        // wait (halo_before) only before their first boundary tile
-        for (int i = blockIdx.x * TILE_T + tid; i < dw.nPush; i += gridDim.x * TILE_T)
-            dw.peerQ[dw.pushNbr[i]][dw.pushDst[i]] = q[dw.pushSrc[i]];
-        __syncthreads();
-        pushPending = PD_PUSH_PUBLISH_TID(tid) && dw.nPush > 0;
-#if PD_PUSH_PUBLISH_EARLY
-        publish();
-#endif
+    if (dw.nPush > 0) {
+        // multi-GPU halo push, spread over all CTAs, fire and forget: every position travels with this phase's tag in one
+        // 16-byte store (DistWait); the exchange overlaps the interior tiles
+        const float tag = halo_tag(*dw.epoch);
+        for (int i = blockIdx.x * TILE_T + tid; i < dw.nPush; i += gridDim.x * TILE_T) {
+            float4 v = q[dw.pushSrc[i]];
+            v.w = tag;
+            st_tagged_sys(&dw.peerQ[dw.pushNbr[i]][dw.pushDst[i]], v);
+        }
     }
-    halo_before(0);
     gather(veN);
     veN = (nIt > 1) ? load_ve(1) : 0xffffffffu;
-    if (nIt > 1) halo_before(1);
     gather(veN);
     veN = (nIt > 2) ? load_ve(2) : 0xffffffffu;                  // vlist entry of tile it+2
     cp_async_wait_1();       // this thread's part of tile 0 has landed
+    halo_check(0);
     __syncthreads();         // tile 0 staged
 
     // the next tile's group words (phase C) ...
@@ -646,12 +654,11 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
         // the record registers are free: fetch the next tile's record (consumed after this tile's phase C)
         if (it + 1 < nIt) load_rec(off16N, ntvN & 0xffffu, r0, r1, r2);
         cp_async_wait_all();   // this thread's part of tile it+1's positions has landed
+        if (it + 1 < nIt) halo_check(it + 1);
         PD_TICK(1)
         __syncthreads();       // H scratch of tile it complete; tile it+1 staged; every warp is past phase C of tile it-1
         PD_TICK(2)
-        publish();             // (multi-GPU, first tile only)
         // staging buffer b and part C buffer (it+1)&1 are free now
-        if (it + 2 < nIt) halo_before(it + 2);
         gather(veN);           // tile it+2 into buffer b (an empty group when there is none)
         if (producer) {
             if (it >= 1 && it + 1 < nIt) fetch_c(it + 1);
@@ -690,6 +697,9 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
 // under-relaxation as one DFMA (the reference's `0.9 *` literal is a double); Chebyshev as one FFMA.
 // Multi-GPU: the halo push of the new positions happens at the start of the NEXT local kernel (k_local, DistWait), in
 // push-list order; this kernel is the same on one and on many GPUs.
+#ifndef PD_FOLD_CC
+#define PD_FOLD_CC 1
+#endif
 #ifndef PD_VERTEX_MINBLOCKS
 #define PD_VERTEX_MINBLOCKS 8      // resident 256-thread blocks per SM (32 registers): measured 66 vs 76 us on grid139 against 6 (40 registers)
 #endif
@@ -737,13 +747,25 @@ __global__ void __launch_bounds__(256, PD_VERTEX_MINBLOCKS) k_vertex_jacobi(int 
                                 float4* __restrict__ qnext, const float4* __restrict__ X0 /* DBCX */, const float4* __restrict__ b0,
                                 const float2* __restrict__ cc, const uint32_t* __restrict__ vslotPtr,
                                 const uint32_t* __restrict__ vslot, const float4* __restrict__ P,
-                                float omega, float wdbc, int pdlLate = 0)
+                                float omega, float wdbc, int flags = 0, unsigned long long* epochBump = nullptr)
 {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    // flags: bit 0 = PD_PDL=2 (see DistWait::pdlLate); bit 1 = blocks walk the vertices from the END of the array (the engine's
+    // default: the slots the local kernel wrote last -- still in L2 -- are read first, and the positions this kernel writes last
+    // are the ones the next local kernel gathers first; -0.4 % per step on grid139)
+    const int pdlLate = flags & 1;
+    const int v = (int)((flags & 2) ? gridDim.x - 1u - blockIdx.x : blockIdx.x) * (int)blockDim.x + (int)threadIdx.x;
     if (pdlLate == 0) pdl_launch_dependents();
-    pdl_wait();              // the slots (and, multi-GPU, the ticket) come from the local kernel just before
+    pdl_wait();              // the slots come from the local kernel just before
+    if (epochBump && blockIdx.x == 0 && threadIdx.x == 0) *epochBump += 1ull;      // multi-GPU: one more phase (see k_predict)
     if (v < nV) {
+        const float4 q = qcur[v], pr = qprev[v];
+#if PD_FOLD_CC
+        // (+-c, +-(c + matrix_diag)) from the w lanes of b0 and of the current iterate (k_predict); the faithful mode, whose owner
+        // slot already holds b0, keeps reading cc
+        const float2 c2 = BASE ? make_float2(b0[v].w, q.w) : cc[v];
+#else
         const float2 c2 = cc[v];
+#endif
         const float c = fabsf(c2.x);
         float bx, by, bz;
         if (c2.x < 0.f) {                 // computeDBCLocal overwrites b for pinned vertices; DBCX = X0 (pdSolver.cu:134)
@@ -752,7 +774,6 @@ __global__ void __launch_bounds__(256, PD_VERTEX_MINBLOCKS) k_vertex_jacobi(int 
         } else {
             vertex_slot_sum<BASE>(v, b0, vslotPtr, vslot, P, bx, by, bz);
         }
-        const float4 q = qcur[v], pr = qprev[v];
         const float den = DRAG ? fabsf(c2.y) : c2.y;
         float nx = __fadd_rn(__fdiv_rn(__fmaf_rn(-c, q.x, bx), den), q.x);
         float ny = __fadd_rn(__fdiv_rn(__fmaf_rn(-c, q.y, by), den), q.y);
@@ -765,7 +786,7 @@ __global__ void __launch_bounds__(256, PD_VERTEX_MINBLOCKS) k_vertex_jacobi(int 
         nx = __fmaf_rn(__fsub_rn(nx, pr.x), omega, pr.x);
         ny = __fmaf_rn(__fsub_rn(ny, pr.y), omega, pr.y);
         nz = __fmaf_rn(__fsub_rn(nz, pr.z), omega, pr.z);
-        const float4 out = make_float4(nx, ny, nz, 0.f);
+        const float4 out = make_float4(nx, ny, nz, q.w);
         qnext[v] = out;
     }
     if (pdlLate) pdl_launch_dependents();

@@ -67,9 +67,9 @@ void step_once(Emu& e, float dt, float gravity, float rho, float muN, float muT,
         const unsigned vg = (unsigned)((r.nOwn + vb - 1) / vb);
         const DragArgs dr{r.more.data(), r.offX.data(), r.dbcx.data(), e.target[0], e.target[1], e.target[2], e.numDBC > 0 ? 1 : 0};
         if (e.drag) pd_emu::launch_flat(vg, vb, k_predict<true>, r.nOwn, r.X.data(), r.V.data(), r.mass.data(), r.dbc.data(), r.md.data(), dt, e.dt2Prepared,
-                                        gravity, r.q[0].data(), r.q[2].data(), r.b0.data(), r.cc.data(), dr);
+                                        gravity, r.q[0].data(), r.q[2].data(), r.b0.data(), r.cc.data(), dr, (unsigned long long*)nullptr);
         else pd_emu::launch_flat(vg, vb, k_predict<false>, r.nOwn, r.X.data(), r.V.data(), r.mass.data(), r.dbc.data(), r.md.data(), dt, e.dt2Prepared,
-                                 gravity, r.q[0].data(), r.q[2].data(), r.b0.data(), r.cc.data(), DragArgs{});
+                                 gravity, r.q[0].data(), r.q[2].data(), r.b0.data(), r.cc.data(), DragArgs{}, (unsigned long long*)nullptr);
     }
     push(e, 0); push(e, 2);
     float omega = 1.0f;
@@ -89,10 +89,10 @@ void step_once(Emu& e, float dt, float gravity, float rho, float muN, float muT,
                            (const float4*)r.b0.data(), r.Pslots.data(), (unsigned long long*)nullptr, dw);
             if (e.drag) pd_emu::launch_flat(vg, vb, k_vertex_jacobi<BASE, true>, r.nOwn, (const float4*)r.q[ic].data(), (const float4*)r.q[ip].data(), r.q[in].data(),
                                             (const float4*)r.dbcx.data(), (const float4*)r.b0.data(), (const float2*)r.cc.data(), (const uint32_t*)r.L.vslotPtr.data(),
-                                            (const uint32_t*)r.L.vslot.data(), (const float4*)r.Pslots.data(), omega, wdbc, 0);
+                                            (const uint32_t*)r.L.vslot.data(), (const float4*)r.Pslots.data(), omega, wdbc, 0, (unsigned long long*)nullptr);
             else pd_emu::launch_flat(vg, vb, k_vertex_jacobi<BASE, false>, r.nOwn, (const float4*)r.q[ic].data(), (const float4*)r.q[ip].data(), r.q[in].data(),
                                      (const float4*)r.dbcx.data(), (const float4*)r.b0.data(), (const float2*)r.cc.data(), (const uint32_t*)r.L.vslotPtr.data(),
-                                     (const uint32_t*)r.L.vslot.data(), (const float4*)r.Pslots.data(), omega, wdbc, 0);
+                                     (const uint32_t*)r.L.vslot.data(), (const float4*)r.Pslots.data(), omega, wdbc, 0, (unsigned long long*)nullptr);
         }
         push(e, in);
     }
@@ -108,8 +108,8 @@ void step_once(Emu& e, float dt, float gravity, float rho, float muN, float muT,
 
 }  // namespace
 
-// One rank's whole step with the halo push INSIDE the local kernel (DistWait: push-list slices by all CTAs, ticket, epoch,
-// flags, wait before the first boundary tile), as Engine::step drives it on one GPU per process.  The ranks run
+// One rank's whole step with the halo push INSIDE the local kernel (DistWait: push-list slices by all CTAs, every position with
+// the phase's tag in its fourth lane; the tag checked on the staged ghosts of the boundary tiles), as Engine::step drives it on one GPU per process.  The ranks run
 // concurrently, one driving thread each, all CTAs of a launch resident at once.
 template <int RM, bool BASE>
 void rank_step_concurrent(Emu& e, Rank& r, float dt, float gravity, float rho, float muN, float muT, int iters)
@@ -119,7 +119,7 @@ void rank_step_concurrent(Emu& e, Rank& r, float dt, float gravity, float rho, f
     const unsigned vg = (unsigned)((r.nOwn + vb - 1) / vb);
     const int base = (int)(r.phase % 3);
     pd_emu::launch_flat(vg, vb, k_predict<false>, r.nOwn, r.X.data(), r.V.data(), r.mass.data(), r.dbc.data(), r.md.data(), dt, e.dt2Prepared,
-                        gravity, r.q[base].data(), r.q[(base + 2) % 3].data(), r.b0.data(), r.cc.data(), DragArgs{});
+                        gravity, r.q[base].data(), r.q[(base + 2) % 3].data(), r.b0.data(), r.cc.data(), DragArgs{}, &r.epoch);
     ++r.phase;
     float omega = 1.0f;
     const int nNbr = (int)r.P.neighbours.size();
@@ -129,16 +129,16 @@ void rank_step_concurrent(Emu& e, Rank& r, float dt, float gravity, float rho, f
         else if (i == 11) omega = 2 / (2 - rho * rho);
         else omega = 4 / (4 - rho * rho * omega);
         DistWait dw{};
-        dw.flags = r.flags.data(); dw.epoch = &r.epoch; dw.nbr = r.P.neighbours.data(); dw.nNbr = nNbr; dw.firstTile = r.P.nInteriorTiles;
+        dw.epoch = &r.epoch; dw.nNbr = nNbr; dw.nOwn = r.nOwn; dw.firstTile = r.P.nInteriorTiles;
         dw.status = &r.status; dw.nPush = (int)r.P.pushSrc.size(); dw.pushSrc = r.P.pushSrc.data(); dw.pushDst = r.P.pushDst.data();
-        dw.pushNbr = r.pushNbr.data(); dw.peerQ = r.peerQ.data() + (size_t)ic * nNbr; dw.peerFlag = r.peerFlag.data(); dw.ticket = &r.ticket;
+        dw.pushNbr = r.pushNbr.data(); dw.peerQ = r.peerQ.data() + (size_t)ic * nNbr;
         const unsigned grid = (unsigned)std::min(r.L.nTiles, e.grid);
         pd_emu::launch_resident(grid, (unsigned)TILE_T, LOCAL_SMEM_BYTES, k_local<RM, true, false>, (const uint8_t*)r.L.records.data(), (const uint32_t*)r.tileTab.data(),
                                 r.L.nTiles, (const uint32_t*)r.L.vstage.data(), (const uint32_t*)r.L.vlist.data(), (const float4*)r.q[ic].data(),
                                 (const float4*)r.b0.data(), r.Pslots.data(), (unsigned long long*)nullptr, dw);
         pd_emu::launch_flat(vg, vb, k_vertex_jacobi<BASE, false>, r.nOwn, (const float4*)r.q[ic].data(), (const float4*)r.q[ip].data(), r.q[in].data(),
                             (const float4*)r.dbcx.data(), (const float4*)r.b0.data(), (const float2*)r.cc.data(), (const uint32_t*)r.L.vslotPtr.data(),
-                            (const uint32_t*)r.L.vslot.data(), (const float4*)r.Pslots.data(), omega, wdbc, 0);
+                            (const uint32_t*)r.L.vslot.data(), (const float4*)r.Pslots.data(), omega, wdbc, 0, &r.epoch);
         ++r.phase;
     }
     pd_emu::launch_flat(vg, vb, k_finish<false>, r.nOwn, (const float4*)r.q[(base + iters) % 3].data(), dtInv, r.X.data(), r.XT.data(), r.V.data(), e.dfb, muT, muN,

@@ -312,3 +312,20 @@ def test_gpu_scripts_parse(tmp_path):
         py_compile.compile(f, doraise=True, cfile=str(tmp_path / (os.path.basename(f) + "c")))
     for f in glob.glob(os.path.join(ROOT, "scripts", "*.sh")):
         subprocess.check_call(["bash", "-n", f])
+
+
+def test_no_ldgsts_with_uniform_register_offset():
+    """ptxas 12.9 folds a uniform-register offset into an LDGSTS that also carries an L2 cache-hint descriptor and emits an
+    encoding the B200 rejects (cudaErrorIllegalInstruction at run time; seen twice: DESIGN.md section 9, measured facts).  The
+    local kernel keeps the destination opaque (pd_kernels.cuh:gather); this checks the built library's SASS."""
+    import shutil
+    import subprocess
+    so = os.path.join(ROOT, "soft-body-simulation-cuda_b200", "libpd_b200.so")
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(so) or not os.path.exists(cuobjdump):
+        pytest.skip("library or cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True, timeout=600).stdout
+    lines = [l for l in sass.splitlines() if "LDGSTS" in l]
+    assert lines, "no LDGSTS at all: the position gather is not asynchronous any more?"
+    bad = [l.strip() for l in lines if "+UR" in l]
+    assert not bad, bad[:3]
