@@ -31,7 +31,12 @@ WORKLOADS = {
     "grid24": (24, 100, "Kuhn 6-tet grid 24^3 cells (82,944 tets) -- CPU-sized sample"),
     # independent (house2 + sphere) contexts, 64 per GPU, no inter-GPU communication (weak scaling)
     "batch64": (0, 100, "64 independent contexts per GPU, each house2 (1,389 tets) + sphere (1,217 tets) over a floor and a fixed sphere, float PD, Chebyshev-Jacobi 100 it/step"),
+    # assets/armadillo0 with the parameters of the shipped "Armadillo&house" context (context.json:121-129).  The bunny of
+    # config 2 is left out of the TIMED scene: its shipped definition diverges under Jacobi PD in the reference itself (NaN within
+    # 5 steps, tests/test_gpu_parity.py::test_vs_reference_cuda_kernels checks exactly that on both sides)
+    "armadillo": (0, 100, "assets/armadillo0 (13,054 verts, 41,960 tets) over the floor and five walls, dt 0.01, gravity 98, float PD, Chebyshev-Jacobi 100 it/step"),
 }
+ASSET_WORKLOADS = {"armadillo": "C2 armadillo"}      # context of the fixture (tests/meshes.py, regenerated from tests/golden/meshes.npz)
 # SURVEY C3 as specified: PD + Jacobi-PCG global step, 10 outer PD iterations per step; (inner max, ||r|| tolerance)
 SOLVER_WORKLOADS = {
     "grid55-pcg": (55, 10, 50, 0.0, "Kuhn 6-tet grid 55^3 cells (175,616 verts, 998,250 tets), float PD, 10 outer iterations x Jacobi-PCG with a FIXED 50 inner iterations (throughput variant)"),
@@ -181,9 +186,36 @@ def make_batch_scene(pd, first, count):
     return sc, p
 
 
+def fixed_arrays(pd, fixed):
+    """pd_fixed_body structs -> (planes [(p0, up)], spheres [(c, r)], cylinders [(c, axis, r)]) as oracle/ref.py takes them"""
+    planes, spheres, cyls = [], [], []
+    for f in fixed:
+        M = np.array(f.model[:], np.float32)
+        if f.type == pd.PD_PLANE:
+            up = np.zeros(3, np.float32)
+            pd.lib().pd_plane_up(M.ctypes.data, up.ctypes.data)
+            planes.append((M[12:15].copy(), up))
+        elif f.type == pd.PD_SPHERE:
+            spheres.append((M[12:15].copy(), f.radius))
+        else:
+            ax = M[4:7] / np.float32(np.linalg.norm(M[4:8]))
+            cyls.append((M[12:15].copy(), ax.astype(np.float32), f.radius))
+    return planes, spheres, cyls
+
+
 def make_scene(pd, workload, rank=0):
     if workload == "batch64":
         return make_batch_scene(pd, rank * BATCH_PER_GPU, BATCH_PER_GPU)
+    if workload in ASSET_WORKLOADS:
+        import tempfile
+        import meshes
+        with tempfile.TemporaryDirectory() as tmp:
+            assets = meshes.write_assets(tmp)
+            sc = pd.Scene.from_json(assets["json"], ASSET_WORKLOADS[workload])
+        p = sc.params
+        p["num_iterations"] = WORKLOADS[workload][1]
+        sc.params = p
+        return sc, p
     cells, iters, _ = WORKLOADS[workload]
     sc = pd.Scene.kuhn_grid(cells, cells, cells, 1.0, JITTER, SEED, (0.0, 10.0, 0.0), MASS, MU)
     if workload in SOLVER_WORKLOADS:
@@ -237,34 +269,39 @@ def workload_config(workload, nV, nT, iters, p, batch, world):
     return {"workload": workload, "description": WORKLOADS[workload][2], "num_verts": nV, "num_tets": nT,
             "pd_iterations_per_step": iters,
             "global_solver": (f"pcg-jacobi (max {SOLVER_WORKLOADS[workload][2]} inner iterations, ||r|| < {SOLVER_WORKLOADS[workload][3]:g}; PD stops at sqrt(err) < 1e-6)"
-                              if workload in SOLVER_WORKLOADS else "chebyshev-jacobi"), "dt": p["dt"], "gravity": p["gravity"], "mu": MU,
+                              if workload in SOLVER_WORKLOADS else "chebyshev-jacobi"), "dt": p["dt"], "gravity": p["gravity"], "mu": 2e6 if workload in ASSET_WORKLOADS else MU,
             "rho": p["rho"], "muN": p["muN"], "muT": p["muT"],
-            "initial_velocity": "0" if batch else "0.5*sin(x/7) y^",
+            "initial_velocity": "0" if (batch or workload in ASSET_WORKLOADS) else "0.5*sin(x/7) y^",
             "l2": (f"inputs larger than L2: ~{stream_mb:.0f} MB of per-tet data are streamed per PD iteration, no flush needed" if stream_mb > 2 * 126
                    else f"working set smaller than L2 (~{stream_mb:.0f} MB per PD iteration): not flushed -- 100 iterations per step re-read the same data, L2-resident is this workload's steady state"),
-            "parallelism": "single GPU" if world == 1 else ("contexts sharded 64 per GPU, no communication" if batch else f"vertex partition over {world} GPUs, tile-replicated boundary, NVLink peer-memory halo push + flags per PD iteration")}
+            "parallelism": "single GPU" if world == 1 else ("contexts sharded 64 per GPU, no communication" if batch else f"vertex partition over {world} GPUs, tile-replicated boundary, NVLink peer-memory halo push (phase tag in every position) per PD iteration")}
 
 
 PARITY_STEPS = 10
 
 
-def reference_positions(a, p, iters, steps, runs=2):
+def ref_scene(pd, a):
+    import ref
+    planes, spheres, cyls = fixed_arrays(pd, a["fixed"])
+    return ref.RefScene(a["X"], a["Tet"], a["mass"], a["mu"], planes=planes, spheres=spheres, cylinders=cyls)
+
+
+def reference_positions(pd, a, p, iters, steps, V0, runs=2):
     """X after `steps` steps of the reference's own CUDA kernels (oracle/_ref, the CHECKER -- never timed here) on the scene
     arrays `a`, `runs` times from the same start (the reference sums with float atomics: the runs differ)."""
-    import ref
-    rs = ref.RefScene(a["X"], a["Tet"], a["mass"], a["mu"], planes=[(np.zeros(3, np.float32), np.array([0, 1, 0], np.float32))])
-    kw = dict(dt=DT, gravity=GRAVITY, rho=p["rho"], muN=p["muN"], muT=p["muT"], num_iterations=iters)
+    rs = ref_scene(pd, a)
+    kw = dict(dt=p["dt"], gravity=p["gravity"], rho=p["rho"], muN=p["muN"], muT=p["muT"], num_iterations=iters)
     out = []
     for _ in range(runs):
-        rs.reset(); rs.set(V=initial_velocity(a["X"]))
+        rs.reset(); rs.set(V=V0)
         rs.step(steps, **kw); rs.sync()
         out.append(rs.get()[0].copy())
     del rs
     return out
 
 
-def engine_positions(eng, X0, steps):
-    eng.Reset(); eng.upload(V=initial_velocity(X0))
+def engine_positions(eng, V0, steps):
+    eng.Reset(); eng.upload(V=V0)
     eng.Update(steps)
     return eng.download()[0]
 
@@ -340,7 +377,8 @@ def run_b200(args):
                      "tets_evaluated_per_rank": allt[:, 2].tolist(), "pushed_verts_per_rank": allt[:, 3].tolist(),
                      "redundant_tet_fraction": float(allt[:, 2].sum() / nT - 1.0)}
     X0 = sc.arrays()["X"]
-    V0 = np.zeros_like(X0) if batch else initial_velocity(X0)
+    asset = args.workload in ASSET_WORKLOADS
+    V0 = np.zeros_like(X0) if (batch or asset) else initial_velocity(X0)
     eng.upload(V=V0)
     info = eng.info()
     trace("engine ready")
@@ -418,11 +456,11 @@ def run_b200(args):
         a = sc.arrays()
         if world == 1:
             import ref
-            Xe = engine_positions(eng, X0, PARITY_STEPS)
+            Xe = engine_positions(eng, V0, PARITY_STEPS)
             parity = {"workload": args.workload, "steps": PARITY_STEPS, "rot_mode": args.rot_mode,
                       "definition": "max_v |x_v - ref_v| / max(|ref_v|, bounding-box diagonal) after `steps` steps from the benchmark's initial state"}
             if ref.available():
-                Xa, Xb = reference_positions(a, p, iters, PARITY_STEPS)
+                Xa, Xb = reference_positions(pd, a, p, iters, PARITY_STEPS, V0)
                 parity.update({"reference": "oracle/_ref: the reference's CUDA kernels compiled verbatim (pdUtil.cu, svd3_cuda.h) replayed by oracle/ref_harness.cu",
                                "rel_err": meshes_rel_err(Xe, Xa), "reference_vs_reference": meshes_rel_err(Xb, Xa)})
             else:
@@ -432,7 +470,7 @@ def run_b200(args):
             # vertices after 3 steps from the benchmark's initial state; rank 0 steps a single-GPU engine on the same mesh.
             import torch.distributed as dist
             steps_bi = 3
-            Xd = engine_positions(eng, X0, steps_bi)            # owned rows filled, others 0
+            Xd = engine_positions(eng, V0, steps_bi)            # owned rows filled, others 0
             trace("parity steps done")
             own = np.zeros(nV, np.uint8); own[eng.owned_ids()] = 1
             t = torch.from_numpy(np.ascontiguousarray(Xd * own[:, None])).cuda()
@@ -441,7 +479,7 @@ def run_b200(args):
             Xall = t.cpu().numpy()
             if rank == 0:
                 one = pd.PdSolver(sc, device=local, rot_mode=args.rot_mode)
-                X1 = engine_positions(one, X0, steps_bi)
+                X1 = engine_positions(one, V0, steps_bi)
                 one.close()
                 same = bool(np.array_equal(Xall, X1)) and bool(np.isfinite(X1).all()) and bool((cnt.cpu().numpy() == 1).all())
                 import hashlib
@@ -464,7 +502,7 @@ def run_b200(args):
         f_ms = fe.step_timed(f_steps) / f_steps
         faithful = {"rot_mode": 1, "steps": f_steps, "ms_per_step": f_ms, "value": nT * iters / (f_ms * 1e-3) / 1e6, "unit": "Mtet-updates/s"}
         if Xa is not None:
-            Xf = engine_positions(fe, X0, PARITY_STEPS)
+            Xf = engine_positions(fe, V0, PARITY_STEPS)
             faithful["parity_rel_err"] = meshes_rel_err(Xf, Xa)
         fe.close()
 
@@ -668,9 +706,9 @@ def run_reference(args):
             "config": workload_config(args.workload, nV, nT, iters, p, False, 1)}
     cpu = cpu_baseline(iters, cores)
     if ref.available():
-        rs = ref.RefScene(a["X"], a["Tet"], a["mass"], a["mu"], planes=[(np.zeros(3, np.float32), np.array([0, 1, 0], np.float32))])
-        rs.set(V=initial_velocity(a["X"]))
-        kw = dict(dt=DT, gravity=GRAVITY, rho=p["rho"], muN=p["muN"], muT=p["muT"], num_iterations=iters)
+        rs = ref_scene(pd, a)       # the scene's own fixed bodies (the grid workloads: one floor plane)
+        rs.set(V=np.zeros_like(a["X"]) if args.workload in ASSET_WORKLOADS else initial_velocity(a["X"]))
+        kw = dict(dt=p["dt"], gravity=p["gravity"], rho=p["rho"], muN=p["muN"], muT=p["muT"], num_iterations=iters)
         rs.step(args.warmup, **kw); rs.sync()
         # same clock as the other arm: CUDA events on the stream the kernels run on (the harness launches on the legacy
         # default stream, which is torch's current stream); the host clock around the same region is kept as a cross-check

@@ -269,7 +269,7 @@ int pd_engine_info(const pd_engine*, int* num_verts, int* num_tets, int* num_til
 int pd_engine_rot_mode(const pd_engine*);
 /* ---- multi-GPU engine (options.world > 1): every rank creates its engine from the SAME scene, exchanges the
  * 64-byte window handles (e.g. torch.distributed.all_gather) and connects; pd_step then runs the ranks in
- * lock step through halo flags in peer memory (no host synchronisation, no NCCL on the data path).
+ * lock step through the phase tags of the halo positions in peer memory (no host synchronisation, no NCCL on the data path).
  * pd_download returns the rank's OWN vertices and zeros elsewhere (sum the ranks' arrays to combine). */
 int pd_dist_window_handle(pd_engine*, void* out64);                       /* cudaIpcMemHandle_t */
 int pd_dist_connect(pd_engine*, const void* handles /* world x 64 bytes, rank order */);

@@ -215,8 +215,9 @@ def fixed_body(kind, pos=(0, 0, 0), rot=(0, 0, 0), scale=(1, 1, 1), radius=1.0):
     elif kind == PD_CYLINDER:
         radius = scale[0]
         scale = (scale[0], scale[1], scale[0])
-    lib().pd_model_matrix(_p(np.asarray(pos, np.float32)), _p(np.asarray(rot, np.float32)),
-                          _p(np.asarray(scale, np.float32)), 0, _p(M))
+    # (named arrays: a temporary handed to _p() is freed before the call and its memory reused by the next temporary)
+    pos_a, rot_a, scale_a = (np.ascontiguousarray(t, np.float32) for t in (pos, rot, scale))
+    lib().pd_model_matrix(_p(pos_a), _p(rot_a), _p(scale_a), 0, _p(M))
     fb.model[:] = M.tolist()
     fb.radius = float(radius)
     return fb

@@ -40,7 +40,8 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 }
 
 // Exchange window of one rank (nLoc = owned + ghost vertices), mapped by its peers:
-//   [q0 | q1 | q2 | pcgP | flags[world] | epoch | ticket, status | pflags[world] | red[2][world][4 doubles]]
+//   [q0 | q1 | q2 | pcgP | (unused: the round-1 halo flags)[world] | epoch | ticket, status | pflags[world] | red[2][world][4 doubles]]
+// (the Jacobi path's halo needs no flags: every pushed position carries its phase tag, DistWait in pd_kernels.cuh)
 struct WindowLayout {
     size_t offP, offFlags, offEpoch, offTicket, offPFlags, offRed, bytes;
     WindowLayout(size_t nLoc, int world)
@@ -82,12 +83,11 @@ struct Engine::Impl {
     // multi-GPU exchange window (this rank's) and the tables that point into the neighbours' windows
     uint8_t* window = nullptr;
     size_t windowBytes = 0;
-    unsigned long long *flags = nullptr, *epoch = nullptr;
+    unsigned long long* epoch = nullptr;       // this rank's phase count = the tag of its halo pushes
     unsigned int *ticket = nullptr, *status = nullptr;
     uint32_t *pushSrc = nullptr, *pushDst = nullptr, *pushNbr = nullptr;
     int* nbrRanks = nullptr;
     float4** peerQ = nullptr;                  // [3 * nNbr]: buffer k of neighbour j
-    unsigned long long** peerFlag = nullptr;   // [nNbr]: this rank's entry in neighbour j's flag array
     int nPush = 0, nNbr = 0;
     // distributed PCG (pd_solvers.cuh: DistSolve): p lives in the window; flags / reduction slots / sequence counters
     unsigned long long *pflags = nullptr, *solveSeq = nullptr;
@@ -197,7 +197,6 @@ Engine::Engine(const Scene& scene, const EngineOptions& opt) : scene_(scene), pa
     CUDA_CHECK(cudaMemset(d.window, 0, d.windowBytes));
     for (int k = 0; k < 3; ++k) d.q[k] = reinterpret_cast<float4*>(d.window) + (size_t)k * nV_;
     d.cgP = reinterpret_cast<float4*>(d.window + wl.offP);
-    d.flags = reinterpret_cast<unsigned long long*>(d.window + wl.offFlags);
     d.epoch = reinterpret_cast<unsigned long long*>(d.window + wl.offEpoch);
     d.ticket = reinterpret_cast<unsigned int*>(d.window + wl.offTicket);
     d.status = d.ticket + 1;
@@ -450,7 +449,13 @@ void Engine::enqueueIteration(int i, bool timed, size_t* ev)
     float4* next = d.q[in];
     rec();
     // multi-GPU: the local kernel first pushes the boundary entries of the buffer it reads (`cur`) to the neighbours,
-    // spread over its CTAs and in push-list order, and waits for theirs only before its first boundary tile
+    // spread over its CTAs and in push-list order, every position tagged with this phase's count E (DistWait), and checks the
+    // tags of the ghosts it stages for its boundary tiles.  Why no acknowledgement is needed (three rotating buffers): this
+    // launch overwrites the neighbour's ghost entries of buffer E % 3, which that neighbour last READ in its local kernel of
+    // phase E - 3.  This rank can only be here after its vertex kernel of phase E - 1, hence after its local kernel of phase
+    // E - 1 consumed the neighbour's push of phase E - 1, which the neighbour issued at the start of ITS local kernel E - 1,
+    // i.e. after it had finished phase E - 2 (stream order) -- so phase E - 3 is long over.  The same argument covers the step
+    // boundary (finish + predictor instead of a vertex kernel).
     if (opt_.world > 1 && !connected_) throw std::runtime_error("multi-GPU engine stepped before pd_dist_connect");
     launchLocal(cur, true, nullptr, (opt_.world > 1 && !lockstep_) ? ic : -1);
     rec();
@@ -595,7 +600,7 @@ void Engine::getCollision(float* tI, float* normals, long long* numPairs)
     }
 }
 
-// multi-GPU: boundary positions of buffer `bufIndex` -> the neighbours' ghost entries, then the flags
+// multi-GPU: boundary positions of buffer `bufIndex` -> the neighbours' ghost entries, tagged with the new phase count
 void Engine::enqueuePush(const float4* q, int bufIndex)
 {
     Impl& d = *d_;
@@ -621,7 +626,7 @@ void Engine::enqueueStep(bool timed)
 }
 
 // One CUDA graph per step.  Multi-GPU: the position buffers rotate across steps (base = phase_ % 3), so up to
-// three graphs exist, one per base; the halo flags make the replayed kernels wait for the neighbours as usual.
+// three graphs exist, one per base; the phase tags make the replayed kernels wait for the neighbours as usual.
 void Engine::buildGraph()
 {
     Impl& d = *d_;
@@ -1277,7 +1282,6 @@ void Engine::setPeers(const std::vector<uint8_t*>& peerBase)
     d.nNbr = (int)P.neighbours.size();
     d.nPush = (int)P.pushSrc.size();
     std::vector<float4*> pq((size_t)3 * std::max(d.nNbr, 1));
-    std::vector<unsigned long long*> pf((size_t)std::max(d.nNbr, 1));
     std::vector<int> nbrIndexOfRank((size_t)opt_.world, -1);
     for (int j = 0; j < d.nNbr; ++j) {
         const int r = P.neighbours[(size_t)j];
@@ -1286,7 +1290,6 @@ void Engine::setPeers(const std::vector<uint8_t*>& peerBase)
         const size_t nLocR = (size_t)P.nLocOf[(size_t)r];
         const WindowLayout wl(nLocR, opt_.world);
         for (int k = 0; k < 3; ++k) pq[(size_t)k * d.nNbr + j] = reinterpret_cast<float4*>(peerBase[(size_t)r]) + (size_t)k * nLocR;
-        pf[(size_t)j] = reinterpret_cast<unsigned long long*>(peerBase[(size_t)r] + wl.offFlags) + opt_.rank;
     }
     {   // distributed PCG: the neighbours' p vectors and p-flags, and EVERY rank's reduction slots (own included)
         std::vector<float4*> pp((size_t)std::max(d.nNbr, 1));
@@ -1315,7 +1318,7 @@ void Engine::setPeers(const std::vector<uint8_t*>& peerBase)
     for (int i = 0; i < d.nPush; ++i) nb[(size_t)i] = (uint32_t)nbrIndexOfRank[(size_t)P.pushRank[(size_t)i]];
     d.pushSrc = dalloc<uint32_t>(d.nPush); d.pushDst = dalloc<uint32_t>(d.nPush); d.pushNbr = dalloc<uint32_t>(d.nPush);
     d.nbrRanks = dalloc<int>(d.nNbr);
-    d.peerQ = dalloc<float4*>(3 * (size_t)d.nNbr); d.peerFlag = dalloc<unsigned long long*>(d.nNbr);
+    d.peerQ = dalloc<float4*>(3 * (size_t)d.nNbr);
     if (d.nPush) {
         CUDA_CHECK(cudaMemcpy(d.pushSrc, P.pushSrc.data(), (size_t)d.nPush * 4, cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaMemcpy(d.pushDst, P.pushDst.data(), (size_t)d.nPush * 4, cudaMemcpyHostToDevice));
@@ -1324,7 +1327,6 @@ void Engine::setPeers(const std::vector<uint8_t*>& peerBase)
     if (d.nNbr) {
         CUDA_CHECK(cudaMemcpy(d.nbrRanks, P.neighbours.data(), (size_t)d.nNbr * sizeof(int), cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaMemcpy(d.peerQ, pq.data(), (size_t)3 * d.nNbr * sizeof(float4*), cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemcpy(d.peerFlag, pf.data(), (size_t)d.nNbr * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
     }
     d.wait = DistWait{d.epoch, d.nNbr, nOwn_, plan_.nInteriorTiles, d.status, 0, d.pushSrc, d.pushDst, d.pushNbr, d.peerQ};
     connected_ = true;
@@ -1372,7 +1374,7 @@ void Engine::connectLocal(Engine* const* engines, int n)
 
 // One host thread drives all ranks phase by phase (tests on one GPU, where a rank's local kernel could
 // otherwise occupy every SM while it waits for a neighbour that cannot be scheduled): after each phase every
-// stream waits for every other stream, so all halo flags are already up when a local kernel starts.
+// stream waits for every other stream, so all tagged ghost positions have landed when a local kernel starts.
 void Engine::stepLockstep(Engine* const* engines, int n, int nSteps)
 {
     auto crossSync = [&]() {
