@@ -53,7 +53,11 @@
 
 class B200PdSolver : public Solver<float> {
 public:
-    /* PdSolver::SolverType (pdSolver.h:15-18); PCGJacobi is the extra back-end of linear/pcgJacobi.cu */
+    /* PdSolver::SolverType (pdSolver.h:15-18); PCGJacobi is the extra back-end of linear/pcgJacobi.cu.
+     * EigenCholesky runs on the engine's own sparse Cholesky like CuSolverCholesky does.  One difference from the reference, kept
+     * on purpose: its Eigen branch never updates `err` (pdSolver.cu:178-185 vs :186-192), so there the PD loop always runs
+     * numIterations; here both direct modes leave the loop once sqrt(err) < tol, as the reference's cuSOLVER branch does --
+     * set SolverParams::tol = 0 to get the Eigen branch's iteration count. */
     enum class SolverType { Jacobi = PD_JACOBI, CuSolverCholesky = PD_CHOLESKY, EigenCholesky = PD_CHOLESKY, PCGJacobi = PD_PCG_JACOBI };
 
     /* Same leading arguments as PdSolver(int, const SolverData<float>&) (pdSolver.cu:22-27).  Unlike

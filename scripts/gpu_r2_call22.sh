@@ -1,0 +1,17 @@
+# Round 2, call 22 (N=1, grid139, same box): vertex kernel with the first four slot indices in one 16-byte word (default) vs pointer + CSR
+# (variants/libpd_csr.so = the previous commit); local kernel compiled for 3 instead of 4 CTAs per SM (variants/libpd_mb3.so, CSR slots)
+mkdir -p gpurun_out
+T=${T:-r2c22}; W=${W:-grid139}
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_dist.py tests/test_gpu_solvers.py -m gpu -q 2>&1 | tail -2
+for rep in 1 2 3; do for v in default csr mb3; do
+  if [ $v = default ]; then unset PD_B200_LIB; else export PD_B200_LIB=$PWD/soft-body-simulation-cuda_b200/variants/libpd_$v.so; fi
+  timeout 300 python bench.py --workload $W --steps 5 --warmup 3 --no-cpu-baseline --no-parity --no-faithful > gpurun_out/${T}_${v}_$rep.json 2> gpurun_out/${T}_${v}_$rep.err
+  python - <<PY
+import json
+try:
+    d=[json.loads(l) for l in open("gpurun_out/${T}_${v}_$rep.json") if l.startswith("{")][-1]; r=d["roofline"]
+    print("$v rep $rep $W ms/step %.3f local %.1f us vertex (alone) %.1f us"%(d["ms_per_step"], r["launch_ms"]*1e3, r["fused_iteration"]["vertex_kernel_ms"]*1e3), d["clocks"]["sm_mhz"])
+except Exception as e: print("$v rep $rep failed", e)
+PY
+done; done
+unset PD_B200_LIB

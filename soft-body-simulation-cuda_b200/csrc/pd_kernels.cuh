@@ -515,8 +515,11 @@ __device__ __forceinline__ void local_phase_b(const float4 r0, const float4 r1, 
         h_store(Hline, 3u, c23 >> 16, h3);
 }
 
+#ifndef PD_VSTAGE_PREFETCH
+#define PD_VSTAGE_PREFETCH 1
+#endif
 template <int ROT_MODE, bool JACOBI, bool PROF = false>
-__global__ void __launch_bounds__(TILE_T, 4)
+__global__ void __launch_bounds__(TILE_T, 4)      // (compiled for 3 CTAs per SM -- 70 registers -- the kernel is 4 % slower: profiles/r2_vslot4_mb3_ab_grid139.txt)
 k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMeta, int nTiles,
         const uint32_t* __restrict__ vstage, const uint32_t* __restrict__ vlist, const float4* __restrict__ q, const float4* __restrict__ b0, float4* __restrict__ P,
         unsigned long long* __restrict__ prof, DistWait dw)
@@ -593,12 +596,22 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
         const uint2 te = __ldg(reinterpret_cast<const uint2*>(meta_of(k)));
         bulk_prefetch_l2(records + 16ull * te.x, te.y & 0xffffu);
     };
+    // ... and the tile's staging list (1 KB of the read-once, DRAM-resident vstage array) -> L2, two tiles before load_ve() reads
+    // it: that load is consumed exactly one tile later by gather(), and a tile (~4,300 cycles per CTA) is about one LOADED HBM
+    // round trip -- the phase profile showed the heaviest warp waiting ~1,000 cycles per tile for it (profiles/r1_phase_profile_*)
+    auto prefetch_vs = [&](int k) {
+#if PD_VSTAGE_PREFETCH
+        bulk_prefetch_l2(vstage + (size_t)(blockIdx.x + k * gridDim.x) * TILE_NLMAX, 4u * TILE_NLMAX);
+#endif
+    };
 
     // ---- prologue: everything here touches only the immutable tile stream
     if (producer) {
         fetch_c(0);
         if (nIt > 1) { fetch_c(1); prefetch_ab(1); }
         if (nIt > 2) prefetch_ab(2);
+        if (nIt > 3) prefetch_vs(3);
+        if (nIt > 4) prefetch_vs(4);
     }
     // tile-table words of the current tile: group `warp` (with the tet count) and, with 16-vertex groups, `warp + 8`
     uint32_t mwA = __ldg(meta_of(0) + 4 + warp), mwB = (TILE_NGROUPS > 8) ? __ldg(meta_of(0) + 4 + (warp + 8) % TILE_NGROUPS) : 0u;
@@ -663,6 +676,7 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
         if (producer) {
             if (it >= 1 && it + 1 < nIt) fetch_c(it + 1);
             if (it + 3 < nIt) prefetch_ab(it + 3);
+            if (it + 5 < nIt) prefetch_vs(it + 5);
         }
         veN = (it + 3 < nIt) ? load_ve(it + 3) : 0xffffffffu;
         PD_TICK(3)
