@@ -15,7 +15,7 @@ eng.upload(V=bench.initial_velocity(sc.arrays()["X"]))
 eng.Update(1)
 a = eng.profile_local().astype(np.float64)
 tiles = a[:, 7].sum()
-names = ["phase B (positions, math, H stores)", "record LDG issue + gather wait", "barrier", "gather issue + producer + table loads", "wait part C (TMA)", "phase C", "(unused)"]
+names = ["phase B (positions, math, H stores)", "record LDG issue + gather wait", "barrier", "producer + vstage load issue", "wait part C (TMA)", "phase C", "gather issue (LDGSTS)"]
 tot = a[:, :7].sum()
 print(f"{workload} ctas/SM {ctas} rot {rot}: grid {a.shape[0]}, tiles {int(tiles)}, cycles per tile per CTA {tot / tiles:.0f}")
 for i, n in enumerate(names):

@@ -580,7 +580,9 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
     // producer duties: lane 0 of the LAST warp (the tile-local vertices are sorted by incidence count, so warp 0
     // carries the longest phase C and the last warp the shortest, usually none at all).  Measured and rejected:
     // heaviest groups on the highest warp ids (+3 %), the record's table entry requested a phase earlier (+1 %),
-    // 16-vertex groups with two lanes per vertex (-50 % longest list, +10 % instructions: +6 %); round 2: warps 7 / 6 / 5
+    // 16-vertex groups with two lanes per vertex (-50 % longest list, +10 % instructions: +6 %); round 2: the position gather issued
+    // by the upper half of the CTA only, two slots per thread (the heavy warps' stall after the barrier GREW: it is the scheduler's
+    // memory-instruction queue behind the partner warp's scattered LDGSTS, +2 %, profiles/r2_half_cta_gather_ab_grid139.txt); warps 7 / 6 / 5
     // summing the odd rows of groups 0 / 1 / 2 and handing them over through shared memory and a named barrier
     // (bar.arrive / bar.sync on 64 threads): +19 % instructions, barrier stall 3.3 -> 4.0 per issue, +25 % time
     // (profiles/r2_k_local_split_c_ncu_summary.txt); x | y | z planes for the H scratch and predicated pad loads: no gain
@@ -673,6 +675,7 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
         PD_TICK(2)
         // staging buffer b and part C buffer (it+1)&1 are free now
         gather(veN);           // tile it+2 into buffer b (an empty group when there is none)
+        PD_TICK(6)
         if (producer) {
             if (it >= 1 && it + 1 < nIt) fetch_c(it + 1);
             if (it + 3 < nIt) prefetch_ab(it + 3);
