@@ -582,7 +582,9 @@ k_local(const uint8_t* __restrict__ records, const uint32_t* __restrict__ tileMe
     // heaviest groups on the highest warp ids (+3 %), the record's table entry requested a phase earlier (+1 %),
     // 16-vertex groups with two lanes per vertex (-50 % longest list, +10 % instructions: +6 %); round 2: the position gather issued
     // by the upper half of the CTA only, two slots per thread (the heavy warps' stall after the barrier GREW: it is the scheduler's
-    // memory-instruction queue behind the partner warp's scattered LDGSTS, +2 %, profiles/r2_half_cta_gather_ab_grid139.txt); warps 7 / 6 / 5
+    // memory-instruction queue behind the partner warp's scattered LDGSTS, +2 %, profiles/r2_half_cta_gather_ab_grid139.txt); two lanes per
+    // vertex for the heaviest 16 vertices of a tile only (longest group 11.8 -> 6.0 rows, fewer rows in total: still +1.6 %,
+    // profiles/r2_mixed_lpv_groups_ab_grid139.txt -- the tile is bound by the SM's throughput, not by its heaviest warp); warps 7 / 6 / 5
     // summing the odd rows of groups 0 / 1 / 2 and handing them over through shared memory and a named barrier
     // (bar.arrive / bar.sync on 64 threads): +19 % instructions, barrier stall 3.3 -> 4.0 per issue, +25 % time
     // (profiles/r2_k_local_split_c_ncu_summary.txt); x | y | z planes for the H scratch and predicated pad loads: no gain
