@@ -23,7 +23,8 @@ namespace pdb200 {
 
 // shared-memory carve-up for capacities (nVmax, nTmax, multiples of 32): q[3] | b0 | cc | H (four corner planes) | incidence
 // pointers (nVmax + 32 words) | incidence entries (4 nTmax u16)
-__host__ __device__ inline size_t body_smem_bytes(uint32_t nVmax, uint32_t nTmax) { return 72ull * nVmax + 64ull * nTmax + 4ull * (nVmax + 32u) + 8ull * nTmax; }
+// pointers (nVmax + 32 words) | incidence entries (4 nTmax u16) | the tets the fast rotation path declined (nTmax u16) | their count
+__host__ __device__ inline size_t body_smem_bytes(uint32_t nVmax, uint32_t nTmax) { return 72ull * nVmax + 64ull * nTmax + 4ull * (nVmax + 32u) + 8ull * nTmax + 2ull * nTmax + 16ull; }
 
 template <int ROT_MODE>
 __global__ void __launch_bounds__(512, 1)
@@ -52,6 +53,8 @@ k_body_step(const BodyDesc* __restrict__ bodies, const uint32_t* __restrict__ bv
     float4* Hs = reinterpret_cast<float4*>(smem + 72ull * nVmax);
     uint32_t* ptrS = reinterpret_cast<uint32_t*>(smem + 72ull * nVmax + 64ull * nTmax);
     uint16_t* incS = reinterpret_cast<uint16_t*>(smem + 72ull * nVmax + 64ull * nTmax + 4ull * (nVmax + 32u));
+    uint16_t* slowS = incS + 4ull * nTmax;                                   // tets whose contribution needs the slow rotation path
+    unsigned int* nSlow = reinterpret_cast<unsigned int*>(slowS + nTmax);     // (nTmax is a multiple of 32: 4-byte aligned)
     const BodyDesc bd = bodies[blockIdx.x];
     const uint32_t tid = threadIdx.x, nth = blockDim.x;
 
@@ -80,6 +83,8 @@ k_body_step(const BodyDesc* __restrict__ bodies, const uint32_t* __restrict__ bv
     __syncthreads();
 
     const uint8_t* rec = brec + 16ull * bd.recOff16;
+    if (tid == 0) *nSlow = 0u;
+    __syncthreads();
     float omega = 1.0f;
     if (timed) tMark = now();
     for (int i = 0; i < iterations; ++i) {
@@ -93,11 +98,39 @@ k_body_step(const BodyDesc* __restrict__ bodies, const uint32_t* __restrict__ bv
             const float4 r0 = __ldg(rp + t), r1 = __ldg(rp + bd.nT + t), r2 = __ldg(rp + 2ull * bd.nT + t);
             const uint32_t c01 = __float_as_uint(r2.z), c23 = __float_as_uint(r2.w);
             float4 h0, h1, h2, h3;
-            tet_contrib<ROT_MODE, true>(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, cur[c01 & 0xffffu], cur[c01 >> 16], cur[c23 & 0xffffu],
-                                        cur[c23 >> 16], h0, h1, h2, h3);
+            if (ROT_MODE == 0) {
+                // the fast rotation path only; a tet it declines (inverted / flat / strongly deformed: a few per cent of a body
+                // that lies on the floor) is put on a list and taken by the slow path BELOW, compacted -- taken in place it drags
+                // its whole warp through the ~900-instruction slow path (36 % of this kernel's instructions on batch64)
+                if (!tet_contrib_fast<true>(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, cur[c01 & 0xffffu], cur[c01 >> 16],
+                                            cur[c23 & 0xffffu], cur[c23 >> 16], h0, h1, h2, h3)) {
+                    slowS[atomicAdd(nSlow, 1u)] = (uint16_t)t;
+                    continue;
+                }
+            } else {
+                tet_contrib_slow<ROT_MODE, true>(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, cur[c01 & 0xffffu], cur[c01 >> 16],
+                                                 cur[c23 & 0xffffu], cur[c23 >> 16], h0, h1, h2, h3);
+            }
             Hs[t] = h0; Hs[nTmax + t] = h1; Hs[2 * nTmax + t] = h2; Hs[3 * nTmax + t] = h3;
         }
         __syncthreads();
+        if (ROT_MODE == 0) {
+            // ... the declined tets, consecutive threads (the list's order varies from run to run, the results do not: every
+            // tet writes its own four entries)
+            const unsigned int ns = *nSlow;
+            for (uint32_t i = tid; i < ns; i += nth) {
+                const uint32_t t = slowS[i];
+                const float4* rp = reinterpret_cast<const float4*>(rec);
+                const float4 r0 = __ldg(rp + t), r1 = __ldg(rp + bd.nT + t), r2 = __ldg(rp + 2ull * bd.nT + t);
+                const uint32_t c01 = __float_as_uint(r2.z), c23 = __float_as_uint(r2.w);
+                float4 h0, h1, h2, h3;
+                tet_contrib_slow<0, true>(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, cur[c01 & 0xffffu], cur[c01 >> 16],
+                                          cur[c23 & 0xffffu], cur[c23 >> 16], h0, h1, h2, h3);
+                Hs[t] = h0; Hs[nTmax + t] = h1; Hs[2 * nTmax + t] = h2; Hs[3 * nTmax + t] = h3;
+            }
+            __syncthreads();
+            if (tid == 0) *nSlow = 0u;       // (the next iteration's first atomicAdd comes after the barrier that ends the sweep below)
+        }
         if (timed) { const unsigned long long t = now(); tLocal += t - tMark; tMark = t; }
         // omega recurrence in float, pdSolver.cu:196-198 (the same operations Engine::enqueueIteration performs on the host)
         if (i <= 10) omega = 1.0f;

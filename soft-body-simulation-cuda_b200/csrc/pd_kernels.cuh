@@ -425,13 +425,16 @@ __device__ __forceinline__ void local_phase_c(const uint8_t* Cb, const uint8_t* 
 // the contributions of ONE tet to the right-hand sides of its four vertices (PdUtil::computeLocal, pdUtil.cu:107-143):
 // F = Ds DmInv, rotation, H = w (R - F) DmInv^T G (Jacobi mode) or w R DmInv^T G (direct / CG modes).  B0..B8 = DmInv
 // (row-major), p0..p3 = the corner positions; shared by the tile kernel below and the per-body kernel (pd_body_kernel.cuh)
-template <int ROT_MODE, bool JACOBI>
-__device__ __forceinline__ void tet_contrib(const float B0, const float B1, const float B2, const float B3, const float B4, const float B5, const float B6,
+// (split in two so that a kernel can run the slow part on a COMPACTED list of the tets that need it: pd_body_kernel.cuh)
+// ... the product default's FAST part: packed FP32, two unrolled polar Newton steps; false (nothing written) when the tet is
+// inverted / flat / strongly deformed and needs tet_contrib_slow
+template <bool JACOBI>
+__device__ __forceinline__ bool tet_contrib_fast(const float B0, const float B1, const float B2, const float B3, const float B4, const float B5, const float B6,
                                             const float B7, const float B8, const float w, const float4 p0, const float4 p1, const float4 p2, const float4 p3,
                                             float4& h0, float4& h1, float4& h2, float4& h3)
 {
         bool done = false;
-        if (ROT_MODE == 0) {
+        {
             // product default: packed FP32 (FFMA2) on matrix columns, rotation.cuh.  Edge k = p_{k+1} - p_0 is
             // column k of Ds; column c of F = sum_k edge_k B[k][c]
             const float2 p0xy = make_float2(p0.x, p0.y);
@@ -472,7 +475,15 @@ __device__ __forceinline__ void tet_contrib(const float B0, const float B1, cons
                 done = true;
             }
         }
-        if (!done) {
+        return done;
+}
+// ... and the scalar part in the reference's operation order (the faithful mode takes it for every tet)
+template <int ROT_MODE, bool JACOBI>
+__device__ __forceinline__ void tet_contrib_slow(const float B0, const float B1, const float B2, const float B3, const float B4, const float B5, const float B6,
+                                            const float B7, const float B8, const float w, const float4 p0, const float4 p1, const float4 p2, const float4 p3,
+                                            float4& h0, float4& h1, float4& h2, float4& h3)
+{
+        {
             // faithful mode, and the default mode's rare inverted / flat / strongly deformed tets: scalar path in
             // the reference's operation order.  Ds columns = edges; F = Ds * DmInv  (row-major F[r][c] = sum_k Ds[r][k] B[k][c])
             const float d00 = p1.x - p0.x, d01 = p2.x - p0.x, d02 = p3.x - p0.x;
@@ -495,6 +506,14 @@ __device__ __forceinline__ void tet_contrib(const float B0, const float B1, cons
             h0.z = __fsub_rn(__fsub_rn(-h1.z, h2.z), h3.z);
             h0.w = h1.w = h2.w = h3.w = 0.f;
         }
+}
+template <int ROT_MODE, bool JACOBI>
+__device__ __forceinline__ void tet_contrib(const float B0, const float B1, const float B2, const float B3, const float B4, const float B5, const float B6,
+                                            const float B7, const float B8, const float w, const float4 p0, const float4 p1, const float4 p2, const float4 p3,
+                                            float4& h0, float4& h1, float4& h2, float4& h3)
+{
+        if (ROT_MODE == 0 && tet_contrib_fast<JACOBI>(B0, B1, B2, B3, B4, B5, B6, B7, B8, w, p0, p1, p2, p3, h0, h1, h2, h3)) return;
+        tet_contrib_slow<ROT_MODE, JACOBI>(B0, B1, B2, B3, B4, B5, B6, B7, B8, w, p0, p1, p2, p3, h0, h1, h2, h3);
 }
 
 // phase B of one tet: record (r0, r1, r2) in registers, positions from the staging buffer qsb, the four corner
