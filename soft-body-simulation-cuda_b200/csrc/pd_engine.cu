@@ -1132,8 +1132,13 @@ void Engine::prepareSolver()
             int perSm2 = 0;
             CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm2, k_chol_solve, SOLVE_THREADS, 0));
             perSm = std::max(1, perSm);
-            d.solveGrid = std::min(numSms_ * perSm, std::min(SOLVE_MAX_PARTIALS, (nOwn_ + SOLVE_THREADS - 1) / SOLVE_THREADS));
+            // at most THREE blocks per SM: a CG iteration at config-3 size is grid barriers and reductions over one slot per block more
+            // than bandwidth (same-box A/B on grid55-pcg: 12.6 ms per step with every resident block, 12.8 / 11.1 / 10.7-11.2 with
+            // 1 / 2 / 3 per SM, profiles/r2_pcg_grid_size_ab.txt)
+            d.solveGrid = std::min(numSms_ * std::min(perSm, 3), std::min(SOLVE_MAX_PARTIALS, (nOwn_ + SOLVE_THREADS - 1) / SOLVE_THREADS));
             d.solveGrid = std::max(d.solveGrid, 1);
+            if (const char* e = std::getenv("PD_SOLVE_BLOCKS_PER_SM"))      // (experiments: fewer blocks = cheaper grid barriers, longer per-thread row loops)
+                d.solveGrid = std::max(1, std::min(d.solveGrid, numSms_ * std::max(1, std::atoi(e))));
             // the triangular solves run one WARP per row: as many resident warps as rows, up to the whole GPU
             // (not more than 4 blocks per SM: warps beyond the rows that can make progress only poll)
             d.cholGrid = std::max(1, std::min(numSms_ * std::min(4, std::max(1, perSm2)), std::min(SOLVE_MAX_PARTIALS, (nOwn_ + SOLVE_THREADS / 32 - 1) / (SOLVE_THREADS / 32))));

@@ -32,7 +32,12 @@ struct CsrDev {
     const float* invDiag;    // ExtractInverseDiagonalKernel, pcgJacobi.cu:6-19
 };
 
-constexpr int SOLVE_THREADS = 256;
+#ifndef PD_SOLVE_THREADS
+#define PD_SOLVE_THREADS 256
+#endif
+constexpr int SOLVE_THREADS = PD_SOLVE_THREADS;
+constexpr int SOLVE_WARPS = SOLVE_THREADS / 32;       // shared scratch of a reduction: 3 * SOLVE_WARPS + 3 doubles
+constexpr int SOLVE_SH = 3 * SOLVE_WARPS + 3;
 constexpr int SOLVE_MAX_PARTIALS = 2048;       // >= grid size of the cooperative kernels
 
 // Deterministic grid-wide sum of up to three doubles per thread: warp shuffle -> block -> one slot per block ->
@@ -51,11 +56,11 @@ __device__ __forceinline__ void grid_sum3(cg::grid_group& grid, double a, double
         c += __shfl_down_sync(0xffffffffu, c, o);
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { sh[warp] = a; sh[8 + warp] = b; sh[16 + warp] = c; }
+    if (lane == 0) { sh[warp] = a; sh[SOLVE_WARPS + warp] = b; sh[2 * SOLVE_WARPS + warp] = c; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double sa = 0, sb = 0, sc = 0;
-        for (int w = 0; w < SOLVE_THREADS / 32; ++w) { sa += sh[w]; sb += sh[8 + w]; sc += sh[16 + w]; }
+        for (int w = 0; w < SOLVE_WARPS; ++w) { sa += sh[w]; sb += sh[SOLVE_WARPS + w]; sc += sh[2 * SOLVE_WARPS + w]; }
         partials[3 * blockIdx.x] = sa; partials[3 * blockIdx.x + 1] = sb; partials[3 * blockIdx.x + 2] = sc;
     }
     grid.sync();
@@ -68,10 +73,10 @@ __device__ __forceinline__ void grid_sum3(cg::grid_group& grid, double a, double
             sb += __shfl_xor_sync(0xffffffffu, sb, o);
             sc += __shfl_xor_sync(0xffffffffu, sc, o);
         }
-        if (lane == 0) { sh[24] = sa; sh[25] = sb; sh[26] = sc; }
+        if (lane == 0) { sh[3 * SOLVE_WARPS] = sa; sh[3 * SOLVE_WARPS + 1] = sb; sh[3 * SOLVE_WARPS + 2] = sc; }
     }
     __syncthreads();
-    out[0] = sh[24]; out[1] = sh[25]; out[2] = sh[26];
+    out[0] = sh[3 * SOLVE_WARPS]; out[1] = sh[3 * SOLVE_WARPS + 1]; out[2] = sh[3 * SOLVE_WARPS + 2];
     __syncthreads();      // sh is reused by the next reduction
 }
 
@@ -140,10 +145,10 @@ __device__ __forceinline__ void dist_allreduce3(const DistSolve& D, unsigned lon
         for (int r = 0; r < D.world; ++r) {          // rank order: every rank gets the same bits
             sa += __shfl_sync(0xffffffffu, a, r); sb += __shfl_sync(0xffffffffu, b, r); sc += __shfl_sync(0xffffffffu, c, r);
         }
-        if (lane == 0) { sh[24] = sa; sh[25] = sb; sh[26] = sc; }
+        if (lane == 0) { sh[3 * SOLVE_WARPS] = sa; sh[3 * SOLVE_WARPS + 1] = sb; sh[3 * SOLVE_WARPS + 2] = sc; }
     }
     __syncthreads();
-    v[0] = sh[24]; v[1] = sh[25]; v[2] = sh[26];
+    v[0] = sh[3 * SOLVE_WARPS]; v[1] = sh[3 * SOLVE_WARPS + 1]; v[2] = sh[3 * SOLVE_WARPS + 2];
     __syncthreads();
 }
 
@@ -240,7 +245,7 @@ k_pcg_solve(CsrDev A, const float4* __restrict__ b, float4* x, float4* __restric
             float4* __restrict__ xprev, int maxIter, float cgTol, float pdTol, SolveState* st, double* partials, DistSolve D)
 {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double sh[27];
+    __shared__ double sh[SOLVE_SH];
     if (st->done) return;                       // uniform over the grid (and over the ranks): this PD iteration is skipped
     const int n = A.n, gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
     unsigned long long pSeq = 0, rSeq = 0;
@@ -385,7 +390,7 @@ k_chol_solve(CholDev C, const float4* __restrict__ b, float4* x, float4* y, floa
              int epochTag, float pdTol, SolveState* st, double* partials)
 {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double sh[27];
+    __shared__ double sh[SOLVE_SH];
     if (st->done) return;
     const int n = C.n, lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;

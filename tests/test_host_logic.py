@@ -329,3 +329,27 @@ def test_no_ldgsts_with_uniform_register_offset():
     assert lines, "no LDGSTS at all: the position gather is not asynchronous any more?"
     bad = [l.strip() for l in lines if "+UR" in l]
     assert not bad, bad[:3]
+
+
+def test_fixed_body_helper_and_bench_scenes(pd):
+    """pd.fixed_body() once handed ctypes the addresses of temporaries that were freed before the call (the benchmark's floor
+    plane ended up at y = 450, upside down); and the scene builders of bench.py, no GPU needed."""
+    import importlib
+    import sys
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    for _ in range(20):          # (the freed memory was reused by the very next temporary: every call was wrong, not one in many)
+        fb = pd.fixed_body(pd.PD_PLANE, pos=(0, 0, 0), scale=(450, 450, 450))
+        M = np.array(fb.model[:], np.float32)
+        up = np.zeros(3, np.float32)
+        pd.lib().pd_plane_up(M.ctypes.data, up.ctypes.data)
+        assert np.allclose(M[12:15], 0.0) and np.allclose(up, [0.0, 1.0, 0.0]), (M[12:15], up)
+    sc, p = bench.make_scene(pd, "grid24")
+    planes, spheres, cyls = bench.fixed_arrays(pd, sc.arrays()["fixed"])
+    assert len(planes) == 1 and not spheres and not cyls and np.allclose(planes[0][0], 0) and np.allclose(planes[0][1], [0, 1, 0])
+    sc, p = bench.make_scene(pd, "armadillo")
+    assert sc.counts()[:2] == (13054, 41960) and p["num_iterations"] == 100 and abs(p["dt"] - 0.01) < 1e-6 and p["gravity"] == 98.0
+    assert len(bench.fixed_arrays(pd, sc.arrays()["fixed"])[0]) == 6          # floor + five walls
+    cfg = bench.workload_config("armadillo", 13054, 41960, 100, p, False, 1)
+    assert cfg["workload"] == "armadillo" and cfg["initial_velocity"] == "0"
