@@ -146,8 +146,10 @@ private:
     bool pdlActive_ = false;
     int vertexFlags_ = 2;     // k_vertex_jacobi flag bit 1: its blocks walk the vertices from the END of the array (-0.4 % per step on grid139,
                               // profiles/r2_vertex_fold_reverse_ab_grid139.txt); PD_VERTEX_REVERSE=0 for A/B runs
-    int pdlLate_ = 0;         // PD_PDL=2: the dependents are released at the END of every CTA's work instead of at its start
-    bool usePdl_ = false;     // programmatic dependent launch of the per-iteration kernels (pd_kernels.cuh: pdl_wait); measured SLOWER
+    int pdlLate_ = 1;         // the dependents are released at the END of every CTA's work (PD_PDL=2, the default); 0: at its start (PD_PDL=1, measured slower)
+    bool usePdl_ = true;      // programmatic dependent launch of the per-iteration kernels (pd_kernels.cuh: pdl_wait), late trigger: the next kernel's launch
+                              // latency and prologue hide behind this one's tail: armadillo -15 %, grid55 -2.2 %, grid139 -1.3 %, N=2 grid70 -1.4 %
+                              // (profiles/r2_pdl_late_ab.txt); PD_PDL=0 switches it off
                               // on B200 (grid139: 42.0 vs 36.9 ms/step, batch64: 2.68 vs 2.23), so it stays an opt-in experiment (PD_PDL=1)
     float dt2Prepared_ = 0.f;
     bool bodyKernel_ = false;             // EXPERIMENT PD_BODY_KERNEL=1: one CTA per small body, one launch per step (pd_body_kernel.cuh)
